@@ -1,0 +1,122 @@
+/*
+ * tnsp_b200.h -- C-ABI of the B200 (sm_100a) kernels behind the TAT/tetragono sampling-VMC hot path.
+ *
+ * This is the drop-in boundary below the Python `TAT` module (reference: PyTAT/PyTAT.cpp:58-166,
+ * PyTAT/PyTAT.hpp:569-1147).  The reference's own lower seam is the Fortran BLAS/LAPACK ABI that
+ * TAT calls once per symmetry sector (contract.hpp:28-160, svd.hpp:30-97, qr.hpp:28-121); each
+ * entry point below replaces one such per-sector loop by a single launch over
+ * (sector x Monte-Carlo chain).  Plain pointers and sizes only; all pointers are DEVICE pointers
+ * unless the name ends in `_host`.  `stream` is a cudaStream_t passed as void*.
+ *
+ * Conventions
+ *   - all data are float64, row-major, dense inside a block;
+ *   - a "batch" is a set of `nb` Monte-Carlo chains sharing one block structure; batch entry b of
+ *     a tensor lives at base + b * bstride (bstride == 0 broadcasts one tensor to all chains);
+ *   - descriptor tables are int64 arrays in device memory, produced by the host planner
+ *     (tnsp_b200/TAT/plan.py) from the reference's integer rules;
+ *   - every function returns 0 on success, non-zero on error (tnsp_last_error() has the text).
+ */
+#ifndef TNSP_B200_H
+#define TNSP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNSP_PACK_MAX_RANK 8
+#define TNSP_PACK_COLS (3 + 3 * TNSP_PACK_MAX_RANK)
+#define TNSP_GEMM_COLS 8
+#define TNSP_SECT_COLS 8
+
+int tnsp_abi_version(void);
+const char* tnsp_last_error(void);
+/* number of kernels launched through this library since load (bench.py's gpu_launches) */
+int64_t tnsp_launch_count(void);
+
+/* ---- K1: sector pairing + transpose (replaces Tensor::edge_operator_implement's copy loop,
+ * TAT/include/TAT/implement/edge_operator.hpp:651-688 + utility/multidimension_span.hpp:250-383).
+ * desc[n][TNSP_PACK_COLS] = (src_off, dst_off, sign | rank<<1, dims[8], src_stride[8], dst_stride[8]);
+ * estart[n+1] = prefix sum of elements per descriptor; total = estart[n]. */
+int tnsp_pack_f64(const int64_t* desc, const int64_t* estart, int n_desc, int64_t total,
+                  const double* src, int64_t src_bstride, double* dst, int64_t dst_bstride, int nb, void* stream);
+
+/* single 2-D transposing descriptor, 32x32 shared-memory tiles (same operation, coalesced both ways):
+ * dst[o*d_outer + j*d_j + i] = (+/-) src[o*s_outer + i*s_i + j] for o < n_outer, i < n_i, j < n_j */
+int tnsp_pack_tiled_f64(int64_t src_off, int64_t dst_off, int64_t n_outer, int64_t n_i, int64_t n_j, int64_t s_outer,
+                        int64_t s_i, int64_t d_outer, int64_t d_j, int neg, const double* src, int64_t src_bstride,
+                        double* dst, int64_t dst_bstride, int nb, void* stream);
+
+/* ---- K2: grouped GEMM over (sector x chain) (replaces detail::gemm_batch, contract.hpp:194-250,
+ * fed by the descriptor loop contract.hpp:539-616 / :826-852).
+ * desc[ng][8] = (m, n, k, a_off, b_off, c_off, flags, alpha); C[m x n] = alpha * op(A) * op(B);
+ * flags bit0: A stored [k x m]; bit1: B stored [n x k]; otherwise [m x k] / [k x n]. */
+int tnsp_gemm_grouped_f64(const int64_t* desc, int ng, const int64_t* desc_host,
+                          const double* a, int64_t a_bstride, const double* b, int64_t b_bstride,
+                          double* c, int64_t c_bstride, int nb, void* stream);
+
+/* ---- K3: batched QR / LQ with explicit Q (replaces ?geqrf/?orgqr and ?gelqf/?orglq per sector,
+ * qr.hpp:178-304).  sect[ns][8] = (m, n, k, a_off, out1_off, out2_off, s_off, -); the m x n input
+ * at a_off is destroyed.  use_qr != 0: out1 = Q (m x k), out2 = R (k x n); else out1 = L, out2 = Q. */
+int tnsp_qr_batched_f64(const int64_t* sect, int ns, const int64_t* sect_host, double* a, int64_t a_bstride,
+                        double* out1, int64_t o1_bstride, double* out2, int64_t o2_bstride,
+                        int use_qr, int nb, void* stream);
+
+/* ---- K4: batched one-sided Jacobi SVD (replaces ?gesvd('S','S') per sector, svd.hpp:104-211).
+ * out1 = U (m x k), s = singular values sorted descending at s_off, out2 = V^T (k x n).
+ * work: scratch of tnsp_svd_work_size() doubles per chain. */
+int64_t tnsp_svd_work_size(const int64_t* sect_host, int ns);
+int tnsp_svd_batched_f64(const int64_t* sect, int ns, const int64_t* sect_host, const double* a, int64_t a_bstride,
+                         double* out1, int64_t o1_bstride, double* s, int64_t s_bstride,
+                         double* out2, int64_t o2_bstride, double* work, int64_t w_bstride,
+                         int nb, void* stream);
+
+/* ---- greedy cross-sector truncation (svd.hpp:429-481): counts[b][i] = kept values of sector i. */
+int tnsp_svd_cut_f64(const int64_t* sect, int ns, int64_t s_total, const double* s, int64_t s_bstride,
+                     int64_t remain_cut, double relative_cut, int32_t* counts, int nb, void* stream);
+/* zero singular triplets beyond counts[b][i] (keeps one block structure for all chains of a batch) */
+int tnsp_svd_mask_f64(const int64_t* sect, int ns, const int32_t* counts, double* out1, int64_t o1_bstride,
+                      double* s, int64_t s_bstride, double* out2, int64_t o2_bstride, int nb, void* stream);
+/* S as diagonal blocks (svd.hpp:213-254): blk[nblk][4] = (s_off, dst_off, r, sign); dst pre-zeroed */
+int tnsp_diag_scatter_f64(const int64_t* blk, int nblk, const double* s, int64_t s_bstride,
+                          double* dst, int64_t dst_bstride, int nb, void* stream);
+
+/* ---- elementwise / reductions (scalar.hpp:46-118, tensor.hpp:631-660, conjugate.hpp:99-116) ---- */
+/* per-chain norms: kind -1 max|x|, 1 sum|x|, 2 sqrt(sum x^2); out[nb] */
+int tnsp_norm_f64(const double* x, int64_t x_bstride, int64_t size, int kind, double* out, int nb, void* stream);
+/* y[b] = alpha[b*alpha_stride] * x[b] (+ beta[b*beta_stride] * y[b] if beta != NULL); op: 0 mul, 1 div by alpha */
+int tnsp_scale_f64(const double* x, int64_t x_bstride, const double* alpha, int64_t alpha_stride, int op,
+                   double* y, int64_t y_bstride, int64_t size, int nb, void* stream);
+/* z = a (op) b elementwise; op 0 +, 1 -, 2 *, 3 / ; bstride 0 broadcasts */
+int tnsp_binary_f64(const double* a, int64_t a_bstride, const double* b, int64_t b_bstride, int op,
+                    double* z, int64_t z_bstride, int64_t size, int nb, void* stream);
+/* z = f(a): op 0 sqrt|a|, 1 reciprocal-except-zero, 2 negate, 3 abs */
+int tnsp_unary_f64(const double* a, int64_t a_bstride, int op, double* z, int64_t z_bstride, int64_t size, int nb, void* stream);
+/* y += w[b] * x  and  ey += w[b] * e[b] * x, reduced over the nb chains of the batch into ONE
+ * accumulator (fused local-energy / log-derivative accumulation, observer.py:399-407) */
+int tnsp_grad_accumulate_f64(const double* holes, int64_t h_bstride, const double* weight, const double* energy,
+                             double* delta, double* edelta, int64_t size, int nb, void* stream);
+/* per-block sign flip copy (conjugate of real fermionic tensors): blk[nblk][3] = (off, size, sign) */
+int tnsp_block_sign_f64(const int64_t* blk, int nblk, const double* x, int64_t x_bstride,
+                        double* y, int64_t y_bstride, int64_t size, int nb, void* stream);
+/* gather rows: dst[b] = src[index[b]] (select the sampled physical slice per chain, lattice.py:319-339) */
+int tnsp_gather_rows_f64(const double* src, int64_t row_size, const int32_t* index, double* dst, int64_t dst_bstride,
+                         int nb, void* stream);
+/* dst[b] = mask[b] ? a[b] : b_[b] (Metropolis accept, sampling.py:138-142) */
+int tnsp_select_f64(const uint8_t* mask, const double* a, int64_t a_bstride, const double* b_, int64_t b_bstride,
+                    double* dst, int64_t dst_bstride, int64_t size, int nb, void* stream);
+
+/* ---- host RNG with libstdc++ semantics (TAT.random, PyTAT.hpp:87-126): one mt19937_64 per chain ---- */
+void* tnsp_rng_create_host(int n_chains);
+void tnsp_rng_destroy_host(void* rng);
+void tnsp_rng_seed_host(void* rng, int chain, uint32_t seed);
+/* out[i] = uniform_int_distribution<int>(lo[i], hi[i]) on chain i where active[i] != 0 */
+void tnsp_rng_uniform_int_host(void* rng, const int32_t* lo, const int32_t* hi, const uint8_t* active, int32_t* out);
+void tnsp_rng_uniform_real_host(void* rng, double lo, double hi, const uint8_t* active, double* out);
+void tnsp_rng_normal_host(void* rng, int chain, double mean, double stddev, int64_t n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

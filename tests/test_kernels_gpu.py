@@ -1,0 +1,168 @@
+"""Kernel-level parity (-m gpu): each C-ABI entry point on the B200 against the numpy checker
+(oracle/numpy_backend.py) on the same descriptor tables, including batched (nb > 1) launches,
+broadcast operands, ragged sector shapes and sizes beyond one tile / shared memory."""
+import numpy as np
+import pytest
+import torch
+
+import tnsp_b200.TAT as TAT
+from tnsp_b200 import backend
+from tnsp_b200.TAT import plan as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _both():
+    from oracle.numpy_backend import NumpyBackend
+    return backend.get(), NumpyBackend()
+
+
+def _u1_edge(dims, arrow=False):
+    E = TAT.BoseU1.Edge
+    return E([(q, d) for q, d in zip(range(-(len(dims) // 2), len(dims)), dims)], arrow)
+
+
+@pytest.mark.parametrize("nb", [1, 7, 300])
+def test_pack_bit_exact(nb):
+    cu, ck = _both()
+    rng = np.random.default_rng(nb)
+    E = TAT.BoseU1.Edge
+    edges = (_u1_edge([3, 4, 2]), _u1_edge([2, 5, 3]), _u1_edge([4, 1, 3]), _u1_edge([2, 2, 2]))
+    names = ("a", "b", "c", "d")
+    p = P.edge_operator_plan(E, names, edges, None, None, {"M": ["c", "a"], "N": ["d", "b"]}, ["N", "M"])
+    src = rng.standard_normal((nb, p.src_size))
+    d_ck = ck.zeros(nb, p.dst_size)
+    ck.pack(p, torch.from_numpy(src), d_ck)
+    p._dev = None
+    d_cu = cu.zeros(nb, p.dst_size)
+    cu.pack(p, cu.from_numpy(src), d_cu)
+    assert np.array_equal(cu.to_numpy(d_cu), d_ck.numpy())
+
+
+@pytest.mark.parametrize("shape", [(5, 7, 3), (16, 16, 16), (64, 16, 4), (33, 65, 17), (130, 70, 200), (300, 257, 129)])
+@pytest.mark.parametrize("flags", [0, 1, 2, 3])
+def test_grouped_gemm(shape, flags):
+    cu, ck = _both()
+    m, n, k = shape
+    rng = np.random.default_rng(m * n + flags)
+    nb = 5
+
+    class Plan:
+        pass
+    p = Plan()
+    # two sectors of different shape in one launch
+    m2, n2, k2 = max(1, m // 2), n + 3, max(1, k - 1)
+    p.gemm = np.array([[m, n, k, 0, 0, 0, flags, 1], [m2, n2, k2, m * k, k * n, m * n, flags, -1]], dtype=np.int64)
+    p._dev = None
+    a = rng.standard_normal((nb, m * k + m2 * k2))
+    b = rng.standard_normal((1, k * n + k2 * n2))  # broadcast operand
+    c_ck = ck.zeros(nb, m * n + m2 * n2)
+    ck.gemm(p, torch.from_numpy(a), torch.from_numpy(b), c_ck)
+    c_cu = cu.zeros(nb, m * n + m2 * n2)
+    cu.gemm(p, cu.from_numpy(a), cu.from_numpy(b), c_cu)
+    ref = c_ck.numpy()
+    # tolerance: float64 GEMM, different summation order -> 1e-13 relative to |A||B| scale
+    assert np.abs(cu.to_numpy(c_cu) - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()) * k
+
+
+def _factor_plan(shapes, flag):
+    class Plan:
+        pass
+    p = Plan()
+    rows, ao, o1, o2, so = [], 0, 0, 0, 0
+    for m, n in shapes:
+        k = min(m, n)
+        rows.append((m, n, k, ao, o1, o2, so, 0))
+        ao += m * n
+        o1 += m * k
+        o2 += k * n
+        so += k
+    p.sectors = np.array(rows, dtype=np.int64).reshape(-1, 8)
+    p.s_total = so
+    p.flag = flag
+    p._dev = None
+    return p, ao, o1, o2, so
+
+
+@pytest.mark.parametrize("shapes", [[(16, 16), (4, 64), (64, 4)], [(64, 16), (16, 64), (1, 1), (5, 3)], [(216, 36)], [(40, 200), (180, 170)]])
+@pytest.mark.parametrize("use_qr", [True, False])
+def test_batched_qr(shapes, use_qr):
+    cu, _ = _both()
+    p, ao, o1, o2, _ = _factor_plan(shapes, use_qr)
+    nb = 3
+    rng = np.random.default_rng(len(shapes))
+    a = rng.standard_normal((nb, ao))
+    t1, t2 = cu.zeros(nb, o1), cu.zeros(nb, o2)
+    cu.qr(p, cu.from_numpy(a), t1, t2)
+    T1, T2 = cu.to_numpy(t1), cu.to_numpy(t2)
+    for (m, n, k, a_off, x1, x2, _, _) in p.sectors:
+        for b in range(nb):
+            M = a[b, a_off:a_off + m * n].reshape(m, n)
+            F1 = T1[b, x1:x1 + m * k].reshape(m, k)
+            F2 = T2[b, x2:x2 + k * n].reshape(k, n)
+            assert np.abs(F1 @ F2 - M).max() <= 1e-12 * max(1.0, np.abs(M).max()) * max(m, n)
+            if use_qr:
+                assert np.abs(F1.T @ F1 - np.eye(k)).max() <= 1e-12
+                assert np.abs(np.tril(F2, -1)).max() == 0.0
+            else:
+                assert np.abs(F2 @ F2.T - np.eye(k)).max() <= 1e-12
+                assert np.abs(np.triu(F1, 1)).max() == 0.0
+
+
+@pytest.mark.parametrize("shapes", [[(16, 16), (4, 64), (64, 4)], [(64, 16), (16, 64), (1, 1), (5, 3)], [(36, 216)], [(150, 120), (60, 60)]])
+def test_batched_svd_and_cut(shapes):
+    cu, ck = _both()
+    p, ao, o1, o2, so = _factor_plan(shapes, True)
+    nb = 3
+    rng = np.random.default_rng(7 + len(shapes))
+    a = rng.standard_normal((nb, ao))
+    t1, t2, s = cu.zeros(nb, o1), cu.zeros(nb, o2), cu.zeros(nb, so)
+    cu.svd(p, cu.from_numpy(a), t1, s, t2)
+    T1, T2, S = cu.to_numpy(t1), cu.to_numpy(t2), cu.to_numpy(s)
+    for (m, n, k, a_off, x1, x2, xs, _) in p.sectors:
+        for b in range(nb):
+            M = a[b, a_off:a_off + m * n].reshape(m, n)
+            U = T1[b, x1:x1 + m * k].reshape(m, k)
+            Vt = T2[b, x2:x2 + k * n].reshape(k, n)
+            sv = S[b, xs:xs + k]
+            ref = np.linalg.svd(M, compute_uv=False)
+            assert np.abs(sv - ref).max() <= 1e-12 * ref.max()          # singular values vs LAPACK
+            assert np.abs((U * sv) @ Vt - M).max() <= 1e-12 * ref.max() * max(m, n)
+            assert np.abs(U.T @ U - np.eye(k)).max() <= 1e-11
+            assert np.abs(Vt @ Vt.T - np.eye(k)).max() <= 1e-11
+    # greedy cut: device ranking == literal restatement of svd.hpp:429-481 (bit-exact integers)
+    for cut, rel in ((5, 0.0), (1 << 40, 0.3), (17, 0.05)):
+        c_cu = cu.to_numpy(cu.svd_cut(p, s, cut, rel))
+        c_ck = ck.svd_cut(p, torch.from_numpy(S), cut, rel).numpy()
+        assert np.array_equal(c_cu, c_ck)
+
+
+def test_streaming_kernels():
+    cu, ck = _both()
+    rng = np.random.default_rng(3)
+    nb, size = 9, 1000
+    x = rng.standard_normal((nb, size))
+    y = rng.standard_normal((nb, size))
+    X, Y = cu.from_numpy(x), cu.from_numpy(y)
+    for kind in (-1, 1, 2):
+        assert np.allclose(cu.to_numpy(cu.norm(X, kind)), ck.norm(torch.from_numpy(x), kind).numpy(), rtol=1e-14, atol=0)
+    al = rng.standard_normal(nb)
+    for op in (0, 1):
+        assert np.array_equal(cu.to_numpy(cu.scale(X, cu.from_numpy(al), op)), ck.scale(torch.from_numpy(x), torch.from_numpy(al), op).numpy())
+    for op in range(4):
+        assert np.array_equal(cu.to_numpy(cu.binary(X, Y, op)), ck.binary(torch.from_numpy(x), torch.from_numpy(y), op).numpy())
+        assert np.array_equal(cu.to_numpy(cu.unary(X, op)), ck.unary(torch.from_numpy(x), op).numpy())
+    idx = rng.integers(0, 4, size=nb).astype(np.int32)
+    src = rng.standard_normal((1, 4 * 50))
+    assert np.array_equal(cu.to_numpy(cu.gather_rows(cu.from_numpy(src), 50, cu.from_numpy(idx))),
+                          ck.gather_rows(torch.from_numpy(src), 50, torch.from_numpy(idx)).numpy())
+    mask = (rng.random(nb) < 0.5).astype(np.uint8)
+    assert np.array_equal(cu.to_numpy(cu.select(cu.from_numpy(mask), X, Y)), ck.select(torch.from_numpy(mask), torch.from_numpy(x), torch.from_numpy(y)).numpy())
+    w, e = rng.random(nb), rng.standard_normal(nb)
+    d0, e0 = np.zeros((1, size)), np.zeros((1, size))
+    D, ED = cu.from_numpy(d0), cu.from_numpy(e0)
+    cu.grad_accumulate(X, cu.from_numpy(w), cu.from_numpy(e), D, ED)
+    td, te = torch.from_numpy(d0.copy()), torch.from_numpy(e0.copy())
+    ck.grad_accumulate(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(e), td, te)
+    assert np.allclose(cu.to_numpy(D), td.numpy(), rtol=1e-13, atol=1e-13)
+    assert np.allclose(cu.to_numpy(ED), te.numpy(), rtol=1e-13, atol=1e-13)

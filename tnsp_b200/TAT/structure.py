@@ -25,7 +25,7 @@ class SymmetryBase(tuple):
 
     __slots__ = ()
     kinds: tuple = ()  # "Z2" or "U1" per component
-    fermi: tuple = ()  # bool per component
+    fermi_flags: tuple = ()  # bool per component
     field_names: tuple = ()
     short_name = "No"
     is_fermi_symmetry = False
@@ -85,7 +85,7 @@ class SymmetryBase(tuple):
     @property
     def parity(self) -> bool:
         r = False
-        for a, f in zip(self, self.fermi):
+        for a, f in zip(self, self.fermi_flags):
             if f:
                 r ^= bool(a % 2) if not isinstance(a, bool) else a
         return r
@@ -112,7 +112,7 @@ def make_symmetry_class(short_name, components):
     ns = {
         "__slots__": (),
         "kinds": tuple(k for _, k, _ in components),
-        "fermi": tuple(f for _, _, f in components),
+        "fermi_flags": tuple(f for _, _, f in components),
         "field_names": tuple(n for n, _, _ in components),
         "short_name": short_name,
         "is_fermi_symmetry": any(f for _, _, f in components),
@@ -294,7 +294,7 @@ class Edge:
                 other = type(self)(other)
             except Exception:
                 return NotImplemented
-        return self.segments == other.segments and self.arrow == other.arrow
+        return type(self) is type(other) and self.segments == other.segments and self.arrow == other.arrow
 
     def __ne__(self, other):
         r = self.__eq__(other)
@@ -302,7 +302,7 @@ class Edge:
 
     def __hash__(self):
         if self._hash is None:
-            self._hash = hash((self.segments, self.arrow))
+            self._hash = hash((self.Symmetry.short_name, self.segments, self.arrow))
         return self._hash
 
     def __repr__(self):

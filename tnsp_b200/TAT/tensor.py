@@ -1,0 +1,785 @@
+"""Device-backed block-symmetric tensor with the PyTAT ``Tensor`` interface.
+
+Mirrors the class bound by the reference at PyTAT/PyTAT.hpp:569-1147 (same method names, argument
+meaning and error behaviour).  Storage is one float64 device buffer of shape [nb, size] where
+``nb`` is the number of Monte-Carlo chains that share this tensor's block structure (nb == 1 is an
+ordinary tensor; every operation then is the reference operation applied to all chains at once by
+a single kernel launch).  All heavy work goes through ``tnsp_b200.backend`` -> C-ABI -> CUDA.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import backend as _bk
+from . import plan as _plan
+from . import structure as _structure
+from .structure import block_table
+
+_PLAN_CACHE: dict = {}
+STATS = {"contract": 0, "svd": 0, "qr": 0, "pack": 0, "flops": 0, "pack_elems": 0}
+
+
+def _cached(key, builder):
+    p = _PLAN_CACHE.get(key)
+    if p is None:
+        p = _PLAN_CACHE[key] = builder()
+    return p
+
+
+def _fs(x):
+    return frozenset(x) if x else frozenset()
+
+
+class BatchScalar:
+    """A per-chain scalar living on the device (result of norm_* on a batched tensor)."""
+
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+    def numpy(self):
+        return _bk.get().to_numpy(self.t)
+
+    def __float__(self):
+        v = self.numpy()
+        if v.size != 1:
+            raise TypeError("batched scalar with more than one chain cannot be converted to float")
+        return float(v[0])
+
+    def _bin(self, other, f):
+        o = other.t if isinstance(other, BatchScalar) else other
+        return BatchScalar(f(self.t, o))
+
+    def __mul__(self, o):
+        return self._bin(o, lambda a, b: a * b)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return self._bin(o, lambda a, b: a / b)
+
+    def __rtruediv__(self, o):
+        return self._bin(o, lambda a, b: b / a)
+
+    def __pow__(self, e):
+        return BatchScalar(self.t**e)
+
+    def __add__(self, o):
+        return self._bin(o, lambda a, b: a + b)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self._bin(o, lambda a, b: a - b)
+
+
+class _EdgesProxy:
+    def __init__(self, tensor):
+        self._t = tensor
+
+    def __getitem__(self, i):
+        return self._t._edges[i]
+
+    def __len__(self):
+        return len(self._t._edges)
+
+    def __iter__(self):
+        return iter(self._t._edges)
+
+    def __call__(self, key):
+        if isinstance(key, str):
+            return self._t.edge_by_name(key)
+        return self._t._edges[key]
+
+
+class _StorageView:
+    """Host view of the storage; writes go back to the device (``tensor.storage[...] = x``)."""
+
+    def __init__(self, tensor):
+        self._t = tensor
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._t._host()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, key):
+        return self._t._host()[key]
+
+    def __setitem__(self, key, value):
+        a = self._t._host().copy()
+        a[key] = value
+        self._t._set_host(a)
+
+    def __len__(self):
+        return self._t._table.size
+
+    @property
+    def size(self):
+        return self._t._table.size
+
+    @property
+    def shape(self):
+        return (self._t._table.size,)
+
+    def tolist(self):
+        return self._t._host().tolist()
+
+    def __repr__(self):
+        return repr(self._t._host())
+
+    def __eq__(self, other):
+        return self._t._host() == np.asarray(other)
+
+
+class _BlocksProxy:
+    def __init__(self, tensor, readonly):
+        self._t = tensor
+        self._ro = readonly
+
+    def _locate(self, position):
+        t = self._t
+        if len(position) and isinstance(position[0], (tuple, list)):
+            names = [n for n, _ in position]
+            syms = {n: t.Symmetry(s) for n, s in position}
+        else:
+            names = list(position)
+            syms = {n: t.Symmetry() for n in names}
+        pos = []
+        for n, e in zip(t.names, t._edges):
+            p = e.find_by_symmetry(syms[n])
+            if p is None:
+                raise RuntimeError("No such symmetry in this edge")
+            pos.append(p)
+        b = t._table.block_by_positions(pos)
+        if b is None:
+            raise RuntimeError("Try to get a block which does not exist")
+        perm = [t.names.index(n) for n in names]
+        return b, perm
+
+    def __getitem__(self, position):
+        b, perm = self._locate(position)
+        t = self._t
+        off, size = int(t._table.offsets[b]), int(t._table.sizes[b])
+        dims = [int(d) for d in t._table.dims[b]]
+        return t._host()[off:off + size].reshape(dims).transpose(perm).copy()
+
+    def __setitem__(self, position, value):
+        b, perm = self._locate(position)
+        t = self._t
+        off, size = int(t._table.offsets[b]), int(t._table.sizes[b])
+        dims = [int(d) for d in t._table.dims[b]]
+        a = t._host().copy()
+        view = a[off:off + size].reshape(dims).transpose(perm)
+        view[...] = value
+        t._set_host(a)
+
+
+class Tensor:
+    """Created per (symmetry, scalar) by ``TAT/__init__.py``; class attributes: Symmetry, Edge, model, dtype ..."""
+
+    __slots__ = ("names", "_edges", "_table", "_data")
+    Symmetry = None
+    Edge = None
+    model = None
+    is_real = True
+    is_complex = False
+    dtype = "float64"
+    btype = "D"
+
+    # -- construction --------------------------------------------------------------------------
+    def __init__(self, *args, **kwargs):
+        if len(args) == 0 and not kwargs:
+            self._init([], [], None)
+            return
+        if len(args) == 1 and not kwargs and isinstance(args[0], Tensor):
+            o = args[0]
+            self.names, self._edges, self._table, self._data = list(o.names), o._edges, o._table, o._data
+            return
+        if len(args) >= 1 and isinstance(args[0], str) and not kwargs:
+            raise NotImplementedError("text constructor is outside the hot path")
+        if (len(args) >= 1 and isinstance(args[0], (int, float, np.number)) and not isinstance(args[0], bool)) or "number" in kwargs:
+            number = kwargs.get("number", args[0] if args else 0)
+            names = list(kwargs.get("names", args[1] if len(args) > 1 else []))
+            syms = list(kwargs.get("edge_symmetry", args[2] if len(args) > 2 else []))
+            arrows = list(kwargs.get("edge_arrow", args[3] if len(args) > 3 else []))
+            edges = []
+            for i in range(len(names)):
+                s = self.Symmetry(syms[i]) if i < len(syms) else self.Symmetry()
+                ar = bool(arrows[i]) if i < len(arrows) else False
+                edges.append(self.Edge(((s, 1),), ar))
+            self._init(names, edges, None)
+            if self._table.size != 1:
+                raise RuntimeError("Invalid symmetries for a rank-0-like tensor")
+            self._set_host(np.array([float(number)]))
+            return
+        names = kwargs.get("names", args[0] if args else [])
+        edges = kwargs.get("edges", args[1] if len(args) > 1 else [])
+        self._init(list(names), [e if type(e) is self.Edge else self.Edge(e) for e in edges], None)
+
+    def _init(self, names, edges, data):
+        if len(names) != len(edges):
+            raise RuntimeError("Different Rank in Tensor Construction")
+        if len(set(names)) != len(names):
+            raise RuntimeError("Duplicated names in Tensor Construction")
+        self.names = list(names)
+        self._edges = tuple(edges)
+        self._table = block_table(self._edges)
+        self._data = data
+
+    @classmethod
+    def _make(cls, names, edges, table, data):
+        t = cls.__new__(cls)
+        t.names = list(names)
+        t._edges = tuple(edges)
+        t._table = table
+        t._data = data
+        return t
+
+    # -- data helpers --------------------------------------------------------------------------
+    @property
+    def data(self):
+        """device buffer [nb, size] (allocated uninitialised on first use, like the reference)"""
+        if self._data is None:
+            self._data = _bk.get().zeros(1, self._table.size)
+        return self._data
+
+    @property
+    def nb(self):
+        return self.data.shape[0]
+
+    def _host(self):
+        a = _bk.get().to_numpy(self.data)
+        return a[0] if a.shape[0] == 1 else a
+
+    def _set_host(self, array):
+        a = np.asarray(array, dtype=np.float64)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        if a.shape[1] != self._table.size:
+            raise ValueError("storage size mismatch")
+        self._data = _bk.get().from_numpy(a)
+
+    @classmethod
+    def from_batch(cls, names, edges, array):
+        """Build a batched tensor from a host array [nb, size] (or a device buffer)."""
+        edges = tuple(e if type(e) is cls.Edge else cls.Edge(e) for e in edges)
+        t = cls._make(names, edges, block_table(edges), None)
+        if isinstance(array, np.ndarray):
+            t._set_host(array)
+        else:
+            t._data = array
+        return t
+
+    # -- simple accessors ----------------------------------------------------------------------
+    @property
+    def edges(self):
+        return _EdgesProxy(self)
+
+    @property
+    def rank(self):
+        return len(self.names)
+
+    def edge_by_name(self, name):
+        try:
+            return self._edges[self.names.index(name)]
+        except ValueError:
+            raise RuntimeError("No such name in tensor") from None
+
+    @property
+    def storage(self):
+        return _StorageView(self)
+
+    @storage.setter
+    def storage(self, value):
+        if isinstance(value, _StorageView):
+            value = np.asarray(value)
+        a = np.empty(self._host().shape, dtype=np.float64)
+        a[...] = value
+        self._set_host(a)
+
+    @property
+    def blocks(self):
+        return _BlocksProxy(self, False)
+
+    @property
+    def const_blocks(self):
+        return _BlocksProxy(self, True)
+
+    def _flat_index(self, position):
+        pos, offs = [], []
+        for n, e in zip(self.names, self._edges):
+            if n not in position:
+                raise RuntimeError("Name not found in position map")
+            v = position[n]
+            if isinstance(v, (tuple, list)):
+                s, o = v
+                p = e.find_by_symmetry(self.Symmetry(s))
+                if p is None:
+                    raise RuntimeError("No such symmetry in this edge")
+                o = int(o)
+            else:
+                p, o = e.coord_by_index(int(v))
+            pos.append(p)
+            offs.append(o)
+        b = self._table.block_by_positions(pos)
+        if b is None:
+            raise RuntimeError("Try to get an element in a block which does not exist")
+        dims = self._table.dims[b]
+        idx = 0
+        for o, d in zip(offs, dims):
+            if o >= d:
+                raise RuntimeError("Index out of range")
+            idx = idx * int(d) + o
+        return int(self._table.offsets[b]) + idx
+
+    def __getitem__(self, position):
+        v = self._host()[..., self._flat_index(position)]
+        return float(v) if np.ndim(v) == 0 else v
+
+    def __setitem__(self, position, value):
+        a = self._host().copy()
+        a[..., self._flat_index(position)] = value
+        self._set_host(a)
+
+    def __float__(self):
+        if self._table.size != 1:
+            raise RuntimeError("Try to get the only element of the tensor which contains more than one element")
+        return float(self._host().reshape(-1)[0])
+
+    def __complex__(self):
+        return complex(float(self))
+
+    def scalar(self):
+        """the single element per chain as a device vector [nb] (batched analogue of float(tensor))"""
+        if self._table.size != 1:
+            raise RuntimeError("Try to get the only element of the tensor which contains more than one element")
+        return BatchScalar(self.data[:, 0])
+
+    def __repr__(self):
+        return f"{self.btype}{self.Symmetry.short_name}Tensor" + self._shape_str()
+
+    def _shape_str(self):
+        return "{names:[" + ",".join(self.names) + "],edges:[" + ",".join(str(e) for e in self._edges) + "]}"
+
+    def __str__(self):
+        blocks = []
+        h = np.atleast_2d(self._host())[0]
+        for b, pos in enumerate(self._table.positions):
+            syms = ",".join(str(e.segments[int(p)][0]) for e, p in zip(self._edges, pos))
+            off, size = int(self._table.offsets[b]), int(self._table.sizes[b])
+            blocks.append("[" + syms + "]:[" + ",".join(repr(float(x)).rstrip("0").rstrip(".") if float(x) == int(x) else repr(float(x))
+                                                       for x in h[off:off + size]) + "]")
+        if self.Symmetry.length == 0:
+            return "{names:[" + ",".join(self.names) + "],edges:[" + ",".join(str(e) for e in self._edges) + "],blocks:" + \
+                (blocks[0].split(":", 1)[1] if blocks else "[]") + "}"
+        return "{names:[" + ",".join(self.names) + "],edges:[" + ",".join(str(e) for e in self._edges) + "],blocks:{" + ",".join(blocks) + "}}"
+
+    # -- copies / fills ------------------------------------------------------------------------
+    def copy(self):
+        return self._make(self.names, self._edges, self._table, self.data.clone())
+
+    __copy__ = copy
+
+    def __deepcopy__(self, memo):
+        return self.copy()
+
+    def same_shape(self):
+        return self._make(self.names, self._edges, self._table, None)
+
+    def zero_(self):
+        self._data = _bk.get().zeros(self.data.shape[0], self._table.size)
+        return self
+
+    zero = zero_
+
+    def range_(self, first=0, step=1):
+        self._set_host(first + step * np.arange(self._table.size, dtype=np.float64))
+        return self
+
+    range = range_
+
+    def set_(self, function):
+        self._set_host(np.array([function() for _ in range(self._table.size)], dtype=np.float64))
+        return self
+
+    set = set_
+
+    def map(self, function):
+        h = np.atleast_2d(self._host())
+        out = np.array([[function(float(x)) for x in row] for row in h], dtype=np.float64)
+        r = self.same_shape()
+        r._set_host(out)
+        return r
+
+    def transform_(self, function):
+        self._data = self.map(function)._data
+        return self
+
+    transform = transform_
+
+    def randn_(self, mean=0.0, stddev=1.0):
+        from . import random as _random
+        self._set_host(_random._normal_fill(self._table.size, mean, stddev))
+        return self
+
+    randn = randn_
+
+    def rand_(self, min=0.0, max=1.0):
+        from . import random as _random
+        self._set_host(_random._uniform_fill(self._table.size, min, max))
+        return self
+
+    rand = rand_
+
+    def to(self, new_type):
+        s = str(new_type)
+        if "float64" in s or s in ("D", "float", "<class 'float'>") or "float" in s and "32" not in s:
+            return self
+        raise NotImplementedError("only float64 tensors are device-backed in this build")
+
+    def sqrt(self):
+        return self._make(self.names, self._edges, self._table, _bk.get().unary(self.data, 0))
+
+    def reciprocal(self):
+        return self._make(self.names, self._edges, self._table, _bk.get().unary(self.data, 1))
+
+    # -- norms ---------------------------------------------------------------------------------
+    def _norm(self, kind):
+        r = _bk.get().norm(self.data, kind)
+        if r.shape[0] == 1:
+            return float(_bk.get().to_numpy(r)[0])
+        return BatchScalar(r)
+
+    def norm_max(self):
+        return self._norm(-1)
+
+    def norm_num(self):
+        return float(self._table.size)
+
+    def norm_sum(self):
+        return self._norm(1)
+
+    def norm_2(self):
+        return self._norm(2)
+
+    # -- arithmetic ----------------------------------------------------------------------------
+    def _scalar_vec(self, value):
+        B = _bk.get()
+        if isinstance(value, BatchScalar):
+            return value.t.contiguous()
+        return B.from_numpy(np.array([float(value)], dtype=np.float64))
+
+    def _aligned(self, other):
+        if other.names != self.names:
+            other = other.transpose(self.names)
+        if other._edges != self._edges:
+            raise RuntimeError("Scalar Operator in different Tensor Shape")
+        return other
+
+    def _binary(self, other, op, reverse=False):
+        B = _bk.get()
+        if isinstance(other, Tensor):
+            if other.rank == 0 or self.rank == 0:
+                # rank-0 operand acts as a scalar (scalar.hpp:60-78)
+                if other.rank == 0 and self.rank != 0:
+                    return self._binary(BatchScalar(other.data[:, 0]), op)
+                if self.rank == 0 and other.rank != 0:
+                    return other._binary(BatchScalar(self.data[:, 0]), op, reverse=True)
+            o = self._aligned(other)
+            a, b = (o.data, self.data) if reverse else (self.data, o.data)
+            return self._make(self.names, self._edges, self._table, B.binary(a, b, op))
+        if op in (2, 3) and not reverse:
+            return self._make(self.names, self._edges, self._table, B.scale(self.data, self._scalar_vec(other), op - 2))
+        if op == 2:
+            return self._make(self.names, self._edges, self._table, B.scale(self.data, self._scalar_vec(other), 0))
+        # scalar (+,-) tensor or scalar / tensor: broadcast the scalar to a tensor
+        vec = self._scalar_vec(other)
+        nb = max(vec.shape[0], self.data.shape[0])
+        ones = B.from_numpy(np.ones((1, self._table.size)))
+        full = B.scale(ones, vec, 0, nb)
+        a, b = (full, self.data) if reverse else (self.data, full)
+        return self._make(self.names, self._edges, self._table, B.binary(a, b, op))
+
+    def __add__(self, o):
+        return self._binary(o, 0)
+
+    def __radd__(self, o):
+        return self._binary(o, 0, True)
+
+    def __sub__(self, o):
+        return self._binary(o, 1)
+
+    def __rsub__(self, o):
+        return self._binary(o, 1, True)
+
+    def __mul__(self, o):
+        return self._binary(o, 2)
+
+    def __rmul__(self, o):
+        return self._binary(o, 2, True)
+
+    def __truediv__(self, o):
+        return self._binary(o, 3)
+
+    def __rtruediv__(self, o):
+        return self._binary(o, 3, True)
+
+    def _inplace(self, o, op):
+        self._data = self._binary(o, op)._data
+        return self
+
+    def __iadd__(self, o):
+        return self._inplace(o, 0)
+
+    def __isub__(self, o):
+        return self._inplace(o, 1)
+
+    def __imul__(self, o):
+        return self._inplace(o, 2)
+
+    def __itruediv__(self, o):
+        return self._inplace(o, 3)
+
+    def __neg__(self):
+        return self._make(self.names, self._edges, self._table, _bk.get().unary(self.data, 2))
+
+    # -- edge operations -----------------------------------------------------------------------
+    def edge_rename(self, dictionary):
+        for n in dictionary:
+            if n not in self.names:
+                raise RuntimeError("Name missing in edge_rename")
+        return self._make([dictionary.get(n, n) for n in self.names], self._edges, self._table, self.data)
+
+    def _run_pack(self, p, src=None):
+        """Apply a PackPlan to this tensor's data -> new device buffer."""
+        B = _bk.get()
+        src = self.data if src is None else src
+        STATS["pack"] += 1
+        if p.identity:
+            return src
+        STATS["pack_elems"] += p.total * src.shape[0]
+        dst = B.empty(src.shape[0], p.dst_size) if p.covers_all else B.zeros(src.shape[0], p.dst_size)
+        B.pack(p, src, dst)
+        return dst
+
+    def _edge_operator(self, split_map, reversed_names, merge_map, new_names, apply_parity=False, excl_split=(), excl_rb=(),
+                       excl_ra=(), excl_merge=()):
+        sm = None
+        if split_map:
+            sm = {}
+            for k, v in split_map.items():
+                sm[k] = [(n, (e.segments if isinstance(e, _structure.Edge) else self.Edge(e).segments)) for n, e in v]
+        key = ("eo", type(self), tuple(self.names), self._edges,
+               tuple(sorted((k, tuple(v)) for k, v in sm.items())) if sm else None,
+               _fs(reversed_names), tuple(sorted((k, tuple(v)) for k, v in merge_map.items())) if merge_map else None,
+               tuple(new_names), bool(apply_parity), _fs(excl_split), _fs(excl_rb), _fs(excl_ra), _fs(excl_merge))
+        p = _cached(key, lambda: _plan.edge_operator_plan(self.Edge, tuple(self.names), self._edges, sm, _fs(reversed_names), merge_map,
+                                                           list(new_names), apply_parity, _fs(excl_split), _fs(excl_rb), _fs(excl_ra),
+                                                           _fs(excl_merge)))
+        return self._make(p.names, p.edges, p.table, self._run_pack(p))
+
+    def edge_operator(self, split_map, reversed_names, merge_map, new_names, apply_parity=False, parity_exclude_names_split=(),
+                      parity_exclude_names_reverse_before_transpose=(), parity_exclude_names_reverse_after_transpose=(),
+                      parity_exclude_names_merge=()):
+        return self._edge_operator(split_map, reversed_names, merge_map, new_names, apply_parity, parity_exclude_names_split,
+                                   parity_exclude_names_reverse_before_transpose, parity_exclude_names_reverse_after_transpose,
+                                   parity_exclude_names_merge)
+
+    def transpose(self, target_names):
+        target_names = list(target_names)
+        if target_names == self.names:
+            return self._make(self.names, self._edges, self._table, self.data)
+        return self._edge_operator(None, None, None, target_names)
+
+    def reverse_edge(self, reversed_names, apply_parity=False, parity_exclude_names=()):
+        return self._edge_operator(None, reversed_names, None, self.names, apply_parity, (), parity_exclude_names)
+
+    def merge_edge(self, merge, apply_parity=False, parity_exclude_names_merge=(), parity_exclude_names_reverse=()):
+        for new_name, olds in merge.items():
+            for o in olds:
+                if o not in self.names:
+                    raise RuntimeError("No such edge in merge map")
+        target = []
+        for name in reversed(self.names):
+            found = False
+            for after, before in merge.items():
+                if name in before:
+                    if name == before[-1]:
+                        target.append(after)
+                    found = True
+                    break
+            if not found:
+                target.append(name)
+        for after, before in merge.items():
+            if len(before) == 0:
+                target.append(after)
+        target.reverse()
+        return self._edge_operator(None, None, {k: list(v) for k, v in merge.items()}, target, apply_parity, (), (),
+                                   parity_exclude_names_reverse, parity_exclude_names_merge)
+
+    def split_edge(self, split, apply_parity=False, parity_exclude_names_split=()):
+        for old in split:
+            if old not in self.names:
+                raise RuntimeError("No such edge in split map")
+        target = []
+        for name in self.names:
+            if name in split:
+                target.extend(n for n, _ in split[name])
+            else:
+                target.append(name)
+        return self._edge_operator(split, None, None, target, apply_parity, parity_exclude_names_split)
+
+    # -- contract ------------------------------------------------------------------------------
+    def contract(self, another_tensor, contract_pairs, fuse_names=frozenset()):
+        other = another_tensor
+        if type(other) is not type(self):
+            raise TypeError("contract needs two tensors of the same type")
+        B = _bk.get()
+        pairs = frozenset((a, b) for a, b in contract_pairs)
+        fuse = _fs(fuse_names)
+        key = ("ct", type(self), tuple(self.names), self._edges, tuple(other.names), other._edges, pairs, fuse)
+        p = _cached(key, lambda: _plan.contract_plan(self.Edge, tuple(self.names), self._edges, tuple(other.names), other._edges,
+                                                      sorted(pairs), fuse))
+        STATS["contract"] += 1
+        d1, d2 = self.data, other.data
+        nb = max(d1.shape[0], d2.shape[0])
+        if d1.shape[0] != d2.shape[0] and min(d1.shape[0], d2.shape[0]) != 1:
+            raise RuntimeError("contract of two batched tensors with different chain counts")
+        STATS["flops"] += p.flops * nb
+        m1 = self._run_pack(p.pack1, d1)
+        m2 = other._run_pack(p.pack2, d2)
+        prod = B.zeros(nb, p.prod_size) if p.zero_fill else B.empty(nb, p.prod_size)
+        if len(p.gemm):
+            B.gemm(p, m1, m2, prod)
+        if p.unpack is not None:
+            prod = self._run_pack(p.unpack, prod)
+        return self._make(p.names, p.edges, p.table, prod)
+
+    # -- conjugate -----------------------------------------------------------------------------
+    def conjugate(self, trivial_metric=False):
+        if self.Symmetry.length == 0:
+            return self._make(self.names, self._edges, self._table, self.data)
+        key = ("cj", type(self), self._edges, bool(trivial_metric))
+
+        def build():
+            edges = tuple(e.conjugate() for e in self._edges)
+            signs = _plan.conjugate_signs(self._edges, self._table, trivial_metric)
+            blk = np.stack([self._table.offsets, self._table.sizes, signs], axis=1).astype(np.int64) if len(signs) else np.zeros((0, 3), np.int64)
+            blk = blk[blk[:, 1] > 0]
+            return edges, block_table(edges), blk, bool(signs.any())
+
+        edges, table, blk, any_sign = _cached(key, build)
+        data = _bk.get().block_sign(blk, self.data) if any_sign else self.data
+        return self._make(self.names, edges, table, data)
+
+    # -- svd / qr ------------------------------------------------------------------------------
+    def svd(self, free_names_u, common_name_u, common_name_v, singular_name_u, singular_name_v, cut=-1):
+        B = _bk.get()
+        free_u = _fs(free_names_u)
+        remain_cut, relative_cut = (1 << 62), 0.0
+        if cut > 0:
+            if cut >= 1:
+                remain_cut = int(cut)
+            else:
+                relative_cut = float(cut)
+        key = ("svd", type(self), tuple(self.names), self._edges, free_u, common_name_u, common_name_v)
+        p = _cached(key, lambda: _plan.svd_plan(self.Edge, tuple(self.names), self._edges, free_u, common_name_u, common_name_v))
+        STATS["svd"] += 1
+        nb = self.data.shape[0]
+        merged = self._run_pack(p.merge)
+        t1 = B.zeros(nb, p.t1_table.size)
+        t2 = B.zeros(nb, p.t2_table.size)
+        s = B.zeros(nb, max(p.s_total, 1))
+        B.svd(p, merged, t1, s, t2)
+        ks = [int(r[2]) for r in p.sectors]
+        ns = len(ks)
+        if self.Symmetry.length == 0 and relative_cut == 0.0 and nb > 1:
+            # one sector, integer cut: structure known without reading the device (exact zeros excepted)
+            remain = [min(ks[0], remain_cut)] if ns else []
+        elif ns == 0:
+            remain = []
+        else:
+            counts = B.svd_cut(p, s, remain_cut, relative_cut)
+            ch = B.to_numpy(counts)
+            remain = [int(x) for x in ch.max(axis=0)]
+            if nb > 1 and (ch != ch.max(axis=0, keepdims=True)).any():
+                B.svd_mask(p, counts, t1, s, t2)
+        skey = ("svd2", key, tuple(remain), singular_name_u, singular_name_v)
+
+        def build2():
+            pu, pv, s_edges, blocks = _plan.svd_split_plans(self.Edge, p, common_name_u, common_name_v, remain)
+            s_table = block_table(s_edges)
+            blk = []
+            for i, r, sign in blocks:
+                sym = p.s_syms[i]
+                bidx = s_table.block_by_positions((s_edges[0].find_by_symmetry(-sym), s_edges[1].find_by_symmetry(sym)))
+                blk.append((int(p.sectors[i][6]), int(s_table.offsets[bidx]), r, int(sign)))
+            return pu, pv, s_edges, s_table, np.array(blk, dtype=np.int64).reshape(-1, 4)
+
+        pu, pv, s_edges, s_table, blk = _cached(skey, build2)
+        tu, tv = (t1, t2) if p.flag else (t2, t1)
+        u = self._make(pu.names, pu.edges, pu.table, self._run_pack(pu, tu))
+        v = self._make(pv.names, pv.edges, pv.table, self._run_pack(pv, tv))
+        sd = B.zeros(nb, s_table.size)
+        B.diag_scatter(blk, s, sd)
+        st = self._make([singular_name_u, singular_name_v], s_edges, s_table, sd)
+        return u, st, v
+
+    def qr(self, free_names_direction, free_names, common_name_q, common_name_r):
+        B = _bk.get()
+        free = _fs(free_names)
+        key = ("qr", type(self), tuple(self.names), self._edges, free_names_direction, free, common_name_q, common_name_r)
+        p = _cached(key, lambda: _plan.qr_plan(self.Edge, tuple(self.names), self._edges, free_names_direction, free, common_name_q,
+                                                common_name_r))
+        STATS["qr"] += 1
+        nb = self.data.shape[0]
+        merged = self._run_pack(p.merge)
+        if merged is self.data:
+            merged = merged.clone()  # the factorization destroys its input
+        t1 = B.zeros(nb, p.t1_table.size)
+        t2 = B.zeros(nb, p.t2_table.size)
+        B.qr(p, merged, t1, t2)
+        p1, p2 = p.extra
+        r1 = self._make(p1.names, p1.edges, p1.table, self._run_pack(p1, t1))
+        r2 = self._make(p2.names, p2.edges, p2.table, self._run_pack(p2, t2))
+        return (r1, r2) if p.flag else (r2, r1)
+
+    # -- identity ------------------------------------------------------------------------------
+    def identity_(self, pairs):
+        """Set to the identity between the paired edges (identity.hpp); host-side fill, not on the hot path."""
+        pairs = [tuple(p) for p in pairs]
+        half = len(pairs)
+        order = [a for a, _ in pairs] + [b for _, b in pairs]
+        t = self.transpose(order) if order != self.names else self
+        a = np.zeros(t._table.size)
+        S = self.Symmetry
+        for b, pos in enumerate(t._table.positions):
+            dims = [int(d) for d in t._table.dims[b]]
+            ok = True
+            for i in range(half):
+                s0 = t._edges[i].segments[int(pos[i])][0]
+                s1 = t._edges[half + i].segments[int(pos[half + i])][0]
+                if not tuple.__eq__(-s0, s1) or dims[i] != dims[half + i]:
+                    ok = False
+            if not ok:
+                continue
+            n = int(np.prod(dims[:half])) if half else 1
+            blockv = np.eye(n).reshape(dims)
+            off = int(t._table.offsets[b])
+            a[off:off + blockv.size] = blockv.reshape(-1)
+        t = t.same_shape()
+        t._set_host(a)
+        if S.is_fermi_symmetry:
+            raise NotImplementedError("identity_ for fermionic tensors is outside the hot path")
+        r = t.transpose(self.names) if order != self.names else t
+        self._data = r._data
+        return self
+
+    identity = identity_
+
+    # -- out of the hot path -------------------------------------------------------------------
+    def _not_on_path(self, *a, **k):
+        raise NotImplementedError("this Tensor method is outside the sampling-VMC hot path (SURVEY.md section 8)")
+
+    trace = exponential = shrink = expand = clear_symmetry = clear_bose_symmetry = clear_fermi_symmetry = dump = load = _not_on_path

@@ -1,0 +1,250 @@
+"""Thin ctypes layer over the C-ABI of ``libtnsp_b200.so`` (include/tnsp_b200.h).
+
+torch tensors are used only as device buffers (allocation, stream, data_ptr); every numerical
+operation of the hot path is a kernel of this repository's CUDA library.  There is NO CPU
+fallback: ``get()`` raises if the CUDA library or a GPU is missing.
+
+Tests of the host-side logic (planner, TAT API, VMC drivers) on machines without a GPU install a
+checker backend explicitly with ``set_backend`` (see oracle/numpy_backend.py); the product never
+selects it by itself.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libtnsp_b200.so")
+HOST_LIB_PATH = os.path.join(LIB_DIR, "libtnsp_host.so")
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_dbl = ctypes.c_double
+c_vp = ctypes.c_void_p
+
+_backend = None
+_host_lib = None
+
+
+class TnspError(RuntimeError):
+    pass
+
+
+def _declare_host(lib):
+    lib.tnsp_abi_version.restype = c_int
+    lib.tnsp_last_error.restype = ctypes.c_char_p
+    lib.tnsp_launch_count.restype = c_i64
+    lib.tnsp_rng_create_host.restype = c_vp
+    lib.tnsp_rng_create_host.argtypes = [c_int]
+    lib.tnsp_rng_destroy_host.argtypes = [c_vp]
+    lib.tnsp_rng_seed_host.argtypes = [c_vp, c_int, ctypes.c_uint32]
+    lib.tnsp_rng_uniform_int_host.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.tnsp_rng_uniform_real_host.argtypes = [c_vp, c_dbl, c_dbl, c_vp, c_vp]
+    lib.tnsp_rng_normal_host.argtypes = [c_vp, c_int, c_dbl, c_dbl, c_i64, c_vp]
+    return lib
+
+
+def host_lib():
+    """Host-only part of the C-ABI (RNG with libstdc++ semantics); needs no GPU."""
+    global _host_lib
+    if _host_lib is None:
+        path = LIB_PATH if (_backend is not None and isinstance(_backend, CudaBackend)) else HOST_LIB_PATH
+        if not os.path.exists(path):
+            raise TnspError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (or make -C tnsp_b200/csrc)")
+        _host_lib = _declare_host(ctypes.CDLL(path))
+    return _host_lib
+
+
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise TnspError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() / make -C tnsp_b200/csrc")
+        if not torch.cuda.is_available():
+            raise TnspError("tnsp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = lib = _declare_host(ctypes.CDLL(LIB_PATH))
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        P = c_vp
+        lib.tnsp_pack_f64.argtypes = [P, P, c_int, c_i64, P, c_i64, P, c_i64, c_int, P]
+        lib.tnsp_pack_tiled_f64.argtypes = [c_i64] * 9 + [c_int, P, c_i64, P, c_i64, c_int, P]
+        lib.tnsp_gemm_grouped_f64.argtypes = [P, c_int, P, P, c_i64, P, c_i64, P, c_i64, c_int, P]
+        lib.tnsp_qr_batched_f64.argtypes = [P, c_int, P, P, c_i64, P, c_i64, P, c_i64, c_int, c_int, P]
+        lib.tnsp_svd_work_size.restype = c_i64
+        lib.tnsp_svd_work_size.argtypes = [P, c_int]
+        lib.tnsp_svd_batched_f64.argtypes = [P, c_int, P, P, c_i64, P, c_i64, P, c_i64, P, c_i64, P, c_i64, c_int, P]
+        lib.tnsp_svd_cut_f64.argtypes = [P, c_int, c_i64, P, c_i64, c_i64, c_dbl, P, c_int, P]
+        lib.tnsp_svd_mask_f64.argtypes = [P, c_int, P, P, c_i64, P, c_i64, P, c_i64, c_int, P]
+        lib.tnsp_diag_scatter_f64.argtypes = [P, c_int, P, c_i64, P, c_i64, c_int, P]
+        lib.tnsp_norm_f64.argtypes = [P, c_i64, c_i64, c_int, P, c_int, P]
+        lib.tnsp_scale_f64.argtypes = [P, c_i64, P, c_i64, c_int, P, c_i64, c_i64, c_int, P]
+        lib.tnsp_binary_f64.argtypes = [P, c_i64, P, c_i64, c_int, P, c_i64, c_i64, c_int, P]
+        lib.tnsp_unary_f64.argtypes = [P, c_i64, c_int, P, c_i64, c_i64, c_int, P]
+        lib.tnsp_grad_accumulate_f64.argtypes = [P, c_i64, P, P, P, P, c_i64, c_int, P]
+        lib.tnsp_block_sign_f64.argtypes = [P, c_int, P, c_i64, P, c_i64, c_i64, c_int, P]
+        lib.tnsp_gather_rows_f64.argtypes = [P, c_i64, P, P, c_i64, c_int, P]
+        lib.tnsp_select_f64.argtypes = [P, P, c_i64, P, c_i64, P, c_i64, c_i64, c_int, P]
+
+    # -- buffers ------------------------------------------------------------------------------
+    def empty(self, nb, size):
+        return torch.empty((nb, size), dtype=torch.float64, device=self.device)
+
+    def zeros(self, nb, size):
+        return torch.zeros((nb, size), dtype=torch.float64, device=self.device)
+
+    def from_numpy(self, array):
+        return torch.from_numpy(np.ascontiguousarray(array)).to(self.device)
+
+    def to_numpy(self, t):
+        return t.detach().cpu().numpy()
+
+    def upload(self, array):
+        return torch.from_numpy(np.ascontiguousarray(array)).to(self.device)
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TnspError(self.lib.tnsp_last_error().decode())
+
+    @staticmethod
+    def _bs(t):
+        """batch stride in elements (0 broadcasts a single entry)"""
+        return 0 if t.shape[0] == 1 else t.stride(0)
+
+    def launch_count(self):
+        return int(self.lib.tnsp_launch_count())
+
+    def synchronize(self):
+        torch.cuda.synchronize()
+
+    # -- kernels ------------------------------------------------------------------------------
+    def pack(self, plan, src, dst):
+        dev = plan._dev
+        if dev is None:
+            dev = plan._dev = (self.upload(plan.desc), self.upload(plan.estart))
+        nb = dst.shape[0]
+        self._ck(self.lib.tnsp_pack_f64(dev[0].data_ptr(), dev[1].data_ptr(), len(plan.desc), plan.total, src.data_ptr(), self._bs(src),
+                                        dst.data_ptr(), dst.stride(0), nb, self._stream()))
+
+    def gemm(self, plan, a, b, c):
+        dev = plan._dev
+        if dev is None:
+            dev = plan._dev = self.upload(plan.gemm)
+        nb = c.shape[0]
+        self._ck(self.lib.tnsp_gemm_grouped_f64(dev.data_ptr(), len(plan.gemm), plan.gemm.ctypes.data, a.data_ptr(), self._bs(a),
+                                                b.data_ptr(), self._bs(b), c.data_ptr(), c.stride(0), nb, self._stream()))
+
+    def _sect(self, plan):
+        dev = plan._dev
+        if dev is None:
+            dev = plan._dev = self.upload(plan.sectors)
+        return dev
+
+    def qr(self, plan, a, out1, out2):
+        dev = self._sect(plan)
+        nb = a.shape[0]
+        self._ck(self.lib.tnsp_qr_batched_f64(dev.data_ptr(), len(plan.sectors), plan.sectors.ctypes.data, a.data_ptr(), a.stride(0),
+                                              out1.data_ptr(), out1.stride(0), out2.data_ptr(), out2.stride(0), int(plan.flag), nb,
+                                              self._stream()))
+
+    def svd(self, plan, a, out1, s, out2):
+        dev = self._sect(plan)
+        nb = a.shape[0]
+        wsize = int(self.lib.tnsp_svd_work_size(plan.sectors.ctypes.data, len(plan.sectors)))
+        work = self.empty(nb, max(wsize, 1))
+        self._ck(self.lib.tnsp_svd_batched_f64(dev.data_ptr(), len(plan.sectors), plan.sectors.ctypes.data, a.data_ptr(), a.stride(0),
+                                               out1.data_ptr(), out1.stride(0), s.data_ptr(), s.stride(0), out2.data_ptr(),
+                                               out2.stride(0), work.data_ptr(), work.stride(0), nb, self._stream()))
+
+    def svd_cut(self, plan, s, remain_cut, relative_cut):
+        dev = self._sect(plan)
+        nb = s.shape[0]
+        counts = torch.empty((nb, len(plan.sectors)), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.tnsp_svd_cut_f64(dev.data_ptr(), len(plan.sectors), plan.s_total, s.data_ptr(), s.stride(0), int(remain_cut),
+                                           float(relative_cut), counts.data_ptr(), nb, self._stream()))
+        return counts
+
+    def svd_mask(self, plan, counts, out1, s, out2):
+        dev = self._sect(plan)
+        nb = s.shape[0]
+        self._ck(self.lib.tnsp_svd_mask_f64(dev.data_ptr(), len(plan.sectors), counts.data_ptr(), out1.data_ptr(), out1.stride(0),
+                                            s.data_ptr(), s.stride(0), out2.data_ptr(), out2.stride(0), nb, self._stream()))
+
+    def diag_scatter(self, blk, s, dst):
+        if len(blk) == 0:
+            return
+        d = self.upload(blk)
+        self._ck(self.lib.tnsp_diag_scatter_f64(d.data_ptr(), len(blk), s.data_ptr(), s.stride(0), dst.data_ptr(), dst.stride(0),
+                                                dst.shape[0], self._stream()))
+
+    def norm(self, x, kind):
+        nb = x.shape[0]
+        out = torch.empty(nb, dtype=torch.float64, device=self.device)
+        self._ck(self.lib.tnsp_norm_f64(x.data_ptr(), x.stride(0), x.shape[1], kind, out.data_ptr(), nb, self._stream()))
+        return out
+
+    def scale(self, x, alpha, op, nb=None):
+        """y[b] = x[b] * alpha[b] (op 0) or x[b] / alpha[b] (op 1); alpha is a device vector of nb or 1 entries."""
+        nb = max(x.shape[0], alpha.shape[0]) if nb is None else nb
+        y = self.empty(nb, x.shape[1])
+        self._ck(self.lib.tnsp_scale_f64(x.data_ptr(), self._bs(x), alpha.data_ptr(), 0 if alpha.shape[0] == 1 else 1, op, y.data_ptr(),
+                                         y.stride(0), x.shape[1], nb, self._stream()))
+        return y
+
+    def binary(self, a, b, op):
+        nb = max(a.shape[0], b.shape[0])
+        z = self.empty(nb, a.shape[1])
+        self._ck(self.lib.tnsp_binary_f64(a.data_ptr(), self._bs(a), b.data_ptr(), self._bs(b), op, z.data_ptr(), z.stride(0), a.shape[1],
+                                          nb, self._stream()))
+        return z
+
+    def unary(self, a, op):
+        z = self.empty(a.shape[0], a.shape[1])
+        self._ck(self.lib.tnsp_unary_f64(a.data_ptr(), a.stride(0), op, z.data_ptr(), z.stride(0), a.shape[1], a.shape[0], self._stream()))
+        return z
+
+    def block_sign(self, blk, x):
+        y = self.empty(x.shape[0], x.shape[1])
+        d = self.upload(blk)
+        self._ck(self.lib.tnsp_block_sign_f64(d.data_ptr(), len(blk), x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[1],
+                                              x.shape[0], self._stream()))
+        return y
+
+    def gather_rows(self, src, row_size, index):
+        """dst[b] = src.view(-1,row_size)[index[b]]; index int32 device vector"""
+        nb = index.shape[0]
+        dst = self.empty(nb, row_size)
+        self._ck(self.lib.tnsp_gather_rows_f64(src.data_ptr(), row_size, index.data_ptr(), dst.data_ptr(), dst.stride(0), nb,
+                                               self._stream()))
+        return dst
+
+    def select(self, mask, a, b):
+        nb = mask.shape[0]
+        dst = self.empty(nb, a.shape[1])
+        self._ck(self.lib.tnsp_select_f64(mask.data_ptr(), a.data_ptr(), self._bs(a), b.data_ptr(), self._bs(b), dst.data_ptr(),
+                                          dst.stride(0), a.shape[1], nb, self._stream()))
+        return dst
+
+    def grad_accumulate(self, holes, weight, energy, delta, edelta):
+        self._ck(self.lib.tnsp_grad_accumulate_f64(holes.data_ptr(), holes.stride(0), weight.data_ptr(), energy.data_ptr(),
+                                                   delta.data_ptr(), edelta.data_ptr(), holes.shape[1], holes.shape[0], self._stream()))
+
+
+def set_backend(backend):
+    """Install a backend object explicitly (tests only)."""
+    global _backend, _host_lib
+    _backend = backend
+    _host_lib = None
+
+
+def get():
+    global _backend
+    if _backend is None:
+        _backend = CudaBackend()
+    return _backend

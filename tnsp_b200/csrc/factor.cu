@@ -1,0 +1,420 @@
+// K3/K4: batched Householder QR/LQ and batched one-sided Jacobi SVD over (sector x chain), plus the
+// reference's greedy cross-sector truncation.
+//
+// Replaces the per-sector LAPACK calls of the reference:
+//   qr.hpp:178-304   (?geqrf + ?orgqr  /  ?gelqf + ?orglq, explicit thin Q)
+//   svd.hpp:104-211  (?gesvd 'S','S')
+//   svd.hpp:429-481  (global greedy cut across sectors)
+// One CTA owns one (sector, chain) matrix; the working set lives in shared memory when it fits
+// (<= kSmemDoubles) and in an L2-resident global scratch otherwise.
+//
+// Roofline: HBM/L2 bound streaming of small matrices; algorithmic bytes are stated in DESIGN.md.
+#include "common.cuh"
+
+namespace tnsp {
+
+constexpr int kFactorThreads = 256;
+constexpr int kSmemDoubles = 24 * 1024;   // 192 KiB of dynamic shared memory for the working set
+
+// ------------------------------------------------------------------------------------------------
+// QR: logical matrix X (p x q), element (i, j) at W[i * rs + j * cs].
+//   use_qr : X = M        (p = m, q = n, rs = n, cs = 1)   out1 = Q (m x k), out2 = R (k x n)
+//   LQ     : X = M^T      (p = n, q = m, rs = 1, cs = n)   out1 = L = R^T (m x k), out2 = Q^T (k x n)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFactorThreads) qr_kernel(const int64_t* __restrict__ sect, double* __restrict__ a, int64_t abs_,
+                                                            double* __restrict__ out1, int64_t o1bs, double* __restrict__ out2,
+                                                            int64_t o2bs, int use_qr, int nb) {
+    extern __shared__ double smem[];
+    __shared__ double red[32];
+    __shared__ double sh_tau, sh_scale, sh_beta;
+    const int64_t* sc = sect + (int64_t)blockIdx.x * TNSP_SECT_COLS;
+    const int64_t m = sc[0], n = sc[1], k = sc[2];
+    if (m * n == 0) return;
+    const int64_t p = use_qr ? m : n, q = use_qr ? n : m;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* tau = smem;                 // [k]
+    double* buf = smem + k;             // [p*q] when it fits
+    const bool in_smem = (p * q + k) <= kSmemDoubles;
+
+    for (int b = blockIdx.y; b < nb; b += gridDim.y) {
+        double* A = a + (int64_t)b * abs_ + sc[3];
+        double* W;
+        int64_t rs, cs;
+        if (in_smem) {
+            // stage row-major X into shared memory (X[i][j] at buf[i*q + j])
+            W = buf; rs = q; cs = 1;
+            if (use_qr) {
+                for (int64_t e = tid; e < p * q; e += nt) buf[e] = A[e];
+            } else {
+                // X = M^T : X[i][j] = M[j][i] = A[j*n + i]; read coalesced over A, scatter into smem
+                for (int64_t e = tid; e < m * n; e += nt) {
+                    const int64_t j = e / n, i = e - j * n;
+                    buf[i * q + j] = A[e];
+                }
+            }
+        } else {
+            W = A;
+            if (use_qr) { rs = n; cs = 1; } else { rs = 1; cs = n; }
+        }
+        __syncthreads();
+
+        for (int64_t j = 0; j < k; ++j) {
+            // Householder vector of column j (LAPACK dlarfg convention: v0 = 1)
+            double part = 0.0;
+            for (int64_t i = j + 1 + tid; i < p; i += nt) {
+                const double v = W[i * rs + j * cs];
+                part += v * v;
+            }
+            const double xnorm2 = block_sum(part, red);
+            if (tid == 0) {
+                const double alpha = W[j * rs + j * cs];
+                if (xnorm2 == 0.0) {
+                    sh_tau = 0.0; sh_scale = 0.0; sh_beta = alpha;
+                } else {
+                    const double beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+                    sh_tau = (beta - alpha) / beta;
+                    sh_scale = 1.0 / (alpha - beta);
+                    sh_beta = beta;
+                }
+                tau[j] = sh_tau;
+                W[j * rs + j * cs] = sh_beta;
+            }
+            __syncthreads();
+            const double tj = sh_tau, scale = sh_scale;
+            if (tj != 0.0) {
+                for (int64_t i = j + 1 + tid; i < p; i += nt) W[i * rs + j * cs] *= scale;
+                __syncthreads();
+                // trailing update, one thread per column (rows serial)
+                for (int64_t cidx = j + 1 + tid; cidx < q; cidx += nt) {
+                    double w = W[j * rs + cidx * cs];
+                    for (int64_t i = j + 1; i < p; ++i) w += W[i * rs + j * cs] * W[i * rs + cidx * cs];
+                    w *= tj;
+                    W[j * rs + cidx * cs] -= w;
+                    for (int64_t i = j + 1; i < p; ++i) W[i * rs + cidx * cs] -= w * W[i * rs + j * cs];
+                }
+            }
+            __syncthreads();
+        }
+
+        // R (k x q): upper trapezoid of W
+        if (use_qr) {
+            double* Rm = out2 + (int64_t)b * o2bs + sc[5];   // k x n
+            for (int64_t e = tid; e < k * q; e += nt) {
+                const int64_t i = e / q, j = e - i * q;
+                Rm[e] = (j >= i) ? W[i * rs + j * cs] : 0.0;
+            }
+        } else {
+            double* Lm = out1 + (int64_t)b * o1bs + sc[4];   // m x k, L[r][i] = R[i][r], q == m
+            for (int64_t e = tid; e < q * k; e += nt) {
+                const int64_t r = e / k, i = e - r * k;
+                Lm[e] = (r >= i) ? W[i * rs + r * cs] : 0.0;
+            }
+        }
+        __syncthreads();
+
+        // explicit Q in place (LAPACK dorg2r), first k columns of W
+        for (int64_t j = k - 1; j >= 0; --j) {
+            const double tj = tau[j];
+            // apply H(j) to W(j:p, j+1:k) from the left with v = [1; W(j+1:p, j)]
+            for (int64_t cidx = j + 1 + tid; cidx < k; cidx += nt) {
+                double w = W[j * rs + cidx * cs];
+                for (int64_t i = j + 1; i < p; ++i) w += W[i * rs + j * cs] * W[i * rs + cidx * cs];
+                w *= tj;
+                W[j * rs + cidx * cs] -= w;
+                for (int64_t i = j + 1; i < p; ++i) W[i * rs + cidx * cs] -= w * W[i * rs + j * cs];
+            }
+            __syncthreads();
+            for (int64_t i = j + 1 + tid; i < p; i += nt) W[i * rs + j * cs] *= -tj;
+            if (tid == 0) W[j * rs + j * cs] = 1.0 - tj;
+            for (int64_t i = tid; i < j; i += nt) W[i * rs + j * cs] = 0.0;
+            __syncthreads();
+        }
+        if (use_qr) {
+            double* Qm = out1 + (int64_t)b * o1bs + sc[4];   // m x k
+            for (int64_t e = tid; e < p * k; e += nt) {
+                const int64_t i = e / k, j = e - i * k;
+                Qm[e] = W[i * rs + j * cs];
+            }
+        } else {
+            double* Qm = out2 + (int64_t)b * o2bs + sc[5];   // k x n, Q[j][i] = Qx[i][j], p == n
+            for (int64_t e = tid; e < k * p; e += nt) {
+                const int64_t j = e / p, i = e - j * p;
+                Qm[e] = W[i * rs + j * cs];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-sided Jacobi (Hestenes) SVD.  Logical X (p x q, p >= q): X = M if m >= n else M^T.
+// G[c][0..p) holds column c of X contiguously, V[c][0..q) column c of the accumulated rotations.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFactorThreads) svd_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a,
+                                                             int64_t abs_, double* __restrict__ out1, int64_t o1bs,
+                                                             double* __restrict__ sv, int64_t sbs, double* __restrict__ out2,
+                                                             int64_t o2bs, double* __restrict__ work, int64_t wbs,
+                                                             const int64_t* __restrict__ work_off, int nb) {
+    extern __shared__ double smem[];
+    __shared__ int sh_rot;
+    const int64_t* sc = sect + (int64_t)blockIdx.x * TNSP_SECT_COLS;
+    const int64_t m = sc[0], n = sc[1], k = sc[2];
+    if (m * n == 0) return;
+    const bool tall = m >= n;
+    const int64_t p = tall ? m : n, q = tall ? n : m;   // q == k
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int64_t need = q * p + q * q + 2 * q;
+    const bool in_smem = need <= kSmemDoubles;
+
+    for (int b = blockIdx.y; b < nb; b += gridDim.y) {
+        const double* A = a + (int64_t)b * abs_ + sc[3];
+        double* base = in_smem ? smem : (work + (int64_t)b * wbs + work_off[blockIdx.x]);
+        double* G = base;
+        double* V = base + q * p;
+        double* sig = V + q * q;
+        int* rnk = reinterpret_cast<int*>(sig + q);
+
+        if (tall) {
+            // G[c][r] = M[r][c]
+            for (int64_t e = tid; e < m * n; e += nt) {
+                const int64_t r = e / n, cidx = e - r * n;
+                G[cidx * p + r] = A[e];
+            }
+        } else {
+            // X = M^T: column c of X is row c of M (contiguous)
+            for (int64_t e = tid; e < m * n; e += nt) G[e] = A[e];
+        }
+        for (int64_t e = tid; e < q * q; e += nt) V[e] = ((e / q) == (e % q)) ? 1.0 : 0.0;
+        __syncthreads();
+
+        const int64_t qe = q + (q & 1);   // even number of players
+        const double tol = fmax(1e-15, sqrt((double)p) * 2.3e-16);
+        for (int sweep = 0; sweep < 60 && q > 1; ++sweep) {
+            if (tid == 0) sh_rot = 0;
+            __syncthreads();
+            for (int64_t round = 0; round < qe - 1; ++round) {
+                for (int64_t pr = warp; pr < qe / 2; pr += nw) {
+                    int64_t i, j;
+                    if (pr == 0) { i = qe - 1; j = round; }
+                    else { i = (round + pr) % (qe - 1); j = (round - pr + (qe - 1)) % (qe - 1); }
+                    if (i >= q || j >= q) continue;
+                    if (i > j) { const int64_t t = i; i = j; j = t; }
+                    double* gi = G + i * p;
+                    double* gj = G + j * p;
+                    double aa = 0.0, bb = 0.0, cc = 0.0;
+                    for (int64_t r = lane; r < p; r += 32) {
+                        const double x = gi[r], y = gj[r];
+                        aa += x * x; bb += y * y; cc += x * y;
+                    }
+                    aa = warp_sum(aa); bb = warp_sum(bb); cc = warp_sum(cc);
+                    if (fabs(cc) > tol * sqrt(aa * bb) && aa * bb > 0.0) {
+                        const double zeta = (bb - aa) / (2.0 * cc);
+                        const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+                        for (int64_t r = lane; r < p; r += 32) {
+                            const double x = gi[r], y = gj[r];
+                            gi[r] = cs * x - sn * y;
+                            gj[r] = sn * x + cs * y;
+                        }
+                        double* vi = V + i * q;
+                        double* vj = V + j * q;
+                        for (int64_t r = lane; r < q; r += 32) {
+                            const double x = vi[r], y = vj[r];
+                            vi[r] = cs * x - sn * y;
+                            vj[r] = sn * x + cs * y;
+                        }
+                        if (lane == 0) sh_rot = 1;
+                    }
+                }
+                __syncthreads();
+            }
+            const int any = sh_rot;
+            __syncthreads();
+            if (!any) break;
+        }
+
+        // singular values and their descending order
+        for (int64_t cidx = warp; cidx < q; cidx += nw) {
+            double s2 = 0.0;
+            for (int64_t r = lane; r < p; r += 32) s2 += G[cidx * p + r] * G[cidx * p + r];
+            s2 = warp_sum(s2);
+            if (lane == 0) sig[cidx] = sqrt(s2);
+        }
+        __syncthreads();
+        for (int64_t cidx = tid; cidx < q; cidx += nt) {
+            const double s = sig[cidx];
+            int r = 0;
+            for (int64_t o = 0; o < q; ++o) {
+                const double so = sig[o];
+                r += (so > s) || (so == s && o < cidx);
+            }
+            rnk[cidx] = r;
+        }
+        __syncthreads();
+        double* S = sv + (int64_t)b * sbs + sc[6];
+        double* O1 = out1 + (int64_t)b * o1bs + sc[4];   // m x k
+        double* O2 = out2 + (int64_t)b * o2bs + sc[5];   // k x n
+        for (int64_t cidx = tid; cidx < q; cidx += nt) S[rnk[cidx]] = sig[cidx];
+        if (tall) {
+            // U[r][jj] = G[c][r] / sigma_c ; Vt[jj][t] = V[c][t]
+            for (int64_t e = tid; e < m * k; e += nt) {
+                const int64_t cidx = e / m, r = e - cidx * m;
+                const double s = sig[cidx];
+                O1[r * k + rnk[cidx]] = s > 0.0 ? G[cidx * p + r] / s : 0.0;
+            }
+            for (int64_t e = tid; e < k * n; e += nt) {
+                const int64_t cidx = e / n, t = e - cidx * n;
+                O2[(int64_t)rnk[cidx] * n + t] = V[cidx * q + t];
+            }
+        } else {
+            // U[t][jj] = V[c][t] ; Vt[jj][r] = G[c][r] / sigma_c
+            for (int64_t e = tid; e < m * k; e += nt) {
+                const int64_t cidx = e / m, t = e - cidx * m;
+                O1[t * k + rnk[cidx]] = V[cidx * q + t];
+            }
+            for (int64_t e = tid; e < k * n; e += nt) {
+                const int64_t cidx = e / n, r = e - cidx * n;
+                const double s = sig[cidx];
+                O2[(int64_t)rnk[cidx] * n + r] = s > 0.0 ? G[cidx * p + r] / s : 0.0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Greedy cross-sector truncation (svd.hpp:429-481) as a global ranking: value (i,t) is kept iff
+// fewer than remain_cut values precede it in (value desc, sector asc, position asc) order and it
+// exceeds relative_cut * max.  One CTA per chain.
+__global__ void svd_cut_kernel(const int64_t* __restrict__ sect, int ns, int64_t s_total, const double* __restrict__ s, int64_t sbs,
+                               int64_t remain_cut, double relative_cut, int32_t* __restrict__ counts) {
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    const double* S = s + (int64_t)b * sbs;
+    int32_t* cnt = counts + (int64_t)b * ns;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) cnt[i] = 0;
+    double mx = 0.0;
+    for (int64_t e = threadIdx.x; e < s_total; e += blockDim.x) mx = fmax(mx, S[e]);
+    mx = block_max(mx, red);
+    const double thr = relative_cut * mx;
+    for (int64_t e = threadIdx.x; e < s_total; e += blockDim.x) {
+        const double v = S[e];
+        if (!(v > thr)) continue;
+        // sector of e
+        int sec = 0;
+        for (; sec < ns; ++sec) {
+            const int64_t off = sect[sec * TNSP_SECT_COLS + 6], kk = sect[sec * TNSP_SECT_COLS + 2];
+            if (e >= off && e < off + kk) break;
+        }
+        int64_t before = 0;
+        for (int64_t o = 0; o < s_total; ++o) {
+            const double w = S[o];
+            before += (w > v) || (w == v && o < e);
+        }
+        if (before < remain_cut) atomicAdd(cnt + sec, 1);
+    }
+}
+
+__global__ void svd_mask_kernel(const int64_t* __restrict__ sect, const int32_t* __restrict__ counts, int ns, double* __restrict__ out1,
+                                int64_t o1bs, double* __restrict__ s, int64_t sbs, double* __restrict__ out2, int64_t o2bs, int nb) {
+    const int64_t* sc = sect + (int64_t)blockIdx.x * TNSP_SECT_COLS;
+    const int64_t m = sc[0], n = sc[1], k = sc[2];
+    for (int b = blockIdx.y; b < nb; b += gridDim.y) {
+        const int64_t keep = counts[(int64_t)b * ns + blockIdx.x];
+        if (keep >= k) continue;
+        double* O1 = out1 + (int64_t)b * o1bs + sc[4];
+        double* O2 = out2 + (int64_t)b * o2bs + sc[5];
+        double* S = s + (int64_t)b * sbs + sc[6];
+        const int64_t w = k - keep;
+        for (int64_t e = threadIdx.x; e < m * w; e += blockDim.x) O1[(e / w) * k + keep + (e % w)] = 0.0;
+        for (int64_t e = threadIdx.x; e < w * n; e += blockDim.x) O2[keep * n + e] = 0.0;
+        for (int64_t e = threadIdx.x; e < w; e += blockDim.x) S[keep + e] = 0.0;
+    }
+}
+
+static int64_t svd_need(int64_t m, int64_t n) {
+    const int64_t p = m >= n ? m : n, q = m >= n ? n : m;
+    return q * p + q * q + 2 * q;
+}
+
+}  // namespace tnsp
+
+using namespace tnsp;
+
+extern "C" int tnsp_qr_batched_f64(const int64_t* sect, int ns, const int64_t* sh, double* a, int64_t abs_, double* out1, int64_t o1bs,
+                                   double* out2, int64_t o2bs, int use_qr, int nb, void* stream) {
+    if (ns == 0 || nb == 0) return 0;
+    int64_t smem = 0;
+    for (int i = 0; i < ns; ++i) {
+        const int64_t m = sh[i * TNSP_SECT_COLS], n = sh[i * TNSP_SECT_COLS + 1], k = sh[i * TNSP_SECT_COLS + 2];
+        int64_t need = (m * n + k <= kSmemDoubles) ? (m * n + k) : k;
+        if (k > kSmemDoubles) { set_error("tnsp_qr_batched_f64: k too large"); return 1; }
+        if (need > smem) smem = need;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDoubles * 8);
+        attr_set = true;
+    }
+    const int gy = nb > 65535 ? 65535 : nb;
+    qr_kernel<<<dim3(ns, gy), kFactorThreads, smem * 8, (cudaStream_t)stream>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb);
+    return check_launch("tnsp_qr_batched_f64");
+}
+
+extern "C" int64_t tnsp_svd_work_size(const int64_t* sh, int ns) {
+    int64_t total = 0;
+    for (int i = 0; i < ns; ++i) total += svd_need(sh[i * TNSP_SECT_COLS], sh[i * TNSP_SECT_COLS + 1]);
+    return total;
+}
+
+extern "C" int tnsp_svd_batched_f64(const int64_t* sect, int ns, const int64_t* sh, const double* a, int64_t abs_, double* out1,
+                                    int64_t o1bs, double* s, int64_t sbs, double* out2, int64_t o2bs, double* work, int64_t wbs,
+                                    int nb, void* stream) {
+    if (ns == 0 || nb == 0) return 0;
+    int64_t smem = 0;
+    // per-sector offsets into the scratch (device copy lives at the tail of `work`'s first chain? no:
+    // offsets are small, pass them through a tiny device buffer allocated once per call site)
+    static int64_t* d_off = nullptr;
+    static int d_off_cap = 0;
+    if (ns > d_off_cap) {
+        if (d_off) cudaFree(d_off);
+        d_off_cap = ns < 64 ? 64 : 2 * ns;
+        if (cudaMalloc(&d_off, sizeof(int64_t) * d_off_cap) != cudaSuccess) { set_error("tnsp_svd_batched_f64: cudaMalloc"); return 1; }
+    }
+    int64_t offs[4096];
+    if (ns > 4096) { set_error("tnsp_svd_batched_f64: too many sectors"); return 1; }
+    int64_t acc = 0;
+    bool need_global = false;
+    for (int i = 0; i < ns; ++i) {
+        offs[i] = acc;
+        const int64_t need = svd_need(sh[i * TNSP_SECT_COLS], sh[i * TNSP_SECT_COLS + 1]);
+        acc += need;
+        if (sh[i * TNSP_SECT_COLS] * sh[i * TNSP_SECT_COLS + 1] == 0) continue;
+        if (need <= kSmemDoubles) { if (need > smem) smem = need; } else need_global = true;
+    }
+    if (need_global && (work == nullptr || wbs < acc)) { set_error("tnsp_svd_batched_f64: scratch too small"); return 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (need_global) cudaMemcpyAsync(d_off, offs, sizeof(int64_t) * ns, cudaMemcpyHostToDevice, st);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(svd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDoubles * 8);
+        attr_set = true;
+    }
+    const int gy = nb > 65535 ? 65535 : nb;
+    svd_kernel<<<dim3(ns, gy), kFactorThreads, smem * 8, st>>>(sect, a, abs_, out1, o1bs, s, sbs, out2, o2bs, work, wbs, d_off, nb);
+    return check_launch("tnsp_svd_batched_f64");
+}
+
+extern "C" int tnsp_svd_cut_f64(const int64_t* sect, int ns, int64_t s_total, const double* s, int64_t sbs, int64_t remain_cut,
+                                double relative_cut, int32_t* counts, int nb, void* stream) {
+    if (nb == 0 || ns == 0) return 0;
+    svd_cut_kernel<<<nb, 128, 0, (cudaStream_t)stream>>>(sect, ns, s_total, s, sbs, remain_cut, relative_cut, counts);
+    return check_launch("tnsp_svd_cut_f64");
+}
+
+extern "C" int tnsp_svd_mask_f64(const int64_t* sect, int ns, const int32_t* counts, double* out1, int64_t o1bs, double* s,
+                                 int64_t sbs, double* out2, int64_t o2bs, int nb, void* stream) {
+    if (nb == 0 || ns == 0) return 0;
+    const int gy = nb > 65535 ? 65535 : nb;
+    svd_mask_kernel<<<dim3(ns, gy), 128, 0, (cudaStream_t)stream>>>(sect, counts, ns, out1, o1bs, s, sbs, out2, o2bs, nb);
+    return check_launch("tnsp_svd_mask_f64");
+}
