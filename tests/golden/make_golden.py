@@ -1,0 +1,222 @@
+"""Generates the golden fixtures of tests/golden/*.npz by running the UNMODIFIED reference
+(PyTAT from oracle/_ref, tetragono/tetraku imported from /root/reference, single-rank mpi4py stub
+from oracle/stubs) in THIS container.  The fixtures travel to the GPU box; the reference does not.
+
+    python tests/golden/make_golden.py            # re-spawns itself with the reference environment
+
+Each fixture holds a complete, self-describing model (edges, Hamiltonian terms, PEPS tensors) plus
+the reference's results on it:
+  ws            amplitude <s|psi> of a fixed configuration, cache-cold (single_layer_auxiliaries.py:710-716)
+  energy_s      local energy E_s of that configuration                  (observer.py:313-398)
+  holes         <psi|s|d_x psi>/<psi|s|psi> for every site              (lattice.py:362-416)
+  traj_*        a sweep-sampling trajectory from a fixed seed           (sampling.py:117-154)
+  energy/gradient/natural gradient accumulated over that trajectory     (observer.py:83-126,542-675)
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = "/root/reference"
+
+
+def _respawn():
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([
+        os.path.join(ROOT, "oracle", "_ref"), os.path.join(ROOT, "oracle", "stubs"), f"{REF}/tetragono", f"{REF}/tetraku",
+        f"{REF}/lazy_graph", f"{REF}/PyScalapack"
+    ])
+    env["TNSP_GOLDEN_CHILD"] = "1"
+    env["OPENBLAS_NUM_THREADS"] = "1"
+    sys.exit(subprocess.call([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env))
+
+
+if os.environ.get("TNSP_GOLDEN_CHILD") != "1":
+    _respawn()
+
+import numpy as np  # noqa: E402
+import TAT  # noqa: E402
+import tetragono as tet  # noqa: E402
+
+FIELDS = {"No": (), "BoseZ2": ("z2",), "BoseU1": ("u1",), "FermiU1": ("fermi",), "FermiZ2": ("parity",),
+          "FermiU1BoseZ2": ("fermi", "z2"), "FermiU1BoseU1": ("fermi", "u1"), "FermiU1FermiU1": ("fermi_0", "fermi_1")}
+
+
+def sym_tuple(sym_name, s):
+    return [int(getattr(s, f)) for f in FIELDS[sym_name]]
+
+
+def edge_desc(sym_name, e):
+    return {"segments": [[sym_tuple(sym_name, s), int(d)] for s, d in e.segments], "arrow": bool(e.arrow)}
+
+
+def tensor_desc(sym_name, t, arrays, key):
+    arrays[key] = np.array(t.storage, dtype=np.float64)
+    return {"names": [str(n) for n in t.names], "edges": [edge_desc(sym_name, t.edge_by_name(n)) for n in t.names], "storage": key}
+
+
+def point_desc(sym_name, p):
+    return [sym_tuple(sym_name, p[0]), int(p[1])]
+
+
+def dump_case(name, sym_name, lattice, Dc, config_points, seed, n_samples, cg_step=2):
+    arrays = {}
+    meta = {"symmetry": sym_name, "L1": lattice.L1, "L2": lattice.L2, "Dc": Dc,
+            "total_symmetry": sym_tuple(sym_name, lattice.total_symmetry)}
+    meta["physics_edges"] = [[{str(o): edge_desc(sym_name, e) for o, e in lattice.physics_edges[l1, l2].items()}
+                              for l2 in range(lattice.L2)] for l1 in range(lattice.L1)]
+    meta["hamiltonians"] = []
+    for i, (positions, h) in enumerate(lattice._hamiltonians.items()):   # insertion order = sweep tie order
+        meta["hamiltonians"].append({"positions": [list(p) for p in positions], "tensor": tensor_desc(sym_name, h, arrays, f"ham_{i}")})
+    meta["sites"] = [[tensor_desc(sym_name, lattice[l1, l2], arrays, f"site_{l1}_{l2}") for l2 in range(lattice.L2)]
+                     for l1 in range(lattice.L1)]
+    meta["config"] = [[{str(o): point_desc(sym_name, config_points[l1][l2][o]) for o in config_points[l1][l2]}
+                       for l2 in range(lattice.L2)] for l1 in range(lattice.L1)]
+
+    # --- single fresh configuration: ws, E_s, holes -------------------------------------------------
+    conf = tet.sampling_lattice.Configuration(lattice, Dc)
+    for l1 in range(lattice.L1):
+        for l2 in range(lattice.L2):
+            for o, p in config_points[l1][l2].items():
+                conf[l1, l2, o] = p
+    ws = conf.hole(())
+    arrays["ws"] = np.array([float(ws)])
+    meta["ws_names"] = [str(n) for n in ws.names]
+    obs = tet.sampling_lattice.Observer(lattice, enable_energy=True, enable_gradient=True)
+    with obs:
+        obs(float(ws)**2, conf)
+    arrays["energy_s"] = np.array([obs._whole_result_reweight["energy"] / obs._total_weight])
+    holes = conf.holes()
+    meta["holes"] = [[tensor_desc(sym_name, holes[l1][l2], arrays, f"hole_{l1}_{l2}") for l2 in range(lattice.L2)]
+                     for l1 in range(lattice.L1)]
+
+    # --- sweep trajectory from a fixed seed -----------------------------------------------------------
+    TAT.random.seed(seed)
+    sampling = tet.sampling_lattice.SweepSampling(lattice, Dc, None, None)
+    for l1 in range(lattice.L1):
+        for l2 in range(lattice.L2):
+            for o, p in config_points[l1][l2].items():
+                sampling.configuration[l1, l2, o] = p
+    obs = tet.sampling_lattice.Observer(lattice, enable_energy=True, enable_gradient=True, enable_natural_gradient=True)
+    traj, poss = [], []
+    with obs:
+        for _ in range(n_samples):
+            p, c = sampling()
+            traj.append(c.export_configuration())
+            poss.append(p)
+            obs(p, c)
+    arrays["traj_config"] = np.array(traj)
+    arrays["traj_possibility"] = np.array(poss)
+    arrays["traj_energy"] = np.array(obs.total_energy)
+    grad = obs.gradient
+    meta["gradient"] = [[tensor_desc(sym_name, grad[l1][l2], arrays, f"grad_{l1}_{l2}") for l2 in range(lattice.L2)]
+                        for l1 in range(lattice.L1)]
+    ng = obs.natural_gradient_by_conjugate_gradient(cg_step, 0.0)
+    meta["natural_gradient"] = [[tensor_desc(sym_name, ng[l1][l2], arrays, f"ng_{l1}_{l2}") for l2 in range(lattice.L2)]
+                                for l1 in range(lattice.L1)]
+    meta["seed"], meta["n_samples"], meta["cg_step"] = seed, n_samples, cg_step
+    arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    out = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(out, **arrays)
+    print(name, "ws", arrays["ws"], "E_s", arrays["energy_s"], "traj E", arrays["traj_energy"], os.path.getsize(out), "bytes")
+
+
+def neel(lattice):
+    S = lattice.Symmetry
+    return [[{0: (S(), (l1 + l2) % 2)} for l2 in range(lattice.L2)] for l1 in range(lattice.L1)]
+
+
+def heisenberg(L1, L2, D):
+    from tetraku.models.heisenberg import abstract_lattice
+    TAT.random.seed(2333)
+    return tet.SamplingLattice(abstract_lattice(L1, L2, D, 1.0))
+
+
+def heisenberg_u1(L1, L2, d):
+    """spin-1/2 Heisenberg with U(1) (2 Sz) symmetric tensors; virtual bonds {-1,0,+1} x d (cfg2 family)"""
+    T = TAT.BoseU1.D.Tensor
+    state = tet.AbstractState(T, L1, L2)
+    pe = [(+1, 1), (-1, 1)]
+    state.physics_edges[...] = pe
+    cpe = [(-1, 1), (+1, 1)]
+    SS = T(["I0", "I1", "O0", "O1"], [cpe, cpe, pe, pe]).zero_()
+    up, dn = (1, 0), (-1, 0)
+    def setel(i0, i1, o0, o1, v):
+        SS[{"I0": (-i0[0], 0), "I1": (-i1[0], 0), "O0": o0, "O1": o1}] = v
+    setel(up, up, up, up, 0.25)
+    setel(dn, dn, dn, dn, 0.25)
+    setel(up, dn, up, dn, -0.25)
+    setel(dn, up, dn, up, -0.25)
+    setel(up, dn, dn, up, 0.5)
+    setel(dn, up, up, dn, 0.5)
+    H = -1.0 * SS
+    state.hamiltonians["vertical_bond"] = H
+    state.hamiltonians["horizontal_bond"] = H
+    lat = tet.AbstractLattice(state)
+    ve = [(-1, d), (0, d), (+1, d)]
+    lat.virtual_bond["R"] = ve
+    lat.virtual_bond["D"] = ve
+    TAT.random.seed(2333)
+    return tet.SamplingLattice(lat)
+
+
+def neel_u1(lattice):
+    S = lattice.Symmetry
+    return [[{0: (S(+1) if (l1 + l2) % 2 == 0 else S(-1), 0)} for l2 in range(lattice.L2)] for l1 in range(lattice.L1)]
+
+
+def tJ(L1, L2, D, T):
+    from tetraku.models.tJ import abstract_lattice
+    TAT.random.seed(2333)
+    return tet.SamplingLattice(abstract_lattice(L1, L2, D, T, 1.0, 0.4))
+
+
+def hubbard_ff(L1, L2, D, T):
+    """FermiU1FermiU1 Hubbard with bonds following the charge-flow pattern of the shipped FermiU1
+    lattice (tetraku/models/hubbard/__init__.py:47-75), one (up, down) pair per row."""
+    from tetraku.models.hubbard.fermi_fermi import abstract_state
+    state = tet.AbstractLattice(abstract_state(L1, L2, T, 1.0, 4.0))
+    half = T // 2
+    def segs(qu, qd):
+        return [((qu + a, qd + b), D) for a in (-1, 0, 1) for b in (-1, 0, 1)]
+    tt = half / L1
+    for l1 in range(L1 - 1):
+        Q = int(half * (L1 - l1 - 1) / L1)
+        state.virtual_bond[l1, 0, "D"] = segs(Q, Q)
+    for l1 in range(L1 - 1):
+        for l2 in range(1, L2):
+            state.virtual_bond[l1, l2, "D"] = [((0, 0), D)]
+    for l1 in range(L1):
+        for l2 in range(L2 - 1):
+            Q = int(tt * (L2 - l2 - 1) / L2)
+            state.virtual_bond[l1, l2, "R"] = segs(Q, Q)
+    TAT.random.seed(2333)
+    return tet.SamplingLattice(state)
+
+
+def main():
+    lat = heisenberg(3, 3, 2)
+    dump_case("heis_3x3_D2_Dc4", "No", lat, 4, neel(lat), seed=11, n_samples=12)
+    lat = heisenberg(4, 4, 4)
+    dump_case("heis_4x4_D4_Dc16", "No", lat, 16, neel(lat), seed=12, n_samples=6)
+    lat = heisenberg(4, 4, 3)
+    dump_case("heis_4x4_D3_Dc5_truncating", "No", lat, 5, neel(lat), seed=13, n_samples=6)
+    lat = heisenberg_u1(4, 4, 1)
+    dump_case("heisU1_4x4_d1_Dc6", "BoseU1", lat, 6, neel_u1(lat), seed=14, n_samples=6)
+    # t-J, 4x4, 4 up + 4 down... tetraku's T is the half particle number
+    lat = tJ(4, 4, 1, 2)
+    S = lat.Symmetry
+    # physical edge of the t-J model: (0,0) hole, (1,+1) up, (1,-1) down; one up and one down in rows 0 and 2
+    hole, up, dn = (S(0, 0), 0), (S(1, 1), 0), (S(1, -1), 0)
+    rows = [[up, hole, dn, hole], [hole, hole, hole, hole], [dn, hole, up, hole], [hole, hole, hole, hole]]
+    dump_case("tJ_4x4_D1_Dc8", "FermiU1BoseU1", lat, 8, [[{0: rows[l1][l2]} for l2 in range(4)] for l1 in range(4)], seed=15, n_samples=6)
+    lat = hubbard_ff(4, 4, 1, 8)
+    S = lat.Symmetry
+    e, u, d_, ud = (S(0, 0), 0), (S(1, 0), 0), (S(0, 1), 0), (S(1, 1), 0)
+    rows = [[u, e, d_, e], [e, u, e, d_], [d_, e, u, e], [e, d_, e, u]]
+    dump_case("hubbardFF_4x4_D1_Dc8", "FermiU1FermiU1", lat, 8, [[{0: rows[l1][l2]} for l2 in range(4)] for l1 in range(4)], seed=16, n_samples=6)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,8 @@
+"""GPU run (-m gpu) of the end-to-end VMC parity tests: golden vectors of the unmodified reference
+and lock-step batching, now through the C-ABI / sm_100a kernels."""
+import pytest
+
+from test_vmc_batched import test_chain_rng_matches_reference_seed_recipe, test_lockstep_equals_independent_chains  # noqa: F401
+from test_vmc_golden import test_amplitude_energy_holes, test_sweep_trajectory_gradient  # noqa: F401
+
+pytestmark = pytest.mark.gpu

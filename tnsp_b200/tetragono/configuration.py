@@ -1,0 +1,218 @@
+"""Sampled configuration(s) with their boundary-MPS environments.
+
+Mirrors ``Configuration`` of the reference (tetragono/tetragono/sampling_lattice/lattice.py:27-416):
+``configuration[l1, l2, orbit] = edge_point``, ``replace``, ``hole``/``holes``, ``copy`` (warm caches),
+``import_/export_configuration`` -- with one extension: a configuration object may hold ``nb``
+Monte-Carlo chains at once (lock-step batch).  All chains of a batch share the symmetry sector of
+every physical index (always true without symmetry); the index inside the sector is per chain.
+An edge point is ``(Symmetry, index)`` where ``index`` is an int or an int array of length nb.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import backend as _bk
+from .auxiliaries import SingleLayerAuxiliaries, safe_rename
+
+
+class Configuration(SingleLayerAuxiliaries):
+    def __init__(self, owner, cut_dimension, nb=1):
+        super().__init__(owner.L1, owner.L2, cut_dimension, False, owner.Tensor)
+        self.owner = owner
+        self.nb = nb
+        # per site: {orbit: (Symmetry, int array [nb]) | None}
+        self._configuration = [[{orbit: None for orbit in owner.physics_edges[l1, l2]} for l2 in range(owner.L2)] for l1 in range(owner.L1)]
+        self._set_site_without_orbit()
+        self._holes = None
+
+    def _set_site_without_orbit(self):
+        for l1, l2 in self.owner.sites():
+            if len(self.owner.physics_edges[l1, l2]) == 0:
+                SingleLayerAuxiliaries.__setitem__(self, (l1, l2), self.owner[l1, l2])
+
+    def copy(self, cp=None):
+        result = super().copy(cp=cp)
+        result.owner = self.owner
+        result.nb = self.nb
+        result._configuration = [[dict(self._configuration[l1][l2]) for l2 in range(self.owner.L2)] for l1 in range(self.owner.L1)]
+        result._holes = self._holes
+        return result
+
+    # -- edge points -----------------------------------------------------------------------------
+    def _construct_edge_point(self, value):
+        if isinstance(value, tuple):
+            symmetry, index = value
+        else:
+            symmetry, index = self.owner.Symmetry(), value
+        index = np.asarray(index, dtype=np.int32).reshape(-1)
+        if index.size == 1 and self.nb != 1:
+            index = np.repeat(index, self.nb)
+        if index.size != self.nb:
+            raise ValueError("edge point index must be a scalar or one index per chain")
+        return (self.owner._construct_symmetry(symmetry), index)
+
+    @staticmethod
+    def _same_point(a, b):
+        return a is not None and b is not None and tuple.__eq__(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+    def site_valid(self, l1, l2):
+        return all(v is not None for v in self._configuration[l1][l2].values())
+
+    def valid(self):
+        return all(self.site_valid(l1, l2) for l1, l2 in self.owner.sites())
+
+    def __getitem__(self, l1l2o):
+        l1, l2, orbit = l1l2o
+        return self._configuration[l1][l2][orbit]
+
+    def __setitem__(self, l1l2o, value):
+        l1, l2, orbit = l1l2o
+        if value is None:
+            self._configuration[l1][l2][orbit] = None
+            SingleLayerAuxiliaries.__setitem__(self, (l1, l2), None)
+            self._holes = None
+            return
+        point = self._construct_edge_point(value)
+        changed = not self._same_point(point, self._configuration[l1][l2][orbit])
+        if changed:
+            self._configuration[l1][l2][orbit] = point
+        if self._lattice[l1][l2]() is None or changed:
+            if self.site_valid(l1, l2):
+                SingleLayerAuxiliaries.__setitem__(self, (l1, l2), self._shrink_configuration((l1, l2), self._configuration[l1][l2]))
+                self._holes = None
+
+    def __delitem__(self, l1l2o):
+        self.__setitem__(l1l2o, None)
+
+    def import_configuration(self, config):
+        """config[l1][l2][orbit] = total edge index (>= 0), -1 absent, -2 None; an extra leading axis of
+        length nb gives one configuration per chain (lattice.py:181-207)."""
+        config = np.asarray(config)
+        batched = config.ndim == 4
+        for l1, l2 in self.owner.sites():
+            for orbit in self.owner.physics_edges[l1, l2]:
+                idx = config[:, l1, l2, orbit] if batched else config[l1, l2, orbit:orbit + 1]
+                if (idx == -2).all():
+                    self[l1, l2, orbit] = None
+                elif (idx == -1).all():
+                    continue
+                elif (idx >= 0).all():
+                    self[l1, l2, orbit] = self._point_by_index(self.owner.physics_edges[l1, l2, orbit], idx)
+                else:
+                    raise RuntimeError("Invalid edge index")
+
+    def export_configuration(self):
+        """int64 array [nb, L1, L2, orbits] (squeezed to [L1, L2, orbits] for a single chain)"""
+        max_orbit = max(orbit for (l1, l2, orbit), _ in self.owner.physics_edges)
+        result = np.zeros([self.nb, self.owner.L1, self.owner.L2, max_orbit + 1], dtype=np.int64) - 1
+        for (l1, l2, orbit), edge in self.owner.physics_edges:
+            point = self[l1, l2, orbit]
+            result[:, l1, l2, orbit] = -2 if point is None else self._index_by_point(edge, point)
+        return result[0] if self.nb == 1 else result
+
+    @staticmethod
+    def _point_by_index(edge, idx):
+        """total index -> (symmetry, offset); all chains must land in one segment"""
+        idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+        p0, _ = edge.coord_by_index(int(idx[0]))
+        start = sum(d for _, d in edge.segments[:p0])
+        off = idx - start
+        if (off < 0).any() or (off >= edge.segments[p0][1]).any():
+            raise NotImplementedError("chains of one lock-step batch must share the symmetry sector of every physical index")
+        return (edge.segments[p0][0], off.astype(np.int32))
+
+    @staticmethod
+    def _index_by_point(edge, point):
+        sym, off = point
+        return edge.index_by_point((sym, 0)) + np.asarray(off, dtype=np.int64)
+
+    # -- shrinking -------------------------------------------------------------------------------
+    def _get_shrinker(self, l1l2, configuration):
+        """one-hot (P, Q) tensors selecting the sampled physical slice (lattice.py:291-317)"""
+        l1, l2 = l1l2
+        for orbit in self.owner.physics_edges[l1, l2]:
+            edge = self.owner.physics_edges[l1, l2, orbit]
+            symmetry, index = configuration[orbit]
+            cedge = edge.conjugate()
+            t = self.Tensor(["P", "Q"], [[(symmetry, 1)], cedge])
+            pos = cedge.position_by_symmetry(-symmetry)
+            start = sum(d for _, d in cedge.segments[:pos])
+            onehot = np.zeros((len(index), t.storage.size))
+            # block (P=symmetry, Q=-symmetry) is the only block; its offset inside storage:
+            b = t._table.block_by_positions((0, pos))
+            base = int(t._table.offsets[b])
+            onehot[np.arange(len(index)), base + index] = 1.0
+            del start
+            yield orbit, type(t).from_batch(t.names, t._edges, onehot)
+
+    def _shrink_configuration(self, l1l2, configuration):
+        l1, l2 = l1l2
+        tensor = self.owner[l1l2]
+        orbits = list(self.owner.physics_edges[l1, l2])
+        # fast path: no symmetry, single orbit stored first -> a row gather of the site tensor
+        if self.Tensor.Symmetry.length == 0 and orbits == [0] and tensor.names[0] == "P0" and tensor.nb == 1:
+            _, index = configuration[0]
+            B = _bk.get()
+            d = tensor._edges[0].dimension
+            row = tensor.storage.size // d
+            data = B.gather_rows(tensor.data, row, B.from_numpy(np.ascontiguousarray(index, dtype=np.int32)))
+            names = tensor.names[1:] + [f"P_{l1}_{l2}_0"]
+            edges = tensor._edges[1:] + (self.owner.Edge(1),)
+            return type(tensor).from_batch(names, edges, data)
+        for orbit, shrinker in self._get_shrinker(l1l2, configuration):
+            tensor = tensor.contract(shrinker.edge_rename({"P": f"P_{l1}_{l2}_{orbit}"}), {(f"P{orbit}", "Q")})
+        return tensor
+
+    def refresh_site(self, l1l2o):
+        configuration = self[l1l2o]
+        del self[l1l2o]
+        self[l1l2o] = configuration
+
+    def refresh_all(self):
+        for l1, l2 in self.owner.sites():
+            for orbit in self.owner.physics_edges[l1, l2]:
+                self.refresh_site((l1, l2, orbit))
+
+    # -- amplitudes ------------------------------------------------------------------------------
+    def replace(self, replacement, *, hint=None):
+        """<s'|psi> with several physical indices replaced (lattice.py:231-267)."""
+        grouped = {}
+        for (l1, l2, orbit), point in replacement.items():
+            grouped.setdefault((l1, l2), {})[orbit] = self._construct_edge_point(point)
+        base = {}
+        for l1l2, site in grouped.items():
+            l1, l2 = l1l2
+            changed = False
+            for orbit, current in self._configuration[l1][l2].items():
+                if orbit not in site:
+                    site[orbit] = current
+                elif not self._same_point(site[orbit], current):
+                    changed = True
+            if changed:
+                base[l1l2] = self._shrink_configuration(l1l2, site)
+        return SingleLayerAuxiliaries.replace(self, base, hint=hint)
+
+    def holes(self):
+        """<psi|s|d_x psi> / <psi|s|psi> for every site tensor x (lattice.py:362-416)."""
+        if self._holes is None:
+            owner = self.owner
+            ws = self.hole(())
+            inv_ws_conj = ws / (ws.norm_2()**2)
+            inv_ws = inv_ws_conj.conjugate()
+            all_name = {("T", "T")} | {(f"P_{l1}_{l2}_{orbit}",) * 2 for l1, l2 in owner.sites() for orbit in owner.physics_edges[l1, l2]}
+            holes = [[None] * owner.L2 for _ in range(owner.L1)]
+            for l1, l2 in owner.sites():
+                hole = self.hole(((l1, l2),))
+                names = set(all_name)
+                for orbit in owner.physics_edges[l1, l2]:
+                    names.discard((f"P_{l1}_{l2}_{orbit}",) * 2)
+                if "T" not in hole.names:
+                    names.discard(("T", "T"))
+                hole = hole.contract(inv_ws, names)
+                hole = safe_rename(hole, {"L0": "R", "R0": "L", "U0": "D", "D0": "U",
+                                          **{f"P_{l1}_{l2}_{orbit}": f"P{orbit}" for orbit in owner.physics_edges[l1, l2]}})
+                for orbit, shrinker in self._get_shrinker((l1, l2), self._configuration[l1][l2]):
+                    hole = hole.contract(shrinker, {(f"P{orbit}", "P")}).edge_rename({"Q": f"P{orbit}"})
+                holes[l1][l2] = hole
+            self._holes = holes
+        return self._holes
