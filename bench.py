@@ -1,0 +1,362 @@
+"""bench.py -- VMC samples/sec of the sampling hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA path)
+    python bench.py --impl reference --steps K --warmup W    # reference CPU implementation on the host cores
+
+One "step" = one lock-step sweep of all chains of a rank (SweepSampling.__call__) + one Observer call
+(local energy + log-derivative accumulation), i.e. `chains` samples per rank; value = samples of all
+ranks / max-over-ranks device time.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (L1, L2, D, Dc, description)
+    "cfg1": (4, 4, 4, 16, "tetragono sampling VMC 4x4 Heisenberg square lattice, no symmetry, D=4, Dc=16, float64"),
+    "heis6": (6, 6, 6, 36, "6x6 Heisenberg, no symmetry (dense stand-in of cfg2), D=6, Dc=36, float64"),
+    "tiny": (3, 3, 2, 4, "3x3 Heisenberg, no symmetry, D=2, Dc=4 (smoke size)"),
+}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's own C++ TAT (oracle/_ref, LAPACK/BLAS per sector on the CPU) driven by
+# the same-semantics Python drivers, one independent Markov chain per host core
+# ---------------------------------------------------------------------------------------------------
+def _reference_worker(args):
+    workload, seed, n_warm, n_samples, use_ref = args
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["OMP_NUM_THREADS"] = "1"
+    L1, L2, D, Dc, _ = WORKLOADS[workload]
+    if use_ref:
+        from oracle.ref import load_reference_tat
+        tat = load_reference_tat()
+    else:
+        tat = None
+    from tnsp_b200.tetragono import models
+    from tnsp_b200.tetragono.observer import Observer
+    from tnsp_b200.tetragono.sampling import SweepSampling
+    from tnsp_b200.tetragono.state import AbstractLattice, AbstractState, SamplingLattice
+    import tnsp_b200.TAT.random as rnd
+    if tat is None:
+        # "port": the numpy checker backend under this repository's planner
+        from oracle import numpy_backend
+        numpy_backend.install()
+        import tnsp_b200.TAT as tat_mod
+        T = tat_mod.No.D.Tensor
+        seed_fn = tat_mod.random.seed
+    else:
+        T = tat.No.D.Tensor
+        seed_fn = tat.random.seed
+    state = AbstractState(T, L1, L2)
+    state.physics_edges[...] = 2
+    H = T(["I0", "I1", "O0", "O1"], [2, 2, 2, 2]).zero_()
+    H.storage = -np.asarray(models.spin_half_SS_array()).reshape(-1)
+    state.hamiltonians["vertical_bond"] = H
+    state.hamiltonians["horizontal_bond"] = H
+    lat = AbstractLattice(state)
+    lat.virtual_bond["R"] = D
+    lat.virtual_bond["D"] = D
+    seed_fn(2333)
+    lat = SamplingLattice(lat)
+    rnd.seed(seed)
+    s = SweepSampling(lat, Dc)
+    s.configuration.import_configuration(models.neel_configuration(L1, L2))
+    obs = Observer(lat, enable_energy=True, enable_gradient=True)
+    with obs:
+        for _ in range(n_warm):
+            p, c = s()
+            obs(p, c)
+        t0 = time.perf_counter()
+        for _ in range(n_samples):
+            p, c = s()
+            obs(p, c)
+        dt = time.perf_counter() - t0
+    return n_samples, dt, obs.energy[0]
+
+
+def run_reference(workload, steps, warmup, samples_per_step, cores=None):
+    """returns dict(value, cores, kind, sample, ms_per_step)"""
+    from oracle.ref import load_reference_tat  # noqa: F401  (checks availability in the parent too)
+    import glob
+    use_ref = bool(glob.glob(os.path.join(ROOT, "oracle", "_ref", "TAT*.so")))
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    per_step = []
+    with ctx.Pool(cores) as pool:
+        if use_ref:
+            ok = pool.map(_probe_ref, range(1))[0]
+            use_ref = ok
+        for st in range(warmup + steps):
+            t0 = time.perf_counter()
+            res = pool.map(_reference_worker, [(workload, 1000 + 97 * st + c, 1, samples_per_step, use_ref) for c in range(cores)])
+            wall = time.perf_counter() - t0
+            # throughput of the step: every core runs one independent chain (sum of per-chain rates)
+            rate = sum(n / dt for n, dt, _ in res)
+            if st >= warmup:
+                per_step.append((rate, wall))
+    value = float(np.mean([r for r, _ in per_step]))
+    return {"value": value, "unit": "samples/s", "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": f"{samples_per_step} samples per chain x {cores} independent chains (one per host core, 1 BLAS thread each) per step, "
+                      f"{steps} steps, workload {workload}",
+            "ms_per_step": float(np.mean([w for _, w in per_step]) * 1e3)}
+
+
+def _probe_ref(_):
+    try:
+        from oracle.ref import load_reference_tat
+        return load_reference_tat() is not None
+    except Exception:
+        return False
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def start(self):
+        def loop():
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            while not self._stop.is_set():
+                try:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
+                except Exception:
+                    pass
+                self._stop.wait(0.2)
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------------
+def run_own(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from tnsp_b200 import backend
+    import tnsp_b200.TAT as TAT
+    from tnsp_b200 import dist as tdist
+    from tnsp_b200.tetragono import models
+    from tnsp_b200.tetragono.observer import Observer
+    from tnsp_b200.tetragono.sampling import ChainRng, SweepSampling
+    B = backend.get()   # raises without the CUDA library / a GPU: no CPU fallback
+
+    L1, L2, D, Dc, desc = WORKLOADS[args.workload]
+    nb = args.chains
+    lat = models.random_sampling_lattice(models.heisenberg_lattice(L1, L2, D), 2333)
+    # one normalisation pass so that amplitudes are O(1) (observer.normalize_lattice)
+    s0 = SweepSampling(lat, Dc, nb=1)
+    s0.configuration.import_configuration(models.neel_configuration(L1, L2))
+    TAT.random.seed(2333)
+    o0 = Observer(lat, enable_energy=True)
+    with o0:
+        for _ in range(2):
+            p, c = s0()
+            o0(p, c)
+    o0.normalize_lattice()
+
+    rng = ChainRng(nb)
+    rng.seed([(2333 + rank * nb + c) % 2**31 for c in range(nb)])
+    rng.uniform_real(None)
+    sampling = SweepSampling(lat, Dc, nb=nb, rng=rng)
+    conf0 = models.neel_configuration(L1, L2)
+    sampling.configuration.import_configuration(np.broadcast_to(conf0, (nb,) + conf0.shape))
+    observer = Observer(lat, enable_energy=True, enable_gradient=True)
+
+    def step():
+        p, c = sampling()
+        observer(p, c)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        tdist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    with observer:
+        for _ in range(args.warmup):
+            step()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        sync_all()
+        l0 = B.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        sync_all()
+        launches = B.launch_count() - l0
+        ms = e0.elapsed_time(e1)
+        clock_info = clocks.stop() if rank == 0 else None
+    energy = observer.energy
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    samples = nb * args.steps * world
+    value = samples / (ms_max * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers --------------------------------------
+    # every step: PEPS tensors host -> device (pinned), refresh the environments, sweep + observe,
+    # gradient and energy device -> host
+    host_sites = [[torch.from_numpy(np.ascontiguousarray(np.asarray(lat[l1, l2].storage))).pin_memory() for l2 in range(L2)] for l1 in range(L1)]
+    h2d = sum(t_.numel() * 8 for row in host_sites for t_ in row)
+    d2h = 0
+    obs2 = Observer(lat, enable_energy=True, enable_gradient=True)
+
+    def e2e_step():
+        nonlocal d2h
+        for l1 in range(L1):
+            for l2 in range(L2):
+                lat[l1, l2]._data = host_sites[l1][l2].to("cuda", non_blocking=True).reshape(1, -1)
+        sampling.configuration.refresh_all()
+        with obs2:
+            p, c = sampling()
+            obs2(p, c)
+        grad = obs2.gradient
+        out = [g.data.cpu() for row in grad for g in row]
+        e = obs2.energy
+        d2h = sum(o.numel() * 8 for o in out) + 16
+        return e, out
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(1, args.steps // 2)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    e1.record()
+    sync_all()
+    wall = time.perf_counter() - t0
+    ms2 = max(e0.elapsed_time(e1), wall * 1e3)
+    t = torch.tensor([ms2], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = nb * n_e2e * world / (float(t.item()) * 1e-3)
+
+    # ---- roofline of the dominant kernel (instrumented pass, outside the timed regions) -----------
+    roofline, breakdown = None, None
+    if rank == 0:
+        from tnsp_b200 import profiling
+        prof = profiling.KernelTimer(B)
+        with observer:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            prof.enable()
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            prof.disable()
+        breakdown = prof.summary()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        roofline = profiling.roofline_of_dominant(breakdown, peaks)
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": "VMC samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (randn_ PEPS seed 2333, Neel start, per-chain mt19937_64 seeds)",
+            "config": {"workload": f"{args.workload}: {desc}", "chains_per_gpu": nb, "samples_per_step": nb * world,
+                       "observer": "energy+gradient", "l2": "working set of a step (all chains' environments) exceeds L2; no flush"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clock_info, "energy_per_site": energy[0],
+            "roofline": roofline, "kernel_breakdown": breakdown,
+        }
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own")
+    ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=4096, help="Markov chains per GPU (lock-step batch)")
+    ap.add_argument("--ref-samples", type=int, default=8, help="samples per chain per step in the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        L1, L2, D, Dc, desc = WORKLOADS[args.workload]
+        r = run_reference(args.workload, args.steps, max(1, args.warmup // 3), args.ref_samples)
+        line = {"impl": "reference", "metric": "VMC samples/sec", "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic (randn_ PEPS seed 2333, Neel start)",
+                "config": {"workload": f"{args.workload}: {desc}", "observer": "energy+gradient"},
+                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    out = run_own(args)
+    if rank == 0:
+        if not args.no_cpu_baseline and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            r = run_reference(args.workload, 2, 1, args.ref_samples)
+            out["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

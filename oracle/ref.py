@@ -18,6 +18,9 @@ def load_reference_tat():
         return None
     saved = sys.modules.get("TAT")
     try:
+        # torch must be imported BEFORE the reference extension: loading them in the other order crashes
+        # inside torch's own pybind initialisation (both embed pybind11 internals / libstdc++ symbols)
+        import torch  # noqa: F401
         spec = importlib.util.spec_from_file_location("TAT", files[0])
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)

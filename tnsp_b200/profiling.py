@@ -1,0 +1,133 @@
+"""Per-kernel-class device timing with CUDA events on the launching stream, plus the algorithmic
+work each launch performs (bytes / flops as defined in DESIGN.md), for bench.py's roofline object.
+Used only in an instrumented pass OUTSIDE the timed regions (the event pairs add launch overhead)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def _nb(t):
+    return t.shape[0]
+
+
+class KernelTimer:
+    CLASSES = ("pack", "gemm", "qr", "svd", "svd_cut", "norm", "scale", "binary", "unary", "gather_rows", "select", "grad_accumulate",
+               "diag_scatter", "block_sign", "svd_mask")
+
+    def __init__(self, backend):
+        self.B = backend
+        self.records = {k: [] for k in self.CLASSES}
+        self._orig = {}
+
+    def _work(self, name, args):
+        """(algorithmic bytes, flops) of one launch"""
+        if name == "pack":
+            plan, src, dst = args[:3]
+            return 16.0 * plan.total * _nb(dst), 0.0
+        if name == "gemm":
+            plan, a, b, c = args[:4]
+            nb = _nb(c)
+            g = plan.gemm
+            flops = float((2 * g[:, 0] * g[:, 1] * g[:, 2]).sum()) * nb
+            by = 8.0 * (float((g[:, 0] * g[:, 2]).sum()) * _nb(a) + float((g[:, 2] * g[:, 1]).sum()) * _nb(b) + float((g[:, 0] * g[:, 1]).sum()) * nb)
+            return by, flops
+        if name in ("qr", "svd"):
+            plan, a = args[:2]
+            s = plan.sectors
+            m, n, k = s[:, 0], s[:, 1], s[:, 2]
+            nb = _nb(a)
+            if name == "qr":
+                return 8.0 * float((2 * m * n + m * k + k * n).sum()) * nb, float((4 * m * n * k).sum()) * nb
+            return 8.0 * float((m * n + m * k + k * n + k).sum()) * nb, 0.0
+        if name in ("scale", "unary", "block_sign"):
+            x = args[1] if name == "block_sign" else args[0]
+            return 16.0 * x.shape[1] * _nb(x), 0.0
+        if name in ("binary", "select"):
+            x = args[1] if name == "select" else args[0]
+            return 24.0 * x.shape[1] * max(_nb(x), 1), 0.0
+        if name == "norm":
+            return 8.0 * args[0].numel(), 0.0
+        if name == "grad_accumulate":
+            return 8.0 * args[0].numel(), 2.0 * args[0].numel()
+        if name == "gather_rows":
+            return 16.0 * args[1] * _nb(args[2]), 0.0
+        return 0.0, 0.0
+
+    def enable(self):
+        for name in self.CLASSES:
+            fn = getattr(self.B, name)
+            self._orig[name] = fn
+
+            def wrapped(*args, _fn=fn, _name=name, **kw):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = _fn(*args, **kw)
+                e1.record()
+                by, fl = self._work(_name, args)
+                self.records[_name].append((e0, e1, by, fl))
+                return r
+
+            setattr(self.B, name, wrapped)
+
+    def disable(self):
+        for name, fn in self._orig.items():
+            try:
+                delattr(self.B, name)   # wrapped functions are instance attributes shadowing the methods
+            except AttributeError:
+                pass
+        self._orig = {}
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in self.records.items():
+            if not recs:
+                continue
+            ms = [a.elapsed_time(b) for a, b, _, _ in recs]
+            out[name] = {"launches": len(recs), "ms": float(np.sum(ms)), "bytes": float(sum(r[2] for r in recs)),
+                         "flops": float(sum(r[3] for r in recs))}
+        total = sum(v["ms"] for v in out.values()) or 1.0
+        for v in out.values():
+            v["share"] = v["ms"] / total
+        return out
+
+
+def measure_fp64_gemm_tflops(n=4096, reps=3):
+    """cuBLAS DGEMM throughput of this GPU (denominator of FP64 tensor-bound kernels; MEASURED_PEAKS.json has no FP64 entry)"""
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n**3 / (best * 1e-3) / 1e12
+
+
+def roofline_of_dominant(breakdown, peaks):
+    if not breakdown:
+        return None
+    name = max(breakdown, key=lambda k: breakdown[k]["ms"])
+    v = breakdown[name]
+    sec = v["ms"] * 1e-3
+    hbm_peak = peaks.get("hbm_gbs")
+    which = "of measured (MEASURED_PEAKS.json hbm_gbs)"
+    if hbm_peak is None:
+        hbm_peak, which = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
+    gbs = v["bytes"] / sec / 1e9
+    intensity = v["flops"] / max(v["bytes"], 1.0)
+    if name == "gemm" and intensity > 6.0:
+        peak = measure_fp64_gemm_tflops()
+        ach = v["flops"] / sec / 1e12
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no FP64 entry in MEASURED_PEAKS.json)",
+                "launches": v["launches"], "avg_launch_us": v["ms"] * 1e3 / v["launches"], "share_of_kernel_time": v["share"]}
+    return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+            "peak_source": which, "launches": v["launches"], "avg_launch_us": v["ms"] * 1e3 / v["launches"],
+            "share_of_kernel_time": v["share"]}

@@ -12,7 +12,18 @@ from __future__ import annotations
 import numpy as np
 
 from .. import backend as _bk
+from ..TAT.tensor import Tensor as _NativeTensor
 from .auxiliaries import SingleLayerAuxiliaries, safe_rename
+
+
+def is_native(Tensor):
+    """True for this repository's device tensors; False for any other PyTAT-compatible class (the
+    drivers then use only the public PyTAT API, one chain at a time -- used to time the reference)."""
+    return isinstance(Tensor, type) and issubclass(Tensor, _NativeTensor)
+
+
+def is_no_symmetry(Tensor):
+    return Tensor.model.__name__.rsplit(".", 1)[-1] in ("No", "Normal")
 
 
 class Configuration(SingleLayerAuxiliaries):
@@ -20,6 +31,9 @@ class Configuration(SingleLayerAuxiliaries):
         super().__init__(owner.L1, owner.L2, cut_dimension, False, owner.Tensor)
         self.owner = owner
         self.nb = nb
+        self._native = is_native(owner.Tensor)
+        if not self._native and nb != 1:
+            raise NotImplementedError("lock-step batches need the device-backed TAT tensors")
         # per site: {orbit: (Symmetry, int array [nb]) | None}
         self._configuration = [[{orbit: None for orbit in owner.physics_edges[l1, l2]} for l2 in range(owner.L2)] for l1 in range(owner.L1)]
         self._set_site_without_orbit()
@@ -34,6 +48,7 @@ class Configuration(SingleLayerAuxiliaries):
         result = super().copy(cp=cp)
         result.owner = self.owner
         result.nb = self.nb
+        result._native = self._native
         result._configuration = [[dict(self._configuration[l1][l2]) for l2 in range(self.owner.L2)] for l1 in range(self.owner.L1)]
         result._holes = self._holes
         return result
@@ -53,7 +68,7 @@ class Configuration(SingleLayerAuxiliaries):
 
     @staticmethod
     def _same_point(a, b):
-        return a is not None and b is not None and tuple.__eq__(a[0], b[0]) and np.array_equal(a[1], b[1])
+        return a is not None and b is not None and a[0] == b[0] and np.array_equal(a[1], b[1])
 
     def site_valid(self, l1, l2):
         return all(v is not None for v in self._configuration[l1][l2].values())
@@ -135,14 +150,15 @@ class Configuration(SingleLayerAuxiliaries):
             symmetry, index = configuration[orbit]
             cedge = edge.conjugate()
             t = self.Tensor(["P", "Q"], [[(symmetry, 1)], cedge])
-            pos = cedge.position_by_symmetry(-symmetry)
-            start = sum(d for _, d in cedge.segments[:pos])
-            onehot = np.zeros((len(index), t.storage.size))
-            # block (P=symmetry, Q=-symmetry) is the only block; its offset inside storage:
-            b = t._table.block_by_positions((0, pos))
-            base = int(t._table.offsets[b])
-            onehot[np.arange(len(index)), base + index] = 1.0
-            del start
+            if not self._native:
+                t.zero_()
+                t[{"Q": (-symmetry, int(index[0])), "P": (symmetry, 0)}] = 1
+                yield orbit, t
+                continue
+            # the only block is (P = symmetry, Q = -symmetry), 1 x d: one-hot at `index`, one row per chain
+            b = t._table.block_by_positions((0, cedge.position_by_symmetry(-symmetry)))
+            onehot = np.zeros((len(index), t._table.size))
+            onehot[np.arange(len(index)), int(t._table.offsets[b]) + index] = 1.0
             yield orbit, type(t).from_batch(t.names, t._edges, onehot)
 
     def _shrink_configuration(self, l1l2, configuration):
@@ -150,7 +166,7 @@ class Configuration(SingleLayerAuxiliaries):
         tensor = self.owner[l1l2]
         orbits = list(self.owner.physics_edges[l1, l2])
         # fast path: no symmetry, single orbit stored first -> a row gather of the site tensor
-        if self.Tensor.Symmetry.length == 0 and orbits == [0] and tensor.names[0] == "P0" and tensor.nb == 1:
+        if self._native and self.Tensor.Symmetry.length == 0 and orbits == [0] and tensor.names[0] == "P0" and tensor.nb == 1:
             _, index = configuration[0]
             B = _bk.get()
             d = tensor._edges[0].dimension

@@ -9,15 +9,18 @@ from .. import TAT
 from .state import AbstractLattice, AbstractState, SamplingLattice
 
 
-def spin_half_SS(Tensor):
-    """S.S of two spin-1/2 as a tensor with names I0 I1 O0 O1 (common_tensor/No.py)"""
-    t = Tensor(["I0", "I1", "O0", "O1"], [2, 2, 2, 2]).zero_()
+def spin_half_SS_array():
+    """S.S of two spin-1/2 as an array [i0, i1, o0, o1]"""
     sx = np.array([[0, 0.5], [0.5, 0]])
     sz = np.array([[0.5, 0], [0, -0.5]])
     isy = np.array([[0, 0.5], [-0.5, 0]])  # i*Sy (real)
-    ss = np.einsum("ac,bd->abcd", sx, sx) - np.einsum("ac,bd->abcd", isy, isy) + np.einsum("ac,bd->abcd", sz, sz)
-    # ss[i0,i1,o0,o1]
-    t.storage = ss.reshape(-1)
+    return np.einsum("ac,bd->abcd", sx, sx) - np.einsum("ac,bd->abcd", isy, isy) + np.einsum("ac,bd->abcd", sz, sz)
+
+
+def spin_half_SS(Tensor):
+    """S.S as a tensor with names I0 I1 O0 O1 (reference: tetragono/common_tensor/No.py)"""
+    t = Tensor(["I0", "I1", "O0", "O1"], [2, 2, 2, 2]).zero_()
+    t.storage = spin_half_SS_array().reshape(-1)
     return t
 
 

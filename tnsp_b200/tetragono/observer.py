@@ -16,7 +16,7 @@ import numpy as np
 
 from .. import backend as _bk
 from .. import dist as _dist
-from .configuration import Configuration
+from .configuration import Configuration, is_native, is_no_symmetry
 from .tensor_element import element_table
 
 
@@ -136,7 +136,7 @@ class Observer:
         self._total_weight_square += float((reweight**2).sum())
         self._total_log_ws += float(np.log(np.abs(ws_val[alive])).sum())
 
-        no_symmetry = owner.Tensor.Symmetry.length == 0
+        no_symmetry = is_no_symmetry(owner.Tensor)
         if not no_symmetry:
             inv_ws_conj = ws / (ws.norm_2()**2)
             all_name = {("T", "T")} | {(f"P_{l1}_{l2}_{orbit}",) * 2 for l1, l2 in owner.sites() for orbit in owner.physics_edges[l1, l2]}
@@ -192,8 +192,21 @@ class Observer:
             if name == "energy":
                 Es = whole
         if self._enable_gradient and Es is not None:
-            B = _bk.get()
             holes = configuration.holes()
+            if not is_native(owner.Tensor):
+                # generic PyTAT path (one chain): plain tensor arithmetic as the reference (observer.py:399-415)
+                w, e = float(reweight[0]), float(Es[0])
+                rows = []
+                for l1, l2 in owner.sites():
+                    hole = holes[l1][l2] * w
+                    self._Delta[l1][l2] += hole
+                    self._EDelta[l1][l2] += e * hole
+                    if self._enable_natural:
+                        rows.append(np.array(holes[l1][l2].transpose(self._Delta[l1][l2].names).storage))
+                if self._enable_natural:
+                    self._Deltas.append((reweight.copy(), Es.copy(), np.concatenate(rows).reshape(1, -1)))
+                return
+            B = _bk.get()
             w_dev = B.from_numpy(np.ascontiguousarray(reweight))
             e_dev = B.from_numpy(np.ascontiguousarray(Es))
             rows = []

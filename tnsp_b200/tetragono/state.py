@@ -78,7 +78,7 @@ class AbstractState:
         self.L1, self.L2 = L1, L2
         self._physics_edges = [[{} for _ in range(L2)] for _ in range(L1)]
         self._hamiltonians = {}
-        self._total_symmetry = Tensor.Symmetry()
+        self._total_symmetry = Tensor.model.Symmetry()
         self.attribute = {}
 
     def _init_by_copy(self, other):

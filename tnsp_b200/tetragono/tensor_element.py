@@ -32,13 +32,14 @@ def _calculate(tensor):
     rank = len(names)
     body = rank // 2
     Edge = tensor.model.Edge
+    Symmetry = tensor.model.Symmetry
     edges = [tensor.edge_by_name(n) for n in names]
-    for pos in itertools.product(*[range(e.segments_size) for e in edges]):
+    for pos in itertools.product(*[range(len(e.segments)) for e in edges]):
         syms = [e.segments[p][0] for e, p in zip(edges, pos)]
-        total = tensor.Symmetry()
+        total = Symmetry()
         for s in syms:
             total = total + s
-        if not tuple.__eq__(total, tensor.Symmetry()):
+        if total != Symmetry():
             continue
         block = tensor.const_blocks[[(n, s) for n, s in zip(names, syms)]]
         for idx in itertools.product(*[range(d) for d in block.shape]):
