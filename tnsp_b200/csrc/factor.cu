@@ -282,6 +282,231 @@ __global__ void __launch_bounds__(kFactorThreads) svd_kernel(const int64_t* __re
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Warp-per-matrix variants for the small sector matrices that dominate the VMC path (cfg1: 16x16,
+// 64x16, 4x64 ...).  One warp owns one (sector, chain) matrix in its private slice of shared memory
+// (padded leading dimension -> conflict-free), so the factorization needs no block barrier at all;
+// a CTA of kWarpsPerCta warps works on kWarpsPerCta chains at once.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWarpsPerCta = 4;
+constexpr int kWarpDoubles = 1536;   // 12 KiB per warp
+
+__device__ __forceinline__ double group_sum(double v, int width) {
+    for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__host__ __device__ inline int64_t qr_warp_need(int64_t p, int64_t q, int64_t k) { return p * (q | 1) + k; }
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta) qr_warp_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a,
+                                                                    int64_t abs_, double* __restrict__ out1, int64_t o1bs,
+                                                                    double* __restrict__ out2, int64_t o2bs, int use_qr, int nb) {
+    extern __shared__ double smem[];
+    const int64_t* sc = sect + (int64_t)blockIdx.x * TNSP_SECT_COLS;
+    const int m = (int)sc[0], n = (int)sc[1], k = (int)sc[2];
+    if (m * n == 0) return;
+    const int p = use_qr ? m : n, q = use_qr ? n : m;
+    const int ld = q | 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* X = smem + (int64_t)warp * kWarpDoubles;   // X[i*ld + j]
+    double* tau = X + p * ld;
+    for (int b = blockIdx.y * kWarpsPerCta + warp; b < nb; b += gridDim.y * kWarpsPerCta) {
+        const double* A = a + (int64_t)b * abs_ + sc[3];
+        if (use_qr) {
+            for (int e = lane; e < m * n; e += 32) X[(e / n) * ld + (e % n)] = A[e];
+        } else {
+            for (int e = lane; e < m * n; e += 32) X[(e % n) * ld + (e / n)] = A[e];   // X = M^T
+        }
+        __syncwarp();
+        const bool by_rows = p >= q;   // lanes over rows (tall) or over columns (wide)
+        for (int j = 0; j < k; ++j) {
+            double part = 0.0;
+            for (int i = j + 1 + lane; i < p; i += 32) { const double v = X[i * ld + j]; part += v * v; }
+            const double xnorm2 = warp_sum(part);
+            const double alpha = X[j * ld + j];
+            double tj = 0.0, scale = 0.0, beta = alpha;
+            if (xnorm2 != 0.0) {
+                beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+                tj = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            __syncwarp();
+            if (tj != 0.0) {
+                for (int i = j + 1 + lane; i < p; i += 32) X[i * ld + j] *= scale;
+                __syncwarp();
+                if (by_rows) {
+                    for (int c = j + 1; c < q; ++c) {
+                        double w = 0.0;
+                        for (int i = j + 1 + lane; i < p; i += 32) w += X[i * ld + j] * X[i * ld + c];
+                        w = (warp_sum(w) + X[j * ld + c]) * tj;
+                        for (int i = j + 1 + lane; i < p; i += 32) X[i * ld + c] -= w * X[i * ld + j];
+                        __syncwarp();
+                        if (lane == 0) X[j * ld + c] -= w;
+                    }
+                } else {
+                    for (int c = j + 1 + lane; c < q; c += 32) {
+                        double w = X[j * ld + c];
+                        for (int i = j + 1; i < p; ++i) w += X[i * ld + j] * X[i * ld + c];
+                        w *= tj;
+                        X[j * ld + c] -= w;
+                        for (int i = j + 1; i < p; ++i) X[i * ld + c] -= w * X[i * ld + j];
+                    }
+                }
+            }
+            if (lane == 0) { tau[j] = tj; X[j * ld + j] = beta; }
+            __syncwarp();
+        }
+        if (use_qr) {
+            double* Rm = out2 + (int64_t)b * o2bs + sc[5];
+            for (int e = lane; e < k * q; e += 32) { const int i = e / q, j = e - i * q; Rm[e] = (j >= i) ? X[i * ld + j] : 0.0; }
+        } else {
+            double* Lm = out1 + (int64_t)b * o1bs + sc[4];
+            for (int e = lane; e < q * k; e += 32) { const int r = e / k, i = e - r * k; Lm[e] = (r >= i) ? X[i * ld + r] : 0.0; }
+        }
+        __syncwarp();
+        for (int j = k - 1; j >= 0; --j) {
+            const double tj = tau[j];
+            if (by_rows) {
+                for (int c = j + 1; c < k; ++c) {
+                    double w = 0.0;
+                    for (int i = j + 1 + lane; i < p; i += 32) w += X[i * ld + j] * X[i * ld + c];
+                    w = (warp_sum(w) + X[j * ld + c]) * tj;
+                    for (int i = j + 1 + lane; i < p; i += 32) X[i * ld + c] -= w * X[i * ld + j];
+                    __syncwarp();
+                    if (lane == 0) X[j * ld + c] -= w;
+                }
+            } else {
+                for (int c = j + 1 + lane; c < k; c += 32) {
+                    double w = X[j * ld + c];
+                    for (int i = j + 1; i < p; ++i) w += X[i * ld + j] * X[i * ld + c];
+                    w *= tj;
+                    X[j * ld + c] -= w;
+                    for (int i = j + 1; i < p; ++i) X[i * ld + c] -= w * X[i * ld + j];
+                }
+            }
+            __syncwarp();
+            for (int i = j + 1 + lane; i < p; i += 32) X[i * ld + j] *= -tj;
+            for (int i = lane; i < j; i += 32) X[i * ld + j] = 0.0;
+            if (lane == 0) X[j * ld + j] = 1.0 - tj;
+            __syncwarp();
+        }
+        if (use_qr) {
+            double* Qm = out1 + (int64_t)b * o1bs + sc[4];
+            for (int e = lane; e < p * k; e += 32) { const int i = e / k, j = e - i * k; Qm[e] = X[i * ld + j]; }
+        } else {
+            double* Qm = out2 + (int64_t)b * o2bs + sc[5];
+            for (int e = lane; e < k * p; e += 32) { const int j = e / p, i = e - j * p; Qm[e] = X[i * ld + j]; }
+        }
+        __syncwarp();
+    }
+}
+
+__host__ __device__ inline int64_t svd_warp_need(int64_t p, int64_t q) { return q * (p | 1) + q * (q | 1) + 2 * q; }
+
+// Jacobi SVD, one warp per matrix; every column pair of a round-robin round is rotated by its own
+// sub-warp group of `gs` lanes (gs = 32 / pairs-in-flight), all rounds separated by __syncwarp only.
+__global__ void __launch_bounds__(32 * kWarpsPerCta) svd_warp_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a,
+                                                                     int64_t abs_, double* __restrict__ out1, int64_t o1bs,
+                                                                     double* __restrict__ sv, int64_t sbs, double* __restrict__ out2,
+                                                                     int64_t o2bs, int nb) {
+    extern __shared__ double smem[];
+    const int64_t* sc = sect + (int64_t)blockIdx.x * TNSP_SECT_COLS;
+    const int m = (int)sc[0], n = (int)sc[1], k = (int)sc[2];
+    if (m * n == 0) return;
+    const bool tall = m >= n;
+    const int p = tall ? m : n, q = tall ? n : m;
+    const int ldp = p | 1, ldq = q | 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* G = smem + (int64_t)warp * kWarpDoubles;   // G[c*ldp + r]
+    double* V = G + q * ldp;                            // V[c*ldq + t]
+    double* sig = V + q * ldq;
+    int* rnk = reinterpret_cast<int*>(sig + q);
+    int gs = 32;                                        // lanes per pair: smallest power of two >= p, at least 4
+    while (gs > 4 && (gs >> 1) >= p) gs >>= 1;
+    const int ngroups = 32 / gs, grp = lane / gs, gl = lane % gs;
+    const int qe = q + (q & 1), npairs = qe / 2;
+    const double tol = fmax(1e-15, sqrt((double)p) * 2.3e-16);
+    for (int b = blockIdx.y * kWarpsPerCta + warp; b < nb; b += gridDim.y * kWarpsPerCta) {
+        const double* A = a + (int64_t)b * abs_ + sc[3];
+        if (tall) {
+            for (int e = lane; e < m * n; e += 32) G[(e % n) * ldp + (e / n)] = A[e];
+        } else {
+            for (int e = lane; e < m * n; e += 32) G[(e / n) * ldp + (e % n)] = A[e];
+        }
+        for (int e = lane; e < q * q; e += 32) V[(e / q) * ldq + (e % q)] = ((e / q) == (e % q)) ? 1.0 : 0.0;
+        __syncwarp();
+        for (int sweep = 0; sweep < 60 && q > 1; ++sweep) {
+            bool rotated = false;
+            for (int round = 0; round < qe - 1; ++round) {
+                for (int base = 0; base < npairs; base += ngroups) {
+                    const int pr = base + grp;
+                    int i = 0, j = 0;
+                    bool valid = pr < npairs;
+                    if (valid) {
+                        if (pr == 0) { i = qe - 1; j = round; }
+                        else { i = (round + pr) % (qe - 1); j = (round - pr + (qe - 1)) % (qe - 1); }
+                        valid = i < q && j < q;
+                        if (i > j) { const int t = i; i = j; j = t; }
+                    }
+                    double* gi = G + i * ldp;
+                    double* gj = G + j * ldp;
+                    double aa = 0.0, bb = 0.0, cc = 0.0;
+                    if (valid)
+                        for (int r = gl; r < p; r += gs) { const double x = gi[r], y = gj[r]; aa += x * x; bb += y * y; cc += x * y; }
+                    aa = group_sum(aa, gs); bb = group_sum(bb, gs); cc = group_sum(cc, gs);
+                    if (valid && fabs(cc) > tol * sqrt(aa * bb) && aa * bb > 0.0) {
+                        const double zeta = (bb - aa) / (2.0 * cc);
+                        const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+                        for (int r = gl; r < p; r += gs) { const double x = gi[r], y = gj[r]; gi[r] = cs * x - sn * y; gj[r] = sn * x + cs * y; }
+                        double* vi = V + i * ldq;
+                        double* vj = V + j * ldq;
+                        for (int r = gl; r < q; r += gs) { const double x = vi[r], y = vj[r]; vi[r] = cs * x - sn * y; vj[r] = sn * x + cs * y; }
+                        rotated = true;
+                    }
+                }
+                __syncwarp();
+            }
+            if (!__any_sync(0xffffffffu, rotated)) break;
+        }
+        for (int c = 0; c < q; ++c) {
+            double s2 = 0.0;
+            for (int r = lane; r < p; r += 32) s2 += G[c * ldp + r] * G[c * ldp + r];
+            s2 = warp_sum(s2);
+            if (lane == 0) sig[c] = sqrt(s2);
+        }
+        __syncwarp();
+        for (int c = lane; c < q; c += 32) {
+            const double s = sig[c];
+            int r = 0;
+            for (int o = 0; o < q; ++o) { const double so = sig[o]; r += (so > s) || (so == s && o < c); }
+            rnk[c] = r;
+        }
+        __syncwarp();
+        double* S = sv + (int64_t)b * sbs + sc[6];
+        double* O1 = out1 + (int64_t)b * o1bs + sc[4];
+        double* O2 = out2 + (int64_t)b * o2bs + sc[5];
+        for (int c = lane; c < q; c += 32) S[rnk[c]] = sig[c];
+        if (tall) {
+            for (int e = lane; e < m * k; e += 32) {
+                const int c = e % k, r = e / k;   // consecutive lanes -> consecutive source columns of one row
+                const double s = sig[c];
+                O1[r * k + rnk[c]] = s > 0.0 ? G[c * ldp + r] / s : 0.0;
+            }
+            for (int e = lane; e < k * n; e += 32) { const int c = e / n, t = e - c * n; O2[rnk[c] * n + t] = V[c * ldq + t]; }
+        } else {
+            for (int e = lane; e < m * k; e += 32) { const int c = e % k, t = e / k; O1[t * k + rnk[c]] = V[c * ldq + t]; }
+            for (int e = lane; e < k * n; e += 32) {
+                const int c = e / n, r = e - c * n;
+                const double s = sig[c];
+                O2[rnk[c] * n + r] = s > 0.0 ? G[c * ldp + r] / s : 0.0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Greedy cross-sector truncation (svd.hpp:429-481) as a global ranking: value (i,t) is kept iff
 // fewer than remain_cut values precede it in (value desc, sector asc, position asc) order and it
 // exceeds relative_cut * max.  One CTA per chain.
@@ -353,7 +578,21 @@ extern "C" int tnsp_qr_batched_f64(const int64_t* sect, int ns, const int64_t* s
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDoubles * 8);
+        cudaFuncSetAttribute(qr_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpsPerCta * kWarpDoubles * 8);
         attr_set = true;
+    }
+    bool small = true;
+    for (int i = 0; i < ns; ++i) {
+        const int64_t m = sh[i * TNSP_SECT_COLS], n = sh[i * TNSP_SECT_COLS + 1], k = sh[i * TNSP_SECT_COLS + 2];
+        if (m * n == 0) continue;
+        if (qr_warp_need(use_qr ? m : n, use_qr ? n : m, k) > kWarpDoubles) small = false;
+    }
+    if (small) {
+        int64_t gy = (nb + kWarpsPerCta - 1) / kWarpsPerCta;
+        if (gy > 65535) gy = 65535;
+        qr_warp_kernel<<<dim3(ns, (unsigned)gy), 32 * kWarpsPerCta, kWarpsPerCta * kWarpDoubles * 8, (cudaStream_t)stream>>>(
+            sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb);
+        return check_launch("tnsp_qr_batched_f64(warp)");
     }
     const int gy = nb > 65535 ? 65535 : nb;
     qr_kernel<<<dim3(ns, gy), kFactorThreads, smem * 8, (cudaStream_t)stream>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb);
@@ -397,7 +636,21 @@ extern "C" int tnsp_svd_batched_f64(const int64_t* sect, int ns, const int64_t* 
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(svd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDoubles * 8);
+        cudaFuncSetAttribute(svd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpsPerCta * kWarpDoubles * 8);
         attr_set = true;
+    }
+    bool small = true;
+    for (int i = 0; i < ns; ++i) {
+        const int64_t m = sh[i * TNSP_SECT_COLS], n = sh[i * TNSP_SECT_COLS + 1];
+        if (m * n == 0) continue;
+        if (svd_warp_need(m >= n ? m : n, m >= n ? n : m) > kWarpDoubles) small = false;
+    }
+    if (small) {
+        int64_t gyw = (nb + kWarpsPerCta - 1) / kWarpsPerCta;
+        if (gyw > 65535) gyw = 65535;
+        svd_warp_kernel<<<dim3(ns, (unsigned)gyw), 32 * kWarpsPerCta, kWarpsPerCta * kWarpDoubles * 8, st>>>(
+            sect, a, abs_, out1, o1bs, s, sbs, out2, o2bs, nb);
+        return check_launch("tnsp_svd_batched_f64(warp)");
     }
     const int gy = nb > 65535 ? 65535 : nb;
     svd_kernel<<<dim3(ns, gy), kFactorThreads, smem * 8, st>>>(sect, a, abs_, out1, o1bs, s, sbs, out2, o2bs, work, wbs, d_off, nb);

@@ -147,6 +147,56 @@ __global__ void __launch_bounds__(128) gemm_grouped_kernel(const int64_t* __rest
     }
 }
 
+
+// Small-sector path (m, n <= 16): one WARP computes the whole C of one (sector, chain) with operand
+// fragments loaded straight from global memory in the DMMA register layout -- no shared memory, no
+// barrier; a CTA of 4 warps covers 4 chains.  This is the shape class of almost every GEMM of the
+// cfg1-sized lattices (16x16x16, 4x4x16, 16x4x64 ...), where launch latency, not bandwidth, rules.
+__global__ void __launch_bounds__(128) gemm_small_kernel(const int64_t* __restrict__ desc, int ng, const double* __restrict__ a,
+                                                         int64_t abs_, const double* __restrict__ b, int64_t bbs,
+                                                         double* __restrict__ c, int64_t cbs, int nb) {
+    const int g = blockIdx.x;
+    const int64_t* d = desc + g * TNSP_GEMM_COLS;
+    const int m = (int)d[0], n = (int)d[1], k = (int)d[2];
+    const int64_t a_off = d[3], b_off = d[4], c_off = d[5], flags = d[6];
+    const double alpha = (double)d[7];
+    const bool a_km = flags & 1, b_nk = flags & 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    for (int bi = blockIdx.y * 4 + warp; bi < nb; bi += gridDim.y * 4) {
+        const double* A = a + (int64_t)bi * abs_ + a_off;
+        const double* B = b + (int64_t)bi * bbs + b_off;
+        double* C = c + (int64_t)bi * cbs + c_off;
+        double acc[2][2][2] = {};
+        for (int k0 = 0; k0 < k; k0 += 4) {
+            const int kk = k0 + tig;
+            double fa[2], fb[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = i * 8 + gid;
+                fa[i] = (r < m && kk < k) ? (a_km ? __ldg(A + (int64_t)kk * m + r) : __ldg(A + (int64_t)r * k + kk)) : 0.0;
+                const int cc = i * 8 + gid;
+                fb[i] = (cc < n && kk < k) ? (b_nk ? __ldg(B + (int64_t)cc * k + kk) : __ldg(B + (int64_t)kk * n + cc)) : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = i * 8 + gid;
+            if (r >= m) continue;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int cc = j * 8 + 2 * tig;
+                if (cc < n) C[(int64_t)r * n + cc] = alpha * acc[i][j][0];
+                if (cc + 1 < n) C[(int64_t)r * n + cc + 1] = alpha * acc[i][j][1];
+            }
+        }
+    }
+}
+
 template <int TM, int TN>
 static int launch_gemm(const int64_t* desc, int ng, const int64_t* dh, const double* a, int64_t abs_, const double* b, int64_t bbs,
                        double* c, int64_t cbs, int nb, cudaStream_t st) {
@@ -184,5 +234,10 @@ extern "C" int tnsp_gemm_grouped_f64(const int64_t* desc, int ng, const int64_t*
     if (mid_m && mid_n) return launch_gemm<2, 2>(desc, ng, desc_host, a, abs_, b, bbs, c, cbs, nb, st);
     if (mid_m) return launch_gemm<2, 1>(desc, ng, desc_host, a, abs_, b, bbs, c, cbs, nb, st);
     if (mid_n) return launch_gemm<1, 2>(desc, ng, desc_host, a, abs_, b, bbs, c, cbs, nb, st);
-    return launch_gemm<1, 1>(desc, ng, desc_host, a, abs_, b, bbs, c, cbs, nb, st);
+    {
+        int64_t gy = (nb + 3) / 4;
+        if (gy > 65535) gy = 65535;
+        gemm_small_kernel<<<dim3(ng, (unsigned)gy), 128, 0, st>>>(desc, ng, a, abs_, b, bbs, c, cbs, nb);
+        return check_launch("tnsp_gemm_grouped_f64(small)");
+    }
 }

@@ -170,17 +170,32 @@ __global__ void unary_kernel(const double* __restrict__ a, int64_t abs_, int op,
     }
 }
 
-// Fused log-derivative accumulation over the chains of a batch (deterministic: fixed chain order).
-__global__ void grad_accumulate_kernel(const double* __restrict__ holes, int64_t hbs, const double* __restrict__ weight,
-                                       const double* __restrict__ energy, double* __restrict__ delta, double* __restrict__ edelta,
-                                       int64_t size, int nb) {
+// Fused log-derivative accumulation over the chains of a batch, in two deterministic stages:
+// stage 1: CTA (x, y) sums chains [y*chunk, (y+1)*chunk) of elements x*128.. into partial[y]
+// stage 2: partials are added in fixed order into the running Delta / E*Delta accumulators.
+__global__ void grad_partial_kernel(const double* __restrict__ holes, int64_t hbs, const double* __restrict__ weight,
+                                    const double* __restrict__ energy, double* __restrict__ partial, int64_t size, int nb, int chunk) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= size) return;
+    const int b0 = blockIdx.y * chunk, b1 = min(nb, b0 + chunk);
     double d = 0.0, ed = 0.0;
-    for (int b = 0; b < nb; ++b) {
+    for (int b = b0; b < b1; ++b) {
         const double h = holes[(int64_t)b * hbs + i] * weight[b];
         d += h;
         ed += h * energy[b];
+    }
+    partial[((int64_t)blockIdx.y * 2) * size + i] = d;
+    partial[((int64_t)blockIdx.y * 2 + 1) * size + i] = ed;
+}
+
+__global__ void grad_final_kernel(const double* __restrict__ partial, int nchunks, double* __restrict__ delta,
+                                  double* __restrict__ edelta, int64_t size) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    double d = 0.0, ed = 0.0;
+    for (int y = 0; y < nchunks; ++y) {
+        d += partial[((int64_t)y * 2) * size + i];
+        ed += partial[((int64_t)y * 2 + 1) * size + i];
     }
     delta[i] += d;
     edelta[i] += ed;
@@ -301,9 +316,25 @@ extern "C" int tnsp_unary_f64(const double* a, int64_t abs_, int op, double* z, 
 extern "C" int tnsp_grad_accumulate_f64(const double* holes, int64_t hbs, const double* weight, const double* energy, double* delta,
                                         double* edelta, int64_t size, int nb, void* stream) {
     if (nb == 0 || size == 0) return 0;
-    grad_accumulate_kernel<<<(unsigned)((size + 127) / 128), 128, 0, (cudaStream_t)stream>>>(holes, hbs, weight, energy, delta, edelta,
-                                                                                           size, nb);
-    return check_launch("tnsp_grad_accumulate_f64");
+    static double* scratch = nullptr;
+    static int64_t scratch_cap = 0;
+    const int64_t gx = (size + 127) / 128;
+    int64_t nchunks = (2 * kSMs + gx - 1) / gx;       // enough CTAs to fill the machine
+    if (nchunks > nb) nchunks = nb;
+    if (nchunks < 1) nchunks = 1;
+    const int chunk = (int)((nb + nchunks - 1) / nchunks);
+    nchunks = (nb + chunk - 1) / chunk;
+    const int64_t need = nchunks * 2 * size;
+    if (need > scratch_cap) {
+        if (scratch) cudaFree(scratch);
+        scratch_cap = need * 2;
+        if (cudaMalloc(&scratch, sizeof(double) * scratch_cap) != cudaSuccess) { set_error("tnsp_grad_accumulate_f64: cudaMalloc"); return 1; }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    grad_partial_kernel<<<dim3((unsigned)gx, (unsigned)nchunks), 128, 0, st>>>(holes, hbs, weight, energy, scratch, size, nb, chunk);
+    if (check_launch("tnsp_grad_accumulate_f64(partial)")) return 1;
+    grad_final_kernel<<<(unsigned)gx, 128, 0, st>>>(scratch, (int)nchunks, delta, edelta, size);
+    return check_launch("tnsp_grad_accumulate_f64(final)");
 }
 
 extern "C" int tnsp_block_sign_f64(const int64_t* blk, int nblk, const double* x, int64_t xbs, double* y, int64_t ybs, int64_t size,
