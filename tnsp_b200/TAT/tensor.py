@@ -394,7 +394,11 @@ class Tensor:
     zero = zero_
 
     def range_(self, first=0, step=1):
-        self._set_host(first + step * np.arange(self._table.size, dtype=np.float64))
+        # the reference fills by repeated addition (now += step), not first + i*step
+        inc = np.full(self._table.size, float(step))
+        if inc.size:
+            inc[0] = float(first)
+        self._set_host(np.cumsum(inc))
         return self
 
     range = range_
