@@ -25,11 +25,30 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (L1, L2, D, Dc, description)
-    "cfg1": (4, 4, 4, 16, "tetragono sampling VMC 4x4 Heisenberg square lattice, no symmetry, D=4, Dc=16, float64"),
-    "heis6": (6, 6, 6, 36, "6x6 Heisenberg, no symmetry (dense stand-in of cfg2), D=6, Dc=36, float64"),
-    "tiny": (3, 3, 2, 4, "3x3 Heisenberg, no symmetry, D=2, Dc=4 (smoke size)"),
+    # name: dict(L1, L2, D, Dc, sym, J2, sr (SR natural gradient by CG with `cg` iterations per step), chains, desc)
+    "cfg1": dict(L1=4, L2=4, D=4, Dc=16, sym="No", J2=0.0, sr=False, cg=0, chains=4096,
+                 desc="tetragono sampling VMC 4x4 Heisenberg square lattice, no symmetry, D=4, Dc=16, float64"),
+    "cfg2": dict(L1=6, L2=6, D=6, Dc=36, sym="BoseU1", J2=0.5, sr=True, cg=20, chains=296,
+                 desc="6x6 J1-J2 Heisenberg (J2=0.5) with U(1) symmetry, D=6 (2+2+2), Dc=36, sweep sampling + SR natural gradient (CG 20), float64"),
+    "cfg2s": dict(L1=4, L2=4, D=3, Dc=9, sym="BoseU1", J2=0.5, sr=True, cg=4, chains=64,
+                  desc="4x4 J1-J2 Heisenberg with U(1) symmetry, D=3, Dc=9, sweep + SR (smoke size of cfg2)"),
+    "heis6": dict(L1=6, L2=6, D=6, Dc=36, sym="No", J2=0.0, sr=False, cg=0, chains=148,
+                  desc="6x6 Heisenberg, no symmetry (dense tensors), D=6, Dc=36, float64"),
+    "tiny": dict(L1=3, L2=3, D=2, Dc=4, sym="No", J2=0.0, sr=False, cg=0, chains=64, desc="3x3 Heisenberg, no symmetry, D=2, Dc=4 (smoke size)"),
 }
+
+
+def build_workload(tat, wl, state_classes=None):
+    """(SamplingLattice on `tat`'s tensors, sweep hopping terms or None, Neel edge points).  The same function
+    builds the model for this repository's device tensors and for the reference PyTAT classes."""
+    from tnsp_b200.tetragono import models
+    from tnsp_b200.tetragono.state import SamplingLattice
+    T = getattr(tat, wl["sym"]).D.Tensor
+    abstract = models.j1j2_abstract_lattice(T, wl["L1"], wl["L2"], wl["D"], 1.0, wl["J2"])
+    tat.random.seed(2333)
+    lat = SamplingLattice(abstract)
+    hopping = models.nearest_neighbour_terms(lat) if wl["J2"] != 0 else None
+    return lat, hopping, models.neel_points(lat)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -40,51 +59,39 @@ def _reference_worker(args):
     workload, seed, n_warm, n_samples, use_ref = args
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     os.environ["OMP_NUM_THREADS"] = "1"
-    L1, L2, D, Dc, _ = WORKLOADS[workload]
+    wl = WORKLOADS[workload]
     if use_ref:
         from oracle.ref import load_reference_tat
         tat = load_reference_tat()
     else:
         tat = None
-    from tnsp_b200.tetragono import models
     from tnsp_b200.tetragono.observer import Observer
     from tnsp_b200.tetragono.sampling import SweepSampling
-    from tnsp_b200.tetragono.state import AbstractLattice, AbstractState, SamplingLattice
     import tnsp_b200.TAT.random as rnd
     if tat is None:
         # "port": the numpy checker backend under this repository's planner
         from oracle import numpy_backend
         numpy_backend.install()
-        import tnsp_b200.TAT as tat_mod
-        T = tat_mod.No.D.Tensor
-        seed_fn = tat_mod.random.seed
-    else:
-        T = tat.No.D.Tensor
-        seed_fn = tat.random.seed
-    state = AbstractState(T, L1, L2)
-    state.physics_edges[...] = 2
-    H = T(["I0", "I1", "O0", "O1"], [2, 2, 2, 2]).zero_()
-    H.storage = -np.asarray(models.spin_half_SS_array()).reshape(-1)
-    state.hamiltonians["vertical_bond"] = H
-    state.hamiltonians["horizontal_bond"] = H
-    lat = AbstractLattice(state)
-    lat.virtual_bond["R"] = D
-    lat.virtual_bond["D"] = D
-    seed_fn(2333)
-    lat = SamplingLattice(lat)
+        import tnsp_b200.TAT as tat
+    lat, hopping, points = build_workload(tat, wl)
     rnd.seed(seed)
-    s = SweepSampling(lat, Dc)
-    s.configuration.import_configuration(models.neel_configuration(L1, L2))
-    obs = Observer(lat, enable_energy=True, enable_gradient=True)
+    s = SweepSampling(lat, wl["Dc"], None, hopping)
+    for l1, row in enumerate(points):
+        for l2, site in enumerate(row):
+            for o, pt in site.items():
+                s.configuration[l1, l2, o] = pt
+    obs = Observer(lat, enable_energy=True, enable_gradient=True, enable_natural_gradient=wl["sr"])
     with obs:
         for _ in range(n_warm):
             p, c = s()
             obs(p, c)
-        t0 = time.perf_counter()
+    t0 = time.perf_counter()
+    with obs:
         for _ in range(n_samples):
             p, c = s()
             obs(p, c)
-        dt = time.perf_counter() - t0
+    g = obs.natural_gradient_by_conjugate_gradient(wl["cg"], 0.0) if wl["sr"] else obs.gradient
+    dt = time.perf_counter() - t0
     return n_samples, dt, obs.energy[0]
 
 
@@ -181,12 +188,22 @@ def run_own(args):
     from tnsp_b200.tetragono.sampling import ChainRng, SweepSampling
     B = backend.get()   # raises without the CUDA library / a GPU: no CPU fallback
 
-    L1, L2, D, Dc, desc = WORKLOADS[args.workload]
-    nb = args.chains
-    lat = models.random_sampling_lattice(models.heisenberg_lattice(L1, L2, D), 2333)
+    wl = WORKLOADS[args.workload]
+    L1, L2, Dc, desc = wl["L1"], wl["L2"], wl["Dc"], wl["desc"]
+    nb = args.chains or wl["chains"]
+    sym_lat, hopping, points = build_workload(TAT, wl)
+    if wl["sym"] == "No":
+        lat = sym_lat
+        conf0 = models.neel_configuration(L1, L2)
+    else:
+        # symmetric PEPS enter the lock-step engine through the charge-dense embedding
+        from tnsp_b200.tetragono import dense_embedding
+        lat = dense_embedding.embed_lattice(sym_lat)
+        conf0 = dense_embedding.embed_configuration(sym_lat, points)
+        hopping = models.nearest_neighbour_terms(lat) if hopping is not None else None
     # one normalisation pass so that amplitudes are O(1) (observer.normalize_lattice)
-    s0 = SweepSampling(lat, Dc, nb=1)
-    s0.configuration.import_configuration(models.neel_configuration(L1, L2))
+    s0 = SweepSampling(lat, Dc, None, hopping, nb=1)
+    s0.configuration.import_configuration(conf0)
     TAT.random.seed(2333)
     o0 = Observer(lat, enable_energy=True)
     with o0:
@@ -194,18 +211,22 @@ def run_own(args):
             p, c = s0()
             o0(p, c)
     o0.normalize_lattice()
+    del s0, o0
 
     rng = ChainRng(nb)
     rng.seed([(2333 + rank * nb + c) % 2**31 for c in range(nb)])
     rng.uniform_real(None)
-    sampling = SweepSampling(lat, Dc, nb=nb, rng=rng)
-    conf0 = models.neel_configuration(L1, L2)
+    sampling = SweepSampling(lat, Dc, None, hopping, nb=nb, rng=rng)
     sampling.configuration.import_configuration(np.broadcast_to(conf0, (nb,) + conf0.shape))
-    observer = Observer(lat, enable_energy=True, enable_gradient=True)
+    observer = Observer(lat, enable_energy=True, enable_gradient=True, enable_natural_gradient=wl["sr"])
 
     def step():
-        p, c = sampling()
-        observer(p, c)
+        """one optimisation step of the reference's gradient_descent loop (gradient.py:327-399) on this rank's
+        chains: sweep + observe every chain, reduce, gradient (SR natural gradient by CG for cfg2)"""
+        with observer:
+            p, c = sampling()
+            observer(p, c)
+        return observer.natural_gradient_by_conjugate_gradient(wl["cg"], 0.0) if wl["sr"] else observer.gradient
 
     def sync_all():
         torch.cuda.synchronize()
@@ -213,23 +234,22 @@ def run_own(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -------------------------------------------------------------------
-    with observer:
-        for _ in range(args.warmup):
-            step()
-        clocks = ClockSampler(local_rank)
-        if rank == 0:
-            clocks.start()
-        sync_all()
-        l0 = B.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            step()
-        e1.record()
-        sync_all()
-        launches = B.launch_count() - l0
-        ms = e0.elapsed_time(e1)
-        clock_info = clocks.stop() if rank == 0 else None
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    sync_all()
+    l0 = B.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    launches = B.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clock_info = clocks.stop() if rank == 0 else None
     energy = observer.energy
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -245,7 +265,6 @@ def run_own(args):
     host_sites = [[torch.from_numpy(np.ascontiguousarray(np.asarray(lat[l1, l2].storage))).pin_memory() for l2 in range(L2)] for l1 in range(L1)]
     h2d = sum(t_.numel() * 8 for row in host_sites for t_ in row)
     d2h = 0
-    obs2 = Observer(lat, enable_energy=True, enable_gradient=True)
 
     def e2e_step():
         nonlocal d2h
@@ -253,12 +272,9 @@ def run_own(args):
             for l2 in range(L2):
                 lat[l1, l2]._data = host_sites[l1][l2].to("cuda", non_blocking=True).reshape(1, -1)
         sampling.configuration.refresh_all()
-        with obs2:
-            p, c = sampling()
-            obs2(p, c)
-        grad = obs2.gradient
+        grad = step()
         out = [g.data.cpu() for row in grad for g in row]
-        e = obs2.energy
+        e = observer.energy
         d2h = sum(o.numel() * 8 for o in out) + 16
         return e, out
 
@@ -286,15 +302,14 @@ def run_own(args):
     if rank == 0:
         from tnsp_b200 import profiling
         prof = profiling.KernelTimer(B)
-        with observer:
-            for _ in range(2):
-                step()
-            torch.cuda.synchronize()
-            prof.enable()
-            for _ in range(3):
-                step()
-            torch.cuda.synchronize()
-            prof.disable()
+        n_prof = 3 if ms_max / args.steps < 2000 else 1
+        step()
+        torch.cuda.synchronize()
+        prof.enable()
+        for _ in range(n_prof):
+            step()
+        torch.cuda.synchronize()
+        prof.disable()
         breakdown = prof.summary()
         peaks = {}
         try:
@@ -310,7 +325,9 @@ def run_own(args):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (randn_ PEPS seed 2333, Neel start, per-chain mt19937_64 seeds)",
             "config": {"workload": f"{args.workload}: {desc}", "chains_per_gpu": nb, "samples_per_step": nb * world,
-                       "observer": "energy+gradient", "l2": "working set of a step (all chains' environments) exceeds L2; no flush"},
+                       "observer": "energy+gradient" + ("+SR natural gradient (CG %d)" % wl["cg"] if wl["sr"] else ""),
+                       "symmetric_engine": None if wl["sym"] == "No" else "charge-dense embedding, sectors discovered on device",
+                       "l2": "working set of a step (all chains' environments) exceeds L2; no flush"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clock_info, "energy_per_site": energy[0],
             "roofline": roofline, "kernel_breakdown": breakdown,
@@ -324,8 +341,8 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own")
-    ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
-    ap.add_argument("--chains", type=int, default=4096, help="Markov chains per GPU (lock-step batch)")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=0, help="Markov chains per GPU (lock-step batch); 0 = the workload's default")
     ap.add_argument("--ref-samples", type=int, default=8, help="samples per chain per step in the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -334,12 +351,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        L1, L2, D, Dc, desc = WORKLOADS[args.workload]
+        desc = WORKLOADS[args.workload]["desc"]
         r = run_reference(args.workload, args.steps, max(1, args.warmup // 3), args.ref_samples)
         line = {"impl": "reference", "metric": "VMC samples/sec", "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic (randn_ PEPS seed 2333, Neel start)",
-                "config": {"workload": f"{args.workload}: {desc}", "observer": "energy+gradient"},
+                "config": {"workload": f"{args.workload}: {desc}", "observer": "energy+gradient" + ("+SR natural gradient" if WORKLOADS[args.workload]["sr"] else "")},
                 "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))

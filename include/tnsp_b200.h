@@ -72,6 +72,20 @@ int tnsp_svd_batched_f64(const int64_t* sect, int ns, const int64_t* sect_host, 
                          double* out2, int64_t o2_bstride, double* work, int64_t w_bstride,
                          int nb, void* stream);
 
+/* ---- K3s/K4s: the same factorisations for ONE dense(-embedded) matrix per chain (ns == 1) whose symmetry
+ * sectors are NOT named by the descriptor but discovered on the device from the zero pattern (connected
+ * components of the row/column graph): the lock-step batch engine stores symmetric tensors densely because
+ * the chains of a batch differ in their sector structure.  Per discovered sector this is qr.hpp:178-304 /
+ * svd.hpp:104-211; the bond index of a sector's factors is a contiguous range (QR) or the global descending
+ * rank of the singular value (SVD), so the first `cut` indices are the greedy cut of svd.hpp:429-481.
+ * Null vectors are zeros (a sector absent on one side does not appear, qr.hpp:419-429).  Outputs must be
+ * zero-initialised; work: tnsp_svd_work_size() doubles per chain. */
+int tnsp_qr_sectors_f64(const int64_t* sect, const int64_t* sect_host, double* a, int64_t a_bstride,
+                        double* out1, int64_t o1_bstride, double* out2, int64_t o2_bstride, int use_qr, int nb, void* stream);
+int tnsp_svd_sectors_f64(const int64_t* sect, const int64_t* sect_host, const double* a, int64_t a_bstride,
+                         double* out1, int64_t o1_bstride, double* s, int64_t s_bstride, double* out2, int64_t o2_bstride,
+                         double* work, int64_t w_bstride, int nb, void* stream);
+
 /* ---- greedy cross-sector truncation (svd.hpp:429-481): counts[b][i] = kept values of sector i. */
 int tnsp_svd_cut_f64(const int64_t* sect, int ns, int64_t s_total, const double* s, int64_t s_bstride,
                      int64_t remain_cut, double relative_cut, int32_t* counts, int nb, void* stream);

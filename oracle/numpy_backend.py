@@ -95,14 +95,25 @@ class NumpyBackend:
                 continue
             for b in range(nb):
                 M = A[b, ao:ao + m * n].reshape(m, n)
-                if plan.flag:
-                    q, r = np.linalg.qr(M, mode="reduced")
-                    O1[b, o1:o1 + m * k] = q.reshape(-1)
-                    O2[b, o2:o2 + k * n] = r.reshape(-1)
-                else:
-                    q, r = np.linalg.qr(M.T, mode="reduced")
-                    O1[b, o1:o1 + m * k] = r.T.reshape(-1)
-                    O2[b, o2:o2 + k * n] = q.T.reshape(-1)
+                F1 = np.zeros((m, k))
+                F2 = np.zeros((k, n))
+                k0 = 0
+                # one descriptor = dense(-embedded) matrix: factorise per connected block of the zero pattern,
+                # null vectors are zeros (what the discovered-sector CUDA kernels do, csrc/factor_sector.cu)
+                for rows, cols in (_zero_pattern_blocks(M) if len(plan.sectors) == 1 else [(np.arange(m), np.arange(n))]):
+                    Ms = M[np.ix_(rows, cols)]
+                    ks = min(Ms.shape)
+                    if plan.flag:
+                        q, r = np.linalg.qr(Ms, mode="reduced")
+                        F1[rows, k0:k0 + ks] = q
+                        F2[np.ix_(np.arange(k0, k0 + ks), cols)] = r
+                    else:
+                        q, r = np.linalg.qr(Ms.T, mode="reduced")
+                        F1[rows, k0:k0 + ks] = r.T
+                        F2[np.ix_(np.arange(k0, k0 + ks), cols)] = q.T
+                    k0 += ks
+                O1[b, o1:o1 + m * k] = F1.reshape(-1)
+                O2[b, o2:o2 + k * n] = F2.reshape(-1)
 
     # K4
     def svd(self, plan, a, out1, s, out2):
@@ -114,7 +125,26 @@ class NumpyBackend:
             if m * n == 0:
                 continue
             for b in range(nb):
-                u, sv, vt = np.linalg.svd(A[b, ao:ao + m * n].reshape(m, n), full_matrices=False)
+                M = A[b, ao:ao + m * n].reshape(m, n)
+                if len(plan.sectors) != 1:
+                    u, sv, vt = np.linalg.svd(M, full_matrices=False)
+                else:
+                    # per connected block of the zero pattern, then merged in descending order (ties: block order)
+                    us, ss, vs = [], [], []
+                    for rows, cols in _zero_pattern_blocks(M):
+                        bu, bs, bv = np.linalg.svd(M[np.ix_(rows, cols)], full_matrices=False)
+                        for t in range(len(bs)):
+                            cu_ = np.zeros(m)
+                            cu_[rows] = bu[:, t]
+                            cv_ = np.zeros(n)
+                            cv_[cols] = bv[t]
+                            us.append(cu_)
+                            ss.append(bs[t])
+                            vs.append(cv_)
+                    order = sorted(range(len(ss)), key=lambda t: (-ss[t], t))
+                    u, sv, vt = np.zeros((m, k)), np.zeros(k), np.zeros((k, n))
+                    for r_, t in enumerate(order):
+                        u[:, r_], sv[r_], vt[r_] = us[t], ss[t], vs[t]
                 O1[b, o1:o1 + m * k] = u.reshape(-1)
                 S[b, so:so + k] = sv
                 O2[b, o2:o2 + k * n] = vt.reshape(-1)
@@ -220,9 +250,29 @@ class NumpyBackend:
 
     def grad_accumulate(self, holes, weight, energy, delta, edelta):
         self.launches += 1
-        h = holes.numpy() * weight.numpy().reshape(-1, 1)
+        w = weight.numpy().reshape(-1, 1)
+        h = np.where(w != 0, holes.numpy(), 0.0) * w   # chains of zero weight (zero amplitude) are skipped
         delta.numpy()[...] += h.sum(axis=0)
         edelta.numpy()[...] += (h * energy.numpy().reshape(-1, 1)).sum(axis=0)
+
+
+def _zero_pattern_blocks(M):
+    """connected components of the bipartite row/column graph of the non-zeros of M, ordered by their first
+    row (the sector order of csrc/factor_sector.cu); all-zero rows / columns belong to no block"""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    m, n = M.shape
+    nz = M != 0
+    g = csr_matrix((np.ones(int(nz.sum()), dtype=np.int8), (np.nonzero(nz)[0], np.nonzero(nz)[1] + m)), shape=(m + n, m + n))
+    _, lab = connected_components(g, directed=False)
+    used_r, used_c = nz.any(axis=1), nz.any(axis=0)
+    out = []
+    seen = set()
+    for i in range(m):
+        if used_r[i] and lab[i] not in seen:
+            seen.add(lab[i])
+            out.append((np.nonzero((lab[:m] == lab[i]) & used_r)[0], np.nonzero((lab[m:] == lab[i]) & used_c)[0]))
+    return out
 
 
 def install():

@@ -60,7 +60,7 @@ def point_desc(sym_name, p):
     return [sym_tuple(sym_name, p[0]), int(p[1])]
 
 
-def dump_case(name, sym_name, lattice, Dc, config_points, seed, n_samples, cg_step=2):
+def dump_case(name, sym_name, lattice, Dc, config_points, seed, n_samples, cg_step=2, hopping=None):
     arrays = {}
     meta = {"symmetry": sym_name, "L1": lattice.L1, "L2": lattice.L2, "Dc": Dc,
             "total_symmetry": sym_tuple(sym_name, lattice.total_symmetry)}
@@ -93,7 +93,8 @@ def dump_case(name, sym_name, lattice, Dc, config_points, seed, n_samples, cg_st
 
     # --- sweep trajectory from a fixed seed -----------------------------------------------------------
     TAT.random.seed(seed)
-    sampling = tet.sampling_lattice.SweepSampling(lattice, Dc, None, None)
+    sampling = tet.sampling_lattice.SweepSampling(lattice, Dc, None, hopping)
+    meta["sweep_nearest_neighbour_only"] = hopping is not None
     for l1 in range(lattice.L1):
         for l2 in range(lattice.L2):
             for o, p in config_points[l1][l2].items():
@@ -161,6 +162,19 @@ def heisenberg_u1(L1, L2, d):
     return tet.SamplingLattice(lat)
 
 
+def j1j2_u1(L1, L2, d, J2):
+    """cfg2 family: J1-J2 Heisenberg with U(1) tensors; diagonal J2 terms are measured by
+    the Observer through the 2x2 replace branch but excluded from the sweep (sampling.py:156-190)"""
+    lat = heisenberg_u1(L1, L2, d)
+    H1 = lat._hamiltonians[((0, 0, 0), (0, 1, 0))]
+    H2 = J2 * H1
+    for l1 in range(L1 - 1):
+        for l2 in range(L2 - 1):
+            lat.hamiltonians[(l1, l2, 0), (l1 + 1, l2 + 1, 0)] = H2
+            lat.hamiltonians[(l1, l2 + 1, 0), (l1 + 1, l2, 0)] = H2
+    return lat
+
+
 def neel_u1(lattice):
     S = lattice.Symmetry
     return [[{0: (S(+1) if (l1 + l2) % 2 == 0 else S(-1), 0)} for l2 in range(lattice.L2)] for l1 in range(lattice.L1)]
@@ -196,6 +210,11 @@ def hubbard_ff(L1, L2, D, T):
 
 
 def main():
+    if "j1j2" in sys.argv[1:]:
+        lat = j1j2_u1(4, 4, 1, 0.5)
+        hop = {k: v for k, v in lat._hamiltonians.items() if k[0][0] == k[1][0] or k[0][1] == k[1][1]}
+        dump_case("j1j2U1_4x4_d1_Dc9", "BoseU1", lat, 9, neel_u1(lat), seed=17, n_samples=6, hopping=hop)
+        return
     lat = heisenberg(3, 3, 2)
     dump_case("heis_3x3_D2_Dc4", "No", lat, 4, neel(lat), seed=11, n_samples=12)
     lat = heisenberg(4, 4, 4)

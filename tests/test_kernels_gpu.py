@@ -166,3 +166,92 @@ def test_streaming_kernels():
     ck.grad_accumulate(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(e), td, te)
     assert np.allclose(cu.to_numpy(D), td.numpy(), rtol=1e-13, atol=1e-13)
     assert np.allclose(cu.to_numpy(ED), te.numpy(), rtol=1e-13, atol=1e-13)
+
+
+def _block_matrix(rng, m, n, n_sec, zero_rows=0, zero_cols=0):
+    """m x n matrix that is block diagonal after chain-specific row / column permutations (what the
+    charge-dense embedding of a symmetric tensor looks like), plus all-zero rows / columns"""
+    M = np.zeros((m, n))
+    rows = rng.permutation(m)[:m - zero_rows]
+    cols = rng.permutation(n)[:n - zero_cols]
+    rcut = np.sort(rng.choice(np.arange(1, len(rows)), n_sec - 1, replace=False)) if n_sec > 1 else []
+    ccut = np.sort(rng.choice(np.arange(1, len(cols)), n_sec - 1, replace=False)) if n_sec > 1 else []
+    ksum = 0
+    for t, (rs, cs) in enumerate(zip(np.split(rows, rcut), np.split(cols, ccut))):
+        blk = rng.standard_normal((len(rs), len(cs)))
+        if t % 2 == 1:
+            # staircase block (what triangular R factors / rank-limited bonds leave inside a sector): still connected
+            blk = np.triu(blk)
+            blk[0, :] = rng.standard_normal(len(cs))
+        elif t % 3 == 2:
+            # rank-1 sector (bond larger than the rank it can carry, as at the lattice boundary)
+            blk = np.outer(rng.standard_normal(len(rs)), rng.standard_normal(len(cs)))
+        M[np.ix_(rs, cs)] = blk
+        ksum += min(len(rs), len(cs))
+    return M, ksum
+
+
+@pytest.fixture
+def discovery():
+    cu, _ = _both()
+    cu.sector_discovery = True
+    yield cu
+    cu.sector_discovery = False
+
+
+@pytest.mark.parametrize("shape", [(300, 120, 5, 3, 2), (120, 300, 4, 0, 5), (216, 216, 7, 0, 0), (700, 216, 1, 0, 0), (90, 90, 90, 0, 0),
+                                   (1296, 216, 6, 0, 0), (6, 36, 3, 0, 4), (36, 6, 3, 2, 0), (6, 6, 2, 2, 2), (1, 5, 1, 0, 0)])
+@pytest.mark.parametrize("use_qr", [True, False])
+def test_sector_discovery_qr(shape, use_qr, discovery):
+    """dense-embedded (block structured, per-chain permuted) matrices: sectors are found on the device"""
+    m, n, n_sec, zr, zc = shape
+    cu = discovery
+    p, ao, o1, o2, _ = _factor_plan([(m, n)], use_qr)
+    nb = 3
+    rng = np.random.default_rng(m + n)
+    mats = [_block_matrix(rng, m, n, n_sec, zr, zc) for _ in range(nb)]
+    a = np.stack([M.reshape(-1) for M, _ in mats])
+    t1, t2 = cu.zeros(nb, o1), cu.zeros(nb, o2)
+    cu.qr(p, cu.from_numpy(a), t1, t2)
+    T1, T2 = cu.to_numpy(t1), cu.to_numpy(t2)
+    k = min(m, n)
+    for b in range(nb):
+        M, ksum = mats[b]
+        F1, F2 = T1[b].reshape(m, k), T2[b].reshape(k, n)
+        assert np.abs(F1 @ F2 - M).max() <= 1e-12 * max(m, n)
+        G = F1.T @ F1 if use_qr else F2 @ F2.T          # isometry on the used bond indices, zero elsewhere
+        d = np.diag(G)
+        assert np.abs(G - np.diag(d)).max() <= 1e-12
+        assert np.all((np.abs(d - 1) <= 1e-12) | (d == 0)) and int(round(d.sum())) <= ksum
+        # the factors keep the sector structure: factor entries are non-zero only on rows / columns of one sector
+        rows_used = (M != 0).any(axis=1)
+        cols_used = (M != 0).any(axis=0)
+        assert not F1[~rows_used].any() and not F2[:, ~cols_used].any()
+
+
+@pytest.mark.parametrize("shape", [(216, 216, 7, 0, 0), (150, 260, 4, 3, 2), (260, 150, 5, 2, 0), (200, 180, 1, 0, 0), (64, 64, 64, 0, 0),
+                                   (300, 300, 1, 0, 0), (6, 36, 3, 0, 4), (36, 6, 3, 2, 0), (6, 6, 2, 2, 2), (1, 5, 1, 0, 0)])
+def test_sector_discovery_svd(shape, discovery):
+    m, n, n_sec, zr, zc = shape
+    cu = discovery
+    p, ao, o1, o2, so = _factor_plan([(m, n)], True)
+    nb = 3
+    rng = np.random.default_rng(m * 3 + n)
+    mats = [_block_matrix(rng, m, n, n_sec, zr, zc) for _ in range(nb)]
+    a = np.stack([M.reshape(-1) for M, _ in mats])
+    t1, t2, s = cu.zeros(nb, o1), cu.zeros(nb, o2), cu.zeros(nb, so)
+    cu.svd(p, cu.from_numpy(a), t1, s, t2)
+    T1, T2, S = cu.to_numpy(t1), cu.to_numpy(t2), cu.to_numpy(s)
+    k = min(m, n)
+    for b in range(nb):
+        M, ksum = mats[b]
+        U, Vt, sv = T1[b].reshape(m, k), T2[b].reshape(k, n), S[b]
+        ref = np.linalg.svd(M, compute_uv=False)
+        assert np.all(np.diff(sv) <= 0)
+        assert np.abs(sv - ref).max() <= 1e-12 * ref.max()
+        assert np.abs((U * sv) @ Vt - M).max() <= 1e-12 * ref.max() * max(m, n)
+        rank = int((ref > 1e-10 * ref.max()).sum())
+        G = U.T @ U
+        assert np.abs(G[:rank, :rank] - np.eye(rank)).max() <= 1e-11
+        G = Vt @ Vt.T
+        assert np.abs(G[:rank, :rank] - np.eye(rank)).max() <= 1e-11

@@ -59,7 +59,11 @@ def test_sweep_trajectory_gradient(case):
     meta, z = load(case)
     lat = build_lattice(meta, z)
     TAT.random.seed(meta["seed"])
-    sampling = SweepSampling(lat, meta["Dc"], None, None)
+    hopping = None
+    if meta.get("sweep_nearest_neighbour_only"):
+        from tnsp_b200.tetragono.models import nearest_neighbour_terms
+        hopping = nearest_neighbour_terms(lat)
+    sampling = SweepSampling(lat, meta["Dc"], None, hopping)
     _set_config(sampling.configuration, config_points(meta))
     obs = Observer(lat, enable_energy=True, enable_gradient=True, enable_natural_gradient=True)
     with obs:

@@ -786,4 +786,51 @@ class Tensor:
     def _not_on_path(self, *a, **k):
         raise NotImplementedError("this Tensor method is outside the sampling-VMC hot path (SURVEY.md section 8)")
 
-    trace = exponential = shrink = expand = clear_symmetry = clear_bose_symmetry = clear_fermi_symmetry = dump = load = _not_on_path
+    trace = exponential = shrink = expand = clear_fermi_symmetry = dump = load = _not_on_path
+
+    # -- dense embedding (clear_symmetry.hpp: bosonic symmetries only) ----------------------------------
+    def _segment_starts(self):
+        return [np.concatenate([[0], np.cumsum(e.dims)[:-1]]).astype(np.int64) if len(e.dims) else np.zeros(0, np.int64) for e in self._edges]
+
+    def clear_symmetry(self):
+        """NoSymmetry tensor with the same names and total dimensions, exact zeros in the forbidden
+        blocks (reference: TAT/include/TAT/implement/clear_symmetry.hpp).  Host-side (set-up only);
+        this is how symmetric PEPS enter the lock-step batch engine."""
+        if self.Symmetry.is_fermi_symmetry:
+            raise NotImplementedError("clear_symmetry of fermionic tensors is outside the hot path")
+        from .. import TAT as _tat
+        No = _tat.No.D.Tensor
+        dims = [e.dimension for e in self._edges]
+        h = np.atleast_2d(self._host())
+        nb = h.shape[0]
+        dense = np.zeros([nb] + dims, dtype=np.float64)
+        starts = self._segment_starts()
+        for b, pos in enumerate(self._table.positions):
+            bd = [int(d) for d in self._table.dims[b]]
+            off, size = int(self._table.offsets[b]), int(self._table.sizes[b])
+            sl = (slice(None),) + tuple(slice(int(starts[i][int(p)]), int(starts[i][int(p)]) + bd[i]) for i, p in enumerate(pos))
+            dense[sl] = h[:, off:off + size].reshape([nb] + bd)
+        return No.from_batch(list(self.names), [No.Edge(d) for d in dims], dense.reshape(nb, -1))
+
+    clear_bose_symmetry = clear_symmetry
+
+    def fill_from_dense(self, dense):
+        """inverse of clear_symmetry: read this tensor's blocks out of a dense array / NoSymmetry tensor
+        with the same names (entries outside the blocks are dropped = projection onto the symmetric sector)"""
+        if isinstance(dense, Tensor):
+            if dense.names != self.names:
+                dense = dense.transpose(self.names)
+            dense = np.atleast_2d(dense._host())
+        dims = [e.dimension for e in self._edges]
+        dense = np.asarray(dense, dtype=np.float64)
+        nb = dense.size // max(1, int(np.prod(dims))) if dims else dense.size
+        dense = dense.reshape([nb] + dims)
+        out = np.zeros((nb, self._table.size))
+        starts = self._segment_starts()
+        for b, pos in enumerate(self._table.positions):
+            bd = [int(d) for d in self._table.dims[b]]
+            off, size = int(self._table.offsets[b]), int(self._table.sizes[b])
+            sl = (slice(None),) + tuple(slice(int(starts[i][int(p)]), int(starts[i][int(p)]) + bd[i]) for i, p in enumerate(pos))
+            out[:, off:off + size] = dense[sl].reshape(nb, size)
+        self._set_host(out)
+        return self

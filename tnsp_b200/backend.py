@@ -77,6 +77,10 @@ class CudaBackend:
         lib.tnsp_svd_work_size.restype = c_i64
         lib.tnsp_svd_work_size.argtypes = [P, c_int]
         lib.tnsp_svd_batched_f64.argtypes = [P, c_int, P, P, c_i64, P, c_i64, P, c_i64, P, c_i64, P, c_i64, c_int, P]
+        lib.tnsp_qr_sectors_f64.argtypes = [P, P, P, c_i64, P, c_i64, P, c_i64, c_int, c_int, P]
+        lib.tnsp_svd_sectors_f64.argtypes = [P, P, P, c_i64, P, c_i64, P, c_i64, P, c_i64, P, c_i64, c_int, P]
+        # set by tetragono.dense_embedding: single-descriptor factorisations discover their sectors on the device
+        self.sector_discovery = False
         lib.tnsp_svd_cut_f64.argtypes = [P, c_int, c_i64, P, c_i64, c_i64, c_dbl, P, c_int, P]
         lib.tnsp_svd_mask_f64.argtypes = [P, c_int, P, P, c_i64, P, c_i64, P, c_i64, c_int, P]
         lib.tnsp_diag_scatter_f64.argtypes = [P, c_int, P, c_i64, P, c_i64, c_int, P]
@@ -149,6 +153,10 @@ class CudaBackend:
     def qr(self, plan, a, out1, out2):
         dev = self._sect(plan)
         nb = a.shape[0]
+        if self.sector_discovery and len(plan.sectors) == 1:
+            self._ck(self.lib.tnsp_qr_sectors_f64(dev.data_ptr(), plan.sectors.ctypes.data, a.data_ptr(), a.stride(0), out1.data_ptr(),
+                                                  out1.stride(0), out2.data_ptr(), out2.stride(0), int(plan.flag), nb, self._stream()))
+            return
         self._ck(self.lib.tnsp_qr_batched_f64(dev.data_ptr(), len(plan.sectors), plan.sectors.ctypes.data, a.data_ptr(), a.stride(0),
                                               out1.data_ptr(), out1.stride(0), out2.data_ptr(), out2.stride(0), int(plan.flag), nb,
                                               self._stream()))
@@ -158,6 +166,11 @@ class CudaBackend:
         nb = a.shape[0]
         wsize = int(self.lib.tnsp_svd_work_size(plan.sectors.ctypes.data, len(plan.sectors)))
         work = self.empty(nb, max(wsize, 1))
+        if self.sector_discovery and len(plan.sectors) == 1:
+            self._ck(self.lib.tnsp_svd_sectors_f64(dev.data_ptr(), plan.sectors.ctypes.data, a.data_ptr(), a.stride(0), out1.data_ptr(),
+                                                   out1.stride(0), s.data_ptr(), s.stride(0), out2.data_ptr(), out2.stride(0),
+                                                   work.data_ptr(), work.stride(0), nb, self._stream()))
+            return
         self._ck(self.lib.tnsp_svd_batched_f64(dev.data_ptr(), len(plan.sectors), plan.sectors.ctypes.data, a.data_ptr(), a.stride(0),
                                                out1.data_ptr(), out1.stride(0), s.data_ptr(), s.stride(0), out2.data_ptr(),
                                                out2.stride(0), work.data_ptr(), work.stride(0), nb, self._stream()))

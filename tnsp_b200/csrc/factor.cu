@@ -565,6 +565,13 @@ static int64_t svd_need(int64_t m, int64_t n) {
 
 using namespace tnsp;
 
+// factor_sector.cu: discovered-sector kernels for one large dense(-embedded) matrix per chain
+int tnsp_qr_sector_launch(const int64_t* sect, const int64_t* sh, const double* a, int64_t abs_, double* out1, int64_t o1bs,
+                          double* out2, int64_t o2bs, int use_qr, int nb, cudaStream_t st);
+int64_t tnsp_svd_sector_work(int64_t m, int64_t n);
+int tnsp_svd_sector_launch(const int64_t* sect, const int64_t* sh, const double* a, int64_t abs_, double* out1, int64_t o1bs,
+                           double* s, int64_t sbs, double* out2, int64_t o2bs, double* work, int64_t wbs, int nb, cudaStream_t st);
+
 extern "C" int tnsp_qr_batched_f64(const int64_t* sect, int ns, const int64_t* sh, double* a, int64_t abs_, double* out1, int64_t o1bs,
                                    double* out2, int64_t o2bs, int use_qr, int nb, void* stream) {
     if (ns == 0 || nb == 0) return 0;
@@ -594,6 +601,10 @@ extern "C" int tnsp_qr_batched_f64(const int64_t* sect, int ns, const int64_t* s
             sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb);
         return check_launch("tnsp_qr_batched_f64(warp)");
     }
+    if (ns == 1) {
+        const int rc = tnsp_qr_sector_launch(sect, sh, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
     const int gy = nb > 65535 ? 65535 : nb;
     qr_kernel<<<dim3(ns, gy), kFactorThreads, smem * 8, (cudaStream_t)stream>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb);
     return check_launch("tnsp_qr_batched_f64");
@@ -602,6 +613,10 @@ extern "C" int tnsp_qr_batched_f64(const int64_t* sect, int ns, const int64_t* s
 extern "C" int64_t tnsp_svd_work_size(const int64_t* sh, int ns) {
     int64_t total = 0;
     for (int i = 0; i < ns; ++i) total += svd_need(sh[i * TNSP_SECT_COLS], sh[i * TNSP_SECT_COLS + 1]);
+    if (ns == 1) {
+        const int64_t w = tnsp_svd_sector_work(sh[0], sh[1]);
+        if (w > total) total = w;
+    }
     return total;
 }
 
@@ -651,6 +666,10 @@ extern "C" int tnsp_svd_batched_f64(const int64_t* sect, int ns, const int64_t* 
         svd_warp_kernel<<<dim3(ns, (unsigned)gyw), 32 * kWarpsPerCta, kWarpsPerCta * kWarpDoubles * 8, st>>>(
             sect, a, abs_, out1, o1bs, s, sbs, out2, o2bs, nb);
         return check_launch("tnsp_svd_batched_f64(warp)");
+    }
+    if (ns == 1) {
+        const int rc = tnsp_svd_sector_launch(sect, sh, a, abs_, out1, o1bs, s, sbs, out2, o2bs, work, wbs, nb, st);
+        if (rc >= 0) return rc;
     }
     const int gy = nb > 65535 ? 65535 : nb;
     svd_kernel<<<dim3(ns, gy), kFactorThreads, smem * 8, st>>>(sect, a, abs_, out1, o1bs, s, sbs, out2, o2bs, work, wbs, d_off, nb);

@@ -1,0 +1,612 @@
+// K3s/K4s: QR/LQ and Jacobi SVD with ON-DEVICE SECTOR DISCOVERY for the lock-step batch engine.
+//
+// In the charge-dense embedding every chain of a batch stores a symmetric
+// tensor as a dense array with exact zeros outside its symmetry blocks; which rows / columns of the
+// merged matrix form a block differs from chain to chain (it follows the sampled physical charges),
+// so no host-side descriptor can name the blocks.  These kernels recover them from the zero pattern:
+//
+//   pass 1  one bit mask of the non-zero columns per row (ballot), kept in shared memory
+//   pass 2  union-find over the columns: all columns sharing a row are merged; the resulting connected
+//           components of the bipartite row/column graph are the reference's symmetry sectors
+//           (contract.hpp:539-580 / qr.hpp:419-429 / svd.hpp:405-427) -- blocks need not be full
+//           (triangular R factors and rank-deficient bonds leave staircase patterns inside a sector)
+//   per sector: gather the compact p x q block into shared memory, factorise it there (Householder
+//           QR as ?geqrf/?orgqr, qr.hpp:178-304; one-sided Jacobi as ?gesvd 'S','S', svd.hpp:104-211),
+//           scatter the factors back into the dense layout.
+//
+// One CTA owns one chain's matrix and walks its sectors; the new bond index of sector s is the
+// contiguous range [K_s, K_s + min(p_s, q_s)) (QR) or the global descending rank of the singular
+// value (SVD), so the first `cut` bond indices are the greedy cross-sector cut of svd.hpp:429-481.
+// Outputs must be zero-initialised by the caller (only sector blocks are written).
+//
+// Roofline: HBM; algorithmic bytes 8*(2mn + mk + kn) (QR), 8*(mn + mk + kn + k) (SVD) per chain.
+#include "common.cuh"
+
+namespace tnsp {
+
+constexpr int kSecThreads = 256;
+constexpr int kSecWarps = kSecThreads / 32;
+constexpr int kSecSmemDoubles = 25 * 1024;   // 200 KiB working set per CTA
+constexpr int kSecMaxDim = 8192;
+
+struct SecMap {
+    int* colkey;         // [n]
+    int* rowkey;         // [m]
+    uint16_t* colsec;    // [n] sector id or 0xFFFF
+    uint16_t* rowsec;    // [m]
+    uint16_t* collist;   // [n] columns grouped by sector, ascending inside a sector
+    uint16_t* rowlist;   // [m]
+    uint16_t* coltmp;    // [n]
+    int* cstart;         // [S+1]
+    int* rstart;         // [S+1]
+    int* kstart;         // [S+1] prefix of min(p_s, q_s)
+    int S;
+};
+
+__host__ __device__ inline int64_t secmap_bytes(int64_t m, int64_t n) {
+    const int64_t s = (m < n ? m : n) + 2;
+    int64_t b = 4 * (n + m) + 2 * 2 * (n + m) + 2 * n + 3 * 4 * s;
+    return (b + 15) / 16 * 16;
+}
+
+__device__ inline void secmap_carve(SecMap& sm, unsigned char* base, int m, int n) {
+    const int s = (m < n ? m : n) + 2;
+    int* ip = reinterpret_cast<int*>(base);
+    sm.colkey = ip; ip += n;
+    sm.rowkey = ip; ip += m;
+    sm.cstart = ip; ip += s;
+    sm.rstart = ip; ip += s;
+    sm.kstart = ip; ip += s;
+    uint16_t* hp = reinterpret_cast<uint16_t*>(ip);
+    sm.colsec = hp; hp += n;
+    sm.rowsec = hp; hp += m;
+    sm.collist = hp; hp += n;
+    sm.rowlist = hp; hp += m;
+    sm.coltmp = hp;
+}
+
+// Discover the sectors of the m x n row-major matrix A = connected components of the bipartite row/column
+// graph of its non-zeros.  The zero pattern is first condensed into one bit mask per row (shared memory,
+// `masks`, m x nw words; may alias the later working set), then a lock-free union-find over the COLUMNS
+// merges, row by row, all columns that share a row (hooking larger roots under smaller ones with atomicMin,
+// repeated until a pass changes nothing).  Sector order = ascending smallest column of the component.
+// All threads of the CTA call this; `mask_cap_words` is the room available for the masks.
+__device__ __forceinline__ int uf_find(const volatile int* parent, int x) {
+    int r = parent[x];
+    while (true) { const int q = parent[r]; if (q == r) break; r = q; }
+    return r;
+}
+
+__device__ void discover_sectors(SecMap& sm, const double* __restrict__ A, int m, int n, int* sh_flag, uint32_t* masks,
+                                 int64_t mask_cap_words) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = (n + 31) >> 5;
+    int* parent = sm.colkey;
+    if ((int64_t)m * nw > mask_cap_words) {
+        // no room for the masks: one dense sector holding every row and column
+        for (int j = tid; j < n; j += kSecThreads) { sm.colsec[j] = 0; sm.collist[j] = (uint16_t)j; }
+        for (int i = tid; i < m; i += kSecThreads) { sm.rowsec[i] = 0; sm.rowlist[i] = (uint16_t)i; }
+        if (tid == 0) {
+            sm.cstart[0] = 0; sm.cstart[1] = n; sm.rstart[0] = 0; sm.rstart[1] = m;
+            sm.kstart[0] = 0; sm.kstart[1] = m < n ? m : n;
+        }
+        sm.S = 1;
+        __syncthreads();
+        return;
+    }
+    for (int j = tid; j < n; j += kSecThreads) parent[j] = j;
+    // row masks (one warp per row, ballot per 32 columns) and the first non-zero column of every row
+    for (int i = warp; i < m; i += kSecWarps) {
+        const double* row = A + (int64_t)i * n;
+        int first = n;
+        for (int w = 0; w < nw; ++w) {
+            const int j = (w << 5) + lane;
+            const unsigned bal = __ballot_sync(0xffffffffu, j < n && row[j] != 0.0);
+            if (lane == 0) masks[(int64_t)i * nw + w] = bal;
+            if (bal && first == n) first = (w << 5) + __ffs(bal) - 1;
+        }
+        if (lane == 0) sm.rowkey[i] = first;
+    }
+    __syncthreads();
+    // union-find over columns
+    while (true) {
+        if (tid == 0) sh_flag[0] = 0;
+        __syncthreads();
+        int changed = 0;
+        for (int i = warp; i < m; i += kSecWarps) {
+            if (sm.rowkey[i] >= n) continue;
+            const uint32_t* mk = masks + (int64_t)i * nw;
+            int rmin = n;
+            for (int w = 0; w < nw; ++w)
+                if ((mk[w] >> lane) & 1u) rmin = min(rmin, uf_find(parent, (w << 5) + lane));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+            for (int w = 0; w < nw; ++w)
+                if ((mk[w] >> lane) & 1u) {
+                    const int r = uf_find(parent, (w << 5) + lane);
+                    if (r != rmin) { atomicMin(&parent[r], rmin); changed = 1; }
+                }
+        }
+        if (changed) sh_flag[0] = 1;
+        __syncthreads();
+        const int any = sh_flag[0];
+        __syncthreads();
+        if (!any) break;
+    }
+    // flatten by pointer jumping (monotone, safe under concurrent updates): parent[j] = root
+    while (true) {
+        int changed = 0;
+        for (int j = tid; j < n; j += kSecThreads) {
+            const int p1 = ((volatile int*)parent)[j];
+            const int p2 = ((volatile int*)parent)[p1];
+            if (p2 != p1) { parent[j] = p2; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    // flag the roots that own at least one row
+    for (int j = tid; j < n; j += kSecThreads) sm.colsec[j] = 0;
+    __syncthreads();
+    for (int i = tid; i < m; i += kSecThreads) {
+        const int f = sm.rowkey[i];
+        if (f < n) { const int r = parent[f]; sm.rowkey[i] = r; sm.colsec[r] = 1; } else sm.rowkey[i] = -1;
+    }
+    __syncthreads();
+    // sector id of root r = number of flagged roots below r (warp 0 scans the n flags) -> coltmp[r]
+    if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int j = base + lane;
+            const int f = (j < n) ? sm.colsec[j] : 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (j < n) sm.coltmp[j] = (uint16_t)(run + __popc(bal & ((1u << lane) - 1)));
+            run += __popc(bal);
+        }
+        if (lane == 0) sh_flag[1] = run;
+    }
+    __syncthreads();
+    const int S = sh_flag[1];
+    sm.S = S;
+    for (int i = tid; i < m; i += kSecThreads) sm.rowsec[i] = (sm.rowkey[i] >= 0) ? sm.coltmp[sm.rowkey[i]] : (uint16_t)0xFFFF;
+    // all-zero columns are their own, unflagged, roots
+    for (int j = tid; j < n; j += kSecThreads) { const int r = parent[j]; sm.collist[j] = sm.colsec[r] ? sm.coltmp[r] : (uint16_t)0xFFFF; }
+    __syncthreads();
+    for (int j = tid; j < n; j += kSecThreads) sm.colsec[j] = sm.collist[j];
+    for (int s = tid; s <= S; s += kSecThreads) { sm.cstart[s] = 0; sm.rstart[s] = 0; }
+    __syncthreads();
+    // counts (integer atomics: deterministic result)
+    for (int j = tid; j < n; j += kSecThreads) if (sm.colsec[j] != 0xFFFF) atomicAdd(&sm.cstart[sm.colsec[j] + 1], 1);
+    for (int i = tid; i < m; i += kSecThreads) if (sm.rowsec[i] != 0xFFFF) atomicAdd(&sm.rstart[sm.rowsec[i] + 1], 1);
+    __syncthreads();
+    if (tid == 0) {
+        sm.kstart[0] = 0;
+        for (int s = 0; s < S; ++s) {
+            const int c = sm.cstart[s + 1], r = sm.rstart[s + 1];
+            sm.kstart[s + 1] = sm.kstart[s] + (c < r ? c : r);
+            sm.cstart[s + 1] += sm.cstart[s];
+            sm.rstart[s + 1] += sm.rstart[s];
+        }
+    }
+    __syncthreads();
+    // stable compaction: warp w fills the lists of sectors w, w + 8, ...
+    for (int s = warp; s < S; s += kSecWarps) {
+        int run = sm.cstart[s];
+        for (int base = 0; base < n; base += 32) {
+            const int j = base + lane;
+            const int f = (j < n) && (sm.colsec[j] == s);
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (f) sm.collist[run + __popc(bal & ((1u << lane) - 1))] = (uint16_t)j;
+            run += __popc(bal);
+        }
+        run = sm.rstart[s];
+        for (int base = 0; base < m; base += 32) {
+            const int i = base + lane;
+            const int f = (i < m) && (sm.rowsec[i] == s);
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (f) sm.rowlist[run + __popc(bal & ((1u << lane) - 1))] = (uint16_t)i;
+            run += __popc(bal);
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Householder QR of the compact p x q matrix W (row stride ld, unit column stride), k = min(p, q):
+// on exit W(:, 0:k) holds the explicit Q and Rout (k x q, row stride q) the upper-trapezoidal R.
+// One warp per trailing column, lanes over rows.  LAPACK dlarfg / dorg2r conventions.
+// ------------------------------------------------------------------------------------------------
+__device__ void householder_qr(double* W, int ld, int p, int q, int k, double* tau, double* Rout, double* red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double sh_tau, sh_scale;
+    for (int j = 0; j < k; ++j) {
+        double part = 0.0;
+        for (int i = j + 1 + tid; i < p; i += kSecThreads) { const double v = W[(int64_t)i * ld + j]; part += v * v; }
+        const double xnorm2 = block_sum(part, red);
+        if (tid == 0) {
+            const double alpha = W[(int64_t)j * ld + j];
+            double tj = 0.0, scale = 0.0, beta = alpha;
+            if (xnorm2 != 0.0) {
+                beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+                tj = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            sh_tau = tj; sh_scale = scale;
+            tau[j] = tj;
+            W[(int64_t)j * ld + j] = beta;
+        }
+        __syncthreads();
+        const double tj = sh_tau, scale = sh_scale;
+        if (tj != 0.0) {
+            for (int i = j + 1 + tid; i < p; i += kSecThreads) W[(int64_t)i * ld + j] *= scale;
+            __syncthreads();
+            for (int c = j + 1 + warp; c < q; c += kSecWarps) {
+                double w = 0.0;
+                for (int i = j + 1 + lane; i < p; i += 32) w += W[(int64_t)i * ld + j] * W[(int64_t)i * ld + c];
+                w = (warp_sum(w) + W[(int64_t)j * ld + c]) * tj;
+                for (int i = j + 1 + lane; i < p; i += 32) W[(int64_t)i * ld + c] -= w * W[(int64_t)i * ld + j];
+                __syncwarp();
+                if (lane == 0) W[(int64_t)j * ld + c] -= w;
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < k * q; e += kSecThreads) {
+        const int i = e / q, j = e - i * q;
+        Rout[e] = (j >= i) ? W[(int64_t)i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    for (int j = k - 1; j >= 0; --j) {
+        const double tj = tau[j];
+        for (int c = j + 1 + warp; c < k; c += kSecWarps) {
+            double w = 0.0;
+            for (int i = j + 1 + lane; i < p; i += 32) w += W[(int64_t)i * ld + j] * W[(int64_t)i * ld + c];
+            w = (warp_sum(w) + W[(int64_t)j * ld + c]) * tj;
+            for (int i = j + 1 + lane; i < p; i += 32) W[(int64_t)i * ld + c] -= w * W[(int64_t)i * ld + j];
+            __syncwarp();
+            if (lane == 0) W[(int64_t)j * ld + c] -= w;
+        }
+        __syncthreads();
+        for (int i = j + 1 + tid; i < p; i += kSecThreads) W[(int64_t)i * ld + j] *= -tj;
+        for (int i = tid; i < j; i += kSecThreads) W[(int64_t)i * ld + j] = 0.0;
+        if (tid == 0) W[(int64_t)j * ld + j] = 1.0 - tj;
+        __syncthreads();
+    }
+}
+
+// sect[8] = (m, n, k, a_off, out1_off, out2_off, -, -)
+__global__ void __launch_bounds__(kSecThreads) qr_sector_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a, int64_t abs_,
+                                                                double* __restrict__ out1, int64_t o1bs, double* __restrict__ out2,
+                                                                int64_t o2bs, int use_qr, int nb, double* __restrict__ scratch,
+                                                                int64_t scratch_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ int sh_flag[2];
+    const int m = (int)sect[0], n = (int)sect[1], k = (int)sect[2];
+    const int tid = threadIdx.x;
+    SecMap sm;
+    secmap_carve(sm, smem_raw, m, n);
+    double* work = reinterpret_cast<double*>(smem_raw + secmap_bytes(m, n));
+    const int64_t cap = kSecSmemDoubles - secmap_bytes(m, n) / 8;
+    double* gscratch = scratch + (int64_t)blockIdx.x * scratch_per_cta;
+
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const double* A = a + (int64_t)b * abs_ + sect[3];
+        double* O1 = out1 + (int64_t)b * o1bs + sect[4];   // m x k
+        double* O2 = out2 + (int64_t)b * o2bs + sect[5];   // k x n
+        discover_sectors(sm, A, m, n, sh_flag, reinterpret_cast<uint32_t*>(work), cap * 2);
+        const int S = sm.S;
+        for (int s = 0; s < S; ++s) {
+            const int r0 = sm.rstart[s], c0 = sm.cstart[s];
+            const int ms = sm.rstart[s + 1] - r0, ns = sm.cstart[s + 1] - c0;
+            if (ms == 0 || ns == 0) continue;
+            const int p = use_qr ? ms : ns, q = use_qr ? ns : ms;
+            const int ks = p < q ? p : q;
+            const int K0 = sm.kstart[s];
+            const int ld = q | 1;
+            const int64_t need = (int64_t)p * ld + ks + (int64_t)ks * q;
+            double* base = (need <= cap) ? work : gscratch;
+            double* W = base;
+            double* tau = W + (int64_t)p * ld;
+            double* Rc = tau + ks;
+            // gather X: use_qr X = M_s ; else X = M_s^T
+            if (use_qr) {
+                for (int e = tid; e < ms * ns; e += kSecThreads) {
+                    const int r = e / ns, c = e - r * ns;
+                    W[(int64_t)r * ld + c] = A[(int64_t)sm.rowlist[r0 + r] * n + sm.collist[c0 + c]];
+                }
+            } else {
+                for (int e = tid; e < ms * ns; e += kSecThreads) {
+                    const int r = e / ns, c = e - r * ns;
+                    W[(int64_t)c * ld + r] = A[(int64_t)sm.rowlist[r0 + r] * n + sm.collist[c0 + c]];
+                }
+            }
+            __syncthreads();
+            householder_qr(W, ld, p, q, ks, tau, Rc, red);
+            if (use_qr) {
+                // Q (m x k): rows of the sector, bond K0..K0+ks ; R (k x n): columns of the sector
+                for (int e = tid; e < ms * ks; e += kSecThreads) {
+                    const int r = e / ks, t = e - r * ks;
+                    O1[(int64_t)sm.rowlist[r0 + r] * k + K0 + t] = W[(int64_t)r * ld + t];
+                }
+                for (int e = tid; e < ks * ns; e += kSecThreads) {
+                    const int t = e / ns, c = e - t * ns;
+                    O2[(int64_t)(K0 + t) * n + sm.collist[c0 + c]] = Rc[(int64_t)t * q + c];
+                }
+            } else {
+                // M = L Q : L (m x k) = R^T, Q (k x n) = Qx^T ; here p = ns, q = ms
+                for (int e = tid; e < ms * ks; e += kSecThreads) {
+                    const int r = e / ks, t = e - r * ks;
+                    O1[(int64_t)sm.rowlist[r0 + r] * k + K0 + t] = Rc[(int64_t)t * q + r];
+                }
+                for (int e = tid; e < ks * ns; e += kSecThreads) {
+                    const int t = e / ns, c = e - t * ns;
+                    O2[(int64_t)(K0 + t) * n + sm.collist[c0 + c]] = W[(int64_t)c * ld + t];
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-sided Jacobi SVD of a compact sector.  X (p x q, p >= q) is held column-wise: G[c*ldp + r];
+// V[c*ldq + t] accumulates the rotations.  Pairs of a round-robin round are distributed over
+// sub-warp groups of `gs` lanes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gsum(double v, int gs) {
+    for (int o = gs >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ void jacobi_svd(double* G, int ldp, double* V, int ldq, int p, int q, int* sh_rot) {
+    const int tid = threadIdx.x;
+    int gs = 32;
+    while (gs > 4 && (gs >> 1) >= p) gs >>= 1;
+    if (q > 2 * (kSecThreads / gs) && gs > 8) gs = 8;   // more pairs in flight for wide sectors
+    const int groups = kSecThreads / gs, grp = tid / gs, gl = tid % gs;
+    const int qe = q + (q & 1), npairs = qe / 2;
+    const double tol = fmax(1e-15, sqrt((double)p) * 2.3e-16);
+    for (int e = tid; e < q * q; e += kSecThreads) V[(e / q) * ldq + (e % q)] = ((e / q) == (e % q)) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int sweep = 0; sweep < 60 && q > 1; ++sweep) {
+        if (tid == 0) *sh_rot = 0;
+        __syncthreads();
+        for (int round = 0; round < qe - 1; ++round) {
+            for (int base = 0; base < npairs; base += groups) {
+                const int pr = base + grp;
+                int i = 0, j = 0;
+                bool valid = pr < npairs;
+                if (valid) {
+                    if (pr == 0) { i = qe - 1; j = round; }
+                    else { i = (round + pr) % (qe - 1); j = (round - pr + (qe - 1)) % (qe - 1); }
+                    valid = i < q && j < q;
+                    if (i > j) { const int t = i; i = j; j = t; }
+                }
+                double* gi = G + (int64_t)i * ldp;
+                double* gj = G + (int64_t)j * ldp;
+                double aa = 0.0, bb = 0.0, cc = 0.0;
+                if (valid)
+                    for (int r = gl; r < p; r += gs) { const double x = gi[r], y = gj[r]; aa += x * x; bb += y * y; cc += x * y; }
+                aa = gsum(aa, gs); bb = gsum(bb, gs); cc = gsum(cc, gs);
+                if (valid && fabs(cc) > tol * sqrt(aa * bb) && aa * bb > 0.0) {
+                    const double zeta = (bb - aa) / (2.0 * cc);
+                    const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+                    for (int r = gl; r < p; r += gs) { const double x = gi[r], y = gj[r]; gi[r] = cs * x - sn * y; gj[r] = sn * x + cs * y; }
+                    double* vi = V + (int64_t)i * ldq;
+                    double* vj = V + (int64_t)j * ldq;
+                    for (int r = gl; r < q; r += gs) { const double x = vi[r], y = vj[r]; vi[r] = cs * x - sn * y; vj[r] = sn * x + cs * y; }
+                    if (gl == 0) *sh_rot = 1;
+                }
+            }
+            __syncthreads();
+        }
+        const int any = *sh_rot;
+        __syncthreads();
+        if (!any) break;
+    }
+}
+
+__host__ __device__ inline int64_t svd_sector_work(int64_t m, int64_t n) {
+    const int64_t k = m < n ? m : n, p = m < n ? n : m;
+    // sigma(k) + sector tags(k) + staged U (m*k) + staged Vt (k*n) + one over-sized sector (p*(k|1) + k*(k|1) + k)
+    return 2 * k + m * k + k * n + p * (k | 1) + k * (k | 1) + k + 8;
+}
+
+// sect[8] = (m, n, k, a_off, out1_off, out2_off, s_off, -)
+__global__ void __launch_bounds__(kSecThreads) svd_sector_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a, int64_t abs_,
+                                                                 double* __restrict__ out1, int64_t o1bs, double* __restrict__ sv,
+                                                                 int64_t sbs, double* __restrict__ out2, int64_t o2bs,
+                                                                 double* __restrict__ workg, int64_t wbs, int nb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int sh_flag[2];
+    __shared__ int sh_rot;
+    const int m = (int)sect[0], n = (int)sect[1], k = (int)sect[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    SecMap sm;
+    secmap_carve(sm, smem_raw, m, n);
+    double* work = reinterpret_cast<double*>(smem_raw + secmap_bytes(m, n));
+    const int64_t cap = kSecSmemDoubles - secmap_bytes(m, n) / 8;
+
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const double* A = a + (int64_t)b * abs_ + sect[3];
+        double* O1 = out1 + (int64_t)b * o1bs + sect[4];   // U  m x k
+        double* O2 = out2 + (int64_t)b * o2bs + sect[5];   // Vt k x n
+        double* Sg = sv + (int64_t)b * sbs + sect[6];
+        double* wg = workg + (int64_t)b * wbs;
+        double* sig_all = wg;                  // [k] singular values in staging order
+        double* Ust = wg + 2 * k;              // staged U blocks, sector s at ms*? offsets (below)
+        double* Vst = Ust + (int64_t)m * k;
+        double* big = Vst + (int64_t)k * n;
+        discover_sectors(sm, A, m, n, sh_flag, reinterpret_cast<uint32_t*>(work), cap * 2);
+        const int S = sm.S;
+        const int ktot = sm.kstart[S];
+        // staged layout: U_s (ms x ks) at Ust + rstart[s]*k... use simple running offsets
+        int64_t uoff = 0, voff = 0;
+        for (int s = 0; s < S; ++s) {
+            const int r0 = sm.rstart[s], c0 = sm.cstart[s];
+            const int ms = sm.rstart[s + 1] - r0, ns = sm.cstart[s + 1] - c0;
+            if (ms == 0 || ns == 0) continue;
+            const bool tall = ms >= ns;
+            const int p = tall ? ms : ns, q = tall ? ns : ms;   // q = ks
+            const int K0 = sm.kstart[s];
+            const int ldp = p | 1, ldq = q | 1;
+            const int64_t need = (int64_t)q * ldp + (int64_t)q * ldq + q;
+            double* base = (need <= cap) ? work : big;
+            double* G = base;
+            double* V = G + (int64_t)q * ldp;
+            double* sig = V + (int64_t)q * ldq;
+            // gather: column c of X.  tall: X = M_s (columns of M_s); wide: X = M_s^T (rows of M_s)
+            for (int e = tid; e < ms * ns; e += kSecThreads) {
+                const int r = e / ns, c = e - r * ns;
+                const double v = A[(int64_t)sm.rowlist[r0 + r] * n + sm.collist[c0 + c]];
+                if (tall) G[(int64_t)c * ldp + r] = v; else G[(int64_t)r * ldp + c] = v;
+            }
+            __syncthreads();
+            jacobi_svd(G, ldp, V, ldq, p, q, &sh_rot);
+            for (int c = warp; c < q; c += kSecWarps) {
+                double s2 = 0.0;
+                for (int r = lane; r < p; r += 32) s2 += G[(int64_t)c * ldp + r] * G[(int64_t)c * ldp + r];
+                s2 = warp_sum(s2);
+                if (lane == 0) { sig[c] = sqrt(s2); sig_all[K0 + c] = sqrt(s2); }
+            }
+            __syncthreads();
+            // stage: U_s (ms x q) row-major at Ust+uoff, Vt_s (q x ns) row-major at Vst+voff
+            double* Us = Ust + uoff;
+            double* Vs = Vst + voff;
+            if (tall) {
+                for (int e = tid; e < ms * q; e += kSecThreads) {
+                    const int r = e / q, c = e - r * q;
+                    const double sg = sig[c];
+                    Us[e] = sg > 0.0 ? G[(int64_t)c * ldp + r] / sg : 0.0;
+                }
+                for (int e = tid; e < q * ns; e += kSecThreads) {
+                    const int c = e / ns, t = e - c * ns;
+                    Vs[e] = V[(int64_t)c * ldq + t];
+                }
+            } else {
+                for (int e = tid; e < ms * q; e += kSecThreads) {
+                    const int t = e / q, c = e - t * q;
+                    Us[e] = V[(int64_t)c * ldq + t];
+                }
+                for (int e = tid; e < q * ns; e += kSecThreads) {
+                    const int c = e / ns, r = e - c * ns;
+                    const double sg = sig[c];
+                    Vs[e] = sg > 0.0 ? G[(int64_t)c * ldp + r] / sg : 0.0;
+                }
+            }
+            uoff += (int64_t)ms * q;
+            voff += (int64_t)q * ns;
+            __syncthreads();
+        }
+        __threadfence_block();
+        __syncthreads();
+        // global descending rank of every staged singular value (ties: staging order, i.e. sector order
+        // then position, as the greedy cut of svd.hpp:455-461 resolves them)
+        uoff = 0; voff = 0;
+        for (int s = 0; s < S; ++s) {
+            const int r0 = sm.rstart[s], c0 = sm.cstart[s];
+            const int ms = sm.rstart[s + 1] - r0, ns = sm.cstart[s + 1] - c0;
+            if (ms == 0 || ns == 0) continue;
+            const int q = ms < ns ? ms : ns;
+            const int K0 = sm.kstart[s];
+            const double* Us = Ust + uoff;
+            const double* Vs = Vst + voff;
+            // ranks of this sector's values into shared scratch (reuse `work` head as int array)
+            int* rk = reinterpret_cast<int*>(work);
+            for (int c = tid; c < q; c += kSecThreads) {
+                const double v = sig_all[K0 + c];
+                int r = 0;
+                for (int o = 0; o < ktot; ++o) { const double w = sig_all[o]; r += (w > v) || (w == v && o < K0 + c); }
+                rk[c] = r;
+                Sg[r] = v;
+            }
+            __syncthreads();
+            for (int e = tid; e < ms * q; e += kSecThreads) {
+                const int r = e / q, c = e - r * q;
+                O1[(int64_t)sm.rowlist[r0 + r] * k + rk[c]] = Us[e];
+            }
+            for (int e = tid; e < q * ns; e += kSecThreads) {
+                const int c = e / ns, t = e - c * ns;
+                O2[(int64_t)rk[c] * n + sm.collist[c0 + t]] = Vs[e];
+            }
+            uoff += (int64_t)ms * q;
+            voff += (int64_t)q * ns;
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
+
+static double* g_qr_scratch = nullptr;
+static int64_t g_qr_scratch_cap = 0;
+
+}  // namespace tnsp
+
+using namespace tnsp;
+
+// Launchers shared by tnsp_qr_batched_f64 / tnsp_svd_batched_f64 (factor.cu: a single LARGE descriptor) and by
+// tnsp_qr_sectors_f64 / tnsp_svd_sectors_f64 below (any size).  Return -1 if the shape is not handled here.
+int tnsp_qr_sector_launch(const int64_t* sect, const int64_t* sh, const double* a, int64_t abs_, double* out1, int64_t o1bs,
+                          double* out2, int64_t o2bs, int use_qr, int nb, cudaStream_t st) {
+    const int64_t m = sh[0], n = sh[1];
+    if (m > kSecMaxDim || n > kSecMaxDim) return -1;
+    if (secmap_bytes(m, n) / 8 + 4096 > kSecSmemDoubles) return -1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(qr_sector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecSmemDoubles * 8);
+        attr_set = true;
+    }
+    int grid = nb < 2 * kSMs ? nb : 2 * kSMs;
+    const int64_t p = use_qr ? m : n, q = use_qr ? n : m, k = p < q ? p : q;
+    const int64_t per_cta = p * (q | 1) + k + k * q + 8;
+    const int64_t need = per_cta * grid;
+    if (need > g_qr_scratch_cap) {
+        if (g_qr_scratch) cudaFree(g_qr_scratch);
+        g_qr_scratch_cap = need;
+        if (cudaMalloc(&g_qr_scratch, sizeof(double) * need) != cudaSuccess) {
+            g_qr_scratch = nullptr; g_qr_scratch_cap = 0;
+            set_error("tnsp_qr_batched_f64(sector): cudaMalloc of the spill scratch failed");
+            return 1;
+        }
+    }
+    qr_sector_kernel<<<grid, kSecThreads, kSecSmemDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb, g_qr_scratch, per_cta);
+    return check_launch("tnsp_qr_batched_f64(sector)");
+}
+
+int64_t tnsp_svd_sector_work(int64_t m, int64_t n) { return svd_sector_work(m, n); }
+
+int tnsp_svd_sector_launch(const int64_t* sect, const int64_t* sh, const double* a, int64_t abs_, double* out1, int64_t o1bs,
+                           double* s, int64_t sbs, double* out2, int64_t o2bs, double* work, int64_t wbs, int nb, cudaStream_t st) {
+    const int64_t m = sh[0], n = sh[1];
+    if (m > kSecMaxDim || n > kSecMaxDim) return -1;
+    if (secmap_bytes(m, n) / 8 + 4096 > kSecSmemDoubles) return -1;
+    if (work == nullptr || wbs < svd_sector_work(m, n)) { set_error("tnsp_svd_batched_f64(sector): scratch too small"); return 1; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(svd_sector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecSmemDoubles * 8);
+        attr_set = true;
+    }
+    const int grid = nb < 2 * kSMs ? nb : 2 * kSMs;
+    svd_sector_kernel<<<grid, kSecThreads, kSecSmemDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, s, sbs, out2, o2bs, work, wbs, nb);
+    return check_launch("tnsp_svd_batched_f64(sector)");
+}
+
+// C-ABI: factorisation of ONE dense(-embedded) matrix per chain with the symmetry sectors discovered on the
+// device (see the header of this file).  Same arguments as tnsp_qr_batched_f64 / tnsp_svd_batched_f64 with ns == 1.
+extern "C" int tnsp_qr_sectors_f64(const int64_t* sect, const int64_t* sect_host, double* a, int64_t abs_, double* out1, int64_t o1bs,
+                                   double* out2, int64_t o2bs, int use_qr, int nb, void* stream) {
+    if (nb == 0 || sect_host[0] * sect_host[1] == 0) return 0;
+    const int rc = tnsp_qr_sector_launch(sect, sect_host, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb, (cudaStream_t)stream);
+    if (rc < 0) { set_error("tnsp_qr_sectors_f64: matrix too large for the discovered-sector kernel"); return 1; }
+    return rc;
+}
+
+extern "C" int tnsp_svd_sectors_f64(const int64_t* sect, const int64_t* sect_host, const double* a, int64_t abs_, double* out1,
+                                    int64_t o1bs, double* s, int64_t sbs, double* out2, int64_t o2bs, double* work, int64_t wbs,
+                                    int nb, void* stream) {
+    if (nb == 0 || sect_host[0] * sect_host[1] == 0) return 0;
+    const int rc = tnsp_svd_sector_launch(sect, sect_host, a, abs_, out1, o1bs, s, sbs, out2, o2bs, work, wbs, nb, (cudaStream_t)stream);
+    if (rc < 0) { set_error("tnsp_svd_sectors_f64: matrix too large for the discovered-sector kernel"); return 1; }
+    return rc;
+}

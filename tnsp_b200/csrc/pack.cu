@@ -180,7 +180,9 @@ __global__ void grad_partial_kernel(const double* __restrict__ holes, int64_t hb
     const int b0 = blockIdx.y * chunk, b1 = min(nb, b0 + chunk);
     double d = 0.0, ed = 0.0;
     for (int b = b0; b < b1; ++b) {
-        const double h = holes[(int64_t)b * hbs + i] * weight[b];
+        const double w = weight[b];
+        if (w == 0.0) continue;   // dead chain (zero amplitude): its hole is 0/0
+        const double h = holes[(int64_t)b * hbs + i] * w;
         d += h;
         ed += h * energy[b];
     }

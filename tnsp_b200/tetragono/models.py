@@ -49,3 +49,74 @@ def neel_configuration(L1, L2):
 def random_sampling_lattice(abstract, seed=2333):
     TAT.random.seed(seed)
     return SamplingLattice(abstract)
+
+
+# ---------------------------------------------------------------------------------------------------
+# generic (TAT-module independent) builders: the same functions build the model on this repository's
+# device tensors and on the reference's PyTAT classes (reference arm of bench.py, golden generator)
+# ---------------------------------------------------------------------------------------------------
+def _is_u1(Tensor):
+    return Tensor.model.__name__.rsplit(".", 1)[-1] in ("BoseU1", "U1")
+
+
+def spin_half_SS_of(Tensor):
+    """S.S for `Tensor`'s symmetry: NoSymmetry (dim-2 edges) or BoseU1 with physical edge
+    [(+1,1),(-1,1)] (charge = 2 Sz); same matrix elements, same basis order (up, down)."""
+    arr = spin_half_SS_array()
+    if not _is_u1(Tensor):
+        t = Tensor(["I0", "I1", "O0", "O1"], [2, 2, 2, 2]).zero_()
+        t.storage = arr.reshape(-1)
+        return t
+    pe, cpe = [(+1, 1), (-1, 1)], [(-1, 1), (+1, 1)]
+    t = Tensor(["I0", "I1", "O0", "O1"], [cpe, cpe, pe, pe]).zero_()
+    q = (+1, -1)
+    for i0 in range(2):
+        for i1 in range(2):
+            for o0 in range(2):
+                for o1 in range(2):
+                    if arr[i0, i1, o0, o1] != 0:
+                        t[{"I0": (-q[i0], 0), "I1": (-q[i1], 0), "O0": (q[o0], 0), "O1": (q[o1], 0)}] = arr[i0, i1, o0, o1]
+    return t
+
+
+def j1j2_abstract_lattice(Tensor, L1, L2, D, J1=1.0, J2=0.5, state_classes=None):
+    """J1-J2 Heisenberg model on the square lattice (cfg2; reference model tetraku/models/J1J2/__init__.py:22-68,
+    which ships NoSymmetry only -- the BoseU1 variant follows SURVEY.md 8d: physical edge [(+1,1),(-1,1)],
+    virtual edges [(-1,d),(0,d),(+1,d)] with D = 3 d, total symmetry 0).
+    Returns (abstract lattice, sweep hopping hamiltonians = nearest-neighbour terms only, because the
+    sweep-order builder rejects diagonal terms, sampling.py:156-190)."""
+    AS, AL = state_classes if state_classes is not None else (AbstractState, AbstractLattice)
+    u1 = _is_u1(Tensor)
+    state = AS(Tensor, L1, L2)
+    state.physics_edges[...] = [(+1, 1), (-1, 1)] if u1 else 2
+    SS = spin_half_SS_of(Tensor)
+    H1, H2 = SS * (-J1), SS * (-J2)
+    state.hamiltonians["vertical_bond"] = H1
+    state.hamiltonians["horizontal_bond"] = H1
+    if J2 != 0:
+        for l1 in range(L1 - 1):
+            for l2 in range(L2 - 1):
+                state.hamiltonians[(l1, l2, 0), (l1 + 1, l2 + 1, 0)] = H2
+                state.hamiltonians[(l1, l2 + 1, 0), (l1 + 1, l2, 0)] = H2
+    lat = AL(state)
+    if u1:
+        if D % 3:
+            raise ValueError("U(1) J1-J2 lattice: D must be a multiple of 3 (segments -1, 0, +1)")
+        ve = [(-1, D // 3), (0, D // 3), (+1, D // 3)]
+    else:
+        ve = D
+    lat.virtual_bond["R"] = ve
+    lat.virtual_bond["D"] = ve
+    return lat
+
+
+def nearest_neighbour_terms(lattice):
+    return {k: v for k, v in lattice._hamiltonians.items() if len(k) == 1 or k[0][0] == k[1][0] or k[0][1] == k[1][1]}
+
+
+def neel_points(lattice):
+    """Neel configuration as edge points [l1][l2] -> {orbit: (symmetry, index)} for No / BoseU1 spin-1/2 lattices"""
+    S = lattice.Tensor.model.Symmetry
+    if _is_u1(lattice.Tensor):
+        return [[{0: (S(+1) if (l1 + l2) % 2 == 0 else S(-1), 0)} for l2 in range(lattice.L2)] for l1 in range(lattice.L1)]
+    return [[{0: (S(), (l1 + l2) % 2)} for l2 in range(lattice.L2)] for l1 in range(lattice.L1)]

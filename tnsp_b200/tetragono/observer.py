@@ -295,6 +295,8 @@ class Observer:
 
     def natural_gradient_by_conjugate_gradient(self, step, error):
         """SR natural gradient, matrix free (observer.py:576-675): solve (D~^T D~) x = D~^T E~, return 2x."""
+        if not is_native(self.owner.Tensor):
+            return self._natural_gradient_host(step, error)
         import torch
         B = _bk.get()
         energy = self._total_energy_value()
@@ -339,6 +341,53 @@ class Observer:
         x = 2 * x
         out = self._array_to_delta(x)
         return [[t.conjugate(True) for t in row] for row in out]
+
+    def _natural_gradient_host(self, step, error):
+        """the same CG on host arrays, for PyTAT-compatible tensor classes other than this repository's
+        (used to time the reference's CPU path through the public PyTAT API only)"""
+        owner = self.owner
+        energy = self._total_energy_value()
+        delta = np.concatenate([np.array(self._Delta[l1][l2].storage, dtype=np.float64) for l1, l2 in owner.sites()]) / self._total_weight
+        w = np.concatenate([d[0] for d in self._Deltas])
+        es = np.concatenate([d[1] for d in self._Deltas])
+        rows = np.concatenate([np.asarray(d[2]) for d in self._Deltas], axis=0)
+        self._Deltas = None
+        param = np.sqrt(w / self._total_weight)
+        Delta = (rows - delta.reshape(1, -1)) * param.reshape(-1, 1)
+        Energy = (es - energy) * param
+
+        def DT(v):
+            return _dist.allreduce_host(Delta.T @ v)
+
+        b = DT(Energy)
+        b_square = float(b @ b)
+        x = np.zeros_like(b)
+        r = b.copy()
+        p = r
+        r_square = float(r @ r)
+        t = 0
+        while t != step:
+            if error != 0.0 and b_square != 0 and error**2 > r_square / b_square:
+                break
+            Dp = Delta @ p
+            alpha = r_square / _dist.allreduce_number(float(Dp @ Dp))
+            x = x + alpha * p
+            r = r - alpha * DT(Dp)
+            new_r_square = float(r @ r)
+            beta = new_r_square / r_square
+            r_square = new_r_square
+            p = r + beta * p
+            t += 1
+        x = 2 * x
+        out = [[None] * owner.L2 for _ in range(owner.L1)]
+        index = 0
+        for l1, l2 in owner.sites():
+            t_ = self._Delta[l1][l2].same_shape()
+            size = len(np.array(self._Delta[l1][l2].storage))
+            t_.storage = x[index:index + size]
+            index += size
+            out[l1][l2] = t_.conjugate(True)
+        return out
 
     def normalize_lattice(self):
         """rescale every site tensor by exp(<log|ws|>/(L1 L2)) (observer.py:909-920)"""
