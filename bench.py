@@ -298,7 +298,7 @@ def run_own(args):
     e2e_value = nb * n_e2e * world / (float(t.item()) * 1e-3)
 
     # ---- roofline of the dominant kernel (instrumented pass, outside the timed regions) -----------
-    roofline, breakdown = None, None
+    roofline, breakdown, top_shapes = None, None, None
     if rank == 0:
         from tnsp_b200 import profiling
         prof = profiling.KernelTimer(B)
@@ -311,6 +311,7 @@ def run_own(args):
         torch.cuda.synchronize()
         prof.disable()
         breakdown = prof.summary()
+        top_shapes = prof.shape_summary()
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -330,7 +331,7 @@ def run_own(args):
                        "l2": "working set of a step (all chains' environments) exceeds L2; no flush"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clock_info, "energy_per_site": energy[0],
-            "roofline": roofline, "kernel_breakdown": breakdown,
+            "roofline": roofline, "kernel_breakdown": breakdown, "top_shapes": top_shapes,
         }
     return out
 

@@ -39,7 +39,8 @@ def test_pack_bit_exact(nb):
     assert np.array_equal(cu.to_numpy(d_cu), d_ck.numpy())
 
 
-@pytest.mark.parametrize("shape", [(5, 7, 3), (16, 16, 16), (64, 16, 4), (33, 65, 17), (130, 70, 200), (300, 257, 129)])
+@pytest.mark.parametrize("shape", [(5, 7, 3), (16, 16, 16), (64, 16, 4), (33, 65, 17), (130, 70, 200), (300, 257, 129), (1, 1, 46656), (2, 3, 5000),
+                                   (40, 1, 9000), (700, 1, 40), (1, 300, 64)])
 @pytest.mark.parametrize("flags", [0, 1, 2, 3])
 def test_grouped_gemm(shape, flags):
     cu, ck = _both()

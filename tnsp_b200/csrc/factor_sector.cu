@@ -28,6 +28,7 @@ constexpr int kSecThreads = 256;
 constexpr int kSecWarps = kSecThreads / 32;
 constexpr int kSecSmemDoubles = 25 * 1024;   // 200 KiB working set per CTA
 constexpr int kSecMaxDim = 8192;
+constexpr int kWarpSectorMax = 40;   // sectors up to this many columns are diagonalised by one warp each, concurrently
 
 struct SecMap {
     int* colkey;         // [n]
@@ -40,12 +41,13 @@ struct SecMap {
     int* cstart;         // [S+1]
     int* rstart;         // [S+1]
     int* kstart;         // [S+1] prefix of min(p_s, q_s)
+    int* repkey;         // [n] representative row of every first-non-zero column (discovery only)
     int S;
 };
 
 __host__ __device__ inline int64_t secmap_bytes(int64_t m, int64_t n) {
     const int64_t s = (m < n ? m : n) + 2;
-    int64_t b = 4 * (n + m) + 2 * 2 * (n + m) + 2 * n + 3 * 4 * s;
+    int64_t b = 4 * (2 * n + m) + 2 * 2 * (n + m) + 2 * n + 3 * 4 * s;
     return (b + 15) / 16 * 16;
 }
 
@@ -57,6 +59,7 @@ __device__ inline void secmap_carve(SecMap& sm, unsigned char* base, int m, int 
     sm.cstart = ip; ip += s;
     sm.rstart = ip; ip += s;
     sm.kstart = ip; ip += s;
+    sm.repkey = ip; ip += n;
     uint16_t* hp = reinterpret_cast<uint16_t*>(ip);
     sm.colsec = hp; hp += n;
     sm.rowsec = hp; hp += m;
@@ -94,27 +97,60 @@ __device__ void discover_sectors(SecMap& sm, const double* __restrict__ A, int m
         __syncthreads();
         return;
     }
-    for (int j = tid; j < n; j += kSecThreads) parent[j] = j;
-    // row masks (one warp per row, ballot per 32 columns) and the first non-zero column of every row
+    for (int j = tid; j < n; j += kSecThreads) { parent[j] = j; sm.repkey[j] = 0; }
+    __syncthreads();
+    // row masks (one warp per row, ballot per 32 columns, 4 loads in flight), first non-zero column and
+    // population count of every row; the row with the most columns among those starting at column f
+    // becomes the representative of f
     for (int i = warp; i < m; i += kSecWarps) {
         const double* row = A + (int64_t)i * n;
-        int first = n;
-        for (int w = 0; w < nw; ++w) {
-            const int j = (w << 5) + lane;
-            const unsigned bal = __ballot_sync(0xffffffffu, j < n && row[j] != 0.0);
-            if (lane == 0) masks[(int64_t)i * nw + w] = bal;
-            if (bal && first == n) first = (w << 5) + __ffs(bal) - 1;
+        int first = n, pc = 0;
+        for (int w0 = 0; w0 < nw; w0 += 4) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int j = ((w0 + u) << 5) + lane; v[u] = (j < n) ? __ldg(row + j) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (w0 + u < nw) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, v[u] != 0.0);
+                    if (lane == 0) masks[(int64_t)i * nw + w0 + u] = bal;
+                    if (bal && first == n) first = ((w0 + u) << 5) + __ffs(bal) - 1;
+                    pc += __popc(bal);
+                }
+            }
         }
-        if (lane == 0) sm.rowkey[i] = first;
+        if (lane == 0) {
+            sm.rowkey[i] = first;
+            if (first < n) atomicMax(&sm.repkey[first], (pc << 16) | (0xFFFF - i));
+        }
     }
     __syncthreads();
-    // union-find over columns
+    // rows whose columns are a subset of their representative's need no processing of their own:
+    // rowsec[i] = 1 marks the rows the union-find has to walk
+    for (int i = warp; i < m; i += kSecWarps) {
+        const int f = sm.rowkey[i];
+        int proc = 0;
+        if (f < n) {
+            const int rep = 0xFFFF - (sm.repkey[f] & 0xFFFF);
+            if (rep == i) proc = 1;
+            else {
+                const uint32_t* mi = masks + (int64_t)i * nw;
+                const uint32_t* mr = masks + (int64_t)rep * nw;
+                int extra = 0;
+                for (int w = lane; w < nw; w += 32) extra |= (mi[w] & ~mr[w]) != 0;
+                proc = __any_sync(0xffffffffu, extra);
+            }
+        }
+        if (lane == 0) sm.rowsec[i] = (uint16_t)proc;
+    }
+    __syncthreads();
+    // union-find over columns, walking the marked rows
     while (true) {
         if (tid == 0) sh_flag[0] = 0;
         __syncthreads();
         int changed = 0;
         for (int i = warp; i < m; i += kSecWarps) {
-            if (sm.rowkey[i] >= n) continue;
+            if (!sm.rowsec[i]) continue;
             const uint32_t* mk = masks + (int64_t)i * nw;
             int rmin = n;
             for (int w = 0; w < nw; ++w)
@@ -123,8 +159,10 @@ __device__ void discover_sectors(SecMap& sm, const double* __restrict__ A, int m
             for (int o = 16; o > 0; o >>= 1) rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
             for (int w = 0; w < nw; ++w)
                 if ((mk[w] >> lane) & 1u) {
-                    const int r = uf_find(parent, (w << 5) + lane);
+                    const int j = (w << 5) + lane;
+                    const int r = uf_find(parent, j);
                     if (r != rmin) { atomicMin(&parent[r], rmin); changed = 1; }
+                    if (j != rmin && parent[j] > rmin) atomicMin(&parent[j], rmin);   // path compression (monotone)
                 }
         }
         if (changed) sh_flag[0] = 1;
@@ -215,57 +253,60 @@ __device__ void discover_sectors(SecMap& sm, const double* __restrict__ A, int m
 // One warp per trailing column, lanes over rows.  LAPACK dlarfg / dorg2r conventions.
 // ------------------------------------------------------------------------------------------------
 __device__ void householder_qr(double* W, int ld, int p, int q, int k, double* tau, double* Rout, double* red) {
+    // Every warp derives the reflector of column j redundantly (norm by warp reduction), so a column step
+    // needs ONE block barrier.  The reflector is kept unscaled in W (v_i = W[i][j] * scl[j], v_j = 1) and the
+    // diagonal of R in dia[j]; tau / scl / dia live in the caller's `tau` array (3k doubles).
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ double sh_tau, sh_scale;
+    double* scl = tau + k;
+    double* dia = tau + 2 * k;
+    (void)red;
     for (int j = 0; j < k; ++j) {
         double part = 0.0;
-        for (int i = j + 1 + tid; i < p; i += kSecThreads) { const double v = W[(int64_t)i * ld + j]; part += v * v; }
-        const double xnorm2 = block_sum(part, red);
-        if (tid == 0) {
-            const double alpha = W[(int64_t)j * ld + j];
-            double tj = 0.0, scale = 0.0, beta = alpha;
-            if (xnorm2 != 0.0) {
-                beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
-                tj = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
-            }
-            sh_tau = tj; sh_scale = scale;
-            tau[j] = tj;
-            W[(int64_t)j * ld + j] = beta;
+        for (int i = j + 1 + lane; i < p; i += 32) { const double v = W[(int64_t)i * ld + j]; part += v * v; }
+        const double xnorm2 = warp_sum(part);
+        const double alpha = W[(int64_t)j * ld + j];
+        double tj = 0.0, scale = 0.0, beta = alpha;
+        if (xnorm2 != 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+            tj = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
         }
-        __syncthreads();
-        const double tj = sh_tau, scale = sh_scale;
         if (tj != 0.0) {
-            for (int i = j + 1 + tid; i < p; i += kSecThreads) W[(int64_t)i * ld + j] *= scale;
-            __syncthreads();
             for (int c = j + 1 + warp; c < q; c += kSecWarps) {
                 double w = 0.0;
                 for (int i = j + 1 + lane; i < p; i += 32) w += W[(int64_t)i * ld + j] * W[(int64_t)i * ld + c];
-                w = (warp_sum(w) + W[(int64_t)j * ld + c]) * tj;
-                for (int i = j + 1 + lane; i < p; i += 32) W[(int64_t)i * ld + c] -= w * W[(int64_t)i * ld + j];
+                w = (warp_sum(w) * scale + W[(int64_t)j * ld + c]) * tj;
+                const double ws = w * scale;
+                for (int i = j + 1 + lane; i < p; i += 32) W[(int64_t)i * ld + c] -= ws * W[(int64_t)i * ld + j];
+                __syncwarp();
+                if (lane == 0) W[(int64_t)j * ld + c] -= w;
+            }
+        }
+        if (tid == 0) { tau[j] = tj; scl[j] = scale; dia[j] = beta; }
+        __syncthreads();
+    }
+    for (int e = tid; e < k * q; e += kSecThreads) {
+        const int i = e / q, j = e - i * q;
+        Rout[e] = (j > i) ? W[(int64_t)i * ld + j] : (j == i ? dia[i] : 0.0);
+    }
+    __syncthreads();
+    // explicit Q (dorg2r): columns k-1 .. 0
+    for (int j = k - 1; j >= 0; --j) {
+        const double tj = tau[j], scale = scl[j];
+        if (tj != 0.0) {
+            for (int c = j + 1 + warp; c < k; c += kSecWarps) {
+                double w = 0.0;
+                for (int i = j + 1 + lane; i < p; i += 32) w += W[(int64_t)i * ld + j] * W[(int64_t)i * ld + c];
+                w = (warp_sum(w) * scale + W[(int64_t)j * ld + c]) * tj;
+                const double ws = w * scale;
+                for (int i = j + 1 + lane; i < p; i += 32) W[(int64_t)i * ld + c] -= ws * W[(int64_t)i * ld + j];
                 __syncwarp();
                 if (lane == 0) W[(int64_t)j * ld + c] -= w;
             }
         }
         __syncthreads();
-    }
-    for (int e = tid; e < k * q; e += kSecThreads) {
-        const int i = e / q, j = e - i * q;
-        Rout[e] = (j >= i) ? W[(int64_t)i * ld + j] : 0.0;
-    }
-    __syncthreads();
-    for (int j = k - 1; j >= 0; --j) {
-        const double tj = tau[j];
-        for (int c = j + 1 + warp; c < k; c += kSecWarps) {
-            double w = 0.0;
-            for (int i = j + 1 + lane; i < p; i += 32) w += W[(int64_t)i * ld + j] * W[(int64_t)i * ld + c];
-            w = (warp_sum(w) + W[(int64_t)j * ld + c]) * tj;
-            for (int i = j + 1 + lane; i < p; i += 32) W[(int64_t)i * ld + c] -= w * W[(int64_t)i * ld + j];
-            __syncwarp();
-            if (lane == 0) W[(int64_t)j * ld + c] -= w;
-        }
-        __syncthreads();
-        for (int i = j + 1 + tid; i < p; i += kSecThreads) W[(int64_t)i * ld + j] *= -tj;
+        const double f = -tj * scale;
+        for (int i = j + 1 + tid; i < p; i += kSecThreads) W[(int64_t)i * ld + j] *= f;
         for (int i = tid; i < j; i += kSecThreads) W[(int64_t)i * ld + j] = 0.0;
         if (tid == 0) W[(int64_t)j * ld + j] = 1.0 - tj;
         __syncthreads();
@@ -302,11 +343,11 @@ __global__ void __launch_bounds__(kSecThreads) qr_sector_kernel(const int64_t* _
             const int ks = p < q ? p : q;
             const int K0 = sm.kstart[s];
             const int ld = q | 1;
-            const int64_t need = (int64_t)p * ld + ks + (int64_t)ks * q;
+            const int64_t need = (int64_t)p * ld + 3 * ks + (int64_t)ks * q;
             double* base = (need <= cap) ? work : gscratch;
             double* W = base;
             double* tau = W + (int64_t)p * ld;
-            double* Rc = tau + ks;
+            double* Rc = tau + 3 * ks;
             // gather X: use_qr X = M_s ; else X = M_s^T
             if (use_qr) {
                 for (int e = tid; e < ms * ns; e += kSecThreads) {
@@ -365,7 +406,7 @@ __device__ void jacobi_svd(double* G, int ldp, double* V, int ldq, int p, int q,
     if (q > 2 * (kSecThreads / gs) && gs > 8) gs = 8;   // more pairs in flight for wide sectors
     const int groups = kSecThreads / gs, grp = tid / gs, gl = tid % gs;
     const int qe = q + (q & 1), npairs = qe / 2;
-    const double tol = fmax(1e-15, sqrt((double)p) * 2.3e-16);
+    const double tol = fmax(1e-15, sqrt((double)p) * 2.3e-16), tol2 = tol * tol;
     for (int e = tid; e < q * q; e += kSecThreads) V[(e / q) * ldq + (e % q)] = ((e / q) == (e % q)) ? 1.0 : 0.0;
     __syncthreads();
     for (int sweep = 0; sweep < 60 && q > 1; ++sweep) {
@@ -388,10 +429,13 @@ __device__ void jacobi_svd(double* G, int ldp, double* V, int ldq, int p, int q,
                 if (valid)
                     for (int r = gl; r < p; r += gs) { const double x = gi[r], y = gj[r]; aa += x * x; bb += y * y; cc += x * y; }
                 aa = gsum(aa, gs); bb = gsum(bb, gs); cc = gsum(cc, gs);
-                if (valid && fabs(cc) > tol * sqrt(aa * bb) && aa * bb > 0.0) {
-                    const double zeta = (bb - aa) / (2.0 * cc);
-                    const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+                if (valid && cc * cc > tol2 * (aa * bb) && aa * bb > 0.0) {
+                    // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) with zeta = (bb - aa) / (2 cc), written with
+                    // one square root, one division and one reciprocal square root
+                    const double dd = bb - aa, c2 = 2.0 * cc;
+                    const double hh = sqrt(dd * dd + c2 * c2);
+                    const double tt = (dd >= 0.0 ? c2 : -c2) / (fabs(dd) + hh);
+                    const double cs = rsqrt(1.0 + tt * tt), sn = cs * tt;
                     for (int r = gl; r < p; r += gs) { const double x = gi[r], y = gj[r]; gi[r] = cs * x - sn * y; gj[r] = sn * x + cs * y; }
                     double* vi = V + (int64_t)i * ldq;
                     double* vj = V + (int64_t)j * ldq;
@@ -404,6 +448,55 @@ __device__ void jacobi_svd(double* G, int ldp, double* V, int ldq, int p, int q,
         const int any = *sh_rot;
         __syncthreads();
         if (!any) break;
+    }
+}
+
+// Warp-level variant: ONE warp owns a whole (small) sector, so the sectors of a matrix are diagonalised
+// concurrently by the warps of the CTA with no block barrier inside the sweeps.  `gs` lanes per column pair.
+__device__ void jacobi_svd_warp(double* G, int ldp, double* V, int ldq, int p, int q) {
+    const int lane = threadIdx.x & 31;
+    const int gs = (p <= 96) ? 4 : 8;
+    const int groups = 32 / gs, grp = lane / gs, gl = lane % gs;
+    const int qe = q + (q & 1), npairs = qe / 2;
+    const double tol = fmax(1e-15, sqrt((double)p) * 2.3e-16), tol2 = tol * tol;
+    for (int e = lane; e < q * q; e += 32) V[(e / q) * ldq + (e % q)] = ((e / q) == (e % q)) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 60 && q > 1; ++sweep) {
+        bool rotated = false;
+        for (int round = 0; round < qe - 1; ++round) {
+            for (int base = 0; base < npairs; base += groups) {
+                const int pr = base + grp;
+                int i = 0, j = 0;
+                bool valid = pr < npairs;
+                if (valid) {
+                    if (pr == 0) { i = qe - 1; j = round; }
+                    else { i = round + pr; if (i >= qe - 1) i -= qe - 1; j = round - pr; if (j < 0) j += qe - 1; }
+                    valid = i < q && j < q;
+                    if (i > j) { const int t = i; i = j; j = t; }
+                }
+                double* gi = G + i * ldp;
+                double* gj = G + j * ldp;
+                double aa = 0.0, bb = 0.0, cc = 0.0;
+                if (valid)
+                    for (int r = gl; r < p; r += gs) { const double x = gi[r], y = gj[r]; aa += x * x; bb += y * y; cc += x * y; }
+                aa = gsum(aa, gs); bb = gsum(bb, gs); cc = gsum(cc, gs);
+                if (valid && cc * cc > tol2 * (aa * bb) && aa * bb > 0.0) {
+                    // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) with zeta = (bb - aa) / (2 cc), written with
+                    // one square root, one division and one reciprocal square root
+                    const double dd = bb - aa, c2 = 2.0 * cc;
+                    const double hh = sqrt(dd * dd + c2 * c2);
+                    const double tt = (dd >= 0.0 ? c2 : -c2) / (fabs(dd) + hh);
+                    const double cs = rsqrt(1.0 + tt * tt), sn = cs * tt;
+                    for (int r = gl; r < p; r += gs) { const double x = gi[r], y = gj[r]; gi[r] = cs * x - sn * y; gj[r] = sn * x + cs * y; }
+                    double* vi = V + i * ldq;
+                    double* vj = V + j * ldq;
+                    for (int r = gl; r < q; r += gs) { const double x = vi[r], y = vj[r]; vi[r] = cs * x - sn * y; vj[r] = sn * x + cs * y; }
+                    rotated = true;
+                }
+            }
+            __syncwarp();
+        }
+        if (!__any_sync(0xffffffffu, rotated)) break;
     }
 }
 
@@ -441,62 +534,114 @@ __global__ void __launch_bounds__(kSecThreads) svd_sector_kernel(const int64_t* 
         discover_sectors(sm, A, m, n, sh_flag, reinterpret_cast<uint32_t*>(work), cap * 2);
         const int S = sm.S;
         const int ktot = sm.kstart[S];
-        // staged layout: U_s (ms x ks) at Ust + rstart[s]*k... use simple running offsets
+        // Sectors are processed in batches of consecutive small sectors, one warp per sector (no block barrier
+        // inside the Jacobi sweeps); a sector too large for that is diagonalised by the whole CTA.
+        // Staged results: U_s (ms x ks) row-major at Ust + uoff, Vt_s (ks x ns) row-major at Vst + voff.
         int64_t uoff = 0, voff = 0;
-        for (int s = 0; s < S; ++s) {
-            const int r0 = sm.rstart[s], c0 = sm.cstart[s];
-            const int ms = sm.rstart[s + 1] - r0, ns = sm.cstart[s + 1] - c0;
-            if (ms == 0 || ns == 0) continue;
-            const bool tall = ms >= ns;
-            const int p = tall ? ms : ns, q = tall ? ns : ms;   // q = ks
-            const int K0 = sm.kstart[s];
-            const int ldp = p | 1, ldq = q | 1;
-            const int64_t need = (int64_t)q * ldp + (int64_t)q * ldq + q;
-            double* base = (need <= cap) ? work : big;
-            double* G = base;
-            double* V = G + (int64_t)q * ldp;
-            double* sig = V + (int64_t)q * ldq;
-            // gather: column c of X.  tall: X = M_s (columns of M_s); wide: X = M_s^T (rows of M_s)
-            for (int e = tid; e < ms * ns; e += kSecThreads) {
-                const int r = e / ns, c = e - r * ns;
-                const double v = A[(int64_t)sm.rowlist[r0 + r] * n + sm.collist[c0 + c]];
-                if (tall) G[(int64_t)c * ldp + r] = v; else G[(int64_t)r * ldp + c] = v;
-            }
-            __syncthreads();
-            jacobi_svd(G, ldp, V, ldq, p, q, &sh_rot);
-            for (int c = warp; c < q; c += kSecWarps) {
-                double s2 = 0.0;
-                for (int r = lane; r < p; r += 32) s2 += G[(int64_t)c * ldp + r] * G[(int64_t)c * ldp + r];
-                s2 = warp_sum(s2);
-                if (lane == 0) { sig[c] = sqrt(s2); sig_all[K0 + c] = sqrt(s2); }
-            }
-            __syncthreads();
-            // stage: U_s (ms x q) row-major at Ust+uoff, Vt_s (q x ns) row-major at Vst+voff
-            double* Us = Ust + uoff;
-            double* Vs = Vst + voff;
-            if (tall) {
+        int s = 0;
+        while (s < S) {
+            const int ms0 = sm.rstart[s + 1] - sm.rstart[s], ns0 = sm.cstart[s + 1] - sm.cstart[s];
+            const int p0 = ms0 >= ns0 ? ms0 : ns0, q0 = ms0 >= ns0 ? ns0 : ms0;
+            const int64_t need0 = (int64_t)q0 * (p0 | 1) + (int64_t)q0 * (q0 | 1) + q0;
+            if (q0 > kWarpSectorMax || need0 > cap / 2) {
+                // ---- whole-CTA mode for one large sector ----
+                const int r0 = sm.rstart[s], c0 = sm.cstart[s];
+                const int ms = ms0, ns = ns0;
+                const bool tall = ms >= ns;
+                const int p = p0, q = q0;
+                const int K0 = sm.kstart[s];
+                const int ldp = p | 1, ldq = q | 1;
+                double* base = (need0 <= cap) ? work : big;
+                double* G = base;
+                double* V = G + (int64_t)q * ldp;
+                double* sig = V + (int64_t)q * ldq;
+                for (int e = tid; e < ms * ns; e += kSecThreads) {
+                    const int r = e / ns, c = e - r * ns;
+                    const double v = A[(int64_t)sm.rowlist[r0 + r] * n + sm.collist[c0 + c]];
+                    if (tall) G[(int64_t)c * ldp + r] = v; else G[(int64_t)r * ldp + c] = v;
+                }
+                __syncthreads();
+                jacobi_svd(G, ldp, V, ldq, p, q, &sh_rot);
+                for (int c = warp; c < q; c += kSecWarps) {
+                    double s2 = 0.0;
+                    for (int r = lane; r < p; r += 32) s2 += G[(int64_t)c * ldp + r] * G[(int64_t)c * ldp + r];
+                    s2 = warp_sum(s2);
+                    if (lane == 0) { sig[c] = sqrt(s2); sig_all[K0 + c] = sqrt(s2); }
+                }
+                __syncthreads();
+                double* Us = Ust + uoff;
+                double* Vs = Vst + voff;
                 for (int e = tid; e < ms * q; e += kSecThreads) {
                     const int r = e / q, c = e - r * q;
-                    const double sg = sig[c];
-                    Us[e] = sg > 0.0 ? G[(int64_t)c * ldp + r] / sg : 0.0;
+                    if (tall) { const double sg = sig[c]; Us[e] = sg > 0.0 ? G[(int64_t)c * ldp + r] / sg : 0.0; }
+                    else Us[e] = V[(int64_t)c * ldq + r];
                 }
                 for (int e = tid; e < q * ns; e += kSecThreads) {
                     const int c = e / ns, t = e - c * ns;
-                    Vs[e] = V[(int64_t)c * ldq + t];
+                    if (tall) Vs[e] = V[(int64_t)c * ldq + t];
+                    else { const double sg = sig[c]; Vs[e] = sg > 0.0 ? G[(int64_t)c * ldp + t] / sg : 0.0; }
                 }
-            } else {
-                for (int e = tid; e < ms * q; e += kSecThreads) {
-                    const int t = e / q, c = e - t * q;
-                    Us[e] = V[(int64_t)c * ldq + t];
+                uoff += (int64_t)ms * q;
+                voff += (int64_t)q * ns;
+                __syncthreads();
+                ++s;
+                continue;
+            }
+            // ---- batch of small sectors [s, e): warp w takes sector s + w ----
+            int e_ = s;
+            int64_t off = 0, my_off = -1, my_u = 0, my_v = 0, bu = uoff, bv = voff;
+            while (e_ < S && e_ - s < kSecWarps) {
+                const int ms = sm.rstart[e_ + 1] - sm.rstart[e_], ns = sm.cstart[e_ + 1] - sm.cstart[e_];
+                const int p = ms >= ns ? ms : ns, q = ms >= ns ? ns : ms;
+                const int64_t need = (int64_t)q * (p | 1) + (int64_t)q * (q | 1) + q;
+                if (q > kWarpSectorMax || need > cap / 2 || off + need > cap) break;
+                if (e_ - s == warp) { my_off = off; my_u = bu; my_v = bv; }
+                off += need;
+                bu += (int64_t)ms * q;
+                bv += (int64_t)q * ns;
+                ++e_;
+            }
+            if (my_off >= 0) {
+                const int sw = s + warp;
+                const int r0 = sm.rstart[sw], c0 = sm.cstart[sw];
+                const int ms = sm.rstart[sw + 1] - r0, ns = sm.cstart[sw + 1] - c0;
+                const bool tall = ms >= ns;
+                const int p = tall ? ms : ns, q = tall ? ns : ms;
+                const int K0 = sm.kstart[sw];
+                const int ldp = p | 1, ldq = q | 1;
+                double* G = work + my_off;
+                double* V = G + q * ldp;
+                double* sig = V + q * ldq;
+                for (int e = lane; e < ms * ns; e += 32) {
+                    const int r = e / ns, c = e - r * ns;
+                    const double v = A[(int64_t)sm.rowlist[r0 + r] * n + sm.collist[c0 + c]];
+                    if (tall) G[c * ldp + r] = v; else G[r * ldp + c] = v;
                 }
-                for (int e = tid; e < q * ns; e += kSecThreads) {
-                    const int c = e / ns, r = e - c * ns;
-                    const double sg = sig[c];
-                    Vs[e] = sg > 0.0 ? G[(int64_t)c * ldp + r] / sg : 0.0;
+                __syncwarp();
+                jacobi_svd_warp(G, ldp, V, ldq, p, q);
+                for (int c = 0; c < q; ++c) {
+                    double s2 = 0.0;
+                    for (int r = lane; r < p; r += 32) s2 += G[c * ldp + r] * G[c * ldp + r];
+                    s2 = warp_sum(s2);
+                    if (lane == 0) { sig[c] = sqrt(s2); sig_all[K0 + c] = sqrt(s2); }
+                }
+                __syncwarp();
+                double* Us = Ust + my_u;
+                double* Vs = Vst + my_v;
+                for (int e = lane; e < ms * q; e += 32) {
+                    const int r = e / q, c = e - r * q;
+                    if (tall) { const double sg = sig[c]; Us[e] = sg > 0.0 ? G[c * ldp + r] / sg : 0.0; }
+                    else Us[e] = V[c * ldq + r];
+                }
+                for (int e = lane; e < q * ns; e += 32) {
+                    const int c = e / ns, t = e - c * ns;
+                    if (tall) Vs[e] = V[c * ldq + t];
+                    else { const double sg = sig[c]; Vs[e] = sg > 0.0 ? G[c * ldp + t] / sg : 0.0; }
                 }
             }
-            uoff += (int64_t)ms * q;
-            voff += (int64_t)q * ns;
+            uoff = bu;
+            voff = bv;
+            s = e_;
             __syncthreads();
         }
         __threadfence_block();
@@ -559,7 +704,7 @@ int tnsp_qr_sector_launch(const int64_t* sect, const int64_t* sh, const double* 
     }
     int grid = nb < 2 * kSMs ? nb : 2 * kSMs;
     const int64_t p = use_qr ? m : n, q = use_qr ? n : m, k = p < q ? p : q;
-    const int64_t per_cta = p * (q | 1) + k + k * q + 8;
+    const int64_t per_cta = p * (q | 1) + 3 * k + k * q + 8;
     const int64_t need = per_cta * grid;
     if (need > g_qr_scratch_cap) {
         if (g_qr_scratch) cudaFree(g_qr_scratch);

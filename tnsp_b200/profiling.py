@@ -18,6 +18,7 @@ class KernelTimer:
     def __init__(self, backend):
         self.B = backend
         self.records = {k: [] for k in self.CLASSES}
+        self.shapes = {}   # (class, shape signature) -> list of (e0, e1, flops, bytes)
         self._orig = {}
 
     def _work(self, name, args):
@@ -66,6 +67,10 @@ class KernelTimer:
                 e1.record()
                 by, fl = self._work(_name, args)
                 self.records[_name].append((e0, e1, by, fl))
+                if _name in ("gemm", "qr", "svd"):
+                    tab = args[0].gemm if _name == "gemm" else args[0].sectors
+                    sig = (_name, len(tab), tuple(int(x) for x in tab[0][:3]), int(args[-1].shape[0]))
+                    self.shapes.setdefault(sig, []).append((e0, e1, fl, by))
                 return r
 
             setattr(self.B, name, wrapped)
@@ -91,6 +96,17 @@ class KernelTimer:
         for v in out.values():
             v["share"] = v["ms"] / total
         return out
+
+    def shape_summary(self, top=12):
+        """heaviest (kernel class, #descriptors, first (m, n, k), chains) signatures"""
+        rows = []
+        for sig, recs in self.shapes.items():
+            ms = float(sum(a.elapsed_time(b) for a, b, _, _ in recs))
+            rows.append({"kernel": sig[0], "descriptors": sig[1], "mnk": list(sig[2]), "chains": sig[3], "launches": len(recs), "ms": ms,
+                         "tflops": float(sum(r[2] for r in recs)) / (ms * 1e9) if ms else 0.0,
+                         "gbs": float(sum(r[3] for r in recs)) / (ms * 1e6) if ms else 0.0})
+        rows.sort(key=lambda r: -r["ms"])
+        return rows[:top]
 
 
 def measure_fp64_gemm_tflops(n=4096, reps=3):
