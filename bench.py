@@ -28,7 +28,7 @@ WORKLOADS = {
     # name: dict(L1, L2, D, Dc, sym, J2, sr (SR natural gradient by CG with `cg` iterations per step), chains, desc)
     "cfg1": dict(L1=4, L2=4, D=4, Dc=16, sym="No", J2=0.0, sr=False, cg=0, chains=4096,
                  desc="tetragono sampling VMC 4x4 Heisenberg square lattice, no symmetry, D=4, Dc=16, float64"),
-    "cfg2": dict(L1=6, L2=6, D=6, Dc=36, sym="BoseU1", J2=0.5, sr=True, cg=20, chains=296,
+    "cfg2": dict(L1=6, L2=6, D=6, Dc=36, sym="BoseU1", J2=0.5, sr=True, cg=20, chains=592,
                  desc="6x6 J1-J2 Heisenberg (J2=0.5) with U(1) symmetry, D=6 (2+2+2), Dc=36, sweep sampling + SR natural gradient (CG 20), float64"),
     "cfg2s": dict(L1=4, L2=4, D=3, Dc=9, sym="BoseU1", J2=0.5, sr=True, cg=4, chains=64,
                   desc="4x4 J1-J2 Heisenberg with U(1) symmetry, D=3, Dc=9, sweep + SR (smoke size of cfg2)"),
@@ -317,7 +317,12 @@ def run_own(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        roofline = profiling.roofline_of_dominant(breakdown, peaks)
+        traffic_table = {}
+        try:
+            traffic_table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            pass
+        roofline = profiling.roofline_of_dominant(breakdown, peaks, top_shapes, traffic_table)
 
     out = None
     if rank == 0:

@@ -126,7 +126,12 @@ def measure_fp64_gemm_tflops(n=4096, reps=3):
     return 2.0 * n**3 / (best * 1e-3) / 1e12
 
 
-def roofline_of_dominant(breakdown, peaks):
+def roofline_of_dominant(breakdown, peaks, top_shapes=None, traffic_table=None):
+    """roofline object of bench.py for the kernel class with the largest share of device time.
+
+    achieved = algorithmic bytes (flops) of all its launches in the instrumented pass / their CUDA-event time;
+    traffic  = DRAM bytes per launch of the class' heaviest shape from the ncu --set full capture recorded in
+               profiles/ncu_traffic.json (None if that shape was not captured), next to its algorithmic bytes."""
     if not breakdown:
         return None
     name = max(breakdown, key=lambda k: breakdown[k]["ms"])
@@ -138,12 +143,24 @@ def roofline_of_dominant(breakdown, peaks):
         hbm_peak, which = 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
     gbs = v["bytes"] / sec / 1e9
     intensity = v["flops"] / max(v["bytes"], 1.0)
+    extra = {"launches": v["launches"], "avg_launch_us": v["ms"] * 1e3 / v["launches"], "share_of_kernel_time": v["share"]}
+    traffic = None
+    if top_shapes:
+        mine = [r for r in top_shapes if r["kernel"] == name]
+        if mine:
+            r = mine[0]
+            key = "%s:%s:%d" % (name, "x".join(str(x) for x in r["mnk"]), r["chains"])
+            extra["heaviest_shape"] = {"mnk": r["mnk"], "chains": r["chains"], "launches": r["launches"], "ms": r["ms"],
+                                       "achieved_gbs": r["gbs"], "achieved_tflops": r["tflops"]}
+            if traffic_table and key in traffic_table:
+                t = traffic_table[key]
+                traffic = t["dram_bytes_per_launch"]
+                extra["heaviest_shape"]["algorithmic_bytes_per_launch"] = t.get("algorithmic_bytes_per_launch")
+                extra["heaviest_shape"]["ncu_report"] = t.get("report")
     if name == "gemm" and intensity > 6.0:
         peak = measure_fp64_gemm_tflops()
         ach = v["flops"] / sec / 1e12
-        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no FP64 entry in MEASURED_PEAKS.json)",
-                "launches": v["launches"], "avg_launch_us": v["ms"] * 1e3 / v["launches"], "share_of_kernel_time": v["share"]}
-    return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
-            "peak_source": which, "launches": v["launches"], "avg_launch_us": v["ms"] * 1e3 / v["launches"],
-            "share_of_kernel_time": v["share"]}
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no FP64 entry in MEASURED_PEAKS.json)", **extra}
+    return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
+            "peak_source": which, **extra}
