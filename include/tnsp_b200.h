@@ -86,6 +86,11 @@ int tnsp_svd_sectors_f64(const int64_t* sect, const int64_t* sect_host, const do
                          double* out1, int64_t o1_bstride, double* s, int64_t s_bstride, double* out2, int64_t o2_bstride,
                          double* work, int64_t w_bstride, int nb, void* stream);
 
+/* Tuning knob of the two entry points above: matrices with >= min_elems elements are factorised sector by
+ * sector from a device-side work queue (several CTAs per SM), smaller ones by one CTA per chain.  Returns the
+ * previous threshold; a negative argument only queries. */
+int64_t tnsp_sector_queue_min(int64_t min_elems);
+
 /* ---- greedy cross-sector truncation (svd.hpp:429-481): counts[b][i] = kept values of sector i. */
 int tnsp_svd_cut_f64(const int64_t* sect, int ns, int64_t s_total, const double* s, int64_t s_bstride,
                      int64_t remain_cut, double relative_cut, int32_t* counts, int nb, void* stream);

@@ -79,6 +79,8 @@ class CudaBackend:
         lib.tnsp_svd_batched_f64.argtypes = [P, c_int, P, P, c_i64, P, c_i64, P, c_i64, P, c_i64, P, c_i64, c_int, P]
         lib.tnsp_qr_sectors_f64.argtypes = [P, P, P, c_i64, P, c_i64, P, c_i64, c_int, c_int, P]
         lib.tnsp_svd_sectors_f64.argtypes = [P, P, P, c_i64, P, c_i64, P, c_i64, P, c_i64, P, c_i64, c_int, P]
+        lib.tnsp_sector_queue_min.restype = c_i64
+        lib.tnsp_sector_queue_min.argtypes = [c_i64]
         # set by tetragono.dense_embedding: single-descriptor factorisations discover their sectors on the device
         self.sector_discovery = False
         lib.tnsp_svd_cut_f64.argtypes = [P, c_int, c_i64, P, c_i64, c_i64, c_dbl, P, c_int, P]

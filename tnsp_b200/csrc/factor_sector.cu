@@ -20,6 +20,8 @@
 // Outputs must be zero-initialised by the caller (only sector blocks are written).
 //
 // Roofline: HBM; algorithmic bytes 8*(2mn + mk + kn) (QR), 8*(mn + mk + kn + k) (SVD) per chain.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tnsp {
@@ -257,6 +259,7 @@ __device__ void householder_qr(double* W, int ld, int p, int q, int k, double* t
     // needs ONE block barrier.  The reflector is kept unscaled in W (v_i = W[i][j] * scl[j], v_j = 1) and the
     // diagonal of R in dia[j]; tau / scl / dia live in the caller's `tau` array (3k doubles).
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     double* scl = tau + k;
     double* dia = tau + 2 * k;
     (void)red;
@@ -272,7 +275,7 @@ __device__ void householder_qr(double* W, int ld, int p, int q, int k, double* t
             scale = 1.0 / (alpha - beta);
         }
         if (tj != 0.0) {
-            for (int c = j + 1 + warp; c < q; c += kSecWarps) {
+            for (int c = j + 1 + warp; c < q; c += nwarps) {
                 double w = 0.0;
                 for (int i = j + 1 + lane; i < p; i += 32) w += W[(int64_t)i * ld + j] * W[(int64_t)i * ld + c];
                 w = (warp_sum(w) * scale + W[(int64_t)j * ld + c]) * tj;
@@ -285,7 +288,7 @@ __device__ void householder_qr(double* W, int ld, int p, int q, int k, double* t
         if (tid == 0) { tau[j] = tj; scl[j] = scale; dia[j] = beta; }
         __syncthreads();
     }
-    for (int e = tid; e < k * q; e += kSecThreads) {
+    for (int e = tid; e < k * q; e += nthreads) {
         const int i = e / q, j = e - i * q;
         Rout[e] = (j > i) ? W[(int64_t)i * ld + j] : (j == i ? dia[i] : 0.0);
     }
@@ -294,7 +297,7 @@ __device__ void householder_qr(double* W, int ld, int p, int q, int k, double* t
     for (int j = k - 1; j >= 0; --j) {
         const double tj = tau[j], scale = scl[j];
         if (tj != 0.0) {
-            for (int c = j + 1 + warp; c < k; c += kSecWarps) {
+            for (int c = j + 1 + warp; c < k; c += nwarps) {
                 double w = 0.0;
                 for (int i = j + 1 + lane; i < p; i += 32) w += W[(int64_t)i * ld + j] * W[(int64_t)i * ld + c];
                 w = (warp_sum(w) * scale + W[(int64_t)j * ld + c]) * tj;
@@ -306,8 +309,8 @@ __device__ void householder_qr(double* W, int ld, int p, int q, int k, double* t
         }
         __syncthreads();
         const double f = -tj * scale;
-        for (int i = j + 1 + tid; i < p; i += kSecThreads) W[(int64_t)i * ld + j] *= f;
-        for (int i = tid; i < j; i += kSecThreads) W[(int64_t)i * ld + j] = 0.0;
+        for (int i = j + 1 + tid; i < p; i += nthreads) W[(int64_t)i * ld + j] *= f;
+        for (int i = tid; i < j; i += nthreads) W[(int64_t)i * ld + j] = 0.0;
         if (tid == 0) W[(int64_t)j * ld + j] = 1.0 - tj;
         __syncthreads();
     }
@@ -400,14 +403,15 @@ __device__ __forceinline__ double gsum(double v, int gs) {
 }
 
 __device__ void jacobi_svd(double* G, int ldp, double* V, int ldq, int p, int q, int* sh_rot) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
     int gs = 32;
     while (gs > 4 && (gs >> 1) >= p) gs >>= 1;
-    if (q > 2 * (kSecThreads / gs) && gs > 8) gs = 8;   // more pairs in flight for wide sectors
-    const int groups = kSecThreads / gs, grp = tid / gs, gl = tid % gs;
+    // as many lanes per pair as still let all pairs of a round run in one pass
+    while (gs > 4 && ((q + 1) >> 1) * gs > nthreads) gs >>= 1;
+    const int groups = nthreads / gs, grp = tid / gs, gl = tid % gs;
     const int qe = q + (q & 1), npairs = qe / 2;
     const double tol = fmax(1e-15, sqrt((double)p) * 2.3e-16), tol2 = tol * tol;
-    for (int e = tid; e < q * q; e += kSecThreads) V[(e / q) * ldq + (e % q)] = ((e / q) == (e % q)) ? 1.0 : 0.0;
+    for (int e = tid; e < q * q; e += nthreads) V[(e / q) * ldq + (e % q)] = ((e / q) == (e % q)) ? 1.0 : 0.0;
     __syncthreads();
     for (int sweep = 0; sweep < 60 && q > 1; ++sweep) {
         if (tid == 0) *sh_rot = 0;
@@ -683,6 +687,409 @@ __global__ void __launch_bounds__(kSecThreads) svd_sector_kernel(const int64_t* 
     }
 }
 
+
+// ================================================================================================
+// Work-queue variant for the larger matrices (the boundary-MPS bonds of cfg2: 216 x 216, 216 x 1296 ...).
+//
+// The single-kernel variants above give one CTA a whole chain; a chain has only ~5 sectors of ~40 columns,
+// so an SM holds 8 warps that mostly wait on shared-memory latency.  Here the work is split by SECTOR:
+//
+//   sector_discover_kernel   one CTA per chain: zero pattern -> sector map in global memory (gmap) and one
+//                            work item (chain, sector) per non-empty sector, pushed into a queue by cost class
+//   qr_work_kernel /         persistent CTAs pop items (heaviest class first) and factorise ONE compact sector
+//   svd_work_kernel          in shared memory; several CTAs per SM (72 KiB class) or one (200 KiB class)
+//   svd_finish_kernel        per chain: global descending rank of the staged singular values (the greedy
+//                            cross-sector cut order of svd.hpp:455-461) and scatter of U / Vt into the dense layout
+// ================================================================================================
+constexpr int kQSmallDoubles = 9 * 1024;    // 72 KiB  -> 3 CTAs / SM
+constexpr int kQSmallThreads = 256;
+constexpr int kQBigDoubles = 25 * 1024;     // 200 KiB -> 1 CTA / SM
+constexpr int kQBigThreads = 1024;
+constexpr int kQClasses = 3;                // 0: big (or spilling), 1: small & heavy, 2: small & light
+// qctl layout: [0..2] item counts per class, [3] ticket of the big kernel, [4] ticket of the small kernel
+
+__host__ __device__ inline int gmap_smax(int m, int n) { return (m < n ? m : n) + 2; }
+__host__ __device__ inline int64_t gmap_stride(int m, int n) { return 2 + 5 * (int64_t)gmap_smax(m, n) + n + m; }
+
+struct GMap {
+    const int* base;
+    int smax, n;
+    __device__ GMap(const int* g, int m_, int n_) : base(g), smax(gmap_smax(m_, n_)), n(n_) {}
+    __device__ int S() const { return base[0]; }
+    __device__ int ktot() const { return base[1]; }
+    __device__ const int* cstart() const { return base + 2; }
+    __device__ const int* rstart() const { return base + 2 + smax; }
+    __device__ const int* kstart() const { return base + 2 + 2 * smax; }
+    __device__ const int* uoff() const { return base + 2 + 3 * smax; }
+    __device__ const int* voff() const { return base + 2 + 4 * smax; }
+    __device__ const int* collist() const { return base + 2 + 5 * smax; }
+    __device__ const int* rowlist() const { return base + 2 + 5 * smax + n; }
+};
+
+__host__ __device__ inline int64_t qr_sector_need(int64_t p, int64_t q) {
+    const int64_t k = p < q ? p : q;
+    return p * (q | 1) + 3 * k + k * q;
+}
+__host__ __device__ inline int64_t svd_sector_need(int64_t p, int64_t q) { return q * (p | 1) + q * (q | 1) + q; }
+
+// kind: 0 = QR of M_s, 1 = LQ of M_s (QR of its transpose), 2 = SVD
+__global__ void __launch_bounds__(kSecThreads) sector_discover_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a,
+                                                                      int64_t abs_, int nb, int kind, int64_t mask_cap_words,
+                                                                      int* __restrict__ gmap, int64_t gstride, int* __restrict__ qctl,
+                                                                      int2* __restrict__ qitems, int64_t qcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int sh_flag[2];
+    const int m = (int)sect[0], n = (int)sect[1];
+    const int tid = threadIdx.x;
+    SecMap sm;
+    secmap_carve(sm, smem_raw, m, n);
+    uint32_t* masks = reinterpret_cast<uint32_t*>(smem_raw + secmap_bytes(m, n));
+    const int smax = gmap_smax(m, n);
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const double* A = a + (int64_t)b * abs_ + sect[3];
+        discover_sectors(sm, A, m, n, sh_flag, masks, mask_cap_words);
+        const int S = sm.S;
+        int* g = gmap + (int64_t)b * gstride;
+        int* g_c = g + 2, *g_r = g_c + smax, *g_k = g_r + smax, *g_u = g_k + smax, *g_v = g_u + smax;
+        int* g_cl = g_v + smax, *g_rl = g_cl + n;
+        for (int s = tid; s <= S; s += kSecThreads) { g_c[s] = sm.cstart[s]; g_r[s] = sm.rstart[s]; g_k[s] = sm.kstart[s]; }
+        for (int j = tid; j < n; j += kSecThreads) g_cl[j] = sm.collist[j];
+        for (int i = tid; i < m; i += kSecThreads) g_rl[i] = sm.rowlist[i];
+        if (tid == 0) {
+            g[0] = S;
+            g[1] = sm.kstart[S];
+            int uo = 0, vo = 0;
+            for (int s = 0; s < S; ++s) {
+                const int ms = sm.rstart[s + 1] - sm.rstart[s], ns = sm.cstart[s + 1] - sm.cstart[s];
+                g_u[s] = uo; g_v[s] = vo;
+                if (ms == 0 || ns == 0) continue;
+                int64_t need, cost;
+                int qq;
+                if (kind == 2) {
+                    const int pp = ms >= ns ? ms : ns; qq = ms >= ns ? ns : ms;
+                    need = svd_sector_need(pp, qq);
+                    cost = (int64_t)pp * qq * qq;
+                    uo += ms * qq; vo += qq * ns;
+                } else {
+                    const int pp = kind == 0 ? ms : ns; qq = kind == 0 ? ns : ms;
+                    need = qr_sector_need(pp, qq);
+                    cost = (int64_t)pp * qq * (pp < qq ? pp : qq);
+                }
+                const int cls = need > kQSmallDoubles ? 0 : (cost >= 16 * 1024 ? 1 : 2);
+                const int at = atomicAdd(&qctl[cls], 1);
+                qitems[(int64_t)cls * qcap + at] = make_int2(b, s);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// pops the next work item of a persistent CTA; which = 0: class 0 (big kernel), 1: classes 1 then 2 (small kernel)
+__device__ __forceinline__ bool pop_item(int which, int* qctl, const int2* qitems, int64_t qcap, int* sh_ticket, int2& item) {
+    __syncthreads();
+    if (threadIdx.x == 0) *sh_ticket = atomicAdd(&qctl[3 + which], 1);
+    __syncthreads();
+    const int t = *sh_ticket;
+    if (which == 0) {
+        if (t >= qctl[0]) return false;
+        item = qitems[t];
+    } else {
+        const int c1 = qctl[1], c2 = qctl[2];
+        if (t >= c1 + c2) return false;
+        item = t < c1 ? qitems[qcap + t] : qitems[2 * qcap + (t - c1)];
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kQBigThreads) qr_work_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a, int64_t abs_, double* __restrict__ out1,
+                               int64_t o1bs, double* __restrict__ out2, int64_t o2bs, int use_qr, const int* __restrict__ gmap,
+                               int64_t gstride, int* qctl, const int2* __restrict__ qitems, int64_t qcap, int which, int64_t cap,
+                               double* __restrict__ scratch, int64_t scratch_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int sh_ticket;
+    double* work = reinterpret_cast<double*>(smem_raw);
+    const int m = (int)sect[0], n = (int)sect[1], k = (int)sect[2];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int2 item;
+    while (pop_item(which, qctl, qitems, qcap, &sh_ticket, item)) {
+        const int b = item.x, s = item.y;
+        const GMap g(gmap + (int64_t)b * gstride, m, n);
+        const double* A = a + (int64_t)b * abs_ + sect[3];
+        double* O1 = out1 + (int64_t)b * o1bs + sect[4];   // m x k
+        double* O2 = out2 + (int64_t)b * o2bs + sect[5];   // k x n
+        const int r0 = g.rstart()[s], c0 = g.cstart()[s];
+        const int ms = g.rstart()[s + 1] - r0, ns = g.cstart()[s + 1] - c0;
+        const int* rl = g.rowlist() + r0;
+        const int* cl = g.collist() + c0;
+        const int p = use_qr ? ms : ns, q = use_qr ? ns : ms;
+        const int ks = p < q ? p : q;
+        const int K0 = g.kstart()[s];
+        const int ld = q | 1;
+        const int64_t need = qr_sector_need(p, q);
+        double* W = (need <= cap) ? work : scratch + (int64_t)blockIdx.x * scratch_per_cta;
+        double* tau = W + (int64_t)p * ld;
+        double* Rc = tau + 3 * ks;
+        if (use_qr) {
+            for (int e = tid; e < ms * ns; e += nt) {
+                const int r = e / ns, c = e - r * ns;
+                W[(int64_t)r * ld + c] = __ldg(A + (int64_t)rl[r] * n + cl[c]);
+            }
+        } else {
+            for (int e = tid; e < ms * ns; e += nt) {
+                const int r = e / ns, c = e - r * ns;
+                W[(int64_t)c * ld + r] = __ldg(A + (int64_t)rl[r] * n + cl[c]);
+            }
+        }
+        __syncthreads();
+        householder_qr(W, ld, p, q, ks, tau, Rc, nullptr);
+        if (use_qr) {
+            for (int e = tid; e < ms * ks; e += nt) {
+                const int r = e / ks, t = e - r * ks;
+                O1[(int64_t)rl[r] * k + K0 + t] = W[(int64_t)r * ld + t];
+            }
+            for (int e = tid; e < ks * ns; e += nt) {
+                const int t = e / ns, c = e - t * ns;
+                O2[(int64_t)(K0 + t) * n + cl[c]] = Rc[(int64_t)t * q + c];
+            }
+        } else {
+            for (int e = tid; e < ms * ks; e += nt) {
+                const int r = e / ks, t = e - r * ks;
+                O1[(int64_t)rl[r] * k + K0 + t] = Rc[(int64_t)t * q + r];
+            }
+            for (int e = tid; e < ks * ns; e += nt) {
+                const int t = e / ns, c = e - t * ns;
+                O2[(int64_t)(K0 + t) * n + cl[c]] = W[(int64_t)c * ld + t];
+            }
+        }
+    }
+}
+
+// work (per chain): sigma in staging order [k] | - [k] | staged U blocks [m*k] | staged Vt blocks [k*n] | ...
+__global__ void __launch_bounds__(kQBigThreads) svd_work_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a, int64_t abs_, double* __restrict__ workg,
+                                int64_t wbs, const int* __restrict__ gmap, int64_t gstride, int* qctl, const int2* __restrict__ qitems,
+                                int64_t qcap, int which, int64_t cap, double* __restrict__ scratch, int64_t scratch_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int sh_ticket;
+    __shared__ int sh_rot;
+    double* work = reinterpret_cast<double*>(smem_raw);
+    const int m = (int)sect[0], n = (int)sect[1], k = (int)sect[2];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    int2 item;
+    while (pop_item(which, qctl, qitems, qcap, &sh_ticket, item)) {
+        const int b = item.x, s = item.y;
+        const GMap g(gmap + (int64_t)b * gstride, m, n);
+        const double* A = a + (int64_t)b * abs_ + sect[3];
+        double* wg = workg + (int64_t)b * wbs;
+        double* sig_all = wg;
+        double* Us = wg + 2 * k + g.uoff()[s];
+        double* Vs = wg + 2 * k + (int64_t)m * k + g.voff()[s];
+        const int r0 = g.rstart()[s], c0 = g.cstart()[s];
+        const int ms = g.rstart()[s + 1] - r0, ns = g.cstart()[s + 1] - c0;
+        const int* rl = g.rowlist() + r0;
+        const int* cl = g.collist() + c0;
+        const bool tall = ms >= ns;
+        const int p = tall ? ms : ns, q = tall ? ns : ms;
+        const int K0 = g.kstart()[s];
+        const int ldp = p | 1, ldq = q | 1;
+        double* G = (svd_sector_need(p, q) <= cap) ? work : scratch + (int64_t)blockIdx.x * scratch_per_cta;
+        double* V = G + (int64_t)q * ldp;
+        double* sig = V + (int64_t)q * ldq;
+        for (int e = tid; e < ms * ns; e += nt) {
+            const int r = e / ns, c = e - r * ns;
+            const double v = __ldg(A + (int64_t)rl[r] * n + cl[c]);
+            if (tall) G[(int64_t)c * ldp + r] = v; else G[(int64_t)r * ldp + c] = v;
+        }
+        __syncthreads();
+        jacobi_svd(G, ldp, V, ldq, p, q, &sh_rot);
+        for (int c = warp; c < q; c += nwarps) {
+            double s2 = 0.0;
+            for (int r = lane; r < p; r += 32) s2 += G[(int64_t)c * ldp + r] * G[(int64_t)c * ldp + r];
+            s2 = warp_sum(s2);
+            if (lane == 0) { sig[c] = sqrt(s2); sig_all[K0 + c] = sqrt(s2); }
+        }
+        __syncthreads();
+        for (int e = tid; e < ms * q; e += nt) {
+            const int r = e / q, c = e - r * q;
+            if (tall) { const double sg = sig[c]; Us[e] = sg > 0.0 ? G[(int64_t)c * ldp + r] / sg : 0.0; }
+            else Us[e] = V[(int64_t)c * ldq + r];
+        }
+        for (int e = tid; e < q * ns; e += nt) {
+            const int c = e / ns, t = e - c * ns;
+            if (tall) Vs[e] = V[(int64_t)c * ldq + t];
+            else { const double sg = sig[c]; Vs[e] = sg > 0.0 ? G[(int64_t)c * ldp + t] / sg : 0.0; }
+        }
+    }
+}
+
+// grid (nb, split): every CTA ranks the chain's staged singular values (value desc, staging order on ties = sector
+// order then position, svd.hpp:455-461); CTA y scatters sectors y, y + split, ...
+__global__ void __launch_bounds__(256) svd_finish_kernel(const int64_t* __restrict__ sect, double* __restrict__ out1, int64_t o1bs,
+                                                         double* __restrict__ sv, int64_t sbs, double* __restrict__ out2, int64_t o2bs,
+                                                         const double* __restrict__ workg, int64_t wbs, const int* __restrict__ gmap,
+                                                         int64_t gstride, int rank_in_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = (int)sect[0], n = (int)sect[1], k = (int)sect[2];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int b = blockIdx.x;
+    const GMap g(gmap + (int64_t)b * gstride, m, n);
+    double* O1 = out1 + (int64_t)b * o1bs + sect[4];   // U  m x k
+    double* O2 = out2 + (int64_t)b * o2bs + sect[5];   // Vt k x n
+    double* Sg = sv + (int64_t)b * sbs + sect[6];
+    const double* wg = workg + (int64_t)b * wbs;
+    const double* sig_all = wg;
+    const int S = g.S(), ktot = g.ktot();
+    double* sg_s = reinterpret_cast<double*>(smem_raw);          // [ktot] when rank_in_smem
+    int* rk = reinterpret_cast<int*>(sg_s + (rank_in_smem ? k : 0));   // [ktot]
+    int* rk_g = reinterpret_cast<int*>(const_cast<double*>(wg) + k);    // [k] ints inside the second k doubles of work
+    if (rank_in_smem) {
+        for (int c = tid; c < ktot; c += nt) sg_s[c] = sig_all[c];
+        __syncthreads();
+        for (int c = tid; c < ktot; c += nt) {
+            const double v = sg_s[c];
+            int r = 0;
+            for (int o = 0; o < ktot; ++o) { const double w = sg_s[o]; r += (w > v) || (w == v && o < c); }
+            rk[c] = r;
+            if (blockIdx.y == 0) Sg[r] = v;
+        }
+        __syncthreads();
+    } else {
+        // very wide bonds: ranks are computed by the y == 0 CTA only into the work buffer (gridDim.y == 1 then)
+        for (int c = tid; c < ktot; c += nt) {
+            const double v = sig_all[c];
+            int r = 0;
+            for (int o = 0; o < ktot; ++o) { const double w = sig_all[o]; r += (w > v) || (w == v && o < c); }
+            rk_g[c] = r;
+            Sg[r] = v;
+        }
+        __threadfence_block();
+        __syncthreads();
+        rk = rk_g;
+    }
+    for (int s = blockIdx.y; s < S; s += gridDim.y) {
+        const int r0 = g.rstart()[s], c0 = g.cstart()[s];
+        const int ms = g.rstart()[s + 1] - r0, ns = g.cstart()[s + 1] - c0;
+        if (ms == 0 || ns == 0) continue;
+        const int q = ms < ns ? ms : ns;
+        const int K0 = g.kstart()[s];
+        const double* Us = wg + 2 * k + g.uoff()[s];
+        const double* Vs = wg + 2 * k + (int64_t)m * k + g.voff()[s];
+        const int* rl = g.rowlist() + r0;
+        const int* cl = g.collist() + c0;
+        for (int e = tid; e < ms * q; e += nt) {
+            const int r = e / q, c = e - r * q;
+            O1[(int64_t)rl[r] * k + rk[K0 + c]] = Us[e];
+        }
+        for (int e = tid; e < q * ns; e += nt) {
+            const int c = e / ns, t = e - c * ns;
+            O2[(int64_t)rk[K0 + c] * n + cl[t]] = Vs[e];
+        }
+    }
+}
+
+// ---- workspace of the work-queue path (grown on demand, reused by every call on the stream) ----
+struct QueueWs {
+    int* gmap = nullptr; int64_t gmap_cap = 0;
+    int* qctl = nullptr;
+    int2* qitems = nullptr; int64_t qitems_cap = 0;
+    double* scratch = nullptr; int64_t scratch_cap = 0;
+};
+static QueueWs g_qws;
+
+template <class T>
+static bool grow(T*& ptr, int64_t& cap, int64_t need) {
+    if (need <= cap) return true;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    if (cudaMalloc(&ptr, sizeof(T) * need) != cudaSuccess) { cudaGetLastError(); return false; }
+    cap = need;
+    return true;
+}
+
+static int64_t g_queue_min = -1;
+static int64_t queue_min_elems() {
+    if (g_queue_min < 0) {
+        const char* e = getenv("TNSP_SECTOR_QUEUE_MIN");
+        g_queue_min = e ? atoll(e) : 2048;
+    }
+    return g_queue_min;
+}
+
+// common front end: sector discovery + queue fill.  Returns 0 ok, 1 error, -1 not applicable.
+static int queue_discover(const int64_t* sect, int64_t m, int64_t n, const double* a, int64_t abs_, int nb, int kind, int64_t per_cta_scratch,
+                          int big_grid, cudaStream_t st, int64_t& gstride, int64_t& qcap) {
+    if (m > kSecMaxDim || n > kSecMaxDim) return -1;
+    if (secmap_bytes(m, n) + 4096 > (int64_t)kSecSmemDoubles * 8) return -1;
+    gstride = gmap_stride((int)m, (int)n);
+    qcap = (int64_t)nb * gmap_smax((int)m, (int)n);
+    if (!g_qws.qctl && cudaMalloc(&g_qws.qctl, 8 * sizeof(int)) != cudaSuccess) { set_error("sector queue: cudaMalloc"); return 1; }
+    if (!grow(g_qws.gmap, g_qws.gmap_cap, gstride * nb) || !grow(g_qws.qitems, g_qws.qitems_cap, kQClasses * qcap) ||
+        !grow(g_qws.scratch, g_qws.scratch_cap, per_cta_scratch * big_grid)) {
+        set_error("sector queue: cudaMalloc of the workspace failed");
+        return 1;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sector_discover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecSmemDoubles * 8);
+        cudaFuncSetAttribute(qr_work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(svd_work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(svd_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_set = true;
+    }
+    cudaMemsetAsync(g_qws.qctl, 0, 8 * sizeof(int), st);
+    const int64_t nw = (n + 31) / 32;
+    const int64_t room = (int64_t)kSecSmemDoubles * 8 - secmap_bytes(m, n);
+    int64_t mask_bytes = m * nw * 4;
+    int64_t mask_cap_words = m * nw;
+    if (mask_bytes > room) { mask_bytes = 0; mask_cap_words = 0; }   // falls back to one dense sector
+    const int grid = nb < 8 * kSMs ? nb : 8 * kSMs;
+    sector_discover_kernel<<<grid, kSecThreads, secmap_bytes(m, n) + mask_bytes, st>>>(sect, a, abs_, nb, kind, mask_cap_words, g_qws.gmap,
+                                                                                       gstride, g_qws.qctl, g_qws.qitems, qcap);
+    return check_launch("tnsp sector discovery");
+}
+
+static int qr_queue_launch(const int64_t* sect, const int64_t* sh, const double* a, int64_t abs_, double* out1, int64_t o1bs, double* out2,
+                           int64_t o2bs, int use_qr, int nb, cudaStream_t st) {
+    const int64_t m = sh[0], n = sh[1];
+    const int64_t p = use_qr ? m : n, q = use_qr ? n : m;
+    const int64_t full = qr_sector_need(p, q);   // the largest sector possible
+    const int64_t per_cta = full > kQBigDoubles ? full + 8 : 0;
+    int64_t gstride, qcap;
+    const int rc = queue_discover(sect, m, n, a, abs_, nb, use_qr ? 0 : 1, per_cta, kSMs, st, gstride, qcap);
+    if (rc != 0) return rc;
+    if (full > kQSmallDoubles) {
+        qr_work_kernel<<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, g_qws.gmap, gstride,
+                                                                     g_qws.qctl, g_qws.qitems, qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
+        if (check_launch("tnsp_qr_sectors_f64(big)")) return 1;
+    }
+    qr_work_kernel<<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, g_qws.gmap, gstride,
+                                                                         g_qws.qctl, g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
+    return check_launch("tnsp_qr_sectors_f64(small)");
+}
+
+static int svd_queue_launch(const int64_t* sect, const int64_t* sh, const double* a, int64_t abs_, double* out1, int64_t o1bs, double* s,
+                            int64_t sbs, double* out2, int64_t o2bs, double* work, int64_t wbs, int nb, cudaStream_t st) {
+    const int64_t m = sh[0], n = sh[1], k = sh[2];
+    const int64_t p = m >= n ? m : n, q = m >= n ? n : m;
+    const int64_t full = svd_sector_need(p, q);
+    const int64_t per_cta = full > kQBigDoubles ? full + 8 : 0;
+    int64_t gstride, qcap;
+    const int rc = queue_discover(sect, m, n, a, abs_, nb, 2, per_cta, kSMs, st, gstride, qcap);
+    if (rc != 0) return rc;
+    if (full > kQSmallDoubles) {
+        svd_work_kernel<<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(sect, a, abs_, work, wbs, g_qws.gmap, gstride, g_qws.qctl, g_qws.qitems,
+                                                                      qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
+        if (check_launch("tnsp_svd_sectors_f64(big)")) return 1;
+    }
+    svd_work_kernel<<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(sect, a, abs_, work, wbs, g_qws.gmap, gstride, g_qws.qctl,
+                                                                          g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
+    if (check_launch("tnsp_svd_sectors_f64(small)")) return 1;
+    const int rank_in_smem = k * 12 <= 96 * 1024;
+    const int split = rank_in_smem ? 4 : 1;
+    svd_finish_kernel<<<dim3(nb, split), 256, rank_in_smem ? k * 12 : 0, st>>>(sect, out1, o1bs, s, sbs, out2, o2bs, work, wbs, g_qws.gmap,
+                                                                                gstride, rank_in_smem);
+    return check_launch("tnsp_svd_sectors_f64(finish)");
+}
+
 static double* g_qr_scratch = nullptr;
 static int64_t g_qr_scratch_cap = 0;
 
@@ -697,6 +1104,10 @@ int tnsp_qr_sector_launch(const int64_t* sect, const int64_t* sh, const double* 
     const int64_t m = sh[0], n = sh[1];
     if (m > kSecMaxDim || n > kSecMaxDim) return -1;
     if (secmap_bytes(m, n) / 8 + 4096 > kSecSmemDoubles) return -1;
+    if (m * n >= queue_min_elems()) {
+        const int rc = qr_queue_launch(sect, sh, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb, st);
+        if (rc >= 0) return rc;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(qr_sector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecSmemDoubles * 8);
@@ -727,6 +1138,10 @@ int tnsp_svd_sector_launch(const int64_t* sect, const int64_t* sh, const double*
     if (m > kSecMaxDim || n > kSecMaxDim) return -1;
     if (secmap_bytes(m, n) / 8 + 4096 > kSecSmemDoubles) return -1;
     if (work == nullptr || wbs < svd_sector_work(m, n)) { set_error("tnsp_svd_batched_f64(sector): scratch too small"); return 1; }
+    if (m * n >= queue_min_elems()) {
+        const int rc = svd_queue_launch(sect, sh, a, abs_, out1, o1bs, s, sbs, out2, o2bs, work, wbs, nb, st);
+        if (rc >= 0) return rc;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(svd_sector_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecSmemDoubles * 8);
@@ -754,4 +1169,12 @@ extern "C" int tnsp_svd_sectors_f64(const int64_t* sect, const int64_t* sect_hos
     const int rc = tnsp_svd_sector_launch(sect, sect_host, a, abs_, out1, o1bs, s, sbs, out2, o2bs, work, wbs, nb, (cudaStream_t)stream);
     if (rc < 0) { set_error("tnsp_svd_sectors_f64: matrix too large for the discovered-sector kernel"); return 1; }
     return rc;
+}
+
+// Tuning knob: matrices with at least `min_elems` elements take the per-sector work-queue path, smaller ones the
+// one-CTA-per-chain kernel.  Returns the previous value; a negative argument only queries.
+extern "C" int64_t tnsp_sector_queue_min(int64_t min_elems) {
+    const int64_t old = queue_min_elems();
+    if (min_elems >= 0) g_queue_min = min_elems;
+    return old;
 }
