@@ -56,6 +56,16 @@ int tnsp_gemm_grouped_f64(const int64_t* desc, int ng, const int64_t* desc_host,
                           const double* a, int64_t a_bstride, const double* b, int64_t b_bstride,
                           double* c, int64_t c_bstride, int nb, void* stream);
 
+/* ---- K2g: contraction of two DENSE(-embedded) tensors read in place (replaces the two edge_operator merges
+ * AND the gemm of contract.hpp:622-857 by one pass): C[b] (m x n, row-major) = alpha * A_g[b] * B_g[b] with
+ *   A_g(r, kk) = a[b * a_bstride + tab[r] + tab[m + kk]],  B_g(kk, c) = b[b * b_bstride + tab[m + k + kk] + tab[m + 2k + c]]
+ * tab: int32[m + 2k + n] element offsets built by the host planner from the edge strides (merge order of
+ * edge_operator.hpp:321-404).  flags bit0: consecutive kk of A_g are (mostly) contiguous in memory, else consecutive r;
+ * bit1: consecutive c of B_g are contiguous, else consecutive kk (decides which index runs along the lanes). */
+int tnsp_gemm_gather_f64(const int32_t* tab, int64_t m, int64_t n, int64_t k, int flags, double alpha,
+                         const double* a, int64_t a_bstride, const double* b, int64_t b_bstride,
+                         double* c, int64_t c_bstride, int nb, void* stream);
+
 /* ---- K3: batched QR / LQ with explicit Q (replaces ?geqrf/?orgqr and ?gelqf/?orglq per sector,
  * qr.hpp:178-304).  sect[ns][8] = (m, n, k, a_off, out1_off, out2_off, s_off, -); the m x n input
  * at a_off is destroyed.  use_qr != 0: out1 = Q (m x k), out2 = R (k x n); else out1 = L, out2 = Q. */

@@ -84,6 +84,22 @@ class NumpyBackend:
             bm = B[:, bo:bo + k * n].reshape(nb, n, k).transpose(0, 2, 1) if flags & 2 else B[:, bo:bo + k * n].reshape(nb, k, n)
             C[:, co:co + m * n] = (float(alpha) * np.matmul(am, bm)).reshape(nb, m * n)
 
+    gather_gemm = True
+
+    def gemm_gather(self, plan, a, b, c):
+        """contract.hpp:622-857 restated without the intermediate merged copies: operands indexed in place"""
+        self.launches += 1
+        tab, flags, m, n, k = plan.gather
+        aro, aco, bro, bco = tab[:m], tab[m:m + k], tab[m + k:m + 2 * k], tab[m + 2 * k:]
+        nb = c.shape[0]
+        A, B = self._v(a, nb), self._v(b, nb)
+        am = A[:, aro[:, None].astype(np.int64) + aco[None, :]]
+        bm = B[:, bro[:, None].astype(np.int64) + bco[None, :]]
+        c.numpy()[:, :m * n] = np.matmul(am, bm).reshape(nb, m * n)
+
+    def qr_destroys_input(self, plan):
+        return False
+
     # K3
     def qr(self, plan, a, out1, out2):
         self.launches += 1

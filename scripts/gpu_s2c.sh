@@ -1,0 +1,8 @@
+set -x
+python -m pytest tests/test_kernels_gpu.py -m gpu -x -q 2>&1 | tail -8 > gpurun_out/s2c_ktests.txt
+(cd scripts && timeout 600 python mb_gemm.py 592 > ../gpurun_out/s2c_mb_gemm.txt 2>&1)
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/s2c_tests.txt
+timeout 900 python bench.py --workload cfg2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/s2c_bench_cfg2.json 2> gpurun_out/s2c_bench_cfg2.err
+cd scripts
+ncu --set full --clock-control none --import-source on -k regex:svd_work -s 3 -c 1 -o ../gpurun_out/s2c_prof_svd_work_216x216 python mb_sector_one.py svd 216 216 296 > ../gpurun_out/s2c_ncu_svd.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_gather -s 4 -c 1 -o ../gpurun_out/s2c_prof_gather python mb_gemm.py 592 > ../gpurun_out/s2c_ncu_gather.log 2>&1

@@ -76,4 +76,5 @@ def main():
             print(f"    max |sigma_queue - sigma_chain| = {float((res['queue'][1][2] - res['chain'][1][2]).abs().max()):.2e}")
     B.lib.tnsp_sector_queue_min(2048)
 
-main()
+if __name__ == "__main__":
+    main()

@@ -291,3 +291,48 @@ def test_sector_paths_agree(shape, queue_min, discovery):
             assert np.abs((U[b] * S[b]) @ Vt[b] - mats[b]).max() <= 1e-12 * ref.max() * max(m, n)
     finally:
         cu.lib.tnsp_sector_queue_min(old)
+
+
+@pytest.mark.parametrize("dims", [
+    # (dims of tensor 1, axes of tensor 1 that are contracted, dims of tensor 2, contracted axes of tensor 2 in pairing order)
+    ((36, 6, 36), (1,), (6, 6, 6), (0,)),            # 1296 x 36 x 6: middle index contracted, k short of a slab
+    ((6, 36, 6, 36), (1, 3), (36, 36, 5), (1, 0)),   # 36 x 5 x 1296 rows small -> still gathered if m >= 48? (m = 36: packed path)
+    ((36, 36, 6), (2,), (6, 216), (0,)),             # 1296 x 216 x 6
+    ((216, 6, 36), (0,), (216, 36), (0,)),           # A stored k-major: 216 x 36 x 216
+    ((8, 27, 37), (1,), (3, 27, 11), (1,)),          # odd sizes, n = 33 not a multiple of 8, k = 27
+    ((1300,), (), (7,), ()),                          # outer product, k = 1
+    ((216, 36, 6), (1, 2), (6, 36, 216), (1, 0)),    # 216 x 216 x 216 with permuted common order
+])
+@pytest.mark.parametrize("nb", [1, 5, 300])
+def test_gemm_gather_in_place_operands(dims, nb):
+    """contract of dense tensors through the offset-table GEMM (no packed operands) against numpy tensordot;
+    one operand broadcast to all chains in a second pass"""
+    import tnsp_b200.TAT as TAT
+    from tnsp_b200.TAT import tensor as tt
+    cu, ck = _both()
+    d1, c1, d2, c2 = dims
+    rng = np.random.default_rng(sum(d1) + 7 * sum(d2) + nb)
+    T = TAT.No.D.Tensor
+    n1 = [f"a{i}" for i in range(len(d1))]
+    n2 = [f"b{i}" for i in range(len(d2))]
+    x1 = rng.standard_normal((nb, int(np.prod(d1))))
+    for nb2 in (nb, 1):
+        x2 = rng.standard_normal((nb2, int(np.prod(d2))))
+        t1 = T.from_batch(n1, [TAT.No.Edge(d) for d in d1], x1)
+        t2 = T.from_batch(n2, [TAT.No.Edge(d) for d in d2], x2)
+        pairs = {(n1[i], n2[j]) for i, j in zip(c1, c2)}
+        got = t1.contract(t2, pairs)
+        want = np.stack([np.tensordot(x1[b].reshape(d1), x2[b % nb2].reshape(d2), axes=(list(c1), list(c2))).reshape(-1) for b in range(nb)])
+        res = np.atleast_2d(np.asarray(got.storage))
+        kk = int(np.prod([d1[i] for i in c1])) if c1 else 1
+        assert res.shape == want.shape
+        assert np.abs(res - want).max() <= 1e-13 * max(1.0, np.abs(want).max()) * max(kk, 1)
+        # the packed path gives the same numbers
+        cu.gather_gemm = False
+        try:
+            tt._PLAN_CACHE.clear()
+            res2 = np.atleast_2d(np.asarray(t1.contract(t2, pairs).storage))
+        finally:
+            cu.gather_gemm = True
+            tt._PLAN_CACHE.clear()
+        assert np.abs(res2 - want).max() <= 1e-13 * max(1.0, np.abs(want).max()) * max(kk, 1)

@@ -390,7 +390,8 @@ def edge_operator_plan(
 # contract
 # ------------------------------------------------------------------------------------------------
 class ContractPlan:
-    __slots__ = ("pack1", "pack2", "unpack", "gemm", "prod_size", "zero_fill", "names", "edges", "table", "flops", "m1_size", "m2_size", "fuse_l", "_dev")
+    __slots__ = ("pack1", "pack2", "unpack", "gemm", "prod_size", "zero_fill", "names", "edges", "table", "flops", "m1_size", "m2_size", "fuse_l", "_dev",
+                 "gather", "_gdev")
 
 
 def _common_order(names_1, names_2, map12, map21, free_1, free_2, size_1, size_2):
@@ -445,6 +446,56 @@ def _common_order(names_1, names_2, map12, map21, free_1, free_2, size_1, size_2
     return common_1, common_2, r1, r2
 
 
+GATHER_MIN_M = 48   # below this the small-tile grouped kernels (on packed operands) are used
+
+
+def _rowstream_fits(n, k):
+    """mirror of rowstream_shape() in csrc/gemm_gather.cu: one n-pass (<= 64 columns) of the zero-padded B operand of a
+    chain must fit in 104 KiB of shared memory (wider B operands are sliced over the grid)"""
+    if n <= 64:
+        nt = (n + 7) // 8
+    else:
+        nt = min(range(8, 4, -1), key=lambda t: (((n + 8 * t - 1) // (8 * t)) * 8 * t - n, -t))
+    return ((k + 3) // 4 * 4) * (8 * nt + 4) * 8 <= 104 * 1024
+
+
+def _gather_tables(names_1, edges_1, names_2, edges_2, free_1, common_1, free_2, common_2, m, n, k):
+    """Offset tables that let the GEMM read both operands of a dense contraction in place (csrc/gemm_gather.cu):
+    element (r, kk) of the merged matrix of tensor 1 is data[row_off[r] + col_off[kk]], where r / kk enumerate the
+    free / common edges row-major in the reference's merge order (edge_operator.hpp:321-404 with one segment per
+    edge; contract.hpp:622-857).  Returns (int32 table aro|aco|bro|bco, flags) or None when the gather path does
+    not apply (tiny or empty problems, offsets beyond int32)."""
+    if m < GATHER_MIN_M or n == 0 or k == 0 or not _rowstream_fits(n, k):
+        return None
+
+    def strides(edges):
+        st, acc = [], 1
+        for e in reversed(edges):
+            st.append(acc)
+            acc *= e.dimension
+        return list(reversed(st)), acc
+
+    def offsets(names, edges, stride, group):
+        o = np.zeros(1, dtype=np.int64)
+        for nm in group:
+            i = names.index(nm)
+            o = (o[:, None] + np.arange(edges[i].dimension, dtype=np.int64)[None, :] * stride[i]).reshape(-1)
+        return o
+
+    s1, size1 = strides(edges_1)
+    s2, size2 = strides(edges_2)
+    if max(size1, size2) >= 2**31:
+        return None
+    aro = offsets(names_1, edges_1, s1, free_1)
+    aco = offsets(names_1, edges_1, s1, common_1)
+    bro = offsets(names_2, edges_2, s2, common_2)
+    bco = offsets(names_2, edges_2, s2, free_2)
+    assert len(aro) == m and len(aco) == k and len(bro) == k and len(bco) == n
+    # lanes run along the direction in which the operand is contiguous in memory: the group holding the last edge
+    flags = (1 if names_1 and names_1[-1] in common_1 else 0) | (2 if names_2 and names_2[-1] in free_2 else 0)
+    return np.concatenate([aro, aco, bro, bco]).astype(np.int32), flags, m, n, k
+
+
 # gemm descriptor row: (m, n, k, a_off, b_off, c_off, flags, alpha_sign)
 #   flags bit0: A stored [k x m] (else [m x k]);  bit1: B stored [n x k] (else [k x n]); row-major, dense
 GEMM_COLS = 8
@@ -463,6 +514,8 @@ def contract_plan(EdgeT, names_1, edges_1, names_2, edges_2, pairs, fuse_names=(
     t1, t2 = block_table(edges_1), block_table(edges_2)
     plan = ContractPlan()
     plan._dev = None
+    plan._gdev = None
+    plan.gather = None
     fuse = [n for n in names_1 if n in fuse_names] if fuse_names else []
     if fuse and S.length != 0:
         raise RuntimeError("fuse_names is only supported for tensors without symmetry")
@@ -506,6 +559,7 @@ def contract_plan(EdgeT, names_1, edges_1, names_2, edges_2, pairs, fuse_names=(
         plan.zero_fill = bool(m and n and not k)
         plan.unpack = None
         plan.fuse_l = l
+        plan.gather = _gather_tables(names_1, edges_1, names_2, edges_2, free_1, common_1, free_2, common_2, m, n, k) if l == 1 and not fuse else None
     else:
         # contract.hpp:306-620
         rev_1, rev_2, rev_res, common_rev_1 = set(), set(), set(), set()

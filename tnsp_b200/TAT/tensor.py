@@ -651,6 +651,11 @@ class Tensor:
         if d1.shape[0] != d2.shape[0] and min(d1.shape[0], d2.shape[0]) != 1:
             raise RuntimeError("contract of two batched tensors with different chain counts")
         STATS["flops"] += p.flops * nb
+        if p.gather is not None and B.gather_gemm:
+            # dense operands are read in place through offset tables: no merged / transposed copies (csrc/gemm_gather.cu)
+            prod = B.empty(nb, p.prod_size)
+            B.gemm_gather(p, d1, d2, prod)
+            return self._make(p.names, p.edges, p.table, prod)
         m1 = self._run_pack(p.pack1, d1)
         m2 = other._run_pack(p.pack2, d2)
         prod = B.zeros(nb, p.prod_size) if p.zero_fill else B.empty(nb, p.prod_size)
@@ -739,8 +744,8 @@ class Tensor:
         STATS["qr"] += 1
         nb = self.data.shape[0]
         merged = self._run_pack(p.merge)
-        if merged is self.data:
-            merged = merged.clone()  # the factorization destroys its input
+        if merged is self.data and B.qr_destroys_input(p):
+            merged = merged.clone()
         t1 = B.zeros(nb, p.t1_table.size)
         t2 = B.zeros(nb, p.t2_table.size)
         B.qr(p, merged, t1, t2)

@@ -79,6 +79,9 @@ class CudaBackend:
         lib.tnsp_svd_batched_f64.argtypes = [P, c_int, P, P, c_i64, P, c_i64, P, c_i64, P, c_i64, P, c_i64, c_int, P]
         lib.tnsp_qr_sectors_f64.argtypes = [P, P, P, c_i64, P, c_i64, P, c_i64, c_int, c_int, P]
         lib.tnsp_svd_sectors_f64.argtypes = [P, P, P, c_i64, P, c_i64, P, c_i64, P, c_i64, P, c_i64, c_int, P]
+        lib.tnsp_gemm_gather_f64.argtypes = [P, c_i64, c_i64, c_i64, c_int, c_dbl, P, c_i64, P, c_i64, P, c_i64, c_int, P]
+        # contract of dense tensors reads its operands in place (no pack); tests switch it off to cover the packed path
+        self.gather_gemm = True
         lib.tnsp_sector_queue_min.restype = c_i64
         lib.tnsp_sector_queue_min.argtypes = [c_i64]
         # set by tetragono.dense_embedding: single-descriptor factorisations discover their sectors on the device
@@ -145,6 +148,19 @@ class CudaBackend:
         nb = c.shape[0]
         self._ck(self.lib.tnsp_gemm_grouped_f64(dev.data_ptr(), len(plan.gemm), plan.gemm.ctypes.data, a.data_ptr(), self._bs(a),
                                                 b.data_ptr(), self._bs(b), c.data_ptr(), c.stride(0), nb, self._stream()))
+
+    def gemm_gather(self, plan, a, b, c):
+        tab, flags, m, n, k = plan.gather
+        dev = plan._gdev
+        if dev is None:
+            dev = plan._gdev = self.upload(tab)
+        nb = c.shape[0]
+        self._ck(self.lib.tnsp_gemm_gather_f64(dev.data_ptr(), m, n, k, flags, 1.0, a.data_ptr(), self._bs(a), b.data_ptr(), self._bs(b),
+                                               c.data_ptr(), c.stride(0), nb, self._stream()))
+
+    def qr_destroys_input(self, plan):
+        """only the descriptor-driven kernel for matrices beyond shared memory factorises in place"""
+        return not (self.sector_discovery and len(plan.sectors) == 1)
 
     def _sect(self, plan):
         dev = plan._dev

@@ -255,65 +255,99 @@ __device__ void discover_sectors(SecMap& sm, const double* __restrict__ A, int m
 // One warp per trailing column, lanes over rows.  LAPACK dlarfg / dorg2r conventions.
 // ------------------------------------------------------------------------------------------------
 __device__ void householder_qr(double* W, int ld, int p, int q, int k, double* tau, double* Rout, double* red) {
-    // Every warp derives the reflector of column j redundantly (norm by warp reduction), so a column step
-    // needs ONE block barrier.  The reflector is kept unscaled in W (v_i = W[i][j] * scl[j], v_j = 1) and the
+    // ONE block barrier per column step.  The warp that updates column j+1 in step j also accumulates the norm of
+    // its new sub-column and derives reflector j+1 right away, so the norm / sqrt / divisions are off the critical
+    // path of the other warps.  The reflector is kept unscaled in W (v_i = W[i][j] * scl[j], v_j = 1) and the
     // diagonal of R in dia[j]; tau / scl / dia live in the caller's `tau` array (3k doubles).
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     double* scl = tau + k;
     double* dia = tau + 2 * k;
     (void)red;
-    for (int j = 0; j < k; ++j) {
-        double part = 0.0;
-        for (int i = j + 1 + lane; i < p; i += 32) { const double v = W[(int64_t)i * ld + j]; part += v * v; }
-        const double xnorm2 = warp_sum(part);
-        const double alpha = W[(int64_t)j * ld + j];
+    // all lanes of one warp: reflector of column j from the squared norm of its rows below the diagonal
+    auto make_reflector = [&](int j, double xnorm2) {
+        const double alpha = W[j * ld + j];
         double tj = 0.0, scale = 0.0, beta = alpha;
         if (xnorm2 != 0.0) {
             beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
             tj = (beta - alpha) / beta;
             scale = 1.0 / (alpha - beta);
         }
-        if (tj != 0.0) {
-            for (int c = j + 1 + warp; c < q; c += nwarps) {
+        if (lane == 0) { tau[j] = tj; scl[j] = scale; dia[j] = beta; }
+    };
+    if (warp == 0 && k > 0) {
+        double part = 0.0;
+        for (int i = 1 + lane; i < p; i += 32) { const double v = W[i * ld]; part += v * v; }
+        make_reflector(0, warp_sum(part));
+    }
+    __syncthreads();
+    for (int j = 0; j < k; ++j) {
+        const double tj = tau[j], scale = scl[j];
+        const double* vj = W + j;            // column j: vj[i * ld]
+        for (int c = j + 1 + warp; c < q; c += nwarps) {
+            double* wc = W + c;
+            const bool next = (c == j + 1) && (c < k);
+            double part = 0.0;
+            if (tj != 0.0) {
                 double w = 0.0;
-                for (int i = j + 1 + lane; i < p; i += 32) w += W[(int64_t)i * ld + j] * W[(int64_t)i * ld + c];
-                w = (warp_sum(w) * scale + W[(int64_t)j * ld + c]) * tj;
+                for (int i = j + 1 + lane; i < p; i += 32) w += vj[i * ld] * wc[i * ld];
+                w = (warp_sum(w) * scale + wc[j * ld]) * tj;
                 const double ws = w * scale;
-                for (int i = j + 1 + lane; i < p; i += 32) W[(int64_t)i * ld + c] -= ws * W[(int64_t)i * ld + j];
+                if (next) {
+                    for (int i = j + 1 + lane; i < p; i += 32) {
+                        const double nv = wc[i * ld] - ws * vj[i * ld];
+                        wc[i * ld] = nv;
+                        if (i > c) part += nv * nv;
+                    }
+                } else {
+                    for (int i = j + 1 + lane; i < p; i += 32) wc[i * ld] -= ws * vj[i * ld];
+                }
                 __syncwarp();
-                if (lane == 0) W[(int64_t)j * ld + c] -= w;
+                if (lane == 0) wc[j * ld] -= w;
+            } else if (next) {
+                for (int i = c + 1 + lane; i < p; i += 32) { const double v = wc[i * ld]; part += v * v; }
+            }
+            if (next) {
+                __syncwarp();
+                make_reflector(c, warp_sum(part));
             }
         }
-        if (tid == 0) { tau[j] = tj; scl[j] = scale; dia[j] = beta; }
         __syncthreads();
     }
     for (int e = tid; e < k * q; e += nthreads) {
         const int i = e / q, j = e - i * q;
-        Rout[e] = (j > i) ? W[(int64_t)i * ld + j] : (j == i ? dia[i] : 0.0);
+        Rout[e] = (j > i) ? W[i * ld + j] : (j == i ? dia[i] : 0.0);
     }
     __syncthreads();
-    // explicit Q (dorg2r): columns k-1 .. 0
+    // explicit Q (dorg2r): columns k-1 .. 0.  Column j+1 (the reflector of the previous step) is turned into a column
+    // of Q by the warp that is about to apply H_j to it (same lane <-> row mapping, so no extra barrier).
+    auto finalize = [&](int j) {             // one warp; lanes own rows j + lane, j + lane + 32, ...
+        const double tj = tau[j];
+        const double f = -tj * scl[j];
+        double* wj = W + j;
+        for (int i = j + lane; i < p; i += 32) wj[i * ld] = (i == j) ? 1.0 - tj : wj[i * ld] * f;
+        for (int i = lane; i < j; i += 32) wj[i * ld] = 0.0;
+    };
     for (int j = k - 1; j >= 0; --j) {
         const double tj = tau[j], scale = scl[j];
-        if (tj != 0.0) {
-            for (int c = j + 1 + warp; c < k; c += nwarps) {
+        const double* vj = W + j;
+        for (int c = j + 1 + warp; c < k; c += nwarps) {
+            double* wc = W + c;
+            if (c == j + 1) { finalize(c); __syncwarp(); }
+            if (tj != 0.0) {
                 double w = 0.0;
-                for (int i = j + 1 + lane; i < p; i += 32) w += W[(int64_t)i * ld + j] * W[(int64_t)i * ld + c];
-                w = (warp_sum(w) * scale + W[(int64_t)j * ld + c]) * tj;
+                for (int i = j + 1 + lane; i < p; i += 32) w += vj[i * ld] * wc[i * ld];
+                w = (warp_sum(w) * scale + wc[j * ld]) * tj;
                 const double ws = w * scale;
-                for (int i = j + 1 + lane; i < p; i += 32) W[(int64_t)i * ld + c] -= ws * W[(int64_t)i * ld + j];
+                for (int i = j + 1 + lane; i < p; i += 32) wc[i * ld] -= ws * vj[i * ld];
                 __syncwarp();
-                if (lane == 0) W[(int64_t)j * ld + c] -= w;
+                if (lane == 0) wc[j * ld] -= w;
             }
         }
         __syncthreads();
-        const double f = -tj * scale;
-        for (int i = j + 1 + tid; i < p; i += nthreads) W[(int64_t)i * ld + j] *= f;
-        for (int i = tid; i < j; i += nthreads) W[(int64_t)i * ld + j] = 0.0;
-        if (tid == 0) W[(int64_t)j * ld + j] = 1.0 - tj;
-        __syncthreads();
     }
+    if (warp == 0 && k > 0) finalize(0);
+    __syncthreads();
 }
 
 // sect[8] = (m, n, k, a_off, out1_off, out2_off, -, -)
@@ -445,6 +479,82 @@ __device__ void jacobi_svd(double* G, int ldp, double* V, int ldq, int p, int q,
                     double* vj = V + (int64_t)j * ldq;
                     for (int r = gl; r < q; r += gs) { const double x = vi[r], y = vj[r]; vi[r] = cs * x - sn * y; vj[r] = sn * x + cs * y; }
                     if (gl == 0) *sh_rot = 1;
+                }
+            }
+            __syncthreads();
+        }
+        const int any = *sh_rot;
+        __syncthreads();
+        if (!any) break;
+    }
+}
+
+// Second generation of the CTA-wide Jacobi (used by the work-queue kernel).  Same mathematics, reorganised around
+// the two limits the first version hit on B200 (ncu: 33 % of the shared-memory wavefronts were bank conflicts and the
+// issue slots were the bottleneck):
+//   * columns are padded to an even length and 16-byte aligned, every lane owns PAIRS of rows and moves them with
+//     128-bit loads / stores -- a group of 8 lanes touches 128 contiguous bytes, i.e. exactly one conflict-free
+//     wavefront, and the number of memory instructions halves;
+//   * the rotation is derived with one rsqrt-based square root, one reciprocal and one rsqrt;
+//   * a sweep whose largest rotation was below 1e-8 (relative) ends the iteration: the cyclic Jacobi method converges
+//     quadratically, so the remaining off-diagonal couplings are O(1e-16) and the confirming sweep is not needed.
+// ldp, ldq even; rows p..ldp-1 of G and q..ldq-1 of V must be (and stay) zero.
+__device__ void jacobi_svd2(double* G, int ldp, double* V, int ldq, int p, int q, int* sh_rot) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int pe = p + (p & 1), qe_rows = q + (q & 1);
+    const int qe = q + (q & 1), npairs = qe / 2;
+    int gs = 32;
+    while (gs > 4 && gs >= pe) gs >>= 1;                       // no more lanes than row pairs
+    while (gs > 4 && npairs * gs > nthreads) gs >>= 1;         // all pairs of a round in one pass when possible
+    const int groups = nthreads / gs, grp = tid / gs, gl = tid % gs;
+    const double tol = fmax(1e-15, sqrt((double)p) * 2.3e-16), tol2 = tol * tol;
+    for (int e = tid; e < q * ldq; e += nthreads) { const int cidx = e / ldq, t = e - cidx * ldq; V[e] = (cidx == t) ? 1.0 : 0.0; }
+    __syncthreads();
+    for (int sweep = 0; sweep < 60 && q > 1; ++sweep) {
+        if (tid == 0) *sh_rot = 0;
+        __syncthreads();
+        for (int round = 0; round < qe - 1; ++round) {
+            for (int base = 0; base < npairs; base += groups) {
+                const int pr = base + grp;
+                int i = 0, j = 0;
+                bool valid = pr < npairs;
+                if (valid) {
+                    if (pr == 0) { i = qe - 1; j = round; }
+                    else { i = round + pr; if (i >= qe - 1) i -= qe - 1; j = round - pr; if (j < 0) j += qe - 1; }
+                    valid = i < q && j < q;
+                    if (i > j) { const int t = i; i = j; j = t; }
+                }
+                double2* gi = reinterpret_cast<double2*>(G + i * ldp);
+                double2* gj = reinterpret_cast<double2*>(G + j * ldp);
+                double aa = 0.0, bb = 0.0, cc = 0.0;
+                if (valid)
+                    for (int r = gl; 2 * r < pe; r += gs) {
+                        const double2 x = gi[r], y = gj[r];
+                        aa = fma(x.x, x.x, aa); aa = fma(x.y, x.y, aa);
+                        bb = fma(y.x, y.x, bb); bb = fma(y.y, y.y, bb);
+                        cc = fma(x.x, y.x, cc); cc = fma(x.y, y.y, cc);
+                    }
+                aa = gsum(aa, gs); bb = gsum(bb, gs); cc = gsum(cc, gs);
+                const double ab = aa * bb, c2q = cc * cc;
+                if (valid && c2q > tol2 * ab && ab > 0.0) {
+                    const double dd = bb - aa, c2 = 2.0 * cc;
+                    const double x2 = fma(dd, dd, c2 * c2);
+                    const double hh = x2 > 1e-280 ? x2 * rsqrt(x2) : sqrt(x2);
+                    const double tt = (dd >= 0.0 ? c2 : -c2) * __drcp_rn(fabs(dd) + hh);
+                    const double cs = rsqrt(fma(tt, tt, 1.0)), sn = cs * tt;
+                    for (int r = gl; 2 * r < pe; r += gs) {
+                        const double2 x = gi[r], y = gj[r];
+                        gi[r] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+                        gj[r] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+                    }
+                    double2* vi = reinterpret_cast<double2*>(V + i * ldq);
+                    double2* vj = reinterpret_cast<double2*>(V + j * ldq);
+                    for (int r = gl; 2 * r < qe_rows; r += gs) {
+                        const double2 x = vi[r], y = vj[r];
+                        vi[r] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+                        vj[r] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+                    }
+                    if (gl == 0 && c2q > 1e-16 * ab) *sh_rot = 1;
                 }
             }
             __syncthreads();
@@ -730,7 +840,7 @@ __host__ __device__ inline int64_t qr_sector_need(int64_t p, int64_t q) {
     const int64_t k = p < q ? p : q;
     return p * (q | 1) + 3 * k + k * q;
 }
-__host__ __device__ inline int64_t svd_sector_need(int64_t p, int64_t q) { return q * (p | 1) + q * (q | 1) + q; }
+__host__ __device__ inline int64_t svd_sector_need(int64_t p, int64_t q) { return q * (p + (p & 1)) + q * (q + (q & 1)) + q + (q & 1); }
 
 // kind: 0 = QR of M_s, 1 = LQ of M_s (QR of its transpose), 2 = SVD
 __global__ void __launch_bounds__(kSecThreads) sector_discover_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a,
@@ -890,7 +1000,7 @@ __global__ void __launch_bounds__(kQBigThreads) svd_work_kernel(const int64_t* _
         const bool tall = ms >= ns;
         const int p = tall ? ms : ns, q = tall ? ns : ms;
         const int K0 = g.kstart()[s];
-        const int ldp = p | 1, ldq = q | 1;
+        const int ldp = p + (p & 1), ldq = q + (q & 1);
         double* G = (svd_sector_need(p, q) <= cap) ? work : scratch + (int64_t)blockIdx.x * scratch_per_cta;
         double* V = G + (int64_t)q * ldp;
         double* sig = V + (int64_t)q * ldq;
@@ -899,8 +1009,9 @@ __global__ void __launch_bounds__(kQBigThreads) svd_work_kernel(const int64_t* _
             const double v = __ldg(A + (int64_t)rl[r] * n + cl[c]);
             if (tall) G[(int64_t)c * ldp + r] = v; else G[(int64_t)r * ldp + c] = v;
         }
+        if (p & 1) for (int c = tid; c < q; c += nt) G[(int64_t)c * ldp + p] = 0.0;
         __syncthreads();
-        jacobi_svd(G, ldp, V, ldq, p, q, &sh_rot);
+        jacobi_svd2(G, ldp, V, ldq, p, q, &sh_rot);
         for (int c = warp; c < q; c += nwarps) {
             double s2 = 0.0;
             for (int r = lane; r < p; r += 32) s2 += G[(int64_t)c * ldp + r] * G[(int64_t)c * ldp + r];
@@ -1071,7 +1182,7 @@ static int svd_queue_launch(const int64_t* sect, const int64_t* sh, const double
     const int64_t m = sh[0], n = sh[1], k = sh[2];
     const int64_t p = m >= n ? m : n, q = m >= n ? n : m;
     const int64_t full = svd_sector_need(p, q);
-    const int64_t per_cta = full > kQBigDoubles ? full + 8 : 0;
+    const int64_t per_cta = full > kQBigDoubles ? ((full + 9) & ~(int64_t)1) : 0;   // even: 16-byte aligned slices
     int64_t gstride, qcap;
     const int rc = queue_discover(sect, m, n, a, abs_, nb, 2, per_cta, kSMs, st, gstride, qcap);
     if (rc != 0) return rc;

@@ -12,7 +12,7 @@ def _nb(t):
 
 
 class KernelTimer:
-    CLASSES = ("pack", "gemm", "qr", "svd", "svd_cut", "norm", "scale", "binary", "unary", "gather_rows", "select", "grad_accumulate",
+    CLASSES = ("pack", "gemm", "gemm_gather", "qr", "svd", "svd_cut", "norm", "scale", "binary", "unary", "gather_rows", "select", "grad_accumulate",
                "diag_scatter", "block_sign", "svd_mask")
 
     def __init__(self, backend):
@@ -33,6 +33,11 @@ class KernelTimer:
             flops = float((2 * g[:, 0] * g[:, 1] * g[:, 2]).sum()) * nb
             by = 8.0 * (float((g[:, 0] * g[:, 2]).sum()) * _nb(a) + float((g[:, 2] * g[:, 1]).sum()) * _nb(b) + float((g[:, 0] * g[:, 1]).sum()) * nb)
             return by, flops
+        if name == "gemm_gather":
+            plan, a, b, c = args[:4]
+            _, _, m, n, k = plan.gather
+            nb = _nb(c)
+            return 8.0 * (m * k * _nb(a) + k * n * _nb(b) + m * n * nb), 2.0 * m * n * k * nb
         if name in ("qr", "svd"):
             plan, a = args[:2]
             s = plan.sectors
@@ -67,8 +72,8 @@ class KernelTimer:
                 e1.record()
                 by, fl = self._work(_name, args)
                 self.records[_name].append((e0, e1, by, fl))
-                if _name in ("gemm", "qr", "svd"):
-                    tab = args[0].gemm if _name == "gemm" else args[0].sectors
+                if _name in ("gemm", "gemm_gather", "qr", "svd"):
+                    tab = args[0].gemm if _name == "gemm" else ([args[0].gather[2:5]] if _name == "gemm_gather" else args[0].sectors)
                     sig = (_name, len(tab), tuple(int(x) for x in tab[0][:3]), int(args[-1].shape[0]))
                     self.shapes.setdefault(sig, []).append((e0, e1, fl, by))
                 return r
@@ -157,7 +162,7 @@ def roofline_of_dominant(breakdown, peaks, top_shapes=None, traffic_table=None):
                 traffic = t["dram_bytes_per_launch"]
                 extra["heaviest_shape"]["algorithmic_bytes_per_launch"] = t.get("algorithmic_bytes_per_launch")
                 extra["heaviest_shape"]["ncu_report"] = t.get("report")
-    if name == "gemm" and intensity > 6.0:
+    if name in ("gemm", "gemm_gather") and intensity > 6.0:
         peak = measure_fp64_gemm_tflops()
         ach = v["flops"] / sec / 1e12
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
