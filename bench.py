@@ -179,7 +179,9 @@ def run_own(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a short collective timeout: a rank that leaves the lock-step fails the run within minutes, not after NCCL's 10
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     from tnsp_b200 import backend
     import tnsp_b200.TAT as TAT
     from tnsp_b200 import dist as tdist
@@ -298,17 +300,20 @@ def run_own(args):
     e2e_value = nb * n_e2e * world / (float(t.item()) * 1e-3)
 
     # ---- roofline of the dominant kernel (instrumented pass, outside the timed regions) -----------
+    # every rank runs the same steps (the observer's exchange is a collective); only rank 0 instruments its kernels
     roofline, breakdown, top_shapes = None, None, None
+    n_prof = 3 if ms_max / args.steps < 2000 else 1
+    prof = None
+    step()
+    torch.cuda.synchronize()
     if rank == 0:
         from tnsp_b200 import profiling
         prof = profiling.KernelTimer(B)
-        n_prof = 3 if ms_max / args.steps < 2000 else 1
-        step()
-        torch.cuda.synchronize()
         prof.enable()
-        for _ in range(n_prof):
-            step()
-        torch.cuda.synchronize()
+    for _ in range(n_prof):
+        step()
+    torch.cuda.synchronize()
+    if rank == 0:
         prof.disable()
         breakdown = prof.summary()
         top_shapes = prof.shape_summary()

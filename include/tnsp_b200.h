@@ -96,6 +96,15 @@ int tnsp_svd_sectors_f64(const int64_t* sect, const int64_t* sect_host, const do
                          double* out1, int64_t o1_bstride, double* s, int64_t s_bstride, double* out2, int64_t o2_bstride,
                          double* work, int64_t w_bstride, int nb, void* stream);
 
+/* The same two factorisations with the m x n operand READ IN PLACE from a dense tensor of any index order: element (i, j)
+ * of the matrix is a[b * a_bstride + rc[i] + rc[m + j]] (int32 element offsets from the host planner).  Replaces the
+ * merge / transpose copy (edge_operator.hpp:651-688) in front of qr.hpp:309-508 / svd.hpp:259-538. */
+int tnsp_qr_sectors_gather_f64(const int64_t* sect, const int64_t* sect_host, const int32_t* rc, const double* a, int64_t a_bstride,
+                               double* out1, int64_t o1_bstride, double* out2, int64_t o2_bstride, int use_qr, int nb, void* stream);
+int tnsp_svd_sectors_gather_f64(const int64_t* sect, const int64_t* sect_host, const int32_t* rc, const double* a, int64_t a_bstride,
+                                double* out1, int64_t o1_bstride, double* s, int64_t s_bstride, double* out2, int64_t o2_bstride,
+                                double* work, int64_t w_bstride, int nb, void* stream);
+
 /* Tuning knob of the two entry points above: matrices with >= min_elems elements are factorised sector by
  * sector from a device-side work queue (several CTAs per SM), smaller ones by one CTA per chain.  Returns the
  * previous threshold; a negative argument only queries. */

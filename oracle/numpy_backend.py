@@ -100,9 +100,21 @@ class NumpyBackend:
     def qr_destroys_input(self, plan):
         return False
 
+    def factor_in_place(self, plan):
+        return len(plan.sectors) == 1 and int(plan.sectors[0][0]) * int(plan.sectors[0][1]) >= 2048
+
+    @staticmethod
+    def _gathered(plan, a):
+        """the merged matrix of every chain, read through the plan's offset table"""
+        m, n = int(plan.sectors[0][0]), int(plan.sectors[0][1])
+        ro, co = plan.rc_tab[:m].astype(np.int64), plan.rc_tab[m:].astype(np.int64)
+        return torch.from_numpy(np.ascontiguousarray(a.numpy()[:, (ro[:, None] + co[None, :]).reshape(-1)]))
+
     # K3
-    def qr(self, plan, a, out1, out2):
+    def qr(self, plan, a, out1, out2, in_place=False):
         self.launches += 1
+        if in_place:
+            a = self._gathered(plan, a)
         nb = a.shape[0]
         A, O1, O2 = a.numpy(), out1.numpy(), out2.numpy()
         for m, n, k, ao, o1, o2, _so, _ in plan.sectors:
@@ -132,8 +144,10 @@ class NumpyBackend:
                 O2[b, o2:o2 + k * n] = F2.reshape(-1)
 
     # K4
-    def svd(self, plan, a, out1, s, out2):
+    def svd(self, plan, a, out1, s, out2, in_place=False):
         self.launches += 1
+        if in_place:
+            a = self._gathered(plan, a)
         nb = a.shape[0]
         A, O1, S, O2 = a.numpy(), out1.numpy(), s.numpy(), out2.numpy()
         for m, n, k, ao, o1, o2, so, _ in plan.sectors:

@@ -23,6 +23,11 @@ CASES = [
     ("216x36x216 plain", (216, 216), (1,), (216, 36), (0,)),
     ("1296x2x1 outer", (1296, 1), (1,), (1, 2), (0,)),
     ("1296x36x6 plain", (1296, 6), (1,), (6, 36), (0,)),
+    ("36x36x216 plain", (36, 216), (1,), (216, 36), (0,)),
+    ("36x216x6 plain", (36, 6), (1,), (6, 216), (0,)),
+    ("36x36x36 plain", (36, 36), (1,), (36, 36), (0,)),
+    ("36x6x216 k-major", (216, 36), (0,), (216, 6), (0,)),
+    ("1x1x7776 dot", (7776,), (0,), (7776,), (0,)),
 ]
 
 

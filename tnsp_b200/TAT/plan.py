@@ -446,7 +446,7 @@ def _common_order(names_1, names_2, map12, map21, free_1, free_2, size_1, size_2
     return common_1, common_2, r1, r2
 
 
-GATHER_MIN_M = 48   # below this the small-tile grouped kernels (on packed operands) are used
+GATHER_MIN_M = 17   # up to 16 rows the one-warp-per-matrix / small-tile kernels (on packed operands) are used
 
 
 def _rowstream_fits(n, k):
@@ -644,7 +644,31 @@ class FactorPlan:
               matrix (row-major m x n), out1 = m x k, out2 = k x n.
     """
     __slots__ = ("merge", "sectors", "t1_names", "t1_edges", "t1_table", "t2_names", "t2_edges", "t2_table",
-                 "s_syms", "s_total", "flag", "extra", "_dev")
+                 "s_syms", "s_total", "flag", "extra", "_dev", "rc_tab", "_rcdev")
+
+
+def _merge_offsets(EdgeT, names, edges, rows_group, cols_group, merge):
+    """int32 table ro[m] | co[n]: element (i, j) of the merged matrix of a DENSE tensor is data[ro[i] + co[j]] (rows /
+    columns enumerate the two name groups row-major, the merge order of edge_operator.hpp:321-404 with one segment
+    per edge), so that qr / svd can read their operand in place (csrc/factor_sector.cu).  None when not applicable."""
+    if EdgeT.Symmetry.length != 0 or merge.identity:
+        return None
+    st, acc = [], 1
+    for e in reversed(edges):
+        st.append(acc)
+        acc *= e.dimension
+    st.reverse()
+    if acc >= 2**31 or acc == 0:
+        return None
+
+    def offsets(group):
+        o = np.zeros(1, dtype=np.int64)
+        for nm in group:
+            i = names.index(nm)
+            o = (o[:, None] + np.arange(edges[i].dimension, dtype=np.int64)[None, :] * st[i]).reshape(-1)
+        return o
+
+    return np.concatenate([offsets(rows_group), offsets(cols_group)]).astype(np.int32)
 
 
 def _factor_common(EdgeT, merged):
@@ -721,6 +745,8 @@ def svd_plan(EdgeT, names, edges, free_names_u, common_name_u, common_name_v):
     p._dev = None
     p.merge = edge_operator_plan(EdgeT, names, edges, None, rev_in, {SVD_U: list_u, SVD_V: list_v},
                                  [SVD_U, SVD_V] if put_v_right else [SVD_V, SVD_U])
+    p._rcdev = None
+    p.rc_tab = _merge_offsets(EdgeT, names, edges, list_u if put_v_right else list_v, list_v if put_v_right else list_u, p.merge)
     c1, c2 = _factor_common(EdgeT, p.merge)
     p.t1_names = (SVD_U, common_name_u) if put_v_right else (SVD_V, common_name_v)
     p.t1_edges = (p.merge.edges[0], c1)
@@ -807,6 +833,8 @@ def qr_plan(EdgeT, names, edges, direction, free_names, common_name_q, common_na
     p = FactorPlan()
     p._dev = None
     p.merge = edge_operator_plan(EdgeT, names, edges, None, rev_in, {QR_1: list_1, QR_2: list_2}, [QR_1, QR_2])
+    p._rcdev = None
+    p.rc_tab = _merge_offsets(EdgeT, names, edges, list_1, list_2, p.merge)
     c1, c2 = _factor_common(EdgeT, p.merge)
     p.t1_names = (QR_1, common_name_q if use_qr else common_name_r)
     p.t1_edges = (p.merge.edges[0], c1)

@@ -696,11 +696,12 @@ class Tensor:
         p = _cached(key, lambda: _plan.svd_plan(self.Edge, tuple(self.names), self._edges, free_u, common_name_u, common_name_v))
         STATS["svd"] += 1
         nb = self.data.shape[0]
-        merged = self._run_pack(p.merge)
+        in_place = p.rc_tab is not None and B.factor_in_place(p)   # operand read through offset tables: no merged copy
+        merged = self.data if in_place else self._run_pack(p.merge)
         t1 = B.zeros(nb, p.t1_table.size)
         t2 = B.zeros(nb, p.t2_table.size)
         s = B.zeros(nb, max(p.s_total, 1))
-        B.svd(p, merged, t1, s, t2)
+        B.svd(p, merged, t1, s, t2, in_place)
         ks = [int(r[2]) for r in p.sectors]
         ns = len(ks)
         if self.Symmetry.length == 0 and relative_cut == 0.0 and nb > 1:
@@ -743,12 +744,13 @@ class Tensor:
                                                 common_name_r))
         STATS["qr"] += 1
         nb = self.data.shape[0]
-        merged = self._run_pack(p.merge)
-        if merged is self.data and B.qr_destroys_input(p):
+        in_place = p.rc_tab is not None and B.factor_in_place(p)
+        merged = self.data if in_place else self._run_pack(p.merge)
+        if merged is self.data and not in_place and B.qr_destroys_input(p):
             merged = merged.clone()
         t1 = B.zeros(nb, p.t1_table.size)
         t2 = B.zeros(nb, p.t2_table.size)
-        B.qr(p, merged, t1, t2)
+        B.qr(p, merged, t1, t2, in_place)
         p1, p2 = p.extra
         r1 = self._make(p1.names, p1.edges, p1.table, self._run_pack(p1, t1))
         r2 = self._make(p2.names, p2.edges, p2.table, self._run_pack(p2, t2))

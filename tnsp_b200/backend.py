@@ -82,6 +82,8 @@ class CudaBackend:
         lib.tnsp_gemm_gather_f64.argtypes = [P, c_i64, c_i64, c_i64, c_int, c_dbl, P, c_i64, P, c_i64, P, c_i64, c_int, P]
         # contract of dense tensors reads its operands in place (no pack); tests switch it off to cover the packed path
         self.gather_gemm = True
+        lib.tnsp_qr_sectors_gather_f64.argtypes = [P, P, P, P, c_i64, P, c_i64, P, c_i64, c_int, c_int, P]
+        lib.tnsp_svd_sectors_gather_f64.argtypes = [P, P, P, P, c_i64, P, c_i64, P, c_i64, P, c_i64, P, c_i64, c_int, P]
         lib.tnsp_sector_queue_min.restype = c_i64
         lib.tnsp_sector_queue_min.argtypes = [c_i64]
         # set by tetragono.dense_embedding: single-descriptor factorisations discover their sectors on the device
@@ -168,9 +170,26 @@ class CudaBackend:
             dev = plan._dev = self.upload(plan.sectors)
         return dev
 
-    def qr(self, plan, a, out1, out2):
+    def factor_in_place(self, plan):
+        """qr / svd of a dense(-embedded) tensor can read the operand through the plan's offset table (no merged copy)
+        when the per-sector work-queue kernels apply"""
+        return (self.sector_discovery and self.gather_gemm and len(plan.sectors) == 1
+                and int(plan.sectors[0][0]) * int(plan.sectors[0][1]) >= int(self.lib.tnsp_sector_queue_min(-1)))
+
+    def _rc(self, plan):
+        dev = plan._rcdev
+        if dev is None:
+            dev = plan._rcdev = self.upload(plan.rc_tab)
+        return dev
+
+    def qr(self, plan, a, out1, out2, in_place=False):
         dev = self._sect(plan)
         nb = a.shape[0]
+        if in_place:
+            self._ck(self.lib.tnsp_qr_sectors_gather_f64(dev.data_ptr(), plan.sectors.ctypes.data, self._rc(plan).data_ptr(), a.data_ptr(),
+                                                         self._bs(a), out1.data_ptr(), out1.stride(0), out2.data_ptr(), out2.stride(0),
+                                                         int(plan.flag), nb, self._stream()))
+            return
         if self.sector_discovery and len(plan.sectors) == 1:
             self._ck(self.lib.tnsp_qr_sectors_f64(dev.data_ptr(), plan.sectors.ctypes.data, a.data_ptr(), a.stride(0), out1.data_ptr(),
                                                   out1.stride(0), out2.data_ptr(), out2.stride(0), int(plan.flag), nb, self._stream()))
@@ -179,11 +198,17 @@ class CudaBackend:
                                               out1.data_ptr(), out1.stride(0), out2.data_ptr(), out2.stride(0), int(plan.flag), nb,
                                               self._stream()))
 
-    def svd(self, plan, a, out1, s, out2):
+    def svd(self, plan, a, out1, s, out2, in_place=False):
         dev = self._sect(plan)
         nb = a.shape[0]
         wsize = int(self.lib.tnsp_svd_work_size(plan.sectors.ctypes.data, len(plan.sectors)))
         work = self.empty(nb, max(wsize, 1))
+        if in_place:
+            self._ck(self.lib.tnsp_svd_sectors_gather_f64(dev.data_ptr(), plan.sectors.ctypes.data, self._rc(plan).data_ptr(), a.data_ptr(),
+                                                          self._bs(a), out1.data_ptr(), out1.stride(0), s.data_ptr(), s.stride(0),
+                                                          out2.data_ptr(), out2.stride(0), work.data_ptr(), work.stride(0), nb,
+                                                          self._stream()))
+            return
         if self.sector_discovery and len(plan.sectors) == 1:
             self._ck(self.lib.tnsp_svd_sectors_f64(dev.data_ptr(), plan.sectors.ctypes.data, a.data_ptr(), a.stride(0), out1.data_ptr(),
                                                    out1.stride(0), s.data_ptr(), s.stride(0), out2.data_ptr(), out2.stride(0),

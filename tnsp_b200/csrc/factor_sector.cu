@@ -82,8 +82,10 @@ __device__ __forceinline__ int uf_find(const volatile int* parent, int x) {
     return r;
 }
 
+// ro / co (optional): element (i, j) of the matrix is A[ro[i] + co[j]] (operand read in place from a tensor of any
+// index order, see tnsp_qr_sectors_gather_f64); nullptr: plain row-major A[i * n + j].
 __device__ void discover_sectors(SecMap& sm, const double* __restrict__ A, int m, int n, int* sh_flag, uint32_t* masks,
-                                 int64_t mask_cap_words) {
+                                 int64_t mask_cap_words, const int* __restrict__ ro = nullptr, const int* __restrict__ co = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw = (n + 31) >> 5;
     int* parent = sm.colkey;
@@ -105,12 +107,15 @@ __device__ void discover_sectors(SecMap& sm, const double* __restrict__ A, int m
     // population count of every row; the row with the most columns among those starting at column f
     // becomes the representative of f
     for (int i = warp; i < m; i += kSecWarps) {
-        const double* row = A + (int64_t)i * n;
+        const double* row = A + (ro ? (int64_t)__ldg(ro + i) : (int64_t)i * n);
         int first = n, pc = 0;
         for (int w0 = 0; w0 < nw; w0 += 4) {
             double v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int j = ((w0 + u) << 5) + lane; v[u] = (j < n) ? __ldg(row + j) : 0.0; }
+            for (int u = 0; u < 4; ++u) {
+                const int j = ((w0 + u) << 5) + lane;
+                v[u] = (j < n) ? __ldg(row + (co ? __ldg(co + j) : j)) : 0.0;
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (w0 + u < nw) {
@@ -348,6 +353,222 @@ __device__ void householder_qr(double* W, int ld, int p, int q, int k, double* t
     }
     if (warp == 0 && k > 0) finalize(0);
     __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blocked Householder QR (LAPACK dgeqrf / dorgqr structure) for the work-queue kernel: panels of 8 columns are
+// factorised with the unblocked code above, the trailing columns are updated with the compact-WY block reflector
+//      A := (I - V T' V^T) A         Z = V^T A  (8 x 8, K = rows)   Y = T' Z   A -= V Y
+// on the FP64 tensor pipe (DMMA m8n8k4): the 8 reflectors of a panel are exactly the M = 8 of the instruction.
+// ncu of the unblocked kernel showed the column-by-column updates to be issue bound (~110 instructions per
+// column and step); a block update costs ~10 instructions per 8 x 8 sub-block.
+//   Vp : [P8][8] explicit reflectors of the current panel (unit diagonal, zeros above, zero padded rows), P8 = rows
+//        below j0 rounded up to 8;   Tm : [2][8][8] Gram matrix and triangular factor.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_f64(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// C fragment (row gid, cols 2 tig, 2 tig + 1) -> the two B fragments (rows tig / tig + 4, col gid) of the same 8 x 8 matrix
+__device__ __forceinline__ void cfrag_to_bfrag(double z0, double z1, int gid, int tig, double& b_lo, double& b_hi) {
+    const int src_lo = tig * 4 + (gid >> 1), src_hi = (tig + 4) * 4 + (gid >> 1);
+    const double l0 = __shfl_sync(0xffffffffu, z0, src_lo), l1 = __shfl_sync(0xffffffffu, z1, src_lo);
+    const double h0 = __shfl_sync(0xffffffffu, z0, src_hi), h1 = __shfl_sync(0xffffffffu, z1, src_hi);
+    b_lo = (gid & 1) ? l1 : l0;
+    b_hi = (gid & 1) ? h1 : h0;
+}
+
+// explicit reflectors of panel [j0, j0 + jb) and its triangular factor T (forward, columnwise: H_1 .. H_jb = I - V T V^T)
+__device__ void build_panel_vt(const double* W, int ld, int p, int j0, int jb, const double* tau, const double* scl, double* Vp,
+                               double* Tm) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int P8 = ((p - j0) + 7) & ~7;
+    for (int e = tid; e < P8 * 8; e += nthreads) {
+        const int i = e >> 3, jj = e & 7;
+        const int gi = j0 + i, gj = j0 + jj;
+        double v = 0.0;
+        if (jj < jb && gi < p) v = (gi == gj) ? 1.0 : (gi > gj ? W[gi * ld + gj] * scl[gj] : 0.0);
+        Vp[e] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double g0 = 0.0, g1 = 0.0;
+        for (int i0 = 0; i0 < P8; i0 += 4) {
+            const double a = Vp[(i0 + tig) * 8 + gid];
+            dmma_f64(g0, g1, a, a);                   // G = V^T V
+        }
+        double* Gs = Tm;          // [8][8]
+        double* T = Tm + 64;      // [8][8]
+        Gs[gid * 8 + 2 * tig] = g0;
+        Gs[gid * 8 + 2 * tig + 1] = g1;
+        __syncwarp();
+        if (lane < 8) {
+            // row `lane` of T: T[i][jj] = -tau_jj * sum_{l = i .. jj-1} T[i][l] G[l][jj]  (i < jj), T[jj][jj] = tau_jj
+            double row[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const double tj = jj < jb ? tau[j0 + jj] : 0.0;
+                double acc = 0.0;
+#pragma unroll
+                for (int l = 0; l < 8; ++l)
+                    if (l < jj && l >= lane) acc += row[l] * Gs[l * 8 + jj];
+                row[jj] = (lane == jj) ? tj : (lane < jj ? -tj * acc : 0.0);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) T[lane * 8 + jj] = row[jj];
+        }
+    }
+    __syncthreads();
+}
+
+// W[j0 : p, c_begin : c_end) := (I - V Tm V^T) W[...]  with Tm = T^T (transpose_t, factorisation) or T (forming Q)
+__device__ void block_reflect(double* W, int ld, int p, int j0, int c_begin, int c_end, const double* Vp, const double* Tm,
+                              bool transpose_t) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int P8 = ((p - j0) + 7) & ~7;
+    const double* T = Tm + 64;
+    // A fragments of the 8 x 8 factor: a(kk) = Tm'[gid][kk0 + tig]
+    const double t_lo = transpose_t ? T[tig * 8 + gid] : T[gid * 8 + tig];
+    const double t_hi = transpose_t ? T[(tig + 4) * 8 + gid] : T[gid * 8 + tig + 4];
+    for (int c0 = c_begin + 8 * warp; c0 < c_end; c0 += 8 * nwarps) {
+        const int cb = c0 + gid;                        // column of this lane's B fragments
+        const bool cb_ok = cb < c_end;
+        double z0 = 0.0, z1 = 0.0;
+        for (int i0 = 0; i0 < P8; i0 += 4) {
+            const int gi = j0 + i0 + tig;
+            const double a = Vp[(i0 + tig) * 8 + gid];
+            const double b = (cb_ok && gi < p) ? W[gi * ld + cb] : 0.0;
+            dmma_f64(z0, z1, a, b);                     // Z = V^T A
+        }
+        double b_lo, b_hi;
+        cfrag_to_bfrag(z0, z1, gid, tig, b_lo, b_hi);
+        double y0 = 0.0, y1 = 0.0;
+        dmma_f64(y0, y1, t_lo, b_lo);
+        dmma_f64(y0, y1, t_hi, b_hi);                   // Y = Tm' Z
+        cfrag_to_bfrag(-y0, -y1, gid, tig, b_lo, b_hi);
+        const int cc = c0 + 2 * tig;                    // columns of this lane's C fragment
+        for (int i0 = 0; i0 < P8; i0 += 8) {
+            const int gi = j0 + i0 + gid;
+            const bool r_ok = gi < p;
+            double* wr = W + gi * ld + cc;
+            double w0 = (r_ok && cc < c_end) ? wr[0] : 0.0;
+            double w1 = (r_ok && cc + 1 < c_end) ? wr[1] : 0.0;
+            dmma_f64(w0, w1, Vp[(i0 + gid) * 8 + tig], b_lo);
+            dmma_f64(w0, w1, Vp[(i0 + gid) * 8 + tig + 4], b_hi);   // A -= V Y
+            if (r_ok && cc < c_end) wr[0] = w0;
+            if (r_ok && cc + 1 < c_end) wr[1] = w1;
+        }
+    }
+}
+
+__host__ __device__ inline int64_t qr_blocked_extra(int64_t p) { return 8 * ((p + 7) & ~(int64_t)7) + 128; }
+
+__device__ void householder_qr_blocked(double* W, int ld, int p, int q, int k, double* tau, double* Rout, double* Vp, double* Tm) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+    double* scl = tau + k;
+    double* dia = tau + 2 * k;
+    auto make_reflector = [&](int j, double xnorm2) {
+        const double alpha = W[j * ld + j];
+        double tj = 0.0, scale = 0.0, beta = alpha;
+        if (xnorm2 != 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+            tj = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        if (lane == 0) { tau[j] = tj; scl[j] = scale; dia[j] = beta; }
+    };
+    for (int j0 = 0; j0 < k; j0 += 8) {
+        const int jb = (k - j0 < 8) ? k - j0 : 8, jend = j0 + jb;
+        if (warp == 0) {
+            double part = 0.0;
+            for (int i = j0 + 1 + lane; i < p; i += 32) { const double v = W[i * ld + j0]; part += v * v; }
+            make_reflector(j0, warp_sum(part));
+        }
+        __syncthreads();
+        for (int j = j0; j < jend; ++j) {
+            const double tj = tau[j], scale = scl[j];
+            const double* vj = W + j;
+            for (int c = j + 1 + warp; c < jend; c += nwarps) {
+                double* wc = W + c;
+                const bool next = (c == j + 1);
+                double part = 0.0;
+                if (tj != 0.0) {
+                    double w = 0.0;
+                    for (int i = j + 1 + lane; i < p; i += 32) w += vj[i * ld] * wc[i * ld];
+                    w = (warp_sum(w) * scale + wc[j * ld]) * tj;
+                    const double ws = w * scale;
+                    if (next) {
+                        for (int i = j + 1 + lane; i < p; i += 32) {
+                            const double nv = wc[i * ld] - ws * vj[i * ld];
+                            wc[i * ld] = nv;
+                            if (i > c) part += nv * nv;
+                        }
+                    } else {
+                        for (int i = j + 1 + lane; i < p; i += 32) wc[i * ld] -= ws * vj[i * ld];
+                    }
+                    __syncwarp();
+                    if (lane == 0) wc[j * ld] -= w;
+                } else if (next) {
+                    for (int i = c + 1 + lane; i < p; i += 32) { const double v = wc[i * ld]; part += v * v; }
+                }
+                if (next) {
+                    __syncwarp();
+                    make_reflector(c, warp_sum(part));
+                }
+            }
+            __syncthreads();
+        }
+        if (jend < q) {
+            build_panel_vt(W, ld, p, j0, jb, tau, scl, Vp, Tm);
+            block_reflect(W, ld, p, j0, jend, q, Vp, Tm, true);
+            __syncthreads();
+        }
+    }
+    for (int e = tid; e < k * q; e += nthreads) {
+        const int i = e / q, j = e - i * q;
+        Rout[e] = (j > i) ? W[i * ld + j] : (j == i ? dia[i] : 0.0);
+    }
+    __syncthreads();
+    auto finalize = [&](int j) {             // one warp; lanes own rows j + lane, j + lane + 32, ...
+        const double tj = tau[j];
+        const double f = -tj * scl[j];
+        double* wj = W + j;
+        for (int i = j + lane; i < p; i += 32) wj[i * ld] = (i == j) ? 1.0 - tj : wj[i * ld] * f;
+        for (int i = lane; i < j; i += 32) wj[i * ld] = 0.0;
+    };
+    for (int j0 = ((k - 1) >> 3) << 3; j0 >= 0; j0 -= 8) {
+        const int jb = (k - j0 < 8) ? k - j0 : 8, jend = j0 + jb;
+        if (jend < k) {
+            build_panel_vt(W, ld, p, j0, jb, tau, scl, Vp, Tm);
+            block_reflect(W, ld, p, j0, jend, k, Vp, Tm, false);
+            __syncthreads();
+        }
+        for (int j = jend - 1; j >= j0; --j) {
+            const double tj = tau[j], scale = scl[j];
+            const double* vj = W + j;
+            for (int c = j + 1 + warp; c < jend; c += nwarps) {
+                double* wc = W + c;
+                if (c == j + 1) { finalize(c); __syncwarp(); }
+                if (tj != 0.0) {
+                    double w = 0.0;
+                    for (int i = j + 1 + lane; i < p; i += 32) w += vj[i * ld] * wc[i * ld];
+                    w = (warp_sum(w) * scale + wc[j * ld]) * tj;
+                    const double ws = w * scale;
+                    for (int i = j + 1 + lane; i < p; i += 32) wc[i * ld] -= ws * vj[i * ld];
+                    __syncwarp();
+                    if (lane == 0) wc[j * ld] -= w;
+                }
+            }
+            __syncthreads();
+        }
+        if (warp == 0) finalize(j0);
+        __syncthreads();
+    }
 }
 
 // sect[8] = (m, n, k, a_off, out1_off, out2_off, -, -)
@@ -819,7 +1040,7 @@ constexpr int kQClasses = 3;                // 0: big (or spilling), 1: small & 
 // qctl layout: [0..2] item counts per class, [3] ticket of the big kernel, [4] ticket of the small kernel
 
 __host__ __device__ inline int gmap_smax(int m, int n) { return (m < n ? m : n) + 2; }
-__host__ __device__ inline int64_t gmap_stride(int m, int n) { return 2 + 5 * (int64_t)gmap_smax(m, n) + n + m; }
+__host__ __device__ inline int64_t gmap_stride(int m, int n) { return 2 + 5 * (int64_t)gmap_smax(m, n) + 2 * ((int64_t)n + m); }
 
 struct GMap {
     const int* base;
@@ -834,19 +1055,22 @@ struct GMap {
     __device__ const int* voff() const { return base + 2 + 4 * smax; }
     __device__ const int* collist() const { return base + 2 + 5 * smax; }
     __device__ const int* rowlist() const { return base + 2 + 5 * smax + n; }
+    // source offsets of the sorted columns / rows: element (rowlist[r], collist[c]) of the matrix is A[aoff_r[r] + aoff_c[c]]
+    __device__ const int* aoff_c(int m_) const { return base + 2 + 5 * smax + n + m_; }
+    __device__ const int* aoff_r(int m_) const { return base + 2 + 5 * smax + 2 * n + m_; }
 };
 
 __host__ __device__ inline int64_t qr_sector_need(int64_t p, int64_t q) {
     const int64_t k = p < q ? p : q;
-    return p * (q | 1) + 3 * k + k * q;
+    return p * (q | 1) + 3 * k + k * q + 8 * ((p + 7) & ~(int64_t)7) + 128;   // W | tau, scl, dia | R | panel reflectors | G, T
 }
 __host__ __device__ inline int64_t svd_sector_need(int64_t p, int64_t q) { return q * (p + (p & 1)) + q * (q + (q & 1)) + q + (q & 1); }
 
 // kind: 0 = QR of M_s, 1 = LQ of M_s (QR of its transpose), 2 = SVD
-__global__ void __launch_bounds__(kSecThreads) sector_discover_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a,
+__global__ void __launch_bounds__(kSecThreads, 4) sector_discover_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a,
                                                                       int64_t abs_, int nb, int kind, int64_t mask_cap_words,
                                                                       int* __restrict__ gmap, int64_t gstride, int* __restrict__ qctl,
-                                                                      int2* __restrict__ qitems, int64_t qcap) {
+                                                                      int2* __restrict__ qitems, int64_t qcap, const int* __restrict__ rc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int sh_flag[2];
     const int m = (int)sect[0], n = (int)sect[1];
@@ -857,14 +1081,25 @@ __global__ void __launch_bounds__(kSecThreads) sector_discover_kernel(const int6
     const int smax = gmap_smax(m, n);
     for (int b = blockIdx.x; b < nb; b += gridDim.x) {
         const double* A = a + (int64_t)b * abs_ + sect[3];
-        discover_sectors(sm, A, m, n, sh_flag, masks, mask_cap_words);
+        const int* ro = rc, *co = rc ? rc + m : nullptr;
+        discover_sectors(sm, A, m, n, sh_flag, masks, mask_cap_words, ro, co);
         const int S = sm.S;
         int* g = gmap + (int64_t)b * gstride;
         int* g_c = g + 2, *g_r = g_c + smax, *g_k = g_r + smax, *g_u = g_k + smax, *g_v = g_u + smax;
         int* g_cl = g_v + smax, *g_rl = g_cl + n;
         for (int s = tid; s <= S; s += kSecThreads) { g_c[s] = sm.cstart[s]; g_r[s] = sm.rstart[s]; g_k[s] = sm.kstart[s]; }
-        for (int j = tid; j < n; j += kSecThreads) g_cl[j] = sm.collist[j];
-        for (int i = tid; i < m; i += kSecThreads) g_rl[i] = sm.rowlist[i];
+        int* g_ac = g_rl + m, *g_ar = g_ac + n;
+        const int nc_used = sm.cstart[S], nr_used = sm.rstart[S];
+        for (int j = tid; j < n; j += kSecThreads) {
+            const int cj = sm.collist[j];
+            g_cl[j] = cj;
+            g_ac[j] = j < nc_used ? (co ? __ldg(co + cj) : cj) : 0;
+        }
+        for (int i = tid; i < m; i += kSecThreads) {
+            const int ri = sm.rowlist[i];
+            g_rl[i] = ri;
+            g_ar[i] = i < nr_used ? (ro ? __ldg(ro + ri) : ri * n) : 0;
+        }
         if (tid == 0) {
             g[0] = S;
             g[1] = sm.kstart[S];
@@ -939,19 +1174,24 @@ __global__ void __launch_bounds__(kQBigThreads) qr_work_kernel(const int64_t* __
         double* W = (need <= cap) ? work : scratch + (int64_t)blockIdx.x * scratch_per_cta;
         double* tau = W + (int64_t)p * ld;
         double* Rc = tau + 3 * ks;
+        double* Vp = Rc + (int64_t)ks * q;
+        double* Tm = Vp + 8 * ((p + 7) & ~7);
+        const int* ar = g.aoff_r(m) + r0;
+        const int* ac = g.aoff_c(m) + c0;
         if (use_qr) {
             for (int e = tid; e < ms * ns; e += nt) {
                 const int r = e / ns, c = e - r * ns;
-                W[(int64_t)r * ld + c] = __ldg(A + (int64_t)rl[r] * n + cl[c]);
+                W[(int64_t)r * ld + c] = __ldg(A + ((int64_t)ar[r] + ac[c]));
             }
         } else {
             for (int e = tid; e < ms * ns; e += nt) {
                 const int r = e / ns, c = e - r * ns;
-                W[(int64_t)c * ld + r] = __ldg(A + (int64_t)rl[r] * n + cl[c]);
+                W[(int64_t)c * ld + r] = __ldg(A + ((int64_t)ar[r] + ac[c]));
             }
         }
         __syncthreads();
-        householder_qr(W, ld, p, q, ks, tau, Rc, nullptr);
+        if (q > 8) householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm);
+        else householder_qr(W, ld, p, q, ks, tau, Rc, nullptr);
         if (use_qr) {
             for (int e = tid; e < ms * ks; e += nt) {
                 const int r = e / ks, t = e - r * ks;
@@ -1004,9 +1244,11 @@ __global__ void __launch_bounds__(kQBigThreads) svd_work_kernel(const int64_t* _
         double* G = (svd_sector_need(p, q) <= cap) ? work : scratch + (int64_t)blockIdx.x * scratch_per_cta;
         double* V = G + (int64_t)q * ldp;
         double* sig = V + (int64_t)q * ldq;
+        const int* ar = g.aoff_r(m) + r0;
+        const int* ac = g.aoff_c(m) + c0;
         for (int e = tid; e < ms * ns; e += nt) {
             const int r = e / ns, c = e - r * ns;
-            const double v = __ldg(A + (int64_t)rl[r] * n + cl[c]);
+            const double v = __ldg(A + ((int64_t)ar[r] + ac[c]));
             if (tall) G[(int64_t)c * ldp + r] = v; else G[(int64_t)r * ldp + c] = v;
         }
         if (p & 1) for (int c = tid; c < q; c += nt) G[(int64_t)c * ldp + p] = 0.0;
@@ -1127,7 +1369,7 @@ static int64_t queue_min_elems() {
 
 // common front end: sector discovery + queue fill.  Returns 0 ok, 1 error, -1 not applicable.
 static int queue_discover(const int64_t* sect, int64_t m, int64_t n, const double* a, int64_t abs_, int nb, int kind, int64_t per_cta_scratch,
-                          int big_grid, cudaStream_t st, int64_t& gstride, int64_t& qcap) {
+                          int big_grid, cudaStream_t st, int64_t& gstride, int64_t& qcap, const int* rc) {
     if (m > kSecMaxDim || n > kSecMaxDim) return -1;
     if (secmap_bytes(m, n) + 4096 > (int64_t)kSecSmemDoubles * 8) return -1;
     gstride = gmap_stride((int)m, (int)n);
@@ -1154,19 +1396,19 @@ static int queue_discover(const int64_t* sect, int64_t m, int64_t n, const doubl
     if (mask_bytes > room) { mask_bytes = 0; mask_cap_words = 0; }   // falls back to one dense sector
     const int grid = nb < 8 * kSMs ? nb : 8 * kSMs;
     sector_discover_kernel<<<grid, kSecThreads, secmap_bytes(m, n) + mask_bytes, st>>>(sect, a, abs_, nb, kind, mask_cap_words, g_qws.gmap,
-                                                                                       gstride, g_qws.qctl, g_qws.qitems, qcap);
+                                                                                       gstride, g_qws.qctl, g_qws.qitems, qcap, rc);
     return check_launch("tnsp sector discovery");
 }
 
 static int qr_queue_launch(const int64_t* sect, const int64_t* sh, const double* a, int64_t abs_, double* out1, int64_t o1bs, double* out2,
-                           int64_t o2bs, int use_qr, int nb, cudaStream_t st) {
+                           int64_t o2bs, int use_qr, int nb, cudaStream_t st, const int* rc = nullptr) {
     const int64_t m = sh[0], n = sh[1];
     const int64_t p = use_qr ? m : n, q = use_qr ? n : m;
     const int64_t full = qr_sector_need(p, q);   // the largest sector possible
     const int64_t per_cta = full > kQBigDoubles ? full + 8 : 0;
     int64_t gstride, qcap;
-    const int rc = queue_discover(sect, m, n, a, abs_, nb, use_qr ? 0 : 1, per_cta, kSMs, st, gstride, qcap);
-    if (rc != 0) return rc;
+    const int err = queue_discover(sect, m, n, a, abs_, nb, use_qr ? 0 : 1, per_cta, kSMs, st, gstride, qcap, rc);
+    if (err != 0) return err;
     if (full > kQSmallDoubles) {
         qr_work_kernel<<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, g_qws.gmap, gstride,
                                                                      g_qws.qctl, g_qws.qitems, qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
@@ -1178,14 +1420,15 @@ static int qr_queue_launch(const int64_t* sect, const int64_t* sh, const double*
 }
 
 static int svd_queue_launch(const int64_t* sect, const int64_t* sh, const double* a, int64_t abs_, double* out1, int64_t o1bs, double* s,
-                            int64_t sbs, double* out2, int64_t o2bs, double* work, int64_t wbs, int nb, cudaStream_t st) {
+                            int64_t sbs, double* out2, int64_t o2bs, double* work, int64_t wbs, int nb, cudaStream_t st,
+                            const int* rc = nullptr) {
     const int64_t m = sh[0], n = sh[1], k = sh[2];
     const int64_t p = m >= n ? m : n, q = m >= n ? n : m;
     const int64_t full = svd_sector_need(p, q);
     const int64_t per_cta = full > kQBigDoubles ? ((full + 9) & ~(int64_t)1) : 0;   // even: 16-byte aligned slices
     int64_t gstride, qcap;
-    const int rc = queue_discover(sect, m, n, a, abs_, nb, 2, per_cta, kSMs, st, gstride, qcap);
-    if (rc != 0) return rc;
+    const int err = queue_discover(sect, m, n, a, abs_, nb, 2, per_cta, kSMs, st, gstride, qcap, rc);
+    if (err != 0) return err;
     if (full > kQSmallDoubles) {
         svd_work_kernel<<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(sect, a, abs_, work, wbs, g_qws.gmap, gstride, g_qws.qctl, g_qws.qitems,
                                                                       qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
@@ -1288,4 +1531,28 @@ extern "C" int64_t tnsp_sector_queue_min(int64_t min_elems) {
     const int64_t old = queue_min_elems();
     if (min_elems >= 0) g_queue_min = min_elems;
     return old;
+}
+
+// The same factorisations with the m x n operand READ IN PLACE from a dense tensor of any index order: element (i, j)
+// of the matrix is a[b * abs + rc[i] + rc[m + j]] (int32 element offsets built by the host planner from the edge strides,
+// merge order of edge_operator.hpp:321-404).  Replaces the merge / transpose copy in front of qr.hpp:309-508 /
+// svd.hpp:259-538.  sect[3] (a_off) must be 0.  Always the work-queue path.
+extern "C" int tnsp_qr_sectors_gather_f64(const int64_t* sect, const int64_t* sect_host, const int32_t* rc, const double* a, int64_t abs_,
+                                          double* out1, int64_t o1bs, double* out2, int64_t o2bs, int use_qr, int nb, void* stream) {
+    if (nb == 0 || sect_host[0] * sect_host[1] == 0) return 0;
+    if (sect_host[0] > kSecMaxDim || sect_host[1] > kSecMaxDim) { set_error("tnsp_qr_sectors_gather_f64: matrix too large"); return 1; }
+    const int err = qr_queue_launch(sect, sect_host, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb, (cudaStream_t)stream, rc);
+    if (err < 0) { set_error("tnsp_qr_sectors_gather_f64: matrix too large for the discovered-sector kernels"); return 1; }
+    return err;
+}
+
+extern "C" int tnsp_svd_sectors_gather_f64(const int64_t* sect, const int64_t* sect_host, const int32_t* rc, const double* a, int64_t abs_,
+                                           double* out1, int64_t o1bs, double* s, int64_t sbs, double* out2, int64_t o2bs, double* work,
+                                           int64_t wbs, int nb, void* stream) {
+    if (nb == 0 || sect_host[0] * sect_host[1] == 0) return 0;
+    if (sect_host[0] > kSecMaxDim || sect_host[1] > kSecMaxDim) { set_error("tnsp_svd_sectors_gather_f64: matrix too large"); return 1; }
+    if (work == nullptr || wbs < svd_sector_work(sect_host[0], sect_host[1])) { set_error("tnsp_svd_sectors_gather_f64: scratch too small"); return 1; }
+    const int err = svd_queue_launch(sect, sect_host, a, abs_, out1, o1bs, s, sbs, out2, o2bs, work, wbs, nb, (cudaStream_t)stream, rc);
+    if (err < 0) { set_error("tnsp_svd_sectors_gather_f64: matrix too large for the discovered-sector kernels"); return 1; }
+    return err;
 }

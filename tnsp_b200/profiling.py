@@ -74,7 +74,7 @@ class KernelTimer:
                 self.records[_name].append((e0, e1, by, fl))
                 if _name in ("gemm", "gemm_gather", "qr", "svd"):
                     tab = args[0].gemm if _name == "gemm" else ([args[0].gather[2:5]] if _name == "gemm_gather" else args[0].sectors)
-                    sig = (_name, len(tab), tuple(int(x) for x in tab[0][:3]), int(args[-1].shape[0]))
+                    sig = (_name, len(tab), tuple(int(x) for x in tab[0][:3]), int(args[3 if _name.startswith('gemm') else 1].shape[0]))
                     self.shapes.setdefault(sig, []).append((e0, e1, fl, by))
                 return r
 
