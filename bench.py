@@ -28,7 +28,7 @@ WORKLOADS = {
     # name: dict(L1, L2, D, Dc, sym, J2, sr (SR natural gradient by CG with `cg` iterations per step), chains, desc)
     "cfg1": dict(L1=4, L2=4, D=4, Dc=16, sym="No", J2=0.0, sr=False, cg=0, chains=4096,
                  desc="tetragono sampling VMC 4x4 Heisenberg square lattice, no symmetry, D=4, Dc=16, float64"),
-    "cfg2": dict(L1=6, L2=6, D=6, Dc=36, sym="BoseU1", J2=0.5, sr=True, cg=20, chains=592,
+    "cfg2": dict(L1=6, L2=6, D=6, Dc=36, sym="BoseU1", J2=0.5, sr=True, cg=20, chains=1184,
                  desc="6x6 J1-J2 Heisenberg (J2=0.5) with U(1) symmetry, D=6 (2+2+2), Dc=36, sweep sampling + SR natural gradient (CG 20), float64"),
     "cfg2s": dict(L1=4, L2=4, D=3, Dc=9, sym="BoseU1", J2=0.5, sr=True, cg=4, chains=64,
                   desc="4x4 J1-J2 Heisenberg with U(1) symmetry, D=3, Dc=9, sweep + SR (smoke size of cfg2)"),
@@ -341,6 +341,7 @@ def run_own(args):
                        "l2": "working set of a step (all chains' environments) exceeds L2; no flush"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clock_info, "energy_per_site": energy[0],
+            "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated() / 1e9,
             "roofline": roofline, "kernel_breakdown": breakdown, "top_shapes": top_shapes,
         }
     return out

@@ -254,7 +254,8 @@ static int launch_gather(const int* tab, int m, int n, int k, int flags, double 
 // otherwise push the kernel past 128 registers (two 256-thread CTAs per SM need <= 128)
 template <int NT> struct RowstreamCfg { static constexpr int RKS = NT >= 6 ? 4 : 8; static constexpr int MINB = 2; };
 
-// grid (x: strip ranges of a chain, y: chain, z: slices of the n-passes); blockDim 128 or 256
+// grid (x: slices of the n-passes, y: chain, z: strip ranges of a chain) -- the slices of one strip range are launched
+// next to each other so that their re-reads of the same A rows hit L2; blockDim 128 or 256
 template <int NT>
 __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_kernel(const int* __restrict__ tab, int m, int n, int k, double alpha,
                                                              const double* __restrict__ a, int64_t abs_, const double* __restrict__ b,
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
     const double* B = b + (int64_t)bi * bbs;
     double* C = c + (int64_t)bi * cbs;
     const int kpad = (k + 3) & ~3;
-    const int pass_begin = blockIdx.z * passes_per_cta;
+    const int pass_begin = blockIdx.x * passes_per_cta;
     const int npass = min(passes_per_cta, npass_total - pass_begin);
     const int ncols = passes_per_cta * 8 * NT;
     const int ldb = ncols + 4;
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
     cp_async_commit();
 
     const int nstrips = (m + 15) >> 4;
-    const int s_begin = blockIdx.x * strips_per_cta;
+    const int s_begin = blockIdx.z * strips_per_cta;
     const int s_end = min(nstrips, s_begin + strips_per_cta);
     const int nchunk = (kpad / 4 + RKS - 1) / RKS;
     const int avail = s_end - s_begin - warp;
@@ -430,7 +431,7 @@ static int launch_rowstream(const int* tab, int m, int n, int k, double alpha, c
     ctas = (nstrips + strips_per_cta - 1) / strips_per_cta;
     const int slices = (npass + passes_per_cta - 1) / passes_per_cta;
     if (nb > 65535) { set_error("tnsp_gemm_gather_f64: more than 65535 chains"); return 1; }
-    gemm_rowstream_kernel<NT><<<dim3(ctas, nb, slices), threads, smem, st>>>(tab, m, n, k, alpha, a, abs_, b, bbs, c, cbs, npass, passes_per_cta,
+    gemm_rowstream_kernel<NT><<<dim3(slices, nb, ctas), threads, smem, st>>>(tab, m, n, k, alpha, a, abs_, b, bbs, c, cbs, npass, passes_per_cta,
                                                                              strips_per_cta);
     return check_launch("tnsp_gemm_gather_f64(rowstream)");
 }
