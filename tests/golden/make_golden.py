@@ -123,6 +123,44 @@ def dump_case(name, sym_name, lattice, Dc, config_points, seed, n_samples, cg_st
     print(name, "ws", arrays["ws"], "E_s", arrays["energy_s"], "traj E", arrays["traj_energy"], os.path.getsize(out), "bytes")
 
 
+def dump_driver_case(name, sym_name, lattice, Dc, config_points, seed, **kwargs):
+    """the reference's own optimisation loop (`gradient_descent`, sampling_lattice/gradient.py:93-445) from a fixed seed:
+    energy of every step and the PEPS tensors after the last update"""
+    arrays = {}
+    meta = {"symmetry": sym_name, "L1": lattice.L1, "L2": lattice.L2, "Dc": Dc,
+            "total_symmetry": sym_tuple(sym_name, lattice.total_symmetry)}
+    meta["physics_edges"] = [[{str(o): edge_desc(sym_name, e) for o, e in lattice.physics_edges[l1, l2].items()}
+                              for l2 in range(lattice.L2)] for l1 in range(lattice.L1)]
+    meta["hamiltonians"] = []
+    for i, (positions, h) in enumerate(lattice._hamiltonians.items()):
+        meta["hamiltonians"].append({"positions": [list(p) for p in positions], "tensor": tensor_desc(sym_name, h, arrays, f"ham_{i}")})
+    meta["sites"] = [[tensor_desc(sym_name, lattice[l1, l2], arrays, f"site_{l1}_{l2}") for l2 in range(lattice.L2)]
+                     for l1 in range(lattice.L1)]
+    conf = tet.sampling_lattice.Configuration(lattice, Dc)
+    for l1 in range(lattice.L1):
+        for l2 in range(lattice.L2):
+            for o, p in config_points[l1][l2].items():
+                conf[l1, l2, o] = p
+    start = conf.export_configuration()
+    arrays["start_configuration"] = np.array(start)
+    sampling_configurations = np.array(start)
+    TAT.random.seed(seed)
+    energies = []
+    from tetragono.sampling_lattice.gradient import gradient_descent as ref_gradient_descent
+    for whole, _ in ref_gradient_descent(lattice, sampling_method="sweep", configuration_cut_dimension=Dc,
+                                                          sampling_configurations=sampling_configurations, **kwargs):
+        energies.append(whole["energy"])
+    arrays["step_energy"] = np.array(energies)
+    arrays["last_configuration"] = np.array(sampling_configurations)
+    meta["final_sites"] = [[tensor_desc(sym_name, lattice[l1, l2], arrays, f"final_{l1}_{l2}") for l2 in range(lattice.L2)]
+                           for l1 in range(lattice.L1)]
+    meta["seed"], meta["kwargs"] = seed, kwargs
+    arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    out = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(out, **arrays)
+    print(name, "step energies", arrays["step_energy"], os.path.getsize(out), "bytes")
+
+
 def neel(lattice):
     S = lattice.Symmetry
     return [[{0: (S(), (l1 + l2) % 2)} for l2 in range(lattice.L2)] for l1 in range(lattice.L1)]
@@ -210,6 +248,18 @@ def hubbard_ff(L1, L2, D, T):
 
 
 def main():
+    if "driver" in sys.argv[1:]:
+        lat = heisenberg(3, 3, 2)
+        dump_driver_case("driver_heis_3x3_D2_Dc4_sr_momentum", "No", lat, 4, neel(lat), seed=21, sampling_total_step=12, grad_total_step=3,
+                         grad_step_size=0.002, use_natural_gradient=True, conjugate_gradient_method_step=2, momentum_parameter=0.5,
+                         use_fix_relative_step_size=True)
+        lat = heisenberg_u1(4, 4, 1)
+        dump_driver_case("driver_heisU1_4x4_d1_Dc6_line_search", "BoseU1", lat, 6, neel_u1(lat), seed=22, sampling_total_step=4,
+                         grad_total_step=2, grad_step_size=0.02, use_line_search=True)
+        lat = heisenberg(3, 3, 2)
+        dump_driver_case("driver_heis_3x3_D2_Dc4_plain", "No", lat, 4, neel(lat), seed=23, sampling_total_step=5, grad_total_step=3,
+                         grad_step_size=0.01, momentum_parameter=0.3, orthogonalize_momentum=True)
+        return
     if "j1j2" in sys.argv[1:]:
         lat = j1j2_u1(4, 4, 1, 0.5)
         hop = {k: v for k, v in lat._hamiltonians.items() if k[0][0] == k[1][0] or k[0][1] == k[1][1]}

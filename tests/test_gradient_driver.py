@@ -1,0 +1,76 @@
+"""The optimisation driver (`gradient_descent`) against the UNMODIFIED reference's own loop
+(sampling_lattice/gradient.py:93-445; fixtures `tests/golden/driver_*.npz` written by make_golden.py driver): same seed ->
+same Markov chains (configurations are integers: exact), energy of every step and the PEPS tensors after the last
+update within 1e-8 (three optimisation steps amplify the 1e-10 per-sample agreement)."""
+import numpy as np
+import pytest
+
+import tnsp_b200.TAT as TAT
+from golden_loader import DRIVER_CASES, build_lattice, load, tensor_from
+from tnsp_b200.tetragono.gradient import gradient_descent, lattice_dot
+
+
+@pytest.mark.parametrize("case", DRIVER_CASES)
+def test_driver_matches_reference_loop(case):
+    meta, z = load(case)
+    lat = build_lattice(meta, z)
+    conf = np.array(z["start_configuration"])
+    TAT.random.seed(meta["seed"])
+    energies = []
+    for whole, _ in gradient_descent(lat, sampling_method="sweep", configuration_cut_dimension=meta["Dc"], sampling_configurations=conf,
+                                     **meta["kwargs"]):
+        energies.append(whole["energy"])
+    want = z["step_energy"]
+    assert np.abs(np.array(energies) - want).max() <= 1e-8 * np.abs(want).max()
+    assert np.array_equal(conf, z["last_configuration"])
+    mod = getattr(TAT, meta["symmetry"])
+    for l1 in range(meta["L1"]):
+        for l2 in range(meta["L2"]):
+            t = tensor_from(mod, meta["final_sites"][l1][l2], z)
+            got, ref = np.asarray(lat[l1, l2].storage), np.asarray(t.storage)
+            assert np.abs(got - ref).max() <= 1e-8 * np.abs(ref).max()
+
+
+def test_driver_rejects_out_of_scope_options():
+    meta, z = load(DRIVER_CASES[0])
+    lat = build_lattice(meta, z)
+    for kw in ({"sampling_method": "direct"}, {"use_natural_gradient_by_direct_pseudo_inverse": True, "grad_step_size": 0.1},
+               {"fix_gauge": True}, {"save_state_file": "x"}, {"use_check_difference": True}):
+        with pytest.raises(NotImplementedError):
+            next(gradient_descent(lat, 1, 1, **{"sampling_configurations": np.array(z["start_configuration"]), **kw}))
+    with pytest.raises(ValueError):
+        next(gradient_descent(lat, 1, 1, sampling_method="nonsense"))
+
+
+def test_lockstep_driver_lowers_the_energy():
+    """8 chains in lock step, SR natural gradient, relative step: the energy estimated from 8 x 6 samples per step goes down"""
+    meta, z = load("driver_heis_3x3_D2_Dc4_plain")
+    lat = build_lattice(meta, z)
+    conf = np.array(z["start_configuration"])
+    TAT.random.seed(3)
+    energies = [whole["energy"][0] for whole, _ in gradient_descent(
+        lat, 48, 6, 0.1, chains=8, sampling_method="sweep", configuration_cut_dimension=4, sampling_configurations=conf,
+        use_natural_gradient=True, conjugate_gradient_method_step=4, use_fix_relative_step_size=True)]
+    assert len(energies) == 6 and np.all(np.isfinite(energies))
+    assert np.mean(energies[-2:]) < np.mean(energies[:2])
+    assert lattice_dot([[lat[0, 0]]], [[lat[0, 0]]]) > 0
+
+
+def test_ergodic_driver_energy_is_exact_expectation():
+    """ergodic enumeration through the driver = sum_s |psi(s)|^2 E_s / sum_s |psi(s)|^2 computed by brute force"""
+    meta, z = load("driver_heis_3x3_D2_Dc4_plain")
+    lat = build_lattice(meta, z)
+    (whole, _), = list(gradient_descent(lat, sampling_method="ergodic", configuration_cut_dimension=4))
+    from tnsp_b200.tetragono.observer import Observer
+    from tnsp_b200.tetragono.sampling import ErgodicSampling
+    s = ErgodicSampling(lat, 4)
+    num = den = 0.0
+    for _ in range(s.total_step):
+        p, c = s()
+        obs = Observer(lat, enable_energy=True)
+        with obs:
+            obs(p, c)
+        w = float(c.hole(()))**2
+        num += w * obs.total_energy[0]
+        den += w
+    assert abs(whole["energy"][0] - num / den) <= 1e-9 * abs(num / den)

@@ -93,7 +93,24 @@ class Copy:
         got = self._map.get(id(node))
         if got is not None:
             return got[1]
-        args = tuple(self._map[id(a)][1] if (isinstance(a, Node) and id(a) in self._map) else a for a in node._args)
+        # clone upstream nodes first, whatever order the caller walks the graph in: a clone must never keep an edge to
+        # a node of the ORIGINAL graph (it would silently follow the original's later updates)
+        stack = [node]
+        while stack:
+            cur = stack[-1]
+            if id(cur) in self._map:
+                stack.pop()
+                continue
+            missing = [a for a in cur._args if isinstance(a, Node) and id(a) not in self._map]
+            if missing:
+                stack.extend(missing)
+                continue
+            self._clone(cur)
+            stack.pop()
+        return self._map[id(node)][1]
+
+    def _clone(self, node):
+        args = tuple(self._map[id(a)][1] if isinstance(a, Node) else a for a in node._args)
         new = Node(node._func, *args)
         valid = True
         for n, o in zip(new.upstream(), node.upstream()):

@@ -330,11 +330,14 @@ class Observer:
             if error != 0.0 and b_square != 0 and error**2 > r_square / b_square:
                 break
             Dp = mv.n(p)
-            alpha = r_square / _dist.allreduce_number(float(torch.dot(Dp, Dp)))
+            # numpy scalars: 0 / 0 of a degenerate sample set gives nan like the reference's numpy arithmetic, no exception
+            with np.errstate(divide="ignore", invalid="ignore"):
+                alpha = float(np.float64(r_square) / np.float64(_dist.allreduce_number(float(torch.dot(Dp, Dp)))))
             x = x + alpha * p
             r = r - alpha * DT(Dp)
             new_r_square = float(torch.dot(r, r))
-            beta = new_r_square / r_square
+            with np.errstate(divide="ignore", invalid="ignore"):
+                beta = float(np.float64(new_r_square) / np.float64(r_square))
             r_square = new_r_square
             p = r + beta * p
             t += 1
@@ -370,11 +373,13 @@ class Observer:
             if error != 0.0 and b_square != 0 and error**2 > r_square / b_square:
                 break
             Dp = Delta @ p
-            alpha = r_square / _dist.allreduce_number(float(Dp @ Dp))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                alpha = float(np.float64(r_square) / np.float64(_dist.allreduce_number(float(Dp @ Dp))))
             x = x + alpha * p
             r = r - alpha * DT(Dp)
             new_r_square = float(r @ r)
-            beta = new_r_square / r_square
+            with np.errstate(divide="ignore", invalid="ignore"):
+                beta = float(np.float64(new_r_square) / np.float64(r_square))
             r_square = new_r_square
             p = r + beta * p
             t += 1
