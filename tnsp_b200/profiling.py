@@ -157,11 +157,23 @@ def roofline_of_dominant(breakdown, peaks, top_shapes=None, traffic_table=None):
             key = "%s:%s:%d" % (name, "x".join(str(x) for x in r["mnk"]), r["chains"])
             extra["heaviest_shape"] = {"mnk": r["mnk"], "chains": r["chains"], "launches": r["launches"], "ms": r["ms"],
                                        "achieved_gbs": r["gbs"], "achieved_tflops": r["tflops"]}
+            scale = 1.0
+            if traffic_table and key not in traffic_table:
+                # the ncu capture may have been taken at another chain count: DRAM bytes per launch are linear in the
+                # number of chains (every chain streams its own operands), scale and say so
+                prefix = key.rsplit(":", 1)[0] + ":"
+                other = [k for k in traffic_table if k.startswith(prefix)]
+                if other:
+                    scale = r["chains"] / float(other[0].rsplit(":", 1)[1])
+                    key = other[0]
             if traffic_table and key in traffic_table:
                 t = traffic_table[key]
-                traffic = t["dram_bytes_per_launch"]
-                extra["heaviest_shape"]["algorithmic_bytes_per_launch"] = t.get("algorithmic_bytes_per_launch")
+                traffic = t["dram_bytes_per_launch"] * scale
+                alg = t.get("algorithmic_bytes_per_launch")
+                extra["heaviest_shape"]["algorithmic_bytes_per_launch"] = alg * scale if alg is not None else None
                 extra["heaviest_shape"]["ncu_report"] = t.get("report")
+                if scale != 1.0:
+                    extra["heaviest_shape"]["traffic_scaled_from"] = key
     if name in ("gemm", "gemm_gather") and intensity > 6.0:
         peak = measure_fp64_gemm_tflops()
         ach = v["flops"] / sec / 1e12
