@@ -137,14 +137,17 @@ class Observer:
         self._total_log_ws += float(np.log(np.abs(ws_val[alive])).sum())
 
         no_symmetry = is_no_symmetry(owner.Tensor)
+        native = is_native(owner.Tensor)
         if not no_symmetry:
             inv_ws_conj = ws / (ws.norm_2()**2)
             all_name = {("T", "T")} | {(f"P_{l1}_{l2}_{orbit}",) * 2 for l1, l2 in owner.sites() for orbit in owner.physics_edges[l1, l2]}
         Es = None
         for name, observers in self._observer.items():
             whole = np.zeros(nb)
+            per_term = []
             for positions, observer in observers.items():
                 body = len(positions)
+                pending = []
                 table = element_table(observer, [owner.physics_edges[p] for p in positions])
                 cur = table.flatten([Configuration._index_by_point(table.edges[i], configuration[positions[i]]) for i in range(body)])
                 count = table.count[cur]
@@ -163,9 +166,14 @@ class Observer:
                     if wss is None:
                         raise NotImplementedError("not implemented replace style")
                     if no_symmetry:
-                        # <psi|s'> H_{s's} / <psi|s>  for real amplitudes
-                        with np.errstate(divide="ignore", invalid="ignore"):
-                            total += np.where(act, h * _values(wss) / ws_val, 0.0)
+                        # <psi|s'> H_{s's} / <psi|s>  for real amplitudes.  Device tensors: the amplitudes are only queued here
+                        # and read back ONCE per observable set (one device -> host copy instead of one blocking copy per
+                        # replaced configuration: the host keeps issuing kernels while the GPU works)
+                        if native:
+                            pending.append((act, h, wss))
+                        else:
+                            with np.errstate(divide="ignore", invalid="ignore"):
+                                total += np.where(act, h * _values(wss) / ws_val, 0.0)
                     else:
                         # tensor form keeps the fermionic signs of the P edges (observer.py:377-383); one chain
                         if float(wss.norm_max()) == 0:
@@ -179,6 +187,18 @@ class Observer:
                         value = (inv_ws_conj.contract(shrunk, {(pn[i], f"I{i}") for i in range(body)})
                                  .edge_rename({f"O{i}": pn[i] for i in range(body)}).contract(wss.conjugate(), all_name))
                         total += _values(value)
+                per_term.append((positions, total, pending))
+            if any(pend for _, _, pend in per_term):
+                import torch
+                flat = [w.data.reshape(-1).expand(nb) for _, _, pend in per_term for _, _, w in pend]
+                host = torch.stack(flat).cpu().numpy()      # [replaced configurations, nb]: the only read-back
+                row = 0
+                for _, total, pend in per_term:
+                    for act, h, _ in pend:
+                        with np.errstate(divide="ignore", invalid="ignore"):
+                            total += np.where(act, h * host[row] / ws_val, 0.0)
+                        row += 1
+            for positions, total, _ in per_term:
                 r, rr, rsr = self._result_reweight[name], self._result_reweight_square[name], self._result_square_reweight_square[name]
                 r[positions] += float((total * reweight).sum())
                 rr[positions] += float((total * reweight**2).sum())
