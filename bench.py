@@ -28,7 +28,7 @@ WORKLOADS = {
     # name: dict(L1, L2, D, Dc, sym, J2, sr (SR natural gradient by CG with `cg` iterations per step), chains, desc)
     "cfg1": dict(L1=4, L2=4, D=4, Dc=16, sym="No", J2=0.0, sr=False, cg=0, chains=4096,
                  desc="tetragono sampling VMC 4x4 Heisenberg square lattice, no symmetry, D=4, Dc=16, float64"),
-    "cfg2": dict(L1=6, L2=6, D=6, Dc=36, sym="BoseU1", J2=0.5, sr=True, cg=20, chains=1184,
+    "cfg2": dict(L1=6, L2=6, D=6, Dc=36, sym="BoseU1", J2=0.5, sr=True, cg=20, chains=2368,
                  desc="6x6 J1-J2 Heisenberg (J2=0.5) with U(1) symmetry, D=6 (2+2+2), Dc=36, sweep sampling + SR natural gradient (CG 20), float64"),
     "cfg2s": dict(L1=4, L2=4, D=3, Dc=9, sym="BoseU1", J2=0.5, sr=True, cg=4, chains=64,
                   desc="4x4 J1-J2 Heisenberg with U(1) symmetry, D=3, Dc=9, sweep + SR (smoke size of cfg2)"),
@@ -95,15 +95,77 @@ def _reference_worker(args):
     return n_samples, dt, obs.energy[0]
 
 
-def run_reference(workload, steps, warmup, samples_per_step, cores=None):
-    """returns dict(value, cores, kind, sample, ms_per_step)"""
+def _plan_flops_worker(args):
+    """GEMM flops of ONE sample (sweep + observe) as the contraction plans enumerate them: sum over sector GEMMs of 2 m n k
+    (SURVEY.md 8d).  Runs this repository's host planner on the CPU checker backend (oracle/, cpu_baseline leg only) twice:
+    on the block-symmetric U(1) tensors -- the reference's own sector plan -- and on their charge-dense embedding, which is
+    what the lock-step GPU engine executes."""
+    workload, = args
+    wl = WORKLOADS[workload]
+    from oracle import numpy_backend
+    numpy_backend.install()
+    from tnsp_b200 import backend
+    import tnsp_b200.TAT as tat
+    import tnsp_b200.TAT.random as rnd
+    from tnsp_b200.tetragono import dense_embedding, models
+    from tnsp_b200.tetragono.observer import Observer
+    from tnsp_b200.tetragono.sampling import SweepSampling
+    B = backend.get()
+    count = {"flops": 0.0}
+    gemm0, gather0 = B.gemm, B.gemm_gather
+
+    def gemm(plan, a, b, c):
+        count["flops"] += float(sum(2.0 * int(m) * int(n) * int(k) for m, n, k, *_ in plan.gemm))
+        return gemm0(plan, a, b, c)
+
+    def gemm_gather(plan, a, b, c):
+        _, _, m, n, k = plan.gather
+        count["flops"] += 2.0 * m * n * k
+        return gather0(plan, a, b, c)
+
+    B.gemm, B.gemm_gather = gemm, gemm_gather
+    sym_lat, hopping, points = build_workload(tat, wl)
+    out = {}
+    for which in ("sector_plan", "dense_embedding"):
+        if which == "sector_plan":
+            lat, hop = sym_lat, hopping
+            s = SweepSampling(lat, wl["Dc"], None, hop)
+            for l1, row in enumerate(points):
+                for l2, site in enumerate(row):
+                    for o, pt in site.items():
+                        s.configuration[l1, l2, o] = pt
+        else:
+            if wl["sym"] == "No":
+                out[which] = out["sector_plan"]
+                continue
+            lat = dense_embedding.embed_lattice(sym_lat)
+            hop = models.nearest_neighbour_terms(lat) if hopping is not None else None
+            s = SweepSampling(lat, wl["Dc"], None, hop)
+            s.configuration.import_configuration(dense_embedding.embed_configuration(sym_lat, points))
+        rnd.seed(4321)
+        obs = Observer(lat, enable_energy=True, enable_gradient=True)
+        with obs:                      # first sample: environments built from scratch
+            p, c = s()
+            obs(p, c)
+        count["flops"] = 0.0
+        with obs:                      # steady state: one sweep + one observation
+            p, c = s()
+            obs(p, c)
+        out[which] = count["flops"]
+    return out
+
+
+def run_reference(workload, steps, warmup, samples_per_step, cores=None, plan_flops=False):
+    """returns dict(value, cores, kind, sample, ms_per_step[, plan_flops])"""
     from oracle.ref import load_reference_tat  # noqa: F401  (checks availability in the parent too)
     import glob
     use_ref = bool(glob.glob(os.path.join(ROOT, "oracle", "_ref", "TAT*.so")))
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     per_step = []
+    flops = None
     with ctx.Pool(cores) as pool:
+        pending_flops = pool.apply_async(_plan_flops_worker, ((workload,),)) if plan_flops else None
         if use_ref:
             ok = pool.map(_probe_ref, range(1))[0]
             use_ref = ok
@@ -115,8 +177,13 @@ def run_reference(workload, steps, warmup, samples_per_step, cores=None):
             rate = sum(n / dt for n, dt, _ in res)
             if st >= warmup:
                 per_step.append((rate, wall))
+        if pending_flops is not None:
+            try:
+                flops = pending_flops.get(timeout=600)
+            except Exception as e:   # the count is a report, never a reason to lose the bench line
+                flops = {"error": repr(e)}
     value = float(np.mean([r for r, _ in per_step]))
-    return {"value": value, "unit": "samples/s", "cores": cores, "kind": "reference" if use_ref else "port",
+    return {"value": value, "plan_flops": flops, "unit": "samples/s", "cores": cores, "kind": "reference" if use_ref else "port",
             "sample": f"{samples_per_step} samples per chain x {cores} independent chains (one per host core, 1 BLAS thread each) per step, "
                       f"{steps} steps, workload {workload}",
             "ms_per_step": float(np.mean([w for _, w in per_step]) * 1e3)}
@@ -377,8 +444,21 @@ def main():
     out = run_own(args)
     if rank == 0:
         if not args.no_cpu_baseline and int(os.environ.get("WORLD_SIZE", "1")) == 1:
-            r = run_reference(args.workload, 2, 1, args.ref_samples)
+            r = run_reference(args.workload, 2, 1, args.ref_samples, plan_flops=True)
             out["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            pf = r.get("plan_flops")
+            if pf and "sector_plan" in pf and out.get("roofline") and out["roofline"].get("unit") == "TFLOP/s":
+                # the roofline's `achieved` counts the flops the kernels execute (dense plan, SURVEY.md 8d quotes the dense
+                # figure for this lattice); the block-sparse U(1) plan of the reference needs fewer: report that too
+                rf = out["roofline"]
+                ratio = pf["sector_plan"] / pf["dense_embedding"] if pf.get("dense_embedding") else None
+                rf["plan_flops_per_sample"] = {"reference_sector_plan": pf["sector_plan"], "dense_embedding_executed": pf["dense_embedding"],
+                                               "sector_over_dense": ratio,
+                                               "note": "GEMM flops of one steady-state sample (sweep + observe) counted by the host planner on the "
+                                                       "CPU checker; achieved x sector_over_dense = throughput in reference-plan flops"}
+                if ratio:
+                    rf["achieved_sector_plan"] = rf["achieved"] * ratio
+                    rf["frac_sector_plan"] = rf["frac"] * ratio
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out))
