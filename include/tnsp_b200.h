@@ -110,6 +110,11 @@ int tnsp_svd_sectors_gather_f64(const int64_t* sect, const int64_t* sect_host, c
  * previous threshold; a negative argument only queries. */
 int64_t tnsp_sector_queue_min(int64_t min_elems);
 
+/* Descriptor-driven sectors beyond the warp class go through blocked Householder on the FP64 tensor pipe and a
+ * QR-preconditioned Jacobi (factor_sector.cu); enable = 0 selects the first-generation column-by-column kernels
+ * (kept for differential tests), < 0 only queries.  Returns the previous setting. */
+int tnsp_factor_desc_kernels(int enable);
+
 /* ---- greedy cross-sector truncation (svd.hpp:429-481): counts[b][i] = kept values of sector i. */
 int tnsp_svd_cut_f64(const int64_t* sect, int ns, int64_t s_total, const double* s, int64_t s_bstride,
                      int64_t remain_cut, double relative_cut, int32_t* counts, int nb, void* stream);

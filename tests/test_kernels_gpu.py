@@ -85,7 +85,8 @@ def _factor_plan(shapes, flag):
     return p, ao, o1, o2, so
 
 
-@pytest.mark.parametrize("shapes", [[(16, 16), (4, 64), (64, 4)], [(64, 16), (16, 64), (1, 1), (5, 3)], [(216, 36)], [(40, 200), (180, 170)]])
+@pytest.mark.parametrize("shapes", [[(16, 16), (4, 64), (64, 4)], [(64, 16), (16, 64), (1, 1), (5, 3)], [(216, 36)], [(40, 200), (180, 170)],
+                                    [(900, 120), (120, 900), (300, 300), (70, 50), (9, 7)], [(2100, 260), (33, 1500)]])
 @pytest.mark.parametrize("use_qr", [True, False])
 def test_batched_qr(shapes, use_qr):
     cu, _ = _both()
@@ -110,7 +111,8 @@ def test_batched_qr(shapes, use_qr):
                 assert np.abs(np.triu(F1, 1)).max() == 0.0
 
 
-@pytest.mark.parametrize("shapes", [[(16, 16), (4, 64), (64, 4)], [(64, 16), (16, 64), (1, 1), (5, 3)], [(36, 216)], [(150, 120), (60, 60)]])
+@pytest.mark.parametrize("shapes", [[(16, 16), (4, 64), (64, 4)], [(64, 16), (16, 64), (1, 1), (5, 3)], [(36, 216)], [(150, 120), (60, 60)],
+                                    [(900, 100), (100, 900), (130, 130), (70, 50), (9, 7)], [(1500, 210), (40, 1200)]])
 def test_batched_svd_and_cut(shapes):
     cu, ck = _both()
     p, ao, o1, o2, so = _factor_plan(shapes, True)
@@ -381,3 +383,39 @@ def test_factor_operand_read_in_place(shape, discovery):
             got = np.sort(np.diag(sv[b].reshape(k, k)))[::-1]
             assert np.abs(got - ref).max() <= 1e-12 * ref.max()
     tt._PLAN_CACHE.clear()
+
+
+@pytest.mark.parametrize("shapes", [[(400, 90), (90, 400), (64, 64)], [(150, 120), (60, 60)]])
+def test_descriptor_kernels_agree_with_first_generation(shapes):
+    """blocked Householder / QR-preconditioned Jacobi against the column-by-column kernels they replace, plus a rank-deficient
+    sector (zero columns): same singular values, both reconstruct"""
+    cu, _ = _both()
+    p, ao, o1, o2, so = _factor_plan(shapes, True)
+    nb = 2
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal((nb, ao))
+    m0, n0 = shapes[0]
+    a[:, :m0 * n0].reshape(nb, m0, n0)[:, :, : n0 // 3] = 0.0          # a third of the first sector's columns vanish
+    out = {}
+    old = cu.lib.tnsp_factor_desc_kernels(-1)
+    try:
+        for gen in (0, 1):
+            cu.lib.tnsp_factor_desc_kernels(gen)
+            t1, t2, s = cu.zeros(nb, o1), cu.zeros(nb, o2), cu.zeros(nb, so)
+            cu.svd(p, cu.from_numpy(a), t1, s, t2)
+            q1, q2 = cu.zeros(nb, o1), cu.zeros(nb, o2)
+            cu.qr(p, cu.from_numpy(a.copy()), q1, q2)
+            out[gen] = [cu.to_numpy(x) for x in (t1, s, t2, q1, q2)]
+    finally:
+        cu.lib.tnsp_factor_desc_kernels(old)
+    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-12 * np.abs(out[0][1]).max()
+    for gen in (0, 1):
+        T1, S, T2, Q1, Q2 = out[gen]
+        for (m, n, k, a_off, x1, x2, xs, _) in p.sectors:
+            for b in range(nb):
+                M = a[b, a_off:a_off + m * n].reshape(m, n)
+                U, Vt, sv = T1[b, x1:x1 + m * k].reshape(m, k), T2[b, x2:x2 + k * n].reshape(k, n), S[b, xs:xs + k]
+                assert np.abs((U * sv) @ Vt - M).max() <= 1e-12 * max(1.0, sv.max()) * max(m, n)
+                assert np.all(np.diff(sv) <= 0)
+                Q, R = Q1[b, x1:x1 + m * k].reshape(m, k), Q2[b, x2:x2 + k * n].reshape(k, n)
+                assert np.abs(Q @ R - M).max() <= 1e-12 * max(1.0, np.abs(M).max()) * max(m, n)

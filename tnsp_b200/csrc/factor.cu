@@ -571,6 +571,19 @@ int tnsp_qr_sector_launch(const int64_t* sect, const int64_t* sh, const double* 
 int64_t tnsp_svd_sector_work(int64_t m, int64_t n);
 int tnsp_svd_sector_launch(const int64_t* sect, const int64_t* sh, const double* a, int64_t abs_, double* out1, int64_t o1bs,
                            double* s, int64_t sbs, double* out2, int64_t o2bs, double* work, int64_t wbs, int nb, cudaStream_t st);
+// factor_sector.cu: descriptor-driven sectors beyond the warp class (blocked Householder on the tensor pipe, QR-preconditioned Jacobi)
+int tnsp_qr_desc_launch(const int64_t* sect, const int64_t* sh, int ns, const double* a, int64_t abs_, double* out1, int64_t o1bs,
+                        double* out2, int64_t o2bs, int use_qr, int nb, cudaStream_t st);
+int tnsp_svd_desc_launch(const int64_t* sect, const int64_t* sh, int ns, const double* a, int64_t abs_, double* out1, int64_t o1bs,
+                         double* s, int64_t sbs, double* out2, int64_t o2bs, int nb, cudaStream_t st);
+
+// the first-generation column-by-column kernels stay selectable for differential tests (tnsp_factor_desc_kernels(0))
+static int g_desc_kernels = 1;
+extern "C" int tnsp_factor_desc_kernels(int enable) {
+    const int old = g_desc_kernels;
+    if (enable >= 0) g_desc_kernels = enable;
+    return old;
+}
 
 extern "C" int tnsp_qr_batched_f64(const int64_t* sect, int ns, const int64_t* sh, double* a, int64_t abs_, double* out1, int64_t o1bs,
                                    double* out2, int64_t o2bs, int use_qr, int nb, void* stream) {
@@ -603,6 +616,10 @@ extern "C" int tnsp_qr_batched_f64(const int64_t* sect, int ns, const int64_t* s
     }
     if (ns == 1) {
         const int rc = tnsp_qr_sector_launch(sect, sh, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
+    if (g_desc_kernels) {
+        const int rc = tnsp_qr_desc_launch(sect, sh, ns, a, abs_, out1, o1bs, out2, o2bs, use_qr, nb, (cudaStream_t)stream);
         if (rc >= 0) return rc;
     }
     const int gy = nb > 65535 ? 65535 : nb;
@@ -669,6 +686,10 @@ extern "C" int tnsp_svd_batched_f64(const int64_t* sect, int ns, const int64_t* 
     }
     if (ns == 1) {
         const int rc = tnsp_svd_sector_launch(sect, sh, a, abs_, out1, o1bs, s, sbs, out2, o2bs, work, wbs, nb, st);
+        if (rc >= 0) return rc;
+    }
+    if (g_desc_kernels) {
+        const int rc = tnsp_svd_desc_launch(sect, sh, ns, a, abs_, out1, o1bs, s, sbs, out2, o2bs, nb, st);
         if (rc >= 0) return rc;
     }
     const int gy = nb > 65535 ? 65535 : nb;

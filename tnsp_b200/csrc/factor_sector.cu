@@ -23,6 +23,9 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include <algorithm>
+#include <utility>
+#include <vector>
 
 namespace tnsp {
 
@@ -1476,9 +1479,338 @@ static int svd_queue_launch(const int64_t* sect, const int64_t* sh, const double
 static double* g_qr_scratch = nullptr;
 static int64_t g_qr_scratch_cap = 0;
 
+
+// ------------------------------------------------------------------------------------------------
+// Descriptor-driven sectors beyond the warp class (block-symmetric tensors whose sector shapes the plan names:
+// cfg3 - cfg5, several hundred to several thousand rows).  The first kernels for these (factor.cu: qr_kernel,
+// svd_kernel) worked column by column out of a global scratch: 9 GB/s for the qr and 2 GB/s for the svd of cfg5.
+// Here one (sector, chain) item at a time goes through the blocked Householder code of the work-queue kernel (panel
+// of 8 columns, compact-WY trailing update on the FP64 tensor pipe); the svd of a sector that does not fit shared
+// memory is preconditioned by that QR (X = Q R, one-sided Jacobi on the small triangular factor, U = Q U_R on the
+// tensor pipe), so the Jacobi sweeps run on q x q instead of p x q.
+// Items are dealt round-robin in the host's order (largest sector shape first, chains of one shape adjacent).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kQBigThreads) qr_desc_kernel(const int64_t* __restrict__ sect, const int* __restrict__ order, int nsel,
+                                                              const double* __restrict__ a, int64_t abs_, double* __restrict__ out1,
+                                                              int64_t o1bs, double* __restrict__ out2, int64_t o2bs, int use_qr, int nb,
+                                                              int64_t cap, double* __restrict__ scratch, int64_t scratch_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* work = reinterpret_cast<double*>(smem_raw);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int64_t total = (int64_t)nsel * nb;
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+        const int64_t* sc = sect + (int64_t)order[item / nb] * TNSP_SECT_COLS;
+        const int b = (int)(item % nb);
+        const int m = (int)sc[0], n = (int)sc[1], k = (int)sc[2];
+        const double* A = a + (int64_t)b * abs_ + sc[3];
+        double* O1 = out1 + (int64_t)b * o1bs + sc[4];   // m x k
+        double* O2 = out2 + (int64_t)b * o2bs + sc[5];   // k x n
+        const int p = use_qr ? m : n, q = use_qr ? n : m;
+        const int ks = p < q ? p : q;                     // == k
+        const int ld = q | 1;
+        const int64_t need = qr_sector_need(p, q);
+        double* W = (need <= cap) ? work : scratch + (int64_t)blockIdx.x * scratch_per_cta;
+        double* tau = W + (int64_t)p * ld;
+        double* Rc = tau + 3 * ks;
+        double* Vp = Rc + (int64_t)ks * q;
+        double* Tm = Vp + 8 * ((p + 7) & ~7);
+        if (use_qr) {
+            for (int e = tid; e < m * n; e += nt) { const int r = e / n, c = e - r * n; W[(int64_t)r * ld + c] = __ldg(A + e); }
+        } else {
+            for (int e = tid; e < m * n; e += nt) { const int r = e / n, c = e - r * n; W[(int64_t)c * ld + r] = __ldg(A + e); }
+        }
+        __syncthreads();
+        if (q > 8) householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm);
+        else householder_qr(W, ld, p, q, ks, tau, Rc, nullptr);
+        if (use_qr) {
+            for (int e = tid; e < m * k; e += nt) { const int r = e / k, t = e - r * k; O1[e] = W[(int64_t)r * ld + t]; }
+            for (int e = tid; e < k * n; e += nt) O2[e] = Rc[e];
+        } else {
+            for (int e = tid; e < m * k; e += nt) { const int r = e / k, t = e - r * k; O1[e] = Rc[(int64_t)t * q + r]; }
+            for (int e = tid; e < k * n; e += nt) { const int t = e / n, c = e - t * n; O2[e] = W[(int64_t)c * ld + t]; }
+        }
+        __syncthreads();
+    }
+}
+
+// room of the Jacobi stage of the preconditioned svd: G2 (q x ldq), V (q x ldq), sigma, ranks
+__host__ __device__ inline int64_t svd_desc_small_need(int64_t q) { const int64_t ldq = q + (q & 1); return 2 * q * ldq + 2 * ldq; }
+// whole footprint of one item in the preconditioned path: the QR working set, then the Jacobi stage
+__host__ __device__ inline int64_t svd_desc_pre_need(int64_t p, int64_t q) { return ((qr_sector_need(p, q) + 1) & ~(int64_t)1) + svd_desc_small_need(q); }
+// direct path (everything in shared memory): G (q x ldp), V (q x ldq), sigma, ranks
+__host__ __device__ inline int64_t svd_desc_direct_need(int64_t p, int64_t q) { return svd_sector_need(p, q) + q + (q & 1) + 2; }
+
+__global__ void __launch_bounds__(kQBigThreads) svd_desc_kernel(const int64_t* __restrict__ sect, const int* __restrict__ order, int nsel,
+                                                               const double* __restrict__ a, int64_t abs_, double* __restrict__ out1,
+                                                               int64_t o1bs, double* __restrict__ sv, int64_t sbs, double* __restrict__ out2,
+                                                               int64_t o2bs, int nb, int64_t cap, double* __restrict__ scratch,
+                                                               int64_t scratch_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int sh_rot;
+    double* work = reinterpret_cast<double*>(smem_raw);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int64_t total = (int64_t)nsel * nb;
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+        const int64_t* sc = sect + (int64_t)order[item / nb] * TNSP_SECT_COLS;
+        const int b = (int)(item % nb);
+        const int m = (int)sc[0], n = (int)sc[1], k = (int)sc[2];
+        const double* A = a + (int64_t)b * abs_ + sc[3];
+        double* O1 = out1 + (int64_t)b * o1bs + sc[4];   // m x k
+        double* O2 = out2 + (int64_t)b * o2bs + sc[5];   // k x n
+        double* S = sv + (int64_t)b * sbs + sc[6];
+        const bool tall = m >= n;
+        const int p = tall ? m : n, q = tall ? n : m;     // X (p x q) = M or M^T, q == k
+        const int ldp = p + (p & 1), ldq = q + (q & 1);
+        double* gscr = scratch + (int64_t)blockIdx.x * scratch_per_cta;
+        if (svd_desc_direct_need(p, q) <= cap) {
+            // ---- whole sector in shared memory: Jacobi on X itself ----
+            double* G = work;
+            double* V = G + (int64_t)q * ldp;
+            double* sig = V + (int64_t)q * ldq;
+            int* rnk = reinterpret_cast<int*>(sig + ldq);
+            for (int e = tid; e < m * n; e += nt) {
+                const int r = e / n, c = e - r * n;
+                const double v = __ldg(A + e);
+                if (tall) G[(int64_t)c * ldp + r] = v; else G[(int64_t)r * ldp + c] = v;
+            }
+            if (p & 1) for (int c = tid; c < q; c += nt) G[(int64_t)c * ldp + p] = 0.0;
+            __syncthreads();
+            jacobi_svd2(G, ldp, V, ldq, p, q, &sh_rot);
+            for (int c = warp; c < q; c += nwarps) {
+                double s2 = 0.0;
+                for (int r = lane; r < p; r += 32) s2 += G[(int64_t)c * ldp + r] * G[(int64_t)c * ldp + r];
+                s2 = warp_sum(s2);
+                if (lane == 0) sig[c] = sqrt(s2);
+            }
+            __syncthreads();
+            for (int c = tid; c < q; c += nt) {
+                const double s = sig[c];
+                int r = 0;
+                for (int o = 0; o < q; ++o) { const double so = sig[o]; r += (so > s) || (so == s && o < c); }
+                rnk[c] = r;
+            }
+            __syncthreads();
+            for (int c = tid; c < q; c += nt) S[rnk[c]] = sig[c];
+            // tall: U[r][j] = G[c][r] / sigma_c, Vt[j][t] = V[c][t];  wide: U[t][j] = V[c][t], Vt[j][r] = G[c][r] / sigma_c
+            for (int e = tid; e < q * p; e += nt) {
+                const int r = e / q, c = e - r * q;         // r: long index (0 .. p), c: column of X
+                const double s = sig[c];
+                const double v = s > 0.0 ? G[(int64_t)c * ldp + r] / s : 0.0;
+                if (tall) O1[(int64_t)r * k + rnk[c]] = v; else O2[(int64_t)rnk[c] * n + r] = v;
+            }
+            for (int e = tid; e < q * q; e += nt) {
+                const int c = e / q, t = e - c * q;
+                const double v = V[(int64_t)c * ldq + t];
+                if (tall) O2[(int64_t)rnk[c] * n + t] = v; else O1[(int64_t)t * k + rnk[c]] = v;
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- preconditioned: X = Q R (blocked Householder out of the global scratch), Jacobi on R ----
+        const int ld = q | 1;
+        double* W = gscr;
+        double* tau = W + (int64_t)p * ld;
+        double* Rc = tau + 3 * q;
+        double* Vp = Rc + (int64_t)q * q;
+        double* Tm = Vp + 8 * ((p + 7) & ~7);
+        double* small = (svd_desc_small_need(q) <= cap) ? work : gscr + ((qr_sector_need(p, q) + 1) & ~(int64_t)1);
+        double* G2 = small;                                  // column c of R at G2[c * ldq]
+        double* V = G2 + (int64_t)q * ldq;
+        double* sig = V + (int64_t)q * ldq;
+        int* rnk = reinterpret_cast<int*>(sig + ldq);
+        for (int e = tid; e < m * n; e += nt) {
+            const int r = e / n, c = e - r * n;
+            const double v = __ldg(A + e);
+            if (tall) W[(int64_t)r * ld + c] = v; else W[(int64_t)c * ld + r] = v;
+        }
+        __syncthreads();
+        if (q > 8) householder_qr_blocked(W, ld, p, q, q, tau, Rc, Vp, Tm);
+        else householder_qr(W, ld, p, q, q, tau, Rc, nullptr);
+        for (int e = tid; e < q * ldq; e += nt) {
+            const int c = e / ldq, r = e - c * ldq;
+            G2[e] = r < q ? Rc[(int64_t)r * q + c] : 0.0;
+        }
+        __syncthreads();
+        jacobi_svd2(G2, ldq, V, ldq, q, q, &sh_rot);
+        for (int c = warp; c < q; c += nwarps) {
+            double s2 = 0.0;
+            for (int r = lane; r < q; r += 32) s2 += G2[(int64_t)c * ldq + r] * G2[(int64_t)c * ldq + r];
+            s2 = warp_sum(s2);
+            if (lane == 0) sig[c] = sqrt(s2);
+        }
+        __syncthreads();
+        for (int c = tid; c < q; c += nt) {
+            const double s = sig[c];
+            int r = 0;
+            for (int o = 0; o < q; ++o) { const double so = sig[o]; r += (so > s) || (so == s && o < c); }
+            rnk[c] = r;
+        }
+        __syncthreads();
+        for (int c = tid; c < q; c += nt) S[rnk[c]] = sig[c];
+        for (int e = tid; e < q * q; e += nt) {
+            const int c = e / q, t = e - c * q;
+            const double v = V[(int64_t)c * ldq + t];
+            if (tall) O2[(int64_t)rnk[c] * n + t] = v; else O1[(int64_t)t * k + rnk[c]] = v;
+        }
+        // left vectors of X: U_X = Q (R V) / sigma = W[:, :q] * G2^T / sigma, 8 rows x 32 columns per warp turn on the tensor pipe
+        const int row_blocks = (p + 7) >> 3, col_groups = (q + 31) >> 5;
+        for (int wt = warp; wt < row_blocks * col_groups; wt += nwarps) {
+            const int i0 = (wt / col_groups) << 3, c0 = (wt % col_groups) << 5;
+            double acc[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = 0.0;
+            const int ri = i0 + gid;
+            const double* wrow = W + (int64_t)(ri < p ? ri : p - 1) * ld;
+            for (int t0 = 0; t0 < q; t0 += 4) {
+                const int t = t0 + tig;
+                const double av = (ri < p && t < q) ? wrow[t] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int cb = c0 + 8 * j + gid;
+                    const double bv = (cb < q && t < q) ? G2[(int64_t)cb * ldq + t] : 0.0;
+                    dmma_f64(acc[j][0], acc[j][1], av, bv);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = c0 + 8 * j + 2 * tig + h;
+                    if (ri < p && c < q) {
+                        const double s = sig[c];
+                        const double v = s > 0.0 ? acc[j][h] / s : 0.0;
+                        if (tall) O1[(int64_t)ri * k + rnk[c]] = v; else O2[(int64_t)rnk[c] * n + ri] = v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side of the descriptor-driven kernels ----
+struct DescOrder {
+    int* dev = nullptr;
+    int64_t cap = 0;
+};
+static DescOrder g_desc_order;
+
+// sectors of class `big` (working set beyond the 72 KiB CTA) or not, largest first; returns their count
+static int desc_select(const int64_t* sh, int ns, bool svd, int use_qr, bool big, std::vector<int>& out, int64_t& scratch_need) {
+    std::vector<std::pair<int64_t, int>> sel;
+    scratch_need = 0;
+    for (int i = 0; i < ns; ++i) {
+        const int64_t m = sh[i * TNSP_SECT_COLS], n = sh[i * TNSP_SECT_COLS + 1];
+        if (m * n == 0) continue;
+        int64_t p, q, need_smem, need_scr = 0;
+        if (svd) {
+            p = m >= n ? m : n; q = m >= n ? n : m;
+            need_smem = svd_desc_direct_need(p, q);
+            if (need_smem > kQBigDoubles) need_scr = svd_desc_pre_need(p, q);
+        } else {
+            p = use_qr ? m : n; q = use_qr ? n : m;
+            need_smem = qr_sector_need(p, q);
+            if (need_smem > kQBigDoubles) need_scr = need_smem;
+        }
+        const bool is_big = need_smem > kQSmallDoubles;
+        if (is_big != big) continue;
+        if (need_scr > scratch_need) scratch_need = need_scr;
+        sel.push_back({-(p * q * q), i});
+    }
+    std::sort(sel.begin(), sel.end());
+    out.clear();
+    for (auto& e : sel) out.push_back(e.second);
+    return (int)out.size();
+}
+
+static int desc_upload(const std::vector<int>& a, const std::vector<int>& b, cudaStream_t st) {
+    const int64_t total = (int64_t)a.size() + b.size();
+    if (total > g_desc_order.cap) {
+        if (g_desc_order.dev) cudaFree(g_desc_order.dev);
+        g_desc_order.cap = total < 256 ? 256 : 2 * total;
+        if (cudaMalloc(&g_desc_order.dev, sizeof(int) * g_desc_order.cap) != cudaSuccess) { set_error("descriptor sectors: cudaMalloc"); return 1; }
+    }
+    // pageable source: the copy is staged before the call returns, the vectors may go out of scope
+    if (!a.empty()) cudaMemcpyAsync(g_desc_order.dev, a.data(), sizeof(int) * a.size(), cudaMemcpyHostToDevice, st);
+    if (!b.empty()) cudaMemcpyAsync(g_desc_order.dev + a.size(), b.data(), sizeof(int) * b.size(), cudaMemcpyHostToDevice, st);
+    return 0;
+}
+
+static bool desc_applicable(const int64_t* sh, int ns) {
+    for (int i = 0; i < ns; ++i) {
+        const int64_t m = sh[i * TNSP_SECT_COLS], n = sh[i * TNSP_SECT_COLS + 1];
+        if (m * n >= (int64_t)1 << 30) return false;      // 32-bit element indices inside the kernels
+    }
+    return true;
+}
 }  // namespace tnsp
 
 using namespace tnsp;
+
+// descriptor-driven sectors beyond the warp class; returns 0 ok, 1 error, -1 not applicable
+int tnsp_qr_desc_launch(const int64_t* sect, const int64_t* sh, int ns, const double* a, int64_t abs_, double* out1, int64_t o1bs,
+                        double* out2, int64_t o2bs, int use_qr, int nb, cudaStream_t st) {
+    if (!desc_applicable(sh, ns)) return -1;
+    std::vector<int> big, small;
+    int64_t scr_big = 0, scr_small = 0;
+    desc_select(sh, ns, false, use_qr, true, big, scr_big);
+    desc_select(sh, ns, false, use_qr, false, small, scr_small);
+    if (desc_upload(big, small, st)) return 1;
+    const int64_t per_cta = scr_big ? scr_big + 8 : 0;
+    if (!grow(g_qws.scratch, g_qws.scratch_cap, per_cta * kSMs)) { set_error("descriptor sectors: cudaMalloc of the scratch failed"); return 1; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(qr_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(svd_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        attr_set = true;
+    }
+    if (!big.empty()) {
+        const int64_t items = (int64_t)big.size() * nb;
+        qr_desc_kernel<<<(unsigned)(items < kSMs ? items : kSMs), kQBigThreads, kQBigDoubles * 8, st>>>(
+            sect, g_desc_order.dev, (int)big.size(), a, abs_, out1, o1bs, out2, o2bs, use_qr, nb, kQBigDoubles, g_qws.scratch, per_cta);
+        if (check_launch("tnsp_qr_batched_f64(descriptor, big)")) return 1;
+    }
+    if (!small.empty()) {
+        const int64_t items = (int64_t)small.size() * nb;
+        qr_desc_kernel<<<(unsigned)(items < 3 * kSMs ? items : 3 * kSMs), kQSmallThreads, kQSmallDoubles * 8, st>>>(
+            sect, g_desc_order.dev + big.size(), (int)small.size(), a, abs_, out1, o1bs, out2, o2bs, use_qr, nb, kQSmallDoubles, nullptr, 0);
+        if (check_launch("tnsp_qr_batched_f64(descriptor, small)")) return 1;
+    }
+    return 0;
+}
+
+int tnsp_svd_desc_launch(const int64_t* sect, const int64_t* sh, int ns, const double* a, int64_t abs_, double* out1, int64_t o1bs,
+                         double* s, int64_t sbs, double* out2, int64_t o2bs, int nb, cudaStream_t st) {
+    if (!desc_applicable(sh, ns)) return -1;
+    std::vector<int> big, small;
+    int64_t scr_big = 0, scr_small = 0;
+    desc_select(sh, ns, true, 0, true, big, scr_big);
+    desc_select(sh, ns, true, 0, false, small, scr_small);
+    if (desc_upload(big, small, st)) return 1;
+    const int64_t per_cta = scr_big ? ((scr_big + 9) & ~(int64_t)1) : 0;
+    if (!grow(g_qws.scratch, g_qws.scratch_cap, per_cta * kSMs)) { set_error("descriptor sectors: cudaMalloc of the scratch failed"); return 1; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(qr_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(svd_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        attr_set = true;
+    }
+    if (!big.empty()) {
+        const int64_t items = (int64_t)big.size() * nb;
+        svd_desc_kernel<<<(unsigned)(items < kSMs ? items : kSMs), kQBigThreads, kQBigDoubles * 8, st>>>(
+            sect, g_desc_order.dev, (int)big.size(), a, abs_, out1, o1bs, s, sbs, out2, o2bs, nb, kQBigDoubles, g_qws.scratch, per_cta);
+        if (check_launch("tnsp_svd_batched_f64(descriptor, big)")) return 1;
+    }
+    if (!small.empty()) {
+        const int64_t items = (int64_t)small.size() * nb;
+        svd_desc_kernel<<<(unsigned)(items < 3 * kSMs ? items : 3 * kSMs), kQSmallThreads, kQSmallDoubles * 8, st>>>(
+            sect, g_desc_order.dev + big.size(), (int)small.size(), a, abs_, out1, o1bs, s, sbs, out2, o2bs, nb, kQSmallDoubles, nullptr, 0);
+        if (check_launch("tnsp_svd_batched_f64(descriptor, small)")) return 1;
+    }
+    return 0;
+}
+
 
 // Launchers shared by tnsp_qr_batched_f64 / tnsp_svd_batched_f64 (factor.cu: a single LARGE descriptor) and by
 // tnsp_qr_sectors_f64 / tnsp_svd_sectors_f64 below (any size).  Return -1 if the shape is not handled here.
