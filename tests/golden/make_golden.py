@@ -248,6 +248,14 @@ def hubbard_ff(L1, L2, D, T):
 
 
 def main():
+    if "state" in sys.argv[1:]:
+        # checkpoints exactly as the reference writes them (utility.py:365-388): pickle of the SamplingLattice
+        import pickle
+        for name, lat in (("state_heisU1_4x4_d1", heisenberg_u1(4, 4, 1)), ("state_tJ_4x4_D1", tJ(4, 4, 1, 2)), ("state_heis_3x3_D2", heisenberg(3, 3, 2))):
+            with open(os.path.join(ROOT, "tests", "golden", name + ".pkl"), "wb") as f:
+                pickle.dump(lat, f)
+            print(name, os.path.getsize(os.path.join(ROOT, "tests", "golden", name + ".pkl")), "bytes")
+        return
     if "driver" in sys.argv[1:]:
         lat = heisenberg(3, 3, 2)
         dump_driver_case("driver_heis_3x3_D2_Dc4_sr_momentum", "No", lat, 4, neel(lat), seed=21, sampling_total_step=12, grad_total_step=3,

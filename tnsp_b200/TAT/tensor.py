@@ -793,7 +793,109 @@ class Tensor:
     def _not_on_path(self, *a, **k):
         raise NotImplementedError("this Tensor method is outside the sampling-VMC hot path (SURVEY.md section 8)")
 
-    trace = exponential = shrink = expand = clear_fermi_symmetry = dump = load = _not_on_path
+    trace = exponential = shrink = expand = clear_fermi_symmetry = _not_on_path
+
+    # -- binary wire format (io.hpp:686-760, version 1) -------------------------------------------
+    # "TAT" | u16 version = 1 | names: u64 count, (u64 length, bytes)* | edges: u64 count, per edge [u8 arrow if the symmetry is
+    # fermionic] u64 segments, (symmetry padded to 8 bytes, u64 dimension)* | storage: u64 count, float64*.
+    # A symmetry is the raw libstdc++ std::tuple of the reference: components in REVERSE order, int32 / bool each aligned to
+    # its size (checked against dumps of the unmodified reference for all eight symmetry types, tests/test_wire_format.py).
+    # The reference pickles a tensor as exactly these bytes (PyTAT.hpp:768-771), so states pickled by either side load on
+    # the other once `TAT.install_as_TAT()` has aliased the module tree (SamplingLattice.__getstate__, lattice.py:706-744).
+    @classmethod
+    def _pack_symmetry(cls, sym):
+        out = bytearray(8)
+        off = 0
+        for v, kind in zip(reversed(tuple(sym)), reversed(cls.Symmetry.kinds)):
+            if kind == "Z2":
+                out[off] = 1 if v else 0
+                off += 1
+            else:
+                off = (off + 3) & ~3
+                out[off:off + 4] = int(v).to_bytes(4, "little", signed=True)
+                off += 4
+        return bytes(out)
+
+    @classmethod
+    def _unpack_symmetry(cls, raw):
+        vals, off = [], 0
+        for kind in reversed(cls.Symmetry.kinds):
+            if kind == "Z2":
+                vals.append(raw[off] != 0)
+                off += 1
+            else:
+                off = (off + 3) & ~3
+                vals.append(int.from_bytes(raw[off:off + 4], "little", signed=True))
+                off += 4
+        return cls.Symmetry(*reversed(vals))
+
+    def dump(self):
+        """bytes of the reference's binary tensor format (a batched tensor must hold a single chain)"""
+        import struct
+        if self.nb != 1:
+            raise RuntimeError("dump: a lock-step batch has no single-tensor wire format; dump the chains one by one")
+        out = [b"TAT", struct.pack("<H", 1), struct.pack("<Q", len(self.names))]
+        for n in self.names:
+            raw = str(n).encode()
+            out += [struct.pack("<Q", len(raw)), raw]
+        out.append(struct.pack("<Q", len(self._edges)))
+        for e in self._edges:
+            if self.Symmetry.is_fermi_symmetry:
+                out.append(b"\x01" if e.arrow else b"\x00")
+            out.append(struct.pack("<Q", len(e.segments)))
+            for sym, dim in e.segments:
+                out += [self._pack_symmetry(sym), struct.pack("<Q", int(dim))]
+        data = np.ascontiguousarray(self._host(), dtype="<f8").reshape(-1)
+        out += [struct.pack("<Q", data.size), data.tobytes()]
+        return b"".join(out)
+
+    def load(self, raw):
+        """replace this tensor by the one stored in `raw` (io.hpp:718-760); returns self"""
+        import struct
+        raw = bytes(raw)
+        if raw[:3] != b"TAT":
+            raise RuntimeError("load: version-0 dumps (TAT < 0.2, old block order) are not supported")
+        version, = struct.unpack_from("<H", raw, 3)
+        if version != 1:
+            raise RuntimeError(f"load: unknown tensor dump version {version}")
+        pos = 5
+
+        def u64():
+            nonlocal pos
+            v, = struct.unpack_from("<Q", raw, pos)
+            pos += 8
+            return v
+
+        names = []
+        for _ in range(u64()):
+            n = u64()
+            names.append(raw[pos:pos + n].decode())
+            pos += n
+        edges = []
+        for _ in range(u64()):
+            arrow = False
+            if self.Symmetry.is_fermi_symmetry:
+                arrow = raw[pos] != 0
+                pos += 1
+            segments = []
+            for _ in range(u64()):
+                sym = self._unpack_symmetry(raw[pos:pos + 8])
+                dim, = struct.unpack_from("<Q", raw, pos + 8)
+                pos += 16
+                segments.append((sym, int(dim)))
+            edges.append(self.Edge(segments, arrow))
+        self._init(names, edges, None)
+        count = u64()
+        if count != self._table.size:
+            raise RuntimeError("load: storage size does not match the block structure")
+        self._set_host(np.frombuffer(raw, dtype="<f8", count=count, offset=pos).copy())
+        return self
+
+    def __getstate__(self):
+        return self.dump()
+
+    def __setstate__(self, state):
+        self.load(state)
 
     # -- dense embedding (clear_symmetry.hpp: bosonic symmetries only) ----------------------------------
     def _segment_starts(self):
