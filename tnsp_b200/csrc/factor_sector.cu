@@ -497,15 +497,96 @@ __device__ void block_reflect(double* W, int ld, int p, int j0, int c_begin, int
     }
 }
 
+// The same update for a W that lives in GLOBAL memory (sectors beyond shared memory): Vp / Tm are in shared memory and the
+// loads of W are issued four k-steps ahead of the DMMAs that consume them (the plain loop above has one dependent L2 round
+// trip per step).
+__device__ void block_reflect_g(double* __restrict__ W, int ld, int p, int j0, int c_begin, int c_end, const double* Vp, const double* Tm,
+                                bool transpose_t) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int P8 = ((p - j0) + 7) & ~7;
+    const double* T = Tm + 64;
+    const double t_lo = transpose_t ? T[tig * 8 + gid] : T[gid * 8 + tig];
+    const double t_hi = transpose_t ? T[(tig + 4) * 8 + gid] : T[gid * 8 + tig + 4];
+    for (int c0 = c_begin + 8 * warp; c0 < c_end; c0 += 8 * nwarps) {
+        const int cb = c0 + gid;
+        const bool cb_ok = cb < c_end;
+        double z0 = 0.0, z1 = 0.0;
+        for (int i0 = 0; i0 < P8; i0 += 16) {
+            double bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int gi = j0 + i0 + 4 * u + tig;
+                bv[u] = (cb_ok && gi < p) ? W[(int64_t)gi * ld + cb] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + 4 * u < P8) dmma_f64(z0, z1, Vp[(i0 + 4 * u + tig) * 8 + gid], bv[u]);     // Z = V^T A
+        }
+        double b_lo, b_hi;
+        cfrag_to_bfrag(z0, z1, gid, tig, b_lo, b_hi);
+        double y0 = 0.0, y1 = 0.0;
+        dmma_f64(y0, y1, t_lo, b_lo);
+        dmma_f64(y0, y1, t_hi, b_hi);                   // Y = Tm' Z
+        cfrag_to_bfrag(-y0, -y1, gid, tig, b_lo, b_hi);
+        const int cc = c0 + 2 * tig;
+        const bool c_ok0 = cc < c_end, c_ok1 = cc + 1 < c_end;
+        for (int i0 = 0; i0 < P8; i0 += 32) {
+            double w0[4], w1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int gi = j0 + i0 + 8 * u + gid;
+                const bool r_ok = gi < p && i0 + 8 * u < P8;
+                const double* wr = W + (int64_t)gi * ld + cc;
+                w0[u] = (r_ok && c_ok0) ? wr[0] : 0.0;
+                w1[u] = (r_ok && c_ok1) ? wr[1] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + 8 * u < P8) {
+                    const int gi = j0 + i0 + 8 * u + gid;
+                    dmma_f64(w0[u], w1[u], Vp[(i0 + 8 * u + gid) * 8 + tig], b_lo);
+                    dmma_f64(w0[u], w1[u], Vp[(i0 + 8 * u + gid) * 8 + tig + 4], b_hi);   // A -= V Y
+                    double* wr = W + (int64_t)gi * ld + cc;
+                    if (gi < p && c_ok0) wr[0] = w0[u];
+                    if (gi < p && c_ok1) wr[1] = w1[u];
+                }
+            }
+        }
+    }
+}
+
 __host__ __device__ inline int64_t qr_blocked_extra(int64_t p) { return 8 * ((p + 7) & ~(int64_t)7) + 128; }
 
-__device__ void householder_qr_blocked(double* W, int ld, int p, int q, int k, double* tau, double* Rout, double* Vp, double* Tm) {
+// Pan (optional): [P8][8] shared-memory buffer for a W in GLOBAL memory.  Every panel is then staged there, factorised in
+// shared memory and written back once, the explicit reflectors are built in place (Vp must alias Pan) and the trailing
+// update streams W through block_reflect_g.
+__device__ void householder_qr_blocked(double* W, int ld, int p, int q, int k, double* tau, double* Rout, double* Vp, double* Tm,
+                                       double* Pan = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     double* scl = tau + k;
     double* dia = tau + 2 * k;
+    double* Wp = W;      // what the panel code addresses: W itself, or the staged panel shifted so that Wp[i * lp + j] is element (i, j)
+    int lp = ld;
+    auto stage_panel = [&](int j0, int jb) {
+        for (int e = tid; e < (p - j0) * 8; e += nthreads) {
+            const int i = e >> 3, jj = e & 7;
+            Pan[e] = jj < jb ? W[(int64_t)(j0 + i) * ld + j0 + jj] : 0.0;
+        }
+        Wp = Pan - (j0 * 8 + j0);
+        lp = 8;
+        __syncthreads();
+    };
+    auto unstage_panel = [&](int j0, int jb) {
+        for (int e = tid; e < (p - j0) * 8; e += nthreads) {
+            const int i = e >> 3, jj = e & 7;
+            if (jj < jb) W[(int64_t)(j0 + i) * ld + j0 + jj] = Pan[e];
+        }
+        __syncthreads();
+    };
     auto make_reflector = [&](int j, double xnorm2) {
-        const double alpha = W[j * ld + j];
+        const double alpha = Wp[j * lp + j];
         double tj = 0.0, scale = 0.0, beta = alpha;
         if (xnorm2 != 0.0) {
             beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
@@ -516,37 +597,38 @@ __device__ void householder_qr_blocked(double* W, int ld, int p, int q, int k, d
     };
     for (int j0 = 0; j0 < k; j0 += 8) {
         const int jb = (k - j0 < 8) ? k - j0 : 8, jend = j0 + jb;
+        if (Pan) stage_panel(j0, jb);
         if (warp == 0) {
             double part = 0.0;
-            for (int i = j0 + 1 + lane; i < p; i += 32) { const double v = W[i * ld + j0]; part += v * v; }
+            for (int i = j0 + 1 + lane; i < p; i += 32) { const double v = Wp[i * lp + j0]; part += v * v; }
             make_reflector(j0, warp_sum(part));
         }
         __syncthreads();
         for (int j = j0; j < jend; ++j) {
             const double tj = tau[j], scale = scl[j];
-            const double* vj = W + j;
+            const double* vj = Wp + j;
             for (int c = j + 1 + warp; c < jend; c += nwarps) {
-                double* wc = W + c;
+                double* wc = Wp + c;
                 const bool next = (c == j + 1);
                 double part = 0.0;
                 if (tj != 0.0) {
                     double w = 0.0;
-                    for (int i = j + 1 + lane; i < p; i += 32) w += vj[i * ld] * wc[i * ld];
-                    w = (warp_sum(w) * scale + wc[j * ld]) * tj;
+                    for (int i = j + 1 + lane; i < p; i += 32) w += vj[i * lp] * wc[i * lp];
+                    w = (warp_sum(w) * scale + wc[j * lp]) * tj;
                     const double ws = w * scale;
                     if (next) {
                         for (int i = j + 1 + lane; i < p; i += 32) {
-                            const double nv = wc[i * ld] - ws * vj[i * ld];
-                            wc[i * ld] = nv;
+                            const double nv = wc[i * lp] - ws * vj[i * lp];
+                            wc[i * lp] = nv;
                             if (i > c) part += nv * nv;
                         }
                     } else {
-                        for (int i = j + 1 + lane; i < p; i += 32) wc[i * ld] -= ws * vj[i * ld];
+                        for (int i = j + 1 + lane; i < p; i += 32) wc[i * lp] -= ws * vj[i * lp];
                     }
                     __syncwarp();
-                    if (lane == 0) wc[j * ld] -= w;
+                    if (lane == 0) wc[j * lp] -= w;
                 } else if (next) {
-                    for (int i = c + 1 + lane; i < p; i += 32) { const double v = wc[i * ld]; part += v * v; }
+                    for (int i = c + 1 + lane; i < p; i += 32) { const double v = wc[i * lp]; part += v * v; }
                 }
                 if (next) {
                     __syncwarp();
@@ -555,51 +637,61 @@ __device__ void householder_qr_blocked(double* W, int ld, int p, int q, int k, d
             }
             __syncthreads();
         }
+        if (Pan) unstage_panel(j0, jb);
         if (jend < q) {
-            build_panel_vt(W, ld, p, j0, jb, tau, scl, Vp, Tm);
-            block_reflect(W, ld, p, j0, jend, q, Vp, Tm, true);
+            build_panel_vt(Wp, lp, p, j0, jb, tau, scl, Vp, Tm);      // in place when Vp aliases the staged panel
+            if (Pan) block_reflect_g(W, ld, p, j0, jend, q, Vp, Tm, true);
+            else block_reflect(W, ld, p, j0, jend, q, Vp, Tm, true);
             __syncthreads();
         }
     }
+    Wp = W;
+    lp = ld;
     for (int e = tid; e < k * q; e += nthreads) {
         const int i = e / q, j = e - i * q;
         Rout[e] = (j > i) ? W[i * ld + j] : (j == i ? dia[i] : 0.0);
     }
     __syncthreads();
-    auto finalize = [&](int j) {             // one warp; lanes own rows j + lane, j + lane + 32, ...
+    auto finalize = [&](int j, int j0) {     // one warp; lanes own rows j + lane, j + lane + 32, ...
         const double tj = tau[j];
         const double f = -tj * scl[j];
-        double* wj = W + j;
-        for (int i = j + lane; i < p; i += 32) wj[i * ld] = (i == j) ? 1.0 - tj : wj[i * ld] * f;
-        for (int i = lane; i < j; i += 32) wj[i * ld] = 0.0;
+        double* wj = Wp + j;
+        for (int i = j + lane; i < p; i += 32) wj[i * lp] = (i == j) ? 1.0 - tj : wj[i * lp] * f;
+        const int first = Pan ? j0 : 0;        // rows above a staged panel are zeroed in W itself
+        for (int i = first + lane; i < j; i += 32) wj[i * lp] = 0.0;
+        if (Pan) for (int i = lane; i < j0; i += 32) W[(int64_t)i * ld + j] = 0.0;
     };
     for (int j0 = ((k - 1) >> 3) << 3; j0 >= 0; j0 -= 8) {
         const int jb = (k - j0 < 8) ? k - j0 : 8, jend = j0 + jb;
         if (jend < k) {
-            build_panel_vt(W, ld, p, j0, jb, tau, scl, Vp, Tm);
-            block_reflect(W, ld, p, j0, jend, k, Vp, Tm, false);
+            if (Pan) stage_panel(j0, jb);
+            build_panel_vt(Wp, lp, p, j0, jb, tau, scl, Vp, Tm);
+            if (Pan) block_reflect_g(W, ld, p, j0, jend, k, Vp, Tm, false);
+            else block_reflect(W, ld, p, j0, jend, k, Vp, Tm, false);
             __syncthreads();
         }
+        if (Pan) stage_panel(j0, jb);          // (again: the reflectors were expanded in place)
         for (int j = jend - 1; j >= j0; --j) {
             const double tj = tau[j], scale = scl[j];
-            const double* vj = W + j;
+            const double* vj = Wp + j;
             for (int c = j + 1 + warp; c < jend; c += nwarps) {
-                double* wc = W + c;
-                if (c == j + 1) { finalize(c); __syncwarp(); }
+                double* wc = Wp + c;
+                if (c == j + 1) { finalize(c, j0); __syncwarp(); }
                 if (tj != 0.0) {
                     double w = 0.0;
-                    for (int i = j + 1 + lane; i < p; i += 32) w += vj[i * ld] * wc[i * ld];
-                    w = (warp_sum(w) * scale + wc[j * ld]) * tj;
+                    for (int i = j + 1 + lane; i < p; i += 32) w += vj[i * lp] * wc[i * lp];
+                    w = (warp_sum(w) * scale + wc[j * lp]) * tj;
                     const double ws = w * scale;
-                    for (int i = j + 1 + lane; i < p; i += 32) wc[i * ld] -= ws * vj[i * ld];
+                    for (int i = j + 1 + lane; i < p; i += 32) wc[i * lp] -= ws * vj[i * lp];
                     __syncwarp();
-                    if (lane == 0) wc[j * ld] -= w;
+                    if (lane == 0) wc[j * lp] -= w;
                 }
             }
             __syncthreads();
         }
-        if (warp == 0) finalize(j0);
+        if (warp == 0) finalize(j0, j0);
         __syncthreads();
+        if (Pan) unstage_panel(j0, jb);
     }
 }
 
@@ -1514,13 +1606,18 @@ __global__ void __launch_bounds__(kQBigThreads) qr_desc_kernel(const int64_t* __
         double* Rc = tau + 3 * ks;
         double* Vp = Rc + (int64_t)ks * q;
         double* Tm = Vp + 8 * ((p + 7) & ~7);
+        double* Pan = nullptr;
+        if (need > cap && 128 + 3 * (int64_t)ks + 8 * (int64_t)((p + 7) & ~7) <= cap) {
+            // W, R in the global scratch; the panel / block reflector, T and tau in shared memory
+            Tm = work; tau = work + 128; Pan = tau + 3 * ks; Vp = Pan;
+        }
         if (use_qr) {
             for (int e = tid; e < m * n; e += nt) { const int r = e / n, c = e - r * n; W[(int64_t)r * ld + c] = __ldg(A + e); }
         } else {
             for (int e = tid; e < m * n; e += nt) { const int r = e / n, c = e - r * n; W[(int64_t)c * ld + r] = __ldg(A + e); }
         }
         __syncthreads();
-        if (q > 8) householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm);
+        if (q > 8) householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm, Pan);
         else householder_qr(W, ld, p, q, ks, tau, Rc, nullptr);
         if (use_qr) {
             for (int e = tid; e < m * k; e += nt) { const int r = e / k, t = e - r * k; O1[e] = W[(int64_t)r * ld + t]; }
@@ -1614,6 +1711,11 @@ __global__ void __launch_bounds__(kQBigThreads) svd_desc_kernel(const int64_t* _
         double* Rc = tau + 3 * q;
         double* Vp = Rc + (int64_t)q * q;
         double* Tm = Vp + 8 * ((p + 7) & ~7);
+        double* Pan = nullptr;
+        if (128 + 3 * (int64_t)q + 8 * (int64_t)((p + 7) & ~7) <= cap) {
+            // QR stage: panel / block reflector, T and tau in shared memory (the Jacobi stage reuses it afterwards)
+            Tm = work; tau = work + 128; Pan = tau + 3 * q; Vp = Pan;
+        }
         double* small = (svd_desc_small_need(q) <= cap) ? work : gscr + ((qr_sector_need(p, q) + 1) & ~(int64_t)1);
         double* G2 = small;                                  // column c of R at G2[c * ldq]
         double* V = G2 + (int64_t)q * ldq;
@@ -1625,8 +1727,9 @@ __global__ void __launch_bounds__(kQBigThreads) svd_desc_kernel(const int64_t* _
             if (tall) W[(int64_t)r * ld + c] = v; else W[(int64_t)c * ld + r] = v;
         }
         __syncthreads();
-        if (q > 8) householder_qr_blocked(W, ld, p, q, q, tau, Rc, Vp, Tm);
+        if (q > 8) householder_qr_blocked(W, ld, p, q, q, tau, Rc, Vp, Tm, Pan);
         else householder_qr(W, ld, p, q, q, tau, Rc, nullptr);
+        __syncthreads();
         for (int e = tid; e < q * ldq; e += nt) {
             const int c = e / ldq, r = e - c * ldq;
             G2[e] = r < q ? Rc[(int64_t)r * q + c] : 0.0;
