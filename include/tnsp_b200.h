@@ -115,6 +115,11 @@ int64_t tnsp_sector_queue_min(int64_t min_elems);
  * (kept for differential tests), < 0 only queries.  Returns the previous setting. */
 int tnsp_factor_desc_kernels(int enable);
 
+/* One-sided Jacobi of the work-queue / descriptor kernels: 1 (default) carries the squared column norms through a sweep
+ * (exact again at the start of the next: one dot product per column pair), 0 recomputes all three dot products per pair.
+ * Both converge to the same factorisation; kept switchable for differential tests.  Returns the previous setting. */
+int tnsp_jacobi_cached_norms(int enable);
+
 /* ---- greedy cross-sector truncation (svd.hpp:429-481): counts[b][i] = kept values of sector i. */
 int tnsp_svd_cut_f64(const int64_t* sect, int ns, int64_t s_total, const double* s, int64_t s_bstride,
                      int64_t remain_cut, double relative_cut, int32_t* counts, int nb, void* stream);

@@ -1,0 +1,5 @@
+set -x
+timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_cfg5.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/s2p_ktests.txt
+(cd scripts && timeout 300 python mb_cfg5.py 64 2048 128 512 > ../gpurun_out/s2p_mb_cfg5.txt 2>&1)
+(cd scripts && timeout 300 python mb_sector.py 296 > ../gpurun_out/s2p_mb_sector.txt 2>&1)
+timeout 900 python bench.py > gpurun_out/s2p_bench_cfg2.json 2> gpurun_out/s2p_bench_cfg2.err

@@ -419,3 +419,45 @@ def test_descriptor_kernels_agree_with_first_generation(shapes):
                 assert np.all(np.diff(sv) <= 0)
                 Q, R = Q1[b, x1:x1 + m * k].reshape(m, k), Q2[b, x2:x2 + k * n].reshape(k, n)
                 assert np.abs(Q @ R - M).max() <= 1e-12 * max(1.0, np.abs(M).max()) * max(m, n)
+
+
+@pytest.mark.parametrize("shape", [(216, 216), (36, 216), (150, 120)])
+def test_jacobi_cached_norms_agree_with_three_dot_products(shape):
+    """the sweeps that carry the column norms (default) and the ones that recompute them per pair give the same singular values
+    and both reconstruct, on block-diagonal (discovered sectors) and dense matrices, including a graded spectrum"""
+    cu, _ = _both()
+    m, n = shape
+    rng = np.random.default_rng(m + n)
+    nb = 4
+    mats = []
+    for b in range(nb):
+        M = rng.standard_normal((m, n))
+        if b % 2 == 0:                       # block diagonal: three sectors
+            mask = (np.arange(m)[:, None] % 3) == (np.arange(n)[None, :] % 3)
+            M = M * mask
+        if b >= 2:                           # graded columns: norms from 1 down to 1e-9
+            M = M * np.logspace(0, -9, n)[None, :]
+        mats.append(M.reshape(-1))
+    a = np.stack(mats)
+    p, ao, o1, o2, so = _factor_plan([shape], True)
+    out = {}
+    old = cu.lib.tnsp_jacobi_cached_norms(-1)
+    saved = cu.sector_discovery
+    try:
+        cu.sector_discovery = True
+        for mode in (0, 1):
+            cu.lib.tnsp_jacobi_cached_norms(mode)
+            t1, t2, s = cu.zeros(nb, o1), cu.zeros(nb, o2), cu.zeros(nb, so)
+            cu.svd(p, cu.from_numpy(a), t1, s, t2)
+            out[mode] = [cu.to_numpy(x) for x in (t1, s, t2)]
+    finally:
+        cu.lib.tnsp_jacobi_cached_norms(old)
+        cu.sector_discovery = saved
+    k = min(m, n)
+    for b in range(nb):
+        ref = np.linalg.svd(a[b].reshape(m, n), compute_uv=False)
+        for mode in (0, 1):
+            U, S, Vt = out[mode][0][b].reshape(m, k), out[mode][1][b], out[mode][2][b].reshape(k, n)
+            sv = np.sort(S)[::-1]
+            assert np.abs(sv - ref).max() <= 1e-12 * ref.max()
+            assert np.abs((U * S) @ Vt - a[b].reshape(m, n)).max() <= 1e-12 * ref.max() * max(m, n)

@@ -501,28 +501,39 @@ __device__ void block_reflect(double* W, int ld, int p, int j0, int c_begin, int
 // loads of W are issued four k-steps ahead of the DMMAs that consume them (the plain loop above has one dependent L2 round
 // trip per step).
 __device__ void block_reflect_g(double* __restrict__ W, int ld, int p, int j0, int c_begin, int c_end, const double* Vp, const double* Tm,
-                                bool transpose_t) {
+                                bool transpose_t, double* Zp) {
+    // Work units are (8-column block, row part): with fewer column blocks than warps the rows of a block are split over
+    // several warps (every warp then has its own loads in flight), the partial Z = V^T A meet in `Zp` (64 doubles per
+    // warp) behind one block barrier and are summed in a fixed order.  ALL threads of the CTA must call this.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int P8 = ((p - j0) + 7) & ~7;
     const double* T = Tm + 64;
     const double t_lo = transpose_t ? T[tig * 8 + gid] : T[gid * 8 + tig];
     const double t_hi = transpose_t ? T[(tig + 4) * 8 + gid] : T[gid * 8 + tig + 4];
-    for (int c0 = c_begin + 8 * warp; c0 < c_end; c0 += 8 * nwarps) {
+    const int nblk = (c_end - c_begin + 7) >> 3;
+    int parts = (Zp != nullptr && nblk < nwarps) ? nwarps / nblk : 1;
+    if (parts > (P8 + 63) / 64) parts = (P8 + 63) / 64;          // at least 64 rows per part
+    if (parts < 1) parts = 1;
+    const int rows_per_part = (((P8 + parts - 1) / parts) + 31) & ~31;
+
+    auto z_partial = [&](int c0, int i_begin, int i_end, double& z0, double& z1) {
         const int cb = c0 + gid;
         const bool cb_ok = cb < c_end;
-        double z0 = 0.0, z1 = 0.0;
-        for (int i0 = 0; i0 < P8; i0 += 16) {
+        z0 = 0.0; z1 = 0.0;
+        for (int i0 = i_begin; i0 < i_end; i0 += 16) {
             double bv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int gi = j0 + i0 + 4 * u + tig;
-                bv[u] = (cb_ok && gi < p) ? W[(int64_t)gi * ld + cb] : 0.0;
+                bv[u] = (cb_ok && gi < p && i0 + 4 * u < i_end) ? W[(int64_t)gi * ld + cb] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (i0 + 4 * u < P8) dmma_f64(z0, z1, Vp[(i0 + 4 * u + tig) * 8 + gid], bv[u]);     // Z = V^T A
+                if (i0 + 4 * u < i_end) dmma_f64(z0, z1, Vp[(i0 + 4 * u + tig) * 8 + gid], bv[u]);     // Z = V^T A
         }
+    };
+    auto update_rows = [&](int c0, int i_begin, int i_end, double z0, double z1) {
         double b_lo, b_hi;
         cfrag_to_bfrag(z0, z1, gid, tig, b_lo, b_hi);
         double y0 = 0.0, y1 = 0.0;
@@ -531,19 +542,19 @@ __device__ void block_reflect_g(double* __restrict__ W, int ld, int p, int j0, i
         cfrag_to_bfrag(-y0, -y1, gid, tig, b_lo, b_hi);
         const int cc = c0 + 2 * tig;
         const bool c_ok0 = cc < c_end, c_ok1 = cc + 1 < c_end;
-        for (int i0 = 0; i0 < P8; i0 += 32) {
+        for (int i0 = i_begin; i0 < i_end; i0 += 32) {
             double w0[4], w1[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int gi = j0 + i0 + 8 * u + gid;
-                const bool r_ok = gi < p && i0 + 8 * u < P8;
+                const bool r_ok = gi < p && i0 + 8 * u < i_end;
                 const double* wr = W + (int64_t)gi * ld + cc;
                 w0[u] = (r_ok && c_ok0) ? wr[0] : 0.0;
                 w1[u] = (r_ok && c_ok1) ? wr[1] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (i0 + 8 * u < P8) {
+                if (i0 + 8 * u < i_end) {
                     const int gi = j0 + i0 + 8 * u + gid;
                     dmma_f64(w0[u], w1[u], Vp[(i0 + 8 * u + gid) * 8 + tig], b_lo);
                     dmma_f64(w0[u], w1[u], Vp[(i0 + 8 * u + gid) * 8 + tig + 4], b_hi);   // A -= V Y
@@ -553,7 +564,43 @@ __device__ void block_reflect_g(double* __restrict__ W, int ld, int p, int j0, i
                 }
             }
         }
+    };
+
+    if (parts == 1) {
+        for (int c0 = c_begin + 8 * warp; c0 < c_end; c0 += 8 * nwarps) {
+            double z0, z1;
+            z_partial(c0, 0, P8, z0, z1);
+            update_rows(c0, 0, P8, z0, z1);
+        }
+        return;
     }
+    const int blk = warp % nblk, part = warp / nblk;
+    const bool active = part < parts;
+    const int c0 = c_begin + 8 * blk;
+    const int i_begin = part * rows_per_part;
+    const int i_end = (i_begin + rows_per_part < P8) ? i_begin + rows_per_part : P8;
+    if (active && i_begin < P8) {
+        double z0, z1;
+        z_partial(c0, i_begin, i_end, z0, z1);
+        double* zp = Zp + (part * nblk + blk) * 64;
+        zp[gid * 8 + 2 * tig] = z0;
+        zp[gid * 8 + 2 * tig + 1] = z1;
+    } else if (active) {
+        double* zp = Zp + (part * nblk + blk) * 64;
+        zp[gid * 8 + 2 * tig] = 0.0;
+        zp[gid * 8 + 2 * tig + 1] = 0.0;
+    }
+    __syncthreads();
+    if (active && i_begin < P8) {
+        double z0 = 0.0, z1 = 0.0;
+        for (int pt = 0; pt < parts; ++pt) {            // fixed order: deterministic
+            const double* zp = Zp + (pt * nblk + blk) * 64;
+            z0 += zp[gid * 8 + 2 * tig];
+            z1 += zp[gid * 8 + 2 * tig + 1];
+        }
+        update_rows(c0, i_begin, i_end, z0, z1);
+    }
+    __syncthreads();                                     // Zp is reused by the next call
 }
 
 __host__ __device__ inline int64_t qr_blocked_extra(int64_t p) { return 8 * ((p + 7) & ~(int64_t)7) + 128; }
@@ -562,7 +609,7 @@ __host__ __device__ inline int64_t qr_blocked_extra(int64_t p) { return 8 * ((p 
 // shared memory and written back once, the explicit reflectors are built in place (Vp must alias Pan) and the trailing
 // update streams W through block_reflect_g.
 __device__ void householder_qr_blocked(double* W, int ld, int p, int q, int k, double* tau, double* Rout, double* Vp, double* Tm,
-                                       double* Pan = nullptr) {
+                                       double* Pan = nullptr, double* Zp = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     double* scl = tau + k;
@@ -640,7 +687,7 @@ __device__ void householder_qr_blocked(double* W, int ld, int p, int q, int k, d
         if (Pan) unstage_panel(j0, jb);
         if (jend < q) {
             build_panel_vt(Wp, lp, p, j0, jb, tau, scl, Vp, Tm);      // in place when Vp aliases the staged panel
-            if (Pan) block_reflect_g(W, ld, p, j0, jend, q, Vp, Tm, true);
+            if (Pan) block_reflect_g(W, ld, p, j0, jend, q, Vp, Tm, true, Zp);
             else block_reflect(W, ld, p, j0, jend, q, Vp, Tm, true);
             __syncthreads();
         }
@@ -666,7 +713,7 @@ __device__ void householder_qr_blocked(double* W, int ld, int p, int q, int k, d
         if (jend < k) {
             if (Pan) stage_panel(j0, jb);
             build_panel_vt(Wp, lp, p, j0, jb, tau, scl, Vp, Tm);
-            if (Pan) block_reflect_g(W, ld, p, j0, jend, k, Vp, Tm, false);
+            if (Pan) block_reflect_g(W, ld, p, j0, jend, k, Vp, Tm, false, Zp);
             else block_reflect(W, ld, p, j0, jend, k, Vp, Tm, false);
             __syncthreads();
         }
@@ -844,7 +891,10 @@ __device__ void jacobi_svd(double* G, int ldp, double* V, int ldq, int p, int q,
 //   * a sweep whose largest rotation was below 1e-8 (relative) ends the iteration: the cyclic Jacobi method converges
 //     quadratically, so the remaining off-diagonal couplings are O(1e-16) and the confirming sweep is not needed.
 // ldp, ldq even; rows p..ldp-1 of G and q..ldq-1 of V must be (and stay) zero.
-__device__ void jacobi_svd2(double* G, int ldp, double* V, int ldq, int p, int q, int* sh_rot) {
+// 1: the Jacobi sweeps carry the squared column norms (tnsp_jacobi_cached_norms); 0: three dot products per pair
+__device__ int g_jacobi_cached_norms = 1;
+
+__device__ void jacobi_svd2(double* G, int ldp, double* V, int ldq, int p, int q, int* sh_rot, double* nrm = nullptr) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int pe = p + (p & 1), qe_rows = q + (q & 1);
     const int qe = q + (q & 1), npairs = qe / 2;
@@ -857,6 +907,20 @@ __device__ void jacobi_svd2(double* G, int ldp, double* V, int ldq, int p, int q
     __syncthreads();
     for (int sweep = 0; sweep < 60 && q > 1; ++sweep) {
         if (tid == 0) *sh_rot = 0;
+        if (nrm) {
+            // squared column norms, exact at the start of every sweep and carried through the rotations of the sweep
+            // (aa' = aa - t cc, bb' = bb + t cc): a pair then costs ONE dot product and one reduction instead of three
+            for (int c0 = 0; c0 < q; c0 += groups) {      // uniform trip count: the reduction shuffles are warp-wide
+                const int c = c0 + grp;
+                double a2 = 0.0;
+                if (c < q) {
+                    const double2* gc = reinterpret_cast<const double2*>(G + c * ldp);
+                    for (int r = gl; 2 * r < pe; r += gs) { const double2 x = gc[r]; a2 = fma(x.x, x.x, a2); a2 = fma(x.y, x.y, a2); }
+                }
+                a2 = gsum(a2, gs);
+                if (c < q && gl == 0) nrm[c] = a2;
+            }
+        }
         __syncthreads();
         for (int round = 0; round < qe - 1; ++round) {
             for (int base = 0; base < npairs; base += groups) {
@@ -872,14 +936,25 @@ __device__ void jacobi_svd2(double* G, int ldp, double* V, int ldq, int p, int q
                 double2* gi = reinterpret_cast<double2*>(G + i * ldp);
                 double2* gj = reinterpret_cast<double2*>(G + j * ldp);
                 double aa = 0.0, bb = 0.0, cc = 0.0;
-                if (valid)
-                    for (int r = gl; 2 * r < pe; r += gs) {
-                        const double2 x = gi[r], y = gj[r];
-                        aa = fma(x.x, x.x, aa); aa = fma(x.y, x.y, aa);
-                        bb = fma(y.x, y.x, bb); bb = fma(y.y, y.y, bb);
-                        cc = fma(x.x, y.x, cc); cc = fma(x.y, y.y, cc);
+                if (nrm) {
+                    if (valid) {
+                        for (int r = gl; 2 * r < pe; r += gs) {
+                            const double2 x = gi[r], y = gj[r];
+                            cc = fma(x.x, y.x, cc); cc = fma(x.y, y.y, cc);
+                        }
+                        aa = fmax(nrm[i], 0.0); bb = fmax(nrm[j], 0.0);
                     }
-                aa = gsum(aa, gs); bb = gsum(bb, gs); cc = gsum(cc, gs);
+                    cc = gsum(cc, gs);
+                } else {
+                    if (valid)
+                        for (int r = gl; 2 * r < pe; r += gs) {
+                            const double2 x = gi[r], y = gj[r];
+                            aa = fma(x.x, x.x, aa); aa = fma(x.y, x.y, aa);
+                            bb = fma(y.x, y.x, bb); bb = fma(y.y, y.y, bb);
+                            cc = fma(x.x, y.x, cc); cc = fma(x.y, y.y, cc);
+                        }
+                    aa = gsum(aa, gs); bb = gsum(bb, gs); cc = gsum(cc, gs);
+                }
                 const double ab = aa * bb, c2q = cc * cc;
                 if (valid && c2q > tol2 * ab && ab > 0.0) {
                     const double dd = bb - aa, c2 = 2.0 * cc;
@@ -899,6 +974,7 @@ __device__ void jacobi_svd2(double* G, int ldp, double* V, int ldq, int p, int q
                         vi[r] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
                         vj[r] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
                     }
+                    if (nrm && gl == 0) { nrm[i] = aa - tt * cc; nrm[j] = bb + tt * cc; }
                     if (gl == 0 && c2q > 1e-16 * ab) *sh_rot = 1;
                 }
             }
@@ -1377,7 +1453,7 @@ __global__ void __launch_bounds__(kQBigThreads) svd_work_kernel(const int64_t* _
         }
         if (p & 1) for (int c = tid; c < q; c += nt) G[(int64_t)c * ldp + p] = 0.0;
         __syncthreads();
-        jacobi_svd2(G, ldp, V, ldq, p, q, &sh_rot);
+        jacobi_svd2(G, ldp, V, ldq, p, q, &sh_rot, g_jacobi_cached_norms ? sig : nullptr);
         for (int c = warp; c < q; c += nwarps) {
             double s2 = 0.0;
             for (int r = lane; r < p; r += 32) s2 += G[(int64_t)c * ldp + r] * G[(int64_t)c * ldp + r];
@@ -1606,10 +1682,10 @@ __global__ void __launch_bounds__(kQBigThreads) qr_desc_kernel(const int64_t* __
         double* Rc = tau + 3 * ks;
         double* Vp = Rc + (int64_t)ks * q;
         double* Tm = Vp + 8 * ((p + 7) & ~7);
-        double* Pan = nullptr;
-        if (need > cap && 128 + 3 * (int64_t)ks + 8 * (int64_t)((p + 7) & ~7) <= cap) {
-            // W, R in the global scratch; the panel / block reflector, T and tau in shared memory
-            Tm = work; tau = work + 128; Pan = tau + 3 * ks; Vp = Pan;
+        double* Pan = nullptr, *Zp = nullptr;
+        if (need > cap && 128 + 2 * (int64_t)nt + 3 * (int64_t)ks + 8 * (int64_t)((p + 7) & ~7) <= cap) {
+            // W, R in the global scratch; the panel / block reflector, T, tau and the partial Z in shared memory
+            Tm = work; Zp = work + 128; tau = Zp + 2 * nt; Pan = tau + 3 * ks; Vp = Pan;
         }
         if (use_qr) {
             for (int e = tid; e < m * n; e += nt) { const int r = e / n, c = e - r * n; W[(int64_t)r * ld + c] = __ldg(A + e); }
@@ -1617,7 +1693,7 @@ __global__ void __launch_bounds__(kQBigThreads) qr_desc_kernel(const int64_t* __
             for (int e = tid; e < m * n; e += nt) { const int r = e / n, c = e - r * n; W[(int64_t)c * ld + r] = __ldg(A + e); }
         }
         __syncthreads();
-        if (q > 8) householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm, Pan);
+        if (q > 8) householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm, Pan, Zp);
         else householder_qr(W, ld, p, q, ks, tau, Rc, nullptr);
         if (use_qr) {
             for (int e = tid; e < m * k; e += nt) { const int r = e / k, t = e - r * k; O1[e] = W[(int64_t)r * ld + t]; }
@@ -1673,7 +1749,7 @@ __global__ void __launch_bounds__(kQBigThreads) svd_desc_kernel(const int64_t* _
             }
             if (p & 1) for (int c = tid; c < q; c += nt) G[(int64_t)c * ldp + p] = 0.0;
             __syncthreads();
-            jacobi_svd2(G, ldp, V, ldq, p, q, &sh_rot);
+            jacobi_svd2(G, ldp, V, ldq, p, q, &sh_rot, g_jacobi_cached_norms ? sig : nullptr);
             for (int c = warp; c < q; c += nwarps) {
                 double s2 = 0.0;
                 for (int r = lane; r < p; r += 32) s2 += G[(int64_t)c * ldp + r] * G[(int64_t)c * ldp + r];
@@ -1711,10 +1787,10 @@ __global__ void __launch_bounds__(kQBigThreads) svd_desc_kernel(const int64_t* _
         double* Rc = tau + 3 * q;
         double* Vp = Rc + (int64_t)q * q;
         double* Tm = Vp + 8 * ((p + 7) & ~7);
-        double* Pan = nullptr;
-        if (128 + 3 * (int64_t)q + 8 * (int64_t)((p + 7) & ~7) <= cap) {
-            // QR stage: panel / block reflector, T and tau in shared memory (the Jacobi stage reuses it afterwards)
-            Tm = work; tau = work + 128; Pan = tau + 3 * q; Vp = Pan;
+        double* Pan = nullptr, *Zp = nullptr;
+        if (128 + 2 * (int64_t)nt + 3 * (int64_t)q + 8 * (int64_t)((p + 7) & ~7) <= cap) {
+            // QR stage: panel / block reflector, T, tau and the partial Z in shared memory (the Jacobi stage reuses it afterwards)
+            Tm = work; Zp = work + 128; tau = Zp + 2 * nt; Pan = tau + 3 * q; Vp = Pan;
         }
         double* small = (svd_desc_small_need(q) <= cap) ? work : gscr + ((qr_sector_need(p, q) + 1) & ~(int64_t)1);
         double* G2 = small;                                  // column c of R at G2[c * ldq]
@@ -1727,7 +1803,7 @@ __global__ void __launch_bounds__(kQBigThreads) svd_desc_kernel(const int64_t* _
             if (tall) W[(int64_t)r * ld + c] = v; else W[(int64_t)c * ld + r] = v;
         }
         __syncthreads();
-        if (q > 8) householder_qr_blocked(W, ld, p, q, q, tau, Rc, Vp, Tm, Pan);
+        if (q > 8) householder_qr_blocked(W, ld, p, q, q, tau, Rc, Vp, Tm, Pan, Zp);
         else householder_qr(W, ld, p, q, q, tau, Rc, nullptr);
         __syncthreads();
         for (int e = tid; e < q * ldq; e += nt) {
@@ -1735,7 +1811,7 @@ __global__ void __launch_bounds__(kQBigThreads) svd_desc_kernel(const int64_t* _
             G2[e] = r < q ? Rc[(int64_t)r * q + c] : 0.0;
         }
         __syncthreads();
-        jacobi_svd2(G2, ldq, V, ldq, q, q, &sh_rot);
+        jacobi_svd2(G2, ldq, V, ldq, q, q, &sh_rot, g_jacobi_cached_norms ? sig : nullptr);
         for (int c = warp; c < q; c += nwarps) {
             double s2 = 0.0;
             for (int r = lane; r < q; r += 32) s2 += G2[(int64_t)c * ldq + r] * G2[(int64_t)c * ldq + r];
@@ -1991,6 +2067,17 @@ extern "C" int tnsp_svd_sectors_f64(const int64_t* sect, const int64_t* sect_hos
 
 // Tuning knob: matrices with at least `min_elems` elements take the per-sector work-queue path, smaller ones the
 // one-CTA-per-chain kernel.  Returns the previous value; a negative argument only queries.
+extern "C" int tnsp_jacobi_cached_norms(int enable) {
+    static int current = 1;
+    const int old = current;
+    if (enable >= 0 && enable != current) {
+        current = enable ? 1 : 0;
+        cudaDeviceSynchronize();
+        if (cudaMemcpyToSymbol(g_jacobi_cached_norms, &current, sizeof(int)) != cudaSuccess) { set_error("tnsp_jacobi_cached_norms: cudaMemcpyToSymbol"); return -1; }
+    }
+    return old;
+}
+
 extern "C" int64_t tnsp_sector_queue_min(int64_t min_elems) {
     const int64_t old = queue_min_elems();
     if (min_elems >= 0) g_queue_min = min_elems;
