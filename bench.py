@@ -165,7 +165,6 @@ def run_reference(workload, steps, warmup, samples_per_step, cores=None, plan_fl
     per_step = []
     flops = None
     with ctx.Pool(cores) as pool:
-        pending_flops = pool.apply_async(_plan_flops_worker, ((workload,),)) if plan_flops else None
         if use_ref:
             ok = pool.map(_probe_ref, range(1))[0]
             use_ref = ok
@@ -177,9 +176,10 @@ def run_reference(workload, steps, warmup, samples_per_step, cores=None, plan_fl
             rate = sum(n / dt for n, dt, _ in res)
             if st >= warmup:
                 per_step.append((rate, wall))
-        if pending_flops is not None:
+        if plan_flops:
+            # after the timed steps: the count must not compete with the baseline's workers for the host cores
             try:
-                flops = pending_flops.get(timeout=600)
+                flops = pool.apply_async(_plan_flops_worker, ((workload,),)).get(timeout=600)
             except Exception as e:   # the count is a report, never a reason to lose the bench line
                 flops = {"error": repr(e)}
     value = float(np.mean([r for r, _ in per_step]))

@@ -115,9 +115,9 @@ int64_t tnsp_sector_queue_min(int64_t min_elems);
  * (kept for differential tests), < 0 only queries.  Returns the previous setting. */
 int tnsp_factor_desc_kernels(int enable);
 
-/* One-sided Jacobi of the work-queue / descriptor kernels: 1 (default) carries the squared column norms through a sweep
- * (exact again at the start of the next: one dot product per column pair), 0 recomputes all three dot products per pair.
- * Both converge to the same factorisation; kept switchable for differential tests.  Returns the previous setting. */
+/* One-sided Jacobi of the work-queue / descriptor kernels: 1 carries the squared column norms through a sweep (exact again
+ * at the start of the next: one dot product per column pair), 0 (default: faster at the column lengths of cfg2, measured)
+ * recomputes all three dot products per pair.  Both converge to the same factorisation.  Returns the previous setting. */
 int tnsp_jacobi_cached_norms(int enable);
 
 /* ---- greedy cross-sector truncation (svd.hpp:429-481): counts[b][i] = kept values of sector i. */

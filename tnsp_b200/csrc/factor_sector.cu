@@ -891,8 +891,11 @@ __device__ void jacobi_svd(double* G, int ldp, double* V, int ldq, int p, int q,
 //   * a sweep whose largest rotation was below 1e-8 (relative) ends the iteration: the cyclic Jacobi method converges
 //     quadratically, so the remaining off-diagonal couplings are O(1e-16) and the confirming sweep is not needed.
 // ldp, ldq even; rows p..ldp-1 of G and q..ldq-1 of V must be (and stay) zero.
-// 1: the Jacobi sweeps carry the squared column norms (tnsp_jacobi_cached_norms); 0: three dot products per pair
-__device__ int g_jacobi_cached_norms = 1;
+// 1: the Jacobi sweeps carry the squared column norms (tnsp_jacobi_cached_norms); 0 (default): three dot products per pair.
+// Measured on B200 (scripts/mb_sector.py, 296 matrices of 216 x 216 in ~7 sectors): 3.26 ms with the carried norms against
+// 2.67 ms without -- the extra shared-memory reads and the per-sweep norm pass cost more than the two saved dot products
+// at these column lengths (30 - 70), so the variant stays off and is kept for longer columns / differential tests.
+__device__ int g_jacobi_cached_norms = 0;
 
 __device__ void jacobi_svd2(double* G, int ldp, double* V, int ldq, int p, int q, int* sh_rot, double* nrm = nullptr) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -2068,7 +2071,7 @@ extern "C" int tnsp_svd_sectors_f64(const int64_t* sect, const int64_t* sect_hos
 // Tuning knob: matrices with at least `min_elems` elements take the per-sector work-queue path, smaller ones the
 // one-CTA-per-chain kernel.  Returns the previous value; a negative argument only queries.
 extern "C" int tnsp_jacobi_cached_norms(int enable) {
-    static int current = 1;
+    static int current = 0;
     const int old = current;
     if (enable >= 0 && enable != current) {
         current = enable ? 1 : 0;
