@@ -423,7 +423,7 @@ def test_descriptor_kernels_agree_with_first_generation(shapes):
 
 @pytest.mark.parametrize("shape", [(216, 216), (36, 216), (150, 120)])
 def test_jacobi_cached_norms_agree_with_three_dot_products(shape):
-    """the sweeps that carry the column norms (default) and the ones that recompute them per pair give the same singular values
+    """the sweeps that carry the column norms and the ones that recompute them per pair (default) give the same singular values
     and both reconstruct, on block-diagonal (discovered sectors) and dense matrices, including a graded spectrum"""
     cu, _ = _both()
     m, n = shape
