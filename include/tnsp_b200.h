@@ -66,6 +66,12 @@ int tnsp_gemm_gather_f64(const int32_t* tab, int64_t m, int64_t n, int64_t k, in
                          const double* a, int64_t a_bstride, const double* b, int64_t b_bstride,
                          double* c, int64_t c_bstride, int nb, void* stream);
 
+/* The row-stream kernel behind tnsp_gemm_gather_f64 skips tensor-core instructions whose A or B fragment is all zero
+ * (block-sparse operands of the charge-dense embedding: 13 % of the fragment pairs of cfg2's 1296 x 216 x 216 contraction are
+ * non-zero).  Results are identical (a product with an all-zero fragment adds exact zeros); enable = 0 switches the test off
+ * for differential tests and dense operands, < 0 only queries.  Returns the previous setting. */
+int tnsp_gemm_skip_zero_fragments(int enable);
+
 /* ---- K3: batched QR / LQ with explicit Q (replaces ?geqrf/?orgqr and ?gelqf/?orglq per sector,
  * qr.hpp:178-304).  sect[ns][8] = (m, n, k, a_off, out1_off, out2_off, s_off, -); the m x n input
  * at a_off is destroyed.  use_qr != 0: out1 = Q (m x k), out2 = R (k x n); else out1 = L, out2 = Q. */

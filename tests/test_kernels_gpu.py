@@ -461,3 +461,33 @@ def test_jacobi_cached_norms_agree_with_three_dot_products(shape):
             sv = np.sort(S)[::-1]
             assert np.abs(sv - ref).max() <= 1e-12 * ref.max()
             assert np.abs((U * S) @ Vt - a[b].reshape(m, n)).max() <= 1e-12 * ref.max() * max(m, n)
+
+
+@pytest.mark.parametrize("dims", [((1296, 216), (216, 216)), ((216, 216), (216, 36)), ((300, 40), (40, 36)), ((64, 7), (7, 100))])
+def test_gemm_zero_fragment_skipping_is_exact(dims):
+    """block-sparse operands (the zero pattern of charge conservation) through the row-stream GEMM with and without the
+    zero-fragment test: identical results, and both equal to the dense product"""
+    cu, _ = _both()
+    (m, k), (_, n) = dims
+    rng = np.random.default_rng(m + n + k)
+    nb = 5
+    qa, qk, qn = rng.integers(0, 5, m), rng.integers(0, 5, k), rng.integers(0, 5, n)
+    a = rng.standard_normal((nb, m, k)) * (qa[:, None] == qk[None, :])
+    b = rng.standard_normal((nb, k, n)) * (qk[:, None] == qn[None, :])
+    a[0] = rng.standard_normal((m, k))          # one fully dense chain, one fully zero
+    b[0] = rng.standard_normal((k, n))
+    a[1] = 0.0
+    T = TAT.No.D.Tensor
+    t1 = T.from_batch(["i", "x"], [TAT.No.Edge(m), TAT.No.Edge(k)], cu.from_numpy(a.reshape(nb, -1)))
+    t2 = T.from_batch(["x", "j"], [TAT.No.Edge(k), TAT.No.Edge(n)], cu.from_numpy(b.reshape(nb, -1)))
+    out = {}
+    old = cu.lib.tnsp_gemm_skip_zero_fragments(-1)
+    try:
+        for mode in (0, 1):
+            cu.lib.tnsp_gemm_skip_zero_fragments(mode)
+            out[mode] = cu.to_numpy(t1.contract(t2, {("x", "x")}).data).reshape(nb, m, n)
+    finally:
+        cu.lib.tnsp_gemm_skip_zero_fragments(old)
+    assert np.array_equal(out[0], out[1])
+    ref = np.matmul(a, b)
+    assert np.abs(out[1] - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()) * k

@@ -87,6 +87,7 @@ class CudaBackend:
         lib.tnsp_sector_queue_min.restype = c_i64
         lib.tnsp_sector_queue_min.argtypes = [c_i64]
         lib.tnsp_factor_desc_kernels.argtypes = [c_int]
+        lib.tnsp_gemm_skip_zero_fragments.argtypes = [c_int]
         lib.tnsp_jacobi_cached_norms.argtypes = [c_int]
         # set by tetragono.dense_embedding: single-descriptor factorisations discover their sectors on the device
         self.sector_discovery = False

@@ -252,6 +252,9 @@ static int launch_gather(const int* tab, int m, int n, int k, int flags, double 
 // ------------------------------------------------------------------------------------------------
 // k-steps (of 4) per register chunk: 8 for the narrow tiles; 4 for NT >= 6, whose 4 * NT accumulator registers would
 // otherwise push the kernel past 128 registers (two 256-thread CTAs per SM need <= 128)
+// zero-fragment skipping of the row-stream GEMM (tnsp_gemm_skip_zero_fragments); on by default
+static int g_skip_zero_fragments = 1;
+
 template <int NT> struct RowstreamCfg { static constexpr int RKS = NT >= 6 ? 4 : 8; static constexpr int MINB = 2; };
 
 // grid (x: slices of the n-passes, y: chain, z: strip ranges of a chain) -- the slices of one strip range are launched
@@ -260,7 +263,7 @@ template <int NT>
 __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_kernel(const int* __restrict__ tab, int m, int n, int k, double alpha,
                                                              const double* __restrict__ a, int64_t abs_, const double* __restrict__ b,
                                                              int64_t bbs, double* __restrict__ c, int64_t cbs, int npass_total,
-                                                             int passes_per_cta, int strips_per_cta) {
+                                                             int passes_per_cta, int strips_per_cta, int skip_zero) {
     constexpr int RKS = RowstreamCfg<NT>::RKS;
     extern __shared__ __align__(16) double gsm[];
     double* Bs = gsm;                                   // [kpad][ldb], zero padded
@@ -321,6 +324,34 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
     cp_async_wait<0>();
     __syncthreads();
 
+    // Zero-fragment map of the staged B slice: bit t of bmask[kstep] is set when the 4 x 8 fragment (k-step, n-tile t) holds a
+    // non-zero.  Symmetric tensors in the charge-dense embedding are block sparse: at cfg2 only 23 % of the B fragments of the
+    // 1296 x 216 x 216 contraction are non-zero (13 % when the A fragment's emptiness is counted too), and a DMMA on an
+    // all-zero fragment cannot change the accumulator -- it is skipped.  The branch is uniform over the CTA (B) / warp (A).
+    unsigned long long* bmask = reinterpret_cast<unsigned long long*>(Bs + (size_t)kpad * ldb);
+    const int ntiles = ncols >> 3;
+    const bool skipping = skip_zero != 0 && ntiles <= 64;
+    if (skipping) {
+        for (int ksb = tid; ksb < kpad / 4; ksb += nthreads) {
+            unsigned long long word = 0ull;
+            for (int t = 0; t < ntiles; ++t) {
+                bool nz = false;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const double* row = Bs + (ksb * 4 + r) * ldb + t * 8;
+#pragma unroll
+                    for (int cc = 0; cc < 8; cc += 2) {
+                        const double2 v = *reinterpret_cast<const double2*>(row + cc);
+                        nz |= (v.x != 0.0) | (v.y != 0.0);
+                    }
+                }
+                if (nz) word |= 1ull << t;
+            }
+            bmask[ksb] = word;
+        }
+        __syncthreads();
+    }
+
     double acc[2][NT][2];
     int seq = 0;
     for (int si = 0; si < my_strips; ++si) {
@@ -340,13 +371,29 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
 #pragma unroll
                     for (int ks = 0; ks < RKS; ++ks) {
                         if (ks < ksteps) {
-                            double fb[NT];
+                            if (skipping) {
+                                const unsigned tiles = (unsigned)(bmask[ch * RKS + ks] >> (pass * NT)) & ((1u << NT) - 1u);
+                                if (tiles == 0u) continue;
+                                const bool a0 = __any_sync(0xffffffffu, fa[0][0][ks] != 0.0);
+                                const bool a1 = __any_sync(0xffffffffu, fa[0][1][ks] != 0.0);
+                                if (!(a0 | a1)) continue;
 #pragma unroll
-                            for (int j = 0; j < NT; ++j) fb[j] = bch[ks * 4 * ldb + j * 8];
+                                for (int j = 0; j < NT; ++j) {
+                                    if (tiles & (1u << j)) {
+                                        const double fbj = bch[ks * 4 * ldb + j * 8];
+                                        if (a0) dmma884(acc[0][j][0], acc[0][j][1], fa[0][0][ks], fbj);
+                                        if (a1) dmma884(acc[1][j][0], acc[1][j][1], fa[0][1][ks], fbj);
+                                    }
+                                }
+                            } else {
+                                double fb[NT];
 #pragma unroll
-                            for (int j = 0; j < NT; ++j) {
-                                dmma884(acc[0][j][0], acc[0][j][1], fa[0][0][ks], fb[j]);
-                                dmma884(acc[1][j][0], acc[1][j][1], fa[0][1][ks], fb[j]);
+                                for (int j = 0; j < NT; ++j) fb[j] = bch[ks * 4 * ldb + j * 8];
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) {
+                                    dmma884(acc[0][j][0], acc[0][j][1], fa[0][0][ks], fb[j]);
+                                    dmma884(acc[1][j][0], acc[1][j][1], fa[0][1][ks], fb[j]);
+                                }
                             }
                         }
                     }
@@ -355,13 +402,29 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
 #pragma unroll
                     for (int ks = 0; ks < RKS; ++ks) {
                         if (ks < ksteps) {
-                            double fb[NT];
+                            if (skipping) {
+                                const unsigned tiles = (unsigned)(bmask[ch * RKS + ks] >> (pass * NT)) & ((1u << NT) - 1u);
+                                if (tiles == 0u) continue;
+                                const bool a0 = __any_sync(0xffffffffu, fa[1][0][ks] != 0.0);
+                                const bool a1 = __any_sync(0xffffffffu, fa[1][1][ks] != 0.0);
+                                if (!(a0 | a1)) continue;
 #pragma unroll
-                            for (int j = 0; j < NT; ++j) fb[j] = bch[ks * 4 * ldb + j * 8];
+                                for (int j = 0; j < NT; ++j) {
+                                    if (tiles & (1u << j)) {
+                                        const double fbj = bch[ks * 4 * ldb + j * 8];
+                                        if (a0) dmma884(acc[0][j][0], acc[0][j][1], fa[1][0][ks], fbj);
+                                        if (a1) dmma884(acc[1][j][0], acc[1][j][1], fa[1][1][ks], fbj);
+                                    }
+                                }
+                            } else {
+                                double fb[NT];
 #pragma unroll
-                            for (int j = 0; j < NT; ++j) {
-                                dmma884(acc[0][j][0], acc[0][j][1], fa[1][0][ks], fb[j]);
-                                dmma884(acc[1][j][0], acc[1][j][1], fa[1][1][ks], fb[j]);
+                                for (int j = 0; j < NT; ++j) fb[j] = bch[ks * 4 * ldb + j * 8];
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) {
+                                    dmma884(acc[0][j][0], acc[0][j][1], fa[1][0][ks], fb[j]);
+                                    dmma884(acc[1][j][0], acc[1][j][1], fa[1][1][ks], fb[j]);
+                                }
                             }
                         }
                     }
@@ -407,8 +470,8 @@ static bool rowstream_shape(int64_t n, int64_t k, int& nt, int& npass, int& pass
     }
     const int64_t kpad = (k + 3) / 4 * 4;
     passes_per_cta = npass;
-    while (passes_per_cta > 1 && kpad * (passes_per_cta * 8 * nt + 4) * 8 > kRowstreamSmemMax) passes_per_cta = (passes_per_cta + 1) / 2;
-    smem = kpad * ((int64_t)passes_per_cta * 8 * nt + 4) * 8;
+    while (passes_per_cta > 1 && kpad * (passes_per_cta * 8 * nt + 4) * 8 + (kpad / 4) * 8 > kRowstreamSmemMax) passes_per_cta = (passes_per_cta + 1) / 2;
+    smem = kpad * ((int64_t)passes_per_cta * 8 * nt + 4) * 8 + (kpad / 4) * 8;     // B slice + zero-fragment map
     return smem <= kRowstreamSmemMax;
 }
 
@@ -432,13 +495,19 @@ static int launch_rowstream(const int* tab, int m, int n, int k, double alpha, c
     const int slices = (npass + passes_per_cta - 1) / passes_per_cta;
     if (nb > 65535) { set_error("tnsp_gemm_gather_f64: more than 65535 chains"); return 1; }
     gemm_rowstream_kernel<NT><<<dim3(slices, nb, ctas), threads, smem, st>>>(tab, m, n, k, alpha, a, abs_, b, bbs, c, cbs, npass, passes_per_cta,
-                                                                             strips_per_cta);
+                                                                             strips_per_cta, g_skip_zero_fragments);
     return check_launch("tnsp_gemm_gather_f64(rowstream)");
 }
 
 }  // namespace tnsp
 
 using namespace tnsp;
+
+extern "C" int tnsp_gemm_skip_zero_fragments(int enable) {
+    const int old = g_skip_zero_fragments;
+    if (enable >= 0) g_skip_zero_fragments = enable ? 1 : 0;
+    return old;
+}
 
 extern "C" int tnsp_gemm_gather_f64(const int32_t* tab, int64_t m, int64_t n, int64_t k, int flags, double alpha, const double* a,
                                     int64_t abs_, const double* b, int64_t bbs, double* c, int64_t cbs, int nb, void* stream) {
