@@ -254,18 +254,17 @@ static int launch_gather(const int* tab, int m, int n, int k, int flags, double 
 // otherwise push the kernel past 128 registers (two 256-thread CTAs per SM need <= 128)
 // zero-fragment skipping of the row-stream GEMM (tnsp_gemm_skip_zero_fragments); on by default
 static int g_skip_zero_fragments = 1;
-// the fragment tests pay for themselves on the tensor-bound shapes; the k = 36 contractions are HBM bound and stay branch free
 constexpr int kSkipMinK = 96;
 
-template <int NT> struct RowstreamCfg { static constexpr int RKS = NT >= 6 ? 4 : (NT == 5 ? 5 : 8); static constexpr int MINB = 2; };
+template <int NT> struct RowstreamCfg { static constexpr int RKS = NT >= 6 ? 4 : 8; static constexpr int MINB = 2; };
 
 // grid (x: slices of the n-passes, y: chain, z: strip ranges of a chain) -- the slices of one strip range are launched
 // next to each other so that their re-reads of the same A rows hit L2; blockDim 128 or 256
-template <int NT>
+template <int NT, bool SKIP>
 __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_kernel(const int* __restrict__ tab, int m, int n, int k, double alpha,
                                                              const double* __restrict__ a, int64_t abs_, const double* __restrict__ b,
                                                              int64_t bbs, double* __restrict__ c, int64_t cbs, int npass_total,
-                                                             int passes_per_cta, int strips_per_cta, int skip_zero) {
+                                                             int passes_per_cta, int strips_per_cta) {
     constexpr int RKS = RowstreamCfg<NT>::RKS;
     extern __shared__ __align__(16) double gsm[];
     double* Bs = gsm;                                   // [kpad][ldb], zero padded
@@ -303,14 +302,6 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
     const int my_strips = avail > 0 ? (avail + nwarps - 1) / nwarps : 0;   // strips s_begin + warp, + nwarps, ...
     const int total = my_strips * npass * nchunk;
 
-    // Zero-fragment map of the staged B slice: bit t of bmask[kstep] is set when the 4 x 8 fragment (k-step, n-tile t) holds a
-    // non-zero.  Symmetric tensors in the charge-dense embedding are block sparse: at cfg2 only 23 % of the B fragments of the
-    // 1296 x 216 x 216 contraction are non-zero (13 % when the A fragment's emptiness is counted too), and a DMMA on an
-    // all-zero fragment cannot change the accumulator -- it is skipped.  The branch is uniform over the CTA (B) / warp (A).
-    unsigned long long* bmask = reinterpret_cast<unsigned long long*>(Bs + (size_t)kpad * ldb);
-    const int ntiles = ncols >> 3;
-    const bool skipping = skip_zero != 0 && ntiles <= 64;
-    const unsigned long long tile_mask = (1ull << NT) - 1ull;
     double fa[2][2][RKS];       // [buffer][row block][k-step]
     int ro0 = -1, ro1 = -1;     // row offsets of the strip the NEXT load belongs to
     auto load_chunk = [&](int seq, int buf) {
@@ -321,24 +312,28 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
             ro0 = r0 < m ? __ldg(aro + r0) : -1;
             ro1 = r1 < m ? __ldg(aro + r1) : -1;
         }
-        const int ps = (seq / nchunk) % npass;
 #pragma unroll
         for (int ks = 0; ks < RKS; ++ks) {
-            const int kstep = ch * RKS + ks;
-            const int kk = kstep * 4 + tig;
-            // a k-step whose B fragments are all zero for this pass is never multiplied: do not fetch its A fragments either
-            const bool wanted = !skipping || (kstep < kpad / 4 && ((bmask[kstep] >> (ps * NT)) & tile_mask) != 0ull);
-            const int co = (wanted && kk < k) ? __ldg(aco + kk) : -1;
+            const int kk = (ch * RKS + ks) * 4 + tig;
+            const int co = kk < k ? __ldg(aco + kk) : -1;
             fa[buf][0][ks] = (co | ro0) >= 0 ? __ldg(A + (ro0 + co)) : 0.0;
             fa[buf][1][ks] = (co | ro1) >= 0 ? __ldg(A + (ro1 + co)) : 0.0;
         }
     };
 
-
-    if (!skipping && total > 0) load_chunk(0, 0);     // overlaps the staging of B
+    if (total > 0) load_chunk(0, 0);
     cp_async_wait<0>();
     __syncthreads();
-    if (skipping) {
+
+    // Zero-fragment map of the staged B slice: bit t of bmask[kstep] is set when the 4 x 8 fragment (k-step, n-tile t) holds a
+    // non-zero.  Symmetric tensors in the charge-dense embedding are block sparse: at cfg2 only 23 % of the B fragments of the
+    // 1296 x 216 x 216 contraction are non-zero (13 % when the A fragment's emptiness is counted too), and a DMMA on an
+    // all-zero fragment cannot change the accumulator -- it is skipped.  The branch is uniform over the CTA (B) / warp (A).
+    // SKIP is a template parameter: the dense instantiation is the branch-free kernel, instruction for instruction (a run-time
+    // switch inside the unrolled loop cost the k = 36 shapes 38 %).  Measured at cfg2 (2368 chains): 1296 x 216 x 216 10.9 -> 8.1 ms.
+    unsigned long long* bmask = reinterpret_cast<unsigned long long*>(Bs + (size_t)kpad * ldb);
+    const int ntiles = ncols >> 3;                      // <= 64 whenever the host selects SKIP
+    if constexpr (SKIP) {
         for (int ksb = tid; ksb < kpad / 4; ksb += nthreads) {
             unsigned long long word = 0ull;
             for (int t = 0; t < ntiles; ++t) {
@@ -357,7 +352,6 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
             bmask[ksb] = word;
         }
         __syncthreads();
-        if (total > 0) load_chunk(0, 0);
     }
 
     double acc[2][NT][2];
@@ -379,23 +373,19 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
 #pragma unroll
                     for (int ks = 0; ks < RKS; ++ks) {
                         if (ks < ksteps) {
-                            if (skipping) {
-                                // coarse tests only (one per k-step and per 8-row block): the NT tensor-core instructions
-                                // behind each stay a branch-free, independent group
-                                if (((bmask[ch * RKS + ks] >> (pass * NT)) & tile_mask) == 0ull) continue;
+                            if constexpr (SKIP) {
+                                const unsigned tiles = (unsigned)(bmask[ch * RKS + ks] >> (pass * NT)) & ((1u << NT) - 1u);
+                                if (tiles == 0u) continue;
                                 const bool a0 = __any_sync(0xffffffffu, fa[0][0][ks] != 0.0);
                                 const bool a1 = __any_sync(0xffffffffu, fa[0][1][ks] != 0.0);
                                 if (!(a0 | a1)) continue;
-                                double fb[NT];
 #pragma unroll
-                                for (int j = 0; j < NT; ++j) fb[j] = bch[ks * 4 * ldb + j * 8];
-                                if (a0) {
-#pragma unroll
-                                    for (int j = 0; j < NT; ++j) dmma884(acc[0][j][0], acc[0][j][1], fa[0][0][ks], fb[j]);
-                                }
-                                if (a1) {
-#pragma unroll
-                                    for (int j = 0; j < NT; ++j) dmma884(acc[1][j][0], acc[1][j][1], fa[0][1][ks], fb[j]);
+                                for (int j = 0; j < NT; ++j) {
+                                    if (tiles & (1u << j)) {
+                                        const double fbj = bch[ks * 4 * ldb + j * 8];
+                                        if (a0) dmma884(acc[0][j][0], acc[0][j][1], fa[0][0][ks], fbj);
+                                        if (a1) dmma884(acc[1][j][0], acc[1][j][1], fa[0][1][ks], fbj);
+                                    }
                                 }
                             } else {
                                 double fb[NT];
@@ -414,23 +404,19 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
 #pragma unroll
                     for (int ks = 0; ks < RKS; ++ks) {
                         if (ks < ksteps) {
-                            if (skipping) {
-                                // coarse tests only (one per k-step and per 8-row block): the NT tensor-core instructions
-                                // behind each stay a branch-free, independent group
-                                if (((bmask[ch * RKS + ks] >> (pass * NT)) & tile_mask) == 0ull) continue;
+                            if constexpr (SKIP) {
+                                const unsigned tiles = (unsigned)(bmask[ch * RKS + ks] >> (pass * NT)) & ((1u << NT) - 1u);
+                                if (tiles == 0u) continue;
                                 const bool a0 = __any_sync(0xffffffffu, fa[1][0][ks] != 0.0);
                                 const bool a1 = __any_sync(0xffffffffu, fa[1][1][ks] != 0.0);
                                 if (!(a0 | a1)) continue;
-                                double fb[NT];
 #pragma unroll
-                                for (int j = 0; j < NT; ++j) fb[j] = bch[ks * 4 * ldb + j * 8];
-                                if (a0) {
-#pragma unroll
-                                    for (int j = 0; j < NT; ++j) dmma884(acc[0][j][0], acc[0][j][1], fa[1][0][ks], fb[j]);
-                                }
-                                if (a1) {
-#pragma unroll
-                                    for (int j = 0; j < NT; ++j) dmma884(acc[1][j][0], acc[1][j][1], fa[1][1][ks], fb[j]);
+                                for (int j = 0; j < NT; ++j) {
+                                    if (tiles & (1u << j)) {
+                                        const double fbj = bch[ks * 4 * ldb + j * 8];
+                                        if (a0) dmma884(acc[0][j][0], acc[0][j][1], fa[1][0][ks], fbj);
+                                        if (a1) dmma884(acc[1][j][0], acc[1][j][1], fa[1][1][ks], fbj);
+                                    }
                                 }
                             } else {
                                 double fb[NT];
@@ -496,7 +482,8 @@ static int launch_rowstream(const int* tab, int m, int n, int k, double alpha, c
                             double* c, int64_t cbs, int nb, int npass, int passes_per_cta, int64_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gemm_rowstream_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowstreamSmemMax);
+        cudaFuncSetAttribute(gemm_rowstream_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowstreamSmemMax);
+        cudaFuncSetAttribute(gemm_rowstream_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowstreamSmemMax);
         attr_set = true;
     }
     // a large B slice limits the CTAs per SM: use 8 warps per CTA then, so that enough loads stay in flight
@@ -510,8 +497,13 @@ static int launch_rowstream(const int* tab, int m, int n, int k, double alpha, c
     ctas = (nstrips + strips_per_cta - 1) / strips_per_cta;
     const int slices = (npass + passes_per_cta - 1) / passes_per_cta;
     if (nb > 65535) { set_error("tnsp_gemm_gather_f64: more than 65535 chains"); return 1; }
-    gemm_rowstream_kernel<NT><<<dim3(slices, nb, ctas), threads, smem, st>>>(tab, m, n, k, alpha, a, abs_, b, bbs, c, cbs, npass, passes_per_cta,
-                                                                             strips_per_cta, (g_skip_zero_fragments && k >= kSkipMinK) ? 1 : 0);
+    // the fragment tests pay for themselves on the tensor-bound shapes (long k, wide n); the others keep the branch-free kernel
+    if (NT >= 6 && g_skip_zero_fragments && k >= kSkipMinK && passes_per_cta * NT <= 64)
+        gemm_rowstream_kernel<NT, true><<<dim3(slices, nb, ctas), threads, smem, st>>>(tab, m, n, k, alpha, a, abs_, b, bbs, c, cbs, npass,
+                                                                                       passes_per_cta, strips_per_cta);
+    else
+        gemm_rowstream_kernel<NT, false><<<dim3(slices, nb, ctas), threads, smem, st>>>(tab, m, n, k, alpha, a, abs_, b, bbs, c, cbs, npass,
+                                                                                        passes_per_cta, strips_per_cta);
     return check_launch("tnsp_gemm_gather_f64(rowstream)");
 }
 
