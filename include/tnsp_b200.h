@@ -68,8 +68,9 @@ int tnsp_gemm_gather_f64(const int32_t* tab, int64_t m, int64_t n, int64_t k, in
 
 /* The row-stream kernel behind tnsp_gemm_gather_f64 skips tensor-core instructions whose A or B fragment is all zero
  * (block-sparse operands of the charge-dense embedding: 13 % of the fragment pairs of cfg2's 1296 x 216 x 216 contraction are
- * non-zero).  Results are identical (a product with an all-zero fragment adds exact zeros); enable = 0 switches the test off
- * for differential tests and dense operands, < 0 only queries.  Returns the previous setting. */
+ * non-zero; 1296 x 216 x 216 x 2368 chains: 10.9 -> 7.9 ms).  Results are identical (a product with an all-zero fragment adds
+ * exact zeros).  Off by default -- on operands without zeros the tests cost 45 % -- and switched on by the dense embedding of
+ * symmetric models; < 0 only queries.  Returns the previous setting. */
 int tnsp_gemm_skip_zero_fragments(int enable);
 
 /* ---- K3: batched QR / LQ with explicit Q (replaces ?geqrf/?orgqr and ?gelqf/?orglq per sector,

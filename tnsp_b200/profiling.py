@@ -178,6 +178,8 @@ def roofline_of_dominant(breakdown, peaks, top_shapes=None, traffic_table=None):
         peak = measure_fp64_gemm_tflops()
         ach = v["flops"] / sec / 1e12
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-                "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no FP64 entry in MEASURED_PEAKS.json)", **extra}
+                "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no FP64 entry in MEASURED_PEAKS.json)",
+                "flop_count": "dense plan 2 m n k per launch; with zero-fragment skipping (symmetric models) fewer tensor-core "
+                              "instructions are issued, so a shape's rate may exceed the pipe's peak", **extra}
     return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
             "peak_source": which, **extra}
