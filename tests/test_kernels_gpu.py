@@ -483,11 +483,12 @@ def test_gemm_zero_fragment_skipping_is_exact(dims):
     out = {}
     old = cu.lib.tnsp_gemm_skip_zero_fragments(-1)
     try:
-        for mode in (0, 1):
+        for mode in range(5):                    # 0 dense, 1 .. 4 the skipping variants
             cu.lib.tnsp_gemm_skip_zero_fragments(mode)
             out[mode] = cu.to_numpy(t1.contract(t2, {("x", "x")}).data).reshape(nb, m, n)
     finally:
         cu.lib.tnsp_gemm_skip_zero_fragments(old)
-    assert np.array_equal(out[0], out[1])
+    for mode in range(1, 5):
+        assert np.array_equal(out[0], out[mode]), mode
     ref = np.matmul(a, b)
     assert np.abs(out[1] - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()) * k

@@ -261,7 +261,10 @@ template <int NT> struct RowstreamCfg { static constexpr int RKS = NT >= 6 ? 4 :
 
 // grid (x: slices of the n-passes, y: chain, z: strip ranges of a chain) -- the slices of one strip range are launched
 // next to each other so that their re-reads of the same A rows hit L2; blockDim 128 or 256
-template <int NT, bool SKIP>
+// SKIP: 0 dense (branch free); 1 fine tests (k-step x tile from the B map, 8-row block of A by warp vote); 2 coarse tests (k-step x
+// pass, 8-row block; the NT instructions behind a test stay one independent group); 3 / 4 = 1 / 2 + the A fragments of k-steps no tile
+// of the pass needs are not fetched
+template <int NT, int SKIP>
 __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_kernel(const int* __restrict__ tab, int m, int n, int k, double alpha,
                                                              const double* __restrict__ a, int64_t abs_, const double* __restrict__ b,
                                                              int64_t bbs, double* __restrict__ c, int64_t cbs, int npass_total,
@@ -285,6 +288,7 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
     const int npass = min(passes_per_cta, npass_total - pass_begin);
     const int ncols = passes_per_cta * 8 * NT;
     const int ldb = ncols + 4;
+    const unsigned long long* bmask_ld = reinterpret_cast<const unsigned long long*>(Bs + (size_t)kpad * ldb);   // zero-fragment map, filled below
     const int colbase = pass_begin * 8 * NT;
 
     // stage this CTA's slice of B: element (kk, cc) <- B[bro[kk] + bco[colbase + cc]]
@@ -313,16 +317,26 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
             ro0 = r0 < m ? __ldg(aro + r0) : -1;
             ro1 = r1 < m ? __ldg(aro + r1) : -1;
         }
+        unsigned long long want = ~0ull;                 // bit ks: some tile of this chunk's pass needs k-step ks
+        if constexpr (SKIP >= 3) {
+            const int ps = (seq / nchunk) % npass;
+            want = 0ull;
+#pragma unroll
+            for (int ks = 0; ks < RKS; ++ks) {
+                const int kstep = ch * RKS + ks;
+                if (kstep < kpad / 4 && ((unsigned)(bmask_ld[kstep] >> (ps * NT)) & ((1u << NT) - 1u)) != 0u) want |= 1ull << ks;
+            }
+        }
 #pragma unroll
         for (int ks = 0; ks < RKS; ++ks) {
             const int kk = (ch * RKS + ks) * 4 + tig;
-            const int co = kk < k ? __ldg(aco + kk) : -1;
+            const int co = (kk < k && ((want >> ks) & 1ull)) ? __ldg(aco + kk) : -1;
             fa[buf][0][ks] = (co | ro0) >= 0 ? __ldg(A + (ro0 + co)) : 0.0;
             fa[buf][1][ks] = (co | ro1) >= 0 ? __ldg(A + (ro1 + co)) : 0.0;
         }
     };
 
-    if (total > 0) load_chunk(0, 0);
+    if (SKIP < 3 && total > 0) load_chunk(0, 0);      // overlaps the staging of B
     cp_async_wait<0>();
     __syncthreads();
 
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
     // switch inside the unrolled loop cost the k = 36 shapes 38 %).  Measured at cfg2 (2368 chains): 1296 x 216 x 216 10.9 -> 8.1 ms.
     unsigned long long* bmask = reinterpret_cast<unsigned long long*>(Bs + (size_t)kpad * ldb);
     const int ntiles = ncols >> 3;                      // <= 64 whenever the host selects SKIP
-    if constexpr (SKIP) {
+    if constexpr (SKIP != 0) {
         for (int ksb = tid; ksb < kpad / 4; ksb += nthreads) {
             unsigned long long word = 0ull;
             for (int t = 0; t < ntiles; ++t) {
@@ -354,6 +368,7 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
         }
         __syncthreads();
     }
+    if (SKIP >= 3 && total > 0) load_chunk(0, 0);
 
     double acc[2][NT][2];
     int seq = 0;
@@ -374,7 +389,7 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
 #pragma unroll
                     for (int ks = 0; ks < RKS; ++ks) {
                         if (ks < ksteps) {
-                            if constexpr (SKIP) {
+                            if constexpr (SKIP == 1 || SKIP == 3) {
                                 const unsigned tiles = (unsigned)(bmask[ch * RKS + ks] >> (pass * NT)) & ((1u << NT) - 1u);
                                 if (tiles == 0u) continue;
                                 const bool a0 = __any_sync(0xffffffffu, fa[0][0][ks] != 0.0);
@@ -387,6 +402,22 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
                                         if (a0) dmma884(acc[0][j][0], acc[0][j][1], fa[0][0][ks], fbj);
                                         if (a1) dmma884(acc[1][j][0], acc[1][j][1], fa[0][1][ks], fbj);
                                     }
+                                }
+                            } else if constexpr (SKIP == 2 || SKIP == 4) {
+                                if (((unsigned)(bmask[ch * RKS + ks] >> (pass * NT)) & ((1u << NT) - 1u)) == 0u) continue;
+                                const bool a0 = __any_sync(0xffffffffu, fa[0][0][ks] != 0.0);
+                                const bool a1 = __any_sync(0xffffffffu, fa[0][1][ks] != 0.0);
+                                if (!(a0 | a1)) continue;
+                                double fb[NT];
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) fb[j] = bch[ks * 4 * ldb + j * 8];
+                                if (a0) {
+#pragma unroll
+                                    for (int j = 0; j < NT; ++j) dmma884(acc[0][j][0], acc[0][j][1], fa[0][0][ks], fb[j]);
+                                }
+                                if (a1) {
+#pragma unroll
+                                    for (int j = 0; j < NT; ++j) dmma884(acc[1][j][0], acc[1][j][1], fa[0][1][ks], fb[j]);
                                 }
                             } else {
                                 double fb[NT];
@@ -405,7 +436,7 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
 #pragma unroll
                     for (int ks = 0; ks < RKS; ++ks) {
                         if (ks < ksteps) {
-                            if constexpr (SKIP) {
+                            if constexpr (SKIP == 1 || SKIP == 3) {
                                 const unsigned tiles = (unsigned)(bmask[ch * RKS + ks] >> (pass * NT)) & ((1u << NT) - 1u);
                                 if (tiles == 0u) continue;
                                 const bool a0 = __any_sync(0xffffffffu, fa[1][0][ks] != 0.0);
@@ -418,6 +449,22 @@ __global__ void __launch_bounds__(256, RowstreamCfg<NT>::MINB) gemm_rowstream_ke
                                         if (a0) dmma884(acc[0][j][0], acc[0][j][1], fa[1][0][ks], fbj);
                                         if (a1) dmma884(acc[1][j][0], acc[1][j][1], fa[1][1][ks], fbj);
                                     }
+                                }
+                            } else if constexpr (SKIP == 2 || SKIP == 4) {
+                                if (((unsigned)(bmask[ch * RKS + ks] >> (pass * NT)) & ((1u << NT) - 1u)) == 0u) continue;
+                                const bool a0 = __any_sync(0xffffffffu, fa[1][0][ks] != 0.0);
+                                const bool a1 = __any_sync(0xffffffffu, fa[1][1][ks] != 0.0);
+                                if (!(a0 | a1)) continue;
+                                double fb[NT];
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) fb[j] = bch[ks * 4 * ldb + j * 8];
+                                if (a0) {
+#pragma unroll
+                                    for (int j = 0; j < NT; ++j) dmma884(acc[0][j][0], acc[0][j][1], fa[1][0][ks], fb[j]);
+                                }
+                                if (a1) {
+#pragma unroll
+                                    for (int j = 0; j < NT; ++j) dmma884(acc[1][j][0], acc[1][j][1], fa[1][1][ks], fb[j]);
                                 }
                             } else {
                                 double fb[NT];
@@ -483,8 +530,13 @@ static int launch_rowstream(const int* tab, int m, int n, int k, double alpha, c
                             double* c, int64_t cbs, int nb, int npass, int passes_per_cta, int64_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gemm_rowstream_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowstreamSmemMax);
-        cudaFuncSetAttribute(gemm_rowstream_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowstreamSmemMax);
+        cudaFuncSetAttribute(gemm_rowstream_kernel<NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowstreamSmemMax);
+        if constexpr (NT >= 6) {
+            cudaFuncSetAttribute(gemm_rowstream_kernel<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowstreamSmemMax);
+            cudaFuncSetAttribute(gemm_rowstream_kernel<NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowstreamSmemMax);
+            cudaFuncSetAttribute(gemm_rowstream_kernel<NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowstreamSmemMax);
+            cudaFuncSetAttribute(gemm_rowstream_kernel<NT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowstreamSmemMax);
+        }
         attr_set = true;
     }
     // a large B slice limits the CTAs per SM: use 8 warps per CTA then, so that enough loads stay in flight
@@ -499,12 +551,22 @@ static int launch_rowstream(const int* tab, int m, int n, int k, double alpha, c
     const int slices = (npass + passes_per_cta - 1) / passes_per_cta;
     if (nb > 65535) { set_error("tnsp_gemm_gather_f64: more than 65535 chains"); return 1; }
     // the fragment tests pay for themselves on the tensor-bound shapes (long k, wide n); the others keep the branch-free kernel
-    if (NT >= 6 && g_skip_zero_fragments && k >= kSkipMinK && passes_per_cta * NT <= 64)
-        gemm_rowstream_kernel<NT, true><<<dim3(slices, nb, ctas), threads, smem, st>>>(tab, m, n, k, alpha, a, abs_, b, bbs, c, cbs, npass,
-                                                                                       passes_per_cta, strips_per_cta);
-    else
-        gemm_rowstream_kernel<NT, false><<<dim3(slices, nb, ctas), threads, smem, st>>>(tab, m, n, k, alpha, a, abs_, b, bbs, c, cbs, npass,
-                                                                                        passes_per_cta, strips_per_cta);
+    const int mode = (NT >= 6 && k >= kSkipMinK && passes_per_cta * NT <= 64) ? g_skip_zero_fragments : 0;
+#define TNSP_ROWSTREAM_LAUNCH(S)                                                                                                         \
+    gemm_rowstream_kernel<NT, S><<<dim3(slices, nb, ctas), threads, smem, st>>>(tab, m, n, k, alpha, a, abs_, b, bbs, c, cbs, npass,    \
+                                                                                passes_per_cta, strips_per_cta)
+    if constexpr (NT >= 6) {
+        switch (mode) {
+            case 1: TNSP_ROWSTREAM_LAUNCH(1); break;
+            case 2: TNSP_ROWSTREAM_LAUNCH(2); break;
+            case 3: TNSP_ROWSTREAM_LAUNCH(3); break;
+            case 4: TNSP_ROWSTREAM_LAUNCH(4); break;
+            default: TNSP_ROWSTREAM_LAUNCH(0); break;
+        }
+    } else {
+        TNSP_ROWSTREAM_LAUNCH(0);
+    }
+#undef TNSP_ROWSTREAM_LAUNCH
     return check_launch("tnsp_gemm_gather_f64(rowstream)");
 }
 
@@ -514,7 +576,7 @@ using namespace tnsp;
 
 extern "C" int tnsp_gemm_skip_zero_fragments(int enable) {
     const int old = g_skip_zero_fragments;
-    if (enable >= 0) g_skip_zero_fragments = enable ? 1 : 0;
+    if (enable >= 0) g_skip_zero_fragments = enable > 4 ? 1 : enable;      // 1 .. 4 select the variant (see the kernel)
     return old;
 }
 
