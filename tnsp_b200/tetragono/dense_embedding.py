@@ -30,7 +30,7 @@ def embed_lattice(lattice, NoTensor=None):
     # operands: 13 % of the fragment pairs of cfg2's heaviest contraction are non-zero); truly dense models keep it off
     B = _bk.get()
     if hasattr(B, "lib") and hasattr(B.lib, "tnsp_gemm_skip_zero_fragments"):
-        B.lib.tnsp_gemm_skip_zero_fragments(1)
+        B.lib.tnsp_gemm_skip_zero_fragments(2)      # coarse tests: marginally the fastest of the four variants (profiles/r01_s9_mb_gemm_sparse.txt)
     state = AbstractState(No, lattice.L1, lattice.L2)
     for (l1, l2, orbit), edge in lattice.physics_edges:
         state.physics_edges[l1, l2, orbit] = edge.dimension
