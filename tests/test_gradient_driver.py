@@ -35,7 +35,7 @@ def test_driver_rejects_out_of_scope_options():
     meta, z = load(DRIVER_CASES[0])
     lat = build_lattice(meta, z)
     for kw in ({"sampling_method": "direct"}, {"use_natural_gradient_by_direct_pseudo_inverse": True, "grad_step_size": 0.1},
-               {"fix_gauge": True}, {"save_state_file": "x"}, {"use_check_difference": True}):
+               {"fix_gauge": True}, {"use_check_difference": True}):
         with pytest.raises(NotImplementedError):
             next(gradient_descent(lat, 1, 1, **{"sampling_configurations": np.array(z["start_configuration"]), **kw}))
     with pytest.raises(ValueError):
@@ -74,3 +74,21 @@ def test_ergodic_driver_energy_is_exact_expectation():
         num += w * obs.total_energy[0]
         den += w
     assert abs(whole["energy"][0] - num / den) <= 1e-9 * abs(num / den)
+
+
+def test_driver_writes_reference_checkpoints(tmp_path):
+    from tnsp_b200.tetragono.checkpoint import load_reference_state, read_configurations
+    meta, z = load("driver_heis_3x3_D2_Dc4_plain")
+    lat = build_lattice(meta, z)
+    conf = np.array(z["start_configuration"])
+    TAT.random.seed(9)
+    steps = list(gradient_descent(lat, 4, 2, 0.01, sampling_method="sweep", configuration_cut_dimension=4, sampling_configurations=conf,
+                                  save_state_file=str(tmp_path / "state_%s.dat"), save_configuration_file=str(tmp_path / "conf_%s.dat")))
+    assert len(steps) == 2
+    back = load_reference_state(str(tmp_path / "state_1.dat"))
+    for l1 in range(lat.L1):
+        for l2 in range(lat.L2):
+            assert np.array_equal(np.asarray(back[l1, l2].storage), np.asarray(lat[l1, l2].storage))
+    assert np.array_equal(read_configurations(str(tmp_path / "conf_1.dat")), conf)
+    raw = np.fromfile(str(tmp_path / "conf_1.dat"), dtype=np.int64)
+    assert list(raw[:2]) == [1, conf.ndim] and list(raw[2:2 + conf.ndim]) == list(conf.shape)      # the reference's header

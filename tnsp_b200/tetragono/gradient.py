@@ -12,8 +12,8 @@ What changes against the reference is only what the B200 design needs:
   for the call sequence.
 
 Entry points that SURVEY.md section 8 marks out of the path raise NotImplementedError instead of silently doing something
-else: direct sampling (8f-1), pseudo-inverse SR (8f-4), gauge fixing (8f-3), numerical check-difference (debug aid),
-state / configuration files (8f-2).
+else: direct sampling (8f-1), pseudo-inverse SR (8f-4), gauge fixing (8f-3), numerical check-difference (debug aid).
+State and configuration files are written in the reference's own formats (checkpoint.py).
 """
 from __future__ import annotations
 
@@ -146,8 +146,6 @@ def gradient_descent(
         raise NotImplementedError("pseudo-inverse SR needs ScaLAPACK (SURVEY.md 8f-4); use the conjugate-gradient SR")
     if fix_gauge:
         raise NotImplementedError("gauge fixing (expand_dimension) is SURVEY.md 8f-3")
-    if save_state_file or save_configuration_file:
-        raise NotImplementedError("state / configuration files are SURVEY.md 8f-2")
     if sampling_method == "ergodic" and chains != 1:
         raise ValueError("the ergodic sampler enumerates configurations one at a time: chains must be 1")
 
@@ -284,6 +282,13 @@ def gradient_descent(
 
         yield (measurement_whole_result, measurement_result)
 
+        # checkpoints in the reference's own formats (utility.py:340-418): its `pickle.load` / `read_configurations` read them
+        if save_state_file and rank == 0:
+            from .checkpoint import save_reference_state
+            save_reference_state(state, save_state_file.replace("%s", str(grad_step)).replace("%t", time_str))
+        if save_configuration_file and isinstance(sampling_configurations, np.ndarray):
+            from .checkpoint import write_configurations
+            write_configurations(sampling_configurations, save_configuration_file.replace("%s", str(grad_step)).replace("%t", time_str))
 
 def bcast_lattice(state, root=0):
     """lattice.py:950-954.  Every rank has applied the same all-reduced update, the parameters are already identical;
