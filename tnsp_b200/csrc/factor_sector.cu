@@ -1239,8 +1239,11 @@ constexpr int kQSmallDoubles = 9 * 1024;    // 72 KiB  -> 3 CTAs / SM
 constexpr int kQSmallThreads = 256;
 constexpr int kQBigDoubles = 25 * 1024;     // 200 KiB -> 1 CTA / SM
 constexpr int kQBigThreads = 1024;
-constexpr int kQClasses = 3;                // 0: big (or spilling), 1: small & heavy, 2: small & light
-// qctl layout: [0..2] item counts per class, [3] ticket of the big kernel, [4] ticket of the small kernel
+constexpr int kQMidDoubles = 7040;          // 55 KiB  -> 4 CTAs / SM (the register file allows no more at 256 threads x ~58 registers)
+constexpr int kQClasses = 3;                // by shared-memory footprint: 0: beyond 72 KiB (big kernel), 1: 55 - 72 KiB, 2: up to 55 KiB
+// qctl layout: [0..2] item counts per class, [3..5] tickets of the kernels that consume class 0 / 1 / 2.
+// The one-sided Jacobi and the panel factorisations are latency chains: what a SM delivers is set by how many independent sectors
+// it holds, i.e. by the footprint class -- most sectors of cfg2 (<= 58 x 58) fit the 55 KiB class and run four to a SM.
 
 __host__ __device__ inline int gmap_smax(int m, int n) { return (m < n ? m : n) + 2; }
 __host__ __device__ inline int64_t gmap_stride(int m, int n) { return 2 + 5 * (int64_t)gmap_smax(m, n) + 2 * ((int64_t)n + m); }
@@ -1323,7 +1326,7 @@ __global__ void __launch_bounds__(kSecThreads, 2) sector_discover_kernel(const i
                     need = qr_sector_need(pp, qq);
                     cost = (int64_t)pp * qq * (pp < qq ? pp : qq);
                 }
-                const int cls = need > kQSmallDoubles ? 0 : (cost >= 16 * 1024 ? 1 : 2);
+                const int cls = need > kQSmallDoubles ? 0 : (need > kQMidDoubles ? 1 : 2);
                 const int at = atomicAdd(&qctl[cls], 1);
                 qitems[(int64_t)cls * qcap + at] = make_int2(b, s);
             }
@@ -1332,20 +1335,14 @@ __global__ void __launch_bounds__(kSecThreads, 2) sector_discover_kernel(const i
     }
 }
 
-// pops the next work item of a persistent CTA; which = 0: class 0 (big kernel), 1: classes 1 then 2 (small kernel)
+// pops the next work item of a persistent CTA of the kernel that consumes class `which`
 __device__ __forceinline__ bool pop_item(int which, int* qctl, const int2* qitems, int64_t qcap, int* sh_ticket, int2& item) {
     __syncthreads();
     if (threadIdx.x == 0) *sh_ticket = atomicAdd(&qctl[3 + which], 1);
     __syncthreads();
     const int t = *sh_ticket;
-    if (which == 0) {
-        if (t >= qctl[0]) return false;
-        item = qitems[t];
-    } else {
-        const int c1 = qctl[1], c2 = qctl[2];
-        if (t >= c1 + c2) return false;
-        item = t < c1 ? qitems[qcap + t] : qitems[2 * qcap + (t - c1)];
-    }
+    if (t >= qctl[which]) return false;
+    item = qitems[(int64_t)which * qcap + t];
     return true;
 }
 
@@ -1619,7 +1616,10 @@ static int qr_queue_launch(const int64_t* sect, const int64_t* sh, const double*
     }
     qr_work_kernel<<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, g_qws.gmap, gstride,
                                                                          g_qws.qctl, g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
-    return check_launch("tnsp_qr_sectors_f64(small)");
+    if (check_launch("tnsp_qr_sectors_f64(72 KiB class)")) return 1;
+    qr_work_kernel<<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, g_qws.gmap, gstride,
+                                                                       g_qws.qctl, g_qws.qitems, qcap, 2, kQMidDoubles, nullptr, 0);
+    return check_launch("tnsp_qr_sectors_f64(55 KiB class)");
 }
 
 static int svd_queue_launch(const int64_t* sect, const int64_t* sh, const double* a, int64_t abs_, double* out1, int64_t o1bs, double* s,
@@ -1639,7 +1639,10 @@ static int svd_queue_launch(const int64_t* sect, const int64_t* sh, const double
     }
     svd_work_kernel<<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(sect, a, abs_, work, wbs, g_qws.gmap, gstride, g_qws.qctl,
                                                                           g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
-    if (check_launch("tnsp_svd_sectors_f64(small)")) return 1;
+    if (check_launch("tnsp_svd_sectors_f64(72 KiB class)")) return 1;
+    svd_work_kernel<<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(sect, a, abs_, work, wbs, g_qws.gmap, gstride, g_qws.qctl,
+                                                                        g_qws.qitems, qcap, 2, kQMidDoubles, nullptr, 0);
+    if (check_launch("tnsp_svd_sectors_f64(55 KiB class)")) return 1;
     const int rank_in_smem = k * 12 <= 96 * 1024;
     const int split = rank_in_smem ? 4 : 1;
     svd_finish_kernel<<<dim3(nb, split), 256, rank_in_smem ? k * 12 : 0, st>>>(sect, out1, o1bs, s, sbs, out2, o2bs, work, wbs, g_qws.gmap,
