@@ -500,7 +500,7 @@ __device__ void block_reflect(double* W, int ld, int p, int j0, int c_begin, int
 // The same update for a W that lives in GLOBAL memory (sectors beyond shared memory): Vp / Tm are in shared memory and the
 // loads of W are issued four k-steps ahead of the DMMAs that consume them (the plain loop above has one dependent L2 round
 // trip per step).
-__device__ void block_reflect_g(double* __restrict__ W, int ld, int p, int j0, int c_begin, int c_end, const double* Vp, const double* Tm,
+__device__ __noinline__ void block_reflect_g(double* __restrict__ W, int ld, int p, int j0, int c_begin, int c_end, const double* Vp, const double* Tm,
                                 bool transpose_t, double* Zp) {
     // Work units are (8-column block, row part): with fewer column blocks than warps the rows of a block are split over
     // several warps (every warp then has its own loads in flight), the partial Z = V^T A meet in `Zp` (64 doubles per
@@ -1346,6 +1346,9 @@ __device__ __forceinline__ bool pop_item(int which, int* qctl, const int2* qitem
     return true;
 }
 
+// STAGED: the instantiation of the big class (over-sized sectors keep W in the global scratch and stage the panel in shared memory);
+// the 72 / 55 KiB classes use the plain instantiation, whose register count the staging code must not raise
+template <bool STAGED>
 __global__ void __launch_bounds__(kQBigThreads) qr_work_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a, int64_t abs_, double* __restrict__ out1,
                                int64_t o1bs, double* __restrict__ out2, int64_t o2bs, int use_qr, const int* __restrict__ gmap,
                                int64_t gstride, int* qctl, const int2* __restrict__ qitems, int64_t qcap, int which, int64_t cap,
@@ -1376,6 +1379,12 @@ __global__ void __launch_bounds__(kQBigThreads) qr_work_kernel(const int64_t* __
         double* Rc = tau + 3 * ks;
         double* Vp = Rc + (int64_t)ks * q;
         double* Tm = Vp + 8 * ((p + 7) & ~7);
+        double* Pan = nullptr, *Zp = nullptr;
+        if (STAGED && need > cap && 128 + 2 * (int64_t)nt + 3 * (int64_t)ks + 8 * (int64_t)((p + 7) & ~7) <= cap) {
+            // an over-sized sector (a dense matrix, for instance): W and R stay in the global scratch, the panel / block reflector,
+            // T, tau and the partial Z are staged in shared memory like in the descriptor kernels
+            Tm = work; Zp = work + 128; tau = Zp + 2 * nt; Pan = tau + 3 * ks; Vp = Pan;
+        }
         const int* ar = g.aoff_r(m) + r0;
         const int* ac = g.aoff_c(m) + c0;
         if (use_qr) {
@@ -1390,8 +1399,10 @@ __global__ void __launch_bounds__(kQBigThreads) qr_work_kernel(const int64_t* __
             }
         }
         __syncthreads();
-        if (q > 8) householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm);
-        else householder_qr(W, ld, p, q, ks, tau, Rc, nullptr);
+        if (q > 8) {
+            if constexpr (STAGED) householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm, Pan, Zp);
+            else householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm);
+        } else householder_qr(W, ld, p, q, ks, tau, Rc, nullptr);
         if (use_qr) {
             for (int e = tid; e < ms * ks; e += nt) {
                 const int r = e / ks, t = e - r * ks;
@@ -1583,7 +1594,8 @@ static int queue_discover(const int64_t* sect, int64_t m, int64_t n, const doubl
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(sector_discover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecSmemDoubles * 8);
-        cudaFuncSetAttribute(qr_work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(qr_work_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(qr_work_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
         cudaFuncSetAttribute(svd_work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
         cudaFuncSetAttribute(svd_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         attr_set = true;
@@ -1610,14 +1622,14 @@ static int qr_queue_launch(const int64_t* sect, const int64_t* sh, const double*
     const int err = queue_discover(sect, m, n, a, abs_, nb, use_qr ? 0 : 1, per_cta, kSMs, st, gstride, qcap, rc);
     if (err != 0) return err;
     if (full > kQSmallDoubles) {
-        qr_work_kernel<<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, g_qws.gmap, gstride,
+        qr_work_kernel<true><<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, g_qws.gmap, gstride,
                                                                      g_qws.qctl, g_qws.qitems, qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
         if (check_launch("tnsp_qr_sectors_f64(big)")) return 1;
     }
-    qr_work_kernel<<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, g_qws.gmap, gstride,
+    qr_work_kernel<false><<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, g_qws.gmap, gstride,
                                                                          g_qws.qctl, g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
     if (check_launch("tnsp_qr_sectors_f64(72 KiB class)")) return 1;
-    qr_work_kernel<<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, g_qws.gmap, gstride,
+    qr_work_kernel<false><<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(sect, a, abs_, out1, o1bs, out2, o2bs, use_qr, g_qws.gmap, gstride,
                                                                        g_qws.qctl, g_qws.qitems, qcap, 2, kQMidDoubles, nullptr, 0);
     return check_launch("tnsp_qr_sectors_f64(55 KiB class)");
 }
