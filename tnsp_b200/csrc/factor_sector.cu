@@ -989,6 +989,129 @@ __device__ void jacobi_svd2(double* G, int ldp, double* V, int ldq, int p, int q
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Block Jacobi for a sector whose G (q columns of p rows) and V (q x q) do not fit shared memory: the columns are cut into
+// blocks of B, every pair of blocks is staged in shared memory (G and V panels of 2 B columns), swept once there and written
+// back; an outer sweep visits all block pairs.  The first version ran the plain sweeps on the global scratch: one dependent
+// L2 round trip per row chunk and pair, 0.9 ms for one dense 216 x 216 matrix.
+// `jacobi_panel_sweep`: one cyclic sweep (all pairs once) over nc staged columns; *sh_rot != 0 afterwards if a rotation above
+// the convergence threshold happened.
+// ------------------------------------------------------------------------------------------------
+__device__ void jacobi_panel_sweep(double* G, int ldp, double* V, int ldq, int p, int vrows, int nc, int* sh_rot) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int pe = p + (p & 1), ve = vrows + (vrows & 1);
+    const int qe = nc + (nc & 1), npairs = qe / 2;
+    int gs = 32;
+    while (gs > 4 && gs >= pe) gs >>= 1;
+    while (gs > 4 && npairs * gs > nthreads) gs >>= 1;
+    const int groups = nthreads / gs, grp = tid / gs, gl = tid % gs;
+    const double tol = fmax(1e-15, sqrt((double)p) * 2.3e-16), tol2 = tol * tol;
+    if (tid == 0) *sh_rot = 0;
+    __syncthreads();
+    for (int round = 0; round < qe - 1; ++round) {
+        for (int base = 0; base < npairs; base += groups) {
+            const int pr = base + grp;
+            int i = 0, j = 0;
+            bool valid = pr < npairs;
+            if (valid) {
+                if (pr == 0) { i = qe - 1; j = round; }
+                else { i = round + pr; if (i >= qe - 1) i -= qe - 1; j = round - pr; if (j < 0) j += qe - 1; }
+                valid = i < nc && j < nc;
+                if (i > j) { const int t = i; i = j; j = t; }
+            }
+            double2* gi = reinterpret_cast<double2*>(G + i * ldp);
+            double2* gj = reinterpret_cast<double2*>(G + j * ldp);
+            double aa = 0.0, bb = 0.0, cc = 0.0;
+            if (valid)
+                for (int r = gl; 2 * r < pe; r += gs) {
+                    const double2 x = gi[r], y = gj[r];
+                    aa = fma(x.x, x.x, aa); aa = fma(x.y, x.y, aa);
+                    bb = fma(y.x, y.x, bb); bb = fma(y.y, y.y, bb);
+                    cc = fma(x.x, y.x, cc); cc = fma(x.y, y.y, cc);
+                }
+            aa = gsum(aa, gs); bb = gsum(bb, gs); cc = gsum(cc, gs);
+            const double ab = aa * bb, c2q = cc * cc;
+            if (valid && c2q > tol2 * ab && ab > 0.0) {
+                const double dd = bb - aa, c2 = 2.0 * cc;
+                const double x2 = fma(dd, dd, c2 * c2);
+                const double hh = x2 > 1e-280 ? x2 * rsqrt(x2) : sqrt(x2);
+                const double tt = (dd >= 0.0 ? c2 : -c2) * __drcp_rn(fabs(dd) + hh);
+                const double cs = rsqrt(fma(tt, tt, 1.0)), sn = cs * tt;
+                for (int r = gl; 2 * r < pe; r += gs) {
+                    const double2 x = gi[r], y = gj[r];
+                    gi[r] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+                    gj[r] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+                }
+                double2* vi = reinterpret_cast<double2*>(V + i * ldq);
+                double2* vj = reinterpret_cast<double2*>(V + j * ldq);
+                for (int r = gl; 2 * r < ve; r += gs) {
+                    const double2 x = vi[r], y = vj[r];
+                    vi[r] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+                    vj[r] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+                }
+                if (gl == 0 && c2q > 1e-16 * ab) *sh_rot = 1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// largest even block width whose pair of G and V panels fits `cap` doubles (0: not even two pairs of columns fit)
+__host__ __device__ inline int jacobi_block_width(int64_t ldp, int64_t ldq, int64_t cap) {
+    const int64_t b = cap / (2 * (ldp + ldq));
+    return (int)(b & ~(int64_t)1);
+}
+
+// G, V in global memory (ldp, ldq even, pad rows zero, 16-byte aligned columns); panels: `cap` doubles of shared memory; flags: 2 ints
+__device__ void jacobi_svd_blocked(double* G, int ldp, double* V, int ldq, int p, int q, double* panels, int64_t cap, int* flags) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    for (int e = tid; e < q * ldq; e += nthreads) { const int cidx = e / ldq, t = e - cidx * ldq; V[e] = (cidx == t) ? 1.0 : 0.0; }
+    const int B = jacobi_block_width(ldp, ldq, cap);
+    const int nblk = (q + B - 1) / B;
+    __syncthreads();
+    for (int outer = 0; outer < 60 && q > 1; ++outer) {
+        if (tid == 0) flags[1] = 0;
+        __syncthreads();
+        for (int I = 0; I < nblk; ++I) {
+            for (int J = (nblk == 1 ? I : I + 1); J < nblk; ++J) {
+                const int i0 = I * B, ni = min(B, q - i0);
+                const int j0 = J * B, nj = (J == I) ? 0 : min(B, q - j0);
+                const int nc = ni + nj;
+                double* Gs = panels;
+                double* Vs = panels + (int64_t)nc * ldp;
+                // columns are contiguous in G and V: straight 16-byte copies
+                for (int e = tid; e < nc * (ldp >> 1); e += nthreads) {
+                    const int c = e / (ldp >> 1), r = e - c * (ldp >> 1);
+                    const int gc = c < ni ? i0 + c : j0 + (c - ni);
+                    reinterpret_cast<double2*>(Gs + (int64_t)c * ldp)[r] = reinterpret_cast<const double2*>(G + (int64_t)gc * ldp)[r];
+                }
+                for (int e = tid; e < nc * (ldq >> 1); e += nthreads) {
+                    const int c = e / (ldq >> 1), r = e - c * (ldq >> 1);
+                    const int gc = c < ni ? i0 + c : j0 + (c - ni);
+                    reinterpret_cast<double2*>(Vs + (int64_t)c * ldq)[r] = reinterpret_cast<const double2*>(V + (int64_t)gc * ldq)[r];
+                }
+                __syncthreads();
+                jacobi_panel_sweep(Gs, ldp, Vs, ldq, p, q, nc, &flags[0]);
+                if (tid == 0 && flags[0]) flags[1] = 1;
+                for (int e = tid; e < nc * (ldp >> 1); e += nthreads) {
+                    const int c = e / (ldp >> 1), r = e - c * (ldp >> 1);
+                    const int gc = c < ni ? i0 + c : j0 + (c - ni);
+                    reinterpret_cast<double2*>(G + (int64_t)gc * ldp)[r] = reinterpret_cast<const double2*>(Gs + (int64_t)c * ldp)[r];
+                }
+                for (int e = tid; e < nc * (ldq >> 1); e += nthreads) {
+                    const int c = e / (ldq >> 1), r = e - c * (ldq >> 1);
+                    const int gc = c < ni ? i0 + c : j0 + (c - ni);
+                    reinterpret_cast<double2*>(V + (int64_t)gc * ldq)[r] = reinterpret_cast<const double2*>(Vs + (int64_t)c * ldq)[r];
+                }
+                __syncthreads();
+            }
+        }
+        const int any = flags[1];
+        __syncthreads();
+        if (!any) break;
+    }
+}
+
 // Warp-level variant: ONE warp owns a whole (small) sector, so the sectors of a matrix are diagonalised
 // concurrently by the warps of the CTA with no block barrier inside the sweeps.  `gs` lanes per column pair.
 __device__ void jacobi_svd_warp(double* G, int ldp, double* V, int ldq, int p, int q) {
@@ -1426,12 +1549,14 @@ __global__ void __launch_bounds__(kQBigThreads) qr_work_kernel(const int64_t* __
 }
 
 // work (per chain): sigma in staging order [k] | - [k] | staged U blocks [m*k] | staged Vt blocks [k*n] | ...
+template <bool BLOCKED>      // the big-class instantiation carries the block Jacobi for over-sized sectors
 __global__ void __launch_bounds__(kQBigThreads) svd_work_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a, int64_t abs_, double* __restrict__ workg,
                                 int64_t wbs, const int* __restrict__ gmap, int64_t gstride, int* qctl, const int2* __restrict__ qitems,
                                 int64_t qcap, int which, int64_t cap, double* __restrict__ scratch, int64_t scratch_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int sh_ticket;
     __shared__ int sh_rot;
+    __shared__ int sh_flags[2];
     double* work = reinterpret_cast<double*>(smem_raw);
     const int m = (int)sect[0], n = (int)sect[1], k = (int)sect[2];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -1464,7 +1589,10 @@ __global__ void __launch_bounds__(kQBigThreads) svd_work_kernel(const int64_t* _
         }
         if (p & 1) for (int c = tid; c < q; c += nt) G[(int64_t)c * ldp + p] = 0.0;
         __syncthreads();
-        jacobi_svd2(G, ldp, V, ldq, p, q, &sh_rot, g_jacobi_cached_norms ? sig : nullptr);
+        if (!BLOCKED || svd_sector_need(p, q) <= cap || jacobi_block_width(ldp, ldq, cap) < 2)
+            jacobi_svd2(G, ldp, V, ldq, p, q, &sh_rot, g_jacobi_cached_norms ? sig : nullptr);
+        else
+            jacobi_svd_blocked(G, ldp, V, ldq, p, q, work, cap, sh_flags);      // over-sized sector: block pairs staged in shared memory
         for (int c = warp; c < q; c += nwarps) {
             double s2 = 0.0;
             for (int r = lane; r < p; r += 32) s2 += G[(int64_t)c * ldp + r] * G[(int64_t)c * ldp + r];
@@ -1596,7 +1724,8 @@ static int queue_discover(const int64_t* sect, int64_t m, int64_t n, const doubl
         cudaFuncSetAttribute(sector_discover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSecSmemDoubles * 8);
         cudaFuncSetAttribute(qr_work_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
         cudaFuncSetAttribute(qr_work_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
-        cudaFuncSetAttribute(svd_work_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(svd_work_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(svd_work_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
         cudaFuncSetAttribute(svd_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         attr_set = true;
     }
@@ -1645,14 +1774,14 @@ static int svd_queue_launch(const int64_t* sect, const int64_t* sh, const double
     const int err = queue_discover(sect, m, n, a, abs_, nb, 2, per_cta, kSMs, st, gstride, qcap, rc);
     if (err != 0) return err;
     if (full > kQSmallDoubles) {
-        svd_work_kernel<<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(sect, a, abs_, work, wbs, g_qws.gmap, gstride, g_qws.qctl, g_qws.qitems,
+        svd_work_kernel<true><<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(sect, a, abs_, work, wbs, g_qws.gmap, gstride, g_qws.qctl, g_qws.qitems,
                                                                       qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
         if (check_launch("tnsp_svd_sectors_f64(big)")) return 1;
     }
-    svd_work_kernel<<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(sect, a, abs_, work, wbs, g_qws.gmap, gstride, g_qws.qctl,
+    svd_work_kernel<false><<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(sect, a, abs_, work, wbs, g_qws.gmap, gstride, g_qws.qctl,
                                                                           g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
     if (check_launch("tnsp_svd_sectors_f64(72 KiB class)")) return 1;
-    svd_work_kernel<<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(sect, a, abs_, work, wbs, g_qws.gmap, gstride, g_qws.qctl,
+    svd_work_kernel<false><<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(sect, a, abs_, work, wbs, g_qws.gmap, gstride, g_qws.qctl,
                                                                         g_qws.qitems, qcap, 2, kQMidDoubles, nullptr, 0);
     if (check_launch("tnsp_svd_sectors_f64(55 KiB class)")) return 1;
     const int rank_in_smem = k * 12 <= 96 * 1024;
@@ -1738,6 +1867,7 @@ __global__ void __launch_bounds__(kQBigThreads) svd_desc_kernel(const int64_t* _
                                                                int64_t scratch_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int sh_rot;
+    __shared__ int sh_flags[2];
     double* work = reinterpret_cast<double*>(smem_raw);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int gid = lane >> 2, tig = lane & 3;
@@ -1829,7 +1959,10 @@ __global__ void __launch_bounds__(kQBigThreads) svd_desc_kernel(const int64_t* _
             G2[e] = r < q ? Rc[(int64_t)r * q + c] : 0.0;
         }
         __syncthreads();
-        jacobi_svd2(G2, ldq, V, ldq, q, q, &sh_rot, g_jacobi_cached_norms ? sig : nullptr);
+        if (small == work || jacobi_block_width(ldq, ldq, cap) < 2)
+            jacobi_svd2(G2, ldq, V, ldq, q, q, &sh_rot, g_jacobi_cached_norms ? sig : nullptr);
+        else
+            jacobi_svd_blocked(G2, ldq, V, ldq, q, q, work, cap, sh_flags);     // q x q factor beyond shared memory
         for (int c = warp; c < q; c += nwarps) {
             double s2 = 0.0;
             for (int r = lane; r < q; r += 32) s2 += G2[(int64_t)c * ldq + r] * G2[(int64_t)c * ldq + r];
