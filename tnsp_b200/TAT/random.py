@@ -1,7 +1,6 @@
 """``TAT.random``: the reference's global ``std::mt19937_64`` with libstdc++ distributions
 (PyTAT/PyTAT.hpp:87-126), reproduced by the host part of the C-ABI so that seeds give the same
 streams (and the same ``randn_`` PEPS) as the reference."""
-import ctypes
 
 import numpy as np
 

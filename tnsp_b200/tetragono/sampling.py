@@ -9,7 +9,6 @@ MPI rank c of the reference would (seed recipe utility.py:146-150).
 """
 from __future__ import annotations
 
-import ctypes
 
 import numpy as np
 
