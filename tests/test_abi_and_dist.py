@@ -82,10 +82,14 @@ with obs:
         p, c = s()
         obs(p, c)
 g = obs.gradient
+saved = list(obs._Deltas)
 ng = obs.natural_gradient_by_conjugate_gradient(3, 0.0)
+obs._Deltas = saved                     # the pseudo-inverse SR of the same sample set (rows all-gathered over the ranks)
+pg = obs.natural_gradient_by_direct_pseudo_inverse(1e-6, 0.0, [])
 out = dict(energy=list(obs.total_energy), count=obs._count,
            grad=[np.asarray(t.storage).tolist() for row in g for t in row],
-           ngrad=[np.asarray(t.storage).tolist() for row in ng for t in row])
+           ngrad=[np.asarray(t.storage).tolist() for row in ng for t in row],
+           pgrad=[np.asarray(t.storage).tolist() for row in pg for t in row])
 if rank == 0:
     json.dump(out, open({out!r}, "w"))
 if world > 1:
@@ -112,7 +116,7 @@ def test_two_ranks_over_gloo_equal_one_rank(tmp_path):
     a, b = json.load(open(f1)), json.load(open(f2))
     assert a["count"] == b["count"] == 12
     assert np.allclose(a["energy"], b["energy"], rtol=1e-12, atol=0)
-    for key, tol in (("grad", 1e-11), ("ngrad", 1e-9)):
+    for key, tol in (("grad", 1e-11), ("ngrad", 1e-9), ("pgrad", 1e-7)):
         scale = max(np.abs(np.array(x)).max() for x in a[key])
         for x, y in zip(a[key], b[key]):
             assert np.abs(np.array(x) - np.array(y)).max() <= tol * scale

@@ -34,8 +34,7 @@ def test_driver_matches_reference_loop(case):
 def test_driver_rejects_out_of_scope_options():
     meta, z = load(DRIVER_CASES[0])
     lat = build_lattice(meta, z)
-    for kw in ({"sampling_method": "direct"}, {"use_natural_gradient_by_direct_pseudo_inverse": True, "grad_step_size": 0.1},
-               {"fix_gauge": True}, {"use_check_difference": True}):
+    for kw in ({"sampling_method": "direct"}, {"fix_gauge": True}, {"use_check_difference": True}):
         with pytest.raises(NotImplementedError):
             next(gradient_descent(lat, 1, 1, **{"sampling_configurations": np.array(z["start_configuration"]), **kw}))
     with pytest.raises(ValueError):
@@ -92,3 +91,42 @@ def test_driver_writes_reference_checkpoints(tmp_path):
     assert np.array_equal(read_configurations(str(tmp_path / "conf_1.dat")), conf)
     raw = np.fromfile(str(tmp_path / "conf_1.dat"), dtype=np.int64)
     assert list(raw[:2]) == [1, conf.ndim] and list(raw[2:2 + conf.ndim]) == list(conf.shape)      # the reference's header
+
+
+def test_pseudo_inverse_natural_gradient_matches_the_reference_formula():
+    """observer.py:697-899 restated with numpy (the reference needs ScaLAPACK, absent here): same Gram matrix, same regularised
+    inverse of its eigenvalues; and, unregularised on a full-rank sample set, the result solves (Delta - <Delta>) NG = conj(E - <E>)"""
+    from tnsp_b200.tetragono.observer import Observer
+    from tnsp_b200.tetragono.sampling import ChainRng, SweepSampling
+    meta, z = load("driver_heis_3x3_D2_Dc4_plain")
+    lat = build_lattice(meta, z)
+    nb = 6
+    rng = ChainRng(nb)
+    rng.seed([11, 12, 13, 14, 15, 16])
+    s = SweepSampling(lat, 4, nb=nb, rng=rng)
+    s.configuration.import_configuration(np.broadcast_to(np.array(z["start_configuration"]), (nb,) + z["start_configuration"].shape))
+    results = {}
+    for which, (r_pinv, a_pinv) in {"regularised": (1e-3, 1e-6), "plain": (0.0, 0.0)}.items():
+        obs = Observer(lat, enable_energy=True, enable_gradient=True, enable_natural_gradient=True)
+        with obs:
+            for _ in range(3):
+                p, c = s()
+                obs(p, c)
+        rows = np.concatenate([np.asarray(d[2]) for d in obs._Deltas], axis=0)
+        es = np.concatenate([d[1] for d in obs._Deltas])
+        delta = np.concatenate([np.asarray(obs._Delta[l1][l2].storage).reshape(-1) for l1, l2 in lat.sites()]) / obs._total_weight
+        energy = obs._total_energy_value()
+        D, e = rows - delta, es - energy
+        L, U = np.linalg.eigh(D @ D.T)
+        num = r_pinv * L[-1] + a_pinv
+        l_inv = np.array([0.0 if l <= 0 else 1 / (l * (1 + (num / l)**6)) for l in L])
+        want = 2 * (D.T @ (U @ (l_inv * (U.T @ e))))
+        got = obs.natural_gradient_by_direct_pseudo_inverse(r_pinv, a_pinv, ["unused"])
+        flat = np.concatenate([np.asarray(got[l1][l2].transpose(obs._Delta[l1][l2].names).storage).reshape(-1) for l1, l2 in lat.sites()])
+        assert np.abs(flat - want).max() <= 1e-9 * np.abs(want).max()
+        results[which] = (D, e, flat)
+    D, e, flat = results["plain"]
+    keep = np.linalg.eigvalsh(D @ D.T) > 1e-9 * np.linalg.eigvalsh(D @ D.T)[-1]
+    if keep.sum() >= len(e) - 1:                     # centred rows: rank Ns - 1 at most
+        resid = D @ (flat / 2) - e
+        assert np.abs(resid - resid.mean()).max() <= 1e-6 * max(1.0, np.abs(e).max())

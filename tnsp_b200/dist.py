@@ -93,3 +93,21 @@ def barrier():
     d = _dist()
     if d:
         d.barrier()
+
+
+def allgather_rows(t):
+    """concatenate a [rows, n] tensor over ranks along the rows (every rank may hold a different number of rows)"""
+    d = _dist()
+    if not d:
+        return t
+    dev = t.device
+    if d.get_backend() == "nccl" and dev.type != "cuda":
+        t = t.cuda()
+    counts = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(d.get_world_size())]
+    d.all_gather(counts, torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device))
+    most = int(max(int(c.item()) for c in counts))
+    padded = torch.zeros((most, t.shape[1]), dtype=t.dtype, device=t.device)
+    padded[:t.shape[0]] = t
+    parts = [torch.empty_like(padded) for _ in range(d.get_world_size())]
+    d.all_gather(parts, padded)
+    return torch.cat([p_[:int(c.item())] for p_, c in zip(parts, counts)], dim=0).to(dev)

@@ -12,7 +12,8 @@ What changes against the reference is only what the B200 design needs:
   for the call sequence.
 
 Entry points that SURVEY.md section 8 marks out of the path raise NotImplementedError instead of silently doing something
-else: direct sampling (8f-1), pseudo-inverse SR (8f-4), gauge fixing (8f-3), numerical check-difference (debug aid).
+else: direct sampling (8f-1), gauge fixing (8f-3), numerical check-difference (debug aid).  The pseudo-inverse SR (8f-4) runs on
+library eigen-solvers instead of ScaLAPACK.
 State and configuration files are written in the reference's own formats (checkpoint.py).
 """
 from __future__ import annotations
@@ -117,6 +118,9 @@ def gradient_descent(
         conjugate_gradient_method_error=0.0,
         cache_natural_delta=None,
         use_natural_gradient_by_direct_pseudo_inverse=False,
+        scalapack_libraries="libscalapack.so",
+        natural_gradient_r_pinv=1e-12,
+        natural_gradient_a_pinv=0,
         # About gauge fixing
         fix_gauge=False,
         # About log and save state
@@ -142,8 +146,6 @@ def gradient_descent(
         raise ValueError("Invalid sampling method")
     if use_check_difference:
         raise NotImplementedError("check_difference is a debugging aid outside the hot path")
-    if use_natural_gradient_by_direct_pseudo_inverse:
-        raise NotImplementedError("pseudo-inverse SR needs ScaLAPACK (SURVEY.md 8f-4); use the conjugate-gradient SR")
     if fix_gauge:
         raise NotImplementedError("gauge fixing (expand_dimension) is SURVEY.md 8f-3")
     if sampling_method == "ergodic" and chains != 1:
@@ -248,7 +250,10 @@ def gradient_descent(
                 print(*observer.energy, file=file)
 
         if use_gradient:
-            if use_natural_gradient:
+            if use_natural_gradient and use_natural_gradient_by_direct_pseudo_inverse:
+                grad = observer.natural_gradient_by_direct_pseudo_inverse(natural_gradient_r_pinv, natural_gradient_a_pinv,
+                                                                          scalapack_libraries.split(","))
+            elif use_natural_gradient:
                 grad = observer.natural_gradient_by_conjugate_gradient(conjugate_gradient_method_step, conjugate_gradient_method_error)
             else:
                 grad = observer.gradient

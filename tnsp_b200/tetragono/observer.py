@@ -365,6 +365,55 @@ class Observer:
         out = self._array_to_delta(x)
         return [[t.conjugate(True) for t in row] for row in out]
 
+    def natural_gradient_by_direct_pseudo_inverse(self, r_pinv, a_pinv, libraries=None):
+        """SR natural gradient through the pseudo inverse of the Ns x Ns Gram matrix (observer.py:697-899; the reference does this
+        with ScaLAPACK pgemm / pheevd, `libraries` names its shared objects and is ignored here):
+
+            D_s = Delta_s - <Delta>,  e_s = conj(E_s) - conj(<E>)        (rows NOT reweighted, as in the reference)
+            T = D D^H = U diag(L) U^H,   l^+ = 1 / (l (1 + (num / l)^6)) for l > 0 else 0,   num = r_pinv L_max + a_pinv
+            NG = D^H U diag(l^+) U^H e,   return 2 NG
+
+        Off the hot path: the Gram product and the symmetric eigen-decomposition are library calls (cuBLAS / cuSOLVER through
+        torch).  Under several ranks the rows are all-gathered first, so every rank solves the same full problem."""
+        import torch
+        if not self._enable_natural:
+            raise RuntimeError("natural gradient is not enabled on this observer")
+        energy = self._total_energy_value()
+        if is_native(self.owner.Tensor):
+            delta = self._delta_to_array(self._Delta) / self._total_weight
+            rows = torch.cat([d[2] for d in self._Deltas], dim=0) if self._Deltas else delta.new_zeros((0, delta.shape[0]))
+        else:
+            owner = self.owner
+            delta = torch.from_numpy(np.concatenate([np.array(self._Delta[l1][l2].storage, dtype=np.float64)
+                                                     for l1, l2 in owner.sites()]) / self._total_weight)
+            rows = torch.from_numpy(np.concatenate([np.asarray(d[2]) for d in self._Deltas], axis=0))
+        es = np.concatenate([d[1] for d in self._Deltas]) if self._Deltas else np.zeros(0)
+        self._Deltas = None
+        D = rows - delta.reshape(1, -1)
+        e = torch.from_numpy(np.ascontiguousarray(es - energy)).to(D.device).reshape(-1, 1)
+        packed = _dist.allgather_rows(torch.cat([D, e], dim=1))           # one exchange: rows and their energies together
+        D, e = packed[:, :-1], packed[:, -1]
+        T = D @ D.T
+        L, U = torch.linalg.eigh(T)
+        num = r_pinv * float(L[-1]) + a_pinv
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            l = L.cpu().numpy()
+            l_inv = np.where(l > 0, 1.0 / (l * (1.0 + (num / np.where(l > 0, l, 1.0))**6)), 0.0)
+        x = 2.0 * (D.T @ (U @ (torch.from_numpy(l_inv).to(U.device) * (U.T @ e))))
+        if is_native(self.owner.Tensor):
+            out = self._array_to_delta(x.contiguous())
+        else:
+            owner = self.owner
+            out = [[None] * owner.L2 for _ in range(owner.L1)]
+            index, xs = 0, x.cpu().numpy()
+            for l1, l2 in owner.sites():
+                t_ = self._Delta[l1][l2].same_shape()
+                size = len(np.array(self._Delta[l1][l2].storage))
+                t_.storage = xs[index:index + size]
+                index += size
+                out[l1][l2] = t_
+        return [[t.conjugate(True) for t in row] for row in out]
+
     def _natural_gradient_host(self, step, error):
         """the same CG on host arrays, for PyTAT-compatible tensor classes other than this repository's
         (used to time the reference's CPU path through the public PyTAT API only)"""
