@@ -793,7 +793,34 @@ class Tensor:
     def _not_on_path(self, *a, **k):
         raise NotImplementedError("this Tensor method is outside the sampling-VMC hot path (SURVEY.md section 8)")
 
-    trace = exponential = shrink = expand = clear_fermi_symmetry = _not_on_path
+    exponential = shrink = expand = clear_fermi_symmetry = _not_on_path
+
+    def trace(self, trace_pairs, fuse_names=None):
+        """Partial trace over pairs of edges (trace.hpp; the reference's DirectSampling uses it): a contraction
+        with the identity between the conjugates of the paired edges -- no kernel of its own.  Bosonic symmetries only (the
+        fermionic version carries the parity signs of trace.hpp:120-160 and is not needed on the sweep / ergodic path)."""
+        if fuse_names:
+            raise NotImplementedError("trace with fuse_names is outside the sampling-VMC hot path")
+        if self.Symmetry.is_fermi_symmetry:
+            raise NotImplementedError("trace of fermionic tensors is outside the sampling-VMC hot path (SURVEY.md 8f-1)")
+        pairs = [tuple(p) for p in trace_pairs]
+        if not pairs:
+            return self.copy()
+        used = [n for p in pairs for n in p]
+        if len(set(used)) != len(used) or any(n not in self.names for n in used):
+            raise RuntimeError("Invalid trace pairs")
+        names, edges, identity_pairs, contract_pairs = [], [], [], set()
+        for i, (a, b) in enumerate(pairs):
+            ea, eb = self.edge_by_name(a), self.edge_by_name(b)
+            if ea.conjugate() != eb:
+                raise RuntimeError("Incompatible edge segments in trace")
+            na, nb_ = f"__trace_a{i}", f"__trace_b{i}"
+            names += [na, nb_]
+            edges += [ea.conjugate(), eb.conjugate()]
+            identity_pairs.append((na, nb_))
+            contract_pairs |= {(a, na), (b, nb_)}
+        eye = type(self)(names, edges).identity_(identity_pairs)
+        return self.contract(eye, contract_pairs)
 
     # -- binary wire format (io.hpp:686-760, version 1) -------------------------------------------
     # "TAT" | u16 version = 1 | names: u64 count, (u64 length, bytes)* | edges: u64 count, per edge [u8 arrow if the symmetry is
