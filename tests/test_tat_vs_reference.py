@@ -178,8 +178,10 @@ def test_trace(ref_tat, sym, seed):
     perm = list(rng.permutation(len(names)))
     names, edges = [names[i] for i in perm], [edges[i] for i in perm]
     a, b = _pair(ref_tat, sym, names, edges, rng)
-    try:
-        want = b.trace(pairs)
-    except (RuntimeError, MemoryError):
-        pytest.skip("the reference itself fails on this block structure (bad optional access / bad_alloc inside trace.hpp)")
-    _same(a.trace(pairs), want, sym, tol=1e-12)
+    got = a.trace(pairs)
+    if np.asarray(got.storage).size == 0:
+        # no block of the result satisfies the symmetry: the reference's trace.hpp fails on this (bad optional access /
+        # bad_alloc); it is never driven there
+        pytest.skip("empty result: outside what the reference's trace supports")
+    want = b.trace(pairs)
+    _same(got, want, sym, tol=1e-12)
