@@ -248,6 +248,26 @@ def hubbard_ff(L1, L2, D, T):
 
 
 def main():
+    if "gauge" in sys.argv[1:]:
+        # gauge fixing (SamplingLattice.expand_dimension(1.0, 0), lattice.py:821-919): the TRUNCATED amplitude of the fixture
+        # configuration afterwards -- it depends on the gauge the reference fixes, not only on the state
+        out = {}
+        for name, lat, Dc, points in (("heis_3x3_D2_Dc4", heisenberg(3, 3, 2), 4, None), ("heis_4x4_D3_Dc5_truncating", heisenberg(4, 4, 3), 5, None),
+                                      ("heisU1_4x4_d1_Dc6", heisenberg_u1(4, 4, 1), 6, "u1")):
+            pts = neel_u1(lat) if points == "u1" else neel(lat)
+            def amplitude(cut):
+                conf = tet.sampling_lattice.Configuration(lat, cut)
+                for l1 in range(lat.L1):
+                    for l2 in range(lat.L2):
+                        for o, p in pts[l1][l2].items():
+                            conf[l1, l2, o] = p
+                return float(conf.hole(()))
+            before = amplitude(Dc)
+            lat.expand_dimension(1.0, 0)
+            out[name] = np.array([before, amplitude(Dc), amplitude(64)])
+            print(name, out[name])
+        np.savez(os.path.join(ROOT, "tests", "golden", "gauge_fixing.npz"), **out)
+        return
     if "state" in sys.argv[1:]:
         # checkpoints exactly as the reference writes them (utility.py:365-388): pickle of the SamplingLattice
         import pickle

@@ -34,7 +34,7 @@ def test_driver_matches_reference_loop(case):
 def test_driver_rejects_out_of_scope_options():
     meta, z = load(DRIVER_CASES[0])
     lat = build_lattice(meta, z)
-    for kw in ({"sampling_method": "direct"}, {"fix_gauge": True}, {"use_check_difference": True}):
+    for kw in ({"sampling_method": "direct"}, {"use_check_difference": True}):
         with pytest.raises(NotImplementedError):
             next(gradient_descent(lat, 1, 1, **{"sampling_configurations": np.array(z["start_configuration"]), **kw}))
     with pytest.raises(ValueError):
@@ -130,3 +130,63 @@ def test_pseudo_inverse_natural_gradient_matches_the_reference_formula():
     if keep.sum() >= len(e) - 1:                     # centred rows: rank Ns - 1 at most
         resid = D @ (flat / 2) - e
         assert np.abs(resid - resid.mean()).max() <= 1e-6 * max(1.0, np.abs(e).max())
+
+
+@pytest.mark.parametrize("case", ["heis_3x3_D2_Dc4", "heis_4x4_D3_Dc5_truncating", "heisU1_4x4_d1_Dc6"])
+def test_gauge_fixing_matches_the_reference(case):
+    """SamplingLattice.expand_dimension(1.0, 0) (lattice.py:821-919): the state is unchanged (amplitude at a truncation-free cut)
+    and the TRUNCATED amplitude -- which depends on the gauge that was fixed -- equals the reference's after ITS gauge fixing
+    (tests/golden/gauge_fixing.npz, written by make_golden.py gauge)"""
+    import os
+    from golden_loader import HERE, config_points
+    from tnsp_b200.tetragono.configuration import Configuration
+    meta, z = load(case)
+    lat = build_lattice(meta, z)
+    want_before, want_after, want_exact = np.load(os.path.join(HERE, "gauge_fixing.npz"))[case]
+
+    def amplitude(cut):
+        conf = Configuration(lat, cut)
+        for l1, row in enumerate(config_points(meta)):
+            for l2, site in enumerate(row):
+                for o, p in site.items():
+                    conf[l1, l2, o] = p
+        return float(conf.hole(()))
+
+    assert abs(amplitude(meta["Dc"]) - want_before) <= 1e-10 * abs(want_before)
+    exact = amplitude(64)
+    lat.expand_dimension(1.0, 0)
+    assert abs(amplitude(64) - exact) <= 1e-12 * abs(exact)
+    assert abs(amplitude(64) - want_exact) <= 1e-10 * abs(want_exact)
+    assert abs(amplitude(meta["Dc"]) - want_after) <= 1e-9 * abs(want_after)
+
+
+def test_bond_expansion_grows_the_bonds_and_perturbs_by_epsilon():
+    meta, z = load("heis_3x3_D2_Dc4")
+    lat = build_lattice(meta, z)
+    from golden_loader import config_points
+    from tnsp_b200.tetragono.configuration import Configuration
+
+    def amplitude():
+        conf = Configuration(lat, 64)
+        for l1, row in enumerate(config_points(meta)):
+            for l2, site in enumerate(row):
+                for o, p in site.items():
+                    conf[l1, l2, o] = p
+        return float(conf.hole(()))
+
+    before = amplitude()
+    TAT.random.seed(77)
+    lat.expand_dimension(3, 1e-6)
+    assert all(lat[l1, l2].edge_by_name("R").dimension == 3 for l1 in range(3) for l2 in range(2))
+    assert all(lat[l1, l2].edge_by_name("D").dimension == 3 for l1 in range(2) for l2 in range(3))
+    assert abs(amplitude() - before) <= 1e-3 * abs(before)
+
+
+def test_driver_fix_gauge_option_runs():
+    meta, z = load("driver_heis_3x3_D2_Dc4_plain")
+    lat = build_lattice(meta, z)
+    conf = np.array(z["start_configuration"])
+    TAT.random.seed(5)
+    energies = [w["energy"][0] for w, _ in gradient_descent(lat, 4, 2, 0.01, sampling_method="sweep", configuration_cut_dimension=4,
+                                                              sampling_configurations=conf, fix_gauge=True)]
+    assert len(energies) == 2 and np.all(np.isfinite(energies))

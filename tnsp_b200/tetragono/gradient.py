@@ -12,7 +12,8 @@ What changes against the reference is only what the B200 design needs:
   for the call sequence.
 
 Entry points that SURVEY.md section 8 marks out of the path raise NotImplementedError instead of silently doing something
-else: direct sampling (8f-1), gauge fixing (8f-3), numerical check-difference (debug aid).  The pseudo-inverse SR (8f-4) runs on
+else: direct sampling (8f-1), numerical check-difference (debug aid).  Gauge fixing (8f-3) is `SamplingLattice.expand_dimension`,
+bosonic / no symmetry.  The pseudo-inverse SR (8f-4) runs on
 library eigen-solvers instead of ScaLAPACK.
 State and configuration files are written in the reference's own formats (checkpoint.py).
 """
@@ -146,8 +147,6 @@ def gradient_descent(
         raise ValueError("Invalid sampling method")
     if use_check_difference:
         raise NotImplementedError("check_difference is a debugging aid outside the hot path")
-    if fix_gauge:
-        raise NotImplementedError("gauge fixing (expand_dimension) is SURVEY.md 8f-3")
     if sampling_method == "ergodic" and chains != 1:
         raise ValueError("the ergodic sampler enumerates configurations one at a time: chains must be 1")
 
@@ -282,6 +281,8 @@ def gradient_descent(
                         total_grad = this_grad   # the reference scales in place: the momentum carries the scaled update
                 state.apply_gradient(this_grad, grad_step_size)
 
+            if fix_gauge:
+                state.expand_dimension(1.0, 0)
             observer.normalize_lattice()
             bcast_lattice(state)
 

@@ -240,3 +240,49 @@ class SamplingLattice(AbstractLattice):
         """theta <- theta - step * g  (lattice.py:921-948, plain update)"""
         for l1, l2 in self.sites():
             self._lattice[l1][l2] = self._lattice[l1][l2] - gradient[l1][l2] * step_size
+
+    # -- gauge fixing / bond expansion (SURVEY.md 8f-3; lattice.py:821-919) ---------------------------------------
+    def expand_dimension(self, new_dimension, epsilon):
+        """Re-factorise every bond: QR of both neighbours, SVD of the product of the two triangular factors (optionally
+        perturbed by `epsilon` x noise and truncated / enlarged to `new_dimension`: an int, or a float factor of the present
+        dimension), the square roots of the singular values shared between the two sites.  With `new_dimension == 1.0` and
+        `epsilon == 0` this only fixes the gauge (the state is unchanged).  Bond order as the reference: vertical bonds below odd
+        rows, below even rows, then horizontal bonds right of odd columns, of even columns; every rank does all bonds, the
+        arithmetic is deterministic (and the noise comes from the shared TAT.random engine), so no broadcast is needed.
+        Bosonic symmetries and no symmetry (the diagonal identity of a fermionic bond is outside the hot path)."""
+        if self.Tensor.Symmetry.is_fermi_symmetry:
+            raise NotImplementedError("expand_dimension for fermionic lattices is outside the sampling-VMC hot path (SURVEY.md 8f-3)")
+        for parity in (0, 1):
+            for l1, l2 in self.sites():
+                if l1 != 0 and l1 % 2 == parity:
+                    self._refactor_bond((l1 - 1, l2), (l1, l2), "D", "U", new_dimension, epsilon)
+        for parity in (0, 1):
+            for l1, l2 in self.sites():
+                if l2 != 0 and l2 % 2 == parity:
+                    self._refactor_bond((l1, l2 - 1), (l1, l2), "R", "L", new_dimension, epsilon)
+
+    def _refactor_bond(self, first, second, bond_1, bond_2, new_dimension, epsilon):
+        """`bond_1` of site `first` is joined to `bond_2` of site `second`"""
+        a, b = self[first], self[second]
+        if isinstance(new_dimension, float):
+            new_dimension = round(a.edge_by_name(bond_1).dimension * new_dimension)
+        keep_1, keep_2 = {bond_1}, {bond_2}
+        if epsilon != 0:       # with noise the physical legs take part, so that the enlarged bond can carry new directions
+            keep_1 |= {n for n in a.names if n.startswith("P")}
+            keep_2 |= {n for n in b.names if n.startswith("P")}
+        a_q, a_r = a.qr("r", keep_1, bond_1, bond_2)
+        b_q, b_r = b.qr("r", keep_2, bond_2, bond_1)
+        a_r = a_r.edge_rename({n: f"A_{n}" for n in a_r.names})
+        b_r = b_r.edge_rename({n: f"B_{n}" for n in b_r.names})
+        core = a_r.contract(b_r, {(f"A_{bond_1}", f"B_{bond_2}")})
+        if epsilon != 0:
+            core = core + core.same_shape().randn_() * (epsilon * float(core.norm_max()))
+        u, sv, v = core.svd({n for n in core.names if n.startswith("A_")}, bond_1, bond_2, bond_2, bond_1, new_dimension)
+        root = sv.sqrt()
+        eye = sv.same_shape().identity_({(bond_2, bond_1)})
+        eye *= root
+        sv *= root.reciprocal()
+        a_new = a_q.contract(u, {(bond_1, f"A_{bond_2}")}).contract(sv, {(bond_1, bond_2)})
+        b_new = b_q.contract(v, {(bond_2, f"B_{bond_1}")}).contract(eye, {(bond_2, bond_1)})
+        self[first] = a_new.edge_rename({n: n[2:] for n in a_new.names if n.startswith("A_")})
+        self[second] = b_new.edge_rename({n: n[2:] for n in b_new.names if n.startswith("B_")})
