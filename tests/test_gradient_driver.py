@@ -190,3 +190,26 @@ def test_driver_fix_gauge_option_runs():
     energies = [w["energy"][0] for w, _ in gradient_descent(lat, 4, 2, 0.01, sampling_method="sweep", configuration_cut_dimension=4,
                                                               sampling_configurations=conf, fix_gauge=True)]
     assert len(energies) == 2 and np.all(np.isfinite(energies))
+
+
+@pytest.mark.parametrize("chains", [64, 100])
+def test_batched_ergodic_enumeration_equals_one_by_one(chains):
+    """nb configurations per call (a9): the exact energy of the 3 x 3 lattice (512 configurations) is the same whether they are
+    enumerated one by one or in lock-step batches, also when the batch size does not divide the count (surplus chains weigh zero)"""
+    meta, z = load("driver_heis_3x3_D2_Dc4_plain")
+    lat = build_lattice(meta, z)
+    (one, _), = list(gradient_descent(lat, sampling_method="ergodic", configuration_cut_dimension=4))
+    (many, _), = list(gradient_descent(lat, sampling_method="ergodic", configuration_cut_dimension=4, chains=chains))
+    assert abs(many["energy"][0] - one["energy"][0]) <= 1e-11 * abs(one["energy"][0])
+
+
+def test_batched_ergodic_sequence_is_the_single_chain_sequence():
+    from tnsp_b200.tetragono.sampling import ErgodicSampling
+    meta, z = load("driver_heis_3x3_D2_Dc4_plain")
+    lat = build_lattice(meta, z)
+    for rank, size in ((0, 1), (1, 3)):
+        single = ErgodicSampling(lat, 4, rank=rank, size=size)
+        batch = ErgodicSampling(lat, 4, rank=rank, size=size, nb=5)
+        want = np.stack([single()[1].export_configuration() for _ in range(10)])
+        got = np.concatenate([batch()[1].export_configuration() for _ in range(2)])
+        assert np.array_equal(got, want)

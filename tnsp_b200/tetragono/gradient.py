@@ -147,8 +147,6 @@ def gradient_descent(
         raise ValueError("Invalid sampling method")
     if use_check_difference:
         raise NotImplementedError("check_difference is a debugging aid outside the hot path")
-    if sampling_method == "ergodic" and chains != 1:
-        raise ValueError("the ergodic sampler enumerates configurations one at a time: chains must be 1")
 
     time_str = datetime.now().strftime("%Y-%m-%d-%H:%M:%S")
     rank, size = _dist.rank(), _dist.world_size()
@@ -224,8 +222,8 @@ def gradient_descent(
                     raise RuntimeError("sweep sampling needs an initial configuration (sampling_configurations)")
                 calls = -(-sampling_total_step // chains)
             else:
-                sampling = ErgodicSampling(state, configuration_cut_dimension, restrict, rank=rank, size=size)
-                calls = sampling.total_step
+                sampling = ErgodicSampling(state, configuration_cut_dimension, restrict, rank=rank, size=size, nb=chains)
+                calls = sampling.calls          # == total_step for chains == 1
             for sampling_step in range(calls):
                 if sampling_step % size == rank:
                     possibility, configuration = sampling()

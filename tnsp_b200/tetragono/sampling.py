@@ -192,19 +192,32 @@ class SweepSampling(Sampling):
 
 
 class ErgodicSampling(Sampling):
-    """Enumerate every configuration (sampling.py:196-249); rank r of `size` takes r, r+size, ..."""
+    """Enumerate every configuration (sampling.py:196-249); rank r of `size` takes r, r+size, ...
 
-    def __init__(self, owner, cut_dimension, restrict_subspace=None, *, rank=0, size=1):
+    `nb` > 1 (new): one call yields nb consecutive configurations of this rank's sequence as a lock-step batch, so that an exact
+    enumeration keeps the GPU busy; the concatenation of the batches is the nb = 1 sequence.  When the sequence is exhausted
+    inside a batch the surplus chains get possibility = inf, i.e. weight zero in the Observer (the reference uses the same
+    device for configurations outside a restricted subspace, sampling.py:244-247)."""
+
+    def __init__(self, owner, cut_dimension, restrict_subspace=None, *, rank=0, size=1, nb=1):
         super().__init__(owner, cut_dimension, restrict_subspace)
-        self.configuration = Configuration(owner, cut_dimension)
+        self.nb = nb
+        self.configuration = Configuration(owner, cut_dimension, nb)
         self._rank, self._size = rank, size
         self.total_step = 1
+        self._digits = []        # (l1, l2, orbit, edge) in the order the reference increments them: first site fastest
         for l1, l2 in owner.sites():
             for orbit, edge in owner.physics_edges[l1, l2].items():
                 self.total_step *= edge.dimension
-        self._zero_configuration()
-        for _ in range(rank):
-            self._next_configuration()
+                self._digits.append((l1, l2, orbit, edge))
+        if nb != 1 and restrict_subspace is not None:
+            raise NotImplementedError("restrict_subspace callbacks are evaluated per chain; use nb=1")
+        self._counter = rank     # number of the configuration the (first) chain currently holds
+        self._served = 0         # configurations of this rank's sequence handed out so far
+        if nb == 1:
+            self._zero_configuration()
+            for _ in range(rank):
+                self._next_configuration()
 
     def _zero_configuration(self):
         for l1, l2 in self.owner.sites():
@@ -225,10 +238,26 @@ class ErgodicSampling(Sampling):
     def refresh_all(self):
         self.configuration.refresh_all()
 
+    @property
+    def calls(self):
+        """calls (over all ranks, like the reference's `total_step` loop) that cover every configuration once"""
+        return -(-self.total_step // self.nb)
+
     def __call__(self):
-        for _ in range(self._size):
-            self._next_configuration()
-        possibility = 1.0
-        if self._restrict_subspace is not None and not self._restrict_subspace(self.configuration):
-            possibility = np.inf
+        if self.nb == 1:
+            for _ in range(self._size):
+                self._next_configuration()
+            possibility = 1.0
+            if self._restrict_subspace is not None and not self._restrict_subspace(self.configuration):
+                possibility = np.inf
+            return possibility, self.configuration.copy()
+        # chain c holds configuration number rank + (served + c + 1) * size (mod total), decoded digit by digit
+        numbers = self._rank + (self._served + np.arange(self.nb, dtype=np.int64) + 1) * self._size
+        mine = -(-(self.total_step - self._rank) // self._size) if self._size > 1 else self.total_step   # length of this rank's sequence
+        possibility = np.where(self._served + np.arange(self.nb) < mine, 1.0, np.inf)
+        rest = numbers % self.total_step
+        for l1, l2, orbit, edge in self._digits:
+            self.configuration[l1, l2, orbit] = Configuration._point_by_index(edge, rest % edge.dimension)
+            rest = rest // edge.dimension
+        self._served += self.nb
         return possibility, self.configuration.copy()
