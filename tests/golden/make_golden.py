@@ -123,7 +123,7 @@ def dump_case(name, sym_name, lattice, Dc, config_points, seed, n_samples, cg_st
     print(name, "ws", arrays["ws"], "E_s", arrays["energy_s"], "traj E", arrays["traj_energy"], os.path.getsize(out), "bytes")
 
 
-def dump_driver_case(name, sym_name, lattice, Dc, config_points, seed, **kwargs):
+def dump_driver_case(name, sym_name, lattice, Dc, config_points, seed, method="sweep", **kwargs):
     """the reference's own optimisation loop (`gradient_descent`, sampling_lattice/gradient.py:93-445) from a fixed seed:
     energy of every step and the PEPS tensors after the last update"""
     arrays = {}
@@ -147,14 +147,14 @@ def dump_driver_case(name, sym_name, lattice, Dc, config_points, seed, **kwargs)
     TAT.random.seed(seed)
     energies = []
     from tetragono.sampling_lattice.gradient import gradient_descent as ref_gradient_descent
-    for whole, _ in ref_gradient_descent(lattice, sampling_method="sweep", configuration_cut_dimension=Dc,
+    for whole, _ in ref_gradient_descent(lattice, sampling_method=method, configuration_cut_dimension=Dc,
                                                           sampling_configurations=sampling_configurations, **kwargs):
         energies.append(whole["energy"])
     arrays["step_energy"] = np.array(energies)
     arrays["last_configuration"] = np.array(sampling_configurations)
     meta["final_sites"] = [[tensor_desc(sym_name, lattice[l1, l2], arrays, f"final_{l1}_{l2}") for l2 in range(lattice.L2)]
                            for l1 in range(lattice.L1)]
-    meta["seed"], meta["kwargs"] = seed, kwargs
+    meta["seed"], meta["kwargs"], meta["method"] = seed, kwargs, method
     arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     out = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(out, **arrays)
@@ -248,6 +248,24 @@ def hubbard_ff(L1, L2, D, T):
 
 
 def main():
+    if "direct" in sys.argv[1:]:
+        # direct sampling (sampling.py:252-371): configurations and their probabilities from a fixed seed
+        out = {}
+        for name, lat, Dc, dl_cut, seed in (("heis_3x3_D2_Dc4", heisenberg(3, 3, 2), 4, 4, 31), ("heis_4x4_D3_Dc5_truncating", heisenberg(4, 4, 3), 5, 3, 32),
+                                            ("heisU1_4x4_d1_Dc6", heisenberg_u1(4, 4, 1), 6, 4, 33)):
+            TAT.random.seed(seed)
+            sampling = tet.sampling_lattice.DirectSampling(lat, Dc, None, dl_cut)
+            confs, poss = [], []
+            for _ in range(6):
+                p, c = sampling()
+                confs.append(c.export_configuration())
+                poss.append(p)
+            out[name + "_conf"] = np.array(confs)
+            out[name + "_poss"] = np.array(poss)
+            out[name + "_par"] = np.array([Dc, dl_cut, seed])
+            print(name, poss)
+        np.savez(os.path.join(ROOT, "tests", "golden", "direct_sampling.npz"), **out)
+        return
     if "gauge" in sys.argv[1:]:
         # gauge fixing (SamplingLattice.expand_dimension(1.0, 0), lattice.py:821-919): the TRUNCATED amplitude of the fixture
         # configuration afterwards -- it depends on the gauge the reference fixes, not only on the state
@@ -284,6 +302,9 @@ def main():
         lat = heisenberg_u1(4, 4, 1)
         dump_driver_case("driver_heisU1_4x4_d1_Dc6_line_search", "BoseU1", lat, 6, neel_u1(lat), seed=22, sampling_total_step=4,
                          grad_total_step=2, grad_step_size=0.02, use_line_search=True)
+        lat = heisenberg(3, 3, 2)
+        dump_driver_case("driver_heis_3x3_D2_Dc4_direct", "No", lat, 4, neel(lat), seed=24, sampling_total_step=5, grad_total_step=2,
+                         grad_step_size=0.01, method="direct", direct_sampling_cut_dimension=4)
         lat = heisenberg(3, 3, 2)
         dump_driver_case("driver_heis_3x3_D2_Dc4_plain", "No", lat, 4, neel(lat), seed=23, sampling_total_step=5, grad_total_step=3,
                          grad_step_size=0.01, momentum_parameter=0.3, orthogonalize_momentum=True)

@@ -12,7 +12,8 @@ What changes against the reference is only what the B200 design needs:
   for the call sequence.
 
 Entry points that SURVEY.md section 8 marks out of the path raise NotImplementedError instead of silently doing something
-else: direct sampling (8f-1), numerical check-difference (debug aid).  Gauge fixing (8f-3) is `SamplingLattice.expand_dimension`,
+else: numerical check-difference (debug aid).  Direct sampling (8f-1, the reference's default) is `direct_sampling.py`, one
+chain per call, bosonic / no symmetry.  Gauge fixing (8f-3) is `SamplingLattice.expand_dimension`,
 bosonic / no symmetry.  The pseudo-inverse SR (8f-4) runs on
 library eigen-solvers instead of ScaLAPACK.
 State and configuration files are written in the reference's own formats (checkpoint.py).
@@ -100,7 +101,7 @@ def gradient_descent(
         cache_configuration=False,
         classical_energy=None,
         # About sampling
-        sampling_method="sweep",
+        sampling_method="direct",
         configuration_cut_dimension=None,
         direct_sampling_cut_dimension=4,
         sampling_configurations=None,
@@ -141,10 +142,10 @@ def gradient_descent(
     `[L1, L2, orbits, 1 + symmetry components]` (or `[chains, ...]`) as written by `Configuration.export_configuration`;
     the last configuration of every step is copied back into it (gradient.py:360-364) when it is an array of the
     right shape."""
-    if sampling_method == "direct":
-        raise NotImplementedError("direct sampling is outside the sweep / ergodic path (SURVEY.md 8f-1)")
-    if sampling_method not in ("sweep", "ergodic"):
+    if sampling_method not in ("sweep", "ergodic", "direct"):
         raise ValueError("Invalid sampling method")
+    if sampling_method == "direct" and chains != 1:
+        raise ValueError("direct sampling draws one configuration per call: chains must be 1")
     if use_check_difference:
         raise NotImplementedError("check_difference is a debugging aid outside the hot path")
 
@@ -221,6 +222,10 @@ def gradient_descent(
                 else:
                     raise RuntimeError("sweep sampling needs an initial configuration (sampling_configurations)")
                 calls = -(-sampling_total_step // chains)
+            elif sampling_method == "direct":
+                from .direct_sampling import DirectSampling
+                sampling = DirectSampling(state, configuration_cut_dimension, restrict, direct_sampling_cut_dimension)
+                calls = sampling_total_step
             else:
                 sampling = ErgodicSampling(state, configuration_cut_dimension, restrict, rank=rank, size=size, nb=chains)
                 calls = sampling.calls          # == total_step for chains == 1
