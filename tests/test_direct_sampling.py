@@ -60,3 +60,22 @@ def test_direct_sampling_probability_is_the_born_probability():
         p, c = sampling()
         ws = float(c.hole(()))
         assert abs(p - ws**2 / norm) <= 1e-9 * p
+
+
+def test_lockstep_direct_sampling_equals_independent_chains():
+    """nb chains per call (no symmetry): chain c draws what a single-chain sampler with the same engine seed draws"""
+    from tnsp_b200.tetragono.sampling import ChainRng
+    meta, z = load("heis_3x3_D2_Dc4")
+    lat = build_lattice(meta, z)
+    seeds = [5, 6, 7, 8]
+    rng = ChainRng(len(seeds))
+    rng.seed(seeds)
+    batch = DirectSampling(lat, 4, None, 4, nb=len(seeds), rng=rng)
+    got = [batch() for _ in range(3)]
+    for c, seed in enumerate(seeds):
+        TAT.random.seed(seed)
+        single = DirectSampling(lat, 4, None, 4)
+        for step in range(3):
+            p, conf = single()
+            assert np.array_equal(got[step][1].export_configuration()[c], conf.export_configuration())
+            assert abs(got[step][0][c] - p) <= 1e-9 * p

@@ -213,3 +213,13 @@ def test_batched_ergodic_sequence_is_the_single_chain_sequence():
         want = np.stack([single()[1].export_configuration() for _ in range(10)])
         got = np.concatenate([batch()[1].export_configuration() for _ in range(2)])
         assert np.array_equal(got, want)
+
+
+def test_driver_with_lockstep_direct_sampling():
+    meta, z = load("driver_heis_3x3_D2_Dc4_plain")
+    lat = build_lattice(meta, z)
+    TAT.random.seed(4)
+    energies = [w["energy"][0] for w, _ in gradient_descent(lat, 24, 3, 0.02, chains=8, sampling_method="direct", configuration_cut_dimension=4,
+                                                              direct_sampling_cut_dimension=4, use_natural_gradient=True,
+                                                              conjugate_gradient_method_step=3, use_fix_relative_step_size=True)]
+    assert len(energies) == 3 and np.all(np.isfinite(energies))

@@ -141,12 +141,27 @@ class _FiveLineRow:
 
 class DirectSampling(Sampling):
     """`DirectSampling(owner, cut_dimension, restrict_subspace, double_layer_cut_dimension)` as the reference; `__call__`
-    returns `(possibility, configuration)`."""
+    returns `(possibility, configuration)`.
 
-    def __init__(self, owner, cut_dimension, restrict_subspace, double_layer_cut_dimension):
+    `nb` > 1 (new, models without symmetry): nb independent configurations per call as a lock-step batch -- the environments
+    carry a chain axis, every chain draws from its own engine (`rng`, a `ChainRng`), and chain c reproduces the single-chain
+    run with the same seed."""
+
+    def __init__(self, owner, cut_dimension, restrict_subspace, double_layer_cut_dimension, *, nb=1, rng=None):
         super().__init__(owner, cut_dimension, restrict_subspace)
         if owner.Tensor.Symmetry.is_fermi_symmetry:
             raise NotImplementedError("direct sampling of fermionic lattices needs the fermionic trace (SURVEY.md 8f-1)")
+        if nb != 1:
+            if owner.Tensor.Symmetry.length != 0:
+                raise NotImplementedError("a lock-step batch needs one block structure for all chains: symmetric lattices sample "
+                                          "one chain per call (or go through dense_embedding)")
+            if restrict_subspace is not None:
+                raise NotImplementedError("restrict_subspace callbacks are evaluated per chain; use nb=1")
+            if rng is None:
+                from .sampling import ChainRng
+                rng = ChainRng(nb)
+                rng.seed_like_reference()
+        self.nb, self.rng = nb, rng
         self._double_layer_cut_dimension = double_layer_cut_dimension
         self.refresh_all()
 
@@ -162,11 +177,43 @@ class DirectSampling(Sampling):
                 return i
         return i
 
+    def _draw(self, hole, hole_edge, uniform):
+        """(choice index per chain, its probability per chain) from the diagonal of the reduced density matrix, or None when
+        some chain has no weight left"""
+        alpha = self.owner.attribute.get("alpha", 1)
+        if self.nb == 1:
+            rho = []
+            for symmetry, _ in hole_edge.segments:
+                rho.extend(np.diagonal(hole.const_blocks[[("I", -symmetry), ("O", symmetry)]]))
+            rho = np.maximum(np.array(rho).real, 0)
+            if np.sum(rho) == 0:
+                return None
+            rho = rho**alpha
+            rho = rho / np.sum(rho)
+            choice = self._choice(uniform(), rho)
+            return choice, rho[choice]
+        d = hole_edge.dimension
+        rho = np.broadcast_to(np.asarray(hole.storage).reshape(-1, d, d), (self.nb, d, d))     # the first site is the same for all chains
+        rho = np.maximum(np.diagonal(rho, axis1=1, axis2=2), 0)
+        if (rho.sum(axis=1) == 0).any():
+            return None
+        rho = rho**alpha
+        rho = rho / rho.sum(axis=1, keepdims=True)
+        p = self.rng.uniform_real(None)
+        choice = np.full(self.nb, d - 1, dtype=np.int64)
+        open_ = np.ones(self.nb, dtype=bool)
+        for i in range(d):                     # the same sequential subtraction as `_choice`, chain by chain
+            p = p - rho[:, i]
+            hit = open_ & (p < 0)
+            choice[hit] = i
+            open_ &= ~hit
+        return choice, rho[np.arange(self.nb), choice]
+
     def __call__(self):
         owner = self.owner
-        configuration = Configuration(owner, self._cut_dimension)
+        configuration = Configuration(owner, self._cut_dimension, self.nb)
         uniform = _random.uniform_real(0, 1)
-        possibility = 1.0
+        possibility = 1.0 if self.nb == 1 else np.ones(self.nb)
         for l1 in range(owner.L1):
             row = _FiveLineRow(owner.L2, owner.Tensor, self._cut_dimension)
             for l2 in range(owner.L2):
@@ -187,17 +234,15 @@ class DirectSampling(Sampling):
                     hole = (site_hole.trace({(f"I{o}", f"O{o}") for o in unsampled}).edge_rename({f"I{orbit}": "I", f"O{orbit}": "O"})
                             .transpose(["I", "O"]))
                     hole_edge = hole.edge_by_name("O")
-                    rho = []
-                    for symmetry, _ in hole_edge.segments:
-                        rho.extend(np.diagonal(hole.const_blocks[[("I", -symmetry), ("O", symmetry)]]))
-                    rho = np.maximum(np.array(rho).real, 0)
-                    if np.sum(rho) == 0:
+                    drawn = self._draw(hole, hole_edge, uniform)
+                    if drawn is None:
                         return self()          # block mismatch or vanishing weight: draw again, like the reference
-                    rho = rho**owner.attribute.get("alpha", 1)
-                    rho = rho / np.sum(rho)
-                    choice = self._choice(uniform(), rho)
-                    possibility *= rho[choice]
-                    configuration[l1, l2, orbit] = hole_edge.point_by_index(choice)
+                    choice, weight = drawn
+                    possibility = possibility * weight
+                    if self.nb == 1:
+                        configuration[l1, l2, orbit] = hole_edge.point_by_index(choice)
+                    else:
+                        configuration[l1, l2, orbit] = Configuration._point_by_index(hole_edge, choice)
                     config[orbit] = configuration[l1, l2, orbit]      # normalised (symmetry, index array) form
                     _, shrinker = next(shrinkers)
                     shrunk = shrunk.contract(shrinker.edge_rename({"P": f"P{orbit}"}), {(f"P{orbit}", "Q")})

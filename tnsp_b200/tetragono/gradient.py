@@ -12,8 +12,8 @@ What changes against the reference is only what the B200 design needs:
   for the call sequence.
 
 Entry points that SURVEY.md section 8 marks out of the path raise NotImplementedError instead of silently doing something
-else: numerical check-difference (debug aid).  Direct sampling (8f-1, the reference's default) is `direct_sampling.py`, one
-chain per call, bosonic / no symmetry.  Gauge fixing (8f-3) is `SamplingLattice.expand_dimension`,
+else: numerical check-difference (debug aid).  Direct sampling (8f-1, the reference's default) is `direct_sampling.py`:
+bosonic / no symmetry, `chains` configurations per call for models without symmetry.  Gauge fixing (8f-3) is `SamplingLattice.expand_dimension`,
 bosonic / no symmetry.  The pseudo-inverse SR (8f-4) runs on
 library eigen-solvers instead of ScaLAPACK.
 State and configuration files are written in the reference's own formats (checkpoint.py).
@@ -144,8 +144,6 @@ def gradient_descent(
     right shape."""
     if sampling_method not in ("sweep", "ergodic", "direct"):
         raise ValueError("Invalid sampling method")
-    if sampling_method == "direct" and chains != 1:
-        raise ValueError("direct sampling draws one configuration per call: chains must be 1")
     if use_check_difference:
         raise NotImplementedError("check_difference is a debugging aid outside the hot path")
 
@@ -224,8 +222,8 @@ def gradient_descent(
                 calls = -(-sampling_total_step // chains)
             elif sampling_method == "direct":
                 from .direct_sampling import DirectSampling
-                sampling = DirectSampling(state, configuration_cut_dimension, restrict, direct_sampling_cut_dimension)
-                calls = sampling_total_step
+                sampling = DirectSampling(state, configuration_cut_dimension, restrict, direct_sampling_cut_dimension, nb=chains, rng=rng)
+                calls = -(-sampling_total_step // chains)
             else:
                 sampling = ErgodicSampling(state, configuration_cut_dimension, restrict, rank=rank, size=size, nb=chains)
                 calls = sampling.calls          # == total_step for chains == 1
