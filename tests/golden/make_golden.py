@@ -252,7 +252,8 @@ def main():
         # direct sampling (sampling.py:252-371): configurations and their probabilities from a fixed seed
         out = {}
         for name, lat, Dc, dl_cut, seed in (("heis_3x3_D2_Dc4", heisenberg(3, 3, 2), 4, 4, 31), ("heis_4x4_D3_Dc5_truncating", heisenberg(4, 4, 3), 5, 3, 32),
-                                            ("heisU1_4x4_d1_Dc6", heisenberg_u1(4, 4, 1), 6, 4, 33)):
+                                            ("heisU1_4x4_d1_Dc6", heisenberg_u1(4, 4, 1), 6, 4, 33), ("tJ_4x4_D1_Dc8", tJ(4, 4, 1, 2), 8, 4, 34),
+                                            ("hubbardFF_4x4_D1_Dc8", hubbard_ff(4, 4, 1, 8), 8, 4, 35)):
             TAT.random.seed(seed)
             sampling = tet.sampling_lattice.DirectSampling(lat, Dc, None, dl_cut)
             confs, poss = [], []
@@ -283,6 +284,19 @@ def main():
             before = amplitude(Dc)
             lat.expand_dimension(1.0, 0)
             out[name] = np.array([before, amplitude(Dc), amplitude(64)])
+            print(name, out[name])
+        for name, lat, Dc, seed in (("tJ_4x4_D1_Dc8", tJ(4, 4, 1, 2), 8, 41), ("hubbardFF_4x4_D1_Dc8", hubbard_ff(4, 4, 1, 8), 8, 42)):
+            TAT.random.seed(seed)
+            _, drawn = tet.sampling_lattice.DirectSampling(lat, Dc, None, 4)()
+            conf_array = drawn.export_configuration()
+            def amplitude(cut):
+                conf = tet.sampling_lattice.Configuration(lat, cut)
+                conf.import_configuration(conf_array)
+                return float(conf.hole(()))
+            before = amplitude(Dc)
+            lat.expand_dimension(1.0, 0)
+            out[name] = np.array([before, amplitude(Dc), amplitude(64)])
+            out[name + "_conf"] = np.array(conf_array)
             print(name, out[name])
         np.savez(os.path.join(ROOT, "tests", "golden", "gauge_fixing.npz"), **out)
         return

@@ -1,7 +1,7 @@
 """Direct sampling against the UNMODIFIED reference (tests/golden/direct_sampling.npz, written by
 `make_golden.py direct`): from the same seed the same configurations are drawn (integers: exact) with the same probabilities
 (<= 1e-9; finite cuts on both the sampled boundary and the double-layer boundary), for a lattice without symmetry, a
-truncating one and a U(1) one.  Plus a physics check: the drawn frequencies follow |psi|^2."""
+truncating one, a U(1) one and two fermionic ones (t-J, Hubbard).  Plus a physics check: the drawn frequencies follow |psi|^2."""
 import os
 
 import numpy as np
@@ -12,7 +12,7 @@ from golden_loader import HERE, build_lattice, load
 from tnsp_b200.tetragono.direct_sampling import DirectSampling, double_layer_rows_from_below
 
 
-@pytest.mark.parametrize("case", ["heis_3x3_D2_Dc4", "heis_4x4_D3_Dc5_truncating", "heisU1_4x4_d1_Dc6"])
+@pytest.mark.parametrize("case", ["heis_3x3_D2_Dc4", "heis_4x4_D3_Dc5_truncating", "heisU1_4x4_d1_Dc6", "tJ_4x4_D1_Dc8", "hubbardFF_4x4_D1_Dc8"])
 def test_direct_sampling_matches_the_reference(case):
     gold = np.load(os.path.join(HERE, "direct_sampling.npz"))
     Dc, dl_cut, seed = (int(x) for x in gold[case + "_par"])

@@ -132,7 +132,7 @@ def test_pseudo_inverse_natural_gradient_matches_the_reference_formula():
         assert np.abs(resid - resid.mean()).max() <= 1e-6 * max(1.0, np.abs(e).max())
 
 
-@pytest.mark.parametrize("case", ["heis_3x3_D2_Dc4", "heis_4x4_D3_Dc5_truncating", "heisU1_4x4_d1_Dc6"])
+@pytest.mark.parametrize("case", ["heis_3x3_D2_Dc4", "heis_4x4_D3_Dc5_truncating", "heisU1_4x4_d1_Dc6", "tJ_4x4_D1_Dc8", "hubbardFF_4x4_D1_Dc8"])
 def test_gauge_fixing_matches_the_reference(case):
     """SamplingLattice.expand_dimension(1.0, 0) (lattice.py:821-919): the state is unchanged (amplitude at a truncation-free cut)
     and the TRUNCATED amplitude -- which depends on the gauge that was fixed -- equals the reference's after ITS gauge fixing
@@ -142,14 +142,18 @@ def test_gauge_fixing_matches_the_reference(case):
     from tnsp_b200.tetragono.configuration import Configuration
     meta, z = load(case)
     lat = build_lattice(meta, z)
-    want_before, want_after, want_exact = np.load(os.path.join(HERE, "gauge_fixing.npz"))[case]
+    gold = np.load(os.path.join(HERE, "gauge_fixing.npz"))
+    want_before, want_after, want_exact = gold[case]
 
     def amplitude(cut):
         conf = Configuration(lat, cut)
-        for l1, row in enumerate(config_points(meta)):
-            for l2, site in enumerate(row):
-                for o, p in site.items():
-                    conf[l1, l2, o] = p
+        if case + "_conf" in gold.files:          # fermionic cases: a configuration drawn by the reference's direct sampler
+            conf.import_configuration(gold[case + "_conf"])
+        else:
+            for l1, row in enumerate(config_points(meta)):
+                for l2, site in enumerate(row):
+                    for o, p in site.items():
+                        conf[l1, l2, o] = p
         return float(conf.hole(()))
 
     assert abs(amplitude(meta["Dc"]) - want_before) <= 1e-10 * abs(want_before)

@@ -160,7 +160,7 @@ def test_svd(ref_tat, sym, seed):
         assert np.abs(p - q).max() <= 1e-9 * max(1.0, np.abs(q).max()) if q.size else True
 
 
-@pytest.mark.parametrize("sym,seed", [(s, i) for s in SYMS if not FERMI[s] for i in range(5)])
+@pytest.mark.parametrize("sym,seed", _cases(6))
 def test_trace(ref_tat, sym, seed):
     """partial trace (bosonic symmetries) against the reference's trace.hpp"""
     rng = np.random.default_rng(7000 + seed)
@@ -185,3 +185,20 @@ def test_trace(ref_tat, sym, seed):
         pytest.skip("empty result: outside what the reference's trace supports")
     want = b.trace(pairs)
     _same(got, want, sym, tol=1e-12)
+
+
+@pytest.mark.parametrize("sym,seed", _cases(5))
+def test_identity(ref_tat, sym, seed):
+    """identity_ between paired edges for all symmetry types, fermionic signs included (identity.hpp)"""
+    rng = np.random.default_rng(8000 + seed)
+    n_pairs = int(rng.integers(1, 3))
+    names, edges, pairs = [], [], set()
+    for i in range(n_pairs):
+        e = rand_edge(rng, sym)
+        names += [f"a{i}", f"b{i}"]
+        edges += [e, conj_edge(sym, e)]
+        pairs.add((f"a{i}", f"b{i}") if rng.integers(0, 2) else (f"b{i}", f"a{i}"))
+    perm = list(rng.permutation(len(names)))
+    names, edges = [names[i] for i in perm], [edges[i] for i in perm]
+    a, b = _pair(ref_tat, sym, names, edges, rng)
+    _same(a.identity_(pairs), b.identity_(pairs), sym)

@@ -758,33 +758,51 @@ class Tensor:
 
     # -- identity ------------------------------------------------------------------------------
     def identity_(self, pairs):
-        """Set to the identity between the paired edges (identity.hpp); host-side fill, not on the hot path."""
+        """Set to the identity between the paired edges (identity.hpp:30-136); host-side fill, not on the hot path.  A block is
+        touched when every pair carries opposite symmetries; its "diagonal" (equal indices inside every pair) is set to +1, or
+        to -1 when bringing every pair into the order (arrow false, arrow true) is an odd permutation of odd-parity edges."""
         pairs = [tuple(p) for p in pairs]
-        half = len(pairs)
-        order = [a for a, _ in pairs] + [b for _, b in pairs]
-        t = self.transpose(order) if order != self.names else self
-        a = np.zeros(t._table.size)
+        rank = len(self.names)
+        partner = {}
+        for a, b in pairs:
+            partner[a], partner[b] = b, a
+        if len(partner) != rank or any(n not in partner for n in self.names):
+            raise RuntimeError("identity_ needs every edge in exactly one pair")
         S = self.Symmetry
-        for b, pos in enumerate(t._table.positions):
-            dims = [int(d) for d in t._table.dims[b]]
-            ok = True
-            for i in range(half):
-                s0 = t._edges[i].segments[int(pos[i])][0]
-                s1 = t._edges[half + i].segments[int(pos[half + i])][0]
-                if not tuple.__eq__(-s0, s1) or dims[i] != dims[half + i]:
-                    ok = False
-            if not ok:
+        ordered, destination, seen, nxt = [], [0] * rank, set(), 0
+        for i, n in enumerate(self.names):
+            if i in seen:
                 continue
-            n = int(np.prod(dims[:half])) if half else 1
-            blockv = np.eye(n).reshape(dims)
-            off = int(t._table.offsets[b])
+            j = self.names.index(partner[n])
+            seen |= {i, j}
+            ordered.append((i, j))
+            first, second = (i, j) if not self._edges[i].arrow else (j, i)
+            destination[first], destination[second] = nxt, nxt + 1
+            nxt += 2
+        t = self._table
+        a = np.zeros(t.size)
+        for b, pos in enumerate(t.positions):
+            syms = [self._edges[i].segments[int(pos[i])][0] for i in range(rank)]
+            dims = [int(d) for d in t.dims[b]]
+            if any(not tuple.__eq__(-syms[i], syms[j]) or dims[i] != dims[j] for i, j in ordered):
+                continue
+            sign = 1.0
+            if S.is_fermi_symmetry:
+                odd = False
+                for i in range(rank):
+                    for j in range(i + 1, rank):
+                        if destination[i] > destination[j]:
+                            odd ^= bool(syms[i].parity) and bool(syms[j].parity)
+                sign = -1.0 if odd else 1.0
+            blockv = np.zeros(dims)
+            grids = np.indices([dims[i] for i, _ in ordered]).reshape(len(ordered), -1)
+            index = [None] * rank
+            for k, (i, j) in enumerate(ordered):
+                index[i] = index[j] = grids[k]
+            blockv[tuple(index)] = sign
+            off = int(t.offsets[b])
             a[off:off + blockv.size] = blockv.reshape(-1)
-        t = t.same_shape()
-        t._set_host(a)
-        if S.is_fermi_symmetry:
-            raise NotImplementedError("identity_ for fermionic tensors is outside the hot path")
-        r = t.transpose(self.names) if order != self.names else t
-        self._data = r._data
+        self._set_host(a)
         return self
 
     identity = identity_
@@ -801,8 +819,6 @@ class Tensor:
         fermionic version carries the parity signs of trace.hpp:120-160 and is not needed on the sweep / ergodic path)."""
         if fuse_names:
             raise NotImplementedError("trace with fuse_names is outside the sampling-VMC hot path")
-        if self.Symmetry.is_fermi_symmetry:
-            raise NotImplementedError("trace of fermionic tensors is outside the sampling-VMC hot path (SURVEY.md 8f-1)")
         pairs = [tuple(p) for p in trace_pairs]
         if not pairs:
             return self.copy()

@@ -11,7 +11,7 @@ The truncation sequences follow the reference step for step, because with a fini
 (parity: tests/test_direct_sampling.py compares trajectories and probabilities with the unmodified reference).
 
 One chain per call (`nb = 1`): the conditional probabilities are read back site by site, a lock-step batch would gain nothing
-for symmetric tensors whose structure changes with every sampled charge.  Bosonic symmetries and no symmetry (`Tensor.trace`).
+for symmetric tensors whose structure changes with every sampled charge.  All symmetry types, fermionic ones included.
 """
 from __future__ import annotations
 
@@ -149,8 +149,6 @@ class DirectSampling(Sampling):
 
     def __init__(self, owner, cut_dimension, restrict_subspace, double_layer_cut_dimension, *, nb=1, rng=None):
         super().__init__(owner, cut_dimension, restrict_subspace)
-        if owner.Tensor.Symmetry.is_fermi_symmetry:
-            raise NotImplementedError("direct sampling of fermionic lattices needs the fermionic trace (SURVEY.md 8f-1)")
         if nb != 1:
             if owner.Tensor.Symmetry.length != 0:
                 raise NotImplementedError("a lock-step batch needs one block structure for all chains: symmetric lattices sample "

@@ -13,8 +13,7 @@ What changes against the reference is only what the B200 design needs:
 
 Entry points that SURVEY.md section 8 marks out of the path raise NotImplementedError instead of silently doing something
 else: numerical check-difference (debug aid).  Direct sampling (8f-1, the reference's default) is `direct_sampling.py`:
-bosonic / no symmetry, `chains` configurations per call for models without symmetry.  Gauge fixing (8f-3) is `SamplingLattice.expand_dimension`,
-bosonic / no symmetry.  The pseudo-inverse SR (8f-4) runs on
+`chains` configurations per call for models without symmetry.  Gauge fixing (8f-3) is `SamplingLattice.expand_dimension`.  The pseudo-inverse SR (8f-4) runs on
 library eigen-solvers instead of ScaLAPACK.
 State and configuration files are written in the reference's own formats (checkpoint.py).
 """

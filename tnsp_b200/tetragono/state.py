@@ -249,9 +249,7 @@ class SamplingLattice(AbstractLattice):
         `epsilon == 0` this only fixes the gauge (the state is unchanged).  Bond order as the reference: vertical bonds below odd
         rows, below even rows, then horizontal bonds right of odd columns, of even columns; every rank does all bonds, the
         arithmetic is deterministic (and the noise comes from the shared TAT.random engine), so no broadcast is needed.
-        Bosonic symmetries and no symmetry (the diagonal identity of a fermionic bond is outside the hot path)."""
-        if self.Tensor.Symmetry.is_fermi_symmetry:
-            raise NotImplementedError("expand_dimension for fermionic lattices is outside the sampling-VMC hot path (SURVEY.md 8f-3)")
+        All symmetry types (the fermionic signs sit in `Tensor.identity_`, identity.hpp)."""
         for parity in (0, 1):
             for l1, l2 in self.sites():
                 if l1 != 0 and l1 % 2 == parity:
