@@ -227,3 +227,29 @@ def test_driver_with_lockstep_direct_sampling():
                                                               direct_sampling_cut_dimension=4, use_natural_gradient=True,
                                                               conjugate_gradient_method_step=3, use_fix_relative_step_size=True)]
     assert len(energies) == 3 and np.all(np.isfinite(energies))
+
+
+def test_driver_embeds_symmetric_lattices_for_lockstep_chains():
+    """a U(1) lattice with chains > 1: the driver samples its charge-dense embedding and projects the gradient back; one chain
+    through the embedded path must reproduce the symmetric single-chain path step by step (same seeds -> same configurations)"""
+    meta, z = load("driver_heisU1_4x4_d1_Dc6_line_search")
+    conf0 = np.array(z["start_configuration"])
+    results = {}
+    for which in ("symmetric", "embedded"):
+        lat = build_lattice(meta, z)
+        conf = conf0.copy()
+        TAT.random.seed(12)
+        kw = dict(sampling_method="sweep", configuration_cut_dimension=meta["Dc"], use_natural_gradient=True, conjugate_gradient_method_step=2)
+        if which == "symmetric":
+            energies = [w["energy"] for w, _ in gradient_descent(lat, 5, 2, 0.01, chain_seeds=[77], sampling_configurations=conf, **kw)]
+        else:
+            # two identical chains (same seed): the batch statistics equal the single chain's
+            energies = [w["energy"] for w, _ in gradient_descent(lat, 10, 2, 0.01, chains=2, chain_seeds=[77, 77],
+                                                                 sampling_configurations=conf, **kw)]
+        results[which] = (np.array(energies), [np.asarray(lat[l1, l2].storage).copy() for l1 in range(lat.L1) for l2 in range(lat.L2)])
+    e_s, t_s = results["symmetric"]
+    e_e, t_e = results["embedded"]
+    assert np.abs(e_s[:, 0] - e_e[:, 0]).max() <= 1e-8 * np.abs(e_s[:, 0]).max()
+    scale = max(np.abs(a).max() for a in t_s)
+    for a, b in zip(t_s, t_e):
+        assert np.abs(a - b).max() <= 1e-7 * scale

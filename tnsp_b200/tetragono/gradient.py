@@ -174,6 +174,17 @@ def gradient_descent(
         energy_observer = Observer(state, enable_energy=True, enable_gradient=True, cache_configuration=cache_configuration,
                                    restrict_subspace=restrict, classical_energy=classical_energy)
 
+    # Lock-step chains of a bosonic-symmetric model run on its charge-dense embedding: the embedding is
+    # rebuilt from the symmetric parameters at the start of every step, sampled and observed, and the gradient is projected back
+    # onto the symmetric blocks (it is exactly zero outside them), so the optimisation itself stays in the symmetric picture.
+    embedded = chains > 1 and state.Tensor.Symmetry.length != 0
+    if embedded:
+        if state.Tensor.Symmetry.is_fermi_symmetry:
+            raise NotImplementedError("lock-step chains of fermionic lattices: run them one chain per call (chains=1)")
+        if sampling_method != "sweep" or measurement or use_line_search or restrict is not None or classical_energy is not None:
+            raise NotImplementedError("the embedded lock-step path supports sweep sampling with energy / gradient / SR only")
+        from . import dense_embedding
+
     # random engines: the reference re-seeds every process around the sampling phase of each step (`seed_differ`,
     # utility.py:138-160): seed = global uniform_int + rank, one uniform_real discarded; afterwards all processes are
     # put back on a common seed.  Chain c of rank r plays the role of process r * chains + c.
@@ -203,12 +214,16 @@ def gradient_descent(
     for grad_step in range(grad_total_step):
         configuration_pool = []
         seed_differ_enter()
+        work = state
+        if embedded:
+            work = dense_embedding.embed_lattice(state)
+            observer = Observer(work, enable_energy=True, enable_gradient=use_gradient, enable_natural_gradient=use_natural_gradient)
         with observer:
             if sampling_method == "sweep":
                 hopping = None
                 if sweep_hopping_hamiltonians is not None:
-                    hopping = _call_or_import(sweep_hopping_hamiltonians, "hopping_hamiltonians")(state)
-                sampling = SweepSampling(state, configuration_cut_dimension, restrict, hopping, nb=chains, rng=rng)
+                    hopping = _call_or_import(sweep_hopping_hamiltonians, "hopping_hamiltonians")(work)
+                sampling = SweepSampling(work, configuration_cut_dimension, restrict, hopping, nb=chains, rng=rng)
                 if configuration is not None:
                     sampling.configuration.import_configuration(configuration.export_configuration())
                 elif sampling_configurations is not None and np.size(sampling_configurations) != 0:
@@ -256,6 +271,8 @@ def gradient_descent(
                 grad = observer.natural_gradient_by_conjugate_gradient(conjugate_gradient_method_step, conjugate_gradient_method_error)
             else:
                 grad = observer.gradient
+            if embedded:
+                grad = dense_embedding.project_gradient(state, grad)
 
             if use_line_search:
                 scale = (lattice_dot(_lattice_of(state), _lattice_of(state)) / lattice_dot(grad, grad))**0.5
@@ -283,7 +300,7 @@ def gradient_descent(
 
             if fix_gauge:
                 state.expand_dimension(1.0, 0)
-            observer.normalize_lattice()
+            observer.normalize_lattice(state if embedded else None)
             bcast_lattice(state)
 
         yield (measurement_whole_result, measurement_result)

@@ -463,11 +463,12 @@ class Observer:
             out[l1][l2] = t_.conjugate(True)
         return out
 
-    def normalize_lattice(self):
-        """rescale every site tensor by exp(<log|ws|>/(L1 L2)) (observer.py:909-920)"""
+    def normalize_lattice(self, target=None):
+        """rescale every site tensor by exp(<log|ws|>/(L1 L2)) (observer.py:909-920); `target`: the lattice to rescale when the
+        observer watched its charge-dense embedding"""
         mean_log_ws = self._total_log_ws / self._count
         param = float(np.exp(mean_log_ws / (self.owner.L1 * self.owner.L2)))
-        owner = self.owner
+        owner = self.owner if target is None else target
         for l1, l2 in owner.sites():
             owner[l1, l2] = owner[l1, l2] / param
 
