@@ -267,6 +267,43 @@ def main():
             print(name, poss)
         np.savez(os.path.join(ROOT, "tests", "golden", "direct_sampling.npz"), **out)
         return
+    if "simple" in sys.argv[1:]:
+        # simple update (simple_update_lattice.py:252-344) from the fixture PEPS, then conversion.py:24-46 to a sampling lattice:
+        # bond environments (singular values), |site tensor| (the sign gauge of the svd is not pinned) and the exact amplitude of
+        # the fixture configuration of the converted state (gauge invariant)
+        out = {}
+        cases = (("heis_3x3_D2_Dc4", heisenberg(3, 3, 2), "neel", 3, 0.05, 2), ("heis_4x4_D3_Dc5_truncating", heisenberg(4, 4, 3), "neel", 2, 0.1, 2),
+                 ("heisU1_4x4_d1_Dc6", heisenberg_u1(4, 4, 1), "u1", 2, 0.05, 3), ("j1j2U1_4x4_d1_Dc9", j1j2_u1(4, 4, 1, 0.5), "u1", 1, 0.05, 3),
+                 ("tJ_4x4_D1_Dc8", tJ(4, 4, 1, 2), None, 2, 0.05, 8), ("hubbardFF_4x4_D1_Dc8", hubbard_ff(4, 4, 1, 8), None, 2, 0.05, 6),
+                 ("heis_3x3_D2_Dc4:relative", heisenberg(3, 3, 2), "neel", 2, 0.05, 0.3))
+        gauge = np.load(os.path.join(ROOT, "tests", "golden", "gauge_fixing.npz"))
+        for name, lat, points, steps, tau, dim in cases:
+            fixture = name.split(":")[0]
+            su = tet.conversion.sampling_lattice_to_simple_update_lattice(lat)
+            su.update(steps, tau, dim)
+            for l1 in range(su.L1):
+                for l2 in range(su.L2):
+                    out[f"{name}_site_{l1}_{l2}"] = np.abs(np.array(su[l1, l2].storage))
+                    out[f"{name}_dims_{l1}_{l2}"] = np.array([su[l1, l2].edge_by_name(n).dimension for n in su[l1, l2].names])
+                    for d in "RD":
+                        env = su.environment[l1, l2, d]
+                        if env is not None:
+                            out[f"{name}_env_{l1}_{l2}_{d}"] = np.array(env.storage)
+            back = tet.conversion.simple_update_lattice_to_sampling_lattice(su)
+            conf = tet.sampling_lattice.Configuration(back, 256)
+            if points is None:
+                conf.import_configuration(gauge[fixture + "_conf"])
+            else:
+                pts = neel_u1(back) if points == "u1" else neel(back)
+                for l1 in range(back.L1):
+                    for l2 in range(back.L2):
+                        for o, p in pts[l1][l2].items():
+                            conf[l1, l2, o] = p
+            out[name + "_par"] = np.array([steps, tau, dim])
+            out[name + "_ws"] = np.array([float(conf.hole(()))])
+            print(name, out[name + "_ws"], [int(x) for x in out[f"{name}_dims_1_1"]])
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "simple_update.npz"), **out)
+        return
     if "gauge" in sys.argv[1:]:
         # gauge fixing (SamplingLattice.expand_dimension(1.0, 0), lattice.py:821-919): the TRUNCATED amplitude of the fixture
         # configuration afterwards -- it depends on the gauge the reference fixes, not only on the state

@@ -202,3 +202,23 @@ def test_identity(ref_tat, sym, seed):
     names, edges = [names[i] for i in perm], [edges[i] for i in perm]
     a, b = _pair(ref_tat, sym, names, edges, rng)
     _same(a.identity_(pairs), b.identity_(pairs), sym)
+
+
+@pytest.mark.parametrize("sym,seed", _cases(6))
+def test_exponential(ref_tat, sym, seed):
+    """tensor exponential over paired edges for all symmetry types (exponential.hpp: merge with the fermionic reverse / merge
+    signs, per-sector Pade scaling-and-squaring, split back); values <= 1e-12 relative (the reference solves with LAPACK gesv)"""
+    rng = np.random.default_rng(9000 + seed)
+    n_pairs = int(rng.integers(1, 3))
+    names, edges, pairs = [], [], set()
+    for i in range(n_pairs):
+        e = rand_edge(rng, sym, max_seg=3, max_dim=2)
+        names += [f"a{i}", f"b{i}"]
+        edges += [e, conj_edge(sym, e)]
+        pairs.add((f"a{i}", f"b{i}") if rng.integers(0, 2) else (f"b{i}", f"a{i}"))
+    perm = list(rng.permutation(len(names)))
+    names, edges = [names[i] for i in perm], [edges[i] for i in perm]
+    a, b = _pair(ref_tat, sym, names, edges, rng)
+    for step in (8, 2):
+        _same(a.exponential(pairs, step), b.exponential(pairs, step), sym, tol=1e-12)
+    _same(a.exponential(pairs), b.exponential(pairs), sym, tol=1e-12)

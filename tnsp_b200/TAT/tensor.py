@@ -175,6 +175,28 @@ class _BlocksProxy:
         t._set_host(a)
 
 
+def _matrix_exponential(a, q):
+    """exp(a) as the reference computes it (exponential.hpp:92-150): scale by 2^-j with j = max(0, 1 + int(log2(max|a|))), the
+    diagonal (q, q) Pade approximant D^-1 N, then j squarings."""
+    n = a.shape[0]
+    if n == 0:
+        return a.copy()
+    biggest = float(np.abs(a).max())
+    j = max(0, 1 + int(np.log2(biggest))) if biggest > 0 else 0
+    a = a / float(1 << j)
+    d, num, x = np.eye(n), np.eye(n), np.eye(n)
+    c = 1.0
+    for k in range(1, q + 1):
+        c = (c * (q - k + 1)) / ((2 * q - k + 1) * k)
+        x = a @ x
+        num = num + c * x
+        d = d + (c if k % 2 == 0 else -c) * x
+    f = np.linalg.solve(d, num)
+    for _ in range(j):
+        f = f @ f
+    return f
+
+
 class Tensor:
     """Created per (symmetry, scalar) by ``TAT/__init__.py``; class attributes: Symmetry, Edge, model, dtype ..."""
 
@@ -811,7 +833,65 @@ class Tensor:
     def _not_on_path(self, *a, **k):
         raise NotImplementedError("this Tensor method is outside the sampling-VMC hot path (SURVEY.md section 8)")
 
-    exponential = shrink = expand = clear_fermi_symmetry = _not_on_path
+    shrink = expand = clear_fermi_symmetry = _not_on_path
+
+    def exponential(self, pairs, step=8):
+        """Tensor exponential over paired edges (reference: TAT/include/TAT/implement/exponential.hpp:155-273, PyTAT default
+        step = 8): merge the first / second names of the pairs into a square matrix of sectors (reversing arrow-true first edges,
+        parity applied on the second edge only, merge sign on the first group only), exponentiate every sector by scaling and
+        squaring of the (step, step) Pade approximant (exponential.hpp:92-150), split back.  Set-up work of simple update (one
+        d^2 x d^2 matrix per Hamiltonian term and call of `update`): the sector matrices are exponentiated on the host, the two
+        edge operators are the device pack kernel."""
+        pairs = [tuple(p) for p in pairs]
+        rank = len(self.names)
+        if 2 * len(pairs) != rank:
+            raise RuntimeError("Invalid pairs in exponential")
+        valid = [True] * rank
+        merge_1, merge_2, split_1, split_2 = [], [], [], []
+        reverse_names, parity_names = set(), set()
+        for i in range(rank - 1, -1, -1):
+            if not valid[i]:
+                continue
+            name = self.names[i]
+            other = former = None
+            for n1, n2 in pairs:
+                if n1 == name:
+                    other, former = n2, True
+                    break
+                if n2 == name:
+                    other, former = n1, False
+                    break
+            if other is None or other not in self.names:
+                raise RuntimeError("Invalid pairs in exponential")
+            j = self.names.index(other)
+            valid[j] = False
+            (name_1, index_1), (name_2, index_2) = ((name, i), (other, j)) if former else ((other, j), (name, i))
+            merge_1.append(name_1)
+            merge_2.append(name_2)
+            split_1.append((name_1, self._edges[index_1]))
+            split_2.append((name_2, self._edges[index_2]))
+            if self._edges[index_1].conjugate() != self._edges[index_2]:
+                raise RuntimeError("Incompatible edges in exponential")
+            if self.Symmetry.is_fermi_symmetry and self._edges[index_1].arrow:
+                reverse_names.update((name_1, name_2))
+                parity_names.add(name_2)
+        for l in (merge_1, merge_2, split_1, split_2):
+            l.reverse()
+        e1, e2 = "Exponential_1", "Exponential_2"
+        merged = self._edge_operator(None, reverse_names, {e1: merge_1, e2: merge_2}, [e1, e2], False, (), parity_names, (), {e2})
+        src = np.atleast_2d(merged._host())
+        out = np.zeros_like(src)
+        t = merged._table
+        for b in range(len(t.positions)):
+            n, m = (int(d) for d in t.dims[b])
+            if n != m:
+                raise RuntimeError("Incompatible edges in exponential")
+            off = int(t.offsets[b])
+            for c in range(src.shape[0]):
+                out[c, off:off + n * n] = _matrix_exponential(src[c, off:off + n * n].reshape(n, n), step).reshape(-1)
+        result = merged.same_shape()
+        result._set_host(out)
+        return result._edge_operator({e1: split_1, e2: split_2}, reverse_names, None, merge_1 + merge_2, False, {e2}, parity_names)
 
     def trace(self, trace_pairs, fuse_names=None):
         """Partial trace over pairs of edges (trace.hpp; the reference's DirectSampling uses it): a contraction
