@@ -337,6 +337,15 @@ def main():
             print(name, out[name])
         np.savez(os.path.join(ROOT, "tests", "golden", "gauge_fixing.npz"), **out)
         return
+    if "sustate" in sys.argv[1:]:
+        # a simple-update checkpoint exactly as the reference writes it: pickle of the SimpleUpdateLattice after an update
+        import pickle
+        lat = heisenberg_u1(4, 4, 1)
+        su = tet.conversion.sampling_lattice_to_simple_update_lattice(lat)
+        su.update(2, 0.05, 3)
+        with open(os.path.join(ROOT, "tests", "golden", "state_su_heisU1_4x4_d1.pkl"), "wb") as f:
+            pickle.dump(su, f)
+        return
     if "state" in sys.argv[1:]:
         # checkpoints exactly as the reference writes them (utility.py:365-388): pickle of the SamplingLattice
         import pickle

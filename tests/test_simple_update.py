@@ -100,3 +100,29 @@ def test_imaginary_time_evolution_lowers_the_energy():
     su.update(20, 0.05, 2)
     after = energy(simple_update_lattice_to_sampling_lattice(su))
     assert after < before - 0.05
+
+
+def test_reference_simple_update_checkpoint_loads():
+    """a `pickle.dump(SimpleUpdateLattice)` of the unmodified reference (state_su_heisU1_4x4_d1.pkl, the heisU1 case above after
+    its update) loads bit-exactly -- tensors and bond environments -- and converts to the sampling state with the same amplitude"""
+    from tnsp_b200.tetragono.checkpoint import load_reference_state
+    gold = np.load(os.path.join(HERE, "simple_update.npz"))
+    case = "heisU1_4x4_d1_Dc6"
+    su = load_reference_state(os.path.join(HERE, "state_su_heisU1_4x4_d1.pkl"))
+    assert isinstance(su, SimpleUpdateLattice)
+    for l1, l2 in su.sites():
+        assert np.array_equal(np.abs(np.asarray(su[l1, l2].storage)), gold[f"{case}_site_{l1}_{l2}"])
+        for d in "RD":
+            env = su.environment[l1, l2, d]
+            key = f"{case}_env_{l1}_{l2}_{d}"
+            assert (env is None) == (key not in gold.files)
+            if env is not None:
+                assert np.array_equal(np.asarray(env.storage), gold[key])
+    meta, _ = load(case)
+    back = simple_update_lattice_to_sampling_lattice(su)
+    conf = Configuration(back, 256)
+    pts = config_points(meta)
+    for l1, l2 in back.sites():
+        for o, p in pts[l1][l2].items():
+            conf[l1, l2, o] = p
+    assert abs(float(conf.hole(())) - gold[case + "_ws"][0]) <= 1e-10 * abs(gold[case + "_ws"][0])

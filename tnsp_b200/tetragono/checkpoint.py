@@ -58,6 +58,10 @@ class _StateShim:
         self.state = state[1] if isinstance(state, tuple) else state
 
 
+class _SimpleUpdateShim(_StateShim):
+    pass
+
+
 def _shim(base, model):
     return type(base.__name__, (base,), {"model": model})
 
@@ -80,6 +84,8 @@ class _ReferenceUnpickler(pickle.Unpickler):
                 return model.D.Tensor
         if module.startswith("tetragono") and name == "SamplingLattice":
             return _StateShim
+        if module.startswith("tetragono") and name == "SimpleUpdateLattice":
+            return _SimpleUpdateShim
         if module.startswith("numpy") and name in ("_reconstruct", "ndarray", "dtype"):
             return getattr(__import__(module, fromlist=[name]), name)
         if (module, name) in (("builtins", "set"), ("builtins", "frozenset"), ("collections", "OrderedDict")):
@@ -100,7 +106,10 @@ def _plain(x):
 
 
 def load_reference_state(source):
-    """`source`: bytes, a path or a binary file object holding the reference's pickle of a SamplingLattice (data_version 6)."""
+    """`source`: bytes, a path or a binary file object holding the reference's pickle of a SamplingLattice (data_version 6), or of a
+    SimpleUpdateLattice (simple_update_lattice.py:148-196, data_version 6: site tensors that include their bond environments +
+    `_environment_h/_v`), which comes back as this repository's `SimpleUpdateLattice` -- convert it with
+    `simple_update_lattice_to_sampling_lattice` to sample it."""
     if isinstance(source, (bytes, bytearray)):
         stream = io.BytesIO(source)
     elif isinstance(source, str):
@@ -120,7 +129,13 @@ def load_reference_state(source):
         raise RuntimeError(f"checkpoint data_version {version}: only version 6 (current reference) is supported; "
                            "re-save the state with the reference first")
     state = {k: _plain(v) for k, v in state.items()}
-    lat = SamplingLattice.__new__(SamplingLattice)
+    if isinstance(shim, _SimpleUpdateShim):
+        from .simple_update import SimpleUpdateLattice
+        lat = SimpleUpdateLattice.__new__(SimpleUpdateLattice)
+        lat._environment_h = [[state["_environment_h"][l1][l2] for l2 in range(int(state["L2"]) - 1)] for l1 in range(int(state["L1"]))]
+        lat._environment_v = [[state["_environment_v"][l1][l2] for l2 in range(int(state["L2"]))] for l1 in range(int(state["L1"]) - 1)]
+    else:
+        lat = SamplingLattice.__new__(SamplingLattice)
     lat.Tensor = state["Tensor"]
     lat.L1, lat.L2 = int(state["L1"]), int(state["L2"])
     lat._physics_edges = [[dict(state["_physics_edges"][l1][l2]) for l2 in range(lat.L2)] for l1 in range(lat.L1)]
