@@ -337,6 +337,45 @@ def main():
             print(name, out[name])
         np.savez(os.path.join(ROOT, "tests", "golden", "gauge_fixing.npz"), **out)
         return
+    if "longrange" in sys.argv[1:]:
+        # observables beyond the 2x2 replace window (ConfigurationPool.wss, lattice.py:562-614; Observer(cache_configuration=True)):
+        # the first two-site Hamiltonian tensor placed on distant pairs of sites, measured on the first sweep samples after the fixture
+        # configuration; Dc large enough that every contraction route is exact
+        out = {}
+        gauge = np.load(os.path.join(ROOT, "tests", "golden", "gauge_fixing.npz"))
+        for name, lat, points, seed in (("heis_3x3_D2_Dc4", heisenberg(3, 3, 2), "neel", 31), ("heisU1_4x4_d1_Dc6", heisenberg_u1(4, 4, 1), "u1", 32),
+                                        ("tJ_4x4_D1_Dc8", tJ(4, 4, 1, 2), None, 33)):
+            L1, L2 = lat.L1, lat.L2
+            term = [h for p, h in lat.hamiltonians if len(p) == 2][0]
+            pairs = [((0, 0, 0), (L1 - 1, L2 - 1, 0)), ((0, 0, 0), (0, L2 - 1, 0)), ((0, 1, 0), (L1 - 1, 1, 0)), ((L1 - 1, 0, 0), (0, L2 - 1, 0)),
+                     ((0, 0, 0), (0, 1, 0))]
+            TAT.random.seed(seed)
+            sampling = tet.sampling_lattice.SweepSampling(lat, 64, None, None)
+            if points is None:
+                sampling.configuration.import_configuration(gauge[name + "_conf"])
+            else:
+                pts = neel_u1(lat) if points == "u1" else neel(lat)
+                for l1 in range(L1):
+                    for l2 in range(L2):
+                        for o, p in pts[l1][l2].items():
+                            sampling.configuration[l1, l2, o] = p
+            for mode in (True, "drop"):
+                obs = tet.sampling_lattice.Observer(lat, cache_configuration=mode)
+                obs.add_observer("far", {pair: term for pair in pairs})
+                confs = []
+                with obs:
+                    for _ in range(3):
+                        p, c = sampling()
+                        confs.append(c.export_configuration())
+                        obs(p, c)
+                tag = name + ("_drop" if mode == "drop" else "")
+                out[tag + "_conf"] = np.array(confs)
+                out[tag + "_far"] = np.array([obs._result_reweight["far"][pair] / obs._total_weight for pair in pairs])
+                print(tag, out[tag + "_far"])
+            out[name + "_pairs"] = np.array(pairs)
+            out[name + "_seed"] = np.array([seed])
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "long_range.npz"), **out)
+        return
     if "sustate" in sys.argv[1:]:
         # a simple-update checkpoint exactly as the reference writes it: pickle of the SimpleUpdateLattice after an update
         import pickle

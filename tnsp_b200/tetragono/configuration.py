@@ -232,3 +232,59 @@ class Configuration(SingleLayerAuxiliaries):
                 holes[l1][l2] = hole
             self._holes = holes
         return self._holes
+
+
+class ConfigurationPool:
+    """Amplitudes of configurations that differ from a sampled one OUTSIDE the 2x2 window of `Configuration.replace`
+    (long-range observables; reference: sampling_lattice/lattice.py:473-700 `ConfigurationPool.wss`).  The replacement is split as
+    the reference splits it (`_split_replacement`, :648-684: the last cluster of changed sites that fits a 2x2 window stays a
+    replacement, the rest is applied to a copy of the configuration), the half-replaced configurations are kept so that the
+    other matrix elements of the same observable reuse their environments.  Where the reference may also answer from the
+    "nearest" configuration it has seen (a different but equivalent contraction route -- equal up to the boundary truncation),
+    this pool always takes the split route.  Only copies made here are stored, never the sampler's live configuration."""
+
+    def __init__(self, owner):
+        self.owner = owner
+        self.tree = {}
+
+    def _key(self, configuration, replacement=None):
+        config = np.array(configuration.export_configuration())
+        if replacement:
+            for (l1, l2, orbit), point in replacement.items():
+                point = configuration._construct_edge_point(point)
+                config[..., l1, l2, orbit] = Configuration._index_by_point(self.owner.physics_edges[l1, l2, orbit], point)
+        return config.tobytes()
+
+    def _split_replacement(self, replacement):
+        first, second = {}, {}
+        up, down, left, right = self.owner.L1, -1, self.owner.L2, -1
+        for l1, l2 in self.owner.sites():
+            for orbit in self.owner.physics_edges[l1, l2]:
+                site = (l1, l2, orbit)
+                if site not in replacement:
+                    continue
+                if down - 2 < l1 < up + 2 and right - 2 < l2 < left + 2:
+                    second[site] = replacement[site]
+                    up, down, left, right = min(up, l1), max(down, l1), min(left, l2), max(right, l2)
+                else:
+                    first[site] = replacement[site]
+        return first, second
+
+    def wss(self, configuration, replacement):
+        wss = configuration.replace(replacement)
+        if wss is not None:
+            return wss
+        whole = self._key(configuration, replacement)
+        if whole in self.tree:
+            return self.tree[whole].hole(())
+        first, second = self._split_replacement(replacement)
+        key = self._key(configuration, first)
+        if key not in self.tree:
+            half = configuration.copy()
+            for site, point in first.items():
+                half[site] = point
+            self.tree[key] = half
+        wss = self.tree[key].replace(second)
+        if wss is None:
+            raise NotImplementedError("not implemented replace style")
+        return wss

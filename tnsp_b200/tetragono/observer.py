@@ -34,8 +34,14 @@ class Observer:
         self._restrict_subspace = restrict_subspace
         self._classical_energy = classical_energy
         self._start = False
-        if cache_natural_delta is not None or cache_configuration:
-            raise NotImplementedError("delta / configuration caches are outside the hot path (SURVEY.md 8f)")
+        if cache_natural_delta is not None:
+            raise NotImplementedError("the natural-gradient delta cache is outside the hot path (SURVEY.md 8f)")
+        if cache_configuration not in (False, True, "drop"):
+            raise ValueError("cache_configuration must be False, True or 'drop'")
+        # observer.py:198,305-331: with a configuration cache, observables beyond the 2x2 replace window are measured through
+        # ConfigurationPool.wss; "drop" starts an empty pool at every sample
+        self._cache_configuration = cache_configuration
+        self._pool = None
         if enable_energy:
             self.add_energy()
         if enable_gradient:
@@ -71,6 +77,7 @@ class Observer:
         z = lambda: {name: {positions: 0.0 for positions in obs} for name, obs in self._observer.items()}  # noqa: E731
         self._result_reweight, self._result_reweight_square, self._result_square_reweight_square = z(), z(), z()
         self._count = 0
+        self._pool = None
         self._total_weight = 0.0
         self._total_weight_square = 0.0
         self._total_log_ws = 0.0
@@ -123,6 +130,9 @@ class Observer:
     def __call__(self, possibility, configuration):
         owner = self.owner
         nb = configuration.nb
+        if self._cache_configuration and (self._pool is None or self._cache_configuration == "drop"):
+            from .configuration import ConfigurationPool
+            self._pool = ConfigurationPool(owner)
         self._count += nb
         ws = configuration.hole(())
         ws_val = _values(ws)
@@ -162,9 +172,12 @@ class Observer:
                     replacement = {positions[i]: Configuration._point_by_index(table.edges[i], new_idx[i]) for i in range(body)}
                     if self._restrict_subspace is not None and not self._restrict_subspace(configuration, replacement):
                         continue
-                    wss = configuration.replace(replacement)
-                    if wss is None:
-                        raise NotImplementedError("not implemented replace style")
+                    if self._pool is not None:
+                        wss = self._pool.wss(configuration, replacement)
+                    else:
+                        wss = configuration.replace(replacement)
+                        if wss is None:
+                            raise NotImplementedError("not implemented replace style, set cache_configuration to True to calculate it")
                     if no_symmetry:
                         # <psi|s'> H_{s's} / <psi|s>  for real amplitudes.  Device tensors: the amplitudes are only queued here
                         # and read back ONCE per observable set (one device -> host copy instead of one blocking copy per
