@@ -376,6 +376,34 @@ def main():
             out[name + "_seed"] = np.array([seed])
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", "long_range.npz"), **out)
         return
+    if "hamiltonian" in sys.argv[1:]:
+        # Hamiltonian bookkeeping (abstract_state.py:200-240, utility.py:421-480) and lattice_dot (lattice.py:921-934) on a
+        # fermionic model, where the renames / traces carry signs
+        arrays, meta = {}, {}
+        lat = tJ(4, 4, 1, 2)
+        pe = lat.physics_edges[0, 0, 0]
+        T = lat.Tensor
+        TAT.random.seed(77)
+        three = T(["I0", "I1", "I2", "O0", "O1", "O2"], [pe.conjugate()] * 3 + [pe] * 3).randn_()
+        four = T(["O0", "I0", "O1", "I1", "O2", "I2", "O3", "I3"], [pe, pe.conjugate()] * 4).randn_()
+        meta["three"] = tensor_desc("FermiU1BoseU1", three, arrays, "three")
+        meta["four"] = tensor_desc("FermiU1BoseU1", four, arrays, "four")
+        meta["cases"] = []
+        for kind, tensor, points in (("trace", "three", ((0, 0, 0), (0, 1, 0), (0, 0, 0))), ("trace", "three", ((0, 1, 0), (0, 1, 0), (0, 0, 0))),
+                                     ("trace", "four", ((1, 1, 0), (0, 0, 0), (1, 1, 0), (0, 0, 0))), ("trace", "four", ((1, 1, 0), (1, 1, 0), (1, 1, 0), (0, 0, 0))),
+                                     ("sort", "three", ((1, 0, 0), (0, 0, 0), (0, 1, 0))), ("sort", "four", ((3, 0, 0), (0, 2, 0), (0, 1, 0), (2, 2, 0)))):
+            fn = tet.utility.trace_repeated if kind == "trace" else tet.utility.sort_points
+            result, new_points = fn({"three": three, "four": four}[tensor], points)
+            i = len(meta["cases"])
+            meta["cases"].append({"kind": kind, "tensor": tensor, "points": [list(p) for p in points], "new_points": [list(p) for p in new_points],
+                                  "result": tensor_desc("FermiU1BoseU1", result, arrays, f"result_{i}")})
+        arrays["lattice_dot"] = np.array([lat.lattice_dot()])
+        herm = three + three.conjugate().edge_rename({f"I{i}": f"O{i}" for i in range(3)} | {f"O{i}": f"I{i}" for i in range(3)})
+        meta["hermitian"] = tensor_desc("FermiU1BoseU1", herm, arrays, "hermitian")
+        arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hamiltonian_tools.npz"), **arrays)
+        print(arrays["lattice_dot"], [c["result"]["names"] for c in meta["cases"]])
+        return
     if "sustate" in sys.argv[1:]:
         # a simple-update checkpoint exactly as the reference writes it: pickle of the SimpleUpdateLattice after an update
         import pickle

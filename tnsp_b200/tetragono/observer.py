@@ -49,6 +49,22 @@ class Observer:
         if enable_natural_gradient:
             self.enable_natural_gradient()
 
+    def set_classical_energy(self, classical_energy=None):
+        """a function of the Configuration whose value is added to the energy (observer.py:213-222)"""
+        self._classical_energy = classical_energy
+
+    def restrict_subspace(self, restrict_subspace):
+        if self._start:
+            raise RuntimeError("Cannot set restrict subspace after sampling start")
+        self._restrict_subspace = restrict_subspace
+
+    def cache_configuration(self, cache_configuration):
+        if self._start:
+            raise RuntimeError("Cannot enable caching after sampling start")
+        if cache_configuration not in (False, True, "drop"):
+            raise ValueError("cache_configuration must be False, True or 'drop'")
+        self._cache_configuration = cache_configuration
+
     def add_observer(self, name, observers):
         if self._start:
             raise RuntimeError("Cannot enable hole after sampling start")

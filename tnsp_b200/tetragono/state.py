@@ -54,6 +54,32 @@ class _Hamiltonians:
     def __contains__(self, key):
         return key in self.owner._hamiltonians
 
+    def _regroup(self, transform):
+        result = {}
+        for key, value in self:
+            value, key = transform(value, key)
+            result[key] = result[key] + value if key in result else value
+        self.owner._hamiltonians = result
+        return self
+
+    def trace_repeated(self):
+        """terms whose point list names a point more than once: contract the output of an earlier occurrence with the input of
+        the next one, so that every point appears once (abstract_state.py:200-212, utility.py:421-465)"""
+        return self._regroup(trace_repeated)
+
+    def sort_points(self):
+        """points of every term in ascending order (edges renamed accordingly), terms on the same points summed
+        (abstract_state.py:214-226, utility.py:468-480)"""
+        return self._regroup(sort_points)
+
+    def check_hermite(self, threshold):
+        for _, value in self:
+            body = len(value.names) // 2
+            swap = {f"I{i}": f"O{i}" for i in range(body)} | {f"O{i}": f"I{i}" for i in range(body)}
+            if float((value - value.conjugate().edge_rename(swap)).norm_max()) > threshold:
+                raise ValueError("The Hamiltonian is not Hermitian")
+        return self
+
     def __setitem__(self, arg, tensor):
         o = self.owner
         if isinstance(arg, str):
@@ -70,6 +96,41 @@ class _Hamiltonians:
                     raise ValueError("Unknown kind of hamiltonian")
         else:
             o._set_hamiltonian(tuple(p if len(p) == 3 else (p[0], p[1], 0) for p in arg), tensor)
+
+
+_REGROUP_POOL = {}
+
+
+def trace_repeated(tensor, points):
+    """-> (tensor with one (I, O) pair per distinct point, the distinct points in order of first appearance); utility.py:421-465.
+    Results are kept per (tensor identity, pattern): the element tables of the samplers are cached by tensor identity too."""
+    uniques, to_unique, first_index = [], [], []
+    for index, point in enumerate(points):
+        if point not in uniques:
+            first_index.append(index)
+            uniques.append(point)
+        to_unique.append(uniques.index(point))
+    key = ("trace", id(tensor), tuple(to_unique))
+    if key not in _REGROUP_POOL:
+        trace_set, rename = set(), {}
+        for u in range(len(uniques)):
+            group = [i for i, v in enumerate(to_unique) if v == u]
+            trace_set.update((f"I{former}", f"O{latter}") for former, latter in zip(group[:-1], group[1:]))
+            rename[f"I{group[-1]}"] = f"I{group[0]}"
+        result = tensor.trace(trace_set).edge_rename(rename)
+        result = result.edge_rename({f"{d}{old}": f"{d}{new}" for new, old in enumerate(first_index) for d in "IO"})
+        _REGROUP_POOL[key] = (tensor, result)
+    return _REGROUP_POOL[key][1], tuple(uniques)
+
+
+def sort_points(tensor, points):
+    """-> (tensor with its (I, O) pairs renumbered to the ascending order of the points, the sorted points); utility.py:468-480"""
+    ordered = tuple(sorted(points))
+    order = tuple(ordered.index(point) for point in points)
+    key = ("sort", id(tensor), order)
+    if key not in _REGROUP_POOL:
+        _REGROUP_POOL[key] = (tensor, tensor.edge_rename({f"{d}{before}": f"{d}{after}" for before, after in enumerate(order) for d in "IO"}))
+    return _REGROUP_POOL[key][1], ordered
 
 
 class AbstractState:
@@ -235,6 +296,16 @@ class SamplingLattice(AbstractLattice):
 
     def __setitem__(self, l1l2, value):
         self._lattice[l1l2[0]][l1l2[1]] = value
+
+    def lattice_dot(self, a=None, b=None):
+        """sum over sites of <a, b> with the trivial metric; the lattice's own tensors where None is given (lattice.py:921-934)"""
+        a = self._lattice if a is None else a
+        b = self._lattice if b is None else b
+        total = 0.0
+        for l1, l2 in self.sites():
+            x, y = a[l1][l2], b[l1][l2]
+            total += float(x.conjugate(True).contract(y, {(name, name) for name in x.names}))
+        return total
 
     def apply_gradient(self, gradient, step_size):
         """theta <- theta - step * g  (lattice.py:921-948, plain update)"""
