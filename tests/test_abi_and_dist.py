@@ -90,6 +90,10 @@ out = dict(energy=list(obs.total_energy), count=obs._count,
            grad=[np.asarray(t.storage).tolist() for row in g for t in row],
            ngrad=[np.asarray(t.storage).tolist() for row in ng for t in row],
            pgrad=[np.asarray(t.storage).tolist() for row in pg for t in row])
+original = float(np.asarray(lat[0, 0].storage).sum())
+lat[0, 0] = lat[0, 0] * float(rank + 2)            # the ranks drift apart ...
+lat.bcast_lattice(root=world - 1)                   # ... and take the last rank's tensors (lattice.py:950-954)
+out["bcast_ratio"] = float(np.asarray(lat[0, 0].storage).sum()) / original
 if rank == 0:
     json.dump(out, open({out!r}, "w"))
 if world > 1:
@@ -115,6 +119,7 @@ def test_two_ranks_over_gloo_equal_one_rank(tmp_path):
     _run(2, 29613, f2)
     a, b = json.load(open(f1)), json.load(open(f2))
     assert a["count"] == b["count"] == 12
+    assert abs(a["bcast_ratio"] - 2.0) < 1e-12 and abs(b["bcast_ratio"] - 3.0) < 1e-12
     assert np.allclose(a["energy"], b["energy"], rtol=1e-12, atol=0)
     for key, tol in (("grad", 1e-11), ("ngrad", 1e-9), ("pgrad", 1e-7)):
         scale = max(np.abs(np.array(x)).max() for x in a[key])

@@ -88,6 +88,12 @@ class Sampling:
         self._cut_dimension = cut_dimension
         self._restrict_subspace = restrict_subspace
 
+    def refresh_all(self):
+        raise NotImplementedError("Not implement in abstract sampling")
+
+    def __call__(self):
+        raise NotImplementedError("Not implement in abstract sampling")
+
 
 class SweepSampling(Sampling):
     def __init__(self, owner, cut_dimension, restrict_subspace=None, hopping_hamiltonians=None, *, nb=1, rng=None):

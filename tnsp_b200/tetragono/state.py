@@ -307,6 +307,11 @@ class SamplingLattice(AbstractLattice):
             total += float(x.conjugate(True).contract(y, {(name, name) for name in x.names}))
         return total
 
+    def bcast_lattice(self, root=0):
+        """all ranks take rank `root`'s site tensors: one broadcast of one flat buffer (lattice.py:950-954)"""
+        from .. import dist
+        dist.broadcast_tensors([self[l1, l2] for l1, l2 in self.sites()], root=root)
+
     def apply_gradient(self, gradient, step_size):
         """theta <- theta - step * g  (lattice.py:921-948, plain update)"""
         for l1, l2 in self.sites():
