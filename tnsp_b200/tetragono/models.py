@@ -120,3 +120,78 @@ def neel_points(lattice):
     if _is_u1(lattice.Tensor):
         return [[{0: (S(+1) if (l1 + l2) % 2 == 0 else S(-1), 0)} for l2 in range(lattice.L2)] for l1 in range(lattice.L1)]
     return [[{0: (S(), (l1 + l2) % 2)} for l2 in range(lattice.L2)] for l1 in range(lattice.L1)]
+
+
+# ---------------------------------------------------------------------------------------------------
+# fermionic models of BASELINE cfg3 / cfg4
+# ---------------------------------------------------------------------------------------------------
+def tJ_abstract_state(L1, L2, T, t, J):
+    """t-J model, symmetry (particle number: FermiU1, 2 Sz: BoseU1), T up and T down particles
+    (tetraku/tetraku/models/tJ/__init__.py:22-45)"""
+    from . import common_tensor
+    op = common_tensor.FermiU1_tJ
+    state = AbstractState(TAT.FermiU1BoseU1.D.Tensor, L1, L2)
+    state.physics_edges[...] = op.EF
+    H = (-t) * op.CC + (J / 2) * (op.SS - op.nn / 4)
+    state.hamiltonians["vertical_bond"] = H
+    state.hamiltonians["horizontal_bond"] = H
+    state.total_symmetry = (T * 2, 0)
+    return state
+
+
+def tJ_abstract_lattice(L1, L2, D, T, t, J):
+    """cfg4 family (tetraku/tetraku/models/tJ/__init__.py:48-80): the particles are fed in through column 0 (its vertical bonds
+    carry the charge still to be distributed over the rows below, +- 2 particles of either spin) and along the rows; all other
+    vertical bonds are trivial.  `D` is the dimension PER charge sector (9 sectors per charged bond)."""
+    state = AbstractLattice(tJ_abstract_state(L1, L2, T, t, J))
+
+    def charged(Q):
+        return [((2 * Q + dn, ds), D) for dn, spins in ((-2, (0,)), (-1, (-1, 1)), (0, (-2, 0, 2)), (1, (-1, 1)), (2, (0,))) for ds in spins]
+
+    per_row = T / L1
+    for l1 in range(L1 - 1):
+        state.virtual_bond[l1, 0, "D"] = charged(int(T * (L1 - l1 - 1) / L1))
+        for l2 in range(1, L2):
+            state.virtual_bond[l1, l2, "D"] = [((0, 0), D)]
+    for l1 in range(L1):
+        for l2 in range(L2 - 1):
+            state.virtual_bond[l1, l2, "R"] = charged(int(per_row * (L2 - l2 - 1) / L2))
+    return state
+
+
+def hubbard_fermi_fermi_abstract_state(L1, L2, T, t, U):
+    """Hubbard model with symmetry FermiU1 (n_up) x FermiU1 (n_down), T particles in total, half of each spin
+    (tetraku/tetraku/models/hubbard/fermi_fermi.py:22-47; cfg3 family)"""
+    from . import common_tensor
+    op = common_tensor.FermiFermi_Hubbard
+    if T % 2:
+        raise RuntimeError("T must be even number")
+    state = AbstractState(TAT.FermiU1FermiU1.D.Tensor, L1, L2)
+    state.total_symmetry = (T // 2, T // 2)
+    state.physics_edges[...] = [((0, 0), 1), ((0, 1), 1), ((1, 0), 1), ((1, 1), 1)]
+    state.hamiltonians["vertical_bond"] = -t * op.CSCS
+    state.hamiltonians["horizontal_bond"] = -t * op.CSCS
+    state.hamiltonians["single_site"] = U * op.NN
+    return state
+
+
+def hubbard_fermi_fermi_abstract_lattice(L1, L2, D, T, t, U):
+    """cfg3 family.  The reference ships no lattice for this symmetry; the bonds follow the charge-flow pattern of its FermiU1
+    Hubbard lattice (tetraku/tetraku/models/hubbard/__init__.py:47-75), as SURVEY.md 8d specifies: column-0 vertical bonds carry
+    the (up, down) charge still to be distributed below, +- 1 of either spin, row bonds the row's share, the rest is trivial;
+    `D` per charge sector (9 sectors per charged bond)."""
+    state = AbstractLattice(hubbard_fermi_fermi_abstract_state(L1, L2, T, t, U))
+    half = T // 2
+
+    def charged(Q):
+        return [((Q + a, Q + b), D) for a in (-1, 0, 1) for b in (-1, 0, 1)]
+
+    per_row = half / L1
+    for l1 in range(L1 - 1):
+        state.virtual_bond[l1, 0, "D"] = charged(int(half * (L1 - l1 - 1) / L1))
+        for l2 in range(1, L2):
+            state.virtual_bond[l1, l2, "D"] = [((0, 0), D)]
+    for l1 in range(L1):
+        for l2 in range(L2 - 1):
+            state.virtual_bond[l1, l2, "R"] = charged(int(per_row * (L2 - l2 - 1) / L2))
+    return state
