@@ -404,6 +404,29 @@ def main():
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hamiltonian_tools.npz"), **arrays)
         print(arrays["lattice_dot"], [c["result"]["names"] for c in meta["cases"]])
         return
+    if "common" in sys.argv[1:]:
+        # every real operator tensor of the reference's common_tensor modules, as its models take them (`.to(float)`)
+        arrays, meta = {}, {}
+        syms = {"No": "No", "Fermi": "FermiU1", "FermiU1_Hubbard": "FermiU1BoseU1", "FermiFermi_Hubbard": "FermiU1FermiU1", "FermiU1_tJ": "FermiU1BoseU1"}
+        for module, sym in syms.items():
+            mod = getattr(tet.common_tensor, module)
+            meta[module] = {"symmetry": sym, "tensors": {}}
+            def visit(prefix, holder):
+                for attr in sorted(vars(holder)):
+                    value = getattr(holder, attr)
+                    if attr.startswith("_"):
+                        continue
+                    if isinstance(value, mod.Tensor):
+                        raw = np.array(value.storage)
+                        if np.abs(raw.imag).max() == 0:
+                            meta[module]["tensors"][prefix + attr] = tensor_desc(sym, value.to(float), arrays, f"{module}.{prefix}{attr}")
+                    elif isinstance(value, type) and attr in ("Up", "Down"):
+                        visit(attr + ".", value)
+            visit("", mod)
+            print(module, sorted(meta[module]["tensors"]))
+        arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "common_tensor.npz"), **arrays)
+        return
     if "sustate" in sys.argv[1:]:
         # a simple-update checkpoint exactly as the reference writes it: pickle of the SimpleUpdateLattice after an update
         import pickle

@@ -66,3 +66,29 @@ def test_fermionic_operator_algebra():
     assert float((tj.SS - tj.SS.conjugate().edge_rename(swap)).norm_max()) <= 1e-15
     with pytest.raises(AttributeError):
         common_tensor.Nothing
+
+
+def test_every_real_common_tensor_equals_the_reference():
+    """tests/golden/common_tensor.npz (`make_golden.py common`): every real operator tensor of the reference's common_tensor modules
+    No, Fermi, FermiU1_Hubbard, FermiFermi_Hubbard, FermiU1_tJ (incl. Up.* / Down.*), as `.to(float)`: same names in the same order,
+    same edges, same values"""
+    import json
+    import os
+    from golden_loader import HERE, tensor_from
+    z = np.load(os.path.join(HERE, "common_tensor.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    checked = 0
+    for module, info in meta.items():
+        mine = getattr(common_tensor, module)
+        mod = getattr(TAT, info["symmetry"])
+        for path, desc in info["tensors"].items():
+            got = mine
+            for part in path.split("."):
+                got = getattr(got, part)
+            want = tensor_from(mod, desc, z)
+            assert got.names == want.names, (module, path)
+            assert got._edges == want._edges, (module, path)
+            a, b = np.asarray(got.storage), np.asarray(want.storage)
+            assert a.shape == b.shape and np.abs(a - b).max() <= 1e-15, (module, path)
+            checked += 1
+    assert checked == 66

@@ -1,5 +1,5 @@
-"""Operator tensors the shipped models are built from, in float64 (reference: tetragono/tetragono/common_tensor/: `No.py`,
-`FermiFermi_Hubbard.py`, `FermiU1_tJ.py` and `tensor_toolkit.py`; the reference defines them as complex128 and its models take
+"""Operator tensors the shipped models are built from, in float64 (reference: tetragono/tetragono/common_tensor/: `No.py`, `Fermi.py`,
+`FermiU1_Hubbard.py`, `FermiFermi_Hubbard.py`, `FermiU1_tJ.py` and `tensor_toolkit.py`; the reference defines them as complex128 and its models take
 `.to(float)`, tetraku/models/*/).  Same attribute names: `common_tensor.No.SS`, `common_tensor.FermiFermi_Hubbard.NN / CSCS / Up.CC ...`,
 `common_tensor.FermiU1_tJ.CC / SS / nn / EF`.  Operators that are not real (`pauli_y`, `Sy`) are absent -- only float64 tensors are
 device-backed; their real products (`SySy`, `pauli_y_pauli_y`) are there.  Built on first access (they need a backend), set-up work.
@@ -73,20 +73,40 @@ def _build_No():
                       SxSx=SxSx, SySy=SySy, SzSz=SzSz, SS=SxSx + SySy + SzSz)
 
 
+def _species(Tensor, EF, ET, charge):
+    """the operators of one fermion species on sites with physical edge EF (and its conjugate ET)"""
+    CP, CM = _ladder(Tensor, EF, ET, charge)
+    C0C1, C1C0 = _hop(CP, CM, 0, 1), _hop(CP, CM, 1, 0)
+    return dict(CP=CP, CM=CM, C0C1=C0C1, C1C0=C1C0, CC=C0C1 + C1C0, I=Tensor(["O0", "I0"], [EF, ET]).identity_({("I0", "O0")}),
+                N=rename_io(CP, [0]).contract(rename_io(CM, [0]), {("T", "T"), ("I0", "O0")}))
+
+
+def _two_species(Tensor, EF, ET, up, down):
+    Up, Down = _Namespace(**_species(Tensor, EF, ET, up)), _Namespace(**_species(Tensor, EF, ET, down))
+    return _Namespace(Tensor=Tensor, EF=EF, ET=ET, Up=Up, Down=Down, NN=Up.N.contract(Down.N, {("I0", "O0")}), CSCS=Up.CC + Down.CC)
+
+
+def _build_Fermi():
+    """spinless fermions, symmetry FermiU1 (Fermi.py:21-39)"""
+    Tensor = _TAT.FermiU1.D.Tensor
+    EF, ET = Tensor.Edge([0, 1], False), Tensor.Edge([0, -1], True)
+    return _Namespace(Tensor=Tensor, EF=EF, ET=ET, **_species(Tensor, EF, ET, (1,)))
+
+
+def _build_FermiU1_Hubbard():
+    """one site = empty, up, down, double; symmetry (particle number: FermiU1, 2 Sz: BoseU1) (FermiU1_Hubbard.py:21-50)"""
+    Tensor = _TAT.FermiU1BoseU1.D.Tensor
+    EF = Tensor.Edge([(0, 0), (1, 1), (1, -1), (2, 0)], False)
+    ET = Tensor.Edge([(0, 0), (-1, -1), (-1, 1), (-2, 0)], True)
+    return _two_species(Tensor, EF, ET, (1, 1), (1, -1))
+
+
 def _build_FermiFermi_Hubbard():
     """one site = (n_up, n_down) in {0,1}^2, symmetry FermiU1 x FermiU1 (FermiFermi_Hubbard.py:22-60)"""
     Tensor = _TAT.FermiU1FermiU1.D.Tensor
     EF = Tensor.Edge([(0, 0), (0, 1), (1, 0), (1, 1)], False)
     ET = Tensor.Edge([(0, 0), (0, -1), (-1, 0), (-1, -1)], True)
-
-    def species(charge):
-        CP, CM = _ladder(Tensor, EF, ET, charge)
-        C0C1, C1C0 = _hop(CP, CM, 0, 1), _hop(CP, CM, 1, 0)
-        return _Namespace(CP=CP, CM=CM, C0C1=C0C1, C1C0=C1C0, CC=C0C1 + C1C0, I=Tensor(["O0", "I0"], [EF, ET]).identity_({("I0", "O0")}),
-                          N=rename_io(CP, [0]).contract(rename_io(CM, [0]), {("T", "T"), ("I0", "O0")}))
-
-    Up, Down = species((1, 0)), species((0, 1))
-    return _Namespace(Tensor=Tensor, EF=EF, ET=ET, Up=Up, Down=Down, NN=Up.N.contract(Down.N, {("I0", "O0")}), CSCS=Up.CC + Down.CC)
+    return _two_species(Tensor, EF, ET, (1, 0), (0, 1))
 
 
 def _build_FermiU1_tJ():
@@ -110,7 +130,8 @@ def _build_FermiU1_tJ():
                       nn=rename_io(n, [0]).contract(rename_io(n, [1]), set()))
 
 
-_BUILDERS = {"No": _build_No, "FermiFermi_Hubbard": _build_FermiFermi_Hubbard, "FermiU1_tJ": _build_FermiU1_tJ}
+_BUILDERS = {"No": _build_No, "Fermi": _build_Fermi, "FermiU1_Hubbard": _build_FermiU1_Hubbard, "FermiFermi_Hubbard": _build_FermiFermi_Hubbard,
+             "FermiU1_tJ": _build_FermiU1_tJ}
 _BUILT = {}
 
 
