@@ -404,10 +404,25 @@ def main():
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hamiltonian_tools.npz"), **arrays)
         print(arrays["lattice_dot"], [c["result"]["names"] for c in meta["cases"]])
         return
+    if "hubbard" in sys.argv[1:]:
+        # structure of the Hubbard lattice the reference ships (tetraku/models/hubbard/__init__.py), FermiU1, 4x4, D = 1, T = 8
+        from tetraku.models.hubbard import abstract_lattice
+        TAT.random.seed(2333)
+        lattice = tet.SamplingLattice(abstract_lattice(4, 4, 1, 8, 1.0, 4.0))
+        arrays, sym_name = {}, "FermiU1"
+        meta = {"symmetry": sym_name, "L1": 4, "L2": 4, "total_symmetry": sym_tuple(sym_name, lattice.total_symmetry)}
+        meta["physics_edges"] = [[{str(o): edge_desc(sym_name, e) for o, e in lattice.physics_edges[l1, l2].items()} for l2 in range(4)] for l1 in range(4)]
+        meta["hamiltonians"] = [{"positions": [list(p) for p in positions], "tensor": tensor_desc(sym_name, h, arrays, f"ham_{i}")}
+                                for i, (positions, h) in enumerate(lattice._hamiltonians.items())]
+        meta["sites"] = [[tensor_desc(sym_name, lattice[l1, l2], arrays, f"site_{l1}_{l2}") for l2 in range(4)] for l1 in range(4)]
+        arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "model_hubbard_4x4_D1.npz"), **arrays)
+        print("hubbard", len(meta["hamiltonians"]), "terms")
+        return
     if "common" in sys.argv[1:]:
         # every real operator tensor of the reference's common_tensor modules, as its models take them (`.to(float)`)
         arrays, meta = {}, {}
-        syms = {"No": "No", "Fermi": "FermiU1", "FermiU1_Hubbard": "FermiU1BoseU1", "FermiFermi_Hubbard": "FermiU1FermiU1", "FermiU1_tJ": "FermiU1BoseU1"}
+        syms = {"No": "No", "Fermi": "FermiU1", "Fermi_Hubbard": "FermiU1", "FermiU1_Hubbard": "FermiU1BoseU1", "FermiFermi_Hubbard": "FermiU1FermiU1", "FermiU1_tJ": "FermiU1BoseU1"}
         for module, sym in syms.items():
             mod = getattr(tet.common_tensor, module)
             meta[module] = {"symmetry": sym, "tensors": {}}

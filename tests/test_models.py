@@ -26,12 +26,14 @@ def _same_model(mine, fixture):
         assert mine[l1, l2].names == fixture[l1, l2].names and mine[l1, l2]._edges == fixture[l1, l2]._edges
 
 
-@pytest.mark.parametrize("case", ["tJ_4x4_D1_Dc8", "hubbardFF_4x4_D1_Dc8"])
+@pytest.mark.parametrize("case", ["tJ_4x4_D1_Dc8", "hubbardFF_4x4_D1_Dc8", "model_hubbard_4x4_D1"])
 def test_fermionic_models_equal_the_reference_models(case):
     meta, z = load(case)
     fixture = build_lattice(meta, z)
     if case.startswith("tJ"):
         abstract = models.tJ_abstract_lattice(4, 4, 1, 2, 1.0, 0.4)
+    elif case.startswith("model_hubbard"):
+        abstract = models.hubbard_abstract_lattice(4, 4, 1, 8, 1.0, 4.0)       # the Hubbard lattice the reference ships (FermiU1)
     else:
         abstract = models.hubbard_fermi_fermi_abstract_lattice(4, 4, 1, 8, 1.0, 4.0)
     TAT.random.seed(2333)
@@ -70,7 +72,7 @@ def test_fermionic_operator_algebra():
 
 def test_every_real_common_tensor_equals_the_reference():
     """tests/golden/common_tensor.npz (`make_golden.py common`): every real operator tensor of the reference's common_tensor modules
-    No, Fermi, FermiU1_Hubbard, FermiFermi_Hubbard, FermiU1_tJ (incl. Up.* / Down.*), as `.to(float)`: same names in the same order,
+    No, Fermi, Fermi_Hubbard, FermiU1_Hubbard, FermiFermi_Hubbard, FermiU1_tJ (incl. Up.* / Down.*), as `.to(float)`: same names in the same order,
     same edges, same values"""
     import json
     import os
@@ -91,4 +93,4 @@ def test_every_real_common_tensor_equals_the_reference():
             a, b = np.asarray(got.storage), np.asarray(want.storage)
             assert a.shape == b.shape and np.abs(a - b).max() <= 1e-15, (module, path)
             checked += 1
-    assert checked == 66
+    assert checked == 79

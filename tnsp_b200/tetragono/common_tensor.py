@@ -1,4 +1,4 @@
-"""Operator tensors the shipped models are built from, in float64 (reference: tetragono/tetragono/common_tensor/: `No.py`, `Fermi.py`,
+"""Operator tensors the shipped models are built from, in float64 (reference: tetragono/tetragono/common_tensor/: `No.py`, `Fermi.py`, `Fermi_Hubbard.py`,
 `FermiU1_Hubbard.py`, `FermiFermi_Hubbard.py`, `FermiU1_tJ.py` and `tensor_toolkit.py`; the reference defines them as complex128 and its models take
 `.to(float)`, tetraku/models/*/).  Same attribute names: `common_tensor.No.SS`, `common_tensor.FermiFermi_Hubbard.NN / CSCS / Up.CC ...`,
 `common_tensor.FermiU1_tJ.CC / SS / nn / EF`.  Operators that are not real (`pauli_y`, `Sy`) are absent -- only float64 tensors are
@@ -93,6 +93,26 @@ def _build_Fermi():
     return _Namespace(Tensor=Tensor, EF=EF, ET=ET, **_species(Tensor, EF, ET, (1,)))
 
 
+def _build_Fermi_Hubbard():
+    """spinful site = (up mode, down mode) of spinless fermions merged into one physical edge, symmetry FermiU1 (total particle
+    number); the merge applies its fermionic sign on the input side only (Fermi_Hubbard.py:18-87)"""
+    f = _build_Fermi() if "Fermi" not in _BUILT else _BUILT["Fermi"]
+
+    def merged(t, sites):
+        # modes 0 .. sites-1 are the up modes of the sites, sites .. 2*sites-1 their down modes
+        groups = {f"{d}{i}": [f"{d}{i}", f"{d}{i + sites}"] for i in range(sites) for d in "IO"}
+        return t.merge_edge(groups, True, {f"O{i}" for i in range(sites)})
+
+    one = lambda t, i: rename_io(t, [i])  # noqa: E731
+    CSCS = merged(kronecker_product(rename_io(f.CC, [0, 1]), one(f.I, 2), one(f.I, 3))
+                  + kronecker_product(rename_io(f.CC, [2, 3]), one(f.I, 0), one(f.I, 1)), 2)
+    N0 = merged(kronecker_product(one(f.N, 0), one(f.I, 1)), 1)
+    N1 = merged(kronecker_product(one(f.I, 0), one(f.N, 1)), 1)
+    return _Namespace(Tensor=f.Tensor, CC=f.CC, I=f.I, N=f.N, C0C1=f.C0C1, C1C0=f.C1C0, CSCS=CSCS,
+                      NN=merged(kronecker_product(one(f.N, 0), one(f.N, 1)), 1), N0=N0, N1=N1, CUCD=merged(f.C0C1, 1), CDCU=merged(f.C1C0, 1),
+                      CUCU=N0, CDCD=N1)
+
+
 def _build_FermiU1_Hubbard():
     """one site = empty, up, down, double; symmetry (particle number: FermiU1, 2 Sz: BoseU1) (FermiU1_Hubbard.py:21-50)"""
     Tensor = _TAT.FermiU1BoseU1.D.Tensor
@@ -130,7 +150,7 @@ def _build_FermiU1_tJ():
                       nn=rename_io(n, [0]).contract(rename_io(n, [1]), set()))
 
 
-_BUILDERS = {"No": _build_No, "Fermi": _build_Fermi, "FermiU1_Hubbard": _build_FermiU1_Hubbard, "FermiFermi_Hubbard": _build_FermiFermi_Hubbard,
+_BUILDERS = {"No": _build_No, "Fermi": _build_Fermi, "Fermi_Hubbard": _build_Fermi_Hubbard, "FermiU1_Hubbard": _build_FermiU1_Hubbard, "FermiFermi_Hubbard": _build_FermiFermi_Hubbard,
              "FermiU1_tJ": _build_FermiU1_tJ}
 _BUILT = {}
 

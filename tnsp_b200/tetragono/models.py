@@ -195,3 +195,34 @@ def hubbard_fermi_fermi_abstract_lattice(L1, L2, D, T, t, U):
         for l2 in range(L2 - 1):
             state.virtual_bond[l1, l2, "R"] = charged(int(per_row * (L2 - l2 - 1) / L2))
     return state
+
+
+def hubbard_abstract_state(L1, L2, T, t, U):
+    """the Hubbard model the reference ships: symmetry FermiU1 (total particle number T), physical edge empty / singly occupied
+    (dimension 2) / doubly occupied (tetraku/tetraku/models/hubbard/__init__.py:22-44)"""
+    from . import common_tensor
+    op = common_tensor.Fermi_Hubbard
+    state = AbstractState(TAT.FermiU1.D.Tensor, L1, L2)
+    state.total_symmetry = T
+    state.physics_edges[...] = [(0, 1), (1, 2), (2, 1)]
+    state.hamiltonians["vertical_bond"] = -t * op.CSCS
+    state.hamiltonians["horizontal_bond"] = -t * op.CSCS
+    state.hamiltonians["single_site"] = U * op.NN
+    return state
+
+
+def hubbard_abstract_lattice(L1, L2, D, T, t, U):
+    """its lattice (hubbard/__init__.py:47-75): column-0 vertical bonds carry the particles still to be distributed below (+- 1),
+    row bonds the row's share, other vertical bonds are trivial; `D` per charge sector"""
+    state = AbstractLattice(hubbard_abstract_state(L1, L2, T, t, U))
+    per_row = T / L1
+    for l1 in range(L1 - 1):
+        Q = int(T * (L1 - l1 - 1) / L1)
+        state.virtual_bond[l1, 0, "D"] = [(Q - 1, D), (Q, D), (Q + 1, D)]
+        for l2 in range(1, L2):
+            state.virtual_bond[l1, l2, "D"] = [(0, D)]
+    for l1 in range(L1):
+        for l2 in range(L2 - 1):
+            Q = int(per_row * (L2 - l2 - 1) / L2)
+            state.virtual_bond[l1, l2, "R"] = [(Q - 1, D), (Q, D), (Q + 1, D)]
+    return state
