@@ -418,6 +418,31 @@ def main():
         arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", "model_hubbard_4x4_D1.npz"), **arrays)
         print("hubbard", len(meta["hamiltonians"]), "terms")
+        # ... and a 2x2 one with 2 particles measured exactly (ergodic enumeration): energy and gradient.  Its physical edge has
+        # a segment of dimension 2 (singly occupied: up / down), unlike the other fixtures
+        TAT.random.seed(2333)
+        lattice = tet.SamplingLattice(abstract_lattice(2, 2, 2, 2, 1.0, 4.0))
+        arrays = {}
+        meta = {"symmetry": sym_name, "L1": 2, "L2": 2, "total_symmetry": sym_tuple(sym_name, lattice.total_symmetry)}
+        meta["physics_edges"] = [[{str(o): edge_desc(sym_name, e) for o, e in lattice.physics_edges[l1, l2].items()} for l2 in range(2)] for l1 in range(2)]
+        meta["hamiltonians"] = [{"positions": [list(p) for p in positions], "tensor": tensor_desc(sym_name, h, arrays, f"ham_{i}")}
+                                for i, (positions, h) in enumerate(lattice._hamiltonians.items())]
+        meta["sites"] = [[tensor_desc(sym_name, lattice[l1, l2], arrays, f"site_{l1}_{l2}") for l2 in range(2)] for l1 in range(2)]
+        sampling = tet.sampling_lattice.ErgodicSampling(lattice, 16, None)
+        obs = tet.sampling_lattice.Observer(lattice, enable_energy=True, enable_gradient=True)
+        count = 0
+        with obs:
+            for _ in range(sampling.total_step):
+                p, c = sampling()
+                obs(p, c)
+                count += 1
+        grad = obs.gradient
+        meta["gradient"] = [[tensor_desc(sym_name, grad[l1][l2], arrays, f"grad_{l1}_{l2}") for l2 in range(2)] for l1 in range(2)]
+        arrays["energy"] = np.array(obs.total_energy)
+        arrays["count"] = np.array([count])
+        arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "model_hubbard_2x2_D2.npz"), **arrays)
+        print("2x2", arrays["energy"], count)
         return
     if "common" in sys.argv[1:]:
         # every real operator tensor of the reference's common_tensor modules, as its models take them (`.to(float)`)

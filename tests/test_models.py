@@ -94,3 +94,33 @@ def test_every_real_common_tensor_equals_the_reference():
             assert a.shape == b.shape and np.abs(a - b).max() <= 1e-15, (module, path)
             checked += 1
     assert checked == 79
+
+
+def test_shipped_hubbard_model_exact_energy_and_gradient():
+    """2x2 Hubbard lattice of the reference's shipped model (FermiU1; the physical edge has a segment of dimension 2), 2 particles,
+    measured exactly by ergodic enumeration: energy (value, deviation) and gradient against the unmodified reference
+    (tests/golden/model_hubbard_2x2_D2.npz, `make_golden.py hubbard`), <= 1e-10"""
+    from golden_loader import tensor_from
+    from tnsp_b200.tetragono.observer import Observer
+    from tnsp_b200.tetragono.sampling import ErgodicSampling
+    meta, z = load("model_hubbard_2x2_D2")
+    fixture = build_lattice(meta, z)
+    TAT.random.seed(2333)
+    mine = SamplingLattice(models.hubbard_abstract_lattice(2, 2, 2, 2, 1.0, 4.0))
+    _same_model(mine, fixture)
+    sampling = ErgodicSampling(fixture, 16, None)
+    assert sampling.total_step == int(z["count"][0])
+    obs = Observer(fixture, enable_energy=True, enable_gradient=True)
+    with obs:
+        for _ in range(sampling.total_step):
+            p, c = sampling()
+            obs(p, c)
+    want = z["energy"]
+    assert np.abs(np.array(obs.total_energy) - want).max() <= 1e-10 * np.abs(want).max()
+    grad = obs.gradient
+    for l1, l2 in fixture.sites():
+        w = tensor_from(TAT.FermiU1, meta["gradient"][l1][l2], z)
+        g = grad[l1][l2].transpose(w.names)
+        assert g._edges == w._edges
+        scale = max(1.0, np.abs(np.asarray(w.storage)).max())
+        assert np.abs(np.asarray(g.storage) - np.asarray(w.storage)).max() <= 1e-10 * scale
