@@ -1,4 +1,4 @@
-"""Operator tensors the shipped models are built from, in float64 (reference: tetragono/tetragono/common_tensor/: `No.py`, `Fermi.py`, `Fermi_Hubbard.py`,
+"""Operator tensors the shipped models are built from, in float64 (reference: tetragono/tetragono/common_tensor/: `No.py`, `Fermi.py`, `Parity.py`, `Fermi_Hubbard.py`,
 `FermiU1_Hubbard.py`, `FermiFermi_Hubbard.py`, `FermiU1_tJ.py` and `tensor_toolkit.py`; the reference defines them as complex128 and its models take
 `.to(float)`, tetraku/models/*/).  Same attribute names: `common_tensor.No.SS`, `common_tensor.FermiFermi_Hubbard.NN / CSCS / Up.CC ...`,
 `common_tensor.FermiU1_tJ.CC / SS / nn / EF`.  Operators that are not real (`pauli_y`, `Sy`) are absent -- only float64 tensors are
@@ -93,6 +93,23 @@ def _build_Fermi():
     return _Namespace(Tensor=Tensor, EF=EF, ET=ET, **_species(Tensor, EF, ET, (1,)))
 
 
+def _build_Parity():
+    """spinless fermions with only the parity conserved, symmetry FermiZ2 (Parity.py:21-44): also the pair creation /
+    annihilation terms CP2 = c^dagger_0 c^dagger_1 and CM2 = c_1 c_0"""
+    Tensor = _TAT.FermiZ2.D.Tensor
+    EF, ET = Tensor.Edge([False, True], False), Tensor.Edge([False, True], True)
+    CP = Tensor(["O0", "I0", "T"], [EF, ET, Tensor.Edge([True], False)]).zero_()
+    CP[{"O0": (True, 0), "I0": (False, 0), "T": (True, 0)}] = 1
+    CM = Tensor(["O0", "I0", "T"], [EF, ET, Tensor.Edge([True], True)]).zero_()
+    CM[{"O0": (False, 0), "I0": (True, 0), "T": (True, 0)}] = 1
+    C0C1, C1C0 = _hop(CP, CM, 0, 1), _hop(CP, CM, 1, 0)
+    return _Namespace(Tensor=Tensor, EF=EF, ET=ET, CP=CP, CM=CM, C0C1=C0C1, C1C0=C1C0, CC=C0C1 + C1C0,
+                      I=Tensor(["O0", "I0"], [EF, ET]).identity_({("I0", "O0")}),
+                      N=rename_io(CP, [0]).contract(rename_io(CM, [0]), {("T", "T"), ("I0", "O0")}),
+                      CP2=rename_io(CP, [0]).contract(rename_io(CP.reverse_edge({"T"}), [1]), {("T", "T")}),
+                      CM2=rename_io(CM, [1]).contract(rename_io(CM.reverse_edge({"T"}), [0]), {("T", "T")}))
+
+
 def _build_Fermi_Hubbard():
     """spinful site = (up mode, down mode) of spinless fermions merged into one physical edge, symmetry FermiU1 (total particle
     number); the merge applies its fermionic sign on the input side only (Fermi_Hubbard.py:18-87)"""
@@ -150,7 +167,7 @@ def _build_FermiU1_tJ():
                       nn=rename_io(n, [0]).contract(rename_io(n, [1]), set()))
 
 
-_BUILDERS = {"No": _build_No, "Fermi": _build_Fermi, "Fermi_Hubbard": _build_Fermi_Hubbard, "FermiU1_Hubbard": _build_FermiU1_Hubbard, "FermiFermi_Hubbard": _build_FermiFermi_Hubbard,
+_BUILDERS = {"No": _build_No, "Fermi": _build_Fermi, "Parity": _build_Parity, "Fermi_Hubbard": _build_Fermi_Hubbard, "FermiU1_Hubbard": _build_FermiU1_Hubbard, "FermiFermi_Hubbard": _build_FermiFermi_Hubbard,
              "FermiU1_tJ": _build_FermiU1_tJ}
 _BUILT = {}
 
