@@ -247,7 +247,27 @@ def hubbard_ff(L1, L2, D, T):
     return tet.SamplingLattice(state)
 
 
+def dump_structure(name, sym_name, lattice):
+    """model only: symmetry, edges, Hamiltonian terms and site tensors (what golden_loader.build_lattice needs)"""
+    arrays = {}
+    L1, L2 = lattice.L1, lattice.L2
+    meta = {"symmetry": sym_name, "L1": L1, "L2": L2, "total_symmetry": sym_tuple(sym_name, lattice.total_symmetry)}
+    meta["physics_edges"] = [[{str(o): edge_desc(sym_name, e) for o, e in lattice.physics_edges[l1, l2].items()} for l2 in range(L2)] for l1 in range(L1)]
+    meta["hamiltonians"] = [{"positions": [list(p) for p in positions], "tensor": tensor_desc(sym_name, h, arrays, f"ham_{i}")}
+                            for i, (positions, h) in enumerate(lattice._hamiltonians.items())]
+    meta["sites"] = [[tensor_desc(sym_name, lattice[l1, l2], arrays, f"site_{l1}_{l2}") for l2 in range(L2)] for l1 in range(L1)]
+    arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **arrays)
+    print(name, len(meta["hamiltonians"]), "terms")
+
+
 def main():
+    if "j1j2model" in sys.argv[1:]:
+        # the J1-J2 model the reference ships (tetraku/models/J1J2/__init__.py, NoSymmetry)
+        from tetraku.models.J1J2 import abstract_lattice
+        TAT.random.seed(2333)
+        dump_structure("model_j1j2_3x4_D2", "No", tet.SamplingLattice(abstract_lattice(3, 4, 2, 1.0, 0.5)))
+        return
     if "direct" in sys.argv[1:]:
         # direct sampling (sampling.py:252-371): configurations and their probabilities from a fixed seed
         out = {}

@@ -40,6 +40,19 @@ def test_fermionic_models_equal_the_reference_models(case):
     _same_model(SamplingLattice(abstract), fixture)
 
 
+def test_shipped_j1j2_model_equals_the_reference():
+    """tests/golden/model_j1j2_3x4_D2.npz (`make_golden.py j1j2model`): same Hamiltonian keys IN THE SAME ORDER, tensors, site structure"""
+    meta, z = load("model_j1j2_3x4_D2")
+    fixture = build_lattice(meta, z)
+    TAT.random.seed(2333)
+    mine = SamplingLattice(models.j1j2_reference_abstract_lattice(3, 4, 2, 1.0, 0.5))
+    _same_model(mine, fixture)
+    assert list(mine._hamiltonians) == [tuple(tuple(p) for p in h["positions"]) for h in meta["hamiltonians"]]
+    # randn_ from the same seed fills the same values: the whole state is the reference's
+    for l1, l2 in fixture.sites():
+        assert np.array_equal(np.asarray(mine[l1, l2].storage), np.asarray(fixture[l1, l2].storage))
+
+
 def test_spin_half_operators():
     op = common_tensor.No
     meta, z = load("heis_3x3_D2_Dc4")

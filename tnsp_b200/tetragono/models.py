@@ -226,3 +226,30 @@ def hubbard_abstract_lattice(L1, L2, D, T, t, U):
             Q = int(per_row * (L2 - l2 - 1) / L2)
             state.virtual_bond[l1, l2, "R"] = [(Q - 1, D), (Q, D), (Q + 1, D)]
     return state
+
+
+def j1j2_reference_abstract_state(L1, L2, J1, J2):
+    """the J1-J2 model exactly as the reference ships it (tetraku/tetraku/models/J1J2/__init__.py:22-50): NoSymmetry, and the
+    anti-diagonal terms keyed (lower-left site, upper-right site) -- `j1j2_abstract_lattice` above keys them the other way round,
+    which is the same operator (SS is symmetric) but another dictionary key and iteration order"""
+    from . import common_tensor
+    state = AbstractState(TAT.No.D.Tensor, L1, L2)
+    state.physics_edges[...] = 2
+    J1SS, J2SS = -J1 * common_tensor.No.SS, -J2 * common_tensor.No.SS
+    for l1, l2 in state.sites():
+        if l1 != L1 - 1:
+            state.hamiltonians[(l1, l2, 0), (l1 + 1, l2, 0)] = J1SS
+        if l2 != L2 - 1:
+            state.hamiltonians[(l1, l2, 0), (l1, l2 + 1, 0)] = J1SS
+            if l1 != L1 - 1:
+                state.hamiltonians[(l1, l2, 0), (l1 + 1, l2 + 1, 0)] = J2SS
+            if l1 != 0:
+                state.hamiltonians[(l1, l2, 0), (l1 - 1, l2 + 1, 0)] = J2SS
+    return state
+
+
+def j1j2_reference_abstract_lattice(L1, L2, D, J1, J2):
+    state = AbstractLattice(j1j2_reference_abstract_state(L1, L2, J1, J2))
+    state.virtual_bond["R"] = D
+    state.virtual_bond["D"] = D
+    return state
