@@ -467,7 +467,7 @@ def main():
     if "common" in sys.argv[1:]:
         # every real operator tensor of the reference's common_tensor modules, as its models take them (`.to(float)`)
         arrays, meta = {}, {}
-        syms = {"No": "No", "Fermi": "FermiU1", "Parity": "FermiZ2", "Fermi_Hubbard": "FermiU1", "FermiU1_Hubbard": "FermiU1BoseU1", "FermiFermi_Hubbard": "FermiU1FermiU1", "FermiU1_tJ": "FermiU1BoseU1"}
+        syms = {"No": "No", "Fermi": "FermiU1", "Parity": "FermiZ2", "Fermi_Hubbard": "FermiU1", "Parity_Hubbard": "FermiZ2", "FermiU1_Hubbard": "FermiU1BoseU1", "FermiFermi_Hubbard": "FermiU1FermiU1", "FermiU1_tJ": "FermiU1BoseU1"}
         for module, sym in syms.items():
             mod = getattr(tet.common_tensor, module)
             meta[module] = {"symmetry": sym, "tensors": {}}

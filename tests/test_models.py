@@ -85,7 +85,7 @@ def test_fermionic_operator_algebra():
 
 def test_every_real_common_tensor_equals_the_reference():
     """tests/golden/common_tensor.npz (`make_golden.py common`): every real operator tensor of the reference's common_tensor modules
-    No, Fermi, Parity, Fermi_Hubbard, FermiU1_Hubbard, FermiFermi_Hubbard, FermiU1_tJ (incl. Up.* / Down.*), as `.to(float)`: same names in the same order,
+    No, Fermi, Parity, Fermi_Hubbard, Parity_Hubbard, FermiU1_Hubbard, FermiFermi_Hubbard, FermiU1_tJ (incl. Up.* / Down.*), as `.to(float)`: same names in the same order,
     same edges, same values"""
     import json
     import os
@@ -106,7 +106,7 @@ def test_every_real_common_tensor_equals_the_reference():
             a, b = np.asarray(got.storage), np.asarray(want.storage)
             assert a.shape == b.shape and np.abs(a - b).max() <= 1e-15, (module, path)
             checked += 1
-    assert checked == 88
+    assert checked == 105
 
 
 def test_shipped_hubbard_model_exact_energy_and_gradient():

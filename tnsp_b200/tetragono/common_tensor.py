@@ -1,4 +1,4 @@
-"""Operator tensors the shipped models are built from, in float64 (reference: tetragono/tetragono/common_tensor/: `No.py`, `Fermi.py`, `Parity.py`, `Fermi_Hubbard.py`,
+"""Operator tensors the shipped models are built from, in float64 (reference: tetragono/tetragono/common_tensor/: `No.py`, `Fermi.py`, `Parity.py`, `Fermi_Hubbard.py`, `Parity_Hubbard.py`,
 `FermiU1_Hubbard.py`, `FermiFermi_Hubbard.py`, `FermiU1_tJ.py` and `tensor_toolkit.py`; the reference defines them as complex128 and its models take
 `.to(float)`, tetraku/models/*/).  Same attribute names: `common_tensor.No.SS`, `common_tensor.FermiFermi_Hubbard.NN / CSCS / Up.CC ...`,
 `common_tensor.FermiU1_tJ.CC / SS / nn / EF`.  Operators that are not real (`pauli_y`, `Sy`) are absent -- only float64 tensors are
@@ -110,24 +110,43 @@ def _build_Parity():
                       CM2=rename_io(CM, [1]).contract(rename_io(CM.reverse_edge({"T"}), [0]), {("T", "T")}))
 
 
-def _build_Fermi_Hubbard():
-    """spinful site = (up mode, down mode) of spinless fermions merged into one physical edge, symmetry FermiU1 (total particle
-    number); the merge applies its fermionic sign on the input side only (Fermi_Hubbard.py:18-87)"""
-    f = _build_Fermi() if "Fermi" not in _BUILT else _BUILT["Fermi"]
+def _merge_spin(t, sites):
+    """modes 0 .. sites-1 are the up modes of the sites, sites .. 2*sites-1 their down modes: merge (up, down) of every site into
+    one physical edge; the merge sign goes to the input side only (the reference's `put_sign_in_H`)"""
+    groups = {f"{d}{i}": [f"{d}{i}", f"{d}{i + sites}"] for i in range(sites) for d in "IO"}
+    return t.merge_edge(groups, True, {f"O{i}" for i in range(sites)})
 
-    def merged(t, sites):
-        # modes 0 .. sites-1 are the up modes of the sites, sites .. 2*sites-1 their down modes
-        groups = {f"{d}{i}": [f"{d}{i}", f"{d}{i + sites}"] for i in range(sites) for d in "IO"}
-        return t.merge_edge(groups, True, {f"O{i}" for i in range(sites)})
 
+def _with_spectators(t, acting_on, modes=4):
+    """`t` on the modes `acting_on`, the identity on the other ones"""
+    f_identity = _with_spectators.identity
+    return kronecker_product(rename_io(t, acting_on), *(rename_io(f_identity, [m]) for m in range(modes) if m not in acting_on))
+
+
+def _spinful(f):
+    """the operators of a spinful site built from two spinless modes `f` (Fermi_Hubbard.py:18-87, Parity_Hubbard.py:18-133)"""
+    _with_spectators.identity = f.I
     one = lambda t, i: rename_io(t, [i])  # noqa: E731
-    CSCS = merged(kronecker_product(rename_io(f.CC, [0, 1]), one(f.I, 2), one(f.I, 3))
-                  + kronecker_product(rename_io(f.CC, [2, 3]), one(f.I, 0), one(f.I, 1)), 2)
-    N0 = merged(kronecker_product(one(f.N, 0), one(f.I, 1)), 1)
-    N1 = merged(kronecker_product(one(f.I, 0), one(f.N, 1)), 1)
-    return _Namespace(Tensor=f.Tensor, CC=f.CC, I=f.I, N=f.N, C0C1=f.C0C1, C1C0=f.C1C0, CSCS=CSCS,
-                      NN=merged(kronecker_product(one(f.N, 0), one(f.N, 1)), 1), N0=N0, N1=N1, CUCD=merged(f.C0C1, 1), CDCU=merged(f.C1C0, 1),
-                      CUCU=N0, CDCD=N1)
+    N0 = _merge_spin(kronecker_product(one(f.N, 0), one(f.I, 1)), 1)
+    N1 = _merge_spin(kronecker_product(one(f.I, 0), one(f.N, 1)), 1)
+    return dict(Tensor=f.Tensor, CC=f.CC, I=f.I, N=f.N, C0C1=f.C0C1, C1C0=f.C1C0,
+                CSCS=_merge_spin(_with_spectators(f.CC, [0, 1]) + _with_spectators(f.CC, [2, 3]), 2),
+                NN=_merge_spin(kronecker_product(one(f.N, 0), one(f.N, 1)), 1), N0=N0, N1=N1,
+                CUCD=_merge_spin(f.C0C1, 1), CDCU=_merge_spin(f.C1C0, 1), CUCU=N0, CDCD=N1)
+
+
+def _build_Fermi_Hubbard():
+    """spinful site = (up mode, down mode) of spinless fermions, symmetry FermiU1 (total particle number)"""
+    return _Namespace(**_spinful(__getattr__("Fermi")))
+
+
+def _build_Parity_Hubbard():
+    """the same with only the parity conserved (FermiZ2), plus the singlet / triplet pair creation + annihilation terms between
+    two sites (Parity_Hubbard.py:38-70)"""
+    f = __getattr__("Parity")
+    items = _spinful(f)
+    a, b = _with_spectators(f.CP2, [0, 3]) + _with_spectators(f.CM2, [3, 0]), _with_spectators(f.CP2, [1, 2]) + _with_spectators(f.CM2, [2, 1])
+    return _Namespace(CP2=f.CP2, CM2=f.CM2, singlet=_merge_spin(a + b, 2), triplet=_merge_spin(a - b, 2), **items)
 
 
 def _build_FermiU1_Hubbard():
@@ -167,7 +186,7 @@ def _build_FermiU1_tJ():
                       nn=rename_io(n, [0]).contract(rename_io(n, [1]), set()))
 
 
-_BUILDERS = {"No": _build_No, "Fermi": _build_Fermi, "Parity": _build_Parity, "Fermi_Hubbard": _build_Fermi_Hubbard, "FermiU1_Hubbard": _build_FermiU1_Hubbard, "FermiFermi_Hubbard": _build_FermiFermi_Hubbard,
+_BUILDERS = {"No": _build_No, "Fermi": _build_Fermi, "Parity": _build_Parity, "Fermi_Hubbard": _build_Fermi_Hubbard, "Parity_Hubbard": _build_Parity_Hubbard, "FermiU1_Hubbard": _build_FermiU1_Hubbard, "FermiFermi_Hubbard": _build_FermiFermi_Hubbard,
              "FermiU1_tJ": _build_FermiU1_tJ}
 _BUILT = {}
 
