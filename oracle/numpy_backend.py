@@ -20,10 +20,12 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .numpy_ragged import RaggedMixin
+
 R = 8
 
 
-class NumpyBackend:
+class NumpyBackend(RaggedMixin):
     name = "numpy-checker"
 
     def __init__(self):
