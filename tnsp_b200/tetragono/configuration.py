@@ -26,12 +26,39 @@ def is_no_symmetry(Tensor):
     return Tensor.model.__name__.rsplit(".", 1)[-1] in ("No", "Normal")
 
 
+# Lock-step batches of a symmetric model: "sector" = sector-compact tensors with per-chain symmetry sectors (TAT/ragged.py: the
+# reference's sector plan, chain by chain); "dense" = the charge-dense embedding of round 1 (dense_embedding.py, bosonic only).
+LOCKSTEP_ENGINE = "sector"
+
+
+def sector_engine_supported(Tensor):
+    kinds = Tensor.Symmetry.kinds
+    return len(kinds) != 0 and all(k == "U1" for k in kinds)
+
+
+class _RaggedFactory:
+    """what SingleLayerAuxiliaries needs of a tensor class (`Tensor(1)`) when the environments are sector-compact tensors"""
+
+    def __init__(self, Tensor):
+        self.Symmetry, self.model = Tensor.Symmetry, Tensor.model
+
+    def __call__(self, number):
+        from ..TAT.ragged import RTensor
+        return RTensor.scalar_one(number)
+
+
 class Configuration(SingleLayerAuxiliaries):
-    def __init__(self, owner, cut_dimension, nb=1):
-        super().__init__(owner.L1, owner.L2, cut_dimension, False, owner.Tensor)
+    def __init__(self, owner, cut_dimension, nb=1, engine=None):
+        native = is_native(owner.Tensor)
+        if engine is None:
+            engine = "sector" if (native and nb > 1 and owner.Tensor.Symmetry.length != 0 and LOCKSTEP_ENGINE == "sector") else "plain"
+        if engine == "sector" and not (native and sector_engine_supported(owner.Tensor)):
+            raise NotImplementedError("lock-step chains of this symmetry type: only integer (U1-type) symmetries have per-chain sectors")
+        self._ragged = engine == "sector"
+        super().__init__(owner.L1, owner.L2, cut_dimension, False, _RaggedFactory(owner.Tensor) if self._ragged else owner.Tensor)
         self.owner = owner
         self.nb = nb
-        self._native = is_native(owner.Tensor)
+        self._native = native
         if not self._native and nb != 1:
             raise NotImplementedError("lock-step batches need the device-backed TAT tensors")
         # per site: {orbit: (Symmetry, int array [nb]) | None}
@@ -49,12 +76,13 @@ class Configuration(SingleLayerAuxiliaries):
         result.owner = self.owner
         result.nb = self.nb
         result._native = self._native
+        result._ragged = self._ragged
         result._configuration = [[dict(self._configuration[l1][l2]) for l2 in range(self.owner.L2)] for l1 in range(self.owner.L1)]
         result._holes = self._holes
         return result
 
     # -- edge points -----------------------------------------------------------------------------
-    def _construct_edge_point(self, value):
+    def _construct_edge_point(self, value, edge=None):
         if isinstance(value, tuple):
             symmetry, index = value
         else:
@@ -64,6 +92,11 @@ class Configuration(SingleLayerAuxiliaries):
             index = np.repeat(index, self.nb)
         if index.size != self.nb:
             raise ValueError("edge point index must be a scalar or one index per chain")
+        if self._ragged:
+            # per-chain sectors: a point is (None, total index per chain)
+            if symmetry is not None:
+                index = (edge.index_by_point((self.owner._construct_symmetry(symmetry), 0)) + index).astype(np.int32)
+            return (None, index)
         return (self.owner._construct_symmetry(symmetry), index)
 
     @staticmethod
@@ -87,7 +120,7 @@ class Configuration(SingleLayerAuxiliaries):
             SingleLayerAuxiliaries.__setitem__(self, (l1, l2), None)
             self._holes = None
             return
-        point = self._construct_edge_point(value)
+        point = self._construct_edge_point(value, self.owner.physics_edges[l1, l2, orbit])
         changed = not self._same_point(point, self._configuration[l1][l2][orbit])
         if changed:
             self._configuration[l1][l2][orbit] = point
@@ -127,18 +160,21 @@ class Configuration(SingleLayerAuxiliaries):
 
     @staticmethod
     def _point_by_index(edge, idx):
-        """total index -> (symmetry, offset); all chains must land in one segment"""
+        """total index -> (symmetry, offset) when all chains land in one segment, else (None, total index per chain): the
+        form only the sector-compact engine accepts"""
         idx = np.asarray(idx, dtype=np.int64).reshape(-1)
         p0, _ = edge.coord_by_index(int(idx[0]))
         start = sum(d for _, d in edge.segments[:p0])
         off = idx - start
         if (off < 0).any() or (off >= edge.segments[p0][1]).any():
-            raise NotImplementedError("chains of one lock-step batch must share the symmetry sector of every physical index")
+            return (None, idx.astype(np.int32))
         return (edge.segments[p0][0], off.astype(np.int32))
 
     @staticmethod
     def _index_by_point(edge, point):
         sym, off = point
+        if sym is None:
+            return np.asarray(off, dtype=np.int64)
         return edge.index_by_point((sym, 0)) + np.asarray(off, dtype=np.int64)
 
     # -- shrinking -------------------------------------------------------------------------------
@@ -148,6 +184,9 @@ class Configuration(SingleLayerAuxiliaries):
         for orbit in self.owner.physics_edges[l1, l2]:
             edge = self.owner.physics_edges[l1, l2, orbit]
             symmetry, index = configuration[orbit]
+            if self._ragged:
+                yield orbit, self._ragged_shrinker(edge, index)
+                continue
             cedge = edge.conjugate()
             t = self.Tensor(["P", "Q"], [[(symmetry, 1)], cedge])
             if not self._native:
@@ -161,8 +200,38 @@ class Configuration(SingleLayerAuxiliaries):
             onehot[np.arange(len(index)), int(t._table.offsets[b]) + index] = 1.0
             yield orbit, type(t).from_batch(t.names, t._edges, onehot)
 
+    def _ragged_shrinker(self, edge, index):
+        """sector-compact (P, Q): P a unit edge carrying the sampled charge of every chain, Q the conjugated physical edge,
+        one-hot at the sampled index"""
+        from ..TAT import ragged
+        B = _bk.get()
+        labels = np.concatenate([np.full(d, ragged.pack_symmetry(s), dtype=np.int32) for s, d in edge.segments])
+        d = edge.dimension
+        chosen = labels[index].astype(np.int32)
+        onehot = np.zeros((len(index), d))
+        onehot[np.arange(len(index)), index] = 1.0
+        edges = [ragged.Edge(1, None, 1, False, chosen), ragged.Edge(d, B.from_numpy(labels.reshape(1, -1)), -1, not edge.arrow)]
+        t = ragged.RTensor.from_dense(["P", "Q"], edges, onehot, (-chosen).astype(np.int32))
+        t.core.fermi = ragged.fermi_mask(self.owner.Symmetry) if self.owner.Symmetry.is_fermi_symmetry else 0
+        return t
+
+    def _ragged_site(self, l1, l2):
+        """sector-compact copy of the owner's site tensor (rebuilt when the owner's tensor object changes)"""
+        from ..TAT import ragged
+        cache = self.owner.__dict__.setdefault("_ragged_sites", {})
+        tensor = self.owner[l1, l2]
+        got = cache.get((l1, l2))
+        if got is None or got[0] is not tensor:
+            got = cache[(l1, l2)] = (tensor, ragged.RTensor.from_symmetric(tensor, unit_names=("T",)))
+        return got[1]
+
     def _shrink_configuration(self, l1l2, configuration):
         l1, l2 = l1l2
+        if self._ragged:
+            tensor = self._ragged_site(l1, l2)
+            for orbit, shrinker in self._get_shrinker(l1l2, configuration):
+                tensor = tensor.contract(shrinker.edge_rename({"P": f"P_{l1}_{l2}_{orbit}"}), {(f"P{orbit}", "Q")})
+            return tensor
         tensor = self.owner[l1l2]
         orbits = list(self.owner.physics_edges[l1, l2])
         # fast path: no symmetry, single orbit stored first -> a row gather of the site tensor
@@ -194,7 +263,7 @@ class Configuration(SingleLayerAuxiliaries):
         """<s'|psi> with several physical indices replaced (lattice.py:231-267)."""
         grouped = {}
         for (l1, l2, orbit), point in replacement.items():
-            grouped.setdefault((l1, l2), {})[orbit] = self._construct_edge_point(point)
+            grouped.setdefault((l1, l2), {})[orbit] = self._construct_edge_point(point, self.owner.physics_edges[l1, l2, orbit])
         base = {}
         for l1l2, site in grouped.items():
             l1, l2 = l1l2
@@ -251,7 +320,7 @@ class ConfigurationPool:
         config = np.array(configuration.export_configuration())
         if replacement:
             for (l1, l2, orbit), point in replacement.items():
-                point = configuration._construct_edge_point(point)
+                point = configuration._construct_edge_point(point, self.owner.physics_edges[l1, l2, orbit])
                 config[..., l1, l2, orbit] = Configuration._index_by_point(self.owner.physics_edges[l1, l2, orbit], point)
         return config.tobytes()
 

@@ -24,6 +24,45 @@ def _values(t):
     return np.atleast_1d(np.asarray(t.storage, dtype=np.float64).reshape(-1))
 
 
+_BLOCK_PLANS = {}
+
+
+def _blocks_of(hole, target):
+    """storage [nb, size] of a sector-compact tensor in the block layout of the symmetric tensor `target` (same names, same edges;
+    core.hpp:162-190): expand to the dense index space, then one pack over the blocks"""
+    from ..TAT.plan import PackPlan
+    B = _bk.get()
+    dense = hole.to_dense()
+    key = (type(target), target._edges)
+    plan = _BLOCK_PLANS.get(key)
+    if plan is None:
+        table = target._table
+        dims = [e.dimension for e in target._edges]
+        strides, acc = [], 1
+        for d in reversed(dims):
+            strides.append(acc)
+            acc *= d
+        strides.reverse()
+        starts = target._segment_starts()
+        rows = []
+        for b, pos in enumerate(table.positions):
+            bd = [int(d) for d in table.dims[b]]
+            if 0 in bd:
+                continue
+            src_off = sum(int(starts[i][int(p)]) * strides[i] for i, p in enumerate(pos))
+            dstr, a = [], 1
+            for d in reversed(bd):
+                dstr.append(a)
+                a *= d
+            dstr.reverse()
+            keep = [i for i, d in enumerate(bd) if d != 1]
+            rows.append((src_off, int(table.offsets[b]), 0, [bd[i] for i in keep], [strides[i] for i in keep], [dstr[i] for i in keep]))
+        plan = _BLOCK_PLANS[key] = PackPlan(tuple(target.names), target._edges, table, rows, acc)
+    out = B.empty(dense.shape[0], target._table.size) if plan.covers_all else B.zeros(dense.shape[0], target._table.size)
+    B.pack(plan, dense, out)
+    return out
+
+
 class Observer:
     def __init__(self, owner, *, observer_set=None, enable_energy=False, enable_gradient=False, enable_natural_gradient=False,
                  cache_natural_delta=None, cache_configuration=False, restrict_subspace=None, classical_energy=None):
@@ -162,7 +201,11 @@ class Observer:
         self._total_weight_square += float((reweight**2).sum())
         self._total_log_ws += float(np.log(np.abs(ws_val[alive])).sum())
 
-        no_symmetry = is_no_symmetry(owner.Tensor)
+        ragged = getattr(configuration, "_ragged", False)
+        if ragged and owner.Tensor.Symmetry.is_fermi_symmetry:
+            return self._call_ragged_fermi(possibility, configuration, ws, ws_val, alive, reweight)
+        # amplitudes of bosonic models are plain numbers: the tensor form below only matters for the fermionic P-edge signs
+        no_symmetry = is_no_symmetry(owner.Tensor) or ragged
         native = is_native(owner.Tensor)
         if not no_symmetry:
             inv_ws_conj = ws / (ws.norm_2()**2)
@@ -219,7 +262,7 @@ class Observer:
                 per_term.append((positions, total, pending))
             if any(pend for _, _, pend in per_term):
                 import torch
-                flat = [w.data.reshape(-1).expand(nb) for _, _, pend in per_term for _, _, w in pend]
+                flat = [(w.scalar().t.reshape(-1) if ragged else w.data.reshape(-1)).expand(nb) for _, _, pend in per_term for _, _, w in pend]
                 host = torch.stack(flat).cpu().numpy()      # [replaced configurations, nb]: the only read-back
                 row = 0
                 for _, total, pend in per_term:
@@ -264,7 +307,7 @@ class Observer:
                 target = self._Delta[l1][l2]
                 if hole.names != target.names:
                     hole = hole.transpose(target.names)
-                data = hole.data
+                data = _blocks_of(hole, target) if ragged else hole.data
                 if data.shape[0] != nb:
                     data = data.expand(nb, data.shape[1]).contiguous()
                 B.grad_accumulate(data, w_dev, e_dev, target.data, self._EDelta[l1][l2].data)

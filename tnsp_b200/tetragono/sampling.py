@@ -172,9 +172,10 @@ class SweepSampling(Sampling):
                 for i in range(table.body):
                     self.configuration[positions[i]] = replacement[positions[i]]
             else:
-                B = _bk.get()
-                mask = B.from_numpy(accept.astype(np.uint8))
-                ws = type(ws).from_batch(ws.names, ws._edges, B.select(mask, wss.data, ws.data))
+                if not getattr(self.configuration, "_ragged", False):   # (the amplitude tensor itself is only carried along)
+                    B = _bk.get()
+                    mask = B.from_numpy(accept.astype(np.uint8))
+                    ws = type(ws).from_batch(ws.names, ws._edges, B.select(mask, wss.data, ws.data))
                 ws_val = np.where(accept, wss_val, ws_val)
                 cur_idx = table.unflatten(cur)
                 for i in range(table.body):
