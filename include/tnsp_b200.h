@@ -162,6 +162,73 @@ int tnsp_gather_rows_f64(const double* src, int64_t row_size, const int32_t* ind
 int tnsp_select_f64(const uint8_t* mask, const double* a, int64_t a_bstride, const double* b_, int64_t b_bstride,
                     double* dst, int64_t dst_bstride, int64_t size, int nb, void* stream);
 
+/* ==== sector-compact lock-step tensors (tnsp_b200/TAT/ragged.py) ============================================================
+ * A lock-step batch of Markov chains holds block-symmetric tensors whose sectors differ from chain to chain.  Every index of an
+ * edge carries an int32 charge label per chain (|label| >= 2^29: the index is dead); a tensor is stored, per chain, as the
+ * sector matrices of one grouping rows | cols of its edges, back to back (even offsets), row-major.  The integer planning the
+ * reference does on the host per tensor (edge_operator.hpp:34-692, contract.hpp:306-620, qr.hpp:309-508, svd.hpp:259-538)
+ * runs on the device from the labels; nothing below needs a device -> host copy.
+ *   group table  int32 [nbT][TNSP_RT_HDR + 2 M]: nsec (-1: more than TNSP_RT_SMAX sectors), nvalid, skey[SMAX] ascending,
+ *                sstart[SMAX + 1], perm[M] (merged indices sorted by (charge, index); dead ones last), inv[M]
+ *   match table  int32 [nb][TNSP_RT_MSTRIDE]: stored elements, overflow flag, moff[SMAX + 1] (offset of row sector i),
+ *                mcol[SMAX] (column sector paired with row sector i or -1)
+ * A stride of 0 broadcasts one table / one tensor to all chains. */
+#define TNSP_RT_SMAX 64
+#define TNSP_RT_HDR (3 + 2 * TNSP_RT_SMAX)
+#define TNSP_RT_MSTRIDE (4 + 2 * TNSP_RT_SMAX)
+typedef struct {
+    const double* data; int64_t data_stride;      /* sector matrices (or a dense array when rt == NULL) */
+    const int32_t* rt; int64_t rt_stride; int64_t M;   /* group table of the rows, its chain stride, merged dimension */
+    const int32_t* ct; int64_t ct_stride; int64_t N;
+    const int32_t* match; int64_t match_stride;
+} tnsp_rt_form;
+
+/* merged edge of a group of <= 8 edges (edge_operator.hpp:321-404, per chain): key(r) = sum_e signs[e] * labels[e][chain][r_e] */
+int tnsp_rt_sort_i32(int n_edges, const int32_t* const* labels, const int64_t* lstrides, const int32_t* dims, const int32_t* signs,
+                     int64_t M, int32_t* table, int nbT, void* stream);
+/* sector pairing rs * rowkey + cs * colkey = s1 * t1[chain] + s2 * t2[chain] (core.hpp:162-190; NULL targets count as 0);
+ * tsum (may be NULL) receives the right-hand side */
+int tnsp_rt_match_i32(const int32_t* rt, int64_t rt_stride, int rs, const int32_t* ct, int64_t ct_stride, int cs, const int32_t* t1,
+                      int t1_stride, int s1, const int32_t* t2, int t2_stride, int s2, int32_t* match, int32_t* tsum, int nbm, void* stream);
+/* regroup (edge_operator.hpp:651-688): plan = int32 [2 + 3 (nr + nc)]: nr, nc, then per destination edge (rows, then cols,
+ * slowest first) dimension, 1 if the edge sits in the source's column group, stride inside that source group.  src->rt == NULL:
+ * dense source; dst->rt == NULL: dense destination of `work` elements; else `work` bounds the stored elements (grid size). */
+int tnsp_rt_repack_f64(const int32_t* plan, const tnsp_rt_form* src, const tnsp_rt_form* dst, double* dst_data, int64_t dst_stride,
+                       int64_t work, int nb, void* stream);
+/* ONE grouped GEMM over (chain x sector) (contract.hpp:582-616): for every row sector i of c (rows of a, columns of b):
+ * C_i = A_i B_i', i' = the row sector of b whose charge is ksign * (charge of the column sector a pairs with i); zeros when absent */
+int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, const tnsp_rt_form* c, double* c_data, int64_t c_stride, int ksign,
+                     int nb, void* stream);
+/* per-sector QR (kind 0; qr.hpp:178-304, common edge qr.hpp:419-429) / SVD with the global greedy cut (kind 2; svd.hpp:104-211,
+ * 429-481) of every (chain, sector) matrix of f.  The bond label of row sector i on the first factor is
+ * t1s * t1[chain] - fsign_rs * rowkey(i).  Three calls: _plan (labels of the QR bond, work queue, work-buffer layout), then the
+ * caller sorts / matches the bond, then _qr writes Q | R, or _svd_work + _svd_finish (labels of the kept bond) + sort / match +
+ * _svd_scatter write U | S | V. */
+int64_t tnsp_rt_factor_ws_ints(int64_t kfull);   /* int32 entries of `ws` per chain, kfull = min(M, N) */
+int64_t tnsp_rt_svd_work_doubles(int64_t M, int64_t N);
+int tnsp_rt_factor_plan(const tnsp_rt_form* f, int kind, int fsign_rs, const int32_t* t1, int t1_stride, int t1s, int64_t kdim,
+                        int32_t* labels, int32_t* ws, int64_t ws_stride, int nb, void* stream);
+int tnsp_rt_qr_f64(const tnsp_rt_form* f, int fsign_rs, const int32_t* t1, int t1_stride, int t1s, const int32_t* bond, int64_t bond_stride,
+                   const int32_t* m_first, double* first, int64_t first_stride, const int32_t* m_second, double* second,
+                   int64_t second_stride, int nb, void* stream);
+int tnsp_rt_svd_work_f64(const tnsp_rt_form* f, double* work, int64_t work_stride, const int32_t* ws, int64_t ws_stride, int nb, void* stream);
+int tnsp_rt_svd_finish_f64(const tnsp_rt_form* f, int fsign_rs, const int32_t* t1, int t1_stride, int t1s, int64_t kdim, int64_t remain_cut,
+                           double relative_cut, const double* work, int64_t work_stride, int32_t* labels, int32_t* ws,
+                           int64_t ws_stride, int nb, void* stream);
+int tnsp_rt_svd_scatter_f64(const tnsp_rt_form* f, int fsign_rs, const int32_t* t1, int t1_stride, int t1s, const int32_t* bond,
+                            int64_t bond_stride, const int32_t* m_first, double* first, int64_t first_stride, const int32_t* m_s, double* s,
+                            int64_t s_stride, const int32_t* m_second, double* second, int64_t second_stride, const double* work,
+                            int64_t work_stride, const int32_t* ws, int64_t ws_stride, int nb, void* stream);
+/* elementwise over the stored sectors (scalar.hpp:46-118, tensor.hpp:631-660): op 0 multiply / 1 divide by alpha[chain];
+ * binary op 0 + 1 - 2 * 3 /; norms kind -1 max 1 sum 2 euclid; scalar: the single element of an all-dimension-1 tensor (0 when
+ * the sector is absent) */
+int tnsp_rt_scale_f64(const double* x, int64_t x_stride, const int32_t* match, int64_t match_stride, const double* alpha, int alpha_stride,
+                      int op, double* y, int64_t y_stride, int64_t cap, int nb, void* stream);
+int tnsp_rt_binary_f64(const double* x, int64_t x_stride, const double* w, int64_t w_stride, const int32_t* match, int64_t match_stride,
+                       int op, double* y, int64_t y_stride, int64_t cap, int nb, void* stream);
+int tnsp_rt_norm_f64(const double* x, int64_t x_stride, const int32_t* match, int64_t match_stride, int kind, double* out, int nb, void* stream);
+int tnsp_rt_scalar_f64(const double* x, int64_t x_stride, const int32_t* match, int64_t match_stride, double* out, int nb, void* stream);
+
 /* ---- host RNG with libstdc++ semantics (TAT.random, PyTAT.hpp:87-126): one mt19937_64 per chain ---- */
 void* tnsp_rng_create_host(int n_chains);
 void tnsp_rng_destroy_host(void* rng);

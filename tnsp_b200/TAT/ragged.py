@@ -145,7 +145,7 @@ class Core:
         match, _ = B.rt_match(rt, rs, ct, cs, self.target, self.tsign, None, 0, self.nb if self.target is not None else max(rt.shape[0], ct.shape[0]))
         M, N = self.group_dim(rows), self.group_dim(cols)
         src = self.forms[self.primary]
-        data = B.rt_alloc(src.data.shape[0], M * N)
+        data = B.rt_alloc(max(src.data.shape[0], match.shape[0]), M * N)
         f = Form(rows, cols, rt, rs, ct, cs, match, data, M, N)
         STATS["repack"] += 1
         B.rt_repack(_repack_plan(self, src, f), src, f)

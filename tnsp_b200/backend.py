@@ -34,6 +34,17 @@ class TnspError(RuntimeError):
     pass
 
 
+class RtForm(ctypes.Structure):
+    """tnsp_rt_form of include/tnsp_b200.h: one sector-compact storage (or a dense array when rt is NULL)"""
+    _fields_ = [("data", c_vp), ("data_stride", c_i64), ("rt", c_vp), ("rt_stride", c_i64), ("M", c_i64), ("ct", c_vp), ("ct_stride", c_i64),
+                ("N", c_i64), ("match", c_vp), ("match_stride", c_i64)]
+
+
+RT_SMAX = 64
+RT_HDR = 3 + 2 * RT_SMAX
+RT_MSTRIDE = 4 + 2 * RT_SMAX
+
+
 def _declare_host(lib):
     lib.tnsp_abi_version.restype = c_int
     lib.tnsp_last_error.restype = ctypes.c_char_p
@@ -102,6 +113,151 @@ class CudaBackend:
         lib.tnsp_block_sign_f64.argtypes = [P, c_int, P, c_i64, P, c_i64, c_i64, c_int, P]
         lib.tnsp_gather_rows_f64.argtypes = [P, c_i64, P, P, c_i64, c_int, P]
         lib.tnsp_select_f64.argtypes = [P, P, c_i64, P, c_i64, P, c_i64, c_i64, c_int, P]
+        self._rt_declare()
+
+    # -- sector-compact lock-step tensors (TAT/ragged.py; csrc/ragged.cu, csrc/factor_sector.cu) ------------------------
+    def _rt_declare(self):
+        lib, P = self.lib, c_vp
+        FP = ctypes.POINTER(RtForm)
+        lib.tnsp_rt_sort_i32.argtypes = [c_int, P, P, P, P, c_i64, P, c_int, P]
+        lib.tnsp_rt_match_i32.argtypes = [P, c_i64, c_int, P, c_i64, c_int, P, c_int, c_int, P, c_int, c_int, P, P, c_int, P]
+        lib.tnsp_rt_repack_f64.argtypes = [P, FP, FP, P, c_i64, c_i64, c_int, P]
+        lib.tnsp_rt_gemm_f64.argtypes = [FP, FP, FP, P, c_i64, c_int, c_int, P]
+        lib.tnsp_rt_factor_ws_ints.restype = c_i64
+        lib.tnsp_rt_factor_ws_ints.argtypes = [c_i64]
+        lib.tnsp_rt_svd_work_doubles.restype = c_i64
+        lib.tnsp_rt_svd_work_doubles.argtypes = [c_i64, c_i64]
+        lib.tnsp_rt_factor_plan.argtypes = [FP, c_int, c_int, P, c_int, c_int, c_i64, P, P, c_i64, c_int, P]
+        lib.tnsp_rt_qr_f64.argtypes = [FP, c_int, P, c_int, c_int, P, c_i64, P, P, c_i64, P, P, c_i64, c_int, P]
+        lib.tnsp_rt_svd_work_f64.argtypes = [FP, P, c_i64, P, c_i64, c_int, P]
+        lib.tnsp_rt_svd_finish_f64.argtypes = [FP, c_int, P, c_int, c_int, c_i64, c_i64, c_dbl, P, c_i64, P, P, c_i64, c_int, P]
+        lib.tnsp_rt_svd_scatter_f64.argtypes = [FP, c_int, P, c_int, c_int, P, c_i64, P, P, c_i64, P, P, c_i64, P, P, c_i64, P, c_i64, P, c_i64,
+                                                c_int, P]
+        lib.tnsp_rt_scale_f64.argtypes = [P, c_i64, P, c_i64, P, c_int, c_int, P, c_i64, c_i64, c_int, P]
+        lib.tnsp_rt_binary_f64.argtypes = [P, c_i64, P, c_i64, P, c_i64, c_int, P, c_i64, c_i64, c_int, P]
+        lib.tnsp_rt_norm_f64.argtypes = [P, c_i64, P, c_i64, c_int, P, c_int, P]
+        lib.tnsp_rt_scalar_f64.argtypes = [P, c_i64, P, c_i64, P, c_int, P]
+
+    @staticmethod
+    def _st(t):
+        """chain stride in elements of a [nb, size] buffer (0 broadcasts)"""
+        return 0 if t.shape[0] == 1 else t.stride(0)
+
+    def _form(self, f, data=None):
+        """ctypes view of a ragged.Form (or of a dense device array)"""
+        if isinstance(f, torch.Tensor):
+            return RtForm(f.data_ptr(), self._st(f), None, 0, 0, None, 0, 0, None, 0)
+        d = f.data if data is None else data
+        return RtForm(d.data_ptr(), self._st(d), f.rt.data_ptr(), self._st(f.rt), f.M, f.ct.data_ptr(), self._st(f.ct), f.N,
+                      f.match.data_ptr(), self._st(f.match))
+
+    def rt_alloc(self, nb, size):
+        return torch.empty((nb, max(int(size), 1) + RT_SMAX), dtype=torch.float64, device=self.device)
+
+    def rt_sort(self, edges):
+        n = len(edges)
+        nbT = max([int(a.shape[0]) for a, _, _ in edges] + [1])
+        M = 1
+        for _, _, d in edges:
+            M *= int(d)
+        table = torch.empty((nbT, RT_HDR + 2 * M), dtype=torch.int32, device=self.device)
+        ptrs = (c_vp * max(n, 1))(*[a.data_ptr() for a, _, _ in edges])
+        strides = (c_i64 * max(n, 1))(*[self._st(a) for a, _, _ in edges])
+        dims = (ctypes.c_int32 * max(n, 1))(*[int(d) for _, _, d in edges])
+        signs = (ctypes.c_int32 * max(n, 1))(*[int(s) for _, s, _ in edges])
+        self._ck(self.lib.tnsp_rt_sort_i32(n, ptrs, strides, dims, signs, M, table.data_ptr(), nbT, self._stream()))
+        return table
+
+    def rt_match(self, rt, rs, ct, cs, t1, s1, t2, s2, nbm):
+        nbm = max(int(nbm), rt.shape[0], ct.shape[0], 1 if t1 is None else t1.shape[0], 1 if t2 is None else t2.shape[0])
+        match = torch.empty((nbm, RT_MSTRIDE), dtype=torch.int32, device=self.device)
+        tsum = torch.empty(nbm, dtype=torch.int32, device=self.device) if (t1 is not None or t2 is not None) else None
+        self._ck(self.lib.tnsp_rt_match_i32(rt.data_ptr(), self._st(rt), int(rs), ct.data_ptr(), self._st(ct), int(cs),
+                                            None if t1 is None else t1.data_ptr(), 0 if t1 is None or t1.shape[0] == 1 else 1, int(s1),
+                                            None if t2 is None else t2.data_ptr(), 0 if t2 is None or t2.shape[0] == 1 else 1, int(s2),
+                                            match.data_ptr(), None if tsum is None else tsum.data_ptr(), nbm, self._stream()))
+        return match, tsum
+
+    def rt_repack(self, plan, src, dst):
+        dst_dense = isinstance(dst, torch.Tensor)
+        out = dst if dst_dense else dst.data
+        nb = out.shape[0]
+        if not isinstance(src, torch.Tensor):
+            nb = max(nb, src.match.shape[0])
+        work = out.shape[1] if dst_dense else dst.M * dst.N + RT_SMAX
+        fs, fd = self._form(src), self._form(dst)
+        self._ck(self.lib.tnsp_rt_repack_f64(plan.data_ptr(), ctypes.byref(fs), ctypes.byref(fd), out.data_ptr(), out.stride(0), int(work), nb,
+                                             self._stream()))
+
+    def rt_gemm(self, A, B, C, ksign, nb):
+        fa, fb, fc = self._form(A), self._form(B), self._form(C)
+        self._ck(self.lib.tnsp_rt_gemm_f64(ctypes.byref(fa), ctypes.byref(fb), ctypes.byref(fc), C.data.data_ptr(), C.data.stride(0), int(ksign),
+                                           nb, self._stream()))
+
+    def rt_factor(self, kind, F, fsign, tt, tts, t1, t1s, kdim, remain_cut, relative_cut, nb):
+        lib, st = self.lib, self._stream()
+        kd = max(int(kdim), 1)
+        kfull = max(min(F.M, F.N), 1)
+        frs = int(fsign) * int(F.rs)
+        ff = self._form(F)
+        t1p = None if t1 is None else t1.data_ptr()
+        t1st = 0 if t1 is None or t1.shape[0] == 1 else 1
+        t1s = int(t1s) if t1 is not None else 0
+        wss = int(lib.tnsp_rt_factor_ws_ints(kfull))
+        ws = torch.empty((nb, wss), dtype=torch.int32, device=self.device)
+        labels = torch.empty((nb, kd), dtype=torch.int32, device=self.device)
+        code = 0 if kind == "qr" else 2
+        self._ck(lib.tnsp_rt_factor_plan(ctypes.byref(ff), code, frs, t1p, t1st, t1s, kd, labels.data_ptr(), ws.data_ptr(), wss, nb, st))
+        if code == 2:
+            work = torch.empty((nb, int(lib.tnsp_rt_svd_work_doubles(F.M, F.N))), dtype=torch.float64, device=self.device)
+            self._ck(lib.tnsp_rt_svd_work_f64(ctypes.byref(ff), work.data_ptr(), work.stride(0), ws.data_ptr(), wss, nb, st))
+            self._ck(lib.tnsp_rt_svd_finish_f64(ctypes.byref(ff), frs, t1p, t1st, t1s, kd, int(min(remain_cut, 1 << 40)), float(relative_cut),
+                                                work.data_ptr(), work.stride(0), labels.data_ptr(), ws.data_ptr(), wss, nb, st))
+        tab = self.rt_sort([(labels, 1, kd)])
+        m_first, _ = self.rt_match(F.rt, F.rs * fsign, tab, 1, t1, t1s, None, 0, nb)
+        m_second, _ = self.rt_match(tab, -1, F.ct, F.cs * fsign, tt, tts, t1, -t1s if t1 is not None else 0, nb)
+        first = self.rt_alloc(nb, F.M * kd)
+        second = self.rt_alloc(nb, kd * F.N)
+        out = {"labels": labels, "bond_col": (tab, 1), "bond_row": (tab, -1), "first": (m_first, first), "second": (m_second, second)}
+        if code == 0:
+            self._ck(lib.tnsp_rt_qr_f64(ctypes.byref(ff), frs, t1p, t1st, t1s, tab.data_ptr(), self._st(tab), m_first.data_ptr(), first.data_ptr(),
+                                        first.stride(0), m_second.data_ptr(), second.data_ptr(), second.stride(0), nb, st))
+            return out
+        m_s, _ = self.rt_match(tab, -1, tab, 1, None, 0, None, 0, nb)
+        s_data = self.rt_alloc(nb, kd * kd)
+        self._ck(lib.tnsp_rt_svd_scatter_f64(ctypes.byref(ff), frs, t1p, t1st, t1s, tab.data_ptr(), self._st(tab), m_first.data_ptr(),
+                                             first.data_ptr(), first.stride(0), m_s.data_ptr(), s_data.data_ptr(), s_data.stride(0),
+                                             m_second.data_ptr(), second.data_ptr(), second.stride(0), work.data_ptr(), work.stride(0),
+                                             ws.data_ptr(), wss, nb, st))
+        out["s"] = (m_s, s_data)
+        return out
+
+    def rt_scale(self, data, match, vec, op):
+        nb = max(data.shape[0], match.shape[0], vec.shape[0])
+        out = torch.empty((nb, data.shape[1]), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.tnsp_rt_scale_f64(data.data_ptr(), self._st(data), match.data_ptr(), self._st(match), vec.data_ptr(),
+                                            0 if vec.shape[0] == 1 else 1, int(op), out.data_ptr(), out.stride(0), data.shape[1], nb, self._stream()))
+        return out
+
+    def rt_binary(self, a, b, match, op):
+        nb = max(a.shape[0], b.shape[0], match.shape[0])
+        out = torch.empty((nb, a.shape[1]), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.tnsp_rt_binary_f64(a.data_ptr(), self._st(a), b.data_ptr(), self._st(b), match.data_ptr(), self._st(match), int(op),
+                                             out.data_ptr(), out.stride(0), a.shape[1], nb, self._stream()))
+        return out
+
+    def rt_norm(self, data, match, kind):
+        nb = max(data.shape[0], match.shape[0])
+        out = torch.empty(nb, dtype=torch.float64, device=self.device)
+        self._ck(self.lib.tnsp_rt_norm_f64(data.data_ptr(), self._st(data), match.data_ptr(), self._st(match), int(kind), out.data_ptr(), nb,
+                                           self._stream()))
+        return out
+
+    def rt_scalar(self, data, match):
+        nb = max(data.shape[0], match.shape[0])
+        out = torch.empty(nb, dtype=torch.float64, device=self.device)
+        self._ck(self.lib.tnsp_rt_scalar_f64(data.data_ptr(), self._st(data), match.data_ptr(), self._st(match), out.data_ptr(), nb, self._stream()))
+        return out
 
     # -- buffers ------------------------------------------------------------------------------
     def empty(self, nb, size):

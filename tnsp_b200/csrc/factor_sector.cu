@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "ragged.cuh"
 #include <algorithm>
 #include <utility>
 #include <vector>
@@ -2074,6 +2075,300 @@ static bool desc_applicable(const int64_t* sh, int ns) {
     }
     return true;
 }
+
+// ================================================================================================
+// Sector-compact lock-step tensors (tnsp_b200/TAT/ragged.py, csrc/ragged.cuh): the sectors of every chain are NAMED by the
+// chain's label tables, stored as contiguous row-major matrices, and factorised from the same footprint-class work queue as
+// above -- no zero-pattern discovery, no gather, and the factors are written sector by sector in the compact layout.
+// qr.hpp:178-304 / 419-429, svd.hpp:104-211 / 429-481 with the sample axis added.
+//   ws (int32 per chain): [0] staged bond size, [1] kept bond size, then per row sector 6 ints
+//   (k0 = staging offset of its bond indices, uoff, voff, q = min(m, n) or 0, kept, new bond offset), then dest[kfull]:
+//   position of a staged singular triplet inside its sector's kept block (-1: cut)
+// ================================================================================================
+constexpr int RT_WS_HDR = 8;
+constexpr int RT_WS_SEC = 6;
+__host__ __device__ inline int64_t rt_ws_stride(int64_t kfull) { return RT_WS_HDR + RT_WS_SEC * RT_SMAX + kfull; }
+
+// one thread per chain: bond layout of the chain + one work item per non-empty sector
+__global__ void __launch_bounds__(128) rt_factor_plan_kernel(RtForm F, int kind, int frs, const int* __restrict__ t1, int t1st, int t1s, int kdim,
+                                                             int* __restrict__ labels, int* __restrict__ ws, long long wss, int* qctl,
+                                                             int2* __restrict__ qitems, long long qcap, int nb) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const RtTab R(F.rt + b * F.rts), C(F.ct + b * F.cts);
+    const RtMatch Mt(F.match + b * F.mts);
+    int* w = ws + (long long)b * wss;
+    const int tq = t1 ? t1s * t1[(long long)b * t1st] : 0;
+    const int nsec = max(R.nsec(), 0);
+    int k0 = 0, uo = 0, vo = 0;
+    for (int i = 0; i < nsec; ++i) {
+        int* e = w + RT_WS_HDR + RT_WS_SEC * i;
+        const int j = Mt.mcol(i);
+        const int m = R.count(i), n = j >= 0 ? C.count(j) : 0;
+        const int q = m < n ? m : n;
+        e[0] = k0; e[1] = uo; e[2] = vo; e[3] = q; e[4] = q; e[5] = k0;
+        if (q == 0) continue;
+        if (kind == 0) {
+            const int lam = tq - frs * R.skey(i);
+            for (int t = 0; t < q; ++t)
+                if (k0 + t < kdim) labels[(long long)b * kdim + k0 + t] = lam;
+        }
+        int64_t need;
+        if (kind == 2) { const int pp = m >= n ? m : n; need = svd_sector_need(pp, q); uo += m * q; vo += q * n; }
+        else need = qr_sector_need(m, n);
+        k0 += q;
+        const int cls = need > kQSmallDoubles ? 0 : (need > kQMidDoubles ? 1 : 2);
+        const int at = atomicAdd(&qctl[cls], 1);
+        qitems[(long long)cls * qcap + at] = make_int2(b, i);
+    }
+    w[0] = k0; w[1] = k0;
+    if (kind == 0)
+        for (int t = k0; t < kdim; ++t) labels[(long long)b * kdim + t] = 1 << 30;    // dead bond indices
+}
+
+// QR of every queued (chain, sector): A_s (m x n, contiguous) = Q_s R_s; Q_s -> first factor at its row sector, R_s -> second
+// factor at the bond sector carrying this sector's label
+template <bool STAGED>
+__global__ void __launch_bounds__(kQBigThreads) rt_qr_work_kernel(RtForm F, int frs, const int* __restrict__ t1, int t1st, int t1s,
+                                                                  const int* __restrict__ bond, long long bonds, const int* __restrict__ m1,
+                                                                  double* __restrict__ first, long long fst, const int* __restrict__ m2,
+                                                                  double* __restrict__ second, long long sst, int* qctl,
+                                                                  const int2* __restrict__ qitems, long long qcap, int which, int64_t cap,
+                                                                  double* __restrict__ scratch, int64_t scratch_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int sh_ticket;
+    double* work = reinterpret_cast<double*>(smem_raw);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int2 item;
+    while (pop_item(which, qctl, qitems, qcap, &sh_ticket, item)) {
+        const int b = item.x, i = item.y;
+        const RtTab R(F.rt + b * F.rts), C(F.ct + b * F.cts), Bd(bond + b * bonds);
+        const RtMatch Mt(F.match + b * F.mts), M1(m1 + (long long)b * RT_MSTRIDE), M2(m2 + (long long)b * RT_MSTRIDE);
+        const int j = Mt.mcol(i);
+        const int ms = R.count(i), ns = C.count(j);
+        const int p = ms, q = ns;
+        const int ks = p < q ? p : q;
+        const double* A = F.data + (long long)b * F.dstride + Mt.moff(i);
+        const int tq = t1 ? t1s * t1[(long long)b * t1st] : 0;
+        const int ib = Bd.find(tq - frs * R.skey(i));
+        double* O1 = first + (long long)b * fst + M1.moff(i);                      // ms x ks
+        double* O2 = ib >= 0 ? second + (long long)b * sst + M2.moff(ib) : nullptr;  // ks x ns
+        const int ld = q | 1;
+        const int64_t need = qr_sector_need(p, q);
+        double* W = (need <= cap) ? work : scratch + (int64_t)blockIdx.x * scratch_per_cta;
+        double* tau = W + (int64_t)p * ld;
+        double* Rc = tau + 3 * ks;
+        double* Vp = Rc + (int64_t)ks * q;
+        double* Tm = Vp + 8 * ((p + 7) & ~7);
+        double* Pan = nullptr, *Zp = nullptr;
+        if (STAGED && need > cap && 128 + 2 * (int64_t)nt + 3 * (int64_t)ks + 8 * (int64_t)((p + 7) & ~7) <= cap) {
+            Tm = work; Zp = work + 128; tau = Zp + 2 * nt; Pan = tau + 3 * ks; Vp = Pan;
+        }
+        for (int e = tid; e < ms * ns; e += nt) {
+            const int r = e / ns, c = e - r * ns;
+            W[(int64_t)r * ld + c] = __ldg(A + e);
+        }
+        __syncthreads();
+        if (q > 8) {
+            if constexpr (STAGED) householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm, Pan, Zp);
+            else householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm);
+        } else householder_qr(W, ld, p, q, ks, tau, Rc, nullptr);
+        for (int e = tid; e < ms * ks; e += nt) {
+            const int r = e / ks, t = e - r * ks;
+            O1[e] = W[(int64_t)r * ld + t];
+        }
+        if (tid == 0 && ((ms * ks) & 1)) O1[ms * ks] = 0.0;
+        if (O2) {
+            for (int e = tid; e < ks * ns; e += nt) O2[e] = Rc[e];
+            if (tid == 0 && ((ks * ns) & 1)) O2[ks * ns] = 0.0;
+        }
+    }
+}
+
+// SVD of every queued (chain, sector) into the chain's staging buffer: sigma at k0, U_s (m x q) at uoff, Vt_s (q x n) at voff
+template <bool BLOCKED>
+__global__ void __launch_bounds__(kQBigThreads) rt_svd_work_kernel(RtForm F, double* __restrict__ workg, long long wbs, const int* __restrict__ ws,
+                                                                   long long wss, int kfull, int* qctl, const int2* __restrict__ qitems,
+                                                                   long long qcap, int which, int64_t cap, double* __restrict__ scratch,
+                                                                   int64_t scratch_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int sh_ticket;
+    __shared__ int sh_rot;
+    __shared__ int sh_flags[2];
+    double* work = reinterpret_cast<double*>(smem_raw);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    int2 item;
+    while (pop_item(which, qctl, qitems, qcap, &sh_ticket, item)) {
+        const int b = item.x, i = item.y;
+        const RtTab R(F.rt + b * F.rts), C(F.ct + b * F.cts);
+        const RtMatch Mt(F.match + b * F.mts);
+        const int* e6 = ws + (long long)b * wss + RT_WS_HDR + RT_WS_SEC * i;
+        const int j = Mt.mcol(i);
+        const int ms = R.count(i), ns = C.count(j);
+        const double* A = F.data + (long long)b * F.dstride + Mt.moff(i);
+        double* wg = workg + (long long)b * wbs;
+        double* sig_all = wg + e6[0];
+        double* Us = wg + kfull + e6[1];
+        double* Vs = wg + kfull + (long long)F.M * kfull + e6[2];
+        const bool tall = ms >= ns;
+        const int p = tall ? ms : ns, q = tall ? ns : ms;
+        const int ldp = p + (p & 1), ldq = q + (q & 1);
+        double* G = (svd_sector_need(p, q) <= cap) ? work : scratch + (int64_t)blockIdx.x * scratch_per_cta;
+        double* V = G + (int64_t)q * ldp;
+        double* sig = V + (int64_t)q * ldq;
+        for (int e = tid; e < ms * ns; e += nt) {
+            const int r = e / ns, c = e - r * ns;
+            const double v = __ldg(A + e);
+            if (tall) G[(int64_t)c * ldp + r] = v; else G[(int64_t)r * ldp + c] = v;
+        }
+        if (p & 1) for (int c = tid; c < q; c += nt) G[(int64_t)c * ldp + p] = 0.0;
+        __syncthreads();
+        if (!BLOCKED || svd_sector_need(p, q) <= cap || jacobi_block_width(ldp, ldq, cap) < 2)
+            jacobi_svd2(G, ldp, V, ldq, p, q, &sh_rot, g_jacobi_cached_norms ? sig : nullptr);
+        else
+            jacobi_svd_blocked(G, ldp, V, ldq, p, q, work, cap, sh_flags);
+        for (int c = warp; c < q; c += nwarps) {
+            double s2 = 0.0;
+            for (int r = lane; r < p; r += 32) s2 += G[(int64_t)c * ldp + r] * G[(int64_t)c * ldp + r];
+            s2 = warp_sum(s2);
+            if (lane == 0) { sig[c] = sqrt(s2); sig_all[c] = sqrt(s2); }
+        }
+        __syncthreads();
+        for (int e = tid; e < ms * q; e += nt) {
+            const int r = e / q, c = e - r * q;
+            if (tall) { const double sg = sig[c]; Us[e] = sg > 0.0 ? G[(int64_t)c * ldp + r] / sg : 0.0; }
+            else Us[e] = V[(int64_t)c * ldq + r];
+        }
+        for (int e = tid; e < q * ns; e += nt) {
+            const int c = e / ns, t = e - c * ns;
+            if (tall) Vs[e] = V[(int64_t)c * ldq + t];
+            else { const double sg = sig[c]; Vs[e] = sg > 0.0 ? G[(int64_t)c * ldp + t] / sg : 0.0; }
+        }
+    }
+}
+
+// one CTA per chain: global descending rank of the staged singular values (ties: staging order = sector order, then position:
+// svd.hpp:455-461), greedy cut (svd.hpp:429-481: the first remain_cut values above relative_cut * sigma_max), kept counts and the
+// labels of the new bond (kept values sector by sector, descending inside a sector)
+__global__ void __launch_bounds__(256) rt_svd_finish_kernel(RtForm F, int frs, const int* __restrict__ t1, int t1st, int t1s, int kdim, int kfull,
+                                                            long long remain_cut, double relative_cut, const double* __restrict__ workg,
+                                                            long long wbs, int* __restrict__ labels, int* __restrict__ ws, long long wss) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ int sec_kept[RT_SMAX], sec_new[RT_SMAX + 1];
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const RtTab R(F.rt + b * F.rts);
+    int* w = ws + (long long)b * wss;
+    const double* sig = workg + (long long)b * wbs;
+    const int ktot = w[0];
+    const int nsec = max(R.nsec(), 0);
+    double* sg = reinterpret_cast<double*>(smem_raw);       // [ktot]
+    int* keep = reinterpret_cast<int*>(sg + kfull);         // [ktot] 1 / 0
+    int* dest = w + RT_WS_HDR + RT_WS_SEC * RT_SMAX;
+    const int tq = t1 ? t1s * t1[(long long)b * t1st] : 0;
+    double mx = 0.0;
+    for (int c = tid; c < ktot; c += nt) { sg[c] = sig[c]; mx = fmax(mx, sig[c]); }
+    mx = block_max(mx, red);
+    const double thr = relative_cut * mx;
+    for (int c = tid; c < ktot; c += nt) {
+        const double v = sg[c];
+        int r = 0;
+        for (int o = 0; o < ktot; ++o) { const double u = sg[o]; r += (u > v) || (u == v && o < c); }
+        keep[c] = (r < remain_cut && v > thr) ? 1 : 0;
+    }
+    for (int i = tid; i < RT_SMAX; i += nt) sec_kept[i] = 0;
+    __syncthreads();
+    // position inside the sector: number of kept sector-mates with a larger value (or equal and earlier)
+    for (int i = 0; i < nsec; ++i) {
+        const int* e6 = w + RT_WS_HDR + RT_WS_SEC * i;
+        const int k0 = e6[0], q = e6[3];
+        for (int c = tid; c < q; c += nt) {
+            int pos = -1;
+            if (keep[k0 + c]) {
+                pos = 0;
+                const double v = sg[k0 + c];
+                for (int o = 0; o < q; ++o) { const double u = sg[k0 + o]; pos += keep[k0 + o] && ((u > v) || (u == v && o < c)); }
+                atomicAdd(&sec_kept[i], 1);
+            }
+            dest[k0 + c] = pos;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int i = 0; i < nsec; ++i) { sec_new[i] = acc; acc += sec_kept[i]; }
+        sec_new[nsec] = acc;
+        w[1] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < nsec; i += nt) {
+        int* e6 = w + RT_WS_HDR + RT_WS_SEC * i;
+        e6[4] = sec_kept[i];
+        e6[5] = sec_new[i];
+    }
+    for (int i = 0; i < nsec; ++i) {
+        const int lam = tq - frs * R.skey(i);
+        for (int t = tid; t < sec_kept[i]; t += nt)
+            if (sec_new[i] + t < kdim) labels[(long long)b * kdim + sec_new[i] + t] = lam;
+    }
+    for (int t = sec_new[nsec] + tid; t < kdim; t += nt) labels[(long long)b * kdim + t] = 1 << 30;
+}
+
+// grid (chain, split): kept columns of U_s, rows of Vt_s and the diagonal S_s into the compact factors
+__global__ void __launch_bounds__(256) rt_svd_scatter_kernel(RtForm F, int frs, const int* __restrict__ t1, int t1st, int t1s,
+                                                             const int* __restrict__ bond, long long bonds, const int* __restrict__ m1,
+                                                             double* __restrict__ first, long long fst, const int* __restrict__ m3,
+                                                             double* __restrict__ sdat, long long sst, const int* __restrict__ m2,
+                                                             double* __restrict__ second, long long cst, const double* __restrict__ workg,
+                                                             long long wbs, const int* __restrict__ ws, long long wss, int kfull) {
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const RtTab R(F.rt + b * F.rts), C(F.ct + b * F.cts), Bd(bond + b * bonds);
+    const RtMatch Mt(F.match + b * F.mts), M1(m1 + (long long)b * RT_MSTRIDE), M2(m2 + (long long)b * RT_MSTRIDE), M3(m3 + (long long)b * RT_MSTRIDE);
+    const int* w = ws + (long long)b * wss;
+    const int* dest = w + RT_WS_HDR + RT_WS_SEC * RT_SMAX;
+    const double* wg = workg + (long long)b * wbs;
+    const int tq = t1 ? t1s * t1[(long long)b * t1st] : 0;
+    const int nsec = max(R.nsec(), 0);
+    for (int i = blockIdx.y; i < nsec; i += gridDim.y) {
+        const int* e6 = w + RT_WS_HDR + RT_WS_SEC * i;
+        const int q = e6[3], kc = e6[4];
+        if (q == 0 || kc == 0) continue;
+        const int j = Mt.mcol(i);
+        const int ms = R.count(i), ns = C.count(j);
+        const int ib = Bd.find(tq - frs * R.skey(i));
+        if (ib < 0) continue;
+        const double* sig = wg + e6[0];
+        const double* Us = wg + kfull + e6[1];
+        const double* Vs = wg + kfull + (long long)F.M * kfull + e6[2];
+        const int* dst = dest + e6[0];
+        double* O1 = first + (long long)b * fst + M1.moff(i);        // ms x kc
+        double* O2 = second + (long long)b * cst + M2.moff(ib);      // kc x ns
+        double* O3 = sdat + (long long)b * sst + M3.moff(ib);        // kc x kc
+        for (int e = tid; e < ms * q; e += nt) {
+            const int r = e / q, c = e - r * q;
+            const int d = dst[c];
+            if (d >= 0) O1[(long long)r * kc + d] = Us[e];
+        }
+        for (int e = tid; e < q * ns; e += nt) {
+            const int c = e / ns, t = e - c * ns;
+            const int d = dst[c];
+            if (d >= 0) O2[(long long)d * ns + t] = Vs[e];
+        }
+        for (int e = tid; e < kc * kc; e += nt) O3[e] = 0.0;
+        __syncthreads();
+        for (int c = tid; c < q; c += nt) {
+            const int d = dst[c];
+            if (d >= 0) O3[(long long)d * kc + d] = sig[c];
+        }
+        if (tid == 0) {
+            if ((ms * kc) & 1) O1[ms * kc] = 0.0;
+            if ((kc * ns) & 1) O2[kc * ns] = 0.0;
+            if ((kc * kc) & 1) O3[kc * kc] = 0.0;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace tnsp
 
 using namespace tnsp;
@@ -2257,4 +2552,127 @@ extern "C" int tnsp_svd_sectors_gather_f64(const int64_t* sect, const int64_t* s
     const int err = svd_queue_launch(sect, sect_host, a, abs_, out1, o1bs, s, sbs, out2, o2bs, work, wbs, nb, (cudaStream_t)stream, rc);
     if (err < 0) { set_error("tnsp_svd_sectors_gather_f64: matrix too large for the discovered-sector kernels"); return 1; }
     return err;
+}
+
+// ---- sector-compact entry points (tnsp_b200/TAT/ragged.py) ----
+static int rt_queue_prepare(int nb, int64_t per_cta_scratch, cudaStream_t st, int64_t& qcap) {
+    qcap = (int64_t)nb * RT_SMAX;
+    if (!g_qws.qctl && cudaMalloc(&g_qws.qctl, 8 * sizeof(int)) != cudaSuccess) { set_error("sector queue: cudaMalloc"); return 1; }
+    if (!grow(g_qws.qitems, g_qws.qitems_cap, kQClasses * qcap) || !grow(g_qws.scratch, g_qws.scratch_cap, per_cta_scratch * kSMs)) {
+        set_error("sector queue: cudaMalloc of the workspace failed");
+        return 1;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(rt_qr_work_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(rt_qr_work_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(rt_svd_work_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(rt_svd_work_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
+        cudaFuncSetAttribute(rt_svd_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_set = true;
+    }
+    return 0;
+}
+
+extern "C" int64_t tnsp_rt_factor_ws_ints(int64_t kfull) { return rt_ws_stride(kfull); }
+extern "C" int64_t tnsp_rt_svd_work_doubles(int64_t M, int64_t N) {
+    const int64_t k = M < N ? M : N;
+    return k + M * k + k * N + 8;
+}
+
+static int64_t rt_scratch_need(int64_t M, int64_t N, int kind) {
+    if (kind == 2) {
+        const int64_t p = M >= N ? M : N, q = M >= N ? N : M;
+        const int64_t full = svd_sector_need(p, q);
+        return full > kQBigDoubles ? ((full + 9) & ~(int64_t)1) : 0;
+    }
+    const int64_t full = qr_sector_need(M, N);
+    return full > kQBigDoubles ? full + 8 : 0;
+}
+
+extern "C" int tnsp_rt_factor_plan(const tnsp_rt_form* f, int kind, int fsign_rs, const int32_t* t1, int t1_stride, int t1s, int64_t kdim,
+                                   int32_t* labels, int32_t* ws, int64_t ws_stride, int nb, void* stream) {
+    if (nb == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t qcap;
+    if (rt_queue_prepare(nb, rt_scratch_need(f->M, f->N, kind), st, qcap)) return 1;
+    cudaMemsetAsync(g_qws.qctl, 0, 8 * sizeof(int), st);
+    rt_factor_plan_kernel<<<(nb + 127) / 128, 128, 0, st>>>(to_form(f), kind, fsign_rs, t1, t1_stride, t1s, (int)kdim, labels, ws, ws_stride,
+                                                            g_qws.qctl, g_qws.qitems, qcap, nb);
+    return check_launch("tnsp_rt_factor_plan");
+}
+
+extern "C" int tnsp_rt_qr_f64(const tnsp_rt_form* f, int fsign_rs, const int32_t* t1, int t1_stride, int t1s, const int32_t* bond,
+                              int64_t bond_stride, const int32_t* m_first, double* first, int64_t first_stride, const int32_t* m_second,
+                              double* second, int64_t second_stride, int nb, void* stream) {
+    if (nb == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const RtForm F = to_form(f);
+    const int64_t qcap = (int64_t)nb * RT_SMAX;
+    const int64_t per_cta = rt_scratch_need(f->M, f->N, 0);
+    if (qr_sector_need(f->M, f->N) > kQSmallDoubles) {
+        rt_qr_work_kernel<true><<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first, first,
+                                                                               first_stride, m_second, second, second_stride, g_qws.qctl,
+                                                                               g_qws.qitems, qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
+        if (check_launch("tnsp_rt_qr_f64(big)")) return 1;
+    }
+    if (qr_sector_need(f->M, f->N) > kQMidDoubles) {
+        rt_qr_work_kernel<false><<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first,
+                                                                                       first, first_stride, m_second, second, second_stride,
+                                                                                       g_qws.qctl, g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
+        if (check_launch("tnsp_rt_qr_f64(72 KiB class)")) return 1;
+    }
+    rt_qr_work_kernel<false><<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first, first,
+                                                                                 first_stride, m_second, second, second_stride, g_qws.qctl,
+                                                                                 g_qws.qitems, qcap, 2, kQMidDoubles, nullptr, 0);
+    return check_launch("tnsp_rt_qr_f64(55 KiB class)");
+}
+
+extern "C" int tnsp_rt_svd_work_f64(const tnsp_rt_form* f, double* work, int64_t work_stride, const int32_t* ws, int64_t ws_stride, int nb,
+                                    void* stream) {
+    if (nb == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const RtForm F = to_form(f);
+    const int64_t qcap = (int64_t)nb * RT_SMAX;
+    const int64_t per_cta = rt_scratch_need(f->M, f->N, 2);
+    const int kfull = (int)(f->M < f->N ? f->M : f->N);
+    const int64_t p = f->M >= f->N ? f->M : f->N, q = f->M >= f->N ? f->N : f->M;
+    const int64_t full = svd_sector_need(p, q);
+    if (full > kQSmallDoubles) {
+        rt_svd_work_kernel<true><<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl, g_qws.qitems,
+                                                                                qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
+        if (check_launch("tnsp_rt_svd_work_f64(big)")) return 1;
+    }
+    if (full > kQMidDoubles) {
+        rt_svd_work_kernel<false><<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
+                                                                                        g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
+        if (check_launch("tnsp_rt_svd_work_f64(72 KiB class)")) return 1;
+    }
+    rt_svd_work_kernel<false><<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
+                                                                                  g_qws.qitems, qcap, 2, kQMidDoubles, nullptr, 0);
+    return check_launch("tnsp_rt_svd_work_f64(55 KiB class)");
+}
+
+extern "C" int tnsp_rt_svd_finish_f64(const tnsp_rt_form* f, int fsign_rs, const int32_t* t1, int t1_stride, int t1s, int64_t kdim,
+                                      int64_t remain_cut, double relative_cut, const double* work, int64_t work_stride, int32_t* labels,
+                                      int32_t* ws, int64_t ws_stride, int nb, void* stream) {
+    if (nb == 0) return 0;
+    const int kfull = (int)(f->M < f->N ? f->M : f->N);
+    const size_t smem = (size_t)kfull * 12 + 16;
+    if (smem > 96 * 1024) { set_error("tnsp_rt_svd_finish_f64: bond beyond 8190 singular values per chain"); return 1; }
+    rt_svd_finish_kernel<<<nb, 256, smem, (cudaStream_t)stream>>>(to_form(f), fsign_rs, t1, t1_stride, t1s, (int)kdim, kfull, remain_cut, relative_cut,
+                                                                  work, work_stride, labels, ws, ws_stride);
+    return check_launch("tnsp_rt_svd_finish_f64");
+}
+
+extern "C" int tnsp_rt_svd_scatter_f64(const tnsp_rt_form* f, int fsign_rs, const int32_t* t1, int t1_stride, int t1s, const int32_t* bond,
+                                       int64_t bond_stride, const int32_t* m_first, double* first, int64_t first_stride, const int32_t* m_s,
+                                       double* s, int64_t s_stride, const int32_t* m_second, double* second, int64_t second_stride,
+                                       const double* work, int64_t work_stride, const int32_t* ws, int64_t ws_stride, int nb, void* stream) {
+    if (nb == 0) return 0;
+    const int kfull = (int)(f->M < f->N ? f->M : f->N);
+    rt_svd_scatter_kernel<<<dim3(nb, 4), 256, 0, (cudaStream_t)stream>>>(to_form(f), fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first, first,
+                                                                        first_stride, m_s, s, s_stride, m_second, second, second_stride, work,
+                                                                        work_stride, ws, ws_stride, kfull);
+    return check_launch("tnsp_rt_svd_scatter_f64");
 }

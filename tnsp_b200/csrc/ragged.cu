@@ -1,0 +1,536 @@
+// Sector-compact lock-step tensors: device-side planning and data movement (tnsp_b200/TAT/ragged.py).
+//
+// A lock-step batch of Monte-Carlo chains holds block-symmetric tensors whose sector structure differs from chain to chain
+// (sampled physical charges, per-chain greedy cuts).  The reference plans every edge operation on the host per tensor
+// (TAT/include/TAT/implement/edge_operator.hpp:34-692, contract.hpp:306-620); here the same integer rules run ON THE DEVICE,
+// one CTA / warp per chain, from per-index charge labels, so that the host never waits for a size:
+//
+//   rt_sort_kernel    merged edge of a group of edges: merged indices sorted by summed charge (edge_operator.hpp:321-404)
+//   rt_match_kernel   pairing of row / column sectors with row charge + column charge = target (core.hpp:162-190,
+//                     contract.hpp:539-560); sector matrices are stored back to back at even offsets
+//   rt_repack_kernel  regroup / transpose between two groupings, or from / to the dense index space
+//                     (edge_operator.hpp:651-688, multidimension_span.hpp:250-383)
+//   rt_gemm_kernel    ONE grouped GEMM over (chain x sector x tile) on the FP64 tensor pipe (contract.hpp:582-616)
+//   elementwise       scale / binary / norms over the stored sectors only (scalar.hpp:46-118, tensor.hpp:631-660)
+//
+// Bounds: sort / match / repack / elementwise are HBM (and integer-issue) bound: algorithmic bytes = 16 B per stored element;
+// the GEMM is HBM-bound for cfg2's sectors (k, n <= 31) and tensor-pipe bound from min(m, n, k) ~ 128.
+#include "common.cuh"
+#include "ragged.cuh"
+#include <climits>
+#include <cstdint>
+
+namespace tnsp {
+
+// ------------------------------------------------------------------------------------------------
+// rt_sort: one CTA per chain
+// ------------------------------------------------------------------------------------------------
+struct RtEdges {
+    const int* lab[8];
+    long long lstride[8];
+    int dim[8];
+    int sign[8];
+    int n;
+};
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kHash = 256;
+
+__device__ __forceinline__ int rt_hash(int key) { return (int)(((unsigned)key * 2654435761u) >> 24) & (kHash - 1); }
+
+__global__ void __launch_bounds__(kSortThreads) rt_sort_kernel(RtEdges E, int M, int* __restrict__ table, long long tstride) {
+    __shared__ int hkey[kHash];
+    __shared__ int hval[kHash];
+    __shared__ int skeys[RT_SMAX + 1];
+    __shared__ int wcnt[kSortWarps][RT_SMAX + 1];
+    __shared__ int base[RT_SMAX + 2];
+    __shared__ int nsec_s, overflow_s;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* T = table + (long long)b * tstride;
+    int* perm = T + RT_HDR;
+    int* inv = T + RT_HDR + M;     // first used as scratch for the keys
+    for (int h = tid; h < kHash; h += kSortThreads) hkey[h] = RT_EMPTY;
+    for (int i = tid; i < kSortWarps * (RT_SMAX + 1); i += kSortThreads) (&wcnt[0][0])[i] = 0;
+    if (tid == 0) overflow_s = 0;
+    __syncthreads();
+    // pass A: keys + set of distinct keys
+    for (int r = tid; r < M; r += kSortThreads) {
+        int rest = r, key = 0;
+        bool dead = false;
+        for (int e = E.n - 1; e >= 0; --e) {
+            const int d = E.dim[e];
+            const int i = rest % d;
+            rest /= d;
+            const int l = __ldg(E.lab[e] + (long long)b * E.lstride[e] + i);
+            if (l >= RT_DEAD_MIN || l <= -RT_DEAD_MIN) dead = true;
+            key += E.sign[e] * l;
+        }
+        if (dead) key = RT_EMPTY;
+        inv[r] = key;
+        if (!dead) {
+            int h = rt_hash(key);
+            for (int probe = 0; probe < kHash; ++probe) {
+                const int old = atomicCAS(&hkey[h], RT_EMPTY, key);
+                if (old == RT_EMPTY || old == key) break;
+                h = (h + 1) & (kHash - 1);
+                if (probe == kHash - 1) overflow_s = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int n = 0;
+        for (int h = 0; h < kHash; ++h) {
+            const int k = hkey[h];
+            if (k == RT_EMPTY) continue;
+            if (n >= RT_SMAX) { overflow_s = 1; break; }
+            int j = n++;
+            while (j > 0 && skeys[j - 1] > k) { skeys[j] = skeys[j - 1]; --j; }
+            skeys[j] = k;
+        }
+        nsec_s = n;
+    }
+    __syncthreads();
+    const int nsec = nsec_s;
+    for (int h = tid; h < kHash; h += kSortThreads) {
+        const int k = hkey[h];
+        int v = nsec;
+        if (k != RT_EMPTY)
+            for (int i = 0; i < nsec; ++i)
+                if (skeys[i] == k) { v = i; break; }
+        hval[h] = v;
+    }
+    __syncthreads();
+    auto sector = [&](int key) -> int {
+        if (key == RT_EMPTY) return nsec;     // dead indices go behind the valid ones
+        int h = rt_hash(key);
+        for (int probe = 0; probe < kHash; ++probe) {
+            if (hkey[h] == key) return hval[h];
+            h = (h + 1) & (kHash - 1);
+        }
+        return nsec;
+    };
+    // every warp owns a contiguous range of merged indices: per-warp histogram, prefix over warps, stable placement
+    int chunk = (M + kSortWarps - 1) / kSortWarps;
+    chunk = (chunk + 31) & ~31;
+    const int r0 = warp * chunk, r1 = min(M, r0 + chunk);
+    for (int r = r0 + lane; r < r1; r += 32) atomicAdd(&wcnt[warp][sector(inv[r])], 1);
+    __syncthreads();
+    if (tid <= nsec) {
+        int tot = 0;
+        for (int w = 0; w < kSortWarps; ++w) { const int t = wcnt[w][tid]; wcnt[w][tid] = tot; tot += t; }
+        base[tid + 1] = tot;    // counts for now
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int s = 0; s <= nsec; ++s) { const int c = base[s + 1]; base[s] = acc; acc += c; }
+        base[nsec + 1] = acc;
+        T[0] = overflow_s ? -1 : nsec;
+        T[1] = base[nsec];
+        for (int s = 0; s < nsec; ++s) T[2 + s] = skeys[s];
+        for (int s = 0; s <= nsec; ++s) T[2 + RT_SMAX + s] = base[s];
+    }
+    __syncthreads();
+    for (int s = lane; s <= nsec; s += 32) wcnt[warp][s] += base[s];
+    __syncwarp();
+    for (int rr = r0; rr < r1; rr += 32) {
+        const int r = rr + lane;
+        const bool on = r < r1;
+        const int sec = on ? sector(inv[r]) : -1 - lane;      // idle lanes never share a group
+        const unsigned mask = __match_any_sync(0xffffffffu, sec);
+        const int rank = __popc(mask & ((1u << lane) - 1u));
+        int pos = 0;
+        if (on) pos = wcnt[warp][sec] + rank;
+        __syncwarp();
+        if (on && rank == 0) wcnt[warp][sec] += __popc(mask);
+        __syncwarp();
+        if (on) { perm[pos] = r; inv[r] = pos; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rt_match: one warp per chain
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rt_match_kernel(const int* __restrict__ rt, long long rts, int rs, const int* __restrict__ ct, long long cts,
+                                                       int cs, const int* __restrict__ t1, int t1s, int s1, const int* __restrict__ t2, int t2s,
+                                                       int s2, int* __restrict__ match, int* __restrict__ tsum, int nbm) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= nbm) return;
+    const RtTab R(rt + (long long)b * rts), C(ct + (long long)b * cts);
+    int t = 0;
+    if (t1) t += s1 * t1[(long long)b * t1s];
+    if (t2) t += s2 * t2[(long long)b * t2s];
+    if (tsum && lane == 0) tsum[b] = t;
+    int* Mrow = match + (long long)b * RT_MSTRIDE;
+    const int nr = max(R.nsec(), 0), nc = max(C.nsec(), 0);
+    int carry = 0;
+    for (int i0 = 0; i0 < nr; i0 += 32) {
+        const int i = i0 + lane;
+        int j = -1, sz = 0;
+        if (i < nr) {
+            const int want = t - rs * R.skey(i);
+            for (int jj = 0; jj < nc; ++jj)
+                if (cs * C.skey(jj) == want) { j = jj; break; }
+            if (j >= 0) { sz = R.count(i) * C.count(j); sz += sz & 1; }
+        }
+        int incl = sz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (i < nr) { Mrow[2 + i] = carry + incl - sz; Mrow[3 + RT_SMAX + i] = j; }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+        Mrow[2 + nr] = carry;
+        Mrow[0] = (R.nsec() < 0 || C.nsec() < 0) ? 0 : carry;
+        Mrow[1] = (R.nsec() < 0 || C.nsec() < 0) ? 1 : 0;      // sector overflow flag
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rt_repack: destination-driven regrouping
+// ------------------------------------------------------------------------------------------------
+constexpr int kRepackThreads = 256;
+constexpr int kPlanMax = 2 + 3 * 24;
+
+template <bool SRC_DENSE, bool DST_DENSE>
+__global__ void __launch_bounds__(kRepackThreads) rt_repack_kernel(const int* __restrict__ plan, RtForm S, RtForm D, double* __restrict__ dst,
+                                                                   long long dst_stride, long long dense_size) {
+    __shared__ int sp[kPlanMax];
+    __shared__ int hdr[4][RT_HDR];
+    __shared__ int mt[2][RT_MSTRIDE];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int n_ent = plan[0] + plan[1];
+    for (int i = tid; i < 2 + 3 * n_ent; i += kRepackThreads) sp[i] = plan[i];
+    if (!SRC_DENSE) {
+        for (int i = tid; i < RT_HDR; i += kRepackThreads) { hdr[0][i] = S.rt[b * S.rts + i]; hdr[1][i] = S.ct[b * S.cts + i]; }
+        for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mt[0][i] = S.match[b * S.mts + i];
+    }
+    if (!DST_DENSE) {
+        for (int i = tid; i < RT_HDR; i += kRepackThreads) { hdr[2][i] = D.rt[b * D.rts + i]; hdr[3][i] = D.ct[b * D.cts + i]; }
+        for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mt[1][i] = D.match[b * D.mts + i];
+    }
+    __syncthreads();
+    const int nr = sp[0], nc = sp[1];
+    const RtTab sR(hdr[0]), sC(hdr[1]), dR(hdr[2]), dC(hdr[3]);
+    const RtMatch sM(mt[0]), dM(mt[1]);
+    const long long total = DST_DENSE ? dense_size : (long long)dM.size();
+    const double* src = S.data + (long long)b * S.dstride;
+    double* out = dst + (long long)b * dst_stride;
+    const int* s_inv_r = SRC_DENSE ? nullptr : S.rt + b * S.rts + RT_HDR + S.M;
+    const int* s_inv_c = SRC_DENSE ? nullptr : S.ct + b * S.cts + RT_HDR + S.N;
+    const int* d_perm_r = DST_DENSE ? nullptr : D.rt + b * D.rts + RT_HDR;
+    const int* d_perm_c = DST_DENSE ? nullptr : D.ct + b * D.cts + RT_HDR;
+    for (long long e = (long long)blockIdx.x * kRepackThreads + tid; e < total; e += (long long)gridDim.x * kRepackThreads) {
+        long long rp, cp;
+        if (DST_DENSE) {
+            rp = e; cp = 0;
+        } else {
+            // sector of destination element e
+            int lo = 0, hi = dR.nsec();
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (dM.moff(mid) <= e) lo = mid; else hi = mid;
+            }
+            // sectors without a partner have zero extent: step back to the one that holds e
+            const int i = lo;
+            const int j = dM.mcol(i);
+            const int local = (int)(e - dM.moff(i));
+            const int n = j >= 0 ? dC.count(j) : 0;
+            const int m = dR.count(i);
+            if (j < 0 || local >= m * n) { out[e] = 0.0; continue; }     // alignment pad
+            const int a = local / n, c = local - a * n;
+            rp = d_perm_r[dR.sstart(i) + a];
+            cp = d_perm_c[dC.sstart(j) + c];
+        }
+        long long sr = 0, sc = 0;
+        for (int k = nr - 1; k >= 0; --k) {
+            const int dim = sp[2 + 3 * k];
+            const long long idx = rp % dim;
+            rp /= dim;
+            if (sp[3 + 3 * k]) sc += idx * sp[4 + 3 * k]; else sr += idx * sp[4 + 3 * k];
+        }
+        for (int k = nr + nc - 1; k >= nr; --k) {
+            const int dim = sp[2 + 3 * k];
+            const long long idx = cp % dim;
+            cp /= dim;
+            if (sp[3 + 3 * k]) sc += idx * sp[4 + 3 * k]; else sr += idx * sp[4 + 3 * k];
+        }
+        double v = 0.0;
+        if (SRC_DENSE) {
+            v = __ldg(src + sr + sc);
+        } else {
+            const int p = s_inv_r[sr], q = s_inv_c[sc];
+            if (p < sR.nvalid() && q < sC.nvalid()) {
+                const int i = sR.sector_of(p);
+                const int j = sM.mcol(i);
+                if (j >= 0 && q >= sC.sstart(j) && q < sC.sstart(j + 1))
+                    v = __ldg(src + sM.moff(i) + (long long)(p - sR.sstart(i)) * sC.count(j) + (q - sC.sstart(j)));
+            }
+        }
+        out[e] = v;
+    }
+}
+
+// the binary search above lands on the LAST sector whose offset is <= e; sectors without partner share the offset of their
+// successor, so the last one with that offset is the one that owns the element (or the final sentinel)
+
+// ------------------------------------------------------------------------------------------------
+// rt_gemm: C_s = A_s * B_s for every (chain, sector); 64 x 64 tiles, K slabs of 16, DMMA m8n8k4
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rt_dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int GT = 64;          // tile rows / columns
+constexpr int GK = 16;          // K slab
+constexpr int GLDA = GK + 4;    // conflict-free fragment reads
+constexpr int GLDB = GT + 8;
+
+__global__ void __launch_bounds__(128) rt_gemm_kernel(RtForm A, RtForm B, RtForm C, double* __restrict__ cdata, long long cstride, int ksign) {
+    __shared__ double As[GT * GLDA];
+    __shared__ double Bs[GK * GLDB];
+    __shared__ int hA[2][RT_HDR];       // A rows, A cols (k)
+    __shared__ int hB[2][RT_HDR];       // B rows (k), B cols
+    __shared__ int mA[RT_MSTRIDE], mB[RT_MSTRIDE], mC[RT_MSTRIDE];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < RT_HDR; i += 128) {
+        hA[0][i] = A.rt[b * A.rts + i]; hA[1][i] = A.ct[b * A.cts + i];
+        hB[0][i] = B.rt[b * B.rts + i]; hB[1][i] = B.ct[b * B.cts + i];
+    }
+    for (int i = tid; i < RT_MSTRIDE; i += 128) { mA[i] = A.match[b * A.mts + i]; mB[i] = B.match[b * B.mts + i]; mC[i] = C.match[b * C.mts + i]; }
+    __syncthreads();
+    const RtTab aR(hA[0]), aK(hA[1]), bK(hB[0]), bN(hB[1]);
+    const RtMatch MA(mA), MB(mB), MC(mC);
+    const double* a = A.data + (long long)b * A.dstride;
+    const double* bb = B.data + (long long)b * B.dstride;
+    double* c = cdata + (long long)b * cstride;
+    const int nsec = max(aR.nsec(), 0);
+    const int g = lane >> 2, q = lane & 3;
+    // flat tile index over (sector, tile_m, tile_n)
+    int tile = blockIdx.x;
+    int first = 0;      // tiles before the current sector
+    for (int i = 0; i < nsec; ++i) {
+        const int jc = MC.mcol(i);
+        if (jc < 0) continue;
+        const int m = aR.count(i), n = bN.count(jc);
+        if (m == 0 || n == 0) continue;
+        const int tm = (m + GT - 1) / GT, tn = (n + GT - 1) / GT;
+        const int here = tm * tn;
+        // operands of this sector
+        int k = 0;
+        long long aoff = 0, boff = 0;
+        const int jk = MA.mcol(i);
+        if (jk >= 0) {
+            const int ib = bK.find(ksign * aK.skey(jk));
+            if (ib >= 0 && MB.mcol(ib) == jc) {
+                k = min(aK.count(jk), bK.count(ib));
+                aoff = MA.moff(i);
+                boff = MB.moff(ib);
+            }
+        }
+        const long long coff = MC.moff(i);
+        for (; tile < first + here; tile += gridDim.x) {
+            const int t = tile - first;
+            const int r0 = (t / tn) * GT, c0 = (t % tn) * GT;
+            const int rows = min(GT, m - r0), cols = min(GT, n - c0);
+            const int nfr = (cols + 7) >> 3;
+            double acc[2][8][2];
+#pragma unroll
+            for (int x = 0; x < 2; ++x)
+#pragma unroll
+                for (int y = 0; y < 8; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+            for (int k0 = 0; k0 < k; k0 += GK) {
+                const int kw = min(GK, k - k0);
+                __syncthreads();
+                // A tile: rows x kw (zero padded to GT x GK)
+                for (int e = tid; e < GT * GK; e += 128) {
+                    const int r = e / GK, kk = e - r * GK;
+                    double v = 0.0;
+                    if (r < rows && kk < kw) v = __ldg(a + aoff + (long long)(r0 + r) * k + k0 + kk);
+                    As[r * GLDA + kk] = v;
+                }
+                for (int e = tid; e < GK * GT; e += 128) {
+                    const int kk = e / GT, cc = e - kk * GT;
+                    double v = 0.0;
+                    if (kk < kw && cc < cols) v = __ldg(bb + boff + (long long)(k0 + kk) * n + c0 + cc);
+                    Bs[kk * GLDB + cc] = v;
+                }
+                __syncthreads();
+                if (warp * 16 < rows) {
+#pragma unroll
+                    for (int ks = 0; ks < GK; ks += 4) {
+                        if (ks >= kw) break;
+                        const double a0 = As[(warp * 16 + g) * GLDA + ks + q];
+                        const double a1 = As[(warp * 16 + 8 + g) * GLDA + ks + q];
+#pragma unroll
+                        for (int y = 0; y < 8; ++y) {
+                            if (y < nfr) {
+                                const double bv = Bs[(ks + q) * GLDB + y * 8 + g];
+                                rt_dmma(acc[0][y][0], acc[0][y][1], a0, bv);
+                                rt_dmma(acc[1][y][0], acc[1][y][1], a1, bv);
+                            }
+                        }
+                    }
+                }
+            }
+            // epilogue: lane holds C[g][2q], C[g][2q+1] of every 8x8 fragment
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const int r = warp * 16 + x * 8 + g;
+                if (r < rows) {
+#pragma unroll
+                    for (int y = 0; y < 8; ++y) {
+                        const int cc = y * 8 + 2 * q;
+                        if (cc < cols) c[coff + (long long)(r0 + r) * n + c0 + cc] = acc[x][y][0];
+                        if (cc + 1 < cols) c[coff + (long long)(r0 + r) * n + c0 + cc + 1] = acc[x][y][1];
+                    }
+                }
+            }
+            if (t == 0 && tid == 0 && ((m * n) & 1)) c[coff + (long long)m * n] = 0.0;     // alignment pad of an odd-sized sector
+        }
+        first += here;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise over the stored sectors (per-chain sizes from the match table)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rt_scale_kernel(const double* __restrict__ x, long long xs, const int* __restrict__ match, long long mts,
+                                                       const double* __restrict__ alpha, int as, int op, double* __restrict__ y, long long ys) {
+    const int b = blockIdx.y;
+    const long long size = match[b * mts];
+    const double a = alpha[(long long)b * as];
+    const double f = op == 0 ? a : 1.0 / a;
+    const double* X = x + b * xs;
+    double* Y = y + b * ys;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < size; e += (long long)gridDim.x * 256)
+        Y[e] = op == 0 ? X[e] * f : X[e] / a;
+}
+
+__global__ void __launch_bounds__(256) rt_binary_kernel(const double* __restrict__ x, long long xs, const double* __restrict__ w, long long ws,
+                                                        const int* __restrict__ match, long long mts, int op, double* __restrict__ y, long long ys) {
+    const int b = blockIdx.y;
+    const long long size = match[b * mts];
+    const double* X = x + b * xs;
+    const double* W = w + b * ws;
+    double* Y = y + b * ys;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < size; e += (long long)gridDim.x * 256) {
+        const double p = X[e], r = W[e];
+        Y[e] = op == 0 ? p + r : op == 1 ? p - r : op == 2 ? p * r : (r == 0.0 ? p : p / r);
+    }
+}
+
+__global__ void __launch_bounds__(256) rt_norm_kernel(const double* __restrict__ x, long long xs, const int* __restrict__ match, long long mts, int kind,
+                                                      double* __restrict__ out) {
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    const long long size = match[b * mts];
+    const double* X = x + b * xs;
+    double v = 0.0;
+    for (long long e = threadIdx.x; e < size; e += 256) {
+        const double t = X[e];
+        if (kind == -1) v = fmax(v, fabs(t));
+        else if (kind == 1) v += fabs(t);
+        else v += t * t;
+    }
+    v = kind == -1 ? block_max(v, red) : block_sum(v, red);
+    if (threadIdx.x == 0) out[b] = kind == 2 ? sqrt(v) : v;
+}
+
+__global__ void rt_scalar_kernel(const double* __restrict__ x, long long xs, const int* __restrict__ match, long long mts, double* __restrict__ out,
+                                 int nb) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    out[b] = match[b * mts] > 0 ? x[b * xs] : 0.0;
+}
+
+}  // namespace tnsp
+
+using namespace tnsp;
+
+extern "C" int tnsp_rt_sort_i32(int n_edges, const int32_t* const* labels, const int64_t* lstrides, const int32_t* dims, const int32_t* signs,
+                                int64_t M, int32_t* table, int nbT, void* stream) {
+    if (n_edges > 8) { set_error("tnsp_rt_sort_i32: at most 8 edges per group"); return 1; }
+    if (M >= (1ll << 31)) { set_error("tnsp_rt_sort_i32: merged dimension beyond int32"); return 1; }
+    RtEdges E;
+    E.n = n_edges;
+    for (int i = 0; i < n_edges; ++i) { E.lab[i] = labels[i]; E.lstride[i] = lstrides[i]; E.dim[i] = dims[i]; E.sign[i] = signs[i]; }
+    if (nbT == 0) return 0;
+    rt_sort_kernel<<<nbT, kSortThreads, 0, (cudaStream_t)stream>>>(E, (int)M, table, RT_HDR + 2 * M);
+    return check_launch("tnsp_rt_sort_i32");
+}
+
+extern "C" int tnsp_rt_match_i32(const int32_t* rt, int64_t rt_stride, int rs, const int32_t* ct, int64_t ct_stride, int cs, const int32_t* t1,
+                                 int t1_stride, int s1, const int32_t* t2, int t2_stride, int s2, int32_t* match, int32_t* tsum, int nbm,
+                                 void* stream) {
+    if (nbm == 0) return 0;
+    rt_match_kernel<<<(nbm + 3) / 4, 128, 0, (cudaStream_t)stream>>>(rt, rt_stride, rs, ct, ct_stride, cs, t1, t1_stride, s1, t2, t2_stride, s2, match,
+                                                                     tsum, nbm);
+    return check_launch("tnsp_rt_match_i32");
+}
+
+extern "C" int tnsp_rt_repack_f64(const int32_t* plan, const tnsp_rt_form* src, const tnsp_rt_form* dst, double* dst_data, int64_t dst_stride,
+                                  int64_t work, int nb, void* stream) {
+    // src->rt == NULL: the source is a dense array (src->data, src->data_stride); dst->rt == NULL: the destination is dense with
+    // `work` elements per chain; otherwise `work` is an upper bound of the stored elements per chain (sizes the grid only)
+    if (nb == 0) return 0;
+    const bool sd = src->rt == nullptr, dd = dst->rt == nullptr;
+    int64_t gx = (work + kRepackThreads * 4 - 1) / (kRepackThreads * 4);
+    if (gx < 1) gx = 1;
+    if (gx > 4096) gx = 4096;
+    dim3 grid((unsigned)gx, (unsigned)nb);
+    const RtForm S = to_form(src), D = to_form(dst);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sd && dd) { set_error("tnsp_rt_repack_f64: one side must be sector-compact"); return 1; }
+    if (sd) rt_repack_kernel<true, false><<<grid, kRepackThreads, 0, st>>>(plan, S, D, dst_data, dst_stride, 0);
+    else if (dd) rt_repack_kernel<false, true><<<grid, kRepackThreads, 0, st>>>(plan, S, D, dst_data, dst_stride, work);
+    else rt_repack_kernel<false, false><<<grid, kRepackThreads, 0, st>>>(plan, S, D, dst_data, dst_stride, 0);
+    return check_launch("tnsp_rt_repack_f64");
+}
+
+extern "C" int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, const tnsp_rt_form* c, double* c_data, int64_t c_stride, int ksign,
+                                int nb, void* stream) {
+    if (nb == 0) return 0;
+    int64_t tiles = ((a->M + GT - 1) / GT) * ((b->N + GT - 1) / GT);
+    if (tiles < 1) tiles = 1;
+    if (tiles > 64) tiles = 64;
+    dim3 grid((unsigned)tiles, (unsigned)nb);
+    rt_gemm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(to_form(a), to_form(b), to_form(c), c_data, c_stride, ksign);
+    return check_launch("tnsp_rt_gemm_f64");
+}
+
+extern "C" int tnsp_rt_scale_f64(const double* x, int64_t x_stride, const int32_t* match, int64_t match_stride, const double* alpha, int alpha_stride,
+                                 int op, double* y, int64_t y_stride, int64_t cap, int nb, void* stream) {
+    if (nb == 0) return 0;
+    int64_t gx = (cap + 1023) / 1024;
+    gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
+    rt_scale_kernel<<<dim3((unsigned)gx, (unsigned)nb), 256, 0, (cudaStream_t)stream>>>(x, x_stride, match, match_stride, alpha, alpha_stride, op, y, y_stride);
+    return check_launch("tnsp_rt_scale_f64");
+}
+
+extern "C" int tnsp_rt_binary_f64(const double* x, int64_t x_stride, const double* w, int64_t w_stride, const int32_t* match, int64_t match_stride,
+                                  int op, double* y, int64_t y_stride, int64_t cap, int nb, void* stream) {
+    if (nb == 0) return 0;
+    int64_t gx = (cap + 1023) / 1024;
+    gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
+    rt_binary_kernel<<<dim3((unsigned)gx, (unsigned)nb), 256, 0, (cudaStream_t)stream>>>(x, x_stride, w, w_stride, match, match_stride, op, y, y_stride);
+    return check_launch("tnsp_rt_binary_f64");
+}
+
+extern "C" int tnsp_rt_norm_f64(const double* x, int64_t x_stride, const int32_t* match, int64_t match_stride, int kind, double* out, int nb,
+                                void* stream) {
+    if (nb == 0) return 0;
+    rt_norm_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(x, x_stride, match, match_stride, kind, out);
+    return check_launch("tnsp_rt_norm_f64");
+}
+
+extern "C" int tnsp_rt_scalar_f64(const double* x, int64_t x_stride, const int32_t* match, int64_t match_stride, double* out, int nb, void* stream) {
+    if (nb == 0) return 0;
+    rt_scalar_kernel<<<(nb + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, x_stride, match, match_stride, out, nb);
+    return check_launch("tnsp_rt_scalar_f64");
+}
