@@ -122,7 +122,7 @@ def test_lockstep_sector_equals_one_by_one_evaluation():
                 want = holes[l1][l2]
                 target = obs._Delta[l1][l2]
                 w = np.asarray(want.transpose(target.names).storage).reshape(-1)
-                g = np.atleast_2d(np.asarray(_blocks_of(holes_b[l1][l2].transpose(target.names), target)))[c]
+                g = np.atleast_2d(TAT.tensor._bk.get().to_numpy(_blocks_of(holes_b[l1][l2].transpose(target.names), target)))[c]
                 assert np.abs(g - w).max() <= RTOL * max(np.abs(w).max(), 1e-300)
     assert abs(obs_b._whole_result_reweight["energy"] - e_sum) <= 1e-9 * abs(e_sum)
 
