@@ -269,9 +269,15 @@ def run_own(args):
     L1, L2, Dc, desc = wl["L1"], wl["L2"], wl["Dc"], wl["desc"]
     nb = args.chains or wl["chains"]
     sym_lat, hopping, points = build_workload(TAT, wl)
+    sector = wl["sym"] != "No" and args.engine == "sector"
     if wl["sym"] == "No":
         lat = sym_lat
         conf0 = models.neel_configuration(L1, L2)
+    elif sector:
+        # symmetric PEPS run on sector-compact tensors: per-chain symmetry sectors, the reference's own sector plan (TAT/ragged.py)
+        from tnsp_b200.tetragono import dense_embedding
+        lat = sym_lat
+        conf0 = dense_embedding.embed_configuration(sym_lat, points)      # total physical indices [L1, L2, orbits]
     else:
         # symmetric PEPS enter the lock-step engine through the charge-dense embedding
         from tnsp_b200.tetragono import dense_embedding
@@ -381,15 +387,20 @@ def run_own(args):
     prof = None
     step()
     torch.cuda.synchronize()
+    rt_counts = None
     if rank == 0:
         from tnsp_b200 import profiling
         prof = profiling.KernelTimer(B)
         prof.enable()
+        if sector:
+            B.rt_stats(enable=1, reset=True)
     for _ in range(n_prof):
         step()
     torch.cuda.synchronize()
     if rank == 0:
         prof.disable()
+        if sector:
+            rt_counts = B.rt_stats(enable=0, read=True)
         breakdown = prof.summary()
         top_shapes = prof.shape_summary()
         peaks = {}
@@ -403,6 +414,23 @@ def run_own(args):
         except Exception:
             pass
         roofline = profiling.roofline_of_dominant(breakdown, peaks, top_shapes, traffic_table)
+        if sector:
+            dgemm = profiling.measure_fp64_gemm_tflops()
+            lines = profiling.sector_engine_rooflines(breakdown, rt_counts, peaks, dgemm)
+            name = max(lines, key=lambda k: lines[k]["seconds"])
+            top = lines[name]
+            hbm_peak = peaks.get("hbm_gbs") or 6650.0
+            if top["bound"] == "tensor":
+                ach, peak, unit = top["algorithmic_tflops"], dgemm, "TFLOP/s"
+            else:
+                ach, peak, unit = top["gbs"], hbm_peak, "GB/s"
+            roofline = {"kernel": name, "bound": top["bound"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
+                        "peak_source": ("MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6.65 TB/s (B200_PROFILING.md)")
+                        if unit == "GB/s" else "cuBLAS DGEMM 4096^3 measured in this run",
+                        "dgemm_peak_tflops": dgemm, "share_of_kernel_time": breakdown[name]["share"], "profiled_steps": n_prof,
+                        "work_counted": "on the device over exactly the timed launches (tnsp_rt_stats): GEMM algorithmic flops = sum over the "
+                                        "sector GEMMs of 2mnk (the reference plan, SURVEY 8d), executed = DMMA.8x8x4 issued x 512",
+                        "classes": lines}
 
     out = None
     if rank == 0:
@@ -412,7 +440,8 @@ def run_own(args):
             "data": "synthetic (randn_ PEPS seed 2333, Neel start, per-chain mt19937_64 seeds)",
             "config": {"workload": f"{args.workload}: {desc}", "chains_per_gpu": nb, "samples_per_step": nb * world,
                        "observer": "energy+gradient" + ("+SR natural gradient (CG %d)" % wl["cg"] if wl["sr"] else ""),
-                       "symmetric_engine": None if wl["sym"] == "No" else "charge-dense embedding, sectors discovered on device",
+                       "symmetric_engine": None if wl["sym"] == "No" else ("sector-compact tensors: per-chain symmetry sectors planned on the device"
+                                                                          if sector else "charge-dense embedding, sectors discovered on device"),
                        "l2": "working set of a step (all chains' environments) exceeds L2; no flush"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clock_info, "energy_per_site": energy[0],
@@ -431,6 +460,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0, help="Markov chains per GPU (lock-step batch); 0 = the workload's default")
     ap.add_argument("--ref-samples", type=int, default=8, help="samples per chain per step in the reference arm")
+    ap.add_argument("--engine", default="sector", choices=["sector", "dense"],
+                    help="lock-step engine of symmetric models: sector-compact tensors (default) or the charge-dense embedding of round 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -183,6 +183,20 @@ typedef struct {
     const int32_t* match; int64_t match_stride;
 } tnsp_rt_form;
 
+/* sector pairing computed INSIDE a consumer kernel instead of a tnsp_rt_match_i32 launch of its own: same rule, the table is
+ * written to match_out (chain stride match_out_stride) and the right-hand side to tsum_out (may be NULL) */
+typedef struct {
+    int rs, cs;
+    const int32_t* t1; int t1_stride, s1;
+    const int32_t* t2; int t2_stride, s2;
+    int32_t* match_out; int64_t match_out_stride;
+    int32_t* tsum_out;
+} tnsp_rt_match_spec;
+
+/* work counters for the bench's roofline (instrumented pass only): enable 0 / 1 (< 0: unchanged); out16 != NULL: copy the 16
+ * uint64 counters to the host (0 gemm algorithmic flops = sum 2mnk over the sectors, 1 gemm executed flops = DMMA issued x 512,
+ * 2 gemm algorithmic bytes, 3 repacked elements, 4 qr bytes, 5 qr flops, 6 svd bytes, 7 sectors factorised, 8 gemm sectors) */
+int tnsp_rt_stats(int enable, uint64_t* out16, int reset);
 /* merged edge of a group of <= 8 edges (edge_operator.hpp:321-404, per chain): key(r) = sum_e signs[e] * labels[e][chain][r_e] */
 int tnsp_rt_sort_i32(int n_edges, const int32_t* const* labels, const int64_t* lstrides, const int32_t* dims, const int32_t* signs,
                      int64_t M, int32_t* table, int nbT, void* stream);
@@ -193,12 +207,17 @@ int tnsp_rt_match_i32(const int32_t* rt, int64_t rt_stride, int rs, const int32_
 /* regroup (edge_operator.hpp:651-688): plan = int32 [2 + 3 (nr + nc)]: nr, nc, then per destination edge (rows, then cols,
  * slowest first) dimension, 1 if the edge sits in the source's column group, stride inside that source group.  src->rt == NULL:
  * dense source; dst->rt == NULL: dense destination of `work` elements; else `work` bounds the stored elements (grid size). */
-int tnsp_rt_repack_f64(const int32_t* plan, const tnsp_rt_form* src, const tnsp_rt_form* dst, double* dst_data, int64_t dst_stride,
-                       int64_t work, int nb, void* stream);
+int tnsp_rt_repack_f64(const int32_t* plan, const tnsp_rt_form* src, const tnsp_rt_form* dst, const tnsp_rt_match_spec* dst_match,
+                       double* dst_data, int64_t dst_stride, int64_t work, int nb, void* stream);
+/* two regroupings (the two operands of a contraction) in one launch; dst_match as above (NULL: dst->match is valid) */
+int tnsp_rt_repack_pair_f64(const int32_t* plan0, const tnsp_rt_form* src0, const tnsp_rt_form* dst0, const tnsp_rt_match_spec* match0,
+                            double* dst_data0, int64_t dst_stride0, int64_t work0, const int32_t* plan1, const tnsp_rt_form* src1,
+                            const tnsp_rt_form* dst1, const tnsp_rt_match_spec* match1, double* dst_data1, int64_t dst_stride1, int64_t work1,
+                            int nb, void* stream);
 /* ONE grouped GEMM over (chain x sector) (contract.hpp:582-616): for every row sector i of c (rows of a, columns of b):
  * C_i = A_i B_i', i' = the row sector of b whose charge is ksign * (charge of the column sector a pairs with i); zeros when absent */
-int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, const tnsp_rt_form* c, double* c_data, int64_t c_stride, int ksign,
-                     int nb, void* stream);
+int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, const tnsp_rt_form* c, const tnsp_rt_match_spec* c_match, double* c_data,
+                     int64_t c_stride, int ksign, int nb, void* stream);
 /* per-sector QR (kind 0; qr.hpp:178-304, common edge qr.hpp:419-429) / SVD with the global greedy cut (kind 2; svd.hpp:104-211,
  * 429-481) of every (chain, sector) matrix of f.  The bond label of row sector i on the first factor is
  * t1s * t1[chain] - fsign_rs * rowkey(i).  Three calls: _plan (labels of the QR bond, work queue, work-buffer layout), then the

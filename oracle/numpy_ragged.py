@@ -170,8 +170,15 @@ class RaggedMixin:
                 r += i * stride
         return r, c
 
-    def rt_repack(self, plan, src, dst):
+    def rt_repack_pair(self, plan0, src0, dst0, spec0, plan1, src1, dst1, spec1):
+        self.rt_repack(plan0, src0, dst0, spec0)
+        self.rt_repack(plan1, src1, dst1, spec1)
+
+    def rt_repack(self, plan, src, dst, match_spec=None):
         self.launches += 1
+        if match_spec is not None:
+            rs, cs, t1, s1, t2, s2 = match_spec
+            dst.match, _ = self.rt_match(dst.rt, rs, dst.ct, cs, t1, s1, t2, s2, 1)
         rows, cols = self._decode(plan)
         src_dense = isinstance(src, torch.Tensor)
         dst_dense = isinstance(dst, torch.Tensor)
@@ -229,8 +236,12 @@ class RaggedMixin:
             D[c, dst_pos] = val
 
     # ---- grouped GEMM over (chain, sector) --------------------------------------------------------------------------
-    def rt_gemm(self, A, B, C, ksign, nb):
+    def rt_gemm(self, A, B, C, ksign, nb, match_spec=None):
         self.launches += 1
+        tsum = None
+        if match_spec is not None:
+            rs, cs, t1, s1, t2, s2 = match_spec
+            C.match, tsum = self.rt_match(C.rt, rs, C.ct, cs, t1, s1, t2, s2, 1)
         Ad, Bd, Cd = _np(A.data), _np(B.data), _np(C.data)
         flops = 0
         for c in range(nb):
@@ -256,6 +267,7 @@ class RaggedMixin:
                         flops += 2 * m * n * k
                 _put(Cd[c], int(cm.moff[i]), out)
         self.rt_flops = getattr(self, "rt_flops", 0) + flops
+        return tsum
 
     # ---- per-sector factorisations ----------------------------------------------------------------------------------
     def rt_factor(self, kind, F, fsign, tt, tts, t1, t1s, kdim, remain_cut, relative_cut, nb):

@@ -121,47 +121,71 @@ class Core:
         return m
 
     def table(self, ids):
-        """(device table, sign) of the merged group `ids`: indices sorted by charge, per chain"""
+        """(device table, sign) of the merged group `ids`: indices sorted by charge, per chain.  Tables depend on the label arrays
+        only, so they are kept ON the first label array (shared by every tensor that carries these edges: site tensors, the
+        boundary tensors derived from them, both sides of a bond)."""
         got = self.tables.get(ids)
         if got is None:
             B = _bk.get()
             es = [self.edges[i] for i in ids]
-            g = es[0].sign if es else 1
-            STATS["sort"] += 1
-            tab = B.rt_sort([(e.arr, e.sign * g, e.dim) for e in es])
-            got = self.tables[ids] = (tab, g)
+            if not es:
+                got = (_empty_table(), 1)
+            else:
+                g = es[0].sign
+                key = tuple((id(e.arr), e.sign * g) for e in es)
+                store = es[0].arr.__dict__.setdefault("_rt_tables", {})
+                hit = store.get(key)
+                if hit is None:
+                    STATS["sort"] += 1
+                    hit = store[key] = (B.rt_sort([(e.arr, e.sign * g, e.dim) for e in es]), tuple(e.arr for e in es))
+                got = (hit[0], g)
+            self.tables[ids] = got
         return got
 
     def form(self, rows, cols):
-        """the storage regrouped as rows | cols (cached; built from the primary form by one repack)"""
-        key = (rows, cols)
-        f = self.forms.get(key)
+        """the storage regrouped as rows | cols (cached; built from the primary form by one launch that also pairs the sectors)"""
+        f = self.forms.get((rows, cols))
         if f is not None:
             return f
+        f, job = self.form_job(rows, cols)
+        _bk.get().rt_repack(*job)
+        return f
+
+    def form_job(self, rows, cols):
+        """(form, arguments of the rt_repack launch that fills it): lets a contraction regroup both operands in ONE launch"""
         B = _bk.get()
         rt, rs = self.table(rows)
         ct, cs = self.table(cols)
-        STATS["match"] += 1
-        match, _ = B.rt_match(rt, rs, ct, cs, self.target, self.tsign, None, 0, self.nb if self.target is not None else max(rt.shape[0], ct.shape[0]))
         M, N = self.group_dim(rows), self.group_dim(cols)
         src = self.forms[self.primary]
-        data = B.rt_alloc(max(src.data.shape[0], match.shape[0]), M * N)
-        f = Form(rows, cols, rt, rs, ct, cs, match, data, M, N)
+        nbd = max(src.data.shape[0], src.match.shape[0], rt.shape[0], ct.shape[0], 1 if self.target is None else self.target.shape[0])
+        f = Form(rows, cols, rt, rs, ct, cs, None, B.rt_alloc(nbd, M * N), M, N)
         STATS["repack"] += 1
-        B.rt_repack(_repack_plan(self, src, f), src, f)
         if len(self.forms) >= 4:          # keep the primary and the most recent regroupings only
             for k in list(self.forms):
                 if k != self.primary:
                     del self.forms[k]
                     break
-        self.forms[key] = f
-        return f
+        self.forms[(rows, cols)] = f
+        return f, (_repack_plan(self, src, f), src, f, (rs, cs, self.target, self.tsign, None, 0))
 
     def set_primary(self, f):
         self.forms[(f.rows, f.cols)] = f
         self.primary = (f.rows, f.cols)
         self.tables.setdefault(f.rows, (f.rt, f.rs))
         self.tables.setdefault(f.cols, (f.ct, f.cs))
+
+
+_EMPTY = {}
+
+
+def _empty_table():
+    """table of the empty edge group (one merged index of charge 0)"""
+    B = _bk.get()
+    t = _EMPTY.get(id(B))
+    if t is None:
+        t = _EMPTY[id(B)] = B.rt_sort([])
+    return t
 
 
 def _repack_plan(core, src, dst):
@@ -521,8 +545,14 @@ def _contract(a, b, pairs):
         p = _PLANS[key] = (tuple(i for i in fa if not ea[i].unit), tuple(ka), tuple(kb), tuple(j for j in fb if not eb[j].unit),
                            tuple(fa), tuple(fb), [a.names[i] for i in fa] + [b.names[j] for j in fb])
     fa_n, ka, kb, fb_n, fa, fb, names = p
-    A = a.core.form(fa_n, ka)
-    Bf = b.core.form(kb, fb_n)
+    A, Bf = a.core.forms.get((fa_n, ka)), b.core.forms.get((kb, fb_n))
+    if A is None and Bf is None and a.core is not b.core:
+        A, job_a = a.core.form_job(fa_n, ka)
+        Bf, job_b = b.core.form_job(kb, fb_n)
+        B.rt_repack_pair(*job_a, *job_b)
+    else:
+        A = a.core.form(fa_n, ka) if A is None else A
+        Bf = b.core.form(kb, fb_n) if Bf is None else Bf
     nb = max(a.core.nb, b.core.nb)
     # result core: free edges of a, then of b, with the operands' conjugation signs folded in
     edges = [a.core.edges[i].flipped(a.sign) for i in fa] + [b.core.edges[j].flipped(b.sign) for j in fb]
@@ -534,13 +564,12 @@ def _contract(a, b, pairs):
     rows = tuple(pos[("a", i)] for i in fa_n)
     cols = tuple(pos[("b", j)] for j in fb_n)
     rs, cs = A.rs * a.sign, Bf.cs * b.sign
-    nbm = nb if (a.core.target is not None or b.core.target is not None) else max(A.rt.shape[0], Bf.ct.shape[0])
-    STATS["match"] += 1
-    match, target = B.rt_match(A.rt, rs, Bf.ct, cs, a.core.target, a.core.tsign * a.sign, b.core.target, b.core.tsign * b.sign, nbm)
+    nb = max(nb, A.match.shape[0], Bf.match.shape[0])
     data = B.rt_alloc(nb, A.M * Bf.N)
-    C = Form(rows, cols, A.rt, rs, Bf.ct, cs, match, data, A.M, Bf.N)
+    C = Form(rows, cols, A.rt, rs, Bf.ct, cs, None, data, A.M, Bf.N)
     ksign = -(a.sign * A.cs) * (b.sign * Bf.rs)
-    B.rt_gemm(A, Bf, C, ksign, nb)
+    # ONE launch: sector pairing of the result (rows of a, columns of b, summed targets) + every sector GEMM of every chain
+    target = B.rt_gemm(A, Bf, C, ksign, nb, (rs, cs, a.core.target, a.core.tsign * a.sign, b.core.target, b.core.tsign * b.sign))
     core = Core(edges, nb, target, 1)
     core.set_primary(C)
     return RTensor(names, core, 1)

@@ -40,6 +40,12 @@ class RtForm(ctypes.Structure):
                 ("N", c_i64), ("match", c_vp), ("match_stride", c_i64)]
 
 
+class RtMatchSpec(ctypes.Structure):
+    """tnsp_rt_match_spec: sector pairing computed inside the consumer kernel"""
+    _fields_ = [("rs", c_int), ("cs", c_int), ("t1", c_vp), ("t1_stride", c_int), ("s1", c_int), ("t2", c_vp), ("t2_stride", c_int), ("s2", c_int),
+                ("match_out", c_vp), ("match_out_stride", c_i64), ("tsum_out", c_vp)]
+
+
 RT_SMAX = 64
 RT_HDR = 3 + 2 * RT_SMAX
 RT_MSTRIDE = 4 + 2 * RT_SMAX
@@ -121,8 +127,10 @@ class CudaBackend:
         FP = ctypes.POINTER(RtForm)
         lib.tnsp_rt_sort_i32.argtypes = [c_int, P, P, P, P, c_i64, P, c_int, P]
         lib.tnsp_rt_match_i32.argtypes = [P, c_i64, c_int, P, c_i64, c_int, P, c_int, c_int, P, c_int, c_int, P, P, c_int, P]
-        lib.tnsp_rt_repack_f64.argtypes = [P, FP, FP, P, c_i64, c_i64, c_int, P]
-        lib.tnsp_rt_gemm_f64.argtypes = [FP, FP, FP, P, c_i64, c_int, c_int, P]
+        SP = ctypes.POINTER(RtMatchSpec)
+        lib.tnsp_rt_repack_f64.argtypes = [P, FP, FP, SP, P, c_i64, c_i64, c_int, P]
+        lib.tnsp_rt_repack_pair_f64.argtypes = [P, FP, FP, SP, P, c_i64, c_i64, P, FP, FP, SP, P, c_i64, c_i64, c_int, P]
+        lib.tnsp_rt_gemm_f64.argtypes = [FP, FP, FP, SP, P, c_i64, c_int, c_int, P]
         lib.tnsp_rt_factor_ws_ints.restype = c_i64
         lib.tnsp_rt_factor_ws_ints.argtypes = [c_i64]
         lib.tnsp_rt_svd_work_doubles.restype = c_i64
@@ -137,6 +145,7 @@ class CudaBackend:
         lib.tnsp_rt_binary_f64.argtypes = [P, c_i64, P, c_i64, P, c_i64, c_int, P, c_i64, c_i64, c_int, P]
         lib.tnsp_rt_norm_f64.argtypes = [P, c_i64, P, c_i64, c_int, P, c_int, P]
         lib.tnsp_rt_scalar_f64.argtypes = [P, c_i64, P, c_i64, P, c_int, P]
+        lib.tnsp_rt_stats.argtypes = [c_int, P, c_int]
 
     @staticmethod
     def _st(t):
@@ -178,24 +187,78 @@ class CudaBackend:
                                             match.data_ptr(), None if tsum is None else tsum.data_ptr(), nbm, self._stream()))
         return match, tsum
 
-    def rt_repack(self, plan, src, dst):
+    def _spec(self, f, spec, nbm, want_tsum):
+        """spec = (rs, cs, t1, s1, t2, s2): allocate the match table of form `f` (and the summed target), to be filled by the kernel"""
+        rs, cs, t1, s1, t2, s2 = spec
+        nbm = max(int(nbm), f.rt.shape[0], f.ct.shape[0], 1 if t1 is None else t1.shape[0], 1 if t2 is None else t2.shape[0])
+        f.match = torch.empty((nbm, RT_MSTRIDE), dtype=torch.int32, device=self.device)
+        tsum = torch.empty(nbm, dtype=torch.int32, device=self.device) if (want_tsum and (t1 is not None or t2 is not None)) else None
+        c = RtMatchSpec(int(rs), int(cs), None if t1 is None else t1.data_ptr(), 0 if t1 is None or t1.shape[0] == 1 else 1, int(s1),
+                        None if t2 is None else t2.data_ptr(), 0 if t2 is None or t2.shape[0] == 1 else 1, int(s2),
+                        f.match.data_ptr(), self._st(f.match), None if tsum is None else tsum.data_ptr())
+        return c, tsum
+
+    def rt_repack(self, plan, src, dst, match_spec=None):
+        """regroup src -> dst; with match_spec the destination's sector pairing is computed by the same launch (dst.match is set)"""
         dst_dense = isinstance(dst, torch.Tensor)
         out = dst if dst_dense else dst.data
         nb = out.shape[0]
         if not isinstance(src, torch.Tensor):
             nb = max(nb, src.match.shape[0])
+        spec = None
+        if match_spec is not None:
+            spec, _ = self._spec(dst, match_spec, 1, False)
+            nb = max(nb, dst.match.shape[0])
         work = out.shape[1] if dst_dense else dst.M * dst.N + RT_SMAX
         fs, fd = self._form(src), self._form(dst)
-        self._ck(self.lib.tnsp_rt_repack_f64(plan.data_ptr(), ctypes.byref(fs), ctypes.byref(fd), out.data_ptr(), out.stride(0), int(work), nb,
-                                             self._stream()))
+        self._ck(self.lib.tnsp_rt_repack_f64(plan.data_ptr(), ctypes.byref(fs), ctypes.byref(fd), None if spec is None else ctypes.byref(spec),
+                                             out.data_ptr(), out.stride(0), int(work), nb, self._stream()))
 
-    def rt_gemm(self, A, B, C, ksign, nb):
+    def rt_repack_pair(self, plan0, src0, dst0, spec0, plan1, src1, dst1, spec1):
+        """the two regroupings of a contraction in one launch"""
+        s0, _ = self._spec(dst0, spec0, 1, False)
+        s1, _ = self._spec(dst1, spec1, 1, False)
+        nb = max(dst0.data.shape[0], dst1.data.shape[0], src0.match.shape[0], src1.match.shape[0], dst0.match.shape[0], dst1.match.shape[0])
+        f = [self._form(x) for x in (src0, dst0, src1, dst1)]
+        self._ck(self.lib.tnsp_rt_repack_pair_f64(plan0.data_ptr(), ctypes.byref(f[0]), ctypes.byref(f[1]), ctypes.byref(s0), dst0.data.data_ptr(),
+                                                  dst0.data.stride(0), dst0.M * dst0.N + RT_SMAX, plan1.data_ptr(), ctypes.byref(f[2]),
+                                                  ctypes.byref(f[3]), ctypes.byref(s1), dst1.data.data_ptr(), dst1.data.stride(0),
+                                                  dst1.M * dst1.N + RT_SMAX, nb, self._stream()))
+
+    def rt_gemm(self, A, B, C, ksign, nb, match_spec=None):
+        """C = A B per (chain, sector); with match_spec C's sector pairing (and summed target, returned) come out of the same launch"""
+        spec, tsum = (None, None)
+        if match_spec is not None:
+            spec, tsum = self._spec(C, match_spec, 1, True)
         fa, fb, fc = self._form(A), self._form(B), self._form(C)
-        self._ck(self.lib.tnsp_rt_gemm_f64(ctypes.byref(fa), ctypes.byref(fb), ctypes.byref(fc), C.data.data_ptr(), C.data.stride(0), int(ksign),
-                                           nb, self._stream()))
+        self._ck(self.lib.tnsp_rt_gemm_f64(ctypes.byref(fa), ctypes.byref(fb), ctypes.byref(fc), None if spec is None else ctypes.byref(spec),
+                                           C.data.data_ptr(), C.data.stride(0), int(ksign), nb, self._stream()))
+        return tsum
+
+    # the factorisation is a short fixed sequence of launches; each step is a method of its own so that the bench's instrumented
+    # pass can time the kernel classes separately (profiling.KernelTimer)
+    def rt_factor_plan(self, ff, code, frs, t1p, t1st, t1s, kd, labels, ws, wss, nb):
+        self._ck(self.lib.tnsp_rt_factor_plan(ctypes.byref(ff), code, frs, t1p, t1st, t1s, kd, labels.data_ptr(), ws.data_ptr(), wss, nb, self._stream()))
+
+    def rt_qr_work(self, ff, frs, t1p, t1st, t1s, tab, m_first, first, m_second, second, nb):
+        self._ck(self.lib.tnsp_rt_qr_f64(ctypes.byref(ff), frs, t1p, t1st, t1s, tab.data_ptr(), self._st(tab), m_first.data_ptr(), first.data_ptr(),
+                                         first.stride(0), m_second.data_ptr(), second.data_ptr(), second.stride(0), nb, self._stream()))
+
+    def rt_svd_work(self, ff, work, ws, wss, nb):
+        self._ck(self.lib.tnsp_rt_svd_work_f64(ctypes.byref(ff), work.data_ptr(), work.stride(0), ws.data_ptr(), wss, nb, self._stream()))
+
+    def rt_svd_finish(self, ff, frs, t1p, t1st, t1s, kd, remain_cut, relative_cut, work, labels, ws, wss, nb):
+        self._ck(self.lib.tnsp_rt_svd_finish_f64(ctypes.byref(ff), frs, t1p, t1st, t1s, kd, int(min(remain_cut, 1 << 40)), float(relative_cut),
+                                                 work.data_ptr(), work.stride(0), labels.data_ptr(), ws.data_ptr(), wss, nb, self._stream()))
+
+    def rt_svd_scatter(self, ff, frs, t1p, t1st, t1s, tab, m_first, first, m_s, s_data, m_second, second, work, ws, wss, nb):
+        self._ck(self.lib.tnsp_rt_svd_scatter_f64(ctypes.byref(ff), frs, t1p, t1st, t1s, tab.data_ptr(), self._st(tab), m_first.data_ptr(),
+                                                  first.data_ptr(), first.stride(0), m_s.data_ptr(), s_data.data_ptr(), s_data.stride(0),
+                                                  m_second.data_ptr(), second.data_ptr(), second.stride(0), work.data_ptr(), work.stride(0),
+                                                  ws.data_ptr(), wss, nb, self._stream()))
 
     def rt_factor(self, kind, F, fsign, tt, tts, t1, t1s, kdim, remain_cut, relative_cut, nb):
-        lib, st = self.lib, self._stream()
+        lib = self.lib
         kd = max(int(kdim), 1)
         kfull = max(min(F.M, F.N), 1)
         frs = int(fsign) * int(F.rs)
@@ -207,12 +270,11 @@ class CudaBackend:
         ws = torch.empty((nb, wss), dtype=torch.int32, device=self.device)
         labels = torch.empty((nb, kd), dtype=torch.int32, device=self.device)
         code = 0 if kind == "qr" else 2
-        self._ck(lib.tnsp_rt_factor_plan(ctypes.byref(ff), code, frs, t1p, t1st, t1s, kd, labels.data_ptr(), ws.data_ptr(), wss, nb, st))
+        self.rt_factor_plan(ff, code, frs, t1p, t1st, t1s, kd, labels, ws, wss, nb)
         if code == 2:
             work = torch.empty((nb, int(lib.tnsp_rt_svd_work_doubles(F.M, F.N))), dtype=torch.float64, device=self.device)
-            self._ck(lib.tnsp_rt_svd_work_f64(ctypes.byref(ff), work.data_ptr(), work.stride(0), ws.data_ptr(), wss, nb, st))
-            self._ck(lib.tnsp_rt_svd_finish_f64(ctypes.byref(ff), frs, t1p, t1st, t1s, kd, int(min(remain_cut, 1 << 40)), float(relative_cut),
-                                                work.data_ptr(), work.stride(0), labels.data_ptr(), ws.data_ptr(), wss, nb, st))
+            self.rt_svd_work(ff, work, ws, wss, nb)
+            self.rt_svd_finish(ff, frs, t1p, t1st, t1s, kd, remain_cut, relative_cut, work, labels, ws, wss, nb)
         tab = self.rt_sort([(labels, 1, kd)])
         m_first, _ = self.rt_match(F.rt, F.rs * fsign, tab, 1, t1, t1s, None, 0, nb)
         m_second, _ = self.rt_match(tab, -1, F.ct, F.cs * fsign, tt, tts, t1, -t1s if t1 is not None else 0, nb)
@@ -220,17 +282,19 @@ class CudaBackend:
         second = self.rt_alloc(nb, kd * F.N)
         out = {"labels": labels, "bond_col": (tab, 1), "bond_row": (tab, -1), "first": (m_first, first), "second": (m_second, second)}
         if code == 0:
-            self._ck(lib.tnsp_rt_qr_f64(ctypes.byref(ff), frs, t1p, t1st, t1s, tab.data_ptr(), self._st(tab), m_first.data_ptr(), first.data_ptr(),
-                                        first.stride(0), m_second.data_ptr(), second.data_ptr(), second.stride(0), nb, st))
+            self.rt_qr_work(ff, frs, t1p, t1st, t1s, tab, m_first, first, m_second, second, nb)
             return out
         m_s, _ = self.rt_match(tab, -1, tab, 1, None, 0, None, 0, nb)
         s_data = self.rt_alloc(nb, kd * kd)
-        self._ck(lib.tnsp_rt_svd_scatter_f64(ctypes.byref(ff), frs, t1p, t1st, t1s, tab.data_ptr(), self._st(tab), m_first.data_ptr(),
-                                             first.data_ptr(), first.stride(0), m_s.data_ptr(), s_data.data_ptr(), s_data.stride(0),
-                                             m_second.data_ptr(), second.data_ptr(), second.stride(0), work.data_ptr(), work.stride(0),
-                                             ws.data_ptr(), wss, nb, st))
+        self.rt_svd_scatter(ff, frs, t1p, t1st, t1s, tab, m_first, first, m_s, s_data, m_second, second, work, ws, wss, nb)
         out["s"] = (m_s, s_data)
         return out
+
+    def rt_stats(self, enable=-1, read=False, reset=False):
+        """device work counters of the sector-compact kernels (include/tnsp_b200.h: tnsp_rt_stats); reading synchronises"""
+        out = (ctypes.c_uint64 * 16)() if read else None
+        self._ck(self.lib.tnsp_rt_stats(int(enable), out, int(bool(reset))))
+        return list(out) if read else None
 
     def rt_scale(self, data, match, vec, op):
         nb = max(data.shape[0], match.shape[0], vec.shape[0])

@@ -2092,7 +2092,7 @@ __host__ __device__ inline int64_t rt_ws_stride(int64_t kfull) { return RT_WS_HD
 // one thread per chain: bond layout of the chain + one work item per non-empty sector
 __global__ void __launch_bounds__(128) rt_factor_plan_kernel(RtForm F, int kind, int frs, const int* __restrict__ t1, int t1st, int t1s, int kdim,
                                                              int* __restrict__ labels, int* __restrict__ ws, long long wss, int* qctl,
-                                                             int2* __restrict__ qitems, long long qcap, int nb) {
+                                                             int2* __restrict__ qitems, long long qcap, int nb, unsigned long long* stats) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     const RtTab R(F.rt + b * F.rts), C(F.ct + b * F.cts);
@@ -2101,6 +2101,7 @@ __global__ void __launch_bounds__(128) rt_factor_plan_kernel(RtForm F, int kind,
     const int tq = t1 ? t1s * t1[(long long)b * t1st] : 0;
     const int nsec = max(R.nsec(), 0);
     int k0 = 0, uo = 0, vo = 0;
+    unsigned long long st_bytes = 0, st_flops = 0, st_n = 0;
     for (int i = 0; i < nsec; ++i) {
         int* e = w + RT_WS_HDR + RT_WS_SEC * i;
         const int j = Mt.mcol(i);
@@ -2116,12 +2117,20 @@ __global__ void __launch_bounds__(128) rt_factor_plan_kernel(RtForm F, int kind,
         int64_t need;
         if (kind == 2) { const int pp = m >= n ? m : n; need = svd_sector_need(pp, q); uo += m * q; vo += q * n; }
         else need = qr_sector_need(m, n);
+        st_n += 1;
+        if (kind == 2) st_bytes += 8ull * ((unsigned long long)m * n + (unsigned long long)m * q + (unsigned long long)q * n + q);
+        else { st_bytes += 8ull * (2ull * m * n + (unsigned long long)m * q + (unsigned long long)q * n); st_flops += 4ull * m * n * q; }
         k0 += q;
         const int cls = need > kQSmallDoubles ? 0 : (need > kQMidDoubles ? 1 : 2);
         const int at = atomicAdd(&qctl[cls], 1);
         qitems[(long long)cls * qcap + at] = make_int2(b, i);
     }
     w[0] = k0; w[1] = k0;
+    if (stats) {
+        atomicAdd(&stats[kind == 2 ? 6 : 4], st_bytes);
+        if (kind != 2) atomicAdd(&stats[5], st_flops);
+        atomicAdd(&stats[7], st_n);
+    }
     if (kind == 0)
         for (int t = k0; t < kdim; ++t) labels[(long long)b * kdim + t] = 1 << 30;    // dead bond indices
 }
@@ -2598,7 +2607,7 @@ extern "C" int tnsp_rt_factor_plan(const tnsp_rt_form* f, int kind, int fsign_rs
     if (rt_queue_prepare(nb, rt_scratch_need(f->M, f->N, kind), st, qcap)) return 1;
     cudaMemsetAsync(g_qws.qctl, 0, 8 * sizeof(int), st);
     rt_factor_plan_kernel<<<(nb + 127) / 128, 128, 0, st>>>(to_form(f), kind, fsign_rs, t1, t1_stride, t1s, (int)kdim, labels, ws, ws_stride,
-                                                            g_qws.qctl, g_qws.qitems, qcap, nb);
+                                                            g_qws.qctl, g_qws.qitems, qcap, nb, rt_stats_ptr());
     return check_launch("tnsp_rt_factor_plan");
 }
 

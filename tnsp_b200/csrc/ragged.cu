@@ -22,6 +22,10 @@
 
 namespace tnsp {
 
+static unsigned long long* g_stats_dev = nullptr;
+static int g_stats_on = 0;
+unsigned long long* rt_stats_ptr() { return g_stats_on ? g_stats_dev : nullptr; }
+
 // ------------------------------------------------------------------------------------------------
 // rt_sort: one CTA per chain
 // ------------------------------------------------------------------------------------------------
@@ -197,9 +201,14 @@ __global__ void __launch_bounds__(128) rt_match_kernel(const int* __restrict__ r
 constexpr int kRepackThreads = 256;
 constexpr int kPlanMax = 2 + 3 * 24;
 
+struct RtRepackArgs {
+    const int* plan; RtForm S, D; RtSpec spec; double* dst; long long dst_stride; long long dense_size;
+};
+struct RtRepackPair { RtRepackArgs a[2]; };
+
 template <bool SRC_DENSE, bool DST_DENSE>
-__global__ void __launch_bounds__(kRepackThreads) rt_repack_kernel(const int* __restrict__ plan, RtForm S, RtForm D, double* __restrict__ dst,
-                                                                   long long dst_stride, long long dense_size) {
+__device__ __forceinline__ void rt_repack_body(const int* __restrict__ plan, const RtForm& S, const RtForm& D, const RtSpec& spec,
+                                               double* __restrict__ dst, long long dst_stride, long long dense_size, unsigned long long* stats) {
     __shared__ int sp[kPlanMax];
     __shared__ int hdr[4][RT_HDR];
     __shared__ int mt[2][RT_MSTRIDE];
@@ -212,15 +221,18 @@ __global__ void __launch_bounds__(kRepackThreads) rt_repack_kernel(const int* __
     }
     if (!DST_DENSE) {
         for (int i = tid; i < RT_HDR; i += kRepackThreads) { hdr[2][i] = D.rt[b * D.rts + i]; hdr[3][i] = D.ct[b * D.cts + i]; }
-        for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mt[1][i] = D.match[b * D.mts + i];
+        if (!spec.on)
+            for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mt[1][i] = D.match[b * D.mts + i];
     }
     __syncthreads();
+    if (!DST_DENSE && spec.on) rt_match_cta(hdr[2], hdr[3], spec, b, mt[1], blockIdx.x == 0);
     const int nr = sp[0], nc = sp[1];
     const RtTab sR(hdr[0]), sC(hdr[1]), dR(hdr[2]), dC(hdr[3]);
     const RtMatch sM(mt[0]), dM(mt[1]);
     const long long total = DST_DENSE ? dense_size : (long long)dM.size();
     const double* src = S.data + (long long)b * S.dstride;
     double* out = dst + (long long)b * dst_stride;
+    if (stats && blockIdx.x == 0 && tid == 0) atomicAdd(&stats[3], (unsigned long long)total);
     const int* s_inv_r = SRC_DENSE ? nullptr : S.rt + b * S.rts + RT_HDR + S.M;
     const int* s_inv_c = SRC_DENSE ? nullptr : S.ct + b * S.cts + RT_HDR + S.N;
     const int* d_perm_r = DST_DENSE ? nullptr : D.rt + b * D.rts + RT_HDR;
@@ -276,6 +288,16 @@ __global__ void __launch_bounds__(kRepackThreads) rt_repack_kernel(const int* __
     }
 }
 
+template <bool SRC_DENSE, bool DST_DENSE>
+__global__ void __launch_bounds__(kRepackThreads) rt_repack_kernel(RtRepackArgs p, unsigned long long* stats) {
+    rt_repack_body<SRC_DENSE, DST_DENSE>(p.plan, p.S, p.D, p.spec, p.dst, p.dst_stride, p.dense_size, stats);
+}
+// the two operands of a contraction in one launch: blockIdx.z selects the operand
+__global__ void __launch_bounds__(kRepackThreads) rt_repack_pair_kernel(RtRepackPair p, unsigned long long* stats) {
+    const RtRepackArgs& q = p.a[blockIdx.z];
+    rt_repack_body<false, false>(q.plan, q.S, q.D, q.spec, q.dst, q.dst_stride, q.dense_size, stats);
+}
+
 // the binary search above lands on the LAST sector whose offset is <= e; sectors without partner share the offset of their
 // successor, so the last one with that offset is the one that owns the element (or the final sentinel)
 
@@ -291,7 +313,8 @@ constexpr int GK = 16;          // K slab
 constexpr int GLDA = GK + 4;    // conflict-free fragment reads
 constexpr int GLDB = GT + 8;
 
-__global__ void __launch_bounds__(128) rt_gemm_kernel(RtForm A, RtForm B, RtForm C, double* __restrict__ cdata, long long cstride, int ksign) {
+__global__ void __launch_bounds__(128) rt_gemm_kernel(RtForm A, RtForm B, RtForm C, RtSpec spec, double* __restrict__ cdata, long long cstride,
+                                                      int ksign, unsigned long long* stats) {
     __shared__ double As[GT * GLDA];
     __shared__ double Bs[GK * GLDB];
     __shared__ int hA[2][RT_HDR];       // A rows, A cols (k)
@@ -302,8 +325,11 @@ __global__ void __launch_bounds__(128) rt_gemm_kernel(RtForm A, RtForm B, RtForm
         hA[0][i] = A.rt[b * A.rts + i]; hA[1][i] = A.ct[b * A.cts + i];
         hB[0][i] = B.rt[b * B.rts + i]; hB[1][i] = B.ct[b * B.cts + i];
     }
-    for (int i = tid; i < RT_MSTRIDE; i += 128) { mA[i] = A.match[b * A.mts + i]; mB[i] = B.match[b * B.mts + i]; mC[i] = C.match[b * C.mts + i]; }
+    for (int i = tid; i < RT_MSTRIDE; i += 128) { mA[i] = A.match[b * A.mts + i]; mB[i] = B.match[b * B.mts + i]; }
+    if (!spec.on)
+        for (int i = tid; i < RT_MSTRIDE; i += 128) mC[i] = C.match[b * C.mts + i];
     __syncthreads();
+    if (spec.on) rt_match_cta(hA[0], hB[1], spec, b, mC, blockIdx.x == 0);
     const RtTab aR(hA[0]), aK(hA[1]), bK(hB[0]), bN(hB[1]);
     const RtMatch MA(mA), MB(mB), MC(mC);
     const double* a = A.data + (long long)b * A.dstride;
@@ -334,6 +360,17 @@ __global__ void __launch_bounds__(128) rt_gemm_kernel(RtForm A, RtForm B, RtForm
             }
         }
         const long long coff = MC.moff(i);
+        if (stats && blockIdx.x == 0 && tid == 0) {
+            unsigned long long issued = 0;
+            for (int t = 0; t < here; ++t) {
+                const int rr = min(GT, m - (t / tn) * GT), cc = min(GT, n - (t % tn) * GT);
+                issued += (unsigned long long)((rr + 15) / 16) * 2 * ((cc + 7) / 8) * ((k + 3) / 4);
+            }
+            atomicAdd(&stats[0], 2ull * m * n * k);
+            atomicAdd(&stats[1], issued * 512ull);
+            atomicAdd(&stats[2], 8ull * ((unsigned long long)m * k + (unsigned long long)k * n + (unsigned long long)m * n));
+            atomicAdd(&stats[8], 1ull);
+        }
         for (; tile < first + here; tile += gridDim.x) {
             const int t = tile - first;
             const int r0 = (t / tn) * GT, c0 = (t % tn) * GT;
@@ -453,6 +490,18 @@ __global__ void rt_scalar_kernel(const double* __restrict__ x, long long xs, con
 
 using namespace tnsp;
 
+extern "C" int tnsp_rt_stats(int enable, uint64_t* out16, int reset) {
+    // enable < 0: leave the switch alone; out16 != NULL: copy the counters to the host (synchronises); reset: zero them
+    if (!g_stats_dev) {
+        if (cudaMalloc(&g_stats_dev, 16 * sizeof(unsigned long long)) != cudaSuccess) { set_error("tnsp_rt_stats: cudaMalloc"); return 1; }
+        cudaMemset(g_stats_dev, 0, 16 * sizeof(unsigned long long));
+    }
+    if (enable >= 0) g_stats_on = enable;
+    if (out16 && cudaMemcpy(out16, g_stats_dev, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("tnsp_rt_stats: copy"); return 1; }
+    if (reset) cudaMemset(g_stats_dev, 0, 16 * sizeof(unsigned long long));
+    return 0;
+}
+
 extern "C" int tnsp_rt_sort_i32(int n_edges, const int32_t* const* labels, const int64_t* lstrides, const int32_t* dims, const int32_t* signs,
                                 int64_t M, int32_t* table, int nbT, void* stream) {
     if (n_edges > 8) { set_error("tnsp_rt_sort_i32: at most 8 edges per group"); return 1; }
@@ -474,33 +523,55 @@ extern "C" int tnsp_rt_match_i32(const int32_t* rt, int64_t rt_stride, int rs, c
     return check_launch("tnsp_rt_match_i32");
 }
 
-extern "C" int tnsp_rt_repack_f64(const int32_t* plan, const tnsp_rt_form* src, const tnsp_rt_form* dst, double* dst_data, int64_t dst_stride,
-                                  int64_t work, int nb, void* stream) {
+static dim3 repack_grid(int64_t work, int nb, int nz) {
+    int64_t gx = (work + kRepackThreads * 4 - 1) / (kRepackThreads * 4);
+    if (gx < 1) gx = 1;
+    if (gx > 4096) gx = 4096;
+    return dim3((unsigned)gx, (unsigned)nb, (unsigned)nz);
+}
+
+extern "C" int tnsp_rt_repack_f64(const int32_t* plan, const tnsp_rt_form* src, const tnsp_rt_form* dst, const tnsp_rt_match_spec* dst_match,
+                                  double* dst_data, int64_t dst_stride, int64_t work, int nb, void* stream) {
     // src->rt == NULL: the source is a dense array (src->data, src->data_stride); dst->rt == NULL: the destination is dense with
     // `work` elements per chain; otherwise `work` is an upper bound of the stored elements per chain (sizes the grid only)
     if (nb == 0) return 0;
     const bool sd = src->rt == nullptr, dd = dst->rt == nullptr;
-    int64_t gx = (work + kRepackThreads * 4 - 1) / (kRepackThreads * 4);
-    if (gx < 1) gx = 1;
-    if (gx > 4096) gx = 4096;
-    dim3 grid((unsigned)gx, (unsigned)nb);
-    const RtForm S = to_form(src), D = to_form(dst);
-    cudaStream_t st = (cudaStream_t)stream;
     if (sd && dd) { set_error("tnsp_rt_repack_f64: one side must be sector-compact"); return 1; }
-    if (sd) rt_repack_kernel<true, false><<<grid, kRepackThreads, 0, st>>>(plan, S, D, dst_data, dst_stride, 0);
-    else if (dd) rt_repack_kernel<false, true><<<grid, kRepackThreads, 0, st>>>(plan, S, D, dst_data, dst_stride, work);
-    else rt_repack_kernel<false, false><<<grid, kRepackThreads, 0, st>>>(plan, S, D, dst_data, dst_stride, 0);
+    RtRepackArgs p;
+    p.plan = plan; p.S = to_form(src); p.D = to_form(dst); p.spec = to_spec(dst_match); p.dst = dst_data; p.dst_stride = dst_stride;
+    p.dense_size = dd ? work : 0;
+    const dim3 grid = repack_grid(work, nb, 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sd) rt_repack_kernel<true, false><<<grid, kRepackThreads, 0, st>>>(p, rt_stats_ptr());
+    else if (dd) rt_repack_kernel<false, true><<<grid, kRepackThreads, 0, st>>>(p, rt_stats_ptr());
+    else rt_repack_kernel<false, false><<<grid, kRepackThreads, 0, st>>>(p, rt_stats_ptr());
     return check_launch("tnsp_rt_repack_f64");
 }
 
-extern "C" int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, const tnsp_rt_form* c, double* c_data, int64_t c_stride, int ksign,
-                                int nb, void* stream) {
+extern "C" int tnsp_rt_repack_pair_f64(const int32_t* plan0, const tnsp_rt_form* src0, const tnsp_rt_form* dst0, const tnsp_rt_match_spec* match0,
+                                       double* dst_data0, int64_t dst_stride0, int64_t work0, const int32_t* plan1, const tnsp_rt_form* src1,
+                                       const tnsp_rt_form* dst1, const tnsp_rt_match_spec* match1, double* dst_data1, int64_t dst_stride1,
+                                       int64_t work1, int nb, void* stream) {
+    if (nb == 0) return 0;
+    if (!src0->rt || !dst0->rt || !src1->rt || !dst1->rt) { set_error("tnsp_rt_repack_pair_f64: both regroupings must be sector-compact"); return 1; }
+    RtRepackPair p;
+    p.a[0].plan = plan0; p.a[0].S = to_form(src0); p.a[0].D = to_form(dst0); p.a[0].spec = to_spec(match0); p.a[0].dst = dst_data0;
+    p.a[0].dst_stride = dst_stride0; p.a[0].dense_size = 0;
+    p.a[1].plan = plan1; p.a[1].S = to_form(src1); p.a[1].D = to_form(dst1); p.a[1].spec = to_spec(match1); p.a[1].dst = dst_data1;
+    p.a[1].dst_stride = dst_stride1; p.a[1].dense_size = 0;
+    rt_repack_pair_kernel<<<repack_grid(work0 > work1 ? work0 : work1, nb, 2), kRepackThreads, 0, (cudaStream_t)stream>>>(p, rt_stats_ptr());
+    return check_launch("tnsp_rt_repack_pair_f64");
+}
+
+extern "C" int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, const tnsp_rt_form* c, const tnsp_rt_match_spec* c_match,
+                                double* c_data, int64_t c_stride, int ksign, int nb, void* stream) {
     if (nb == 0) return 0;
     int64_t tiles = ((a->M + GT - 1) / GT) * ((b->N + GT - 1) / GT);
     if (tiles < 1) tiles = 1;
     if (tiles > 64) tiles = 64;
     dim3 grid((unsigned)tiles, (unsigned)nb);
-    rt_gemm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(to_form(a), to_form(b), to_form(c), c_data, c_stride, ksign);
+    rt_gemm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(to_form(a), to_form(b), to_form(c), to_spec(c_match), c_data, c_stride, ksign,
+                                                           rt_stats_ptr());
     return check_launch("tnsp_rt_gemm_f64");
 }
 

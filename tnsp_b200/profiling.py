@@ -13,7 +13,11 @@ def _nb(t):
 
 class KernelTimer:
     CLASSES = ("pack", "gemm", "gemm_gather", "qr", "svd", "svd_cut", "norm", "scale", "binary", "unary", "gather_rows", "select", "grad_accumulate",
-               "diag_scatter", "block_sign", "svd_mask")
+               "diag_scatter", "block_sign", "svd_mask",
+               # sector-compact engine (TAT/ragged.py): algorithmic work of these classes is counted ON THE DEVICE (per-chain sector
+               # sizes are never known to the host): backend.rt_stats
+               "rt_sort", "rt_match", "rt_repack", "rt_gemm", "rt_factor_plan", "rt_qr_work", "rt_svd_work", "rt_svd_finish", "rt_svd_scatter",
+               "rt_scale", "rt_binary", "rt_norm", "rt_scalar")
 
     def __init__(self, backend):
         self.B = backend
@@ -62,7 +66,9 @@ class KernelTimer:
 
     def enable(self):
         for name in self.CLASSES:
-            fn = getattr(self.B, name)
+            fn = getattr(self.B, name, None)
+            if fn is None:
+                continue
             self._orig[name] = fn
 
             def wrapped(*args, _fn=fn, _name=name, **kw):
@@ -72,7 +78,10 @@ class KernelTimer:
                 e1.record()
                 by, fl = self._work(_name, args)
                 self.records[_name].append((e0, e1, by, fl))
-                if _name in ("gemm", "gemm_gather", "qr", "svd"):
+                if _name == "rt_gemm":
+                    sig = (_name, 0, (int(args[0].M), int(args[1].N), int(args[0].N)), int(args[4]))
+                    self.shapes.setdefault(sig, []).append((e0, e1, fl, by))
+                elif _name in ("gemm", "gemm_gather", "qr", "svd"):
                     tab = args[0].gemm if _name == "gemm" else ([args[0].gather[2:5]] if _name == "gemm_gather" else args[0].sectors)
                     sig = (_name, len(tab), tuple(int(x) for x in tab[0][:3]), int(args[3 if _name.startswith('gemm') else 1].shape[0]))
                     self.shapes.setdefault(sig, []).append((e0, e1, fl, by))
@@ -183,3 +192,36 @@ def roofline_of_dominant(breakdown, peaks, top_shapes=None, traffic_table=None):
                               "instructions are issued, so a shape's rate may exceed the pipe's peak", **extra}
     return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
             "peak_source": which, **extra}
+
+
+def sector_engine_rooflines(breakdown, stats, peaks, dgemm_peak):
+    """roofline lines of the sector-compact engine from THIS run's timers and device counters (algorithmic GEMM work
+    = sum over the reference plan's sector GEMMs of 2 m n k; executed = DMMA.8x8x4 issued x 512):
+    stats = backend.rt_stats counters accumulated over exactly the launches `breakdown` timed."""
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    out = {}
+
+    def sec(name):
+        return breakdown[name]["ms"] * 1e-3 if name in breakdown else 0.0
+
+    t = sec("rt_gemm")
+    if t:
+        alg, issued, by = float(stats[0]), float(stats[1]), float(stats[2])
+        out["rt_gemm"] = {"bound": "hbm" if alg / max(by, 1.0) < 6.0 else "tensor", "seconds": t, "sector_gemms": int(stats[8]),
+                          "algorithmic_flops": alg, "executed_flops": issued, "executed_over_algorithmic": issued / alg if alg else None,
+                          "algorithmic_tflops": alg / t / 1e12, "frac_of_dgemm_peak": alg / t / 1e12 / dgemm_peak if dgemm_peak else None,
+                          "executed_frac_of_dgemm_peak": issued / t / 1e12 / dgemm_peak if dgemm_peak else None,
+                          "algorithmic_bytes": by, "gbs": by / t / 1e9, "frac_of_hbm_peak": by / t / 1e9 / hbm}
+    t = sec("rt_repack")
+    if t:
+        out["rt_repack"] = {"bound": "hbm", "seconds": t, "algorithmic_bytes": 16.0 * stats[3], "gbs": 16.0 * stats[3] / t / 1e9,
+                            "frac_of_hbm_peak": 16.0 * stats[3] / t / 1e9 / hbm}
+    t = sec("rt_qr_work")
+    if t:
+        out["rt_qr_work"] = {"bound": "hbm", "seconds": t, "algorithmic_bytes": float(stats[4]), "gbs": stats[4] / t / 1e9,
+                             "frac_of_hbm_peak": stats[4] / t / 1e9 / hbm, "flops": float(stats[5]), "tflops": stats[5] / t / 1e12}
+    t = sec("rt_svd_work")
+    if t:
+        out["rt_svd_work"] = {"bound": "hbm", "seconds": t, "algorithmic_bytes": float(stats[6]), "gbs": stats[6] / t / 1e9,
+                              "frac_of_hbm_peak": stats[6] / t / 1e9 / hbm, "note": "bytes of one pass; the Jacobi sweeps run in shared memory"}
+    return out

@@ -221,8 +221,8 @@ class Configuration(SingleLayerAuxiliaries):
         cache = self.owner.__dict__.setdefault("_ragged_sites", {})
         tensor = self.owner[l1, l2]
         got = cache.get((l1, l2))
-        if got is None or got[0] is not tensor:
-            got = cache[(l1, l2)] = (tensor, ragged.RTensor.from_symmetric(tensor, unit_names=("T",)))
+        if got is None or got[0] is not tensor or got[2] is not tensor._data:
+            got = cache[(l1, l2)] = (tensor, ragged.RTensor.from_symmetric(tensor, unit_names=("T",)), tensor._data)
         return got[1]
 
     def _shrink_configuration(self, l1l2, configuration):
