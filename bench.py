@@ -296,6 +296,11 @@ def run_own(args):
     o0.normalize_lattice()
     del s0, o0
 
+    if sector and nb > 148:
+        # buffer capacities of the sector-compact engine are learnt on a small throw-away batch first (TAT/ragged.py)
+        from tnsp_b200.tetragono.sampling import calibrate_sector_engine
+        calibrate_sector_engine(lat, Dc, conf0, hopping, chains=148, sweeps=2,
+                                observer_options=dict(enable_energy=True, enable_gradient=True, enable_natural_gradient=wl["sr"]))
     rng = ChainRng(nb)
     rng.seed([(2333 + rank * nb + c) % 2**31 for c in range(nb)])
     rng.uniform_real(None)

@@ -191,10 +191,11 @@ typedef struct {
     const int32_t* t2; int t2_stride, s2;
     int32_t* match_out; int64_t match_out_stride;
     int32_t* tsum_out;
+    int64_t cap;   /* elements the destination holds per chain; a chain that needs more is stored EMPTY and counted (0: unchecked) */
 } tnsp_rt_match_spec;
 
 /* work counters for the bench's roofline (instrumented pass only): enable 0 / 1 (< 0: unchanged); out16 != NULL: copy the 16
- * uint64 counters to the host (0 gemm algorithmic flops = sum 2mnk over the sectors, 1 gemm executed flops = DMMA issued x 512,
+ * uint64 counters to the host (15: chains dropped by a capacity check, cleared by reset == 2 only; 0 gemm algorithmic flops = sum 2mnk over the sectors, 1 gemm executed flops = DMMA issued x 512,
  * 2 gemm algorithmic bytes, 3 repacked elements, 4 qr bytes, 5 qr flops, 6 svd bytes, 7 sectors factorised, 8 gemm sectors) */
 int tnsp_rt_stats(int enable, uint64_t* out16, int reset);
 /* merged edge of a group of <= 8 edges (edge_operator.hpp:321-404, per chain): key(r) = sum_e signs[e] * labels[e][chain][r_e] */
@@ -203,7 +204,8 @@ int tnsp_rt_sort_i32(int n_edges, const int32_t* const* labels, const int64_t* l
 /* sector pairing rs * rowkey + cs * colkey = s1 * t1[chain] + s2 * t2[chain] (core.hpp:162-190; NULL targets count as 0);
  * tsum (may be NULL) receives the right-hand side */
 int tnsp_rt_match_i32(const int32_t* rt, int64_t rt_stride, int rs, const int32_t* ct, int64_t ct_stride, int cs, const int32_t* t1,
-                      int t1_stride, int s1, const int32_t* t2, int t2_stride, int s2, int32_t* match, int32_t* tsum, int nbm, void* stream);
+                      int t1_stride, int s1, const int32_t* t2, int t2_stride, int s2, int32_t* match, int32_t* tsum, int nbm, int64_t cap,
+                      void* stream);
 /* regroup (edge_operator.hpp:651-688): plan = int32 [2 + 3 (nr + nc)]: nr, nc, then per destination edge (rows, then cols,
  * slowest first) dimension, 1 if the edge sits in the source's column group, stride inside that source group.  src->rt == NULL:
  * dense source; dst->rt == NULL: dense destination of `work` elements; else `work` bounds the stored elements (grid size). */

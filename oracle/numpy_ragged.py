@@ -114,7 +114,7 @@ class RaggedMixin:
         return torch.from_numpy(out)
 
     # ---- sector pairing -------------------------------------------------------------------------------------------
-    def rt_match(self, rt, rs, ct, cs, t1, s1, t2, s2, nbm):
+    def rt_match(self, rt, rs, ct, cs, t1, s1, t2, s2, nbm, cap=0):
         self.launches += 1
         R, C = _np(rt), _np(ct)
         M, N = table_M(R), table_M(C)
@@ -145,6 +145,11 @@ class RaggedMixin:
                     off += off & 1          # sector matrices start at even element offsets (16-byte aligned bulk copies)
             row[2 + tr.nsec] = off
             row[0] = off
+            if cap and off > cap:          # learnt capacity exceeded: the chain is stored empty and counted
+                self.rt_overflows = getattr(self, "rt_overflows", 0) + 1
+                row[:] = 0
+                row[1] = 1
+                row[3 + SMAX:3 + 2 * SMAX] = -1
         return torch.from_numpy(out), (torch.from_numpy(tsum) if (t1 is not None or t2 is not None) else None)
 
     # ---- regroup --------------------------------------------------------------------------------------------------
@@ -178,7 +183,7 @@ class RaggedMixin:
         self.launches += 1
         if match_spec is not None:
             rs, cs, t1, s1, t2, s2 = match_spec
-            dst.match, _ = self.rt_match(dst.rt, rs, dst.ct, cs, t1, s1, t2, s2, 1)
+            dst.match, _ = self.rt_match(dst.rt, rs, dst.ct, cs, t1, s1, t2, s2, 1, dst.data.shape[1])
         rows, cols = self._decode(plan)
         src_dense = isinstance(src, torch.Tensor)
         dst_dense = isinstance(dst, torch.Tensor)
@@ -241,7 +246,7 @@ class RaggedMixin:
         tsum = None
         if match_spec is not None:
             rs, cs, t1, s1, t2, s2 = match_spec
-            C.match, tsum = self.rt_match(C.rt, rs, C.ct, cs, t1, s1, t2, s2, 1)
+            C.match, tsum = self.rt_match(C.rt, rs, C.ct, cs, t1, s1, t2, s2, 1, C.data.shape[1])
         Ad, Bd, Cd = _np(A.data), _np(B.data), _np(C.data)
         flops = 0
         for c in range(nb):
@@ -270,7 +275,13 @@ class RaggedMixin:
         return tsum
 
     # ---- per-sector factorisations ----------------------------------------------------------------------------------
-    def rt_factor(self, kind, F, fsign, tt, tts, t1, t1s, kdim, remain_cut, relative_cut, nb):
+    def rt_overflow(self, clear=True):
+        n = getattr(self, "rt_overflows", 0)
+        if clear:
+            self.rt_overflows = 0
+        return n
+
+    def rt_factor(self, kind, F, fsign, tt, tts, t1, t1s, kdim, remain_cut, relative_cut, nb, caps=None):
         """F = rows | cols storage of the tensor (effective labels = fsign * stored), (tt, tts) its target, (t1, t1s) the target
         of the first factor.  Bond label of row sector i on the first factor: lam = t1 - (row charge of i)."""
         self.launches += 1
@@ -325,12 +336,12 @@ class RaggedMixin:
         lab_t = torch.from_numpy(labels)
         tab = self.rt_sort([(lab_t, 1, kd)])
         out = {"labels": lab_t, "bond_col": (tab, 1), "bond_row": (tab, -1)}
-        m_first, _ = self.rt_match(F.rt, F.rs * fsign, tab, 1, t1, t1s, None, 0, nb)
-        m_second, _ = self.rt_match(tab, -1, F.ct, F.cs * fsign, tt, tts, t1, -t1s if t1 is not None else 0, nb)
-        m_s, _ = self.rt_match(tab, -1, tab, 1, None, 0, None, 0, nb)
-        first = self.rt_alloc(nb, F.M * kd)
-        second = self.rt_alloc(nb, kd * F.N)
+        first = self.rt_alloc(nb, caps[0] if caps else F.M * kd)
+        second = self.rt_alloc(nb, caps[1] if caps else kd * F.N)
         s_data = self.rt_alloc(nb, kd * kd)
+        m_first, _ = self.rt_match(F.rt, F.rs * fsign, tab, 1, t1, t1s, None, 0, nb, first.shape[1])
+        m_second, _ = self.rt_match(tab, -1, F.ct, F.cs * fsign, tt, tts, t1, -t1s if t1 is not None else 0, nb, second.shape[1])
+        m_s, _ = self.rt_match(tab, -1, tab, 1, None, 0, None, 0, nb, s_data.shape[1])
         fd, sd, ssd = first.numpy(), second.numpy(), s_data.numpy()
         for c in range(nb):
             tr, tc = Table(_row(_np(F.rt), c), F.M), Table(_row(_np(F.ct), c), F.N)
@@ -342,6 +353,8 @@ class RaggedMixin:
                     continue
                 i, j = x["i"], x["j"]
                 ib = tb.find(x["lam"])
+                if int(m1.mcol[i]) < 0 or int(m2.mcol[ib]) < 0:
+                    continue                     # (dropped by a capacity check)
                 assert ib >= 0 and tb.count(ib) == k and int(m1.mcol[i]) == ib, "rt_factor: first factor layout"
                 _put(fd[c], int(m1.moff[i]), x["first"][:, :k])
                 assert int(m2.mcol[ib]) == j, "rt_factor: second factor layout"

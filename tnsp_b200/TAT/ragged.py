@@ -38,6 +38,31 @@ STATS = {"contract": 0, "qr": 0, "svd": 0, "repack": 0, "sort": 0, "match": 0}
 
 _PLANS: dict = {}
 
+# Learnt capacities.  The stored size of a sector-compact tensor is only known on the device; allocating the dense bound
+# prod(dims) for every result would keep the zero-padded footprint of round 1 (165 GB at 592 chains of cfg2).  Every operation
+# signature therefore measures the largest per-chain size of its first CAP_LEARN executions (the only device -> host reads of the
+# engine, gone after the first sweep) and later allocates CAP_FACTOR x that.  A chain that still does not fit is stored EMPTY and
+# counted on the device (backend.rt_overflow, checked by the samplers once per sweep): never silent, never out of bounds.
+_CAPS: dict = {}
+CAP_LEARN = 3
+CAP_FACTOR = 2.0
+CAPS_ENABLED = True
+
+
+def _cap(key, dense):
+    """(elements to allocate, learning?)"""
+    c = _CAPS.get(key)
+    if not CAPS_ENABLED or c is None or c[0] < CAP_LEARN:
+        return dense, CAPS_ENABLED
+    return min(dense, int(c[1] * CAP_FACTOR) + 16), False
+
+
+def _learn(key, match):
+    B = _bk.get()
+    mx = int(B.to_numpy(match[:, 0]).max()) if match.shape[0] else 0
+    c = _CAPS.get(key)
+    _CAPS[key] = [1, mx] if c is None else [c[0] + 1, max(c[1], mx)]
+
 
 def pack_symmetry(sym):
     """integer label of a symmetry value: component i weighs 65536^i (sums of labels = labels of sums)"""
@@ -147,8 +172,10 @@ class Core:
         f = self.forms.get((rows, cols))
         if f is not None:
             return f
-        f, job = self.form_job(rows, cols)
+        f, job, ckey = self.form_job(rows, cols)
         _bk.get().rt_repack(*job)
+        if ckey is not None:
+            _learn(ckey, f.match)
         return f
 
     def form_job(self, rows, cols):
@@ -159,7 +186,9 @@ class Core:
         M, N = self.group_dim(rows), self.group_dim(cols)
         src = self.forms[self.primary]
         nbd = max(src.data.shape[0], src.match.shape[0], rt.shape[0], ct.shape[0], 1 if self.target is None else self.target.shape[0])
-        f = Form(rows, cols, rt, rs, ct, cs, None, B.rt_alloc(nbd, M * N), M, N)
+        ckey = ("form", tuple(e.dim for e in self.edges), src.rows, src.cols, rows, cols)
+        cap, learning = _cap(ckey, M * N)
+        f = Form(rows, cols, rt, rs, ct, cs, None, B.rt_alloc(nbd, cap), M, N)
         STATS["repack"] += 1
         if len(self.forms) >= 4:          # keep the primary and the most recent regroupings only
             for k in list(self.forms):
@@ -167,7 +196,7 @@ class Core:
                     del self.forms[k]
                     break
         self.forms[(rows, cols)] = f
-        return f, (_repack_plan(self, src, f), src, f, (rs, cs, self.target, self.tsign, None, 0))
+        return f, (_repack_plan(self, src, f), src, f, (rs, cs, self.target, self.tsign, None, 0)), (ckey if learning else None)
 
     def set_primary(self, f):
         self.forms[(f.rows, f.cols)] = f
@@ -547,9 +576,13 @@ def _contract(a, b, pairs):
     fa_n, ka, kb, fb_n, fa, fb, names = p
     A, Bf = a.core.forms.get((fa_n, ka)), b.core.forms.get((kb, fb_n))
     if A is None and Bf is None and a.core is not b.core:
-        A, job_a = a.core.form_job(fa_n, ka)
-        Bf, job_b = b.core.form_job(kb, fb_n)
+        A, job_a, key_a = a.core.form_job(fa_n, ka)
+        Bf, job_b, key_b = b.core.form_job(kb, fb_n)
         B.rt_repack_pair(*job_a, *job_b)
+        if key_a is not None:
+            _learn(key_a, A.match)
+        if key_b is not None:
+            _learn(key_b, Bf.match)
     else:
         A = a.core.form(fa_n, ka) if A is None else A
         Bf = b.core.form(kb, fb_n) if Bf is None else Bf
@@ -565,11 +598,14 @@ def _contract(a, b, pairs):
     cols = tuple(pos[("b", j)] for j in fb_n)
     rs, cs = A.rs * a.sign, Bf.cs * b.sign
     nb = max(nb, A.match.shape[0], Bf.match.shape[0])
-    data = B.rt_alloc(nb, A.M * Bf.N)
+    cap, learning = _cap(key, A.M * Bf.N)
+    data = B.rt_alloc(nb, cap)
     C = Form(rows, cols, A.rt, rs, Bf.ct, cs, None, data, A.M, Bf.N)
     ksign = -(a.sign * A.cs) * (b.sign * Bf.rs)
     # ONE launch: sector pairing of the result (rows of a, columns of b, summed targets) + every sector GEMM of every chain
     target = B.rt_gemm(A, Bf, C, ksign, nb, (rs, cs, a.core.target, a.core.tsign * a.sign, b.core.target, b.core.tsign * b.sign))
+    if learning:
+        _learn(key, C.match)
     core = Core(edges, nb, target, 1)
     core.set_primary(C)
     return RTensor(names, core, 1)
@@ -619,7 +655,13 @@ def _factor(t, first_names, kind, name_1, name_2, sing_1, sing_2, cut):
     else:
         t1, t1s = None, 0
     # bond labels + per-sector factorisation, all planned on the device
-    out = B.rt_factor(kind, F, t.sign, core.target, core.tsign * t.sign, t1, t1s, kdim, remain_cut, relative_cut, nb)
+    fkey = ("fac", kind, tuple(e.dim for e in core.edges), rows, cols, kdim)
+    c1, l1 = _cap(fkey + (1,), F.M * max(kdim, 1))
+    c2, l2 = _cap(fkey + (2,), max(kdim, 1) * F.N)
+    out = B.rt_factor(kind, F, t.sign, core.target, core.tsign * t.sign, t1, t1s, kdim, remain_cut, relative_cut, nb, (c1, c2))
+    if l1:
+        _learn(fkey + (1,), out["first"][0])
+        _learn(fkey + (2,), out["second"][0])
     lab = out["labels"]                      # device int32 [nb, kdim]: effective label of the bond on the first factor
     e1 = [core.edges[i].flipped(t.sign) for i in first]
     e2 = [core.edges[i].flipped(t.sign) for i in second]

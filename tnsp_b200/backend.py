@@ -43,7 +43,7 @@ class RtForm(ctypes.Structure):
 class RtMatchSpec(ctypes.Structure):
     """tnsp_rt_match_spec: sector pairing computed inside the consumer kernel"""
     _fields_ = [("rs", c_int), ("cs", c_int), ("t1", c_vp), ("t1_stride", c_int), ("s1", c_int), ("t2", c_vp), ("t2_stride", c_int), ("s2", c_int),
-                ("match_out", c_vp), ("match_out_stride", c_i64), ("tsum_out", c_vp)]
+                ("match_out", c_vp), ("match_out_stride", c_i64), ("tsum_out", c_vp), ("cap", c_i64)]
 
 
 RT_SMAX = 64
@@ -126,7 +126,7 @@ class CudaBackend:
         lib, P = self.lib, c_vp
         FP = ctypes.POINTER(RtForm)
         lib.tnsp_rt_sort_i32.argtypes = [c_int, P, P, P, P, c_i64, P, c_int, P]
-        lib.tnsp_rt_match_i32.argtypes = [P, c_i64, c_int, P, c_i64, c_int, P, c_int, c_int, P, c_int, c_int, P, P, c_int, P]
+        lib.tnsp_rt_match_i32.argtypes = [P, c_i64, c_int, P, c_i64, c_int, P, c_int, c_int, P, c_int, c_int, P, P, c_int, c_i64, P]
         SP = ctypes.POINTER(RtMatchSpec)
         lib.tnsp_rt_repack_f64.argtypes = [P, FP, FP, SP, P, c_i64, c_i64, c_int, P]
         lib.tnsp_rt_repack_pair_f64.argtypes = [P, FP, FP, SP, P, c_i64, c_i64, P, FP, FP, SP, P, c_i64, c_i64, c_int, P]
@@ -177,14 +177,14 @@ class CudaBackend:
         self._ck(self.lib.tnsp_rt_sort_i32(n, ptrs, strides, dims, signs, M, table.data_ptr(), nbT, self._stream()))
         return table
 
-    def rt_match(self, rt, rs, ct, cs, t1, s1, t2, s2, nbm):
+    def rt_match(self, rt, rs, ct, cs, t1, s1, t2, s2, nbm, cap=0):
         nbm = max(int(nbm), rt.shape[0], ct.shape[0], 1 if t1 is None else t1.shape[0], 1 if t2 is None else t2.shape[0])
         match = torch.empty((nbm, RT_MSTRIDE), dtype=torch.int32, device=self.device)
         tsum = torch.empty(nbm, dtype=torch.int32, device=self.device) if (t1 is not None or t2 is not None) else None
         self._ck(self.lib.tnsp_rt_match_i32(rt.data_ptr(), self._st(rt), int(rs), ct.data_ptr(), self._st(ct), int(cs),
                                             None if t1 is None else t1.data_ptr(), 0 if t1 is None or t1.shape[0] == 1 else 1, int(s1),
                                             None if t2 is None else t2.data_ptr(), 0 if t2 is None or t2.shape[0] == 1 else 1, int(s2),
-                                            match.data_ptr(), None if tsum is None else tsum.data_ptr(), nbm, self._stream()))
+                                            match.data_ptr(), None if tsum is None else tsum.data_ptr(), nbm, int(cap), self._stream()))
         return match, tsum
 
     def _spec(self, f, spec, nbm, want_tsum):
@@ -195,7 +195,7 @@ class CudaBackend:
         tsum = torch.empty(nbm, dtype=torch.int32, device=self.device) if (want_tsum and (t1 is not None or t2 is not None)) else None
         c = RtMatchSpec(int(rs), int(cs), None if t1 is None else t1.data_ptr(), 0 if t1 is None or t1.shape[0] == 1 else 1, int(s1),
                         None if t2 is None else t2.data_ptr(), 0 if t2 is None or t2.shape[0] == 1 else 1, int(s2),
-                        f.match.data_ptr(), self._st(f.match), None if tsum is None else tsum.data_ptr())
+                        f.match.data_ptr(), self._st(f.match), None if tsum is None else tsum.data_ptr(), int(f.data.shape[1]))
         return c, tsum
 
     def rt_repack(self, plan, src, dst, match_spec=None):
@@ -257,7 +257,7 @@ class CudaBackend:
                                                   m_second.data_ptr(), second.data_ptr(), second.stride(0), work.data_ptr(), work.stride(0),
                                                   ws.data_ptr(), wss, nb, self._stream()))
 
-    def rt_factor(self, kind, F, fsign, tt, tts, t1, t1s, kdim, remain_cut, relative_cut, nb):
+    def rt_factor(self, kind, F, fsign, tt, tts, t1, t1s, kdim, remain_cut, relative_cut, nb, caps=None):
         lib = self.lib
         kd = max(int(kdim), 1)
         kfull = max(min(F.M, F.N), 1)
@@ -276,19 +276,25 @@ class CudaBackend:
             self.rt_svd_work(ff, work, ws, wss, nb)
             self.rt_svd_finish(ff, frs, t1p, t1st, t1s, kd, remain_cut, relative_cut, work, labels, ws, wss, nb)
         tab = self.rt_sort([(labels, 1, kd)])
-        m_first, _ = self.rt_match(F.rt, F.rs * fsign, tab, 1, t1, t1s, None, 0, nb)
-        m_second, _ = self.rt_match(tab, -1, F.ct, F.cs * fsign, tt, tts, t1, -t1s if t1 is not None else 0, nb)
-        first = self.rt_alloc(nb, F.M * kd)
-        second = self.rt_alloc(nb, kd * F.N)
+        first = self.rt_alloc(nb, caps[0] if caps else F.M * kd)
+        second = self.rt_alloc(nb, caps[1] if caps else kd * F.N)
+        m_first, _ = self.rt_match(F.rt, F.rs * fsign, tab, 1, t1, t1s, None, 0, nb, first.shape[1])
+        m_second, _ = self.rt_match(tab, -1, F.ct, F.cs * fsign, tt, tts, t1, -t1s if t1 is not None else 0, nb, second.shape[1])
         out = {"labels": labels, "bond_col": (tab, 1), "bond_row": (tab, -1), "first": (m_first, first), "second": (m_second, second)}
         if code == 0:
             self.rt_qr_work(ff, frs, t1p, t1st, t1s, tab, m_first, first, m_second, second, nb)
             return out
-        m_s, _ = self.rt_match(tab, -1, tab, 1, None, 0, None, 0, nb)
         s_data = self.rt_alloc(nb, kd * kd)
+        m_s, _ = self.rt_match(tab, -1, tab, 1, None, 0, None, 0, nb, s_data.shape[1])
         self.rt_svd_scatter(ff, frs, t1p, t1st, t1s, tab, m_first, first, m_s, s_data, m_second, second, work, ws, wss, nb)
         out["s"] = (m_s, s_data)
         return out
+
+    def rt_overflow(self, clear=True):
+        """number of (chain, tensor) pairs dropped because their sectors did not fit a learnt capacity (synchronises)"""
+        out = (ctypes.c_uint64 * 16)()
+        self._ck(self.lib.tnsp_rt_stats(-1, out, 2 if clear else 0))
+        return int(out[15])
 
     def rt_stats(self, enable=-1, read=False, reset=False):
         """device work counters of the sector-compact kernels (include/tnsp_b200.h: tnsp_rt_stats); reading synchronises"""

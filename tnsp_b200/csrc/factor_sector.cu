@@ -2160,8 +2160,9 @@ __global__ void __launch_bounds__(kQBigThreads) rt_qr_work_kernel(RtForm F, int 
         const double* A = F.data + (long long)b * F.dstride + Mt.moff(i);
         const int tq = t1 ? t1s * t1[(long long)b * t1st] : 0;
         const int ib = Bd.find(tq - frs * R.skey(i));
-        double* O1 = first + (long long)b * fst + M1.moff(i);                      // ms x ks
-        double* O2 = ib >= 0 ? second + (long long)b * sst + M2.moff(ib) : nullptr;  // ks x ns
+        // (a factor whose sectors did not fit its learnt capacity is stored empty: mcol < 0, nothing is written)
+        double* O1 = M1.mcol(i) >= 0 ? first + (long long)b * fst + M1.moff(i) : nullptr;                      // ms x ks
+        double* O2 = (ib >= 0 && M2.mcol(ib) >= 0) ? second + (long long)b * sst + M2.moff(ib) : nullptr;  // ks x ns
         const int ld = q | 1;
         const int64_t need = qr_sector_need(p, q);
         double* W = (need <= cap) ? work : scratch + (int64_t)blockIdx.x * scratch_per_cta;
@@ -2182,11 +2183,13 @@ __global__ void __launch_bounds__(kQBigThreads) rt_qr_work_kernel(RtForm F, int 
             if constexpr (STAGED) householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm, Pan, Zp);
             else householder_qr_blocked(W, ld, p, q, ks, tau, Rc, Vp, Tm);
         } else householder_qr(W, ld, p, q, ks, tau, Rc, nullptr);
-        for (int e = tid; e < ms * ks; e += nt) {
-            const int r = e / ks, t = e - r * ks;
-            O1[e] = W[(int64_t)r * ld + t];
+        if (O1) {
+            for (int e = tid; e < ms * ks; e += nt) {
+                const int r = e / ks, t = e - r * ks;
+                O1[e] = W[(int64_t)r * ld + t];
+            }
+            if (tid == 0 && ((ms * ks) & 1)) O1[ms * ks] = 0.0;
         }
-        if (tid == 0 && ((ms * ks) & 1)) O1[ms * ks] = 0.0;
         if (O2) {
             for (int e = tid; e < ks * ns; e += nt) O2[e] = Rc[e];
             if (tid == 0 && ((ks * ns) & 1)) O2[ks * ns] = 0.0;
@@ -2345,7 +2348,7 @@ __global__ void __launch_bounds__(256) rt_svd_scatter_kernel(RtForm F, int frs, 
         const int j = Mt.mcol(i);
         const int ms = R.count(i), ns = C.count(j);
         const int ib = Bd.find(tq - frs * R.skey(i));
-        if (ib < 0) continue;
+        if (ib < 0 || M1.mcol(i) < 0 || M2.mcol(ib) < 0 || M3.mcol(ib) < 0) continue;     // (dropped by a capacity check)
         const double* sig = wg + e6[0];
         const double* Us = wg + kfull + e6[1];
         const double* Vs = wg + kfull + (long long)F.M * kfull + e6[2];

@@ -24,7 +24,11 @@ namespace tnsp {
 
 static unsigned long long* g_stats_dev = nullptr;
 static int g_stats_on = 0;
+static void stats_alloc() {
+    if (!g_stats_dev && cudaMalloc(&g_stats_dev, 16 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(g_stats_dev, 0, 16 * sizeof(unsigned long long));
+}
 unsigned long long* rt_stats_ptr() { return g_stats_on ? g_stats_dev : nullptr; }
+unsigned long long* rt_overflow_ptr() { stats_alloc(); return g_stats_dev ? g_stats_dev + 15 : nullptr; }
 
 // ------------------------------------------------------------------------------------------------
 // rt_sort: one CTA per chain
@@ -158,7 +162,8 @@ __global__ void __launch_bounds__(kSortThreads) rt_sort_kernel(RtEdges E, int M,
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) rt_match_kernel(const int* __restrict__ rt, long long rts, int rs, const int* __restrict__ ct, long long cts,
                                                        int cs, const int* __restrict__ t1, int t1s, int s1, const int* __restrict__ t2, int t2s,
-                                                       int s2, int* __restrict__ match, int* __restrict__ tsum, int nbm) {
+                                                       int s2, int* __restrict__ match, int* __restrict__ tsum, int nbm, long long cap,
+                                                       unsigned long long* flag) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= nbm) return;
@@ -188,10 +193,18 @@ __global__ void __launch_bounds__(128) rt_match_kernel(const int* __restrict__ r
         if (i < nr) { Mrow[2 + i] = carry + incl - sz; Mrow[3 + RT_SMAX + i] = j; }
         carry += __shfl_sync(0xffffffffu, incl, 31);
     }
+    const bool over = cap > 0 && carry > cap;
+    if (over) {
+        __syncwarp();
+        for (int i = lane; i <= nr; i += 32) Mrow[2 + i] = 0;
+        for (int i = lane; i < nr; i += 32) Mrow[3 + RT_SMAX + i] = -1;
+        if (lane == 0 && flag) atomicAdd(flag, 1ull);
+    }
     if (lane == 0) {
-        Mrow[2 + nr] = carry;
-        Mrow[0] = (R.nsec() < 0 || C.nsec() < 0) ? 0 : carry;
-        Mrow[1] = (R.nsec() < 0 || C.nsec() < 0) ? 1 : 0;      // sector overflow flag
+        if (!over) Mrow[2 + nr] = carry;
+        const bool bad = over || R.nsec() < 0 || C.nsec() < 0;
+        Mrow[0] = bad ? 0 : carry;
+        Mrow[1] = bad ? 1 : 0;      // sector / capacity overflow flag
     }
 }
 
@@ -492,13 +505,12 @@ using namespace tnsp;
 
 extern "C" int tnsp_rt_stats(int enable, uint64_t* out16, int reset) {
     // enable < 0: leave the switch alone; out16 != NULL: copy the counters to the host (synchronises); reset: zero them
-    if (!g_stats_dev) {
-        if (cudaMalloc(&g_stats_dev, 16 * sizeof(unsigned long long)) != cudaSuccess) { set_error("tnsp_rt_stats: cudaMalloc"); return 1; }
-        cudaMemset(g_stats_dev, 0, 16 * sizeof(unsigned long long));
-    }
+    stats_alloc();
+    if (!g_stats_dev) { set_error("tnsp_rt_stats: cudaMalloc"); return 1; }
     if (enable >= 0) g_stats_on = enable;
     if (out16 && cudaMemcpy(out16, g_stats_dev, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("tnsp_rt_stats: copy"); return 1; }
-    if (reset) cudaMemset(g_stats_dev, 0, 16 * sizeof(unsigned long long));
+    if (reset == 1) cudaMemset(g_stats_dev, 0, 15 * sizeof(unsigned long long));      // slot 15 (overflows) is only cleared by reset == 2
+    if (reset == 2) cudaMemset(g_stats_dev + 15, 0, sizeof(unsigned long long));
     return 0;
 }
 
@@ -516,10 +528,10 @@ extern "C" int tnsp_rt_sort_i32(int n_edges, const int32_t* const* labels, const
 
 extern "C" int tnsp_rt_match_i32(const int32_t* rt, int64_t rt_stride, int rs, const int32_t* ct, int64_t ct_stride, int cs, const int32_t* t1,
                                  int t1_stride, int s1, const int32_t* t2, int t2_stride, int s2, int32_t* match, int32_t* tsum, int nbm,
-                                 void* stream) {
+                                 int64_t cap, void* stream) {
     if (nbm == 0) return 0;
     rt_match_kernel<<<(nbm + 3) / 4, 128, 0, (cudaStream_t)stream>>>(rt, rt_stride, rs, ct, ct_stride, cs, t1, t1_stride, s1, t2, t2_stride, s2, match,
-                                                                     tsum, nbm);
+                                                                     tsum, nbm, cap, rt_overflow_ptr());
     return check_launch("tnsp_rt_match_i32");
 }
 

@@ -14,7 +14,8 @@ constexpr int RT_EMPTY = INT_MIN;
 // work counters of the instrumented bench pass (bench.py roofline): 0 gemm algorithmic flops (sum 2 m n k over the sectors),
 // 1 gemm executed flops (DMMA.8x8x4 issued x 512), 2 gemm algorithmic bytes 8 (mk + kn + mn), 3 repack elements, 4 qr bytes
 // 8 (2mn + mk + kn), 5 qr flops 4 m n k, 6 svd bytes 8 (mn + mk + kn + k), 7 sectors factorised, 8 gemm sectors
-unsigned long long* rt_stats_ptr();      // device pointer to the 16 counters, nullptr while the counters are switched off
+unsigned long long* rt_stats_ptr();
+unsigned long long* rt_overflow_ptr();    // device counter of chains dropped because their sectors did not fit the destination buffer      // device pointer to the 16 counters, nullptr while the counters are switched off
 
 // decoded view of one chain's group table
 struct RtTab {
@@ -64,13 +65,15 @@ struct RtSpec {
     const int* t2; int t2st, s2;
     int* out; long long outs;
     int* tsum;
+    long long cap;                  // elements the destination buffer holds per chain (0: not checked)
+    unsigned long long* flag;       // overflow counter: a chain whose sectors do not fit is stored EMPTY and counted here
 };
 inline RtSpec to_spec(const tnsp_rt_match_spec* p) {
     RtSpec r;
     r.on = p != nullptr;
     if (p) { r.rs = p->rs; r.cs = p->cs; r.t1 = p->t1; r.t1st = p->t1_stride; r.s1 = p->s1; r.t2 = p->t2; r.t2st = p->t2_stride; r.s2 = p->s2;
-             r.out = p->match_out; r.outs = p->match_out_stride; r.tsum = p->tsum_out; }
-    else { r.rs = r.cs = 1; r.t1 = r.t2 = nullptr; r.t1st = r.t2st = r.s1 = r.s2 = 0; r.out = nullptr; r.outs = 0; r.tsum = nullptr; }
+             r.out = p->match_out; r.outs = p->match_out_stride; r.tsum = p->tsum_out; r.cap = p->cap; r.flag = rt_overflow_ptr(); }
+    else { r.rs = r.cs = 1; r.t1 = r.t2 = nullptr; r.t1st = r.t2st = r.s1 = r.s2 = 0; r.out = nullptr; r.outs = 0; r.tsum = nullptr; r.cap = 0; r.flag = nullptr; }
     return r;
 }
 // all threads of the CTA; hR / hC: table headers in shared memory; m: MSTRIDE ints of shared memory
@@ -95,7 +98,13 @@ __device__ __forceinline__ void rt_match_cta(const int* hR, const int* hC, const
         int acc = 0;
         for (int i = 0; i < nr; ++i) { const int sz = m[2 + i]; m[2 + i] = acc; acc += sz; }
         m[2 + nr] = acc;
-        const bool bad = hR[0] < 0 || hC[0] < 0;
+        bool bad = hR[0] < 0 || hC[0] < 0;
+        if (sp.cap > 0 && acc > sp.cap) {            // learnt capacity exceeded: the chain is stored empty, loudly (backend.rt_overflow)
+            bad = true;
+            if (store && sp.flag) atomicAdd(sp.flag, 1ull);
+            for (int i = 0; i <= nr; ++i) m[2 + i] = 0;
+            for (int i = 0; i < nr; ++i) m[3 + RT_SMAX + i] = -1;
+        }
         m[0] = bad ? 0 : acc;
         m[1] = bad ? 1 : 0;
         if (store && sp.tsum) sp.tsum[sp.outs ? b : 0] = t;     // one row for all chains when the pairing is chain-independent

@@ -177,7 +177,10 @@ def gradient_descent(
     # Lock-step chains of a bosonic-symmetric model run on its charge-dense embedding: the embedding is
     # rebuilt from the symmetric parameters at the start of every step, sampled and observed, and the gradient is projected back
     # onto the symmetric blocks (it is exactly zero outside them), so the optimisation itself stays in the symmetric picture.
-    embedded = chains > 1 and state.Tensor.Symmetry.length != 0
+    from . import configuration as _configuration
+    sector = (chains > 1 and state.Tensor.Symmetry.length != 0 and _configuration.LOCKSTEP_ENGINE == "sector"
+              and _configuration.sector_engine_supported(state.Tensor))
+    embedded = chains > 1 and state.Tensor.Symmetry.length != 0 and not sector
     if embedded:
         if state.Tensor.Symmetry.is_fermi_symmetry:
             raise NotImplementedError("lock-step chains of fermionic lattices: run them one chain per call (chains=1)")

@@ -316,6 +316,9 @@ class Observer:
             if self._enable_natural:
                 import torch
                 self._Deltas.append((reweight.copy(), Es.copy(), torch.cat(rows, dim=1)))
+        if ragged:
+            from .sampling import _check_capacity
+            _check_capacity()
 
     # -- results -------------------------------------------------------------------------------------
     def _expect_and_deviation(self, total_reweight, total_reweight_square, total_square_reweight_square):

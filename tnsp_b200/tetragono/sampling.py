@@ -77,9 +77,34 @@ class _GlobalRng:
         return np.array([_random.uniform_real(0, 1)()])
 
 
+def _check_capacity():
+    """sector-compact engine: a chain whose sectors outgrew a learnt buffer capacity was stored empty (TAT/ragged.py) -- fail loudly"""
+    dropped = _bk.get().rt_overflow()
+    if dropped:
+        raise RuntimeError(f"sector-compact engine: {dropped} (chain, tensor) pairs exceeded their learnt capacity; raise "
+                           "tnsp_b200.TAT.ragged.CAP_FACTOR (now %g) or set CAPS_ENABLED = False" % __import__("tnsp_b200.TAT.ragged", fromlist=["x"]).CAP_FACTOR)
+
+
 def _amplitude_values(ws):
     """host float array [nb] of a one-element (batched) tensor"""
     return np.atleast_1d(np.asarray(ws.storage, dtype=np.float64).reshape(-1))
+
+
+def calibrate_sector_engine(owner, cut_dimension, configuration, hopping_hamiltonians=None, chains=148, sweeps=1, observer_options=None):
+    """Learn the buffer capacities of the sector-compact engine (TAT/ragged.py) on a small throw-away batch BEFORE a large lock-step
+    batch allocates anything: `chains` chains with their own random streams (the caller's engines are not touched) sweep and are
+    observed once from the start `configuration` ([L1, L2, orbits] total physical indices).  No effect on any result."""
+    from .observer import Observer
+    rng = ChainRng(chains)
+    rng.seed([(911 + 7 * c) % 2**31 for c in range(chains)])
+    s = SweepSampling(owner, cut_dimension, None, hopping_hamiltonians, nb=chains, rng=rng)
+    conf = np.asarray(configuration)
+    s.configuration.import_configuration(np.broadcast_to(conf, (chains,) + conf.shape) if conf.ndim == 3 else conf[:chains])
+    obs = Observer(owner, **(observer_options or dict(enable_energy=True, enable_gradient=True)))
+    with obs:
+        for _ in range(sweeps):
+            p, c = s()
+            obs(p, c)
 
 
 class Sampling:
@@ -192,6 +217,8 @@ class SweepSampling(Sampling):
             ws, ws_val = self._single_term(positions, self._hopping_hamiltonians[positions], ws, ws_val)
         alpha = self.owner.attribute.get("alpha", 1)
         possibility = np.abs(ws_val)**(2 * alpha)
+        if getattr(self.configuration, "_ragged", False):
+            _check_capacity()
         return (float(possibility[0]) if self.nb == 1 else possibility), self.configuration.copy()
 
     def refresh_all(self):
