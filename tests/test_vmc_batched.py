@@ -84,3 +84,24 @@ def test_chain_rng_matches_reference_seed_recipe():
     want = [TAT.random.uniform_int(0, 9)() for _ in range(5)]
     got = [int(rng.uniform_int(np.full(3, 9), None)[0]) for _ in range(5)]
     assert got == want
+
+
+@pytest.mark.parametrize("size,nb", [(2, 3), (4, 5), (3, 7)])
+def test_batched_ergodic_enumeration_covers_every_configuration_on_every_rank(size, nb):
+    """several ranks x lock-step batches that do not divide the number of configurations: the union of what the ranks are handed
+    (driver rule: rank r takes the calls with step % size == r) is every configuration exactly once"""
+    from tnsp_b200.tetragono.sampling import ErgodicSampling
+    lat = models.random_sampling_lattice(models.heisenberg_lattice(3, 3, 2), 5)
+    seen = []
+    calls = None
+    for rank in range(size):
+        s = ErgodicSampling(lat, 4, rank=rank, size=size, nb=nb)
+        calls = s.calls
+        for step in range(calls):
+            if step % size == rank:
+                p, c = s()
+                conf = c.export_configuration().reshape(nb, -1)
+                for k in range(nb):
+                    if np.isfinite(np.atleast_1d(p)[k]):
+                        seen.append(int("".join(str(int(x)) for x in conf[k]), 2))
+    assert len(seen) == 512 and sorted(seen) == list(range(512))

@@ -25,6 +25,8 @@ and handles only; every array operation is a kernel behind ``backend.rt_*`` (csr
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 
 from .. import backend as _bk
@@ -47,6 +49,7 @@ _CAPS: dict = {}
 CAP_LEARN = 3
 CAP_FACTOR = 2.0
 CAPS_ENABLED = True
+TABLE_CACHE_MAX = 4096       # merged dimension up to which a group table is shared through its label arrays
 
 
 def _cap(key, dense):
@@ -157,12 +160,22 @@ class Core:
                 got = (_empty_table(), 1)
             else:
                 g = es[0].sign
-                key = tuple((id(e.arr), e.sign * g) for e in es)
-                store = es[0].arr.__dict__.setdefault("_rt_tables", {})
-                hit = store.get(key)
-                if hit is None:
+                M = self.group_dim(ids)
+                if M > TABLE_CACHE_MAX:
+                    # a group spanning (most of) a big tensor: its table is as large as the tensor, keep it with the tensor only
                     STATS["sort"] += 1
-                    hit = store[key] = (B.rt_sort([(e.arr, e.sign * g, e.dim) for e in es]), tuple(e.arr for e in es))
+                    hit = (B.rt_sort([(e.arr, e.sign * g, e.dim) for e in es]),)
+                else:
+                    key = tuple((id(e.arr), e.sign * g) for e in es)
+                    store = es[0].arr.__dict__.setdefault("_rt_tables", {})
+                    hit = store.get(key)
+                    if hit is not None and not all(r() is e.arr for r, e in zip(hit[1], es[1:])):
+                        hit = None          # an id was recycled by another array
+                    if hit is None:
+                        STATS["sort"] += 1
+                        # weak references to the other arrays: no reference cycles through the cache (device memory is freed by
+                        # reference counting, not by the cycle collector)
+                        hit = store[key] = (B.rt_sort([(e.arr, e.sign * g, e.dim) for e in es]), tuple(weakref.ref(e.arr) for e in es[1:]))
                 got = (hit[0], g)
             self.tables[ids] = got
         return got

@@ -448,6 +448,115 @@ __global__ void __launch_bounds__(128) rt_gemm_kernel(RtForm A, RtForm B, RtForm
 }
 
 // ------------------------------------------------------------------------------------------------
+// rt_gemm for SMALL sectors (cfg2: k, n of a sector <= ~40): one warp owns a 16-row x 32-column piece of one sector and runs on
+// its own -- no shared-memory tiles, no block barriers.  Every lane loads its DMMA fragment elements straight from global memory:
+// a sector matrix is contiguous and row-major, so the 8 x 4 A fragment of a warp-wide load covers 8 rows x 32 B of a k-wide row
+// block (whole sectors for small k) and the B sector (<= 10 KiB) stays in L1.  HBM-bound by construction: A and C are streamed
+// once, nothing else is touched (the tiled kernel above spent its time on header copies, zero-padded shared-memory tiles and two
+// barriers per tile: 3 CTAs / SM, 0.25 TFLOP/s on cfg2).
+// ------------------------------------------------------------------------------------------------
+constexpr int WR = 16;          // rows per warp item
+constexpr int WC = 32;          // columns per warp item (4 DMMA fragments)
+constexpr int kGemmWarps = 8;
+
+__global__ void __launch_bounds__(kGemmWarps * 32, 4) rt_gemm_warp_kernel(RtForm A, RtForm B, RtForm C, RtSpec spec, double* __restrict__ cdata,
+                                                                          long long cstride, int ksign, unsigned long long* stats) {
+    __shared__ int mC[RT_MSTRIDE];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* gAr = A.rt + b * A.rts;
+    const int* gAk = A.ct + b * A.cts;
+    const int* gBk = B.rt + b * B.rts;
+    const int* gBn = B.ct + b * B.cts;
+    if (spec.on) rt_match_cta(gAr, gBn, spec, b, mC, blockIdx.x == 0);
+    else {
+        for (int i = tid; i < RT_MSTRIDE; i += kGemmWarps * 32) mC[i] = C.match[b * C.mts + i];
+        __syncthreads();
+    }
+    const RtTab aR(gAr), aK(gAk), bK(gBk), bN(gBn);
+    const RtMatch MA(A.match + b * A.mts), MB(B.match + b * B.mts), MC(mC);
+    const double* a = A.data + (long long)b * A.dstride;
+    const double* bb = B.data + (long long)b * B.dstride;
+    double* c = cdata + (long long)b * cstride;
+    const int nsec = max(aR.nsec(), 0);
+    const int g = lane >> 2, q = lane & 3;
+    int item = blockIdx.x * kGemmWarps + warp;
+    const int step = gridDim.x * kGemmWarps;
+    int first = 0;
+    for (int i = 0; i < nsec; ++i) {
+        const int jc = MC.mcol(i);
+        if (jc < 0) continue;
+        const int m = aR.count(i), n = bN.count(jc);
+        if (m == 0 || n == 0) continue;
+        const int tm = (m + WR - 1) / WR, tn = (n + WC - 1) / WC;
+        const int here = tm * tn;
+        if (item >= first + here) { first += here; continue; }
+        int k = 0;
+        long long aoff = 0, boff = 0;
+        const int jk = MA.mcol(i);
+        if (jk >= 0) {
+            const int ib = bK.find(ksign * aK.skey(jk));
+            if (ib >= 0 && MB.mcol(ib) == jc) {
+                k = min(aK.count(jk), bK.count(ib));
+                aoff = MA.moff(i);
+                boff = MB.moff(ib);
+            }
+        }
+        const long long coff = MC.moff(i);
+        if (stats && blockIdx.x == 0 && tid == 0) {
+            unsigned long long issued = 0;
+            for (int t = 0; t < tn; ++t) issued += (unsigned long long)tm * 2 * ((min(WC, n - t * WC) + 7) / 8) * ((k + 3) / 4);
+            atomicAdd(&stats[0], 2ull * m * n * k);
+            atomicAdd(&stats[1], issued * 512ull);
+            atomicAdd(&stats[2], 8ull * ((unsigned long long)m * k + (unsigned long long)k * n + (unsigned long long)m * n));
+            atomicAdd(&stats[8], 1ull);
+        }
+        for (; item < first + here; item += step) {
+            const int t = item - first;
+            const int r0 = (t / tn) * WR, c0 = (t % tn) * WC;
+            const int cols = min(WC, n - c0);
+            const int nfr = (cols + 7) >> 3;
+            double acc[2][4][2];
+#pragma unroll
+            for (int x = 0; x < 2; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+            const bool row0 = r0 + g < m, row1 = r0 + 8 + g < m;
+            const double* ap0 = a + aoff + (long long)(r0 + g) * k + q;
+            const double* ap1 = ap0 + 8ll * k;
+            const double* bp = bb + boff + (long long)q * n + c0 + g;
+            for (int ks = 0; ks < k; ks += 4) {
+                const bool kin = ks + q < k;
+                const double a0 = (kin && row0) ? __ldg(ap0 + ks) : 0.0;
+                const double a1 = (kin && row1) ? __ldg(ap1 + ks) : 0.0;
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    if (y < nfr) {
+                        const double bv = (kin && y * 8 + g < cols) ? __ldg(bp + (long long)ks * n + y * 8) : 0.0;
+                        rt_dmma(acc[0][y][0], acc[0][y][1], a0, bv);
+                        rt_dmma(acc[1][y][0], acc[1][y][1], a1, bv);
+                    }
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const int r = r0 + x * 8 + g;
+                if (r < m) {
+                    double* cp = c + coff + (long long)r * n + c0;
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const int cc = y * 8 + 2 * q;
+                        if (cc < cols) cp[cc] = acc[x][y][0];
+                        if (cc + 1 < cols) cp[cc + 1] = acc[x][y][1];
+                    }
+                }
+            }
+            if (t == 0 && lane == 0 && ((m * n) & 1)) c[coff + (long long)m * n] = 0.0;     // alignment pad of an odd-sized sector
+        }
+        first += here;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // elementwise over the stored sectors (per-chain sizes from the match table)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rt_scale_kernel(const double* __restrict__ x, long long xs, const int* __restrict__ match, long long mts,
@@ -578,6 +687,16 @@ extern "C" int tnsp_rt_repack_pair_f64(const int32_t* plan0, const tnsp_rt_form*
 extern "C" int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, const tnsp_rt_form* c, const tnsp_rt_match_spec* c_match,
                                 double* c_data, int64_t c_stride, int ksign, int nb, void* stream) {
     if (nb == 0) return 0;
+    if (a->N <= 512 && b->N <= 512) {
+        // small sectors: warp-autonomous kernel; the grid covers the most items a chain can have (every sector adds at most one
+        // partial piece per direction), spare CTAs leave at once
+        int64_t items = ((a->M + WR - 1) / WR + RT_SMAX / 4) * ((b->N + WC - 1) / WC);
+        int64_t gx = (items + 2 * kGemmWarps - 1) / (2 * kGemmWarps);      // about two items per warp
+        if (gx > 256) gx = 256;
+        rt_gemm_warp_kernel<<<dim3((unsigned)gx, (unsigned)nb), kGemmWarps * 32, 0, (cudaStream_t)stream>>>(
+            to_form(a), to_form(b), to_form(c), to_spec(c_match), c_data, c_stride, ksign, rt_stats_ptr());
+        return check_launch("tnsp_rt_gemm_f64(warp)");
+    }
     int64_t tiles = ((a->M + GT - 1) / GT) * ((b->N + GT - 1) / GT);
     if (tiles < 1) tiles = 1;
     if (tiles > 64) tiles = 64;

@@ -16,7 +16,7 @@ class KernelTimer:
                "diag_scatter", "block_sign", "svd_mask",
                # sector-compact engine (TAT/ragged.py): algorithmic work of these classes is counted ON THE DEVICE (per-chain sector
                # sizes are never known to the host): backend.rt_stats
-               "rt_sort", "rt_match", "rt_repack", "rt_gemm", "rt_factor_plan", "rt_qr_work", "rt_svd_work", "rt_svd_finish", "rt_svd_scatter",
+               "rt_sort", "rt_match", "rt_repack", "rt_repack_pair", "rt_gemm", "rt_factor_plan", "rt_qr_work", "rt_svd_work", "rt_svd_finish", "rt_svd_scatter",
                "rt_scale", "rt_binary", "rt_norm", "rt_scalar")
 
     def __init__(self, backend):
@@ -81,6 +81,24 @@ class KernelTimer:
                 if _name == "rt_gemm":
                     sig = (_name, 0, (int(args[0].M), int(args[1].N), int(args[0].N)), int(args[4]))
                     self.shapes.setdefault(sig, []).append((e0, e1, fl, by))
+                elif _name == "rt_sort":
+                    M = 1
+                    for _, _, d in args[0]:
+                        M *= int(d)
+                    sig = (_name, len(args[0]), (M, 0, 0), max([int(a.shape[0]) for a, _, _ in args[0]] + [1]))
+                    self.shapes.setdefault(sig, []).append((e0, e1, fl, by))
+                elif _name == "rt_repack":
+                    dst = args[2]
+                    dims = (int(dst.M), int(dst.N), 0) if hasattr(dst, "M") else (int(dst.shape[1]), 0, -1)
+                    sig = (_name, 0, dims, int(dst.data.shape[0]) if hasattr(dst, "M") else int(dst.shape[0]))
+                    self.shapes.setdefault(sig, []).append((e0, e1, fl, by))
+                elif _name == "rt_repack_pair":
+                    d0, d1 = args[2], args[6]
+                    sig = (_name, 0, (int(d0.M * d0.N), int(d1.M * d1.N), 0), int(d0.data.shape[0]))
+                    self.shapes.setdefault(sig, []).append((e0, e1, fl, by))
+                elif _name in ("rt_qr_work", "rt_svd_work"):
+                    sig = (_name, 0, (int(args[0].M), int(args[0].N), 0), int(args[-1]))
+                    self.shapes.setdefault(sig, []).append((e0, e1, fl, by))
                 elif _name in ("gemm", "gemm_gather", "qr", "svd"):
                     tab = args[0].gemm if _name == "gemm" else ([args[0].gather[2:5]] if _name == "gemm_gather" else args[0].sectors)
                     sig = (_name, len(tab), tuple(int(x) for x in tab[0][:3]), int(args[3 if _name.startswith('gemm') else 1].shape[0]))
@@ -111,7 +129,7 @@ class KernelTimer:
             v["share"] = v["ms"] / total
         return out
 
-    def shape_summary(self, top=12):
+    def shape_summary(self, top=40):
         """heaviest (kernel class, #descriptors, first (m, n, k), chains) signatures"""
         rows = []
         for sig, recs in self.shapes.items():
@@ -212,7 +230,7 @@ def sector_engine_rooflines(breakdown, stats, peaks, dgemm_peak):
                           "algorithmic_tflops": alg / t / 1e12, "frac_of_dgemm_peak": alg / t / 1e12 / dgemm_peak if dgemm_peak else None,
                           "executed_frac_of_dgemm_peak": issued / t / 1e12 / dgemm_peak if dgemm_peak else None,
                           "algorithmic_bytes": by, "gbs": by / t / 1e9, "frac_of_hbm_peak": by / t / 1e9 / hbm}
-    t = sec("rt_repack")
+    t = sec("rt_repack") + sec("rt_repack_pair")
     if t:
         out["rt_repack"] = {"bound": "hbm", "seconds": t, "algorithmic_bytes": 16.0 * stats[3], "gbs": 16.0 * stats[3] / t / 1e9,
                             "frac_of_hbm_peak": 16.0 * stats[3] / t / 1e9 / hbm}

@@ -137,10 +137,10 @@ def gradient_descent(
         measurement=None):
     """Generator: one `(whole_result, result)` pair per optimisation step, like the reference.
 
-    `sampling_configurations` is the start configuration of the sweep sampler, an int64 array
-    `[L1, L2, orbits, 1 + symmetry components]` (or `[chains, ...]`) as written by `Configuration.export_configuration`;
-    the last configuration of every step is copied back into it (gradient.py:360-364) when it is an array of the
-    right shape."""
+    `sampling_configurations` is the start configuration of the sweep sampler: an int64 array `[L1, L2, orbits]` of total
+    physical edge indices (-1: no such orbit), or `[chains, L1, L2, orbits]` with one configuration per chain, as written by
+    `Configuration.export_configuration`; the last configurations of every step are written back into it (resized in place
+    when it held a single configuration, gradient.py:360-364)."""
     if sampling_method not in ("sweep", "ergodic", "direct"):
         raise ValueError("Invalid sampling method")
     if use_check_difference:
@@ -230,9 +230,11 @@ def gradient_descent(
                 if configuration is not None:
                     sampling.configuration.import_configuration(configuration.export_configuration())
                 elif sampling_configurations is not None and np.size(sampling_configurations) != 0:
+                    # [L1, L2, orbits] (one start configuration for every chain) or [chains, L1, L2, orbits] as written by
+                    # `Configuration.export_configuration`; import_configuration broadcasts the former itself
                     conf = np.asarray(sampling_configurations)
-                    if chains > 1 and conf.ndim == 4:
-                        conf = np.broadcast_to(conf, (chains,) + conf.shape)
+                    if conf.ndim == 4 and conf.shape[0] != chains:
+                        raise ValueError(f"sampling_configurations holds {conf.shape[0]} configurations for {chains} chains")
                     sampling.configuration.import_configuration(conf)
                 else:
                     raise RuntimeError("sweep sampling needs an initial configuration (sampling_configurations)")
@@ -251,9 +253,15 @@ def gradient_descent(
                     if need_energy_observer:
                         configuration_pool.append((possibility, configuration))
             if sampling_method != "ergodic" and configuration is not None and isinstance(sampling_configurations, np.ndarray):
+                # keep the caller's array current (gradient.py:360-364 resizes it in place too): the configuration file written
+                # below and the next call of the driver start from the last configurations of this step
                 new_conf = configuration.export_configuration()
-                if sampling_configurations.shape == new_conf.shape:
-                    np.copyto(sampling_configurations, new_conf)
+                if sampling_configurations.shape != new_conf.shape:
+                    try:
+                        sampling_configurations.resize(new_conf.shape, refcheck=False)
+                    except ValueError:
+                        sampling_configurations = np.array(new_conf)
+                np.copyto(sampling_configurations, new_conf)
         seed_differ_exit()
 
         measurement_result = observer.result

@@ -312,6 +312,11 @@ class Observer:
                     data = data.expand(nb, data.shape[1]).contiguous()
                 B.grad_accumulate(data, w_dev, e_dev, target.data, self._EDelta[l1][l2].data)
                 if self._enable_natural:
+                    if not alive.all():
+                        # a chain with zero amplitude has 0 / 0 holes: the reference never stores such a sample
+                        # (observer.py:333-335 returns early); keep its row exactly zero so that 0 weight x NaN cannot poison the CG
+                        import torch
+                        data = torch.where(B.from_numpy(alive)[:, None], data, torch.zeros((), dtype=data.dtype, device=data.device))
                     rows.append(data)
             if self._enable_natural:
                 import torch

@@ -274,8 +274,11 @@ class ErgodicSampling(Sampling):
 
     @property
     def calls(self):
-        """calls (over all ranks, like the reference's `total_step` loop) that cover every configuration once"""
-        return -(-self.total_step // self.nb)
+        """calls over ALL ranks (the driver gives rank r the calls with step % size == r, like the reference's `total_step` loop)
+        that cover every configuration once: every rank must get ceil(longest rank sequence / nb) calls -- rank 0's sequence,
+        ceil(total / size) configurations, is the longest; surplus chains of the last batch carry possibility = inf"""
+        longest = -(-self.total_step // self._size)
+        return self._size * (-(-longest // self.nb))
 
     def __call__(self):
         if self.nb == 1:
