@@ -284,6 +284,30 @@ def run_own(args):
         lat = dense_embedding.embed_lattice(sym_lat)
         conf0 = dense_embedding.embed_configuration(sym_lat, points)
         hopping = models.nearest_neighbour_terms(lat) if hopping is not None else None
+    # ---- parity line: cache-cold amplitude and local energy of the start configuration, ALL through the engine being timed, against
+    # the fixture the unmodified reference wrote for exactly this PEPS (tests/golden/make_golden.py cfg2size) -------------------------
+    parity = None
+    fixture = {"cfg2": "j1j2U1_6x6_d2_Dc36", "cfg2s": "j1j2U1_4x4_d1_Dc9"}.get(args.workload)
+    fpath = os.path.join(ROOT, "tests", "golden", f"{fixture}.npz") if fixture else None
+    if fpath and os.path.exists(fpath) and rank == 0 and (args.workload != "cfg2s"):
+        from tnsp_b200.tetragono.configuration import Configuration
+        z = np.load(fpath)
+        n_par = min(nb, 148)
+        pc = Configuration(lat, Dc, n_par)
+        pc.import_configuration(np.broadcast_to(conf0, (n_par,) + conf0.shape))
+        ws_p = np.asarray(pc.hole(()).storage).reshape(-1)
+        po = Observer(lat, enable_energy=True)
+        with po:
+            po(ws_p**2, pc)
+        e_p = po._whole_result_reweight["energy"] / po._total_weight
+        parity = {"fixture": f"tests/golden/{fixture}.npz (unmodified reference, cache-cold Neel configuration)", "chains": n_par,
+                  "ws_reference": float(z["ws"][0]), "ws_max_rel_err": float(np.abs(ws_p - z["ws"][0]).max() / abs(z["ws"][0])),
+                  "local_energy_reference": float(z["energy_s"][0]),
+                  "local_energy_rel_err": float(abs(e_p - z["energy_s"][0]) / abs(z["energy_s"][0])), "tolerance": 1e-10}
+        parity["ok"] = bool(parity["ws_max_rel_err"] <= 1e-10 and parity["local_energy_rel_err"] <= 1e-10)
+        if not parity["ok"]:
+            raise RuntimeError(f"bench parity check failed: {parity}")
+        del pc, po
     # one normalisation pass so that amplitudes are O(1) (observer.normalize_lattice)
     s0 = SweepSampling(lat, Dc, None, hopping, nb=1)
     s0.configuration.import_configuration(conf0)
@@ -449,7 +473,7 @@ def run_own(args):
                                                                           if sector else "charge-dense embedding, sectors discovered on device"),
                        "l2": "working set of a step (all chains' environments) exceeds L2; no flush"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clock_info, "energy_per_site": energy[0],
+            "gpu_launches": int(launches), "clocks": clock_info, "energy_per_site": energy[0], "parity_check": parity,
             "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated() / 1e9,
             "roofline": roofline, "kernel_breakdown": breakdown, "top_shapes": top_shapes,
         }

@@ -220,6 +220,13 @@ int tnsp_rt_repack_pair_f64(const int32_t* plan0, const tnsp_rt_form* src0, cons
  * C_i = A_i B_i', i' = the row sector of b whose charge is ksign * (charge of the column sector a pairs with i); zeros when absent */
 int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, const tnsp_rt_form* c, const tnsp_rt_match_spec* c_match, double* c_data,
                      int64_t c_stride, int ksign, int nb, void* stream);
+/* contraction over ALL edges of two tensors (closing contraction of a strip, amplitude x hole): out[chain][0] = sum over the stored
+ * elements of dst of dst[e] * src[same multi-index]; plan as for tnsp_rt_repack_f64 with dst's grouping as the destination.  No
+ * merged group over the whole tensor is built.  match / tsum: pairing table ([nb][TNSP_RT_MSTRIDE]) and summed target of the
+ * one-element result (targets as in tnsp_rt_match_i32; the element exists iff the sum vanishes). */
+int tnsp_rt_dot_f64(const int32_t* plan, const tnsp_rt_form* src, const tnsp_rt_form* dst, const int32_t* t1, int t1_stride, int s1,
+                    const int32_t* t2, int t2_stride, int s2, double* out, int64_t out_stride, int32_t* match, int32_t* tsum, int nb,
+                    void* stream);
 /* per-sector QR (kind 0; qr.hpp:178-304, common edge qr.hpp:419-429) / SVD with the global greedy cut (kind 2; svd.hpp:104-211,
  * 429-481) of every (chain, sector) matrix of f.  The bond label of row sector i on the first factor is
  * t1s * t1[chain] - fsign_rs * rowkey(i).  Three calls: _plan (labels of the QR bond, work queue, work-buffer layout), then the

@@ -157,7 +157,7 @@ class RaggedMixin:
     def _decode(plan):
         p = _np(plan)
         nr, nc = int(p[0]), int(p[1])
-        ent = p[2:].reshape(-1, 3)
+        ent = p[2:].reshape(-1, 5)[:, :3]          # (dim, source group, source stride); the magic numbers are for the device
         return [tuple(int(x) for x in e) for e in ent[:nr]], [tuple(int(x) for x in e) for e in ent[nr:nr + nc]]
 
     @staticmethod
@@ -239,6 +239,39 @@ class RaggedMixin:
                         continue
                     val[k] = srow[int(mt.moff[i]) + (p[k] - tr.sstart[i]) * tc.count(j) + (q[k] - tc.sstart[j])]
             D[c, dst_pos] = val
+
+    def rt_dot(self, plan, src, dst, t1, s1, t2, s2, nb):
+        """full contraction: sum over the stored elements of dst of dst[e] * src[same multi-index] (specification: regroup src into
+        dst's layout, multiply elementwise, add)"""
+        self.launches += 1
+
+        class _F:
+            pass
+        tmp = _F()
+        for k in ("rows", "cols", "rt", "rs", "ct", "cs", "match", "M", "N"):
+            setattr(tmp, k, getattr(dst, k))
+        tmp.data = self.rt_alloc(max(nb, dst.data.shape[0]), dst.M * dst.N)
+        self.rt_repack(plan, src, tmp)
+        D, T = _np(dst.data), _np(tmp.data)
+        out = self.rt_alloc(nb, 2)
+        o = out.numpy()
+        match = np.zeros((nb, MSTRIDE), dtype=np.int32)
+        tsum = np.zeros(nb, dtype=np.int32)
+        for c in range(nb):
+            t = 0
+            if t1 is not None:
+                t += int(s1) * int(_row(_np(t1).reshape(-1, 1), c)[0])
+            if t2 is not None:
+                t += int(s2) * int(_row(_np(t2).reshape(-1, 1), c)[0])
+            tsum[c] = t
+            size = int(_row(_np(dst.match), c)[0])
+            o[c, 0] = float(np.dot(_row(D, c)[:size], _row(T, c)[:size])) if t == 0 else 0.0
+            o[c, 1] = 0.0
+            if t == 0:
+                match[c, 0], match[c, 3] = 2, 2
+            else:
+                match[c, 3 + SMAX] = -1
+        return out, torch.from_numpy(match), (torch.from_numpy(tsum) if (t1 is not None or t2 is not None) else None)
 
     # ---- grouped GEMM over (chain, sector) --------------------------------------------------------------------------
     def rt_gemm(self, A, B, C, ksign, nb, match_spec=None):

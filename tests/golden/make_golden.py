@@ -262,6 +262,13 @@ def dump_structure(name, sym_name, lattice):
 
 
 def main():
+    if "cfg2size" in sys.argv[1:]:
+        # the benched configuration at its REAL size (BASELINE cfg2: 6x6 J1-J2 U(1), D = 2+2+2, Dc = 36): cache-cold ws / E_s /
+        # holes of the Neel configuration and a 3-sample sweep trajectory with gradient + SR-CG, the at-size pin of bench.py
+        lat = j1j2_u1(6, 6, 2, 0.5)
+        hop = {k: v for k, v in lat._hamiltonians.items() if k[0][0] == k[1][0] or k[0][1] == k[1][1]}
+        dump_case("j1j2U1_6x6_d2_Dc36", "BoseU1", lat, 36, neel_u1(lat), seed=18, n_samples=3, hopping=hop)
+        return
     if "j1j2model" in sys.argv[1:]:
         # the J1-J2 model the reference ships (tetraku/models/J1J2/__init__.py, NoSymmetry)
         from tetraku.models.J1J2 import abstract_lattice

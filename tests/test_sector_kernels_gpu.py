@@ -58,6 +58,7 @@ def _run(B, case, cut):
     out["usv"] = num(u.contract(s, {("U", "SU")}).contract(v, {("SV", "V")}).transpose(c.names).to_dense())
     sd = num(s.to_dense()).reshape(case["nb"], s.core.edges[0].dim, -1)
     out["sv"] = np.sort(np.diagonal(sd, axis1=1, axis2=2), axis=1)[:, ::-1]
+    out["dot"] = np.asarray(c.conjugate().contract(c, {(n, n) for n in c.names}).storage)      # full contraction (rt_dot)
     out["norm"] = np.asarray(c.norm_2().numpy())
     out["nmax"] = np.asarray(c.norm_max().numpy())
     out["scaled"] = num((c / c.norm_max()).to_dense())
@@ -100,7 +101,8 @@ def test_kernels_equal_specification(shape):
     assert np.abs(got["qq"] - want["qq"]).max() <= 1e-11
     assert np.abs(got["sv"] - want["sv"]).max() <= 1e-11 * scale
     assert np.abs(got["usv"] - want["usv"]).max() <= 1e-9 * scale
-    for k in ("norm", "nmax"):
+    assert np.allclose(got["dot"], got["norm"]**2, rtol=1e-12, atol=0)
+    for k in ("norm", "nmax", "dot"):
         assert np.allclose(got[k], want[k], rtol=1e-13, atol=0)
     for k in ("scaled", "sum"):
         assert np.abs(got[k] - want[k]).max() <= 1e-12 * scale

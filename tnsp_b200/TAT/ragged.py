@@ -230,6 +230,17 @@ def _empty_table():
     return t
 
 
+def _plan_array(rows, cols):
+    """int32 descriptor [nr, nc, then per destination edge: dim, source group, source stride, magic lo, magic hi] with
+    magic = floor(2^64 / dim) + 1 (exact division of a 32-bit index by one multiply-high on the device)"""
+    out = [len(rows), len(cols)]
+    for dim, grp, stride in rows + cols:
+        m = (1 << 64) // dim + 1
+        lo, hi = m & 0xFFFFFFFF, (m >> 32) & 0xFFFFFFFF
+        out += [dim, grp, stride, lo - (1 << 32) if lo >= (1 << 31) else lo, hi - (1 << 32) if hi >= (1 << 31) else hi]
+    return np.array(out, dtype=np.int32)
+
+
 def _repack_plan(core, src, dst):
     """int32 descriptor of a regrouping: for every edge of the destination row group, then column group (slowest first):
     dimension, 1 if the edge sits in the source's column group, its stride inside that source group"""
@@ -244,8 +255,7 @@ def _repack_plan(core, src, dst):
                 stride *= core.edges[i].dim
         rows = [(core.edges[i].dim,) + where[i] for i in dst.rows if core.edges[i].dim != 1]
         cols = [(core.edges[i].dim,) + where[i] for i in dst.cols if core.edges[i].dim != 1]
-        arr = np.array([len(rows), len(cols)] + [x for t in rows + cols for x in t], dtype=np.int32)
-        p = _PLANS[key] = _bk.get().upload(arr)
+        p = _PLANS[key] = _bk.get().upload(_plan_array(rows, cols))
     return p
 
 
@@ -271,8 +281,7 @@ def _dense_plan(dims, order_rows, order_cols, to_dense):
         else:
             rows = [(dims[i], 0, strides[i]) for i in order_rows if dims[i] != 1]
             cols = [(dims[i], 0, strides[i]) for i in order_cols if dims[i] != 1]
-        arr = np.array([len(rows), len(cols)] + [x for t in rows + cols for x in t], dtype=np.int32)
-        p = _PLANS[key] = _bk.get().upload(arr)
+        p = _PLANS[key] = _bk.get().upload(_plan_array(rows, cols))
     return p
 
 
@@ -587,6 +596,8 @@ def _contract(a, b, pairs):
         p = _PLANS[key] = (tuple(i for i in fa if not ea[i].unit), tuple(ka), tuple(kb), tuple(j for j in fb if not eb[j].unit),
                            tuple(fa), tuple(fb), [a.names[i] for i in fa] + [b.names[j] for j in fb])
     fa_n, ka, kb, fb_n, fa, fb, names = p
+    if not fa_n and not fb_n and ka:
+        return _dot(a, b, ka, kb, fa, fb, names)
     A, Bf = a.core.forms.get((fa_n, ka)), b.core.forms.get((kb, fb_n))
     if A is None and Bf is None and a.core is not b.core:
         A, job_a, key_a = a.core.form_job(fa_n, ka)
@@ -621,6 +632,40 @@ def _contract(a, b, pairs):
         _learn(key, C.match)
     core = Core(edges, nb, target, 1)
     core.set_primary(C)
+    return RTensor(names, core, 1)
+
+
+def _dot(a, b, ka, kb, fa, fb, names):
+    """contraction over every indexed edge of both tensors: one pass over the stored elements of `a` (the larger data is walked in
+    its own layout, `b` is read through its tables) -- no regrouping, no table over the whole tensor"""
+    B = _bk.get()
+    if b.core.forms[b.core.primary].M * b.core.forms[b.core.primary].N > a.core.forms[a.core.primary].M * a.core.forms[a.core.primary].N:
+        a, b, ka, kb, fa, fb = b, a, kb, ka, fb, fa       # walk the operand with the larger index space
+        swapped = True
+    else:
+        swapped = False
+    A, S = a.core.forms[a.core.primary], b.core.forms[b.core.primary]
+    key = ("dot", tuple(e.dim for e in a.core.edges), A.rows, A.cols, tuple(e.dim for e in b.core.edges), S.rows, S.cols, ka, kb)
+    plan = _PLANS.get(key)
+    if plan is None:
+        pair = dict(zip(ka, kb))
+        where = {}
+        for grp, ids in ((0, S.rows), (1, S.cols)):
+            stride = 1
+            for j in reversed(ids):
+                where[j] = (grp, stride)
+                stride *= b.core.edges[j].dim
+        rows = [(a.core.edges[i].dim,) + where[pair[i]] for i in A.rows if a.core.edges[i].dim != 1]
+        cols = [(a.core.edges[i].dim,) + where[pair[i]] for i in A.cols if a.core.edges[i].dim != 1]
+        plan = _PLANS[key] = B.upload(_plan_array(rows, cols))
+    nb = max(a.core.nb, b.core.nb, A.match.shape[0], S.match.shape[0])
+    data, match, target = B.rt_dot(plan, S, A, a.core.target, a.core.tsign * a.sign, b.core.target, b.core.tsign * b.sign, nb)
+    if swapped:
+        a, b, fa, fb = b, a, fb, fa
+    edges = [a.core.edges[i].flipped(a.sign) for i in fa] + [b.core.edges[j].flipped(b.sign) for j in fb]
+    core = Core(edges, nb, target, 1)
+    empty = _empty_table()
+    core.set_primary(Form((), (), empty, 1, empty, 1, match, data, 1, 1))
     return RTensor(names, core, 1)
 
 

@@ -131,6 +131,7 @@ class CudaBackend:
         lib.tnsp_rt_repack_f64.argtypes = [P, FP, FP, SP, P, c_i64, c_i64, c_int, P]
         lib.tnsp_rt_repack_pair_f64.argtypes = [P, FP, FP, SP, P, c_i64, c_i64, P, FP, FP, SP, P, c_i64, c_i64, c_int, P]
         lib.tnsp_rt_gemm_f64.argtypes = [FP, FP, FP, SP, P, c_i64, c_int, c_int, P]
+        lib.tnsp_rt_dot_f64.argtypes = [P, FP, FP, P, c_int, c_int, P, c_int, c_int, P, c_i64, P, P, c_int, P]
         lib.tnsp_rt_factor_ws_ints.restype = c_i64
         lib.tnsp_rt_factor_ws_ints.argtypes = [c_i64]
         lib.tnsp_rt_svd_work_doubles.restype = c_i64
@@ -234,6 +235,18 @@ class CudaBackend:
         self._ck(self.lib.tnsp_rt_gemm_f64(ctypes.byref(fa), ctypes.byref(fb), ctypes.byref(fc), None if spec is None else ctypes.byref(spec),
                                            C.data.data_ptr(), C.data.stride(0), int(ksign), nb, self._stream()))
         return tsum
+
+    def rt_dot(self, plan, src, dst, t1, s1, t2, s2, nb):
+        """full contraction of two tensors -> (data [nb, 2 + SMAX], match, summed target or None)"""
+        out = self.rt_alloc(nb, 2)
+        match = torch.empty((nb, RT_MSTRIDE), dtype=torch.int32, device=self.device)
+        tsum = torch.empty(nb, dtype=torch.int32, device=self.device) if (t1 is not None or t2 is not None) else None
+        fs, fd = self._form(src), self._form(dst)
+        self._ck(self.lib.tnsp_rt_dot_f64(plan.data_ptr(), ctypes.byref(fs), ctypes.byref(fd), None if t1 is None else t1.data_ptr(),
+                                          0 if t1 is None or t1.shape[0] == 1 else 1, int(s1), None if t2 is None else t2.data_ptr(),
+                                          0 if t2 is None or t2.shape[0] == 1 else 1, int(s2), out.data_ptr(), out.stride(0), match.data_ptr(),
+                                          None if tsum is None else tsum.data_ptr(), nb, self._stream()))
+        return out, match, tsum
 
     # the factorisation is a short fixed sequence of launches; each step is a method of its own so that the bench's instrumented
     # pass can time the kernel classes separately (profiling.KernelTimer)

@@ -212,7 +212,24 @@ __global__ void __launch_bounds__(128) rt_match_kernel(const int* __restrict__ r
 // rt_repack: destination-driven regrouping
 // ------------------------------------------------------------------------------------------------
 constexpr int kRepackThreads = 256;
-constexpr int kPlanMax = 2 + 3 * 24;
+constexpr int kPlanEnt = 5;      // per destination edge: dim, source group (0 rows / 1 cols), source stride, magic lo, magic hi
+constexpr int kPlanMax = 2 + kPlanEnt * 24;
+
+// exact x / d for x < 2^32 with the precomputed magic m = floor(2^64 / d) + 1 (one 64-bit multiply-high instead of a division)
+__device__ __forceinline__ unsigned rt_div(unsigned x, const int* ent) {
+    const unsigned long long m = ((unsigned long long)(unsigned)ent[4] << 32) | (unsigned)ent[3];
+    return (unsigned)__umul64hi((unsigned long long)x, m);
+}
+// merged destination index -> contributions to the source's row / column merged indices
+__device__ __forceinline__ void rt_decode(const int* sp, int first, int last, unsigned idx, unsigned& sr, unsigned& sc) {
+    for (int k = last - 1; k >= first; --k) {
+        const int* ent = sp + 2 + kPlanEnt * k;
+        const unsigned qd = rt_div(idx, ent);
+        const unsigned r = idx - qd * (unsigned)ent[0];
+        idx = qd;
+        if (ent[1]) sc += r * (unsigned)ent[2]; else sr += r * (unsigned)ent[2];
+    }
+}
 
 struct RtRepackArgs {
     const int* plan; RtForm S, D; RtSpec spec; double* dst; long long dst_stride; long long dense_size;
@@ -227,7 +244,7 @@ __device__ __forceinline__ void rt_repack_body(const int* __restrict__ plan, con
     __shared__ int mt[2][RT_MSTRIDE];
     const int b = blockIdx.y, tid = threadIdx.x;
     const int n_ent = plan[0] + plan[1];
-    for (int i = tid; i < 2 + 3 * n_ent; i += kRepackThreads) sp[i] = plan[i];
+    for (int i = tid; i < 2 + kPlanEnt * n_ent; i += kRepackThreads) sp[i] = plan[i];
     if (!SRC_DENSE) {
         for (int i = tid; i < RT_HDR; i += kRepackThreads) { hdr[0][i] = S.rt[b * S.rts + i]; hdr[1][i] = S.ct[b * S.cts + i]; }
         for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mt[0][i] = S.match[b * S.mts + i];
@@ -272,22 +289,12 @@ __device__ __forceinline__ void rt_repack_body(const int* __restrict__ plan, con
             rp = d_perm_r[dR.sstart(i) + a];
             cp = d_perm_c[dC.sstart(j) + c];
         }
-        long long sr = 0, sc = 0;
-        for (int k = nr - 1; k >= 0; --k) {
-            const int dim = sp[2 + 3 * k];
-            const long long idx = rp % dim;
-            rp /= dim;
-            if (sp[3 + 3 * k]) sc += idx * sp[4 + 3 * k]; else sr += idx * sp[4 + 3 * k];
-        }
-        for (int k = nr + nc - 1; k >= nr; --k) {
-            const int dim = sp[2 + 3 * k];
-            const long long idx = cp % dim;
-            cp /= dim;
-            if (sp[3 + 3 * k]) sc += idx * sp[4 + 3 * k]; else sr += idx * sp[4 + 3 * k];
-        }
+        unsigned sr = 0, sc = 0;
+        rt_decode(sp, 0, nr, (unsigned)rp, sr, sc);
+        rt_decode(sp, nr, nr + nc, (unsigned)cp, sr, sc);
         double v = 0.0;
         if (SRC_DENSE) {
-            v = __ldg(src + sr + sc);
+            v = __ldg(src + (long long)sr + sc);
         } else {
             const int p = s_inv_r[sr], q = s_inv_c[sc];
             if (p < sR.nvalid() && q < sC.nvalid()) {
@@ -309,6 +316,84 @@ __global__ void __launch_bounds__(kRepackThreads) rt_repack_kernel(RtRepackArgs 
 __global__ void __launch_bounds__(kRepackThreads) rt_repack_pair_kernel(RtRepackPair p, unsigned long long* stats) {
     const RtRepackArgs& q = p.a[blockIdx.z];
     rt_repack_body<false, false>(q.plan, q.S, q.D, q.spec, q.dst, q.dst_stride, q.dense_size, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+// rt_dot: contraction of ALL edges of two tensors (the closing contraction of a strip, amplitude x hole, ...): per chain the sum
+// over the stored elements of D of D[e] * S[the same multi-index].  Same index walk as the regrouping above, but nothing is
+// regrouped or written: no merged group over the whole tensor (whose table would be as large as the tensor), no sorted copy.
+// One CTA per chain, fixed summation order (deterministic).  Also writes the 1-element result's pairing table.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDotThreads = 512;
+__global__ void __launch_bounds__(kDotThreads) rt_dot_kernel(const int* __restrict__ plan, RtForm S, RtForm D, const int* __restrict__ t1, int t1st,
+                                                             int s1, const int* __restrict__ t2, int t2st, int s2, double* __restrict__ out,
+                                                             long long out_stride, int* __restrict__ match, int* __restrict__ tsum,
+                                                             unsigned long long* stats) {
+    __shared__ int sp[kPlanMax];
+    __shared__ int hdr[4][RT_HDR];
+    __shared__ int mt[2][RT_MSTRIDE];
+    __shared__ double red[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n_ent = plan[0] + plan[1];
+    for (int i = tid; i < 2 + kPlanEnt * n_ent; i += kDotThreads) sp[i] = plan[i];
+    for (int i = tid; i < RT_HDR; i += kDotThreads) {
+        hdr[0][i] = S.rt[b * S.rts + i]; hdr[1][i] = S.ct[b * S.cts + i];
+        hdr[2][i] = D.rt[b * D.rts + i]; hdr[3][i] = D.ct[b * D.cts + i];
+    }
+    for (int i = tid; i < RT_MSTRIDE; i += kDotThreads) { mt[0][i] = S.match[b * S.mts + i]; mt[1][i] = D.match[b * D.mts + i]; }
+    __syncthreads();
+    const int nr = sp[0], nc = sp[1];
+    const RtTab sR(hdr[0]), sC(hdr[1]), dR(hdr[2]), dC(hdr[3]);
+    const RtMatch sM(mt[0]), dM(mt[1]);
+    const long long total = dM.size();
+    const double* src = S.data + (long long)b * S.dstride;
+    const double* dat = D.data + (long long)b * D.dstride;
+    const int* s_inv_r = S.rt + b * S.rts + RT_HDR + S.M;
+    const int* s_inv_c = S.ct + b * S.cts + RT_HDR + S.N;
+    const int* d_perm_r = D.rt + b * D.rts + RT_HDR;
+    const int* d_perm_c = D.ct + b * D.cts + RT_HDR;
+    double acc = 0.0;
+    for (long long e = tid; e < total; e += kDotThreads) {
+        int lo = 0, hi = dR.nsec();
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (dM.moff(mid) <= e) lo = mid; else hi = mid;
+        }
+        const int i = lo;
+        const int j = dM.mcol(i);
+        const int local = (int)(e - dM.moff(i));
+        const int n = j >= 0 ? dC.count(j) : 0;
+        const int m = dR.count(i);
+        if (j < 0 || local >= m * n) continue;
+        const int a = local / n, c = local - a * n;
+        long long rp = d_perm_r[dR.sstart(i) + a];
+        long long cp = d_perm_c[dC.sstart(j) + c];
+        unsigned sr = 0, sc = 0;
+        rt_decode(sp, 0, nr, (unsigned)rp, sr, sc);
+        rt_decode(sp, nr, nr + nc, (unsigned)cp, sr, sc);
+        const int p = s_inv_r[sr], q = s_inv_c[sc];
+        if (p < sR.nvalid() && q < sC.nvalid()) {
+            const int si = sR.sector_of(p);
+            const int sj = sM.mcol(si);
+            if (sj >= 0 && q >= sC.sstart(sj) && q < sC.sstart(sj + 1))
+                acc += dat[e] * __ldg(src + sM.moff(si) + (long long)(p - sR.sstart(si)) * sC.count(sj) + (q - sC.sstart(sj)));
+        }
+    }
+    acc = block_sum(acc, red);
+    if (tid == 0) {
+        int t = 0;
+        if (t1) t += s1 * t1[(long long)b * t1st];
+        if (t2) t += s2 * t2[(long long)b * t2st];
+        if (tsum) tsum[b] = t;
+        // the result has no indexed edge: its single element exists iff the summed target vanishes
+        int* Mrow = match + (long long)b * RT_MSTRIDE;
+        Mrow[0] = t == 0 ? 2 : 0; Mrow[1] = 0; Mrow[2] = 0; Mrow[3] = t == 0 ? 2 : 0; Mrow[3 + RT_SMAX] = t == 0 ? 0 : -1;
+        double* o = out + (long long)b * out_stride;
+        o[0] = t == 0 ? acc : 0.0;
+        o[1] = 0.0;
+        if (stats) { atomicAdd(&stats[0], 2ull * (unsigned long long)total); atomicAdd(&stats[1], 2ull * (unsigned long long)total);
+                     atomicAdd(&stats[2], 16ull * (unsigned long long)total); atomicAdd(&stats[8], 1ull); }
+    }
 }
 
 // the binary search above lands on the LAST sector whose offset is <= e; sectors without partner share the offset of their
@@ -704,6 +789,15 @@ extern "C" int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, co
     rt_gemm_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(to_form(a), to_form(b), to_form(c), to_spec(c_match), c_data, c_stride, ksign,
                                                            rt_stats_ptr());
     return check_launch("tnsp_rt_gemm_f64");
+}
+
+extern "C" int tnsp_rt_dot_f64(const int32_t* plan, const tnsp_rt_form* src, const tnsp_rt_form* dst, const int32_t* t1, int t1_stride, int s1,
+                               const int32_t* t2, int t2_stride, int s2, double* out, int64_t out_stride, int32_t* match, int32_t* tsum, int nb,
+                               void* stream) {
+    if (nb == 0) return 0;
+    rt_dot_kernel<<<nb, kDotThreads, 0, (cudaStream_t)stream>>>(plan, to_form(src), to_form(dst), t1, t1_stride, s1, t2, t2_stride, s2, out, out_stride,
+                                                                match, tsum, rt_stats_ptr());
+    return check_launch("tnsp_rt_dot_f64");
 }
 
 extern "C" int tnsp_rt_scale_f64(const double* x, int64_t x_stride, const int32_t* match, int64_t match_stride, const double* alpha, int alpha_stride,
