@@ -319,6 +319,124 @@ __global__ void __launch_bounds__(kRepackThreads) rt_repack_pair_kernel(RtRepack
 }
 
 // ------------------------------------------------------------------------------------------------
+// Regrouping between two sector-compact layouts, tile by tile: a CTA owns RTR destination rows x RTC destination columns of ONE
+// destination sector, decodes every row and every column of the tile once (RTR + RTC index decodes into shared memory instead of
+// RTR x RTC) and then moves the elements with two additions, two table look-ups and one sector search each.
+// ------------------------------------------------------------------------------------------------
+constexpr int RTR = 128, RTC = 128;      // largest tile extents; the tile shape is chosen per sector: tc = 2^ceil(log2 n) <= 128, tr = 2048 / tc <= 128
+struct RtTileDesc { int m, n, tn, start, rstart, cstart, moff, tr, tc; };
+
+__device__ __forceinline__ void rt_repack_tiles(const int* __restrict__ plan, const RtForm& S, const RtForm& D, const RtSpec& spec,
+                                                double* __restrict__ dst, long long dst_stride, unsigned long long* stats) {
+    __shared__ int sp[kPlanMax];
+    __shared__ int hS[2][RT_HDR];
+    __shared__ int mS[RT_MSTRIDE], mD[RT_MSTRIDE];
+    __shared__ RtTileDesc dsc[RT_SMAX];
+    __shared__ int n_desc, n_items, cnt[2], tot[2];
+    __shared__ unsigned rsr[RTR], rsc[RTR], csr[RTC], csc[RTC];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_ent = plan[0] + plan[1];
+    for (int i = tid; i < 2 + kPlanEnt * n_ent; i += kRepackThreads) sp[i] = plan[i];
+    for (int i = tid; i < RT_HDR; i += kRepackThreads) { hS[0][i] = S.rt[b * S.rts + i]; hS[1][i] = S.ct[b * S.cts + i]; }
+    for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mS[i] = S.match[b * S.mts + i];
+    const int* gDr = D.rt + b * D.rts;
+    const int* gDc = D.ct + b * D.cts;
+    if (spec.on) rt_match_cta(gDr, gDc, spec, b, mD, blockIdx.x == 0);
+    else {
+        for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mD[i] = D.match[b * D.mts + i];
+        __syncthreads();
+    }
+    {
+        const RtTab dR(gDr), dC(gDc);
+        const RtMatch dM(mD);
+        const int nsec = max(dR.nsec(), 0);
+        int here = 0;
+        RtTileDesc d;
+        d.m = d.n = d.tn = d.start = d.rstart = d.cstart = d.moff = 0; d.tr = d.tc = 1;
+        if (tid < nsec) {
+            const int j = dM.mcol(tid);
+            if (j >= 0) {
+                d.m = dR.count(tid); d.n = dC.count(j);
+                if (d.m > 0 && d.n > 0) {
+                    int tc = 1;
+                    while (tc < d.n && tc < RTC) tc <<= 1;
+                    d.tc = tc;
+                    d.tr = min(RTR, 2048 / tc);
+                    d.tn = (d.n + d.tc - 1) / d.tc;
+                    here = ((d.m + d.tr - 1) / d.tr) * d.tn;
+                    d.rstart = dR.sstart(tid); d.cstart = dC.sstart(j); d.moff = dM.moff(tid);
+                }
+            }
+        }
+        const unsigned has = __ballot_sync(0xffffffffu, here > 0);
+        int incl = here;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (warp < 2 && lane == 31) { cnt[warp] = __popc(has); tot[warp] = incl; }
+        __syncthreads();
+        if (warp < 2 && here > 0) {
+            const int slot = (warp ? cnt[0] : 0) + __popc(has & ((1u << lane) - 1u));
+            d.start = (warp ? tot[0] : 0) + incl - here;
+            dsc[slot] = d;
+        }
+        if (tid == 0) { n_desc = cnt[0] + cnt[1]; n_items = tot[0] + tot[1]; }
+        __syncthreads();
+        if (stats && blockIdx.x == 0 && tid == 0) atomicAdd(&stats[3], (unsigned long long)dM.size());
+    }
+    const int nr = sp[0], nc = sp[1];
+    const RtTab sR(hS[0]), sC(hS[1]);
+    const RtMatch sM(mS);
+    const double* src = S.data + (long long)b * S.dstride;
+    double* out = dst + (long long)b * dst_stride;
+    const int* s_inv_r = S.rt + b * S.rts + RT_HDR + S.M;
+    const int* s_inv_c = S.ct + b * S.cts + RT_HDR + S.N;
+    const int* d_perm_r = gDr + RT_HDR;
+    const int* d_perm_c = gDc + RT_HDR;
+    const int nd = n_desc, total = n_items;
+    const int s_nvr = sR.nvalid(), s_nvc = sC.nvalid();
+    int cur = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        while (cur + 1 < nd && dsc[cur + 1].start <= item) ++cur;
+        const RtTileDesc e = dsc[cur];
+        const int t = item - e.start;
+        const int r0 = (t / e.tn) * e.tr, c0 = (t % e.tn) * e.tc;
+        const int rows = min(e.tr, e.m - r0), cols = min(e.tc, e.n - c0);
+        __syncthreads();        // the previous tile's contributions are no longer read
+        if (tid < rows) {
+            unsigned x = 0, y = 0;
+            rt_decode(sp, 0, nr, (unsigned)d_perm_r[e.rstart + r0 + tid], x, y);
+            rsr[tid] = x; rsc[tid] = y;
+        } else if (tid >= 128 && tid - 128 < cols) {
+            unsigned x = 0, y = 0;
+            rt_decode(sp, nr, nr + nc, (unsigned)d_perm_c[e.cstart + c0 + tid - 128], x, y);
+            csr[tid - 128] = x; csc[tid - 128] = y;
+        }
+        __syncthreads();
+        for (int el = tid; el < rows * cols; el += kRepackThreads) {
+            const int a = el / cols, c = el - a * cols;
+            const int p = s_inv_r[rsr[a] + csr[c]], q = s_inv_c[rsc[a] + csc[c]];
+            double v = 0.0;
+            if (p < s_nvr && q < s_nvc) {
+                const int i = sR.sector_of(p);
+                const int j = sM.mcol(i);
+                if (j >= 0 && q >= sC.sstart(j) && q < sC.sstart(j + 1))
+                    v = __ldg(src + sM.moff(i) + (long long)(p - sR.sstart(i)) * sC.count(j) + (q - sC.sstart(j)));
+            }
+            out[e.moff + (long long)(r0 + a) * e.n + c0 + c] = v;
+        }
+        if (t == 0 && tid == 0 && ((e.m * e.n) & 1)) out[e.moff + (long long)e.m * e.n] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(kRepackThreads) rt_repack_tile_kernel(RtRepackArgs p, unsigned long long* stats) {
+    rt_repack_tiles(p.plan, p.S, p.D, p.spec, p.dst, p.dst_stride, stats);
+}
+__global__ void __launch_bounds__(kRepackThreads) rt_repack_tile_pair_kernel(RtRepackPair p, unsigned long long* stats) {
+    const RtRepackArgs& q = p.a[blockIdx.z];
+    rt_repack_tiles(q.plan, q.S, q.D, q.spec, q.dst, q.dst_stride, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
 // rt_dot: contraction of ALL edges of two tensors (the closing contraction of a strip, amplitude x hole, ...): per chain the sum
 // over the stored elements of D of D[e] * S[the same multi-index].  Same index walk as the regrouping above, but nothing is
 // regrouped or written: no merged group over the whole tensor (whose table would be as large as the tensor), no sorted copy.
@@ -544,9 +662,14 @@ constexpr int WR = 16;          // rows per warp item
 constexpr int WC = 32;          // columns per warp item (4 DMMA fragments)
 constexpr int kGemmWarps = 8;
 
+// per-sector descriptor built once per CTA in shared memory: the warps then find their items without touching the tables again
+struct RtGemmDesc { int m, n, k, tn, start; long long aoff, boff, coff; };
+
 __global__ void __launch_bounds__(kGemmWarps * 32, 4) rt_gemm_warp_kernel(RtForm A, RtForm B, RtForm C, RtSpec spec, double* __restrict__ cdata,
                                                                           long long cstride, int ksign, unsigned long long* stats) {
     __shared__ int mC[RT_MSTRIDE];
+    __shared__ RtGemmDesc dsc[RT_SMAX];
+    __shared__ int n_desc, n_items;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int* gAr = A.rt + b * A.rts;
     const int* gAk = A.ct + b * A.cts;
@@ -557,87 +680,111 @@ __global__ void __launch_bounds__(kGemmWarps * 32, 4) rt_gemm_warp_kernel(RtForm
         for (int i = tid; i < RT_MSTRIDE; i += kGemmWarps * 32) mC[i] = C.match[b * C.mts + i];
         __syncthreads();
     }
-    const RtTab aR(gAr), aK(gAk), bK(gBk), bN(gBn);
-    const RtMatch MA(A.match + b * A.mts), MB(B.match + b * B.mts), MC(mC);
+    {
+        const RtTab aR(gAr), aK(gAk), bK(gBk), bN(gBn);
+        const RtMatch MA(A.match + b * A.mts), MB(B.match + b * B.mts), MC(mC);
+        const int nsec = max(aR.nsec(), 0);
+        // one thread per row sector: operands and tile counts (every thread's loads are independent: one latency, not nsec)
+        int here = 0;
+        RtGemmDesc d;
+        d.m = d.n = d.k = d.tn = d.start = 0; d.aoff = d.boff = d.coff = 0;
+        if (tid < nsec) {
+            const int i = tid;
+            const int jc = MC.mcol(i);
+            if (jc >= 0) {
+                d.m = aR.count(i); d.n = bN.count(jc);
+                if (d.m > 0 && d.n > 0) {
+                    d.tn = (d.n + WC - 1) / WC;
+                    here = ((d.m + WR - 1) / WR) * d.tn;
+                    d.coff = MC.moff(i);
+                    const int jk = MA.mcol(i);
+                    if (jk >= 0) {
+                        const int ib = bK.find(ksign * aK.skey(jk));
+                        if (ib >= 0 && MB.mcol(ib) == jc) {
+                            d.k = min(aK.count(jk), bK.count(ib));
+                            d.aoff = MA.moff(i);
+                            d.boff = MB.moff(ib);
+                        }
+                    }
+                }
+            }
+        }
+        // compact the non-empty sectors (order preserved) with a warp-level scan over <= 64 entries (two warps)
+        __shared__ int cnt[2], tot[2];
+        const unsigned has = __ballot_sync(0xffffffffu, here > 0);
+        int incl = here;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (warp < 2 && lane == 31) { cnt[warp] = __popc(has); tot[warp] = incl; }
+        __syncthreads();
+        if (warp < 2 && here > 0) {
+            const int slot = (warp ? cnt[0] : 0) + __popc(has & ((1u << lane) - 1u));
+            d.start = (warp ? tot[0] : 0) + incl - here;
+            dsc[slot] = d;
+        }
+        if (tid == 0) { n_desc = cnt[0] + cnt[1]; n_items = tot[0] + tot[1]; }
+        __syncthreads();
+        if (stats && blockIdx.x == 0 && tid < n_desc) {
+            const RtGemmDesc& e = dsc[tid];
+            const int tm = (e.m + WR - 1) / WR;
+            unsigned long long issued = 0;
+            for (int t = 0; t < e.tn; ++t) issued += (unsigned long long)tm * 2 * ((min(WC, e.n - t * WC) + 7) / 8) * ((e.k + 3) / 4);
+            atomicAdd(&stats[0], 2ull * e.m * e.n * e.k);
+            atomicAdd(&stats[1], issued * 512ull);
+            atomicAdd(&stats[2], 8ull * ((unsigned long long)e.m * e.k + (unsigned long long)e.k * e.n + (unsigned long long)e.m * e.n));
+            atomicAdd(&stats[8], 1ull);
+        }
+    }
     const double* a = A.data + (long long)b * A.dstride;
     const double* bb = B.data + (long long)b * B.dstride;
     double* c = cdata + (long long)b * cstride;
-    const int nsec = max(aR.nsec(), 0);
     const int g = lane >> 2, q = lane & 3;
-    int item = blockIdx.x * kGemmWarps + warp;
-    const int step = gridDim.x * kGemmWarps;
-    int first = 0;
-    for (int i = 0; i < nsec; ++i) {
-        const int jc = MC.mcol(i);
-        if (jc < 0) continue;
-        const int m = aR.count(i), n = bN.count(jc);
-        if (m == 0 || n == 0) continue;
-        const int tm = (m + WR - 1) / WR, tn = (n + WC - 1) / WC;
-        const int here = tm * tn;
-        if (item >= first + here) { first += here; continue; }
-        int k = 0;
-        long long aoff = 0, boff = 0;
-        const int jk = MA.mcol(i);
-        if (jk >= 0) {
-            const int ib = bK.find(ksign * aK.skey(jk));
-            if (ib >= 0 && MB.mcol(ib) == jc) {
-                k = min(aK.count(jk), bK.count(ib));
-                aoff = MA.moff(i);
-                boff = MB.moff(ib);
+    const int nd = n_desc, total = n_items;
+    int cur = 0;
+    for (int item = blockIdx.x * kGemmWarps + warp; item < total; item += gridDim.x * kGemmWarps) {
+        while (cur + 1 < nd && dsc[cur + 1].start <= item) ++cur;
+        const RtGemmDesc& e = dsc[cur];
+        const int m = e.m, n = e.n, k = e.k;
+        const int t = item - e.start;
+        const int r0 = (t / e.tn) * WR, c0 = (t % e.tn) * WC;
+        const int cols = min(WC, n - c0);
+        const int nfr = (cols + 7) >> 3;
+        double acc[2][4][2];
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+        const bool row0 = r0 + g < m, row1 = r0 + 8 + g < m;
+        const double* ap0 = a + e.aoff + (long long)(r0 + g) * k + q;
+        const double* ap1 = ap0 + 8ll * k;
+        const double* bp = bb + e.boff + (long long)q * n + c0 + g;
+        for (int ks = 0; ks < k; ks += 4) {
+            const bool kin = ks + q < k;
+            const double a0 = (kin && row0) ? __ldg(ap0 + ks) : 0.0;
+            const double a1 = (kin && row1) ? __ldg(ap1 + ks) : 0.0;
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                if (y < nfr) {
+                    const double bv = (kin && y * 8 + g < cols) ? __ldg(bp + (long long)ks * n + y * 8) : 0.0;
+                    rt_dmma(acc[0][y][0], acc[0][y][1], a0, bv);
+                    rt_dmma(acc[1][y][0], acc[1][y][1], a1, bv);
+                }
             }
         }
-        const long long coff = MC.moff(i);
-        if (stats && blockIdx.x == 0 && tid == 0) {
-            unsigned long long issued = 0;
-            for (int t = 0; t < tn; ++t) issued += (unsigned long long)tm * 2 * ((min(WC, n - t * WC) + 7) / 8) * ((k + 3) / 4);
-            atomicAdd(&stats[0], 2ull * m * n * k);
-            atomicAdd(&stats[1], issued * 512ull);
-            atomicAdd(&stats[2], 8ull * ((unsigned long long)m * k + (unsigned long long)k * n + (unsigned long long)m * n));
-            atomicAdd(&stats[8], 1ull);
-        }
-        for (; item < first + here; item += step) {
-            const int t = item - first;
-            const int r0 = (t / tn) * WR, c0 = (t % tn) * WC;
-            const int cols = min(WC, n - c0);
-            const int nfr = (cols + 7) >> 3;
-            double acc[2][4][2];
 #pragma unroll
-            for (int x = 0; x < 2; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-            const bool row0 = r0 + g < m, row1 = r0 + 8 + g < m;
-            const double* ap0 = a + aoff + (long long)(r0 + g) * k + q;
-            const double* ap1 = ap0 + 8ll * k;
-            const double* bp = bb + boff + (long long)q * n + c0 + g;
-            for (int ks = 0; ks < k; ks += 4) {
-                const bool kin = ks + q < k;
-                const double a0 = (kin && row0) ? __ldg(ap0 + ks) : 0.0;
-                const double a1 = (kin && row1) ? __ldg(ap1 + ks) : 0.0;
+        for (int x = 0; x < 2; ++x) {
+            const int r = r0 + x * 8 + g;
+            if (r < m) {
+                double* cp = c + e.coff + (long long)r * n + c0;
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
-                    if (y < nfr) {
-                        const double bv = (kin && y * 8 + g < cols) ? __ldg(bp + (long long)ks * n + y * 8) : 0.0;
-                        rt_dmma(acc[0][y][0], acc[0][y][1], a0, bv);
-                        rt_dmma(acc[1][y][0], acc[1][y][1], a1, bv);
-                    }
+                    const int cc = y * 8 + 2 * q;
+                    if (cc < cols) cp[cc] = acc[x][y][0];
+                    if (cc + 1 < cols) cp[cc + 1] = acc[x][y][1];
                 }
             }
-#pragma unroll
-            for (int x = 0; x < 2; ++x) {
-                const int r = r0 + x * 8 + g;
-                if (r < m) {
-                    double* cp = c + coff + (long long)r * n + c0;
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const int cc = y * 8 + 2 * q;
-                        if (cc < cols) cp[cc] = acc[x][y][0];
-                        if (cc + 1 < cols) cp[cc + 1] = acc[x][y][1];
-                    }
-                }
-            }
-            if (t == 0 && lane == 0 && ((m * n) & 1)) c[coff + (long long)m * n] = 0.0;     // alignment pad of an odd-sized sector
         }
-        first += here;
+        if (t == 0 && lane == 0 && ((m * n) & 1)) c[e.coff + (long long)m * n] = 0.0;     // alignment pad of an odd-sized sector
     }
 }
 
@@ -729,6 +876,14 @@ extern "C" int tnsp_rt_match_i32(const int32_t* rt, int64_t rt_stride, int rs, c
     return check_launch("tnsp_rt_match_i32");
 }
 
+// tiles of the densest possible layout / 2 (a CTA loops over its tiles; sectors only cover a fraction of the M x N index space)
+static dim3 tile_grid(int64_t M, int64_t N, int nb, int nz) {
+    int64_t gx = (M * N / 2048 + 7) / 8;
+    if (gx < 1) gx = 1;
+    if (gx > 512) gx = 512;
+    return dim3((unsigned)gx, (unsigned)nb, (unsigned)nz);
+}
+
 static dim3 repack_grid(int64_t work, int nb, int nz) {
     int64_t gx = (work + kRepackThreads * 4 - 1) / (kRepackThreads * 4);
     if (gx < 1) gx = 1;
@@ -750,7 +905,7 @@ extern "C" int tnsp_rt_repack_f64(const int32_t* plan, const tnsp_rt_form* src, 
     cudaStream_t st = (cudaStream_t)stream;
     if (sd) rt_repack_kernel<true, false><<<grid, kRepackThreads, 0, st>>>(p, rt_stats_ptr());
     else if (dd) rt_repack_kernel<false, true><<<grid, kRepackThreads, 0, st>>>(p, rt_stats_ptr());
-    else rt_repack_kernel<false, false><<<grid, kRepackThreads, 0, st>>>(p, rt_stats_ptr());
+    else rt_repack_tile_kernel<<<tile_grid(dst->M, dst->N, nb, 1), kRepackThreads, 0, st>>>(p, rt_stats_ptr());
     return check_launch("tnsp_rt_repack_f64");
 }
 
@@ -765,7 +920,8 @@ extern "C" int tnsp_rt_repack_pair_f64(const int32_t* plan0, const tnsp_rt_form*
     p.a[0].dst_stride = dst_stride0; p.a[0].dense_size = 0;
     p.a[1].plan = plan1; p.a[1].S = to_form(src1); p.a[1].D = to_form(dst1); p.a[1].spec = to_spec(match1); p.a[1].dst = dst_data1;
     p.a[1].dst_stride = dst_stride1; p.a[1].dense_size = 0;
-    rt_repack_pair_kernel<<<repack_grid(work0 > work1 ? work0 : work1, nb, 2), kRepackThreads, 0, (cudaStream_t)stream>>>(p, rt_stats_ptr());
+    const dim3 g0 = tile_grid(dst0->M, dst0->N, nb, 2), g1 = tile_grid(dst1->M, dst1->N, nb, 2);
+    rt_repack_tile_pair_kernel<<<dim3(g0.x > g1.x ? g0.x : g1.x, nb, 2), kRepackThreads, 0, (cudaStream_t)stream>>>(p, rt_stats_ptr());
     return check_launch("tnsp_rt_repack_pair_f64");
 }
 
@@ -776,7 +932,7 @@ extern "C" int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, co
         // small sectors: warp-autonomous kernel; the grid covers the most items a chain can have (every sector adds at most one
         // partial piece per direction), spare CTAs leave at once
         int64_t items = ((a->M + WR - 1) / WR + RT_SMAX / 4) * ((b->N + WC - 1) / WC);
-        int64_t gx = (items + 2 * kGemmWarps - 1) / (2 * kGemmWarps);      // about two items per warp
+        int64_t gx = (items + 4 * kGemmWarps - 1) / (4 * kGemmWarps);      // a few items per warp: the CTA prologue is amortised
         if (gx > 256) gx = 256;
         rt_gemm_warp_kernel<<<dim3((unsigned)gx, (unsigned)nb), kGemmWarps * 32, 0, (cudaStream_t)stream>>>(
             to_form(a), to_form(b), to_form(c), to_spec(c_match), c_data, c_stride, ksign, rt_stats_ptr());
