@@ -2085,6 +2085,34 @@ static bool desc_applicable(const int64_t* sh, int ns) {
 //   (k0 = staging offset of its bond indices, uoff, voff, q = min(m, n) or 0, kept, new bond offset), then dest[kfull]:
 //   position of a staged singular triplet inside its sector's kept block (-1: cut)
 // ================================================================================================
+constexpr bool kRtUseWarpClass = false;
+constexpr int kRtClasses = 4;                 // work queue of the rt_* kernels: counts at qctl[0..3], tickets at qctl[4..7]
+constexpr int kRtQrWarpDoubles = 6144;        // 48 KiB per warp, 4 warps per CTA
+constexpr int kRtQrWarps = 4;
+constexpr int kRtSvdWarpDoubles = 3072;       // 24 KiB per warp, 8 warps per CTA
+constexpr int kRtSvdWarps = 8;
+__host__ __device__ inline int64_t rt_qr_warp_need(int64_t p, int64_t q, int64_t k) { return p * (q | 1) + k + 2; }
+__host__ __device__ inline int64_t rt_svd_warp_need(int64_t p, int64_t q) { return q * (p + (p & 1)) + q * (q + (q & 1)) + q + 2; }
+
+// pops the next item of class `which` (rt layout of qctl) for a whole CTA / for one warp
+__device__ __forceinline__ bool rt_pop_cta(int which, int* qctl, const int2* qitems, long long qcap, int* sh_ticket, int2& item) {
+    __syncthreads();
+    if (threadIdx.x == 0) *sh_ticket = atomicAdd(&qctl[4 + which], 1);
+    __syncthreads();
+    const int t = *sh_ticket;
+    if (t >= qctl[which]) return false;
+    item = qitems[(long long)which * qcap + t];
+    return true;
+}
+__device__ __forceinline__ bool rt_pop_warp(int which, int* qctl, const int2* qitems, long long qcap, int2& item) {
+    int t = 0;
+    if ((threadIdx.x & 31) == 0) t = atomicAdd(&qctl[4 + which], 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= qctl[which]) return false;
+    item = qitems[(long long)which * qcap + t];
+    return true;
+}
+
 constexpr int RT_WS_HDR = 8;
 constexpr int RT_WS_SEC = 6;
 __host__ __device__ inline int64_t rt_ws_stride(int64_t kfull) { return RT_WS_HDR + RT_WS_SEC * RT_SMAX + kfull; }
@@ -2121,7 +2149,14 @@ __global__ void __launch_bounds__(128) rt_factor_plan_kernel(RtForm F, int kind,
         if (kind == 2) st_bytes += 8ull * ((unsigned long long)m * n + (unsigned long long)m * q + (unsigned long long)q * n + q);
         else { st_bytes += 8ull * (2ull * m * n + (unsigned long long)m * q + (unsigned long long)q * n); st_flops += 4ull * m * n * q; }
         k0 += q;
-        const int cls = need > kQSmallDoubles ? 0 : (need > kQMidDoubles ? 1 : 2);
+        int cls = need > kQSmallDoubles ? 0 : (need > kQMidDoubles ? 1 : 2);
+        // optional class 3: one WARP per small sector, no block barrier inside the factorisation.  MEASURED SLOWER on cfg2 (B200, 2368
+        // chains: QR 1296 x 216 10.5 vs 6.5 ms, SVD 216 x 216 10.0 vs 8.9 ms per launch: a single warp's dependent shuffle chains
+        // take longer than the barriers they save, and 48 KiB per sector leave 4 sectors per SM), so it is switched off.
+        if (kRtUseWarpClass) {
+            if (kind == 2) { const int pp = m >= n ? m : n; if (q <= kWarpSectorMax && rt_svd_warp_need(pp, q) <= kRtSvdWarpDoubles) cls = 3; }
+            else if (rt_qr_warp_need(m, n, q) <= kRtQrWarpDoubles) cls = 3;
+        }
         const int at = atomicAdd(&qctl[cls], 1);
         qitems[(long long)cls * qcap + at] = make_int2(b, i);
     }
@@ -2149,7 +2184,7 @@ __global__ void __launch_bounds__(kQBigThreads) rt_qr_work_kernel(RtForm F, int 
     double* work = reinterpret_cast<double*>(smem_raw);
     const int tid = threadIdx.x, nt = blockDim.x;
     int2 item;
-    while (pop_item(which, qctl, qitems, qcap, &sh_ticket, item)) {
+    while (rt_pop_cta(which, qctl, qitems, qcap, &sh_ticket, item)) {
         const int b = item.x, i = item.y;
         const RtTab R(F.rt + b * F.rts), C(F.ct + b * F.cts), Bd(bond + b * bonds);
         const RtMatch Mt(F.match + b * F.mts), M1(m1 + (long long)b * RT_MSTRIDE), M2(m2 + (long long)b * RT_MSTRIDE);
@@ -2210,7 +2245,7 @@ __global__ void __launch_bounds__(kQBigThreads) rt_svd_work_kernel(RtForm F, dou
     double* work = reinterpret_cast<double*>(smem_raw);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     int2 item;
-    while (pop_item(which, qctl, qitems, qcap, &sh_ticket, item)) {
+    while (rt_pop_cta(which, qctl, qitems, qcap, &sh_ticket, item)) {
         const int b = item.x, i = item.y;
         const RtTab R(F.rt + b * F.rts), C(F.ct + b * F.cts);
         const RtMatch Mt(F.match + b * F.mts);
@@ -2256,6 +2291,167 @@ __global__ void __launch_bounds__(kQBigThreads) rt_svd_work_kernel(RtForm F, dou
             if (tall) Vs[e] = V[(int64_t)c * ldq + t];
             else { const double sg = sig[c]; Vs[e] = sg > 0.0 ? G[(int64_t)c * ldp + t] / sg : 0.0; }
         }
+    }
+}
+
+// one WARP per small sector (class 3 of the queue): unblocked Householder QR in the warp's private slice of shared memory, lanes
+// over rows (tall) or over columns (wide); no block barrier anywhere (cfg2: 185 x 31 sectors, ~30 us each instead of ~170 us on a
+// 256-thread CTA whose every panel column costs a barrier)
+__global__ void __launch_bounds__(32 * kRtQrWarps) rt_qr_warp_kernel(RtForm F, int frs, const int* __restrict__ t1, int t1st, int t1s,
+                                                                     const int* __restrict__ bond, long long bonds, const int* __restrict__ m1,
+                                                                     double* __restrict__ first, long long fst, const int* __restrict__ m2,
+                                                                     double* __restrict__ second, long long sst, int* qctl,
+                                                                     const int2* __restrict__ qitems, long long qcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* X = reinterpret_cast<double*>(smem_raw) + (size_t)warp * kRtQrWarpDoubles;
+    int2 item;
+    while (rt_pop_warp(3, qctl, qitems, qcap, item)) {
+        const int b = item.x, i = item.y;
+        const RtTab R(F.rt + b * F.rts), C(F.ct + b * F.cts), Bd(bond + b * bonds);
+        const RtMatch Mt(F.match + b * F.mts), M1(m1 + (long long)b * RT_MSTRIDE), M2(m2 + (long long)b * RT_MSTRIDE);
+        const int j = Mt.mcol(i);
+        const int p = R.count(i), q = C.count(j);
+        const int k = p < q ? p : q;
+        const int ld = q | 1;
+        double* tau = X + p * ld;
+        const double* A = F.data + (long long)b * F.dstride + Mt.moff(i);
+        const int tq = t1 ? t1s * t1[(long long)b * t1st] : 0;
+        const int ib = Bd.find(tq - frs * R.skey(i));
+        double* O1 = M1.mcol(i) >= 0 ? first + (long long)b * fst + M1.moff(i) : nullptr;
+        double* O2 = (ib >= 0 && M2.mcol(ib) >= 0) ? second + (long long)b * sst + M2.moff(ib) : nullptr;
+        for (int e = lane; e < p * q; e += 32) X[(e / q) * ld + (e % q)] = __ldg(A + e);
+        __syncwarp();
+        const bool by_rows = p >= q;
+        for (int c0 = 0; c0 < k; ++c0) {
+            double part = 0.0;
+            for (int r = c0 + 1 + lane; r < p; r += 32) { const double v = X[r * ld + c0]; part += v * v; }
+            const double xnorm2 = warp_sum(part);
+            const double alpha = X[c0 * ld + c0];
+            double tj = 0.0, scale = 0.0, beta = alpha;
+            if (xnorm2 != 0.0) {
+                beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+                tj = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            __syncwarp();
+            if (tj != 0.0) {
+                for (int r = c0 + 1 + lane; r < p; r += 32) X[r * ld + c0] *= scale;
+                __syncwarp();
+                if (by_rows) {
+                    for (int c = c0 + 1; c < q; ++c) {
+                        double w = 0.0;
+                        for (int r = c0 + 1 + lane; r < p; r += 32) w += X[r * ld + c0] * X[r * ld + c];
+                        w = (warp_sum(w) + X[c0 * ld + c]) * tj;
+                        for (int r = c0 + 1 + lane; r < p; r += 32) X[r * ld + c] -= w * X[r * ld + c0];
+                        __syncwarp();
+                        if (lane == 0) X[c0 * ld + c] -= w;
+                    }
+                } else {
+                    for (int c = c0 + 1 + lane; c < q; c += 32) {
+                        double w = X[c0 * ld + c];
+                        for (int r = c0 + 1; r < p; ++r) w += X[r * ld + c0] * X[r * ld + c];
+                        w *= tj;
+                        X[c0 * ld + c] -= w;
+                        for (int r = c0 + 1; r < p; ++r) X[r * ld + c] -= w * X[r * ld + c0];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { tau[c0] = tj; X[c0 * ld + c0] = beta; }
+            __syncwarp();
+        }
+        if (O2) {
+            for (int e = lane; e < k * q; e += 32) { const int r = e / q, c = e - r * q; O2[e] = (c >= r) ? X[r * ld + c] : 0.0; }
+            if (lane == 0 && ((k * q) & 1)) O2[k * q] = 0.0;
+        }
+        __syncwarp();
+        for (int c0 = k - 1; c0 >= 0; --c0) {
+            const double tj = tau[c0];
+            if (by_rows) {
+                for (int c = c0 + 1; c < k; ++c) {
+                    double w = 0.0;
+                    for (int r = c0 + 1 + lane; r < p; r += 32) w += X[r * ld + c0] * X[r * ld + c];
+                    w = (warp_sum(w) + X[c0 * ld + c]) * tj;
+                    for (int r = c0 + 1 + lane; r < p; r += 32) X[r * ld + c] -= w * X[r * ld + c0];
+                    __syncwarp();
+                    if (lane == 0) X[c0 * ld + c] -= w;
+                }
+            } else {
+                for (int c = c0 + 1 + lane; c < k; c += 32) {
+                    double w = X[c0 * ld + c];
+                    for (int r = c0 + 1; r < p; ++r) w += X[r * ld + c0] * X[r * ld + c];
+                    w *= tj;
+                    X[c0 * ld + c] -= w;
+                    for (int r = c0 + 1; r < p; ++r) X[r * ld + c] -= w * X[r * ld + c0];
+                }
+            }
+            __syncwarp();
+            for (int r = c0 + 1 + lane; r < p; r += 32) X[r * ld + c0] *= -tj;
+            for (int r = lane; r < c0; r += 32) X[r * ld + c0] = 0.0;
+            if (lane == 0) X[c0 * ld + c0] = 1.0 - tj;
+            __syncwarp();
+        }
+        if (O1) {
+            for (int e = lane; e < p * k; e += 32) { const int r = e / k, c = e - r * k; O1[e] = X[r * ld + c]; }
+            if (lane == 0 && ((p * k) & 1)) O1[p * k] = 0.0;
+        }
+        __syncwarp();
+    }
+}
+
+// one WARP per small sector: one-sided Jacobi without block barriers (jacobi_svd_warp), results staged like rt_svd_work_kernel
+__global__ void __launch_bounds__(32 * kRtSvdWarps) rt_svd_warp_kernel(RtForm F, double* __restrict__ workg, long long wbs, const int* __restrict__ ws,
+                                                                       long long wss, int kfull, int* qctl, const int2* __restrict__ qitems,
+                                                                       long long qcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* G = reinterpret_cast<double*>(smem_raw) + (size_t)warp * kRtSvdWarpDoubles;
+    int2 item;
+    while (rt_pop_warp(3, qctl, qitems, qcap, item)) {
+        const int b = item.x, i = item.y;
+        const RtTab R(F.rt + b * F.rts), C(F.ct + b * F.cts);
+        const RtMatch Mt(F.match + b * F.mts);
+        const int* e6 = ws + (long long)b * wss + RT_WS_HDR + RT_WS_SEC * i;
+        const int j = Mt.mcol(i);
+        const int ms = R.count(i), ns = C.count(j);
+        const double* A = F.data + (long long)b * F.dstride + Mt.moff(i);
+        double* wg = workg + (long long)b * wbs;
+        double* sig_all = wg + e6[0];
+        double* Us = wg + kfull + e6[1];
+        double* Vs = wg + kfull + (long long)F.M * kfull + e6[2];
+        const bool tall = ms >= ns;
+        const int p = tall ? ms : ns, q = tall ? ns : ms;
+        const int ldp = p + (p & 1), ldq = q + (q & 1);
+        double* V = G + (size_t)q * ldp;
+        double* sig = V + (size_t)q * ldq;
+        for (int e = lane; e < ms * ns; e += 32) {
+            const int r = e / ns, c = e - r * ns;
+            const double v = __ldg(A + e);
+            if (tall) G[c * ldp + r] = v; else G[r * ldp + c] = v;
+        }
+        if (p & 1) for (int c = lane; c < q; c += 32) G[c * ldp + p] = 0.0;
+        __syncwarp();
+        jacobi_svd_warp(G, ldp, V, ldq, p, q);
+        __syncwarp();
+        for (int c = 0; c < q; ++c) {
+            double s2 = 0.0;
+            for (int r = lane; r < p; r += 32) s2 += G[c * ldp + r] * G[c * ldp + r];
+            s2 = warp_sum(s2);
+            if (lane == 0) { sig[c] = sqrt(s2); sig_all[c] = sqrt(s2); }
+        }
+        __syncwarp();
+        for (int e = lane; e < ms * q; e += 32) {
+            const int r = e / q, c = e - r * q;
+            if (tall) { const double sg = sig[c]; Us[e] = sg > 0.0 ? G[c * ldp + r] / sg : 0.0; }
+            else Us[e] = V[c * ldq + r];
+        }
+        for (int e = lane; e < q * ns; e += 32) {
+            const int c = e / ns, t = e - c * ns;
+            if (tall) Vs[e] = V[c * ldq + t];
+            else { const double sg = sig[c]; Vs[e] = sg > 0.0 ? G[c * ldp + t] / sg : 0.0; }
+        }
+        __syncwarp();
     }
 }
 
@@ -2570,12 +2766,14 @@ extern "C" int tnsp_svd_sectors_gather_f64(const int64_t* sect, const int64_t* s
 static int rt_queue_prepare(int nb, int64_t per_cta_scratch, cudaStream_t st, int64_t& qcap) {
     qcap = (int64_t)nb * RT_SMAX;
     if (!g_qws.qctl && cudaMalloc(&g_qws.qctl, 8 * sizeof(int)) != cudaSuccess) { set_error("sector queue: cudaMalloc"); return 1; }
-    if (!grow(g_qws.qitems, g_qws.qitems_cap, kQClasses * qcap) || !grow(g_qws.scratch, g_qws.scratch_cap, per_cta_scratch * kSMs)) {
+    if (!grow(g_qws.qitems, g_qws.qitems_cap, kRtClasses * qcap) || !grow(g_qws.scratch, g_qws.scratch_cap, per_cta_scratch * kSMs)) {
         set_error("sector queue: cudaMalloc of the workspace failed");
         return 1;
     }
     static bool attr_set = false;
     if (!attr_set) {
+        cudaFuncSetAttribute(rt_qr_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtQrWarps * kRtQrWarpDoubles * 8);
+        cudaFuncSetAttribute(rt_svd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSvdWarps * kRtSvdWarpDoubles * 8);
         cudaFuncSetAttribute(rt_qr_work_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
         cudaFuncSetAttribute(rt_qr_work_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
         cudaFuncSetAttribute(rt_svd_work_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQBigDoubles * 8);
@@ -2622,6 +2820,13 @@ extern "C" int tnsp_rt_qr_f64(const tnsp_rt_form* f, int fsign_rs, const int32_t
     const RtForm F = to_form(f);
     const int64_t qcap = (int64_t)nb * RT_SMAX;
     const int64_t per_cta = rt_scratch_need(f->M, f->N, 0);
+    if (kRtUseWarpClass) {
+        rt_qr_warp_kernel<<<kSMs, 32 * kRtQrWarps, kRtQrWarps * kRtQrWarpDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first,
+                                                                                            first, first_stride, m_second, second, second_stride,
+                                                                                            g_qws.qctl, g_qws.qitems, qcap);
+        if (check_launch("tnsp_rt_qr_f64(warp class)")) return 1;
+        if (rt_qr_warp_need(f->M, f->N, f->M < f->N ? f->M : f->N) <= kRtQrWarpDoubles) return 0;     // nothing can be larger
+    }
     if (qr_sector_need(f->M, f->N) > kQSmallDoubles) {
         rt_qr_work_kernel<true><<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first, first,
                                                                                first_stride, m_second, second, second_stride, g_qws.qctl,
@@ -2650,6 +2855,12 @@ extern "C" int tnsp_rt_svd_work_f64(const tnsp_rt_form* f, double* work, int64_t
     const int kfull = (int)(f->M < f->N ? f->M : f->N);
     const int64_t p = f->M >= f->N ? f->M : f->N, q = f->M >= f->N ? f->N : f->M;
     const int64_t full = svd_sector_need(p, q);
+    if (kRtUseWarpClass) {
+        rt_svd_warp_kernel<<<kSMs, 32 * kRtSvdWarps, kRtSvdWarps * kRtSvdWarpDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
+                                                                                                g_qws.qitems, qcap);
+        if (check_launch("tnsp_rt_svd_work_f64(warp class)")) return 1;
+        if (q <= kWarpSectorMax && rt_svd_warp_need(p, q) <= kRtSvdWarpDoubles) return 0;
+    }
     if (full > kQSmallDoubles) {
         rt_svd_work_kernel<true><<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl, g_qws.qitems,
                                                                                 qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
