@@ -225,9 +225,64 @@ class Configuration(SingleLayerAuxiliaries):
             got = cache[(l1, l2)] = (tensor, ragged.RTensor.from_symmetric(tensor, unit_names=("T",)), tensor._data)
         return got[1]
 
+    def _ragged_variants(self, l1, l2, orbit):
+        """the d shrunk versions of a single-orbit site tensor (one per physical index), stacked: every chain of a batch then
+        SELECTS its version with one row gather instead of contracting with its own one-hot tensor (lattice.py:319-339)"""
+        from ..TAT import ragged
+        B = _bk.get()
+        site = self._ragged_site(l1, l2)
+        cache = self.owner.__dict__.setdefault("_ragged_variants", {})
+        got = cache.get((l1, l2))
+        if got is not None and got[0] is site:
+            return got[1]
+        edge = self.owner.physics_edges[l1, l2, orbit]
+        forms, names = [], None
+        for p in range(edge.dimension):
+            shr = self._ragged_shrinker(edge, np.array([p], dtype=np.int32))
+            v = site.contract(shr.edge_rename({"P": f"P_{l1}_{l2}_{orbit}"}), {(f"P{orbit}", "Q")})
+            forms.append(v._primary())
+            names = v.names
+            proto = v
+        import torch
+        cap = max(f.data.shape[1] for f in forms)
+        data = B.zeros(len(forms), cap)
+        for p, f in enumerate(forms):
+            data[p, :f.data.shape[1]] = f.data[0]
+        match = torch.cat([f.match for f in forms], dim=0).contiguous()
+        labels = np.concatenate([np.full(d, ragged.pack_symmetry(sy), dtype=np.int32) for sy, d in edge.segments])
+        out = (proto, data, match.view(torch.float64), labels, cap)
+        cache[(l1, l2)] = (site, out)
+        return out
+
+    def _shrink_by_selection(self, l1, l2, orbit, index):
+        from ..TAT import ragged
+        import torch
+        B = _bk.get()
+        proto, data, match64, labels, cap = self._ragged_variants(l1, l2, orbit)
+        idx = B.from_numpy(np.ascontiguousarray(index, dtype=np.int32))
+        sel_data = B.gather_rows(data, data.shape[1], idx)
+        sel_match = B.gather_rows(match64, match64.shape[1], idx).view(torch.int32)
+        chosen = labels[index].astype(np.int32)
+        f = proto._primary()
+        pcore = proto.core
+        edges = [e if not (e.unit and n == f"P_{l1}_{l2}_{orbit}") else ragged.Edge(1, None, e.sign, e.arrow, chosen)
+                 for n, e in zip(proto.names, pcore.edges)]
+        # target of the shrunk tensor: the site's own (the T edge) minus the sampled physical charge, per chain
+        unit_sum = np.zeros(len(index), dtype=np.int64)
+        for e in edges:
+            if e.unit:
+                unit_sum = unit_sum + e.sign * np.asarray(e.harr, dtype=np.int64).reshape(-1)
+        core = ragged.Core(edges, len(index), B.from_numpy((-unit_sum).astype(np.int32)), 1, pcore.fermi)
+        core.tables = dict(pcore.tables)
+        core.set_primary(ragged.Form(f.rows, f.cols, f.rt, f.rs, f.ct, f.cs, sel_match, sel_data, f.M, f.N))
+        return ragged.RTensor(proto.names, core, 1)
+
     def _shrink_configuration(self, l1l2, configuration):
         l1, l2 = l1l2
         if self._ragged:
+            orbits = list(self.owner.physics_edges[l1, l2])
+            if len(orbits) == 1:
+                return self._shrink_by_selection(l1, l2, orbits[0], configuration[orbits[0]][1])
             tensor = self._ragged_site(l1, l2)
             for orbit, shrinker in self._get_shrinker(l1l2, configuration):
                 tensor = tensor.contract(shrinker.edge_rename({"P": f"P_{l1}_{l2}_{orbit}"}), {(f"P{orbit}", "Q")})
