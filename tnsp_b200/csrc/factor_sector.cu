@@ -2086,6 +2086,8 @@ static bool desc_applicable(const int64_t* sh, int ns) {
 //   position of a staged singular triplet inside its sector's kept block (-1: cut)
 // ================================================================================================
 constexpr bool kRtUseWarpClass = false;
+constexpr int kRtTinyDoubles = 2560;          // 20 KiB: class 3 of the queue when the warp class is off
+constexpr int kRtTinyThreads = 128;
 constexpr int kRtClasses = 4;                 // work queue of the rt_* kernels: counts at qctl[0..3], tickets at qctl[4..7]
 constexpr int kRtQrWarpDoubles = 6144;        // 48 KiB per warp, 4 warps per CTA
 constexpr int kRtQrWarps = 4;
@@ -2156,6 +2158,8 @@ __global__ void __launch_bounds__(128) rt_factor_plan_kernel(RtForm F, int kind,
         if (kRtUseWarpClass) {
             if (kind == 2) { const int pp = m >= n ? m : n; if (q <= kWarpSectorMax && rt_svd_warp_need(pp, q) <= kRtSvdWarpDoubles) cls = 3; }
             else if (rt_qr_warp_need(m, n, q) <= kRtQrWarpDoubles) cls = 3;
+        } else if (need <= kRtTinyDoubles) {
+            cls = 3;       // tiny sectors (cfg2: the 31 x 31 sectors of a 216 x 216 bond matrix): 128-thread CTAs, ~8 per SM
         }
         const int at = atomicAdd(&qctl[cls], 1);
         qitems[(long long)cls * qcap + at] = make_int2(b, i);
@@ -2839,6 +2843,13 @@ extern "C" int tnsp_rt_qr_f64(const tnsp_rt_form* f, int fsign_rs, const int32_t
                                                                                        g_qws.qctl, g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
         if (check_launch("tnsp_rt_qr_f64(72 KiB class)")) return 1;
     }
+    if (!kRtUseWarpClass) {
+        rt_qr_work_kernel<false><<<8 * kSMs, kRtTinyThreads, kRtTinyDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first,
+                                                                                       first, first_stride, m_second, second, second_stride,
+                                                                                       g_qws.qctl, g_qws.qitems, qcap, 3, kRtTinyDoubles, nullptr, 0);
+        if (check_launch("tnsp_rt_qr_f64(tiny class)")) return 1;
+        if (qr_sector_need(f->M, f->N) <= kRtTinyDoubles) return 0;
+    }
     rt_qr_work_kernel<false><<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first, first,
                                                                                  first_stride, m_second, second, second_stride, g_qws.qctl,
                                                                                  g_qws.qitems, qcap, 2, kQMidDoubles, nullptr, 0);
@@ -2870,6 +2881,12 @@ extern "C" int tnsp_rt_svd_work_f64(const tnsp_rt_form* f, double* work, int64_t
         rt_svd_work_kernel<false><<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
                                                                                         g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
         if (check_launch("tnsp_rt_svd_work_f64(72 KiB class)")) return 1;
+    }
+    if (!kRtUseWarpClass) {
+        rt_svd_work_kernel<false><<<8 * kSMs, kRtTinyThreads, kRtTinyDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
+                                                                                        g_qws.qitems, qcap, 3, kRtTinyDoubles, nullptr, 0);
+        if (check_launch("tnsp_rt_svd_work_f64(tiny class)")) return 1;
+        if (full <= kRtTinyDoubles) return 0;
     }
     rt_svd_work_kernel<false><<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
                                                                                   g_qws.qitems, qcap, 2, kQMidDoubles, nullptr, 0);

@@ -337,17 +337,20 @@ __device__ __forceinline__ void rt_repack_tiles(const int* __restrict__ plan, co
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_ent = plan[0] + plan[1];
     for (int i = tid; i < 2 + kPlanEnt * n_ent; i += kRepackThreads) sp[i] = plan[i];
-    for (int i = tid; i < RT_HDR; i += kRepackThreads) { hS[0][i] = S.rt[b * S.rts + i]; hS[1][i] = S.ct[b * S.cts + i]; }
-    for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mS[i] = S.match[b * S.mts + i];
+    __shared__ int hD[2][RT_HDR];
     const int* gDr = D.rt + b * D.rts;
     const int* gDc = D.ct + b * D.cts;
-    if (spec.on) rt_match_cta(gDr, gDc, spec, b, mD, blockIdx.x == 0);
-    else {
-        for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mD[i] = D.match[b * D.mts + i];
-        __syncthreads();
+    for (int i = tid; i < RT_HDR; i += kRepackThreads) {
+        hS[0][i] = S.rt[b * S.rts + i]; hS[1][i] = S.ct[b * S.cts + i];
+        hD[0][i] = gDr[i]; hD[1][i] = gDc[i];
     }
+    for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mS[i] = S.match[b * S.mts + i];
+    if (!spec.on)
+        for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mD[i] = D.match[b * D.mts + i];
+    __syncthreads();
+    if (spec.on) rt_match_cta(hD[0], hD[1], spec, b, mD, blockIdx.x == 0);
     {
-        const RtTab dR(gDr), dC(gDc);
+        const RtTab dR(hD[0]), dC(hD[1]);
         const RtMatch dM(mD);
         const int nsec = max(dR.nsec(), 0);
         int here = 0;
@@ -670,19 +673,24 @@ __global__ void __launch_bounds__(kGemmWarps * 32, 4) rt_gemm_warp_kernel(RtForm
     __shared__ int mC[RT_MSTRIDE];
     __shared__ RtGemmDesc dsc[RT_SMAX];
     __shared__ int n_desc, n_items;
+    __shared__ int hh[4][RT_HDR];          // A rows, A cols (k), B rows (k), B cols: headers only (sector keys / starts)
+    __shared__ int mAB[2][RT_MSTRIDE];
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int* gAr = A.rt + b * A.rts;
-    const int* gAk = A.ct + b * A.cts;
-    const int* gBk = B.rt + b * B.rts;
-    const int* gBn = B.ct + b * B.cts;
-    if (spec.on) rt_match_cta(gAr, gBn, spec, b, mC, blockIdx.x == 0);
-    else {
-        for (int i = tid; i < RT_MSTRIDE; i += kGemmWarps * 32) mC[i] = C.match[b * C.mts + i];
+    {
+        // every table is read ONCE, all loads independent (one global-memory latency for the whole prologue)
+        const int* src[4] = {A.rt + b * A.rts, A.ct + b * A.cts, B.rt + b * B.rts, B.ct + b * B.cts};
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            for (int i = tid; i < RT_HDR; i += kGemmWarps * 32) hh[t][i] = src[t][i];
+        for (int i = tid; i < RT_MSTRIDE; i += kGemmWarps * 32) { mAB[0][i] = A.match[b * A.mts + i]; mAB[1][i] = B.match[b * B.mts + i]; }
+        if (!spec.on)
+            for (int i = tid; i < RT_MSTRIDE; i += kGemmWarps * 32) mC[i] = C.match[b * C.mts + i];
         __syncthreads();
     }
+    if (spec.on) rt_match_cta(hh[0], hh[3], spec, b, mC, blockIdx.x == 0);
     {
-        const RtTab aR(gAr), aK(gAk), bK(gBk), bN(gBn);
-        const RtMatch MA(A.match + b * A.mts), MB(B.match + b * B.mts), MC(mC);
+        const RtTab aR(hh[0]), aK(hh[1]), bK(hh[2]), bN(hh[3]);
+        const RtMatch MA(mAB[0]), MB(mAB[1]), MC(mC);
         const int nsec = max(aR.nsec(), 0);
         // one thread per row sector: operands and tile counts (every thread's loads are independent: one latency, not nsec)
         int here = 0;
@@ -932,7 +940,7 @@ extern "C" int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, co
         // small sectors: warp-autonomous kernel; the grid covers the most items a chain can have (every sector adds at most one
         // partial piece per direction), spare CTAs leave at once
         int64_t items = ((a->M + WR - 1) / WR + RT_SMAX / 4) * ((b->N + WC - 1) / WC);
-        int64_t gx = (items + 4 * kGemmWarps - 1) / (4 * kGemmWarps);      // a few items per warp: the CTA prologue is amortised
+        int64_t gx = (items + 8 * kGemmWarps - 1) / (8 * kGemmWarps);      // several items per warp: the CTA prologue is amortised
         if (gx > 256) gx = 256;
         rt_gemm_warp_kernel<<<dim3((unsigned)gx, (unsigned)nb), kGemmWarps * 32, 0, (cudaStream_t)stream>>>(
             to_form(a), to_form(b), to_form(c), to_spec(c_match), c_data, c_stride, ksign, rt_stats_ptr());
