@@ -179,7 +179,31 @@ class RaggedMixin:
         self.rt_repack(plan0, src0, dst0, spec0)
         self.rt_repack(plan1, src1, dst1, spec1)
 
-    def rt_repack(self, plan, src, dst, match_spec=None):
+    @staticmethod
+    def _parity(labels, mask):
+        labels = np.asarray(labels, dtype=np.int64)
+        c0 = ((labels + 32768) % 65536) - 32768
+        c1 = (labels - c0) // 65536
+        p = np.zeros(labels.shape, dtype=np.int64)
+        if mask & 1:
+            p ^= c0 & 1
+        if mask & 2:
+            p ^= c1 & 1
+        return p
+
+    def _entry_bits(self, entries, first, idx, labels, c, mask):
+        """parity bit k (k = first + position in `entries`) of every merged destination index in `idx`"""
+        bits = np.zeros_like(idx)
+        rest = idx.copy()
+        for k in range(len(entries) - 1, -1, -1):
+            dim = entries[k][0]
+            i = rest % dim
+            rest = rest // dim
+            lab = _row(_np(labels[first + k][0]), c)
+            bits |= self._parity(lab[i], mask) << (first + k)
+        return bits
+
+    def rt_repack(self, plan, src, dst, match_spec=None, sign=None):
         self.launches += 1
         if match_spec is not None:
             rs, cs, t1, s1, t2, s2 = match_spec
@@ -238,6 +262,21 @@ class RaggedMixin:
                     if j < 0 or not (tc.sstart[j] <= q[k] < tc.sstart[j + 1]):
                         continue
                     val[k] = srow[int(mt.moff[i]) + (p[k] - tr.sstart[i]) * tc.count(j) + (q[k] - tc.sstart[j])]
+            if sign is not None:
+                # sign(element) = s0 + lin . x + sum_{k<j} Q_kj x_k x_j over the parity bits x of the destination's indexed edges
+                quad, per_chain, labels, mask = sign
+                quad, pc = _np(quad).astype(np.int64), int(_row(_np(per_chain).reshape(-1, 1), c)[0])
+                x = self._entry_bits(rows, 0, r_idx, labels, c, mask) | self._entry_bits(cols, len(rows), c_idx, labels, c, mask)
+                sg = np.full(len(x), (pc >> 31) & 1, dtype=np.int64)
+                y = x & (pc & 0x7FFFFFFF)
+                for k in range(len(rows) + len(cols)):
+                    sg ^= (y >> k) & 1
+                    z = x & int(quad[k]) if k < len(quad) else np.zeros_like(x)
+                    par = np.zeros_like(x)
+                    for j in range(len(rows) + len(cols)):
+                        par ^= (z >> j) & 1
+                    sg ^= ((x >> k) & 1) & par
+                val = np.where(sg == 1, -val, val)
             D[c, dst_pos] = val
 
     def rt_dot(self, plan, src, dst, t1, s1, t2, s2, nb):

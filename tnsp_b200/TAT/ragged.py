@@ -297,7 +297,7 @@ class RTensor:
 
     # ---- construction ---------------------------------------------------------------------------
     @classmethod
-    def from_dense(cls, names, edges, dense, target=None, rows=None):
+    def from_dense(cls, names, edges, dense, target=None, rows=None, fermi=0):
         """tensor from a dense device / host array [nb, prod dims] (entries outside the sectors are dropped)"""
         B = _bk.get()
         if isinstance(dense, np.ndarray):
@@ -308,7 +308,7 @@ class RTensor:
         if isinstance(target, np.ndarray):
             nb = max(nb, target.shape[0])
             target = B.from_numpy(np.ascontiguousarray(target, dtype=np.int32))
-        core = Core(edges, nb, target, 1)
+        core = Core(edges, nb, target, 1, fermi)
         nonunit = tuple(i for i, e in enumerate(core.edges) if not e.unit)
         if rows is None:
             rows = nonunit[:1]
@@ -351,9 +351,8 @@ class RTensor:
                 target -= int(lab[0])
             else:
                 edges.append(Edge(e.dimension, B.from_numpy(lab.reshape(1, -1)), 1, e.arrow))
-        t = cls.from_dense(list(tensor.names), edges, dense.reshape(nb, -1), np.array([target], dtype=np.int32) if target else None)
-        t.core.fermi = fermi_mask(S) if S.is_fermi_symmetry else 0
-        return t
+        return cls.from_dense(list(tensor.names), edges, dense.reshape(nb, -1), np.array([target], dtype=np.int32) if target else None,
+                              fermi=fermi_mask(S) if S.is_fermi_symmetry else 0)
 
     @classmethod
     def scalar_one(cls, value=1.0):
@@ -428,7 +427,7 @@ class RTensor:
     def _with_data(self, data):
         core, f = self.core, self._primary()
         nb = max(core.nb, data.shape[0])
-        new = Core(core.edges, nb, core.target, core.tsign)
+        new = Core(core.edges, nb, core.target, core.tsign, core.fermi)
         new.tables = dict(core.tables)
         new.set_primary(Form(f.rows, f.cols, f.rt, f.rs, f.ct, f.cs, f.match, data, f.M, f.N))
         return RTensor(self.names, new, self.sign)
@@ -472,6 +471,8 @@ class RTensor:
         f = self._primary()
         if other.rank == 0 and self.rank != 0:
             return self._scale(other.scalar(), {2: 0, 3: 1}[op])
+        if _is_fermi(self) and other.names != self.names:
+            other = other.transpose(self.names)
         order = [other.names.index(n) for n in self.names]
         g = other.core.form(tuple(order[i] for i in f.rows), tuple(order[i] for i in f.cols))
         return self._with_data(B.rt_binary(f.data, g.data, f.match, op))
@@ -550,7 +551,7 @@ def _reordered(t, target_names):
         raise RuntimeError("Tensor to transpose with incompatible name list")
     core = t.core
     inv = {old: new for new, old in enumerate(order)}
-    new = Core([core.edges[i] for i in order], core.nb, core.target, core.tsign)
+    new = Core([core.edges[i] for i in order], core.nb, core.target, core.tsign, core.fermi)
     f = core.forms[core.primary]
     rows, cols = tuple(inv[i] for i in f.rows), tuple(inv[i] for i in f.cols)
     new.set_primary(Form(rows, cols, f.rt, f.rs, f.ct, f.cs, f.match, f.data, f.M, f.N))
@@ -630,7 +631,7 @@ def _contract(a, b, pairs):
     target = B.rt_gemm(A, Bf, C, ksign, nb, (rs, cs, a.core.target, a.core.tsign * a.sign, b.core.target, b.core.tsign * b.sign))
     if learning:
         _learn(key, C.match)
-    core = Core(edges, nb, target, 1)
+    core = Core(edges, nb, target, 1, a.core.fermi)
     core.set_primary(C)
     return RTensor(names, core, 1)
 
@@ -663,7 +664,7 @@ def _dot(a, b, ka, kb, fa, fb, names):
     if swapped:
         a, b, fa, fb = b, a, fb, fa
     edges = [a.core.edges[i].flipped(a.sign) for i in fa] + [b.core.edges[j].flipped(b.sign) for j in fb]
-    core = Core(edges, nb, target, 1)
+    core = Core(edges, nb, target, 1, a.core.fermi)
     empty = _empty_table()
     core.set_primary(Form((), (), empty, 1, empty, 1, match, data, 1, 1))
     return RTensor(names, core, 1)
@@ -691,7 +692,10 @@ def _factor(t, first_names, kind, name_1, name_2, sing_1, sing_2, cut):
     second = [i for i in range(len(t.names)) if i not in first]
     rows = tuple(i for i in first if not core.edges[i].unit)
     cols = tuple(i for i in second if not core.edges[i].unit)
-    F = core.form(rows, cols)
+    fermi = core.fermi != 0
+    # fermionic tensors: the transposition to (first..., second...) carries its sign; the new bond points from the second factor
+    # to the first (arrow true on Q / U, false on R / V; S: false, true) as in the reference's use_qr / put_v_right branch
+    F = _signed_form(t, rows, cols, _fermi_factor_form(t, first, second)) if fermi else core.form(rows, cols)
     nb = max(core.nb, F.match.shape[0])
     kdim = min(F.M, F.N)
     remain_cut, relative_cut = (1 << 30), 0.0
@@ -723,11 +727,11 @@ def _factor(t, first_names, kind, name_1, name_2, sing_1, sing_2, cut):
     lab = out["labels"]                      # device int32 [nb, kdim]: effective label of the bond on the first factor
     e1 = [core.edges[i].flipped(t.sign) for i in first]
     e2 = [core.edges[i].flipped(t.sign) for i in second]
-    bond_1 = Edge(kdim, lab, 1)
-    bond_2 = Edge(kdim, lab, -1)
+    bond_1 = Edge(kdim, lab, 1, fermi)
+    bond_2 = Edge(kdim, lab, -1, False)
 
     def make(names, edges, rows_ids, cols_ids, form_data, target, tsign, tables):
-        c = Core(edges, nb, target, tsign)
+        c = Core(edges, nb, target, tsign, core.fermi)
         for ids, tb in tables.items():
             c.tables[ids] = tb
         rt, rs = c.table(rows_ids)
@@ -768,3 +772,14 @@ def _fermi_transpose(t, names):
 
 def _fermi_conjugate(t, trivial_metric):
     raise NotImplementedError("fermionic sector-compact tensors: signs not installed")
+
+
+def _fermi_factor_form(t, first, second):
+    raise NotImplementedError("fermionic sector-compact tensors: signs not installed")
+
+
+def _signed_form(t, rows, cols, form):
+    raise NotImplementedError("fermionic sector-compact tensors: signs not installed")
+
+
+from . import ragged_fermi as _ragged_fermi  # noqa: E402,F401  (installs the fermionic variants above)

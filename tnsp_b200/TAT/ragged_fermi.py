@@ -1,0 +1,254 @@
+"""Fermionic signs of sector-compact tensors (TAT/ragged.py).
+
+The reference attaches a sign to every block an edge operation moves (TAT/include/TAT/implement/edge_operator.hpp:497-555, 591,
+612): the XOR of (i) the parities of reversed edges that are flagged to carry a sign, (ii) one factor per pair of odd edges whose
+order the transpose swaps, (iii) the "reverse the order of n_odd fermions" factor (n_odd & 2) of every flagged merge / split group.
+All three are polynomials of degree <= 2 over GF(2) in the PARITIES of the element's indices, so for a lock-step batch -- where
+the parity of an index differs from chain to chain -- a sign is described once per operation by a quadratic form
+
+    sign(element) = s0 + sum_i L_i p_i + sum_{i<j} Q_ij p_i p_j        (mod 2; p_i = parity of the element's index on edge i)
+
+(`SignForm`), and evaluated per element on the device from the per-chain labels.  Dimension-1 edges with host-known charges (the
+physical P edges, the total-symmetry edge) have one parity per chain: they are folded on the host into a per-chain constant and
+per-chain linear coefficients of the remaining edges.
+
+The forms below follow the host planner of tnsp_b200/TAT/plan.py rule for rule (contract.hpp:365-412, 488-517, 570-580; svd.hpp:
+312-350; qr.hpp:339-394; conjugate.hpp:48-97); tests/test_sector_fermi.py checks every one of them against that planner (itself
+pinned to the unmodified reference) on random tensors of all fermionic integer symmetries.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import backend as _bk
+from . import ragged
+from .ragged import Core, Edge, Form, RTensor, STATS, _PLANS, label_parity
+
+
+class SignForm:
+    """quadratic form over GF(2) on the edge positions of one tensor: lin = set of positions, quad = set of frozenset pairs"""
+    __slots__ = ("lin", "quad")
+
+    def __init__(self):
+        self.lin = set()
+        self.quad = set()
+
+    def add_lin(self, i):
+        self.lin ^= {i}
+
+    def add_pair(self, i, j):
+        if i != j:
+            self.quad ^= {frozenset((i, j))}
+
+    def add_clique(self, group):
+        """(n_odd & 2) of a group of edges = sum over its pairs"""
+        g = list(group)
+        for a in range(len(g)):
+            for b in range(a + 1, len(g)):
+                self.add_pair(g[a], g[b])
+
+    def add_transposition(self, order):
+        """order[k] = original position of the edge that ends at place k: one factor per inverted pair"""
+        for a in range(len(order)):
+            for b in range(a + 1, len(order)):
+                if order[a] > order[b]:
+                    self.add_pair(order[a], order[b])
+
+    def empty(self):
+        return not self.lin and not self.quad
+
+    def key(self):
+        return (tuple(sorted(self.lin)), tuple(sorted(tuple(sorted(p)) for p in self.quad)))
+
+
+def unit_parities(t, mask):
+    """{position: int array [nbL] of parities} of the unit edges of tensor view `t` (effective labels)"""
+    out = {}
+    for i, e in enumerate(t.core.edges):
+        if e.unit:
+            out[i] = label_parity(e.sign * t.sign * np.asarray(e.harr, dtype=np.int64).reshape(-1), mask)
+    return out
+
+
+def fold_units(form, t, entries):
+    """Reduce a sign form to the indexed edges `entries` (positions of the non-unit edges in the order the kernel sees them).
+
+    Returns (quad masks int32 [n_ent]: bit j of entry k set iff Q_kj = 1 and j > k; per-chain int32 [nb or 1]: bits 0..n_ent-1
+    the linear coefficients, bit 31 the constant).  None, None when the form vanishes identically."""
+    mask = t.core.fermi
+    up = unit_parities(t, mask)
+    slot = {pos: k for k, pos in enumerate(entries)}
+    n = len(entries)
+    if n > 30:
+        raise NotImplementedError("sign form over more than 30 indexed edges")
+    quad = np.zeros(max(n, 1), dtype=np.int64)
+    nb = max([v.shape[0] for v in up.values()] + [1])
+    const = np.zeros(nb, dtype=np.int64)
+    lin = np.zeros(nb, dtype=np.int64)
+    for i in form.lin:
+        if i in slot:
+            lin ^= 1 << slot[i]
+        elif i in up:
+            const ^= up[i]
+    for pr in form.quad:
+        i, j = tuple(pr)
+        if i in slot and j in slot:
+            a, b = sorted((slot[i], slot[j]))
+            quad[a] ^= 1 << b
+        elif i in slot and j in up:
+            lin ^= up[j] << slot[i]
+        elif j in slot and i in up:
+            lin ^= up[i] << slot[j]
+        elif i in up and j in up:
+            const ^= up[i] & up[j]
+    if not quad.any() and not lin.any() and not const.any():
+        return None, None
+    per_chain = (lin & 0x7FFFFFFF) | ((const & 1) << 31)
+    per_chain = np.where(per_chain >= (1 << 31), per_chain - (1 << 32), per_chain).astype(np.int32)
+    return quad.astype(np.int32), per_chain
+
+
+# -------------------------------------------------------------------------------------------------
+# signed regrouping
+# -------------------------------------------------------------------------------------------------
+def signed_form(t, rows, cols, form):
+    """storage of tensor view `t` regrouped as rows | cols with the sign form applied (a fresh Form; never cached: it belongs to
+    one operation).  Falls back to the cached unsigned regrouping when the form vanishes."""
+    core = t.core
+    if form.empty():
+        return core.form(rows, cols)
+    entries = [i for i in rows if core.edges[i].dim != 1] + [i for i in cols if core.edges[i].dim != 1]
+    quad, per_chain = fold_units(form, t, entries)
+    if quad is None:
+        return core.form(rows, cols)
+    B = _bk.get()
+    src = core.forms[core.primary]
+    rt, rs = core.table(rows)
+    ct, cs = core.table(cols)
+    M, N = core.group_dim(rows), core.group_dim(cols)
+    ckey = ("form", tuple(e.dim for e in core.edges), src.rows, src.cols, rows, cols)
+    cap, learning = ragged._cap(ckey, M * N)
+    nbd = max(src.data.shape[0], src.match.shape[0], rt.shape[0], ct.shape[0], per_chain.shape[0], 1 if core.target is None else core.target.shape[0])
+    f = Form(rows, cols, rt, rs, ct, cs, None, B.rt_alloc(nbd, cap), M, N)
+    STATS["repack"] += 1
+    labels = [(core.edges[i].arr, core.edges[i].dim) for i in entries]
+    B.rt_repack(ragged._repack_plan(core, src, f), src, f, (rs, cs, core.target, core.tsign, None, 0),
+                sign=(B.upload(quad), B.upload(per_chain), labels, core.fermi))
+    if learning:
+        ragged._learn(ckey, f.match)
+    return f
+
+
+def _with_primary(t, f, edges=None, names=None, sign=None):
+    core = t.core
+    new = Core(core.edges if edges is None else edges, max(core.nb, f.data.shape[0]), core.target, core.tsign, core.fermi)
+    new.set_primary(f)
+    return RTensor(t.names if names is None else names, new, t.sign if sign is None else sign)
+
+
+def fermi_transpose(t, target_names):
+    """transpose = relabelling of the edge order + one factor per swapped pair of odd edges (edge_operator.hpp:521-555)"""
+    order = [t.names.index(n) for n in target_names]
+    if sorted(order) != list(range(len(t.names))):
+        raise RuntimeError("Tensor to transpose with incompatible name list")
+    form = SignForm()
+    form.add_transposition(order)
+    core = t.core
+    p = core.forms[core.primary]
+    f = signed_form(t, p.rows, p.cols, form)
+    inv = {old: new for new, old in enumerate(order)}
+    new = Core([core.edges[i] for i in order], max(core.nb, f.data.shape[0]), core.target, core.tsign, core.fermi)
+    new.set_primary(Form(tuple(inv[i] for i in f.rows), tuple(inv[i] for i in f.cols), f.rt, f.rs, f.ct, f.cs, f.match, f.data, f.M, f.N))
+    return RTensor(list(target_names), new, t.sign)
+
+
+def fermi_conjugate(t, trivial_metric):
+    """conjugate.hpp:48-97: labels and arrows flip; sign = (n_odd & 2) + (trivial_metric: parities of the edges with arrow true)"""
+    form = SignForm()
+    n = len(t.names)
+    form.add_clique(range(n))
+    if trivial_metric:
+        for i in range(n):
+            if t.effective_edge(i).arrow:
+                form.add_lin(i)
+    core = t.core
+    p = core.forms[core.primary]
+    f = signed_form(t, p.rows, p.cols, form)
+    new = Core(core.edges, max(core.nb, f.data.shape[0]), core.target, core.tsign, core.fermi)
+    new.tables = dict(core.tables)
+    new.set_primary(f)
+    return RTensor(t.names, new, -t.sign)
+
+
+def fermi_contract(a, b, pairs):
+    """contract.hpp:306-620 with the operand layout fixed to (free | common) x (common | free), for which the sector GEMMs need no
+    extra factor (contract.hpp:570-580: alpha = -1 only when exactly one operand has its common edges first):
+      operand 1: common edges are brought to arrow true WITH sign (the odd ones among those that had arrow false), free edges to
+                 arrow false without; transposition to (free..., common...); merge sign (n_odd & 2) on the common group;
+      operand 2: reversals without sign; transposition to (common in the order of operand 1..., free...)."""
+    pairs = list(pairs)
+    map12 = dict(pairs)
+    for x, y in pairs:
+        if x not in a.names or y not in b.names:
+            raise RuntimeError("Missing name in contract")
+    used_b = set(map12.values())
+    ka_all = [i for i, n in enumerate(a.names) if n in map12]
+    kb_all = [b.names.index(map12[a.names[i]]) for i in ka_all]
+    fa = [i for i, n in enumerate(a.names) if n not in map12]
+    fb = [j for j, n in enumerate(b.names) if n not in used_b]
+    form_a, form_b = SignForm(), SignForm()
+    for i in ka_all:
+        if not a.effective_edge(i).arrow:
+            form_a.add_lin(i)
+    form_a.add_transposition(fa + ka_all)
+    form_a.add_clique(ka_all)
+    form_b.add_transposition(kb_all + fb)
+    ea, eb = a.core.edges, b.core.edges
+    for i, j in zip(ka_all, kb_all):
+        if ea[i].dim != eb[j].dim:
+            raise RuntimeError("Contracting two edge with different dimension")
+        if ea[i].unit != eb[j].unit:
+            raise NotImplementedError("contract of a host-labelled dimension-1 edge with a device-labelled one")
+    fa_n = tuple(i for i in fa if not ea[i].unit)
+    fb_n = tuple(j for j in fb if not eb[j].unit)
+    ka = tuple(i for i in ka_all if not ea[i].unit)
+    kb = tuple(j for i, j in zip(ka_all, kb_all) if not ea[i].unit)
+    names = [a.names[i] for i in fa] + [b.names[j] for j in fb]
+    B = _bk.get()
+    STATS["contract"] += 1
+    A = signed_form(a, fa_n, ka, form_a)
+    Bf = signed_form(b, kb, fb_n, form_b)
+    nb = max(a.core.nb, b.core.nb, A.match.shape[0], Bf.match.shape[0], A.data.shape[0], Bf.data.shape[0])
+    edges = [ea[i].flipped(a.sign) for i in fa] + [eb[j].flipped(b.sign) for j in fb]
+    rows = tuple(k for k, i in enumerate(fa) if not ea[i].unit)
+    cols = tuple(len(fa) + k for k, j in enumerate(fb) if not eb[j].unit)
+    rs, cs = A.rs * a.sign, Bf.cs * b.sign
+    key = ("fct", tuple(e.dim for e in ea), fa_n, ka, tuple(e.dim for e in eb), kb, fb_n)
+    cap, learning = ragged._cap(key, A.M * Bf.N)
+    C = Form(rows, cols, A.rt, rs, Bf.ct, cs, None, B.rt_alloc(nb, cap), A.M, Bf.N)
+    ksign = -(a.sign * A.cs) * (b.sign * Bf.rs)
+    target = B.rt_gemm(A, Bf, C, ksign, nb, (rs, cs, a.core.target, a.core.tsign * a.sign, b.core.target, b.core.tsign * b.sign))
+    if learning:
+        ragged._learn(key, C.match)
+    core = Core(edges, nb, target, 1, a.core.fermi)
+    core.set_primary(C)
+    return RTensor(names, core, 1)
+
+
+def fermi_factor_input(t, first, second):
+    """svd.hpp:312-350 / qr.hpp:339-394 with the matrix laid out as (first | second) (the reference's put_v_right / use_qr branch):
+    edges with arrow true are reversed WITHOUT sign, the transposition to (first..., second...) carries its sign"""
+    form = SignForm()
+    form.add_transposition(list(first) + list(second))
+    return form
+
+
+def install():
+    ragged._fermi_contract = fermi_contract
+    ragged._fermi_transpose = fermi_transpose
+    ragged._fermi_conjugate = fermi_conjugate
+    ragged._fermi_factor_form = fermi_factor_input
+    ragged._signed_form = signed_form
+
+
+install()

@@ -211,9 +211,8 @@ class Configuration(SingleLayerAuxiliaries):
         onehot = np.zeros((len(index), d))
         onehot[np.arange(len(index)), index] = 1.0
         edges = [ragged.Edge(1, None, 1, False, chosen), ragged.Edge(d, B.from_numpy(labels.reshape(1, -1)), -1, not edge.arrow)]
-        t = ragged.RTensor.from_dense(["P", "Q"], edges, onehot, (-chosen).astype(np.int32))
-        t.core.fermi = ragged.fermi_mask(self.owner.Symmetry) if self.owner.Symmetry.is_fermi_symmetry else 0
-        return t
+        return ragged.RTensor.from_dense(["P", "Q"], edges, onehot, (-chosen).astype(np.int32),
+                                         fermi=ragged.fermi_mask(self.owner.Symmetry) if self.owner.Symmetry.is_fermi_symmetry else 0)
 
     def _ragged_site(self, l1, l2):
         """sector-compact copy of the owner's site tensor (rebuilt when the owner's tensor object changes)"""
