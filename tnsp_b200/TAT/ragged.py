@@ -235,16 +235,17 @@ def _plan_array(rows, cols):
     magic = floor(2^64 / dim) + 1 (exact division of a 32-bit index by one multiply-high on the device)"""
     out = [len(rows), len(cols)]
     for dim, grp, stride in rows + cols:
-        m = (1 << 64) // dim + 1
+        m = ((1 << 64) // dim + 1) if dim > 1 else 0        # dimension 1 (kept for fermionic parities): the device skips the division
         lo, hi = m & 0xFFFFFFFF, (m >> 32) & 0xFFFFFFFF
         out += [dim, grp, stride, lo - (1 << 32) if lo >= (1 << 31) else lo, hi - (1 << 32) if hi >= (1 << 31) else hi]
     return np.array(out, dtype=np.int32)
 
 
-def _repack_plan(core, src, dst):
+def _repack_plan(core, src, dst, keep_dim1=False):
     """int32 descriptor of a regrouping: for every edge of the destination row group, then column group (slowest first):
-    dimension, 1 if the edge sits in the source's column group, its stride inside that source group"""
-    key = ("rp", tuple(e.dim for e in core.edges), src.rows, src.cols, dst.rows, dst.cols)
+    dimension, 1 if the edge sits in the source's column group, its stride inside that source group.  Edges of dimension 1 are
+    dropped unless `keep_dim1` (signed regroupings of fermionic tensors need the parity of every device-labelled edge)"""
+    key = ("rp", tuple(e.dim for e in core.edges), src.rows, src.cols, dst.rows, dst.cols, keep_dim1)
     p = _PLANS.get(key)
     if p is None:
         where = {}
@@ -253,8 +254,8 @@ def _repack_plan(core, src, dst):
             for i in reversed(ids):
                 where[i] = (grp, stride)
                 stride *= core.edges[i].dim
-        rows = [(core.edges[i].dim,) + where[i] for i in dst.rows if core.edges[i].dim != 1]
-        cols = [(core.edges[i].dim,) + where[i] for i in dst.cols if core.edges[i].dim != 1]
+        rows = [(core.edges[i].dim,) + where[i] for i in dst.rows if core.edges[i].dim != 1 or keep_dim1]
+        cols = [(core.edges[i].dim,) + where[i] for i in dst.cols if core.edges[i].dim != 1 or keep_dim1]
         p = _PLANS[key] = _bk.get().upload(_plan_array(rows, cols))
     return p
 
@@ -355,8 +356,8 @@ class RTensor:
                               fermi=fermi_mask(S) if S.is_fermi_symmetry else 0)
 
     @classmethod
-    def scalar_one(cls, value=1.0):
-        return cls.from_dense([], [], np.array([[float(value)]]))
+    def scalar_one(cls, value=1.0, fermi=0):
+        return cls.from_dense([], [], np.array([[float(value)]]), fermi=fermi)
 
     def to_dense(self):
         """dense device array [nb, prod dims] in this tensor's edge order (zeros outside the sectors)"""
@@ -631,7 +632,7 @@ def _contract(a, b, pairs):
     target = B.rt_gemm(A, Bf, C, ksign, nb, (rs, cs, a.core.target, a.core.tsign * a.sign, b.core.target, b.core.tsign * b.sign))
     if learning:
         _learn(key, C.match)
-    core = Core(edges, nb, target, 1, a.core.fermi)
+    core = Core(edges, nb, target, 1, a.core.fermi | b.core.fermi)
     core.set_primary(C)
     return RTensor(names, core, 1)
 
@@ -664,7 +665,7 @@ def _dot(a, b, ka, kb, fa, fb, names):
     if swapped:
         a, b, fa, fb = b, a, fb, fa
     edges = [a.core.edges[i].flipped(a.sign) for i in fa] + [b.core.edges[j].flipped(b.sign) for j in fb]
-    core = Core(edges, nb, target, 1, a.core.fermi)
+    core = Core(edges, nb, target, 1, a.core.fermi | b.core.fermi)
     empty = _empty_table()
     core.set_primary(Form((), (), empty, 1, empty, 1, match, data, 1, 1))
     return RTensor(names, core, 1)

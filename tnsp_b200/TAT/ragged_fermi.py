@@ -117,7 +117,7 @@ def signed_form(t, rows, cols, form):
     core = t.core
     if form.empty():
         return core.form(rows, cols)
-    entries = [i for i in rows if core.edges[i].dim != 1] + [i for i in cols if core.edges[i].dim != 1]
+    entries = list(rows) + list(cols)          # every device-labelled edge, dimension 1 included: its parity is only known there
     quad, per_chain = fold_units(form, t, entries)
     if quad is None:
         return core.form(rows, cols)
@@ -132,7 +132,7 @@ def signed_form(t, rows, cols, form):
     f = Form(rows, cols, rt, rs, ct, cs, None, B.rt_alloc(nbd, cap), M, N)
     STATS["repack"] += 1
     labels = [(core.edges[i].arr, core.edges[i].dim) for i in entries]
-    B.rt_repack(ragged._repack_plan(core, src, f), src, f, (rs, cs, core.target, core.tsign, None, 0),
+    B.rt_repack(ragged._repack_plan(core, src, f, True), src, f, (rs, cs, core.target, core.tsign, None, 0),
                 sign=(B.upload(quad), B.upload(per_chain), labels, core.fermi))
     if learning:
         ragged._learn(ckey, f.match)
@@ -230,7 +230,7 @@ def fermi_contract(a, b, pairs):
     target = B.rt_gemm(A, Bf, C, ksign, nb, (rs, cs, a.core.target, a.core.tsign * a.sign, b.core.target, b.core.tsign * b.sign))
     if learning:
         ragged._learn(key, C.match)
-    core = Core(edges, nb, target, 1, a.core.fermi)
+    core = Core(edges, nb, target, 1, a.core.fermi | b.core.fermi)
     core.set_primary(C)
     return RTensor(names, core, 1)
 

@@ -43,8 +43,8 @@ class _RaggedFactory:
         self.Symmetry, self.model = Tensor.Symmetry, Tensor.model
 
     def __call__(self, number):
-        from ..TAT.ragged import RTensor
-        return RTensor.scalar_one(number)
+        from ..TAT.ragged import RTensor, fermi_mask
+        return RTensor.scalar_one(number, fermi_mask(self.Symmetry) if self.Symmetry.is_fermi_symmetry else 0)
 
 
 class Configuration(SingleLayerAuxiliaries):

@@ -183,7 +183,7 @@ def gradient_descent(
     embedded = chains > 1 and state.Tensor.Symmetry.length != 0 and not sector
     if embedded:
         if state.Tensor.Symmetry.is_fermi_symmetry:
-            raise NotImplementedError("lock-step chains of fermionic lattices: run them one chain per call (chains=1)")
+            raise NotImplementedError("lock-step chains of fermionic lattices need the sector-compact engine (integer symmetries)")
         if sampling_method != "sweep" or measurement or use_line_search or restrict is not None or classical_energy is not None:
             raise NotImplementedError("the embedded lock-step path supports sweep sampling with energy / gradient / SR only")
         from . import dense_embedding

@@ -27,6 +27,22 @@ def _values(t):
 _BLOCK_PLANS = {}
 
 
+def _batched_element(observer, table, cur_idx, new_idx, values):
+    """one-element Hamiltonian tensors <s'|H|s> of a lock-step batch as ONE sector-compact tensor: names and arrows of the term
+    tensor, every edge a unit edge carrying the chain's charge on it (tensor_element.py:41-53 per chain), data = matrix element"""
+    from ..TAT import ragged
+    labels = {}
+    for i, e in enumerate(table.edges):
+        lab = np.concatenate([np.full(d, ragged.pack_symmetry(sy), dtype=np.int32) for sy, d in e.segments])
+        labels[f"I{i}"] = (-lab[np.asarray(cur_idx[i], dtype=np.int64)]).astype(np.int32)
+        labels[f"O{i}"] = lab[np.asarray(new_idx[i], dtype=np.int64)].astype(np.int32)
+    names = list(observer.names)
+    edges = [ragged.Edge(1, None, 1, observer.edge_by_name(n).arrow, labels[n]) for n in names]
+    S = observer.Symmetry
+    return ragged.RTensor.from_dense(names, edges, np.asarray(values, dtype=np.float64).reshape(-1, 1), None,
+                                     fermi=ragged.fermi_mask(S) if S.is_fermi_symmetry else 0)
+
+
 def _blocks_of(hole, target):
     """storage [nb, size] of a sector-compact tensor in the block layout of the symmetric tensor `target` (same names, same edges;
     core.hpp:162-190): expand to the dense index space, then one pack over the blocks"""
@@ -202,10 +218,9 @@ class Observer:
         self._total_log_ws += float(np.log(np.abs(ws_val[alive])).sum())
 
         ragged = getattr(configuration, "_ragged", False)
-        if ragged and owner.Tensor.Symmetry.is_fermi_symmetry:
-            return self._call_ragged_fermi(possibility, configuration, ws, ws_val, alive, reweight)
+        ragged_fermi = ragged and owner.Tensor.Symmetry.is_fermi_symmetry
         # amplitudes of bosonic models are plain numbers: the tensor form below only matters for the fermionic P-edge signs
-        no_symmetry = is_no_symmetry(owner.Tensor) or ragged
+        no_symmetry = is_no_symmetry(owner.Tensor) or (ragged and not ragged_fermi)
         native = is_native(owner.Tensor)
         if not no_symmetry:
             inv_ws_conj = ws / (ws.norm_2()**2)
@@ -246,6 +261,15 @@ class Observer:
                         else:
                             with np.errstate(divide="ignore", invalid="ignore"):
                                 total += np.where(act, h * _values(wss) / ws_val, 0.0)
+                    elif ragged_fermi:
+                        # tensor form for a lock-step batch: the one-element Hamiltonian tensor of every chain (its unit edges carry
+                        # that chain's in / out charges, hence parities) contracted like the reference does (observer.py:377-383)
+                        cur_idx = table.unflatten(cur)
+                        shrunk = _batched_element(observer, table, cur_idx, new_idx, h)
+                        pn = [f"P_{l1}_{l2}_{orbit}" for l1, l2, orbit in positions]
+                        value = (inv_ws_conj.contract(shrunk, {(pn[i], f"I{i}") for i in range(body)})
+                                 .edge_rename({f"O{i}": pn[i] for i in range(body)}).contract(wss.conjugate(), all_name))
+                        pending.append((act, np.ones(nb), value))
                     else:
                         # tensor form keeps the fermionic signs of the P edges (observer.py:377-383); one chain
                         if float(wss.norm_max()) == 0:
@@ -260,7 +284,7 @@ class Observer:
                                  .edge_rename({f"O{i}": pn[i] for i in range(body)}).contract(wss.conjugate(), all_name))
                         total += _values(value)
                 per_term.append((positions, total, pending))
-            if any(pend for _, _, pend in per_term):
+            if any(pend for _, _, pend in per_term):  # noqa: E501
                 import torch
                 flat = [(w.scalar().t.reshape(-1) if ragged else w.data.reshape(-1)).expand(nb) for _, _, pend in per_term for _, _, w in pend]
                 host = torch.stack(flat).cpu().numpy()      # [replaced configurations, nb]: the only read-back
@@ -268,7 +292,7 @@ class Observer:
                 for _, total, pend in per_term:
                     for act, h, _ in pend:
                         with np.errstate(divide="ignore", invalid="ignore"):
-                            total += np.where(act, h * host[row] / ws_val, 0.0)
+                            total += np.where(act, host[row], 0.0) if ragged_fermi else np.where(act, h * host[row] / ws_val, 0.0)
                         row += 1
             for positions, total, _ in per_term:
                 r, rr, rsr = self._result_reweight[name], self._result_reweight_square[name], self._result_square_reweight_square[name]
