@@ -211,6 +211,14 @@ int tnsp_rt_match_i32(const int32_t* rt, int64_t rt_stride, int rs, const int32_
  * dense source; dst->rt == NULL: dense destination of `work` elements; else `work` bounds the stored elements (grid size). */
 int tnsp_rt_repack_f64(const int32_t* plan, const tnsp_rt_form* src, const tnsp_rt_form* dst, const tnsp_rt_match_spec* dst_match,
                        double* dst_data, int64_t dst_stride, int64_t work, int nb, void* stream);
+/* regrouping of a FERMIONIC tensor with the sign the reference attaches to every moved block (edge_operator.hpp:497-555, 591, 612),
+ * evaluated per element: sign = s0 + lin . x + sum_{k<j} Q_kj x_k x_j (mod 2) over the parity bits x of the n_entries indexed edges
+ * of the plan (dimension-1 edges included); quad[k] = bit mask of the j > k with Q_kj = 1; per_chain[chain] = lin bits | s0 << 31
+ * (the host folds the dimension-1 edges with host-known charges into them); labels[k] / lstrides[k]: label array of entry k and its
+ * chain stride; fermi_mask bit i: component i of a packed label (16 bits each) is fermionic */
+int tnsp_rt_repack_signed_f64(const int32_t* plan, const tnsp_rt_form* src, const tnsp_rt_form* dst, const tnsp_rt_match_spec* dst_match,
+                              double* dst_data, int64_t dst_stride, const int32_t* quad, const int32_t* per_chain, int64_t per_chain_stride,
+                              int n_entries, const int32_t* const* labels, const int64_t* lstrides, int fermi_mask, int nb, void* stream);
 /* two regroupings (the two operands of a contraction) in one launch; dst_match as above (NULL: dst->match is valid) */
 int tnsp_rt_repack_pair_f64(const int32_t* plan0, const tnsp_rt_form* src0, const tnsp_rt_form* dst0, const tnsp_rt_match_spec* match0,
                             double* dst_data0, int64_t dst_stride0, int64_t work0, const int32_t* plan1, const tnsp_rt_form* src1,

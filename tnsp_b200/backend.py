@@ -129,6 +129,7 @@ class CudaBackend:
         lib.tnsp_rt_match_i32.argtypes = [P, c_i64, c_int, P, c_i64, c_int, P, c_int, c_int, P, c_int, c_int, P, P, c_int, c_i64, P]
         SP = ctypes.POINTER(RtMatchSpec)
         lib.tnsp_rt_repack_f64.argtypes = [P, FP, FP, SP, P, c_i64, c_i64, c_int, P]
+        lib.tnsp_rt_repack_signed_f64.argtypes = [P, FP, FP, SP, P, c_i64, P, P, c_i64, c_int, P, P, c_int, c_int, P]
         lib.tnsp_rt_repack_pair_f64.argtypes = [P, FP, FP, SP, P, c_i64, c_i64, P, FP, FP, SP, P, c_i64, c_i64, c_int, P]
         lib.tnsp_rt_gemm_f64.argtypes = [FP, FP, FP, SP, P, c_i64, c_int, c_int, P]
         lib.tnsp_rt_dot_f64.argtypes = [P, FP, FP, P, c_int, c_int, P, c_int, c_int, P, c_i64, P, P, c_int, P]
@@ -199,8 +200,11 @@ class CudaBackend:
                         f.match.data_ptr(), self._st(f.match), None if tsum is None else tsum.data_ptr(), int(f.data.shape[1]))
         return c, tsum
 
-    def rt_repack(self, plan, src, dst, match_spec=None):
-        """regroup src -> dst; with match_spec the destination's sector pairing is computed by the same launch (dst.match is set)"""
+    def rt_repack(self, plan, src, dst, match_spec=None, sign=None):
+        """regroup src -> dst; with match_spec the destination's sector pairing is computed by the same launch (dst.match is set);
+        sign = (quad, per_chain, [(label array, dim)...], fermi mask): fermionic sign of every element (TAT/ragged_fermi.py)"""
+        if sign is not None:
+            return self._rt_repack_signed(plan, src, dst, match_spec, sign)
         dst_dense = isinstance(dst, torch.Tensor)
         out = dst if dst_dense else dst.data
         nb = out.shape[0]
@@ -214,6 +218,18 @@ class CudaBackend:
         fs, fd = self._form(src), self._form(dst)
         self._ck(self.lib.tnsp_rt_repack_f64(plan.data_ptr(), ctypes.byref(fs), ctypes.byref(fd), None if spec is None else ctypes.byref(spec),
                                              out.data_ptr(), out.stride(0), int(work), nb, self._stream()))
+
+    def _rt_repack_signed(self, plan, src, dst, match_spec, sign):
+        quad, per_chain, labels, fermi = sign
+        spec, _ = self._spec(dst, match_spec, 1, False)
+        nb = max(dst.data.shape[0], src.match.shape[0], dst.match.shape[0], per_chain.shape[0])
+        n = len(labels)
+        ptrs = (c_vp * max(n, 1))(*[a.data_ptr() for a, _ in labels])
+        strides = (c_i64 * max(n, 1))(*[self._st(a) for a, _ in labels])
+        fs, fd = self._form(src), self._form(dst)
+        self._ck(self.lib.tnsp_rt_repack_signed_f64(plan.data_ptr(), ctypes.byref(fs), ctypes.byref(fd), ctypes.byref(spec), dst.data.data_ptr(),
+                                                    dst.data.stride(0), quad.data_ptr(), per_chain.data_ptr(), 0 if per_chain.shape[0] == 1 else 1,
+                                                    n, ptrs, strides, int(fermi), nb, self._stream()))
 
     def rt_repack_pair(self, plan0, src0, dst0, spec0, plan1, src1, dst1, spec1):
         """the two regroupings of a contraction in one launch"""

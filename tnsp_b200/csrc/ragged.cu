@@ -221,9 +221,40 @@ __device__ __forceinline__ unsigned rt_div(unsigned x, const int* ent) {
     return (unsigned)__umul64hi((unsigned long long)x, m);
 }
 // merged destination index -> contributions to the source's row / column merged indices
+// fermionic signs (TAT/ragged_fermi.py): sign(element) = s0 + lin . x + sum_{k<j} Q_kj x_k x_j over the parity bits x of the
+// destination's indexed edges; quad[k] = mask of the j > k with Q_kj = 1, per_chain[b] = lin bits | s0 << 31
+struct RtSign {
+    const int* quad;
+    const int* per_chain; long long pcs;
+    const int* lab[24]; long long lst[24];
+    int fermi;                  // bit i: component i of a packed label is fermionic
+};
+__device__ __forceinline__ unsigned rt_label_parity(int label, int fermi) {
+    const int c0 = ((label + 32768) & 0xffff) - 32768;
+    const int c1 = (label - c0) >> 16;
+    return (unsigned)(((fermi & 1) ? c0 : 0) ^ ((fermi & 2) ? c1 : 0)) & 1u;
+}
+// as rt_decode, and the parity bits of the decoded edges (bit k for plan entry k)
+__device__ __forceinline__ unsigned rt_decode_bits(const int* sp, int first, int last, unsigned idx, unsigned& sr, unsigned& sc, const RtSign& sg,
+                                                   int b) {
+    unsigned bits = 0;
+    for (int k = last - 1; k >= first; --k) {
+        const int* ent = sp + 2 + kPlanEnt * k;
+        unsigned r = 0;
+        if (ent[0] > 1) {
+            const unsigned qd = rt_div(idx, ent);
+            r = idx - qd * (unsigned)ent[0];
+            idx = qd;
+        }
+        if (ent[1]) sc += r * (unsigned)ent[2]; else sr += r * (unsigned)ent[2];
+        bits |= rt_label_parity(__ldg(sg.lab[k] + (long long)b * sg.lst[k] + r), sg.fermi) << k;
+    }
+    return bits;
+}
 __device__ __forceinline__ void rt_decode(const int* sp, int first, int last, unsigned idx, unsigned& sr, unsigned& sc) {
     for (int k = last - 1; k >= first; --k) {
         const int* ent = sp + 2 + kPlanEnt * k;
+        if (ent[0] <= 1) continue;
         const unsigned qd = rt_div(idx, ent);
         const unsigned r = idx - qd * (unsigned)ent[0];
         idx = qd;
@@ -326,8 +357,11 @@ __global__ void __launch_bounds__(kRepackThreads) rt_repack_pair_kernel(RtRepack
 constexpr int RTR = 128, RTC = 128;      // largest tile extents; the tile shape is chosen per sector: tc = 2^ceil(log2 n) <= 128, tr = 2048 / tc <= 128
 struct RtTileDesc { int m, n, tn, start, rstart, cstart, moff, tr, tc; };
 
+template <bool SIGNED>
 __device__ __forceinline__ void rt_repack_tiles(const int* __restrict__ plan, const RtForm& S, const RtForm& D, const RtSpec& spec,
-                                                double* __restrict__ dst, long long dst_stride, unsigned long long* stats) {
+                                                double* __restrict__ dst, long long dst_stride, unsigned long long* stats, const RtSign* sgp) {
+    __shared__ unsigned s_fr[SIGNED ? RTR : 1], s_mr[SIGNED ? RTR : 1], s_fc[SIGNED ? RTC : 1], s_bc[SIGNED ? RTC : 1];
+    __shared__ int s_quad[SIGNED ? 24 : 1];
     __shared__ int sp[kPlanMax];
     __shared__ int hS[2][RT_HDR];
     __shared__ int mS[RT_MSTRIDE], mD[RT_MSTRIDE];
@@ -397,6 +431,13 @@ __device__ __forceinline__ void rt_repack_tiles(const int* __restrict__ plan, co
     const int* d_perm_c = gDc + RT_HDR;
     const int nd = n_desc, total = n_items;
     const int s_nvr = sR.nvalid(), s_nvc = sC.nvalid();
+    unsigned lin = 0, s0 = 0;
+    if (SIGNED) {
+        const int pc = sgp->per_chain[(long long)b * sgp->pcs];
+        lin = (unsigned)pc & 0x7fffffffu; s0 = ((unsigned)pc >> 31) & 1u;
+        if (tid < nr + nc) s_quad[tid] = sgp->quad[tid];
+        __syncthreads();
+    }
     int cur = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
         while (cur + 1 < nd && dsc[cur + 1].start <= item) ++cur;
@@ -407,11 +448,24 @@ __device__ __forceinline__ void rt_repack_tiles(const int* __restrict__ plan, co
         __syncthreads();        // the previous tile's contributions are no longer read
         if (tid < rows) {
             unsigned x = 0, y = 0;
-            rt_decode(sp, 0, nr, (unsigned)d_perm_r[e.rstart + r0 + tid], x, y);
+            if (SIGNED) {
+                const unsigned bits = rt_decode_bits(sp, 0, nr, (unsigned)d_perm_r[e.rstart + r0 + tid], x, y, *sgp, b);
+                // f_r = lin . bits + quadratic part inside the row group; m_r = rows of Q selected by the bits (for the cross term)
+                unsigned f = __popc(bits & lin) & 1u, mk = 0;
+                for (int k = 0; k < nr; ++k)
+                    if ((bits >> k) & 1u) { f ^= __popc(bits & (unsigned)s_quad[k]) & 1u; mk ^= (unsigned)s_quad[k]; }
+                s_fr[tid] = f; s_mr[tid] = mk;
+            } else rt_decode(sp, 0, nr, (unsigned)d_perm_r[e.rstart + r0 + tid], x, y);
             rsr[tid] = x; rsc[tid] = y;
         } else if (tid >= 128 && tid - 128 < cols) {
             unsigned x = 0, y = 0;
-            rt_decode(sp, nr, nr + nc, (unsigned)d_perm_c[e.cstart + c0 + tid - 128], x, y);
+            if (SIGNED) {
+                const unsigned bits = rt_decode_bits(sp, nr, nr + nc, (unsigned)d_perm_c[e.cstart + c0 + tid - 128], x, y, *sgp, b);
+                unsigned f = __popc(bits & lin) & 1u;
+                for (int k = nr; k < nr + nc; ++k)
+                    if ((bits >> k) & 1u) f ^= __popc(bits & (unsigned)s_quad[k]) & 1u;
+                s_fc[tid - 128] = f; s_bc[tid - 128] = bits;
+            } else rt_decode(sp, nr, nr + nc, (unsigned)d_perm_c[e.cstart + c0 + tid - 128], x, y);
             csr[tid - 128] = x; csc[tid - 128] = y;
         }
         __syncthreads();
@@ -425,6 +479,10 @@ __device__ __forceinline__ void rt_repack_tiles(const int* __restrict__ plan, co
                 if (j >= 0 && q >= sC.sstart(j) && q < sC.sstart(j + 1))
                     v = __ldg(src + sM.moff(i) + (long long)(p - sR.sstart(i)) * sC.count(j) + (q - sC.sstart(j)));
             }
+            if (SIGNED) {
+                const unsigned sgn = s0 ^ s_fr[a] ^ s_fc[c] ^ (__popc(s_mr[a] & s_bc[c]) & 1u);
+                if (sgn) v = -v;
+            }
             out[e.moff + (long long)(r0 + a) * e.n + c0 + c] = v;
         }
         if (t == 0 && tid == 0 && ((e.m * e.n) & 1)) out[e.moff + (long long)e.m * e.n] = 0.0;
@@ -432,11 +490,15 @@ __device__ __forceinline__ void rt_repack_tiles(const int* __restrict__ plan, co
 }
 
 __global__ void __launch_bounds__(kRepackThreads) rt_repack_tile_kernel(RtRepackArgs p, unsigned long long* stats) {
-    rt_repack_tiles(p.plan, p.S, p.D, p.spec, p.dst, p.dst_stride, stats);
+    rt_repack_tiles<false>(p.plan, p.S, p.D, p.spec, p.dst, p.dst_stride, stats, nullptr);
 }
 __global__ void __launch_bounds__(kRepackThreads) rt_repack_tile_pair_kernel(RtRepackPair p, unsigned long long* stats) {
     const RtRepackArgs& q = p.a[blockIdx.z];
-    rt_repack_tiles(q.plan, q.S, q.D, q.spec, q.dst, q.dst_stride, stats);
+    rt_repack_tiles<false>(q.plan, q.S, q.D, q.spec, q.dst, q.dst_stride, stats, nullptr);
+}
+// the same regrouping with the fermionic sign of every element (edge_operator.hpp:497-555, 591, 612 evaluated per element)
+__global__ void __launch_bounds__(kRepackThreads) rt_repack_signed_kernel(RtRepackArgs p, RtSign sg, unsigned long long* stats) {
+    rt_repack_tiles<true>(p.plan, p.S, p.D, p.spec, p.dst, p.dst_stride, stats, &sg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -915,6 +977,22 @@ extern "C" int tnsp_rt_repack_f64(const int32_t* plan, const tnsp_rt_form* src, 
     else if (dd) rt_repack_kernel<false, true><<<grid, kRepackThreads, 0, st>>>(p, rt_stats_ptr());
     else rt_repack_tile_kernel<<<tile_grid(dst->M, dst->N, nb, 1), kRepackThreads, 0, st>>>(p, rt_stats_ptr());
     return check_launch("tnsp_rt_repack_f64");
+}
+
+extern "C" int tnsp_rt_repack_signed_f64(const int32_t* plan, const tnsp_rt_form* src, const tnsp_rt_form* dst, const tnsp_rt_match_spec* dst_match,
+                                         double* dst_data, int64_t dst_stride, const int32_t* quad, const int32_t* per_chain,
+                                         int64_t per_chain_stride, int n_entries, const int32_t* const* labels, const int64_t* lstrides,
+                                         int fermi_mask, int nb, void* stream) {
+    if (nb == 0) return 0;
+    if (!src->rt || !dst->rt) { set_error("tnsp_rt_repack_signed_f64: both layouts must be sector-compact"); return 1; }
+    if (n_entries > 24) { set_error("tnsp_rt_repack_signed_f64: at most 24 indexed edges"); return 1; }
+    RtRepackArgs p;
+    p.plan = plan; p.S = to_form(src); p.D = to_form(dst); p.spec = to_spec(dst_match); p.dst = dst_data; p.dst_stride = dst_stride; p.dense_size = 0;
+    RtSign sg;
+    sg.quad = quad; sg.per_chain = per_chain; sg.pcs = per_chain_stride; sg.fermi = fermi_mask;
+    for (int i = 0; i < 24; ++i) { sg.lab[i] = i < n_entries ? labels[i] : nullptr; sg.lst[i] = i < n_entries ? lstrides[i] : 0; }
+    rt_repack_signed_kernel<<<tile_grid(dst->M, dst->N, nb, 1), kRepackThreads, 0, (cudaStream_t)stream>>>(p, sg, rt_stats_ptr());
+    return check_launch("tnsp_rt_repack_signed_f64");
 }
 
 extern "C" int tnsp_rt_repack_pair_f64(const int32_t* plan0, const tnsp_rt_form* src0, const tnsp_rt_form* dst0, const tnsp_rt_match_spec* match0,
