@@ -35,6 +35,17 @@ WORKLOADS = {
     "heis6": dict(L1=6, L2=6, D=6, Dc=36, sym="No", J2=0.0, sr=False, cg=0, chains=148,
                   desc="6x6 Heisenberg, no symmetry (dense tensors), D=6, Dc=36, float64"),
     "tiny": dict(L1=3, L2=3, D=2, Dc=4, sym="No", J2=0.0, sr=False, cg=0, chains=64, desc="3x3 Heisenberg, no symmetry, D=2, Dc=4 (smoke size)"),
+    # fermionic lock-step chains (sector-compact engine; bond profiles as SURVEY.md 8d prescribes, tetragono/models.py)
+    "cfg3": dict(model="hubbard_ff", L1=8, L2=8, D=8, Dc=64, sym="FermiU1FermiU1", T=64, U=8.0, sr=False, cg=0, chains=74,
+                 desc="8x8 fermionic Hubbard (FermiU1 x FermiU1 edges, half filling, U/t = 8), D=8 (2+1+1+1+1+1+1 over the charge "
+                      "fluctuations of a bond), Dc=64, sweep sampling + gradient, float64"),
+    "cfg3s": dict(model="hubbard_ff", L1=4, L2=4, D=8, Dc=16, sym="FermiU1FermiU1", T=16, U=8.0, sr=False, cg=0, chains=64,
+                  desc="4x4 fermionic Hubbard (FermiU1 x FermiU1), D=8, Dc=16 (smoke size of cfg3)"),
+    "cfg4": dict(model="tJ", L1=10, L2=10, D=10, Dc=100, sym="FermiU1BoseU1", T=40, J=0.4, sr=True, cg=20, chains=37,
+                 desc="10x10 t-J model (FermiU1 x BoseU1 edges, 80 particles), D=10 (1,1,1,1,2,1,1,1,1), Dc=100, sweep sampling "
+                      "(ergodic enumeration of 3^100 configurations is not feasible) + gradient + SR natural gradient (CG 20), float64"),
+    "cfg4s": dict(model="tJ", L1=4, L2=4, D=10, Dc=16, sym="FermiU1BoseU1", T=2, J=0.4, sr=True, cg=4, chains=64,
+                  desc="4x4 t-J model (FermiU1 x BoseU1), D=10 (1,1,1,1,2,1,1,1,1), Dc=16 (smoke size of cfg4)"),
 }
 
 
@@ -43,12 +54,62 @@ def build_workload(tat, wl, state_classes=None):
     builds the model for this repository's device tensors and for the reference PyTAT classes."""
     from tnsp_b200.tetragono import models
     from tnsp_b200.tetragono.state import SamplingLattice
+    if wl.get("model") in ("hubbard_ff", "tJ"):
+        return build_fermionic_workload(tat, wl)
     T = getattr(tat, wl["sym"]).D.Tensor
     abstract = models.j1j2_abstract_lattice(T, wl["L1"], wl["L2"], wl["D"], 1.0, wl["J2"])
     tat.random.seed(2333)
     lat = SamplingLattice(abstract)
     hopping = models.nearest_neighbour_terms(lat) if wl["J2"] != 0 else None
     return lat, hopping, models.neel_points(lat)
+
+
+def fermionic_start(wl):
+    """total physical indices [L1, L2, 1] of the start configuration: the particles of every row staggered, rows shifted by one site.
+    Hubbard: physical edge (empty, down, up, double) -> alternating up / down (half filling); t-J: (hole, down, up), T / L1 up and
+    T / L1 down particles per row, the holes spread evenly (for 4 x 4, T = 2: the fixture's pattern, particles in rows 0 and 2)"""
+    L1, L2 = wl["L1"], wl["L2"]
+    out = np.zeros((L1, L2, 1), dtype=np.int64)
+    if wl["model"] == "hubbard_ff":
+        for l1 in range(L1):
+            for l2 in range(L2):
+                out[l1, l2, 0] = 2 if (l1 + l2) % 2 == 0 else 1
+        return out
+    per_row = 2 * wl["T"] // L1
+    if per_row == 0 or (2 * wl["T"]) % L1:
+        rows = [r for r in range(L1) if r % 2 == 0][:wl["T"]]          # one up + one down in every other row
+        for k, r in enumerate(rows):
+            out[r, 0, 0], out[r, 2, 0] = (2, 1) if k % 2 == 0 else (1, 2)
+        return out
+    for l1 in range(L1):
+        holes = L2 - per_row
+        hole_at = {int((h + 1) * L2 / holes) - 1 for h in range(holes)} if holes else set()
+        k = l1
+        for l2 in range(L2):
+            if l2 in hole_at:
+                continue
+            out[l1, l2, 0] = 2 if k % 2 == 0 else 1
+            k += 1
+    return out
+
+
+def build_fermionic_workload(tat, wl):
+    """cfg3 / cfg4 families on this repository's tensors (the reference arm builds the same model with the reference's own tetraku
+    modules, `_reference_fermionic_workload`)"""
+    from tnsp_b200.tetragono import models
+    from tnsp_b200.tetragono.state import SamplingLattice
+    L1, L2 = wl["L1"], wl["L2"]
+    if wl["model"] == "hubbard_ff":
+        D = models.HUBBARD_D8 if wl["D"] == 8 else wl["D"]
+        abstract = models.hubbard_fermi_fermi_abstract_lattice(L1, L2, D, wl["T"], 1.0, wl["U"])
+    else:
+        D = models.TJ_D10 if wl["D"] == 10 else wl["D"]
+        abstract = models.tJ_abstract_lattice(L1, L2, D, wl["T"], 1.0, wl["J"])
+    tat.random.seed(2333)
+    lat = SamplingLattice(abstract)
+    start = fermionic_start(wl)
+    points = [[{0: lat.physics_edges[l1, l2, 0].point_by_index(int(start[l1, l2, 0]))} for l2 in range(L2)] for l1 in range(L1)]
+    return lat, None, points
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -269,7 +330,7 @@ def run_own(args):
     L1, L2, Dc, desc = wl["L1"], wl["L2"], wl["Dc"], wl["desc"]
     nb = args.chains or wl["chains"]
     sym_lat, hopping, points = build_workload(TAT, wl)
-    sector = wl["sym"] != "No" and args.engine == "sector"
+    sector = wl["sym"] != "No" and (args.engine == "sector" or wl["sym"].startswith("Fermi"))
     if wl["sym"] == "No":
         lat = sym_lat
         conf0 = models.neel_configuration(L1, L2)
@@ -320,10 +381,11 @@ def run_own(args):
     o0.normalize_lattice()
     del s0, o0
 
-    if sector and nb > 148:
+    n_cal = min(148, max(4, nb // 8))
+    if sector and nb > n_cal:
         # buffer capacities of the sector-compact engine are learnt on a small throw-away batch first (TAT/ragged.py)
         from tnsp_b200.tetragono.sampling import calibrate_sector_engine
-        calibrate_sector_engine(lat, Dc, conf0, hopping, chains=148, sweeps=2,
+        calibrate_sector_engine(lat, Dc, conf0, hopping, chains=n_cal, sweeps=2,
                                 observer_options=dict(enable_energy=True, enable_gradient=True, enable_natural_gradient=wl["sr"]))
     rng = ChainRng(nb)
     rng.seed([(2333 + rank * nb + c) % 2**31 for c in range(nb)])

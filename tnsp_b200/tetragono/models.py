@@ -144,9 +144,14 @@ def tJ_abstract_lattice(L1, L2, D, T, t, J):
     carry the charge still to be distributed over the rows below, +- 2 particles of either spin) and along the rows; all other
     vertical bonds are trivial.  `D` is the dimension PER charge sector (9 sectors per charged bond)."""
     state = AbstractLattice(tJ_abstract_state(L1, L2, T, t, J))
+    # `D`: dimension per charge sector, or the 9 per-sector dimensions in the order of the list below (BASELINE cfg4: D = 10 as
+    # 1,1,1,1,2,1,1,1,1, SURVEY.md 8d); an uncharged bond then carries their sum in its single sector
+    profile = [D] * 9 if isinstance(D, int) else list(D)
+    D = D if isinstance(D, int) else sum(profile)
 
     def charged(Q):
-        return [((2 * Q + dn, ds), D) for dn, spins in ((-2, (0,)), (-1, (-1, 1)), (0, (-2, 0, 2)), (1, (-1, 1)), (2, (0,))) for ds in spins]
+        sectors = [(dn, ds) for dn, spins in ((-2, (0,)), (-1, (-1, 1)), (0, (-2, 0, 2)), (1, (-1, 1)), (2, (0,))) for ds in spins]
+        return [((2 * Q + dn, ds), d) for (dn, ds), d in zip(sectors, profile) if d > 0]
 
     per_row = T / L1
     for l1 in range(L1 - 1):
@@ -157,6 +162,24 @@ def tJ_abstract_lattice(L1, L2, D, T, t, J):
         for l2 in range(L2 - 1):
             state.virtual_bond[l1, l2, "R"] = charged(int(per_row * (L2 - l2 - 1) / L2))
     return state
+
+
+# BASELINE cfg3 (D = 8 on a bond with 9 possible charge fluctuations): two states without fluctuation, one for every single-particle
+# fluctuation of either spin, one for each spin flip (n_up +- 1, n_down -+ 1); the double fluctuations (+-1, +-1) are left out
+HUBBARD_D8 = {(0, 0): 2, (1, 0): 1, (-1, 0): 1, (0, 1): 1, (0, -1): 1, (1, -1): 1, (-1, 1): 1}
+TJ_D10 = (1, 1, 1, 1, 2, 1, 1, 1, 1)
+
+
+def staggered_fermion_configuration(lattice, per_row):
+    """total physical indices [L1, L2, 1] of a start configuration with `per_row` = (pattern of length L2) cycled and shifted by
+    one site from row to row; pattern entries are indices of the physical edge"""
+    L1, L2 = lattice.L1, lattice.L2
+    import numpy as np
+    out = np.zeros((L1, L2, 1), dtype=np.int64)
+    for l1 in range(L1):
+        for l2 in range(L2):
+            out[l1, l2, 0] = per_row[l1 % len(per_row)][l2]
+    return out
 
 
 def hubbard_fermi_fermi_abstract_state(L1, L2, T, t, U):
@@ -182,9 +205,13 @@ def hubbard_fermi_fermi_abstract_lattice(L1, L2, D, T, t, U):
     `D` per charge sector (9 sectors per charged bond)."""
     state = AbstractLattice(hubbard_fermi_fermi_abstract_state(L1, L2, T, t, U))
     half = T // 2
+    # `D`: dimension per charge sector, or {(a, b): dimension} for the fluctuations (a, b) in {-1, 0, 1}^2 of (n_up, n_down) around
+    # the mean charge of the bond (BASELINE cfg3: D = 8, see HUBBARD_D8); an uncharged bond carries the sum in its single sector
+    profile = {(a, b): D for a in (-1, 0, 1) for b in (-1, 0, 1)} if isinstance(D, int) else dict(D)
+    D = D if isinstance(D, int) else sum(profile.values())
 
     def charged(Q):
-        return [((Q + a, Q + b), D) for a in (-1, 0, 1) for b in (-1, 0, 1)]
+        return [((Q + a, Q + b), profile[a, b]) for a in (-1, 0, 1) for b in (-1, 0, 1) if profile.get((a, b), 0) > 0]
 
     per_row = half / L1
     for l1 in range(L1 - 1):
