@@ -42,29 +42,43 @@ _PLANS: dict = {}
 
 # Learnt capacities.  The stored size of a sector-compact tensor is only known on the device; allocating the dense bound
 # prod(dims) for every result would keep the zero-padded footprint of round 1 (165 GB at 592 chains of cfg2).  Every operation
-# signature therefore measures the largest per-chain size of its first CAP_LEARN executions (the only device -> host reads of the
-# engine, gone after the first sweep) and later allocates CAP_FACTOR x that.  A chain that still does not fit is stored EMPTY and
+# signature therefore measures its largest per-chain size during a learning phase (a small calibration batch, or the first two sweeps:
+# the only device -> host reads of the engine) and later allocates CAP_FACTOR x that.  A chain that still does not fit is stored EMPTY and
 # counted on the device (backend.rt_overflow, checked by the samplers once per sweep): never silent, never out of bounds.
 _CAPS: dict = {}
-CAP_LEARN = 3
 CAP_FACTOR = 2.0
 CAPS_ENABLED = True
 TABLE_CACHE_MAX = 4096       # merged dimension up to which a group table is shared through its label arrays
+_LEARN = {"all": True, "cycles": 0}     # learning phase: every operation allocates the dense bound and records its largest size
+
+
+def freeze_capacities():
+    """end of the learning phase: from now on an operation signature seen before allocates CAP_FACTOR x its largest recorded size"""
+    _LEARN["all"] = False
+
+
+def learning_cycle_done(cycles=2):
+    """called by the drivers after every sweep + observation while learning: the phase ends after `cycles` of them"""
+    if _LEARN["all"]:
+        _LEARN["cycles"] += 1
+        if _LEARN["cycles"] >= cycles:
+            freeze_capacities()
 
 
 def _cap(key, dense):
     """(elements to allocate, learning?)"""
+    if not CAPS_ENABLED:
+        return dense, False
     c = _CAPS.get(key)
-    if not CAPS_ENABLED or c is None or c[0] < CAP_LEARN:
-        return dense, CAPS_ENABLED
-    return min(dense, int(c[1] * CAP_FACTOR) + 16), False
+    if _LEARN["all"] or c is None:
+        return dense, True
+    return min(dense, int(c * CAP_FACTOR) + 64), False
 
 
 def _learn(key, match):
     B = _bk.get()
     mx = int(B.to_numpy(match[:, 0]).max()) if match.shape[0] else 0
-    c = _CAPS.get(key)
-    _CAPS[key] = [1, mx] if c is None else [c[0] + 1, max(c[1], mx)]
+    _CAPS[key] = max(_CAPS.get(key, 0), mx)
 
 
 def pack_symmetry(sym):

@@ -346,8 +346,10 @@ class Observer:
                 import torch
                 self._Deltas.append((reweight.copy(), Es.copy(), torch.cat(rows, dim=1)))
         if ragged:
+            from ..TAT import ragged as _ragged
             from .sampling import _check_capacity
             _check_capacity()
+            _ragged.learning_cycle_done()
 
     # -- results -------------------------------------------------------------------------------------
     def _expect_and_deviation(self, total_reweight, total_reweight_square, total_square_reweight_square):

@@ -100,11 +100,14 @@ def calibrate_sector_engine(owner, cut_dimension, configuration, hopping_hamilto
     s = SweepSampling(owner, cut_dimension, None, hopping_hamiltonians, nb=chains, rng=rng)
     conf = np.asarray(configuration)
     s.configuration.import_configuration(np.broadcast_to(conf, (chains,) + conf.shape) if conf.ndim == 3 else conf[:chains])
+    from ..TAT import ragged
+    ragged._LEARN["all"], ragged._LEARN["cycles"] = True, 0
     obs = Observer(owner, **(observer_options or dict(enable_energy=True, enable_gradient=True)))
     with obs:
         for _ in range(sweeps):
             p, c = s()
             obs(p, c)
+    ragged.freeze_capacities()
 
 
 class Sampling:
