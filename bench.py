@@ -370,7 +370,7 @@ def run_own(args):
             raise RuntimeError(f"bench parity check failed: {parity}")
         del pc, po
     # one normalisation pass so that amplitudes are O(1) (observer.normalize_lattice)
-    s0 = SweepSampling(lat, Dc, None, hopping, nb=1)
+    s0 = SweepSampling(lat, Dc, None, hopping, nb=1, engine="sector" if sector else None)
     s0.configuration.import_configuration(conf0)
     TAT.random.seed(2333)
     o0 = Observer(lat, enable_energy=True)
@@ -380,8 +380,14 @@ def run_own(args):
             o0(p, c)
     o0.normalize_lattice()
     del s0, o0
+    if sector:
+        # the single normalisation chain must not define the buffer capacities of the batch: learn again (calibration batch below, or
+        # the first two warm-up steps)
+        from tnsp_b200.TAT import ragged as _ragged
+        _ragged._CAPS.clear()
+        _ragged._LEARN.update(all=True, cycles=0)
 
-    n_cal = min(148, max(4, nb // 8))
+    n_cal = min(148, max(32, nb // 8))
     if sector and nb > n_cal:
         # buffer capacities of the sector-compact engine are learnt on a small throw-away batch first (TAT/ragged.py)
         from tnsp_b200.tetragono.sampling import calibrate_sector_engine

@@ -46,7 +46,7 @@ _PLANS: dict = {}
 # the only device -> host reads of the engine) and later allocates CAP_FACTOR x that.  A chain that still does not fit is stored EMPTY and
 # counted on the device (backend.rt_overflow, checked by the samplers once per sweep): never silent, never out of bounds.
 _CAPS: dict = {}
-CAP_FACTOR = 2.0
+CAP_FACTOR = 3.0
 CAPS_ENABLED = True
 TABLE_CACHE_MAX = 4096       # merged dimension up to which a group table is shared through its label arrays
 _LEARN = {"all": True, "cycles": 0}     # learning phase: every operation allocates the dense bound and records its largest size

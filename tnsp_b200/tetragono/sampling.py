@@ -124,10 +124,10 @@ class Sampling:
 
 
 class SweepSampling(Sampling):
-    def __init__(self, owner, cut_dimension, restrict_subspace=None, hopping_hamiltonians=None, *, nb=1, rng=None):
+    def __init__(self, owner, cut_dimension, restrict_subspace=None, hopping_hamiltonians=None, *, nb=1, rng=None, engine=None):
         super().__init__(owner, cut_dimension, restrict_subspace)
         self.nb = nb
-        self.configuration = Configuration(owner, cut_dimension, nb)
+        self.configuration = Configuration(owner, cut_dimension, nb, engine=engine)
         self._hopping_hamiltonians = hopping_hamiltonians if hopping_hamiltonians is not None else owner._hamiltonians
         self._sweep_order = self._get_proper_position_order()
         self.rng = rng if rng is not None else (_GlobalRng() if nb == 1 else ChainRng(nb))
