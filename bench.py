@@ -388,7 +388,9 @@ def run_own(args):
         _ragged._LEARN.update(all=True, cycles=0)
 
     n_cal = min(148, max(32, nb // 8))
-    if sector and nb > n_cal:
+    if sector and wl["sym"].startswith("Fermi"):
+        _ragged.CAP_FACTOR = 3.0          # few chains per GPU: the calibration maxima are noisier, memory is not the limit
+    if sector and nb > n_cal and nb >= _ragged.CAP_MIN_CHAINS:
         # buffer capacities of the sector-compact engine are learnt on a small throw-away batch first (TAT/ragged.py)
         from tnsp_b200.tetragono.sampling import calibrate_sector_engine
         calibrate_sector_engine(lat, Dc, conf0, hopping, chains=n_cal, sweeps=2,

@@ -46,7 +46,8 @@ _PLANS: dict = {}
 # the only device -> host reads of the engine) and later allocates CAP_FACTOR x that.  A chain that still does not fit is stored EMPTY and
 # counted on the device (backend.rt_overflow, checked by the samplers once per sweep): never silent, never out of bounds.
 _CAPS: dict = {}
-CAP_FACTOR = 3.0
+CAP_FACTOR = 2.0
+CAP_MIN_CHAINS = 64          # smaller batches always allocate the dense bound: their maxima fluctuate too much and memory is no issue
 CAPS_ENABLED = True
 TABLE_CACHE_MAX = 4096       # merged dimension up to which a group table is shared through its label arrays
 _LEARN = {"all": True, "cycles": 0}     # learning phase: every operation allocates the dense bound and records its largest size
@@ -65,9 +66,11 @@ def learning_cycle_done(cycles=2):
             freeze_capacities()
 
 
-def _cap(key, dense):
+def _cap(key, dense, nb=None):
     """(elements to allocate, learning?)"""
     if not CAPS_ENABLED:
+        return dense, False
+    if nb is not None and nb < CAP_MIN_CHAINS and not _LEARN["all"]:
         return dense, False
     c = _CAPS.get(key)
     if _LEARN["all"] or c is None:
@@ -214,7 +217,7 @@ class Core:
         src = self.forms[self.primary]
         nbd = max(src.data.shape[0], src.match.shape[0], rt.shape[0], ct.shape[0], 1 if self.target is None else self.target.shape[0])
         ckey = ("form", tuple(e.dim for e in self.edges), src.rows, src.cols, rows, cols)
-        cap, learning = _cap(ckey, M * N)
+        cap, learning = _cap(ckey, M * N, nbd)
         f = Form(rows, cols, rt, rs, ct, cs, None, B.rt_alloc(nbd, cap), M, N)
         STATS["repack"] += 1
         if len(self.forms) >= 4:          # keep the primary and the most recent regroupings only
@@ -638,7 +641,7 @@ def _contract(a, b, pairs):
     cols = tuple(pos[("b", j)] for j in fb_n)
     rs, cs = A.rs * a.sign, Bf.cs * b.sign
     nb = max(nb, A.match.shape[0], Bf.match.shape[0])
-    cap, learning = _cap(key, A.M * Bf.N)
+    cap, learning = _cap(key, A.M * Bf.N, nb)
     data = B.rt_alloc(nb, cap)
     C = Form(rows, cols, A.rt, rs, Bf.ct, cs, None, data, A.M, Bf.N)
     ksign = -(a.sign * A.cs) * (b.sign * Bf.rs)
@@ -733,8 +736,8 @@ def _factor(t, first_names, kind, name_1, name_2, sing_1, sing_2, cut):
         t1, t1s = None, 0
     # bond labels + per-sector factorisation, all planned on the device
     fkey = ("fac", kind, tuple(e.dim for e in core.edges), rows, cols, kdim)
-    c1, l1 = _cap(fkey + (1,), F.M * max(kdim, 1))
-    c2, l2 = _cap(fkey + (2,), max(kdim, 1) * F.N)
+    c1, l1 = _cap(fkey + (1,), F.M * max(kdim, 1), nb)
+    c2, l2 = _cap(fkey + (2,), max(kdim, 1) * F.N, nb)
     out = B.rt_factor(kind, F, t.sign, core.target, core.tsign * t.sign, t1, t1s, kdim, remain_cut, relative_cut, nb, (c1, c2))
     if l1:
         _learn(fkey + (1,), out["first"][0])

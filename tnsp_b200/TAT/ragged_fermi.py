@@ -127,8 +127,8 @@ def signed_form(t, rows, cols, form):
     ct, cs = core.table(cols)
     M, N = core.group_dim(rows), core.group_dim(cols)
     ckey = ("form", tuple(e.dim for e in core.edges), src.rows, src.cols, rows, cols)
-    cap, learning = ragged._cap(ckey, M * N)
     nbd = max(src.data.shape[0], src.match.shape[0], rt.shape[0], ct.shape[0], per_chain.shape[0], 1 if core.target is None else core.target.shape[0])
+    cap, learning = ragged._cap(ckey, M * N, nbd)
     f = Form(rows, cols, rt, rs, ct, cs, None, B.rt_alloc(nbd, cap), M, N)
     STATS["repack"] += 1
     labels = [(core.edges[i].arr, core.edges[i].dim) for i in entries]
@@ -224,7 +224,7 @@ def fermi_contract(a, b, pairs):
     cols = tuple(len(fa) + k for k, j in enumerate(fb) if not eb[j].unit)
     rs, cs = A.rs * a.sign, Bf.cs * b.sign
     key = ("fct", tuple(e.dim for e in ea), fa_n, ka, tuple(e.dim for e in eb), kb, fb_n)
-    cap, learning = ragged._cap(key, A.M * Bf.N)
+    cap, learning = ragged._cap(key, A.M * Bf.N, nb)
     C = Form(rows, cols, A.rt, rs, Bf.ct, cs, None, B.rt_alloc(nb, cap), A.M, Bf.N)
     ksign = -(a.sign * A.cs) * (b.sign * Bf.rs)
     target = B.rt_gemm(A, Bf, C, ksign, nb, (rs, cs, a.core.target, a.core.tsign * a.sign, b.core.target, b.core.tsign * b.sign))
