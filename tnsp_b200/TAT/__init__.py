@@ -5,7 +5,8 @@ sampling-VMC hot path: same submodule / class tree, tensors live on the B200.
         .Symmetry  .Edge  .EdgeSegment  .{S,D,C,Z}.Tensor   (+ float/complex/float64/... aliases)
     TAT.{Normal,Z2,U1} aliases, TAT.random, TAT.version
 
-Only float64 ("D") tensors are device-backed; the other scalar types raise on construction.
+Only float64 ("D") tensors are device-backed (the hot path); S / C / Z tensors are host-side constants for model definitions
+(TAT/host_scalars.py).
 """
 import sys
 import types
@@ -49,11 +50,11 @@ def _build():
         m.EdgeSegment = E
         for short, dtype, real in (("S", "float32", True), ("D", "float64", True), ("C", "complex64", False), ("Z", "complex128", False)):
             sm = types.ModuleType(f"{__name__}.{sym_name}.{short}")
-            if short == "D":
-                T = type("Tensor", (_TensorBase,), {"__slots__": (), "Symmetry": S, "Edge": E, "model": m, "dtype": dtype, "btype": short,
-                                                    "is_real": real, "is_complex": not real})
-            else:
-                T = _unsupported_scalar(short, sym_name)
+            import numpy as _np
+            T = type("Tensor", (_TensorBase,), {"__slots__": (), "Symmetry": S, "Edge": E, "model": m, "dtype": dtype, "btype": short,
+                                                "is_real": real, "is_complex": not real, "_np": _np.dtype(dtype),
+                                                # float64 lives on the B200; the other scalar types are host-side constants
+                                                "_host_only": short != "D"})
             T.__module__ = sm.__name__
             T.__qualname__ = "Tensor"
             sm.Tensor = T
@@ -71,6 +72,16 @@ def _build():
 
 
 _build()
+
+
+class _CallableModule(types.ModuleType):
+    """`TAT()` returns the build information, like the reference module (PyTAT.hpp:77-84)"""
+
+    def __call__(self):
+        return self.information
+
+
+sys.modules[__name__].__class__ = _CallableModule
 
 
 def parity(p):

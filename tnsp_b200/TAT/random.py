@@ -22,6 +22,19 @@ def seed(seed):
     _bk.host_lib().tnsp_rng_seed_host(_rng(), 0, int(seed) & 0xFFFFFFFF)
 
 
+class _Distribution:
+    """what TAT.random.uniform_int / uniform_real / normal return: a callable OBJECT, like the builtin pybind11 hands out
+    (PyTAT.hpp:96-126).  The reference stores it as a class attribute and calls `self.random_int()` (tetragono/utility.py:143-153):
+    a plain Python function would be bound to the instance there, an object with __call__ is not."""
+    __slots__ = ("_draw",)
+
+    def __init__(self, draw):
+        self._draw = draw
+
+    def __call__(self):
+        return self._draw()
+
+
 def uniform_int(min=0, max=1):
     lo = np.array([min], dtype=np.int32)
     hi = np.array([max], dtype=np.int32)
@@ -31,7 +44,7 @@ def uniform_int(min=0, max=1):
         _bk.host_lib().tnsp_rng_uniform_int_host(_rng(), lo.ctypes.data, hi.ctypes.data, None, out.ctypes.data)
         return int(out[0])
 
-    return draw
+    return _Distribution(draw)
 
 
 def uniform_real(min=0, max=1):
@@ -41,7 +54,7 @@ def uniform_real(min=0, max=1):
         _bk.host_lib().tnsp_rng_uniform_real_host(_rng(), float(min), float(max), None, out.ctypes.data)
         return float(out[0])
 
-    return draw
+    return _Distribution(draw)
 
 
 def normal(mean=0, stddev=1):
@@ -55,7 +68,7 @@ def normal(mean=0, stddev=1):
             buf.extend([out[1], out[0]])
         return float(buf.pop())
 
-    return draw
+    return _Distribution(draw)
 
 
 def _normal_fill(n, mean, stddev):

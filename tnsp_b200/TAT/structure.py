@@ -120,7 +120,25 @@ def make_symmetry_class(short_name, components):
     }
     for i, (field, _, _) in enumerate(components):
         ns[field] = property(lambda self, i=i: tuple.__getitem__(self, i))
-    return type(short_name + "Symmetry", (SymmetryBase,), ns)
+    cls = type(short_name + "Symmetry", (SymmetryBase,), ns)
+    cls.__module__ = __name__
+    globals()[cls.__name__] = cls          # picklable by reference (PyTAT.hpp:160-175 pickles symmetries)
+    return cls
+
+
+class _Segments(tuple):
+    """segment list of an edge: an immutable tuple inside (edges are hashable plan-cache keys) that compares equal to the Python
+    list PyTAT returns (PyTAT.hpp:257-262)"""
+    __slots__ = ()
+
+    def __eq__(self, other):
+        return tuple.__eq__(self, tuple(other)) if isinstance(other, (list, tuple)) else NotImplemented
+
+    def __ne__(self, other):
+        r = self.__eq__(other)
+        return r if r is NotImplemented else not r
+
+    __hash__ = tuple.__hash__
 
 
 class Edge:
@@ -168,7 +186,7 @@ class Edge:
     def _normalize(cls, segs):
         S = cls.Symmetry
         if isinstance(segs, (int, np.integer)) and not isinstance(segs, bool):
-            return ((S(), int(segs)),)
+            return _Segments(((S(), int(segs)),))
         out = []
         for item in segs:
             if isinstance(item, S):
@@ -177,7 +195,7 @@ class Edge:
                 out.append((S(item[0]), int(item[1])))
             else:
                 out.append((S(item), 1))
-        return tuple(out)
+        return _Segments(out)
 
     @classmethod
     def _is_pair(cls, item):

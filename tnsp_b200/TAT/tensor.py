@@ -39,7 +39,7 @@ class BatchScalar:
         self.t = t
 
     def numpy(self):
-        return _bk.get().to_numpy(self.t)
+        return self.t.detach().cpu().numpy()
 
     def __float__(self):
         v = self.numpy()
@@ -93,43 +93,42 @@ class _EdgesProxy:
         return self._t._edges[key]
 
 
-class _StorageView:
-    """Host view of the storage; writes go back to the device (``tensor.storage[...] = x``)."""
+class _StorageView(np.ndarray):
+    """What `tensor.storage` returns: a numpy array of the tensor's elements (PyTAT.hpp:461-506 hands out an ndarray that aliases the
+    tensor's memory).  Here the elements live on the device: the array is a host snapshot, and every write through it
+    (`storage[...] = x`, in-place arithmetic) is sent back to the tensor."""
 
-    def __init__(self, tensor):
-        self._t = tensor
+    def __new__(cls, tensor):
+        host = np.asarray(tensor._host(), dtype=tensor._np)      # (aliases the tensor's memory when the buffers live on the host)
+        obj = host.view(cls)
+        obj._t = tensor
+        return obj
 
-    def __array__(self, dtype=None, copy=None):
-        a = self._t._host()
-        return a if dtype is None else a.astype(dtype)
+    def __array_finalize__(self, obj):
+        self._t = getattr(obj, "_t", None) if obj is not None and getattr(obj, "base", None) is None else None
 
-    def __getitem__(self, key):
-        return self._t._host()[key]
+    def _push(self):
+        owner = self
+        while isinstance(owner.base, np.ndarray) and getattr(owner.base, "_t", None) is not None:
+            owner = owner.base
+        if getattr(owner, "_t", None) is not None:
+            owner._t._set_host(np.asarray(owner))
 
     def __setitem__(self, key, value):
-        a = self._t._host().copy()
-        a[key] = value
-        self._t._set_host(a)
+        np.ndarray.__setitem__(self, key, value)
+        if self._t is not None:
+            self._push()
 
-    def __len__(self):
-        return self._t._table.size
-
-    @property
-    def size(self):
-        return self._t._table.size
-
-    @property
-    def shape(self):
-        return (self._t._table.size,)
-
-    def tolist(self):
-        return self._t._host().tolist()
-
-    def __repr__(self):
-        return repr(self._t._host())
-
-    def __eq__(self, other):
-        return self._t._host() == np.asarray(other)
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        plain = tuple(np.asarray(x) if isinstance(x, _StorageView) else x for x in inputs)
+        if out is not None:
+            targets = tuple(np.asarray(o) if isinstance(o, _StorageView) else o for o in out)
+            result = getattr(ufunc, method)(*plain, out=targets, **kwargs)
+            for o in out:
+                if isinstance(o, _StorageView) and o._t is not None:
+                    o._push()
+            return out[0] if len(out) == 1 else out
+        return getattr(ufunc, method)(*plain, **kwargs)
 
 
 class _BlocksProxy:
@@ -208,6 +207,15 @@ class Tensor:
     is_complex = False
     dtype = "float64"
     btype = "D"
+    _np = np.dtype("float64")
+    _host_only = False        # S / C / Z scalar types: model-definition constants, host arithmetic (TAT/host_scalars.py)
+
+    @classmethod
+    def _B(cls):
+        if cls._host_only:
+            from . import host_scalars
+            return host_scalars.backend(cls.dtype)
+        return _bk.get()
 
     # -- construction --------------------------------------------------------------------------
     def __init__(self, *args, **kwargs):
@@ -233,7 +241,7 @@ class Tensor:
             self._init(names, edges, None)
             if self._table.size != 1:
                 raise RuntimeError("Invalid symmetries for a rank-0-like tensor")
-            self._set_host(np.array([float(number)]))
+            self._set_host(np.array([number]))
             return
         names = kwargs.get("names", args[0] if args else [])
         edges = kwargs.get("edges", args[1] if len(args) > 1 else [])
@@ -263,7 +271,7 @@ class Tensor:
     def data(self):
         """device buffer [nb, size] (allocated uninitialised on first use, like the reference)"""
         if self._data is None:
-            self._data = _bk.get().zeros(1, self._table.size)
+            self._data = self._B().zeros(1, self._table.size)
         return self._data
 
     @property
@@ -271,16 +279,19 @@ class Tensor:
         return self.data.shape[0]
 
     def _host(self):
-        a = _bk.get().to_numpy(self.data)
+        a = self._B().to_numpy(self.data)
         return a[0] if a.shape[0] == 1 else a
 
     def _set_host(self, array):
-        a = np.asarray(array, dtype=np.float64)
+        a = np.asarray(array)
+        if a.dtype.kind == "c" and self._np.kind != "c":
+            a = a.real
+        a = a.astype(self._np)
         if a.ndim == 1:
             a = a.reshape(1, -1)
         if a.shape[1] != self._table.size:
             raise ValueError("storage size mismatch")
-        self._data = _bk.get().from_numpy(a)
+        self._data = self._B().from_numpy(a)
 
     @classmethod
     def from_batch(cls, names, edges, array):
@@ -316,7 +327,7 @@ class Tensor:
     def storage(self, value):
         if isinstance(value, _StorageView):
             value = np.asarray(value)
-        a = np.empty(self._host().shape, dtype=np.float64)
+        a = np.empty(self._host().shape, dtype=self._np)
         a[...] = value
         self._set_host(a)
 
@@ -357,7 +368,9 @@ class Tensor:
 
     def __getitem__(self, position):
         v = self._host()[..., self._flat_index(position)]
-        return float(v) if np.ndim(v) == 0 else v
+        if np.ndim(v) == 0:
+            return complex(v) if self.is_complex else float(v)
+        return v
 
     def __setitem__(self, position, value):
         a = self._host().copy()
@@ -365,12 +378,21 @@ class Tensor:
         self._set_host(a)
 
     def __float__(self):
+        if self._table.size == 0:
+            return 0.0      # no block satisfies the symmetry: the reference converts such a tensor to zero (tensor.hpp:296-310)
         if self._table.size != 1:
             raise RuntimeError("Try to get the only element of the tensor which contains more than one element")
-        return float(self._host().reshape(-1)[0])
+        v = self._host().reshape(-1)[0]
+        if self.is_complex:
+            raise TypeError("can't convert complex to float")
+        return float(v)
 
     def __complex__(self):
-        return complex(float(self))
+        if self._table.size == 0:
+            return 0j
+        if self._table.size != 1:
+            raise RuntimeError("Try to get the only element of the tensor which contains more than one element")
+        return complex(self._host().reshape(-1)[0])
 
     def scalar(self):
         """the single element per chain as a device vector [nb] (batched analogue of float(tensor))"""
@@ -410,30 +432,30 @@ class Tensor:
         return self._make(self.names, self._edges, self._table, None)
 
     def zero_(self):
-        self._data = _bk.get().zeros(self.data.shape[0], self._table.size)
+        self._data = self._B().zeros(self.data.shape[0], self._table.size)
         return self
 
     zero = zero_
 
     def range_(self, first=0, step=1):
         # the reference fills by repeated addition (now += step), not first + i*step
-        inc = np.full(self._table.size, float(step))
+        inc = np.full(self._table.size, step, dtype=self._np if self.is_complex else np.float64)
         if inc.size:
-            inc[0] = float(first)
+            inc[0] = first
         self._set_host(np.cumsum(inc))
         return self
 
     range = range_
 
     def set_(self, function):
-        self._set_host(np.array([function() for _ in range(self._table.size)], dtype=np.float64))
+        self._set_host(np.array([function() for _ in range(self._table.size)], dtype=self._np))
         return self
 
     set = set_
 
     def map(self, function):
         h = np.atleast_2d(self._host())
-        out = np.array([[function(float(x)) for x in row] for row in h], dtype=np.float64)
+        out = np.array([[function(complex(x) if self.is_complex else float(x)) for x in row] for row in h], dtype=self._np)
         r = self.same_shape()
         r._set_host(out)
         return r
@@ -459,22 +481,30 @@ class Tensor:
     rand = rand_
 
     def to(self, new_type):
-        s = str(new_type)
-        if "float64" in s or s in ("D", "float", "<class 'float'>") or "float" in s and "32" not in s:
+        """scalar type conversion (PyTAT.hpp:611-640): a type object (float / complex), a numpy-style name or the one-letter code"""
+        s = new_type if isinstance(new_type, str) else getattr(new_type, "__name__", str(new_type))
+        code = {"float": "D", "float64": "D", "D": "D", "complex": "Z", "complex128": "Z", "Z": "Z", "float32": "S", "S": "S",
+                "complex64": "C", "C": "C"}.get(s)
+        if code is None:
+            raise RuntimeError(f"Invalid scalar type {new_type!r} in Tensor.to")
+        if code == self.btype:
             return self
-        raise NotImplementedError("only float64 tensors are device-backed in this build")
+        target = getattr(self.model, code).Tensor
+        r = target._make(self.names, self._edges, self._table, None)
+        r._set_host(np.atleast_2d(self._host()))
+        return r
 
     def sqrt(self):
-        return self._make(self.names, self._edges, self._table, _bk.get().unary(self.data, 0))
+        return self._make(self.names, self._edges, self._table, self._B().unary(self.data, 0))
 
     def reciprocal(self):
-        return self._make(self.names, self._edges, self._table, _bk.get().unary(self.data, 1))
+        return self._make(self.names, self._edges, self._table, self._B().unary(self.data, 1))
 
     # -- norms ---------------------------------------------------------------------------------
     def _norm(self, kind):
-        r = _bk.get().norm(self.data, kind)
+        r = self._B().norm(self.data, kind)
         if r.shape[0] == 1:
-            return float(_bk.get().to_numpy(r)[0])
+            return float(self._B().to_numpy(r)[0])
         return BatchScalar(r)
 
     def norm_max(self):
@@ -491,10 +521,10 @@ class Tensor:
 
     # -- arithmetic ----------------------------------------------------------------------------
     def _scalar_vec(self, value):
-        B = _bk.get()
+        B = self._B()
         if isinstance(value, BatchScalar):
             return value.t.contiguous()
-        return B.from_numpy(np.array([float(value)], dtype=np.float64))
+        return B.from_numpy(np.array([value], dtype=self._np if (self.is_complex or not isinstance(value, complex)) else np.complex128))
 
     def _aligned(self, other):
         if other.names != self.names:
@@ -504,7 +534,7 @@ class Tensor:
         return other
 
     def _binary(self, other, op, reverse=False):
-        B = _bk.get()
+        B = self._B()
         if isinstance(other, Tensor):
             if other.rank == 0 or self.rank == 0:
                 # rank-0 operand acts as a scalar (scalar.hpp:60-78)
@@ -522,7 +552,7 @@ class Tensor:
         # scalar (+,-) tensor or scalar / tensor: broadcast the scalar to a tensor
         vec = self._scalar_vec(other)
         nb = max(vec.shape[0], self.data.shape[0])
-        ones = B.from_numpy(np.ones((1, self._table.size)))
+        ones = B.from_numpy(np.ones((1, self._table.size), dtype=self._np))
         full = B.scale(ones, vec, 0, nb)
         a, b = (full, self.data) if reverse else (self.data, full)
         return self._make(self.names, self._edges, self._table, B.binary(a, b, op))
@@ -568,7 +598,7 @@ class Tensor:
         return self._inplace(o, 3)
 
     def __neg__(self):
-        return self._make(self.names, self._edges, self._table, _bk.get().unary(self.data, 2))
+        return self._make(self.names, self._edges, self._table, self._B().unary(self.data, 2))
 
     # -- edge operations -----------------------------------------------------------------------
     def edge_rename(self, dictionary):
@@ -579,7 +609,7 @@ class Tensor:
 
     def _run_pack(self, p, src=None):
         """Apply a PackPlan to this tensor's data -> new device buffer."""
-        B = _bk.get()
+        B = self._B()
         src = self.data if src is None else src
         STATS["pack"] += 1
         if p.identity:
@@ -661,7 +691,7 @@ class Tensor:
         other = another_tensor
         if type(other) is not type(self):
             raise TypeError("contract needs two tensors of the same type")
-        B = _bk.get()
+        B = self._B()
         pairs = frozenset((a, b) for a, b in contract_pairs)
         fuse = _fs(fuse_names)
         key = ("ct", type(self), tuple(self.names), self._edges, tuple(other.names), other._edges, pairs, fuse)
@@ -689,8 +719,16 @@ class Tensor:
 
     # -- conjugate -----------------------------------------------------------------------------
     def conjugate(self, trivial_metric=False):
+        if self.is_complex:
+            values = self._B().unary(self.data, 4)
+            if self.Symmetry.length == 0:
+                return self._make(self.names, self._edges, self._table, values)
+            return self._make(self.names, self._edges, self._table, values)._conjugate_structure(trivial_metric)
         if self.Symmetry.length == 0:
             return self._make(self.names, self._edges, self._table, self.data)
+        return self._conjugate_structure(trivial_metric)
+
+    def _conjugate_structure(self, trivial_metric):
         key = ("cj", type(self), self._edges, bool(trivial_metric))
 
         def build():
@@ -701,12 +739,12 @@ class Tensor:
             return edges, block_table(edges), blk, bool(signs.any())
 
         edges, table, blk, any_sign = _cached(key, build)
-        data = _bk.get().block_sign(blk, self.data) if any_sign else self.data
+        data = self._B().block_sign(blk, self.data) if any_sign else self.data
         return self._make(self.names, edges, table, data)
 
     # -- svd / qr ------------------------------------------------------------------------------
     def svd(self, free_names_u, common_name_u, common_name_v, singular_name_u, singular_name_v, cut=-1):
-        B = _bk.get()
+        B = self._B()
         free_u = _fs(free_names_u)
         remain_cut, relative_cut = (1 << 62), 0.0
         if cut > 0:
@@ -759,7 +797,7 @@ class Tensor:
         return u, st, v
 
     def qr(self, free_names_direction, free_names, common_name_q, common_name_r):
-        B = _bk.get()
+        B = self._B()
         free = _fs(free_names)
         key = ("qr", type(self), tuple(self.names), self._edges, free_names_direction, free, common_name_q, common_name_r)
         p = _cached(key, lambda: _plan.qr_plan(self.Edge, tuple(self.names), self._edges, free_names_direction, free, common_name_q,
@@ -816,12 +854,17 @@ class Tensor:
                         if destination[i] > destination[j]:
                             odd ^= bool(syms[i].parity) and bool(syms[j].parity)
                 sign = -1.0 if odd else 1.0
+            if 0 in dims:
+                continue
             blockv = np.zeros(dims)
-            grids = np.indices([dims[i] for i, _ in ordered]).reshape(len(ordered), -1)
-            index = [None] * rank
-            for k, (i, j) in enumerate(ordered):
-                index[i] = index[j] = grids[k]
-            blockv[tuple(index)] = sign
+            if not ordered:
+                blockv[...] = sign          # rank 0: the identity is the number one
+            else:
+                grids = np.indices([dims[i] for i, _ in ordered]).reshape(len(ordered), -1)
+                index = [None] * rank
+                for k, (i, j) in enumerate(ordered):
+                    index[i] = index[j] = grids[k]
+                blockv[tuple(index)] = sign
             off = int(t.offsets[b])
             a[off:off + blockv.size] = blockv.reshape(-1)
         self._set_host(a)
@@ -833,7 +876,7 @@ class Tensor:
     def _not_on_path(self, *a, **k):
         raise NotImplementedError("this Tensor method is outside the sampling-VMC hot path (SURVEY.md section 8)")
 
-    shrink = expand = clear_fermi_symmetry = _not_on_path
+    shrink = expand = _not_on_path
 
     def exponential(self, pairs, step=8):
         """Tensor exponential over paired edges (reference: TAT/include/TAT/implement/exponential.hpp:155-273, PyTAT default
@@ -898,7 +941,21 @@ class Tensor:
         with the identity between the conjugates of the paired edges -- no kernel of its own.  Bosonic symmetries only (the
         fermionic version carries the parity signs of trace.hpp:120-160 and is not needed on the sweep / ergodic path)."""
         if fuse_names:
-            raise NotImplementedError("trace with fuse_names is outside the sampling-VMC hot path")
+            # fuse (trace.hpp:60-118, tensors without symmetry): out[.., x, ..] = in[.., a = x, b = x, ..]; a contraction with the
+            # three-index delta for every fused pair, then the ordinary trace of the remaining pairs
+            if self.Symmetry.length != 0:
+                raise RuntimeError("fuse_names is only supported for tensors without symmetry")
+            result = self
+            for new_name, (n1, n2) in dict(fuse_names).items():
+                d = result.edge_by_name(n1).dimension
+                if result.edge_by_name(n2).dimension != d:
+                    raise RuntimeError("Cannot fuse two edge with different shape")
+                delta = np.zeros((d, d, d))
+                idx = np.arange(d)
+                delta[idx, idx, idx] = 1.0
+                tee = type(self).from_batch(["__fuse_a", "__fuse_b", new_name], [d, d, d], delta.reshape(1, -1))
+                result = tee.contract(result, {("__fuse_a", n1), ("__fuse_b", n2)})
+            return result.trace(trace_pairs) if trace_pairs else result
         pairs = [tuple(p) for p in trace_pairs]
         if not pairs:
             return self.copy()
@@ -1025,17 +1082,57 @@ class Tensor:
         return [np.concatenate([[0], np.cumsum(e.dims)[:-1]]).astype(np.int64) if len(e.dims) else np.zeros(0, np.int64) for e in self._edges]
 
     def clear_symmetry(self):
-        """NoSymmetry tensor with the same names and total dimensions, exact zeros in the forbidden
-        blocks (reference: TAT/include/TAT/implement/clear_symmetry.hpp).  Host-side (set-up only);
-        this is how symmetric PEPS enter the lock-step batch engine."""
+        """NoSymmetry tensor with the same names and total dimensions, exact zeros in the forbidden blocks; a FERMIONIC tensor is
+        converted to the parity-symmetry tensor instead (reference: TAT/include/TAT/implement/clear_symmetry.hpp:30-134, PyTAT
+        `clear_symmetry`).  Host-side (set-up only)."""
         if self.Symmetry.is_fermi_symmetry:
-            raise NotImplementedError("clear_symmetry of fermionic tensors is outside the hot path")
+            return self.clear_fermi_symmetry()
+        return self.clear_bose_symmetry()
+
+    def clear_fermi_symmetry(self):
+        """FermiZ2 tensor: every edge keeps its arrow and gets the segments (even, total even dimension), (odd, total odd dimension);
+        a block lands at the offsets its segments have among the segments of equal parity (clear_symmetry.hpp:69-134)"""
+        if not self.Symmetry.is_fermi_symmetry:
+            raise RuntimeError("It is invalid to call clear fermi symmetry on a bose symmetry tensor")
         from .. import TAT as _tat
-        No = _tat.No.D.Tensor
+        Z2 = getattr(_tat.FermiZ2, self.btype).Tensor
+        edges, offsets = [], []
+        for e in self._edges:
+            dims, offs = [0, 0], []
+            for sym, d in e.segments:
+                p = int(bool(sym.parity))
+                offs.append((p, dims[p]))
+                dims[p] += d
+            edges.append(Z2.Edge([(bool(p), dims[p]) for p in (0, 1) if dims[p]], e.arrow))
+            offsets.append(offs)
+        result = Z2(list(self.names), edges).zero_()
+        h = np.atleast_2d(self._host())
+        nb = h.shape[0]
+        out = np.zeros((nb, result._table.size), dtype=self._np)
+        rt = result._table
+        for b, pos in enumerate(self._table.positions):
+            bd = [int(d) for d in self._table.dims[b]]
+            if 0 in bd:
+                continue
+            par = [offsets[i][int(p)][0] for i, p in enumerate(pos)]
+            start = [offsets[i][int(p)][1] for i, p in enumerate(pos)]
+            rpos = [result._edges[i].find_by_symmetry(result.Symmetry(bool(par[i]))) for i in range(len(pos))]
+            rb = rt.block_by_positions(rpos)
+            rd = [int(d) for d in rt.dims[rb]]
+            view = out[:, int(rt.offsets[rb]):int(rt.offsets[rb]) + int(rt.sizes[rb])].reshape([nb] + rd)
+            sl = (slice(None),) + tuple(slice(start[i], start[i] + bd[i]) for i in range(len(pos)))
+            off, size = int(self._table.offsets[b]), int(self._table.sizes[b])
+            view[sl] = h[:, off:off + size].reshape([nb] + bd)
+        result._set_host(out)
+        return result
+
+    def clear_bose_symmetry(self):
+        from .. import TAT as _tat
+        No = getattr(_tat.No, self.btype).Tensor
         dims = [e.dimension for e in self._edges]
         h = np.atleast_2d(self._host())
         nb = h.shape[0]
-        dense = np.zeros([nb] + dims, dtype=np.float64)
+        dense = np.zeros([nb] + dims, dtype=self._np)
         starts = self._segment_starts()
         for b, pos in enumerate(self._table.positions):
             bd = [int(d) for d in self._table.dims[b]]
@@ -1044,7 +1141,6 @@ class Tensor:
             dense[sl] = h[:, off:off + size].reshape([nb] + bd)
         return No.from_batch(list(self.names), [No.Edge(d) for d in dims], dense.reshape(nb, -1))
 
-    clear_bose_symmetry = clear_symmetry
 
     def fill_from_dense(self, dense):
         """inverse of clear_symmetry: read this tensor's blocks out of a dense array / NoSymmetry tensor

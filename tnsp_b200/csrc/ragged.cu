@@ -76,12 +76,18 @@ __global__ void __launch_bounds__(kSortThreads) rt_sort_kernel(RtEdges E, int M,
         if (dead) key = RT_EMPTY;
         inv[r] = key;
         if (!dead) {
-            int h = rt_hash(key);
-            for (int probe = 0; probe < kHash; ++probe) {
-                const int old = atomicCAS(&hkey[h], RT_EMPTY, key);
-                if (old == RT_EMPTY || old == key) break;
-                h = (h + 1) & (kHash - 1);
-                if (probe == kHash - 1) overflow_s = 1;
+            // one lane per distinct key of the warp inserts it (a group has ~10 distinct charges: without the vote every element
+            // would hammer the same few shared-memory words with atomics)
+            const unsigned peers = __match_any_sync(__activemask(), key);
+            if ((int)(__ffs(peers) - 1) == lane) {
+                int h = rt_hash(key);
+                for (int probe = 0; probe < kHash; ++probe) {
+                    if (hkey[h] == key) break;
+                    const int old = atomicCAS(&hkey[h], RT_EMPTY, key);
+                    if (old == RT_EMPTY || old == key) break;
+                    h = (h + 1) & (kHash - 1);
+                    if (probe == kHash - 1) overflow_s = 1;
+                }
             }
         }
     }
@@ -122,7 +128,13 @@ __global__ void __launch_bounds__(kSortThreads) rt_sort_kernel(RtEdges E, int M,
     int chunk = (M + kSortWarps - 1) / kSortWarps;
     chunk = (chunk + 31) & ~31;
     const int r0 = warp * chunk, r1 = min(M, r0 + chunk);
-    for (int r = r0 + lane; r < r1; r += 32) atomicAdd(&wcnt[warp][sector(inv[r])], 1);
+    for (int rr = r0; rr < r1; rr += 32) {
+        const int r = rr + lane;
+        const int sec = r < r1 ? sector(inv[r]) : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, sec);
+        if (r < r1 && (int)(__ffs(peers) - 1) == lane) wcnt[warp][sec] += __popc(peers);      // the warp owns its row of counters
+        __syncwarp();
+    }
     __syncthreads();
     if (tid <= nsec) {
         int tot = 0;
