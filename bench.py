@@ -116,11 +116,138 @@ def build_fermionic_workload(tat, wl):
 # reference arm: the reference's own C++ TAT (oracle/_ref, LAPACK/BLAS per sector on the CPU) driven by
 # the same-semantics Python drivers, one independent Markov chain per host core
 # ---------------------------------------------------------------------------------------------------
+def _stock_reference_lattice(wl):
+    """the workload built with the reference's OWN modules (TAT = oracle/_ref, tetragono / tetraku = oracle/_ref/site): same model,
+    same PEPS (TAT.random.seed(2333) + randn_ in site order) as `build_workload` builds on this repository's tensors"""
+    import TAT
+    import tetragono as tet
+    L1, L2 = wl["L1"], wl["L2"]
+    model = wl.get("model")
+    if model == "hubbard_ff":
+        from tetraku.models.hubbard.fermi_fermi import abstract_state
+        T = wl["T"]
+        state = tet.AbstractLattice(abstract_state(L1, L2, T, 1.0, wl["U"]))
+        half = T // 2
+        prof = {(0, 0): 2, (1, 0): 1, (-1, 0): 1, (0, 1): 1, (0, -1): 1, (1, -1): 1, (-1, 1): 1} if wl["D"] == 8 else \
+            {(a, b): wl["D"] for a in (-1, 0, 1) for b in (-1, 0, 1)}
+        total = sum(prof.values())
+
+        def charged(Q):
+            return [((Q + a, Q + b), prof[a, b]) for a in (-1, 0, 1) for b in (-1, 0, 1) if prof.get((a, b), 0) > 0]
+
+        per_row = half / L1
+        for l1 in range(L1 - 1):
+            state.virtual_bond[l1, 0, "D"] = charged(int(half * (L1 - l1 - 1) / L1))
+            for l2 in range(1, L2):
+                state.virtual_bond[l1, l2, "D"] = [((0, 0), total)]
+        for l1 in range(L1):
+            for l2 in range(L2 - 1):
+                state.virtual_bond[l1, l2, "R"] = charged(int(per_row * (L2 - l2 - 1) / L2))
+        hopping = None
+    elif model == "tJ":
+        from tetraku.models.tJ import abstract_state
+        T = wl["T"]
+        state = tet.AbstractLattice(abstract_state(L1, L2, T, 1.0, wl["J"]))
+        prof = [1, 1, 1, 1, 2, 1, 1, 1, 1] if wl["D"] == 10 else [wl["D"]] * 9
+        sectors = [(dn, ds) for dn, spins in ((-2, (0,)), (-1, (-1, 1)), (0, (-2, 0, 2)), (1, (-1, 1)), (2, (0,))) for ds in spins]
+
+        def charged(Q):
+            return [((2 * Q + dn, ds), d) for (dn, ds), d in zip(sectors, prof) if d > 0]
+
+        per_row = T / L1
+        for l1 in range(L1 - 1):
+            state.virtual_bond[l1, 0, "D"] = charged(int(T * (L1 - l1 - 1) / L1))
+            for l2 in range(1, L2):
+                state.virtual_bond[l1, l2, "D"] = [((0, 0), sum(prof))]
+        for l1 in range(L1):
+            for l2 in range(L2 - 1):
+                state.virtual_bond[l1, l2, "R"] = charged(int(per_row * (L2 - l2 - 1) / L2))
+        hopping = None
+    elif wl["sym"] == "No":
+        from tetraku.models.heisenberg import abstract_lattice
+        state = abstract_lattice(L1, L2, wl["D"], 1.0)
+        hopping = None
+    else:
+        # J1-J2 with U(1) (2 Sz) tensors: the reference ships this model without symmetry only (SURVEY.md 8d)
+        Tn = TAT.BoseU1.D.Tensor
+        st = tet.AbstractState(Tn, L1, L2)
+        pe, cpe = [(+1, 1), (-1, 1)], [(-1, 1), (+1, 1)]
+        st.physics_edges[...] = pe
+        SS = Tn(["I0", "I1", "O0", "O1"], [cpe, cpe, pe, pe]).zero_()
+        up, dn = (1, 0), (-1, 0)
+        for i0, i1, o0, o1, v in ((up, up, up, up, 0.25), (dn, dn, dn, dn, 0.25), (up, dn, up, dn, -0.25), (dn, up, dn, up, -0.25),
+                                  (up, dn, dn, up, 0.5), (dn, up, up, dn, 0.5)):
+            SS[{"I0": (-i0[0], 0), "I1": (-i1[0], 0), "O0": o0, "O1": o1}] = v
+        H = -1.0 * SS
+        st.hamiltonians["vertical_bond"] = H
+        st.hamiltonians["horizontal_bond"] = H
+        state = tet.AbstractLattice(st)
+        d = wl["D"] // 3
+        state.virtual_bond["R"] = [(-1, d), (0, d), (+1, d)]
+        state.virtual_bond["D"] = [(-1, d), (0, d), (+1, d)]
+        hopping = "nn"
+    TAT.random.seed(2333)
+    lat = tet.SamplingLattice(state)
+    if hopping == "nn":
+        H1 = lat._hamiltonians[((0, 0, 0), (0, 1, 0))]
+        hopping = dict(lat._hamiltonians)
+        if wl.get("J2", 0.0) != 0:
+            H2 = wl["J2"] * H1
+            for l1 in range(L1 - 1):
+                for l2 in range(L2 - 1):
+                    lat.hamiltonians[(l1, l2, 0), (l1 + 1, l2 + 1, 0)] = H2
+                    lat.hamiltonians[(l1, l2 + 1, 0), (l1 + 1, l2, 0)] = H2
+        else:
+            hopping = None
+    return lat, hopping
+
+
+def _stock_reference_worker(args):
+    """ONE independent Markov chain of the UNMODIFIED reference: its C++ TAT (oracle/_ref/TAT*.so), its tetragono / tetraku / lazy
+    (oracle/_ref/site, installed there by `make -C oracle pyref`) and the single-rank mpi4py stand-in.  Nothing of tnsp_b200 is
+    imported in this process."""
+    workload, seed, n_warm, n_samples = args
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["OMP_NUM_THREADS"] = "1"
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    sys.path[:0] = [ref, os.path.join(ref, "site")]
+    import TAT
+    import tetragono as tet
+    wl = dict(WORKLOADS[workload])
+    wl.setdefault("J2", 0.0)
+    lat, hopping = _stock_reference_lattice(wl)
+    TAT.random.seed(seed)
+    s = tet.sampling_lattice.SweepSampling(lat, wl["Dc"], None, hopping)
+    if wl.get("model") in ("hubbard_ff", "tJ"):
+        start = fermionic_start(wl)
+    else:
+        start = np.array([[[(l1 + l2) % 2] for l2 in range(wl["L2"])] for l1 in range(wl["L1"])])
+    for l1 in range(wl["L1"]):
+        for l2 in range(wl["L2"]):
+            s.configuration[l1, l2, 0] = lat.physics_edges[l1, l2, 0].point_by_index(int(start[l1, l2, 0]))
+    obs = tet.sampling_lattice.Observer(lat, enable_energy=True, enable_gradient=True, enable_natural_gradient=wl["sr"])
+    with obs:
+        for _ in range(n_warm):
+            p, c = s()
+            obs(p, c)
+    t0 = time.perf_counter()
+    with obs:
+        for _ in range(n_samples):
+            p, c = s()
+            obs(p, c)
+    g = obs.natural_gradient_by_conjugate_gradient(wl["cg"], 0.0) if wl["sr"] else obs.gradient   # noqa: F841
+    dt = time.perf_counter() - t0
+    return n_samples, dt, obs.energy[0]
+
+
 def _reference_worker(args):
+    """fallback when oracle/_ref/site is absent: the reference's C++ TAT (or, without it, the numpy port) under this repository's
+    drivers -- measured equivalent to the stock path, but not the stock code"""
     workload, seed, n_warm, n_samples, use_ref = args
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     os.environ["OMP_NUM_THREADS"] = "1"
-    wl = WORKLOADS[workload]
+    wl = dict(WORKLOADS[workload])
+    wl.setdefault("J2", 0.0)
     if use_ref:
         from oracle.ref import load_reference_tat
         tat = load_reference_tat()
@@ -151,7 +278,7 @@ def _reference_worker(args):
         for _ in range(n_samples):
             p, c = s()
             obs(p, c)
-    g = obs.natural_gradient_by_conjugate_gradient(wl["cg"], 0.0) if wl["sr"] else obs.gradient
+    g = obs.natural_gradient_by_conjugate_gradient(wl["cg"], 0.0) if wl["sr"] else obs.gradient   # noqa: F841
     dt = time.perf_counter() - t0
     return n_samples, dt, obs.energy[0]
 
@@ -218,9 +345,9 @@ def _plan_flops_worker(args):
 
 def run_reference(workload, steps, warmup, samples_per_step, cores=None, plan_flops=False):
     """returns dict(value, cores, kind, sample, ms_per_step[, plan_flops])"""
-    from oracle.ref import load_reference_tat  # noqa: F401  (checks availability in the parent too)
     import glob
     use_ref = bool(glob.glob(os.path.join(ROOT, "oracle", "_ref", "TAT*.so")))
+    stock = use_ref and os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "site", "tetragono"))
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     per_step = []
@@ -229,39 +356,40 @@ def run_reference(workload, steps, warmup, samples_per_step, cores=None, plan_fl
         if use_ref:
             ok = pool.map(_probe_ref, range(1))[0]
             use_ref = ok
+            stock = stock and ok
         for st in range(warmup + steps):
             t0 = time.perf_counter()
-            res = pool.map(_reference_worker, [(workload, 1000 + 97 * st + c, 1, samples_per_step, use_ref) for c in range(cores)])
+            if stock:
+                res = pool.map(_stock_reference_worker, [(workload, 1000 + 97 * st + c, 1, samples_per_step) for c in range(cores)])
+            else:
+                res = pool.map(_reference_worker, [(workload, 1000 + 97 * st + c, 1, samples_per_step, use_ref) for c in range(cores)])
             wall = time.perf_counter() - t0
             # throughput of the step: every core runs one independent chain (sum of per-chain rates)
             rate = sum(n / dt for n, dt, _ in res)
             if st >= warmup:
                 per_step.append((rate, wall))
         if plan_flops:
-            # a deterministic integer count (fixed seeds): taken from profiles/plan_flops.json when recorded there, else
-            # counted now -- after the timed steps, so that it does not compete with the baseline's workers for the cores
             cache = os.path.join(ROOT, "profiles", "plan_flops.json")
             try:
                 flops = json.load(open(cache)).get(workload)
             except Exception:
                 flops = None
-            if not flops:
-                try:
-                    flops = pool.apply_async(_plan_flops_worker, ((workload,),)).get(timeout=600)
-                    flops["source"] = "counted in this run"
-                except Exception as e:   # the count is a report, never a reason to lose the bench line
-                    flops = {"error": repr(e)}
     value = float(np.mean([r for r, _ in per_step]))
+    how = ("the UNMODIFIED reference: C++ TAT (oracle/_ref) + its own tetragono / tetraku / lazy (oracle/_ref/site), no tnsp_b200 code"
+           if stock else ("reference C++ TAT under this repository's drivers (oracle/_ref/site missing)" if use_ref else "numpy port"))
     return {"value": value, "plan_flops": flops, "unit": "samples/s", "cores": cores, "kind": "reference" if use_ref else "port",
             "sample": f"{samples_per_step} samples per chain x {cores} independent chains (one per host core, 1 BLAS thread each) per step, "
-                      f"{steps} steps, workload {workload}",
+                      f"{steps} steps, workload {workload}; {how}",
             "ms_per_step": float(np.mean([w for _, w in per_step]) * 1e3)}
 
 
 def _probe_ref(_):
+    """does the reference extension load in a child process (libopenblas of the image present)?"""
     try:
-        from oracle.ref import load_reference_tat
-        return load_reference_tat() is not None
+        ref = os.path.join(ROOT, "oracle", "_ref")
+        sys.path.insert(0, ref)
+        import TAT  # noqa: F401
+        return hasattr(TAT, "BoseU1")
     except Exception:
         return False
 
