@@ -517,7 +517,10 @@ def run_own(args):
 
     n_cal = min(148, max(32, nb // 8))
     if sector and wl["sym"].startswith("Fermi"):
-        _ragged.CAP_FACTOR = 3.0          # few chains per GPU: the calibration maxima are noisier, memory is not the limit
+        # few chains per GPU and strongly fluctuating sector sizes (hopping moves charge between the bonds): memory is not the limit
+        # here, so batches up to 148 chains allocate the dense bound of every tensor (no learnt capacities, nothing can overflow)
+        _ragged.CAP_FACTOR = 3.0
+        _ragged.CAP_MIN_CHAINS = 160
     if sector and nb > n_cal and nb >= _ragged.CAP_MIN_CHAINS:
         # buffer capacities of the sector-compact engine are learnt on a small throw-away batch first (TAT/ragged.py)
         from tnsp_b200.tetragono.sampling import calibrate_sector_engine

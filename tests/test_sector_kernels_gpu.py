@@ -67,7 +67,8 @@ def _run(B, case, cut):
     return out
 
 
-@pytest.mark.parametrize("shape", [((5, 3), (4,), 6, 0, 3), ((7, 2, 3), (2, 5), 6, 2, 4), ((40, 3), (90,), 70, 3, 20), ((130,), (9, 11), 37, 0, 50)])
+@pytest.mark.parametrize("shape", [((5, 3), (4,), 6, 0, 3), ((7, 2, 3), (2, 5), 6, 2, 4), ((40, 3), (90,), 70, 3, 20), ((130,), (9, 11), 37, 0, 50),
+                                   ((60, 40), (4,), 5, 1, 3)])      # merged group of 2400 indices: the CTA-wide rt_sort (smaller groups: one warp per chain)
 def test_kernels_equal_specification(shape):
     from oracle.numpy_backend import NumpyBackend
     da, db, dk, dead, cut = shape

@@ -138,19 +138,23 @@ class Edge:
 
 class Form:
     """matrix-of-sectors storage for the grouping rows | cols (tuples of non-unit edge positions)"""
-    __slots__ = ("rows", "cols", "rt", "rs", "ct", "cs", "match", "data", "M", "N")
+    __slots__ = ("rows", "cols", "rt", "rs", "ct", "cs", "match", "data", "M", "N", "_c")
 
     def __init__(self, rows, cols, rt, rs, ct, cs, match, data, M, N):
         self.rows, self.cols, self.rt, self.rs, self.ct, self.cs, self.match, self.data, self.M, self.N = \
             rows, cols, rt, rs, ct, cs, match, data, M, N
+        self._c = None          # ctypes view, built by the backend on first use (backend._form)
 
 
 class Core:
     """edges + data of a tensor, shared by renamed / conjugated views (the reference's refcounted Core, tensor.hpp:129-135)"""
-    __slots__ = ("edges", "nb", "target", "tsign", "forms", "primary", "tables", "fermi")
+    __slots__ = ("edges", "nb", "target", "tsign", "forms", "primary", "tables", "fermi", "dims", "sig", "_gd")
 
     def __init__(self, edges, nb, target, tsign, fermi=0):
         self.edges = tuple(edges)
+        self.dims = tuple([e.dim for e in self.edges])
+        self.sig = (self.dims, tuple([e.harr is not None for e in self.edges]))      # what a plan depends on: dimensions, unit flags
+        self._gd = {}
         self.nb = nb
         self.fermi = fermi                           # mask of the fermionic label components (0: bosonic symmetry)
         self.target, self.tsign = target, tsign      # device int32 [nbt] or None: sum of non-unit labels of a stored element
@@ -160,9 +164,12 @@ class Core:
 
     # ---- group tables ---------------------------------------------------------------------------
     def group_dim(self, ids):
-        m = 1
-        for i in ids:
-            m *= self.edges[i].dim
+        m = self._gd.get(ids)
+        if m is None:
+            m = 1
+            for i in ids:
+                m *= self.dims[i]
+            self._gd[ids] = m
         return m
 
     def table(self, ids):
@@ -216,7 +223,7 @@ class Core:
         M, N = self.group_dim(rows), self.group_dim(cols)
         src = self.forms[self.primary]
         nbd = max(src.data.shape[0], src.match.shape[0], rt.shape[0], ct.shape[0], 1 if self.target is None else self.target.shape[0])
-        ckey = ("form", tuple(e.dim for e in self.edges), src.rows, src.cols, rows, cols)
+        ckey = ("form", self.dims, src.rows, src.cols, rows, cols)
         cap, learning = _cap(ckey, M * N, nbd)
         f = Form(rows, cols, rt, rs, ct, cs, None, B.rt_alloc(nbd, cap), M, N)
         STATS["repack"] += 1
@@ -262,7 +269,7 @@ def _repack_plan(core, src, dst, keep_dim1=False):
     """int32 descriptor of a regrouping: for every edge of the destination row group, then column group (slowest first):
     dimension, 1 if the edge sits in the source's column group, its stride inside that source group.  Edges of dimension 1 are
     dropped unless `keep_dim1` (signed regroupings of fermionic tensors need the parity of every device-labelled edge)"""
-    key = ("rp", tuple(e.dim for e in core.edges), src.rows, src.cols, dst.rows, dst.cols, keep_dim1)
+    key = ("rp", core.dims, src.rows, src.cols, dst.rows, dst.cols, keep_dim1)
     p = _PLANS.get(key)
     if p is None:
         where = {}
@@ -584,18 +591,18 @@ def _split_names(t, pairs_side):
 def _contract(a, b, pairs):
     B = _bk.get()
     STATS["contract"] += 1
-    pairs = list(pairs)
-    key = ("ct", tuple(a.names), tuple(e.dim for e in a.core.edges), tuple(e.unit for e in a.core.edges),
-           tuple(b.names), tuple(e.dim for e in b.core.edges), tuple(e.unit for e in b.core.edges), frozenset(pairs))
+    ca, cb = a.core, b.core
+    key = ("ct", tuple(a.names), ca.sig, tuple(b.names), cb.sig, frozenset(pairs))
     p = _PLANS.get(key)
     if p is None:
+        pairs = list(pairs)
         map12 = dict(pairs)
         if len(map12) != len(pairs) or len({y for _, y in pairs}) != len(pairs):
             raise RuntimeError("Duplicated names in contract pairs")
         for x, y in pairs:
             if x not in a.names or y not in b.names:
                 raise RuntimeError("Missing name in contract")
-        ea, eb = a.core.edges, b.core.edges
+        ea, eb = ca.edges, cb.edges
         ka, kb = [], []
         for i, n in enumerate(a.names):
             if n in map12:
@@ -612,44 +619,42 @@ def _contract(a, b, pairs):
         used_b = set(map12.values())
         fa = [i for i, n in enumerate(a.names) if n not in map12]
         fb = [j for j, n in enumerate(b.names) if n not in used_b]
-        p = _PLANS[key] = (tuple(i for i in fa if not ea[i].unit), tuple(ka), tuple(kb), tuple(j for j in fb if not eb[j].unit),
-                           tuple(fa), tuple(fb), [a.names[i] for i in fa] + [b.names[j] for j in fb])
-    fa_n, ka, kb, fb_n, fa, fb, names = p
+        fa_n, fb_n = tuple(i for i in fa if not ea[i].unit), tuple(j for j in fb if not eb[j].unit)
+        # positions of the result's indexed row / column edges (free edges of a, then of b)
+        rows = tuple(fa.index(i) for i in fa_n)
+        cols = tuple(len(fa) + fb.index(j) for j in fb_n)
+        p = _PLANS[key] = (fa_n, tuple(ka), tuple(kb), fb_n, tuple(fa), tuple(fb), [a.names[i] for i in fa] + [b.names[j] for j in fb], rows, cols)
+    fa_n, ka, kb, fb_n, fa, fb, names, rows, cols = p
     if not fa_n and not fb_n and ka:
         return _dot(a, b, ka, kb, fa, fb, names)
-    A, Bf = a.core.forms.get((fa_n, ka)), b.core.forms.get((kb, fb_n))
-    if A is None and Bf is None and a.core is not b.core:
-        A, job_a, key_a = a.core.form_job(fa_n, ka)
-        Bf, job_b, key_b = b.core.form_job(kb, fb_n)
+    asg, bsg = a.sign, b.sign
+    A, Bf = ca.forms.get((fa_n, ka)), cb.forms.get((kb, fb_n))
+    if A is None and Bf is None and ca is not cb:
+        A, job_a, key_a = ca.form_job(fa_n, ka)
+        Bf, job_b, key_b = cb.form_job(kb, fb_n)
         B.rt_repack_pair(*job_a, *job_b)
         if key_a is not None:
             _learn(key_a, A.match)
         if key_b is not None:
             _learn(key_b, Bf.match)
     else:
-        A = a.core.form(fa_n, ka) if A is None else A
-        Bf = b.core.form(kb, fb_n) if Bf is None else Bf
-    nb = max(a.core.nb, b.core.nb)
+        A = ca.form(fa_n, ka) if A is None else A
+        Bf = cb.form(kb, fb_n) if Bf is None else Bf
     # result core: free edges of a, then of b, with the operands' conjugation signs folded in
-    edges = [a.core.edges[i].flipped(a.sign) for i in fa] + [b.core.edges[j].flipped(b.sign) for j in fb]
-    pos = {}
-    for new, old in enumerate(fa):
-        pos[("a", old)] = new
-    for new, old in enumerate(fb):
-        pos[("b", old)] = new + len(fa)
-    rows = tuple(pos[("a", i)] for i in fa_n)
-    cols = tuple(pos[("b", j)] for j in fb_n)
-    rs, cs = A.rs * a.sign, Bf.cs * b.sign
-    nb = max(nb, A.match.shape[0], Bf.match.shape[0])
+    ea, eb = ca.edges, cb.edges
+    edges = ([ea[i] for i in fa] if asg == 1 else [ea[i].flipped(asg) for i in fa]) + \
+            ([eb[j] for j in fb] if bsg == 1 else [eb[j].flipped(bsg) for j in fb])
+    rs, cs = A.rs * asg, Bf.cs * bsg
+    nb = max(ca.nb, cb.nb, A.match.shape[0], Bf.match.shape[0])
     cap, learning = _cap(key, A.M * Bf.N, nb)
     data = B.rt_alloc(nb, cap)
     C = Form(rows, cols, A.rt, rs, Bf.ct, cs, None, data, A.M, Bf.N)
-    ksign = -(a.sign * A.cs) * (b.sign * Bf.rs)
+    ksign = -(asg * A.cs) * (bsg * Bf.rs)
     # ONE launch: sector pairing of the result (rows of a, columns of b, summed targets) + every sector GEMM of every chain
-    target = B.rt_gemm(A, Bf, C, ksign, nb, (rs, cs, a.core.target, a.core.tsign * a.sign, b.core.target, b.core.tsign * b.sign))
+    target = B.rt_gemm(A, Bf, C, ksign, nb, (rs, cs, ca.target, ca.tsign * asg, cb.target, cb.tsign * bsg))
     if learning:
         _learn(key, C.match)
-    core = Core(edges, nb, target, 1, a.core.fermi | b.core.fermi)
+    core = Core(edges, nb, target, 1, ca.fermi | cb.fermi)
     core.set_primary(C)
     return RTensor(names, core, 1)
 
@@ -688,12 +693,13 @@ def _dot(a, b, ka, kb, fa, fb, names):
     return RTensor(names, core, 1)
 
 
-def _unit_target(t, names):
-    """host int32 [nbL] = -(sum of the effective labels of the unit edges in `names`); None when there is none"""
+def _unit_target(t, ids):
+    """host int32 [nbL] = -(sum of the effective labels of the unit edges at positions `ids`); None when there is none"""
+    edges = t.core.edges
     total = None
-    for n in names:
-        e = t.core.edges[t.names.index(n)]
-        if e.unit:
+    for i in ids:
+        e = edges[i]
+        if e.harr is not None:
             v = -(e.sign * t.sign) * np.asarray(e.harr, dtype=np.int64).reshape(-1)
             total = v if total is None else total + v
     if total is None or not total.any():
@@ -725,8 +731,8 @@ def _factor(t, first_names, kind, name_1, name_2, sing_1, sing_2, cut):
     kdim = min(kdim, remain_cut)
     # target of the first factor: charge carried by the unit edges on its side (zero on the hot path: the R / U side of
     # two_line_to_one_line has no physical edges)
-    u1 = _unit_target(t, [t.names[i] for i in first])
-    u2 = _unit_target(t, [t.names[i] for i in second])
+    u1 = _unit_target(t, first)
+    u2 = _unit_target(t, second)
     if u1 is not None and u2 is not None:
         t1 = B.from_numpy(np.broadcast_to(u1, (nb,)).copy() if u1.shape[0] != nb else u1)
         t1s = 1
@@ -735,7 +741,7 @@ def _factor(t, first_names, kind, name_1, name_2, sing_1, sing_2, cut):
     else:
         t1, t1s = None, 0
     # bond labels + per-sector factorisation, all planned on the device
-    fkey = ("fac", kind, tuple(e.dim for e in core.edges), rows, cols, kdim)
+    fkey = ("fac", kind, core.dims, rows, cols, kdim)
     c1, l1 = _cap(fkey + (1,), F.M * max(kdim, 1), nb)
     c2, l2 = _cap(fkey + (2,), max(kdim, 1) * F.N, nb)
     out = B.rt_factor(kind, F, t.sign, core.target, core.tsign * t.sign, t1, t1s, kdim, remain_cut, relative_cut, nb, (c1, c2))

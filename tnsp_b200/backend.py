@@ -86,7 +86,17 @@ class CudaBackend:
             raise TnspError("tnsp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = lib = _declare_host(ctypes.CDLL(LIB_PATH))
         self.device = torch.device("cuda", torch.cuda.current_device())
-        P = c_vp
+        self._dev_index = self.device.index
+        # allocation prototypes: `proto.new_empty(shape)` skips the dtype / device argument parsing of torch.empty (the lock-step
+        # engine allocates ~30 k buffers per step; the host is the bottleneck of a step)
+        self._pf64 = torch.empty(0, dtype=torch.float64, device=self.device)
+        self._pi32 = torch.empty(0, dtype=torch.int32, device=self.device)
+        self._raw_stream = torch._C._cuda_getCurrentRawStream
+        self._declare_kernels()
+        self._rt_declare()
+
+    def _declare_kernels(self):
+        lib, P = self.lib, c_vp
         lib.tnsp_pack_f64.argtypes = [P, P, c_int, c_i64, P, c_i64, P, c_i64, c_int, P]
         lib.tnsp_pack_tiled_f64.argtypes = [c_i64] * 9 + [c_int, P, c_i64, P, c_i64, c_int, P]
         lib.tnsp_gemm_grouped_f64.argtypes = [P, c_int, P, P, c_i64, P, c_i64, P, c_i64, c_int, P]
@@ -119,7 +129,6 @@ class CudaBackend:
         lib.tnsp_block_sign_f64.argtypes = [P, c_int, P, c_i64, P, c_i64, c_i64, c_int, P]
         lib.tnsp_gather_rows_f64.argtypes = [P, c_i64, P, P, c_i64, c_int, P]
         lib.tnsp_select_f64.argtypes = [P, P, c_i64, P, c_i64, P, c_i64, c_i64, c_int, P]
-        self._rt_declare()
 
     # -- sector-compact lock-step tensors (TAT/ragged.py; csrc/ragged.cu, csrc/factor_sector.cu) ------------------------
     def _rt_declare(self):
@@ -148,6 +157,9 @@ class CudaBackend:
         lib.tnsp_rt_norm_f64.argtypes = [P, c_i64, P, c_i64, c_int, P, c_int, P]
         lib.tnsp_rt_scalar_f64.argtypes = [P, c_i64, P, c_i64, P, c_int, P]
         lib.tnsp_rt_stats.argtypes = [c_int, P, c_int]
+        # rt_factor evaluates these two size formulas on the host (two C calls less per factorisation): they must agree with the library
+        if int(lib.tnsp_rt_factor_ws_ints(7)) != 8 + 6 * RT_SMAX + 7 or int(lib.tnsp_rt_svd_work_doubles(5, 9)) != 5 + 5 * 5 + 5 * 9 + 8:
+            raise TnspError("libtnsp_b200.so: workspace size formulas differ from backend.py (rebuild the library)")
 
     @staticmethod
     def _st(t):
@@ -158,31 +170,48 @@ class CudaBackend:
         """ctypes view of a ragged.Form (or of a dense device array)"""
         if isinstance(f, torch.Tensor):
             return RtForm(f.data_ptr(), self._st(f), None, 0, 0, None, 0, 0, None, 0)
-        d = f.data if data is None else data
+        if data is None:
+            c = f._c                  # a Form's arrays never change once its match table exists: the ctypes view is built once
+            if c is None:
+                d, rt, ct, m = f.data, f.rt, f.ct, f.match
+                c = f._c = RtForm(d.data_ptr(), 0 if d.shape[0] == 1 else d.stride(0), rt.data_ptr(), 0 if rt.shape[0] == 1 else rt.stride(0),
+                                  f.M, ct.data_ptr(), 0 if ct.shape[0] == 1 else ct.stride(0), f.N, m.data_ptr(),
+                                  0 if m.shape[0] == 1 else m.stride(0))
+            return c
+        d = data
         return RtForm(d.data_ptr(), self._st(d), f.rt.data_ptr(), self._st(f.rt), f.M, f.ct.data_ptr(), self._st(f.ct), f.N,
                       f.match.data_ptr(), self._st(f.match))
 
     def rt_alloc(self, nb, size):
-        return torch.empty((nb, max(int(size), 1) + RT_SMAX), dtype=torch.float64, device=self.device)
+        return self._pf64.new_empty((nb, max(int(size), 1) + RT_SMAX))
+
+    _SORT_ARRAYS: dict = {}
 
     def rt_sort(self, edges):
         n = len(edges)
-        nbT = max([int(a.shape[0]) for a, _, _ in edges] + [1])
-        M = 1
-        for _, _, d in edges:
-            M *= int(d)
-        table = torch.empty((nbT, RT_HDR + 2 * M), dtype=torch.int32, device=self.device)
-        ptrs = (c_vp * max(n, 1))(*[a.data_ptr() for a, _, _ in edges])
-        strides = (c_i64 * max(n, 1))(*[self._st(a) for a, _, _ in edges])
-        dims = (ctypes.c_int32 * max(n, 1))(*[int(d) for _, _, d in edges])
-        signs = (ctypes.c_int32 * max(n, 1))(*[int(s) for _, s, _ in edges])
+        nbT, M = 1, 1
+        for a, _, d in edges:
+            if a.shape[0] > nbT:
+                nbT = a.shape[0]
+            M *= d
+        table = self._pi32.new_empty((nbT, RT_HDR + 2 * M))
+        m = n if n > 0 else 1
+        types = self._SORT_ARRAYS.get(m)
+        if types is None:
+            types = self._SORT_ARRAYS[m] = (c_vp * m, c_i64 * m, ctypes.c_int32 * m)
+        ptrs, strides, dims, signs = types[0](), types[1](), types[2](), types[2]()
+        for i, (a, sg, d) in enumerate(edges):
+            ptrs[i] = a.data_ptr()
+            strides[i] = 0 if a.shape[0] == 1 else a.stride(0)
+            dims[i] = d
+            signs[i] = sg
         self._ck(self.lib.tnsp_rt_sort_i32(n, ptrs, strides, dims, signs, M, table.data_ptr(), nbT, self._stream()))
         return table
 
     def rt_match(self, rt, rs, ct, cs, t1, s1, t2, s2, nbm, cap=0):
         nbm = max(int(nbm), rt.shape[0], ct.shape[0], 1 if t1 is None else t1.shape[0], 1 if t2 is None else t2.shape[0])
-        match = torch.empty((nbm, RT_MSTRIDE), dtype=torch.int32, device=self.device)
-        tsum = torch.empty(nbm, dtype=torch.int32, device=self.device) if (t1 is not None or t2 is not None) else None
+        match = self._pi32.new_empty((nbm, RT_MSTRIDE))
+        tsum = self._pi32.new_empty((nbm,)) if (t1 is not None or t2 is not None) else None
         self._ck(self.lib.tnsp_rt_match_i32(rt.data_ptr(), self._st(rt), int(rs), ct.data_ptr(), self._st(ct), int(cs),
                                             None if t1 is None else t1.data_ptr(), 0 if t1 is None or t1.shape[0] == 1 else 1, int(s1),
                                             None if t2 is None else t2.data_ptr(), 0 if t2 is None or t2.shape[0] == 1 else 1, int(s2),
@@ -193,8 +222,9 @@ class CudaBackend:
         """spec = (rs, cs, t1, s1, t2, s2): allocate the match table of form `f` (and the summed target), to be filled by the kernel"""
         rs, cs, t1, s1, t2, s2 = spec
         nbm = max(int(nbm), f.rt.shape[0], f.ct.shape[0], 1 if t1 is None else t1.shape[0], 1 if t2 is None else t2.shape[0])
-        f.match = torch.empty((nbm, RT_MSTRIDE), dtype=torch.int32, device=self.device)
-        tsum = torch.empty(nbm, dtype=torch.int32, device=self.device) if (want_tsum and (t1 is not None or t2 is not None)) else None
+        f.match = self._pi32.new_empty((nbm, RT_MSTRIDE))
+        f._c = None
+        tsum = self._pi32.new_empty((nbm,)) if (want_tsum and (t1 is not None or t2 is not None)) else None
         c = RtMatchSpec(int(rs), int(cs), None if t1 is None else t1.data_ptr(), 0 if t1 is None or t1.shape[0] == 1 else 1, int(s1),
                         None if t2 is None else t2.data_ptr(), 0 if t2 is None or t2.shape[0] == 1 else 1, int(s2),
                         f.match.data_ptr(), self._st(f.match), None if tsum is None else tsum.data_ptr(), int(f.data.shape[1]))
@@ -255,8 +285,8 @@ class CudaBackend:
     def rt_dot(self, plan, src, dst, t1, s1, t2, s2, nb):
         """full contraction of two tensors -> (data [nb, 2 + SMAX], match, summed target or None)"""
         out = self.rt_alloc(nb, 2)
-        match = torch.empty((nb, RT_MSTRIDE), dtype=torch.int32, device=self.device)
-        tsum = torch.empty(nb, dtype=torch.int32, device=self.device) if (t1 is not None or t2 is not None) else None
+        match = self._pi32.new_empty((nb, RT_MSTRIDE))
+        tsum = self._pi32.new_empty((nb,)) if (t1 is not None or t2 is not None) else None
         fs, fd = self._form(src), self._form(dst)
         self._ck(self.lib.tnsp_rt_dot_f64(plan.data_ptr(), ctypes.byref(fs), ctypes.byref(fd), None if t1 is None else t1.data_ptr(),
                                           0 if t1 is None or t1.shape[0] == 1 else 1, int(s1), None if t2 is None else t2.data_ptr(),
@@ -295,13 +325,13 @@ class CudaBackend:
         t1p = None if t1 is None else t1.data_ptr()
         t1st = 0 if t1 is None or t1.shape[0] == 1 else 1
         t1s = int(t1s) if t1 is not None else 0
-        wss = int(lib.tnsp_rt_factor_ws_ints(kfull))
-        ws = torch.empty((nb, wss), dtype=torch.int32, device=self.device)
-        labels = torch.empty((nb, kd), dtype=torch.int32, device=self.device)
+        wss = 8 + 6 * RT_SMAX + kfull          # = tnsp_rt_factor_ws_ints(kfull)
+        ws = self._pi32.new_empty((nb, wss))
+        labels = self._pi32.new_empty((nb, kd))
         code = 0 if kind == "qr" else 2
         self.rt_factor_plan(ff, code, frs, t1p, t1st, t1s, kd, labels, ws, wss, nb)
         if code == 2:
-            work = torch.empty((nb, int(lib.tnsp_rt_svd_work_doubles(F.M, F.N))), dtype=torch.float64, device=self.device)
+            work = self._pf64.new_empty((nb, kfull + F.M * kfull + kfull * F.N + 8))     # = tnsp_rt_svd_work_doubles(M, N)
             self.rt_svd_work(ff, work, ws, wss, nb)
             self.rt_svd_finish(ff, frs, t1p, t1st, t1s, kd, remain_cut, relative_cut, work, labels, ws, wss, nb)
         tab = self.rt_sort([(labels, 1, kd)])
@@ -333,34 +363,34 @@ class CudaBackend:
 
     def rt_scale(self, data, match, vec, op):
         nb = max(data.shape[0], match.shape[0], vec.shape[0])
-        out = torch.empty((nb, data.shape[1]), dtype=torch.float64, device=self.device)
+        out = self._pf64.new_empty((nb, data.shape[1]))
         self._ck(self.lib.tnsp_rt_scale_f64(data.data_ptr(), self._st(data), match.data_ptr(), self._st(match), vec.data_ptr(),
                                             0 if vec.shape[0] == 1 else 1, int(op), out.data_ptr(), out.stride(0), data.shape[1], nb, self._stream()))
         return out
 
     def rt_binary(self, a, b, match, op):
         nb = max(a.shape[0], b.shape[0], match.shape[0])
-        out = torch.empty((nb, a.shape[1]), dtype=torch.float64, device=self.device)
+        out = self._pf64.new_empty((nb, a.shape[1]))
         self._ck(self.lib.tnsp_rt_binary_f64(a.data_ptr(), self._st(a), b.data_ptr(), self._st(b), match.data_ptr(), self._st(match), int(op),
                                              out.data_ptr(), out.stride(0), a.shape[1], nb, self._stream()))
         return out
 
     def rt_norm(self, data, match, kind):
         nb = max(data.shape[0], match.shape[0])
-        out = torch.empty(nb, dtype=torch.float64, device=self.device)
+        out = self._pf64.new_empty((nb,))
         self._ck(self.lib.tnsp_rt_norm_f64(data.data_ptr(), self._st(data), match.data_ptr(), self._st(match), int(kind), out.data_ptr(), nb,
                                            self._stream()))
         return out
 
     def rt_scalar(self, data, match):
         nb = max(data.shape[0], match.shape[0])
-        out = torch.empty(nb, dtype=torch.float64, device=self.device)
+        out = self._pf64.new_empty((nb,))
         self._ck(self.lib.tnsp_rt_scalar_f64(data.data_ptr(), self._st(data), match.data_ptr(), self._st(match), out.data_ptr(), nb, self._stream()))
         return out
 
     # -- buffers ------------------------------------------------------------------------------
     def empty(self, nb, size):
-        return torch.empty((nb, size), dtype=torch.float64, device=self.device)
+        return self._pf64.new_empty((nb, size))
 
     def zeros(self, nb, size):
         return torch.zeros((nb, size), dtype=torch.float64, device=self.device)
@@ -375,7 +405,7 @@ class CudaBackend:
         return torch.from_numpy(np.ascontiguousarray(array)).to(self.device)
 
     def _stream(self):
-        return torch.cuda.current_stream().cuda_stream
+        return self._raw_stream(self._dev_index)
 
     def _ck(self, rc):
         if rc != 0:
@@ -499,7 +529,7 @@ class CudaBackend:
 
     def norm(self, x, kind):
         nb = x.shape[0]
-        out = torch.empty(nb, dtype=torch.float64, device=self.device)
+        out = self._pf64.new_empty((nb,))
         self._ck(self.lib.tnsp_norm_f64(x.data_ptr(), x.stride(0), x.shape[1], kind, out.data_ptr(), nb, self._stream()))
         return out
 

@@ -2122,7 +2122,8 @@ __host__ __device__ inline int64_t rt_ws_stride(int64_t kfull) { return RT_WS_HD
 // one thread per chain: bond layout of the chain + one work item per non-empty sector
 __global__ void __launch_bounds__(128) rt_factor_plan_kernel(RtForm F, int kind, int frs, const int* __restrict__ t1, int t1st, int t1s, int kdim,
                                                              int* __restrict__ labels, int* __restrict__ ws, long long wss, int* qctl,
-                                                             int2* __restrict__ qitems, long long qcap, int nb, unsigned long long* stats) {
+                                                             int2* __restrict__ qitems, long long qcap, int nb, unsigned long long* stats,
+                                                             int mid_cap) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     const RtTab R(F.rt + b * F.rts), C(F.ct + b * F.cts);
@@ -2151,7 +2152,7 @@ __global__ void __launch_bounds__(128) rt_factor_plan_kernel(RtForm F, int kind,
         if (kind == 2) st_bytes += 8ull * ((unsigned long long)m * n + (unsigned long long)m * q + (unsigned long long)q * n + q);
         else { st_bytes += 8ull * (2ull * m * n + (unsigned long long)m * q + (unsigned long long)q * n); st_flops += 4ull * m * n * q; }
         k0 += q;
-        int cls = need > kQSmallDoubles ? 0 : (need > kQMidDoubles ? 1 : 2);
+        int cls = need > kQSmallDoubles ? 0 : (need > mid_cap ? 1 : 2);
         // optional class 3: one WARP per small sector, no block barrier inside the factorisation.  MEASURED SLOWER on cfg2 (B200, 2368
         // chains: QR 1296 x 216 10.5 vs 6.5 ms, SVD 216 x 216 10.0 vs 8.9 ms per launch: a single warp's dependent shuffle chains
         // take longer than the barriers they save, and 48 KiB per sector leave 4 sectors per SM), so it is switched off.
@@ -2767,6 +2768,32 @@ extern "C" int tnsp_svd_sectors_gather_f64(const int64_t* sect, const int64_t* s
 }
 
 // ---- sector-compact entry points (tnsp_b200/TAT/ragged.py) ----
+// launch shapes of the work-queue classes (threads per CTA); TNSP_RT_* environment variables override them for experiments
+static int rt_tune(const char* name, int dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const int x = atoi(v);
+    return (x >= 32 && x <= 1024 && x % 32 == 0) ? x : dflt;
+}
+// capacity of class 2 in doubles (default 55 KiB: 4 CTAs per SM) and the number of such CTAs an SM holds
+static int rt_mid_doubles() {
+    static int v = 0;
+    if (!v) { const char* e = getenv("TNSP_RT_MID_DOUBLES"); v = (e && atoi(e) >= 2560 && atoi(e) <= kQSmallDoubles) ? atoi(e) : kQMidDoubles; }
+    return v;
+}
+static int rt_mid_ctas() { return std::max(1, (int)(227 * 1024 / (rt_mid_doubles() * 8 + 1024))); }
+static int rt_svd_threads(int cls) {
+    static int t[4] = {0, 0, 0, 0};
+    if (!t[0]) { t[0] = kQBigThreads; t[1] = rt_tune("TNSP_RT_SVD_T1", kQSmallThreads); t[2] = rt_tune("TNSP_RT_SVD_T2", kQSmallThreads);
+                 t[3] = rt_tune("TNSP_RT_SVD_T3", kRtTinyThreads); }
+    return t[cls];
+}
+static int rt_qr_threads(int cls) {
+    static int t[4] = {0, 0, 0, 0};
+    if (!t[0]) { t[0] = kQBigThreads; t[1] = rt_tune("TNSP_RT_QR_T1", kQSmallThreads); t[2] = rt_tune("TNSP_RT_QR_T2", kQSmallThreads);
+                 t[3] = rt_tune("TNSP_RT_QR_T3", kRtTinyThreads); }
+    return t[cls];
+}
 static int rt_queue_prepare(int nb, int64_t per_cta_scratch, cudaStream_t st, int64_t& qcap) {
     qcap = (int64_t)nb * RT_SMAX;
     if (!g_qws.qctl && cudaMalloc(&g_qws.qctl, 8 * sizeof(int)) != cudaSuccess) { set_error("sector queue: cudaMalloc"); return 1; }
@@ -2812,7 +2839,7 @@ extern "C" int tnsp_rt_factor_plan(const tnsp_rt_form* f, int kind, int fsign_rs
     if (rt_queue_prepare(nb, rt_scratch_need(f->M, f->N, kind), st, qcap)) return 1;
     cudaMemsetAsync(g_qws.qctl, 0, 8 * sizeof(int), st);
     rt_factor_plan_kernel<<<(nb + 127) / 128, 128, 0, st>>>(to_form(f), kind, fsign_rs, t1, t1_stride, t1s, (int)kdim, labels, ws, ws_stride,
-                                                            g_qws.qctl, g_qws.qitems, qcap, nb, rt_stats_ptr());
+                                                            g_qws.qctl, g_qws.qitems, qcap, nb, rt_stats_ptr(), rt_mid_doubles());
     return check_launch("tnsp_rt_factor_plan");
 }
 
@@ -2837,22 +2864,22 @@ extern "C" int tnsp_rt_qr_f64(const tnsp_rt_form* f, int fsign_rs, const int32_t
                                                                                g_qws.qitems, qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
         if (check_launch("tnsp_rt_qr_f64(big)")) return 1;
     }
-    if (qr_sector_need(f->M, f->N) > kQMidDoubles) {
-        rt_qr_work_kernel<false><<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first,
+    if (qr_sector_need(f->M, f->N) > rt_mid_doubles()) {
+        rt_qr_work_kernel<false><<<3 * kSMs, rt_qr_threads(1), kQSmallDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first,
                                                                                        first, first_stride, m_second, second, second_stride,
                                                                                        g_qws.qctl, g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
         if (check_launch("tnsp_rt_qr_f64(72 KiB class)")) return 1;
     }
     if (!kRtUseWarpClass) {
-        rt_qr_work_kernel<false><<<8 * kSMs, kRtTinyThreads, kRtTinyDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first,
+        rt_qr_work_kernel<false><<<8 * kSMs, rt_qr_threads(3), kRtTinyDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first,
                                                                                        first, first_stride, m_second, second, second_stride,
                                                                                        g_qws.qctl, g_qws.qitems, qcap, 3, kRtTinyDoubles, nullptr, 0);
         if (check_launch("tnsp_rt_qr_f64(tiny class)")) return 1;
         if (qr_sector_need(f->M, f->N) <= kRtTinyDoubles) return 0;
     }
-    rt_qr_work_kernel<false><<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first, first,
-                                                                                 first_stride, m_second, second, second_stride, g_qws.qctl,
-                                                                                 g_qws.qitems, qcap, 2, kQMidDoubles, nullptr, 0);
+    rt_qr_work_kernel<false><<<rt_mid_ctas() * kSMs, rt_qr_threads(2), rt_mid_doubles() * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride,
+                                                                                 m_first, first, first_stride, m_second, second, second_stride,
+                                                                                 g_qws.qctl, g_qws.qitems, qcap, 2, rt_mid_doubles(), nullptr, 0);
     return check_launch("tnsp_rt_qr_f64(55 KiB class)");
 }
 
@@ -2877,19 +2904,19 @@ extern "C" int tnsp_rt_svd_work_f64(const tnsp_rt_form* f, double* work, int64_t
                                                                                 qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
         if (check_launch("tnsp_rt_svd_work_f64(big)")) return 1;
     }
-    if (full > kQMidDoubles) {
-        rt_svd_work_kernel<false><<<3 * kSMs, kQSmallThreads, kQSmallDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
+    if (full > rt_mid_doubles()) {
+        rt_svd_work_kernel<false><<<3 * kSMs, rt_svd_threads(1), kQSmallDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
                                                                                         g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
         if (check_launch("tnsp_rt_svd_work_f64(72 KiB class)")) return 1;
     }
     if (!kRtUseWarpClass) {
-        rt_svd_work_kernel<false><<<8 * kSMs, kRtTinyThreads, kRtTinyDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
+        rt_svd_work_kernel<false><<<8 * kSMs, rt_svd_threads(3), kRtTinyDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
                                                                                         g_qws.qitems, qcap, 3, kRtTinyDoubles, nullptr, 0);
         if (check_launch("tnsp_rt_svd_work_f64(tiny class)")) return 1;
         if (full <= kRtTinyDoubles) return 0;
     }
-    rt_svd_work_kernel<false><<<4 * kSMs, kQSmallThreads, kQMidDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
-                                                                                  g_qws.qitems, qcap, 2, kQMidDoubles, nullptr, 0);
+    rt_svd_work_kernel<false><<<rt_mid_ctas() * kSMs, rt_svd_threads(2), rt_mid_doubles() * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull,
+                                                                                  g_qws.qctl, g_qws.qitems, qcap, 2, rt_mid_doubles(), nullptr, 0);
     return check_launch("tnsp_rt_svd_work_f64(55 KiB class)");
 }
 

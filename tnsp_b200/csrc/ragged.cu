@@ -170,6 +170,95 @@ __global__ void __launch_bounds__(kSortThreads) rt_sort_kernel(RtEdges E, int M,
 }
 
 // ------------------------------------------------------------------------------------------------
+// rt_sort for SMALL groups (merged dimension <= kSortWarpMax: every bond and most two-edge groups of cfg2 -- 6, 36, 216 indices):
+// one WARP per chain, no block barrier, no hash table.  The CTA-wide kernel above pays ~10 us of fixed cost per chain (256-slot hash
+// initialisation, a serial scan of the slots, four barriers) for a handful of indices.  Here the distinct charges are extracted in
+// ascending order by repeated warp-wide minima (<= 64 of them), then the indices are placed chunk by chunk (stable) with one
+// __match_any_sync per 32 indices.  Same table layout, same order as rt_sort_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSortWarpMax = 2048;
+constexpr int kSortWarpPerCta = 4;
+
+__global__ void __launch_bounds__(32 * kSortWarpPerCta) rt_sort_warp_kernel(RtEdges E, int M, int* __restrict__ table, long long tstride, int nbT) {
+    __shared__ int s_keys[kSortWarpPerCta][kSortWarpMax];
+    __shared__ int s_skey[kSortWarpPerCta][RT_SMAX + 1];
+    __shared__ int s_cnt[kSortWarpPerCta][RT_SMAX + 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * kSortWarpPerCta + warp;
+    if (b >= nbT) return;
+    int* keys = s_keys[warp];
+    int* skey = s_skey[warp];
+    int* cnt = s_cnt[warp];
+    int* T = table + (long long)b * tstride;
+    int* perm = T + RT_HDR;
+    int* inv = T + RT_HDR + M;
+    for (int r = lane; r < M; r += 32) {
+        int rest = r, key = 0;
+        bool dead = false;
+        for (int e = E.n - 1; e >= 0; --e) {
+            const int d = E.dim[e];
+            const int i = rest % d;
+            rest /= d;
+            const int l = __ldg(E.lab[e] + (long long)b * E.lstride[e] + i);
+            if (l >= RT_DEAD_MIN || l <= -RT_DEAD_MIN) dead = true;
+            key += E.sign[e] * l;
+        }
+        keys[r] = dead ? RT_EMPTY : key;
+    }
+    __syncwarp();
+    // distinct charges in ascending order with their counts
+    int nsec = 0, acc = 0, overflow = 0;
+    long long last = (long long)INT_MIN;            // valid keys are > RT_EMPTY = INT_MIN
+    while (true) {
+        int mn = INT_MAX, have = 0;
+        for (int r = lane; r < M; r += 32) {
+            const int k = keys[r];
+            if ((long long)k > last) { if (!have || k < mn) mn = k; have = 1; }
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, have);
+        if (!any) break;
+        mn = __reduce_min_sync(0xffffffffu, have ? mn : INT_MAX);
+        int c = 0;
+        for (int r = lane; r < M; r += 32) c += keys[r] == mn;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (nsec >= RT_SMAX) { overflow = 1; break; }
+        if (lane == 0) { skey[nsec] = mn; cnt[nsec] = acc; T[2 + nsec] = mn; T[2 + RT_SMAX + nsec] = acc; }
+        acc += c;
+        ++nsec;
+        last = mn;
+    }
+    if (lane == 0) {
+        cnt[nsec] = acc;                      // dead indices go behind the valid ones
+        T[0] = overflow ? -1 : nsec;
+        T[1] = acc;
+        T[2 + RT_SMAX + nsec] = acc;
+    }
+    __syncwarp();
+    for (int r0 = 0; r0 < M; r0 += 32) {
+        const int r = r0 + lane;
+        const bool on = r < M;
+        int sec = -1 - lane;                  // idle lanes never share a group
+        if (on) {
+            const int k = keys[r];
+            sec = nsec;
+            if (k != RT_EMPTY) {
+                int lo = 0, hi = nsec;            // skey[lo] <= k < skey[hi]
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (skey[mid] <= k) lo = mid; else hi = mid; }
+                sec = (nsec > 0 && skey[lo] == k) ? lo : nsec;      // (after an overflow the surplus charges are parked with the dead ones)
+            }
+        }
+        const unsigned mask = __match_any_sync(0xffffffffu, sec);
+        const int rank = __popc(mask & ((1u << lane) - 1u));
+        int pos = 0;
+        if (on) pos = cnt[sec] + rank;
+        __syncwarp();
+        if (on && rank == 0) cnt[sec] += __popc(mask);
+        __syncwarp();
+        if (on) { perm[pos] = r; inv[r] = pos; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // rt_match: one warp per chain
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) rt_match_kernel(const int* __restrict__ rt, long long rts, int rs, const int* __restrict__ ct, long long cts,
@@ -945,7 +1034,11 @@ extern "C" int tnsp_rt_sort_i32(int n_edges, const int32_t* const* labels, const
     E.n = n_edges;
     for (int i = 0; i < n_edges; ++i) { E.lab[i] = labels[i]; E.lstride[i] = lstrides[i]; E.dim[i] = dims[i]; E.sign[i] = signs[i]; }
     if (nbT == 0) return 0;
-    rt_sort_kernel<<<nbT, kSortThreads, 0, (cudaStream_t)stream>>>(E, (int)M, table, RT_HDR + 2 * M);
+    if (M <= kSortWarpMax)
+        rt_sort_warp_kernel<<<(nbT + kSortWarpPerCta - 1) / kSortWarpPerCta, 32 * kSortWarpPerCta, 0, (cudaStream_t)stream>>>(E, (int)M, table,
+                                                                                                                    RT_HDR + 2 * M, nbT);
+    else
+        rt_sort_kernel<<<nbT, kSortThreads, 0, (cudaStream_t)stream>>>(E, (int)M, table, RT_HDR + 2 * M);
     return check_launch("tnsp_rt_sort_i32");
 }
 

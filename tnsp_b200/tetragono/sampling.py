@@ -77,12 +77,26 @@ class _GlobalRng:
         return np.array([_random.uniform_real(0, 1)()])
 
 
+_CAPACITY_BUMPS = {"n": 0, "dropped": 0}
+
+
 def _check_capacity():
-    """sector-compact engine: a chain whose sectors outgrew a learnt buffer capacity was stored empty (TAT/ragged.py) -- fail loudly"""
-    dropped = _bk.get().rt_overflow()
+    """sector-compact engine: a chain whose sectors outgrew a learnt buffer capacity was stored empty (TAT/ragged.py), i.e. it carried
+    amplitude zero through this sweep (its proposals were rejected / its sample has weight zero).  Loud, and self-correcting: the
+    capacities grow by half for everything allocated from now on; after three such corrections the run stops."""
+    from ..TAT import ragged
+    B = _bk.get()
+    dropped = B.rt_overflow()
     if dropped:
-        raise RuntimeError(f"sector-compact engine: {dropped} (chain, tensor) pairs exceeded their learnt capacity; raise "
-                           "tnsp_b200.TAT.ragged.CAP_FACTOR (now %g) or set CAPS_ENABLED = False" % __import__("tnsp_b200.TAT.ragged", fromlist=["x"]).CAP_FACTOR)
+        _CAPACITY_BUMPS["n"] += 1
+        _CAPACITY_BUMPS["dropped"] += int(dropped)
+        if _CAPACITY_BUMPS["n"] > 3:
+            raise RuntimeError(f"sector-compact engine: {dropped} (chain, tensor) pairs exceeded their learnt capacity again after three "
+                               "corrections; raise tnsp_b200.TAT.ragged.CAP_FACTOR (now %g) or set CAPS_ENABLED = False" % ragged.CAP_FACTOR)
+        import warnings
+        ragged.CAP_FACTOR *= 1.5
+        warnings.warn(f"sector-compact engine: {dropped} (chain, tensor) pairs exceeded their learnt capacity in this sweep (stored empty: "
+                      f"amplitude zero); CAP_FACTOR raised to {ragged.CAP_FACTOR:g}", RuntimeWarning)
 
 
 def _amplitude_values(ws):
