@@ -681,6 +681,25 @@ def run_own(args):
     return out
 
 
+def run_secondary(workloads=("cfg1", "cfg3s", "cfg4s"), steps=2, warmup=3):
+    """short runs of the other BASELINE configurations (cfg1 at its full size; the fermionic cfg3 / cfg4 at their 4x4 smoke sizes --
+    their full sizes are `--workload cfg3 | cfg4`, minutes per run), each in a fresh process: same metric, device-timed value and
+    end-to-end value through host buffers.  Reported beside the headline line, never mixed into it."""
+    out = {}
+    for w in workloads:
+        t0 = time.perf_counter()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", w, "--steps", str(steps), "--warmup", str(warmup),
+                                "--no-cpu-baseline", "--no-secondary"], capture_output=True, text=True, timeout=600)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            out[w] = {"workload": d["config"]["workload"], "chains_per_gpu": d["config"]["chains_per_gpu"], "value": d["value"], "unit": d["unit"],
+                      "e2e": d["e2e"]["value"], "ms_per_step": d["ms_per_step"], "gpu_launches": d["gpu_launches"],
+                      "energy_per_site": d["energy_per_site"], "wall_s": time.perf_counter() - t0}
+        except Exception as e:       # a report, never a reason to lose the headline line
+            out[w] = {"error": repr(e)[:200]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -693,6 +712,7 @@ def main():
     ap.add_argument("--engine", default="sector", choices=["sector", "dense"],
                     help="lock-step engine of symmetric models: sector-compact tensors (default) or the charge-dense embedding of round 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short runs of the other BASELINE configurations (`secondary` key)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
 
@@ -730,6 +750,8 @@ def main():
                     rf["frac_sector_plan"] = rf["frac"] * ratio
         else:
             out["cpu_baseline"] = None
+        if args.workload == "cfg2" and not args.no_secondary and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            out["secondary"] = run_secondary()
         print(json.dumps(out))
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist

@@ -183,7 +183,8 @@ class CudaBackend:
                       f.match.data_ptr(), self._st(f.match))
 
     def rt_alloc(self, nb, size):
-        return self._pf64.new_empty((nb, max(int(size), 1) + RT_SMAX))
+        # even row length: every chain's storage starts 16-byte aligned (the GEMM brings whole B operands in by TMA bulk copies)
+        return self._pf64.new_empty((nb, ((max(int(size), 1) + 1) & ~1) + RT_SMAX))
 
     _SORT_ARRAYS: dict = {}
 

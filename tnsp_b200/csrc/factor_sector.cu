@@ -2784,13 +2784,13 @@ static int rt_mid_doubles() {
 static int rt_mid_ctas() { return std::max(1, (int)(227 * 1024 / (rt_mid_doubles() * 8 + 1024))); }
 static int rt_svd_threads(int cls) {
     static int t[4] = {0, 0, 0, 0};
-    if (!t[0]) { t[0] = kQBigThreads; t[1] = rt_tune("TNSP_RT_SVD_T1", kQSmallThreads); t[2] = rt_tune("TNSP_RT_SVD_T2", kQSmallThreads);
+    if (!t[0]) { t[0] = rt_tune("TNSP_RT_SVD_T0", kQBigThreads); t[1] = rt_tune("TNSP_RT_SVD_T1", kQSmallThreads); t[2] = rt_tune("TNSP_RT_SVD_T2", kQSmallThreads);
                  t[3] = rt_tune("TNSP_RT_SVD_T3", kRtTinyThreads); }
     return t[cls];
 }
 static int rt_qr_threads(int cls) {
     static int t[4] = {0, 0, 0, 0};
-    if (!t[0]) { t[0] = kQBigThreads; t[1] = rt_tune("TNSP_RT_QR_T1", kQSmallThreads); t[2] = rt_tune("TNSP_RT_QR_T2", kQSmallThreads);
+    if (!t[0]) { t[0] = rt_tune("TNSP_RT_QR_T0", kQBigThreads); t[1] = rt_tune("TNSP_RT_QR_T1", kQSmallThreads); t[2] = rt_tune("TNSP_RT_QR_T2", kQSmallThreads);
                  t[3] = rt_tune("TNSP_RT_QR_T3", kRtTinyThreads); }
     return t[cls];
 }
@@ -2859,7 +2859,7 @@ extern "C" int tnsp_rt_qr_f64(const tnsp_rt_form* f, int fsign_rs, const int32_t
         if (rt_qr_warp_need(f->M, f->N, f->M < f->N ? f->M : f->N) <= kRtQrWarpDoubles) return 0;     // nothing can be larger
     }
     if (qr_sector_need(f->M, f->N) > kQSmallDoubles) {
-        rt_qr_work_kernel<true><<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first, first,
+        rt_qr_work_kernel<true><<<kSMs, rt_qr_threads(0), kQBigDoubles * 8, st>>>(F, fsign_rs, t1, t1_stride, t1s, bond, bond_stride, m_first, first,
                                                                                first_stride, m_second, second, second_stride, g_qws.qctl,
                                                                                g_qws.qitems, qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
         if (check_launch("tnsp_rt_qr_f64(big)")) return 1;
@@ -2900,7 +2900,7 @@ extern "C" int tnsp_rt_svd_work_f64(const tnsp_rt_form* f, double* work, int64_t
         if (q <= kWarpSectorMax && rt_svd_warp_need(p, q) <= kRtSvdWarpDoubles) return 0;
     }
     if (full > kQSmallDoubles) {
-        rt_svd_work_kernel<true><<<kSMs, kQBigThreads, kQBigDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl, g_qws.qitems,
+        rt_svd_work_kernel<true><<<kSMs, rt_svd_threads(0), kQBigDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl, g_qws.qitems,
                                                                                 qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
         if (check_launch("tnsp_rt_svd_work_f64(big)")) return 1;
     }

@@ -19,6 +19,7 @@
 #include "ragged.cuh"
 #include <climits>
 #include <cstdint>
+#include <cstdlib>
 
 namespace tnsp {
 
@@ -455,10 +456,12 @@ __global__ void __launch_bounds__(kRepackThreads) rt_repack_pair_kernel(RtRepack
 // destination sector, decodes every row and every column of the tile once (RTR + RTC index decodes into shared memory instead of
 // RTR x RTC) and then moves the elements with two additions, two table look-ups and one sector search each.
 // ------------------------------------------------------------------------------------------------
+constexpr int kRepackTileThreads = 128;      // default CTA sizes of the tile kernels (see repack_threads)
+constexpr int kRepackPairThreads = 64;
 constexpr int RTR = 128, RTC = 128;      // largest tile extents; the tile shape is chosen per sector: tc = 2^ceil(log2 n) <= 128, tr = 2048 / tc <= 128
 struct RtTileDesc { int m, n, tn, start, rstart, cstart, moff, tr, tc; };
 
-template <bool SIGNED>
+template <bool SIGNED, int NT>
 __device__ __forceinline__ void rt_repack_tiles(const int* __restrict__ plan, const RtForm& S, const RtForm& D, const RtSpec& spec,
                                                 double* __restrict__ dst, long long dst_stride, unsigned long long* stats, const RtSign* sgp) {
     __shared__ unsigned s_fr[SIGNED ? RTR : 1], s_mr[SIGNED ? RTR : 1], s_fc[SIGNED ? RTC : 1], s_bc[SIGNED ? RTC : 1];
@@ -471,17 +474,17 @@ __device__ __forceinline__ void rt_repack_tiles(const int* __restrict__ plan, co
     __shared__ unsigned rsr[RTR], rsc[RTR], csr[RTC], csc[RTC];
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_ent = plan[0] + plan[1];
-    for (int i = tid; i < 2 + kPlanEnt * n_ent; i += kRepackThreads) sp[i] = plan[i];
+    for (int i = tid; i < 2 + kPlanEnt * n_ent; i += NT) sp[i] = plan[i];
     __shared__ int hD[2][RT_HDR];
     const int* gDr = D.rt + b * D.rts;
     const int* gDc = D.ct + b * D.cts;
-    for (int i = tid; i < RT_HDR; i += kRepackThreads) {
+    for (int i = tid; i < RT_HDR; i += NT) {
         hS[0][i] = S.rt[b * S.rts + i]; hS[1][i] = S.ct[b * S.cts + i];
         hD[0][i] = gDr[i]; hD[1][i] = gDc[i];
     }
-    for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mS[i] = S.match[b * S.mts + i];
+    for (int i = tid; i < RT_MSTRIDE; i += NT) mS[i] = S.match[b * S.mts + i];
     if (!spec.on)
-        for (int i = tid; i < RT_MSTRIDE; i += kRepackThreads) mD[i] = D.match[b * D.mts + i];
+        for (int i = tid; i < RT_MSTRIDE; i += NT) mD[i] = D.match[b * D.mts + i];
     __syncthreads();
     if (spec.on) rt_match_cta(hD[0], hD[1], spec, b, mD, blockIdx.x == 0);
     {
@@ -547,30 +550,37 @@ __device__ __forceinline__ void rt_repack_tiles(const int* __restrict__ plan, co
         const int r0 = (t / e.tn) * e.tr, c0 = (t % e.tn) * e.tc;
         const int rows = min(e.tr, e.m - r0), cols = min(e.tc, e.n - c0);
         __syncthreads();        // the previous tile's contributions are no longer read
-        if (tid < rows) {
-            unsigned x = 0, y = 0;
-            if (SIGNED) {
-                const unsigned bits = rt_decode_bits(sp, 0, nr, (unsigned)d_perm_r[e.rstart + r0 + tid], x, y, *sgp, b);
-                // f_r = lin . bits + quadratic part inside the row group; m_r = rows of Q selected by the bits (for the cross term)
-                unsigned f = __popc(bits & lin) & 1u, mk = 0;
-                for (int k = 0; k < nr; ++k)
-                    if ((bits >> k) & 1u) { f ^= __popc(bits & (unsigned)s_quad[k]) & 1u; mk ^= (unsigned)s_quad[k]; }
-                s_fr[tid] = f; s_mr[tid] = mk;
-            } else rt_decode(sp, 0, nr, (unsigned)d_perm_r[e.rstart + r0 + tid], x, y);
-            rsr[tid] = x; rsc[tid] = y;
-        } else if (tid >= 128 && tid - 128 < cols) {
-            unsigned x = 0, y = 0;
-            if (SIGNED) {
-                const unsigned bits = rt_decode_bits(sp, nr, nr + nc, (unsigned)d_perm_c[e.cstart + c0 + tid - 128], x, y, *sgp, b);
-                unsigned f = __popc(bits & lin) & 1u;
-                for (int k = nr; k < nr + nc; ++k)
-                    if ((bits >> k) & 1u) f ^= __popc(bits & (unsigned)s_quad[k]) & 1u;
-                s_fc[tid - 128] = f; s_bc[tid - 128] = bits;
-            } else rt_decode(sp, nr, nr + nc, (unsigned)d_perm_c[e.cstart + c0 + tid - 128], x, y);
-            csr[tid - 128] = x; csc[tid - 128] = y;
+        for (int x_ = tid; x_ < rows + cols; x_ += NT) {
+            if (x_ < rows) {
+                const int rr = x_;
+                unsigned x = 0, y = 0;
+                if (SIGNED) {
+                    const unsigned bits = rt_decode_bits(sp, 0, nr, (unsigned)d_perm_r[e.rstart + r0 + rr], x, y, *sgp, b);
+                    // f_r = lin . bits + quadratic part inside the row group; m_r = rows of Q selected by the bits (for the cross term)
+                    unsigned f = __popc(bits & lin) & 1u, mk = 0;
+                    for (int k = 0; k < nr; ++k)
+                        if ((bits >> k) & 1u) { f ^= __popc(bits & (unsigned)s_quad[k]) & 1u; mk ^= (unsigned)s_quad[k]; }
+                    s_fr[rr] = f; s_mr[rr] = mk;
+                } else rt_decode(sp, 0, nr, (unsigned)d_perm_r[e.rstart + r0 + rr], x, y);
+                rsr[rr] = x; rsc[rr] = y;
+            } else {
+                const int cc_ = x_ - rows;
+                unsigned x = 0, y = 0;
+                if (SIGNED) {
+                    const unsigned bits = rt_decode_bits(sp, nr, nr + nc, (unsigned)d_perm_c[e.cstart + c0 + cc_], x, y, *sgp, b);
+                    unsigned f = __popc(bits & lin) & 1u;
+                    for (int k = nr; k < nr + nc; ++k)
+                        if ((bits >> k) & 1u) f ^= __popc(bits & (unsigned)s_quad[k]) & 1u;
+                    s_fc[cc_] = f; s_bc[cc_] = bits;
+                } else rt_decode(sp, nr, nr + nc, (unsigned)d_perm_c[e.cstart + c0 + cc_], x, y);
+                csr[cc_] = x; csc[cc_] = y;
+            }
         }
         __syncthreads();
-        for (int el = tid; el < rows * cols; el += kRepackThreads) {
+        // (a variant that kept four elements per thread in flight -- index look-ups, sector search, data loads and stores in phases --
+        // measured SLOWER on cfg2: 54 instead of 40 registers cost two of six resident CTAs, and with ~1.7 k stored elements per
+        // chain and regrouping the CTA count in flight, not the loads per thread, is what hides the latency)
+        for (int el = tid; el < rows * cols; el += NT) {
             const int a = el / cols, c = el - a * cols;
             const int p = s_inv_r[rsr[a] + csr[c]], q = s_inv_c[rsc[a] + csc[c]];
             double v = 0.0;
@@ -590,16 +600,19 @@ __device__ __forceinline__ void rt_repack_tiles(const int* __restrict__ plan, co
     }
 }
 
-__global__ void __launch_bounds__(kRepackThreads) rt_repack_tile_kernel(RtRepackArgs p, unsigned long long* stats) {
-    rt_repack_tiles<false>(p.plan, p.S, p.D, p.spec, p.dst, p.dst_stride, stats, nullptr);
+template <int NT>
+__global__ void __launch_bounds__(NT) rt_repack_tile_kernel(RtRepackArgs p, unsigned long long* stats) {
+    rt_repack_tiles<false, NT>(p.plan, p.S, p.D, p.spec, p.dst, p.dst_stride, stats, nullptr);
 }
-__global__ void __launch_bounds__(kRepackThreads) rt_repack_tile_pair_kernel(RtRepackPair p, unsigned long long* stats) {
+template <int NT>
+__global__ void __launch_bounds__(NT) rt_repack_tile_pair_kernel(RtRepackPair p, unsigned long long* stats) {
     const RtRepackArgs& q = p.a[blockIdx.z];
-    rt_repack_tiles<false>(q.plan, q.S, q.D, q.spec, q.dst, q.dst_stride, stats, nullptr);
+    rt_repack_tiles<false, NT>(q.plan, q.S, q.D, q.spec, q.dst, q.dst_stride, stats, nullptr);
 }
 // the same regrouping with the fermionic sign of every element (edge_operator.hpp:497-555, 591, 612 evaluated per element)
-__global__ void __launch_bounds__(kRepackThreads) rt_repack_signed_kernel(RtRepackArgs p, RtSign sg, unsigned long long* stats) {
-    rt_repack_tiles<true>(p.plan, p.S, p.D, p.spec, p.dst, p.dst_stride, stats, &sg);
+template <int NT>
+__global__ void __launch_bounds__(NT) rt_repack_signed_kernel(RtRepackArgs p, RtSign sg, unsigned long long* stats) {
+    rt_repack_tiles<true, NT>(p.plan, p.S, p.D, p.spec, p.dst, p.dst_stride, stats, &sg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -824,14 +837,15 @@ __global__ void __launch_bounds__(128) rt_gemm_kernel(RtForm A, RtForm B, RtForm
 // once, nothing else is touched (the tiled kernel above spent its time on header copies, zero-padded shared-memory tiles and two
 // barriers per tile: 3 CTAs / SM, 0.25 TFLOP/s on cfg2).
 // ------------------------------------------------------------------------------------------------
+constexpr int kGemmDefault = 18;   // TNSP_RT_GEMM default (see tnsp_rt_gemm_f64)
 constexpr int WR = 16;          // rows per warp item
 constexpr int WC = 32;          // columns per warp item (4 DMMA fragments)
-constexpr int kGemmWarps = 8;
 
 // per-sector descriptor built once per CTA in shared memory: the warps then find their items without touching the tables again
 struct RtGemmDesc { int m, n, k, tn, start; long long aoff, boff, coff; };
 
-__global__ void __launch_bounds__(kGemmWarps * 32, 4) rt_gemm_warp_kernel(RtForm A, RtForm B, RtForm C, RtSpec spec, double* __restrict__ cdata,
+template <int kGemmWarps>
+__global__ void __launch_bounds__(kGemmWarps * 32, 32 / kGemmWarps) rt_gemm_warp_kernel(RtForm A, RtForm B, RtForm C, RtSpec spec, double* __restrict__ cdata,
                                                                           long long cstride, int ksign, unsigned long long* stats) {
     __shared__ int mC[RT_MSTRIDE];
     __shared__ RtGemmDesc dsc[RT_SMAX];
@@ -960,6 +974,215 @@ __global__ void __launch_bounds__(kGemmWarps * 32, 4) rt_gemm_warp_kernel(RtForm
 }
 
 // ------------------------------------------------------------------------------------------------
+// rt_gemm, second generation of the small-sector kernel (the default): same work decomposition (one warp per 16 x 32 piece of one
+// sector), two changes aimed at what ncu showed for the first one (a latency chain per item: one exposed global-memory round trip
+// per k-step, 32 warps per SM, 10 % issue utilisation):
+//   * B operand by TMA: the chain's whole B storage (all its sectors, back to back, even offsets) is brought into shared memory by
+//     ONE bulk copy per CTA (cp.async.bulk + mbarrier, issued by one thread before the sector pairing is computed, so that it
+//     overlaps the rest of the prologue); every B fragment then comes from shared memory instead of 4 L1 requests per k-step.
+//     Falls back to global loads when the storage exceeds the buffer (cfg2: only the 216 x 216 operands) or is not 16-byte aligned;
+//   * A operand software-pipelined ACROSS items: while a warp multiplies its current piece, the first 16 k of its NEXT piece are
+//     already in flight (two pieces per warp in the memory system instead of one serialised k-loop; most cfg2 sectors have k <= 16).
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned rt_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+struct RtGemmItem { int k, n, cols, rows0, rows1; long long aoff, coff; int boff, r0, c0, m, first; };
+
+template <int kGemm2Warps, bool PREFETCH, int kGemmBsmem, int MINB>
+__global__ void __launch_bounds__(kGemm2Warps * 32, MINB) rt_gemm_warp2_kernel(RtForm A, RtForm B, RtForm C, RtSpec spec, double* __restrict__ cdata,
+                                                                            long long cstride, int ksign, unsigned long long* stats) {
+    __shared__ __align__(16) double Bs[kGemmBsmem];
+    __shared__ __align__(8) unsigned long long bbar;
+    __shared__ int mC[RT_MSTRIDE];
+    __shared__ RtGemmDesc dsc[RT_SMAX];
+    __shared__ int n_desc, n_items;
+    __shared__ int hh[4][RT_HDR];
+    __shared__ int mAB[2][RT_MSTRIDE];
+    constexpr int NT = kGemm2Warps * 32;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* bb = B.data + (long long)b * B.dstride;
+    {
+        const int* src[4] = {A.rt + b * A.rts, A.ct + b * A.cts, B.rt + b * B.rts, B.ct + b * B.cts};
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            for (int i = tid; i < RT_HDR; i += NT) hh[t][i] = src[t][i];
+        for (int i = tid; i < RT_MSTRIDE; i += NT) { mAB[0][i] = A.match[b * A.mts + i]; mAB[1][i] = B.match[b * B.mts + i]; }
+        if (!spec.on)
+            for (int i = tid; i < RT_MSTRIDE; i += NT) mC[i] = C.match[b * C.mts + i];
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(rt_smem_addr(&bbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+    }
+    // B storage of this chain -> shared memory, one bulk copy (size = stored elements: every sector padded to an even count)
+    const int bsize = mAB[1][0];
+    const bool b_smem = bsize > 0 && bsize <= kGemmBsmem && ((reinterpret_cast<unsigned long long>(bb) & 15ull) == 0);
+    if (b_smem && tid == 0) {
+        const unsigned bytes = (unsigned)bsize * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(rt_smem_addr(&bbar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(rt_smem_addr(Bs)), "l"(bb),
+                     "r"(bytes), "r"(rt_smem_addr(&bbar))
+                     : "memory");
+    }
+    if (spec.on) rt_match_cta(hh[0], hh[3], spec, b, mC, blockIdx.x == 0);
+    {
+        const RtTab aR(hh[0]), aK(hh[1]), bK(hh[2]), bN(hh[3]);
+        const RtMatch MA(mAB[0]), MB(mAB[1]), MC(mC);
+        const int nsec = max(aR.nsec(), 0);
+        int here = 0;
+        RtGemmDesc d;
+        d.m = d.n = d.k = d.tn = d.start = 0; d.aoff = d.boff = d.coff = 0;
+        if (tid < nsec) {
+            const int i = tid;
+            const int jc = MC.mcol(i);
+            if (jc >= 0) {
+                d.m = aR.count(i); d.n = bN.count(jc);
+                if (d.m > 0 && d.n > 0) {
+                    d.tn = (d.n + WC - 1) / WC;
+                    here = ((d.m + WR - 1) / WR) * d.tn;
+                    d.coff = MC.moff(i);
+                    const int jk = MA.mcol(i);
+                    if (jk >= 0) {
+                        const int ib = bK.find(ksign * aK.skey(jk));
+                        if (ib >= 0 && MB.mcol(ib) == jc) {
+                            d.k = min(aK.count(jk), bK.count(ib));
+                            d.aoff = MA.moff(i);
+                            d.boff = MB.moff(ib);
+                        }
+                    }
+                }
+            }
+        }
+        __shared__ int cnt[2], tot[2];
+        const unsigned has = __ballot_sync(0xffffffffu, here > 0);
+        int incl = here;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (warp < 2 && lane == 31) { cnt[warp] = __popc(has); tot[warp] = incl; }
+        __syncthreads();
+        if (warp < 2 && here > 0) {
+            const int slot = (warp ? cnt[0] : 0) + __popc(has & ((1u << lane) - 1u));
+            d.start = (warp ? tot[0] : 0) + incl - here;
+            dsc[slot] = d;
+        }
+        if (tid == 0) { n_desc = cnt[0] + cnt[1]; n_items = tot[0] + tot[1]; }
+        __syncthreads();
+        if (stats && blockIdx.x == 0 && tid < n_desc) {
+            const RtGemmDesc& e = dsc[tid];
+            const int tm = (e.m + WR - 1) / WR;
+            unsigned long long issued = 0;
+            for (int t = 0; t < e.tn; ++t) issued += (unsigned long long)tm * 2 * ((min(WC, e.n - t * WC) + 7) / 8) * ((e.k + 3) / 4);
+            atomicAdd(&stats[0], 2ull * e.m * e.n * e.k);
+            atomicAdd(&stats[1], issued * 512ull);
+            atomicAdd(&stats[2], 8ull * ((unsigned long long)e.m * e.k + (unsigned long long)e.k * e.n + (unsigned long long)e.m * e.n));
+            atomicAdd(&stats[8], 1ull);
+        }
+    }
+    const double* a = A.data + (long long)b * A.dstride;
+    double* c = cdata + (long long)b * cstride;
+    const int g = lane >> 2, q = lane & 3;
+    const int nd = n_desc, total = n_items;
+    const int stride = gridDim.x * kGemm2Warps;
+    if (b_smem) {
+        // all threads wait for the bulk copy (phase 0 of the barrier)
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(rt_smem_addr(&bbar)) : "memory");
+    }
+    // item -> descriptor (cursor only moves forward) and the first 16 k of its A rows
+    auto locate = [&](int item, int& cur, RtGemmItem& it) {
+        while (cur + 1 < nd && dsc[cur + 1].start <= item) ++cur;
+        const RtGemmDesc& e = dsc[cur];
+        const int t = item - e.start;
+        it.m = e.m; it.n = e.n; it.k = e.k;
+        it.r0 = (t / e.tn) * WR; it.c0 = (t % e.tn) * WC;
+        it.cols = min(WC, e.n - it.c0);
+        it.aoff = e.aoff; it.coff = e.coff; it.boff = (int)e.boff;
+        it.rows0 = it.r0 + g < e.m; it.rows1 = it.r0 + 8 + g < e.m;
+        it.first = t == 0;
+    };
+    auto load_a = [&](const RtGemmItem& it, int kc, double (&x0)[4], double (&x1)[4]) {
+        const double* ap0 = a + it.aoff + (long long)(it.r0 + g) * it.k + q + kc;
+        const double* ap1 = ap0 + 8ll * it.k;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool kin = kc + 4 * j + q < it.k;
+            x0[j] = (kin && it.rows0) ? __ldg(ap0 + 4 * j) : 0.0;
+            x1[j] = (kin && it.rows1) ? __ldg(ap1 + 4 * j) : 0.0;
+        }
+    };
+    int item = blockIdx.x * kGemm2Warps + warp;
+    int cur = 0, ncur = 0;
+    RtGemmItem it;
+    double a0[4], a1[4], n0[4], n1[4];
+    bool have = item < total;
+    if (have) { locate(item, cur, it); load_a(it, 0, a0, a1); ncur = cur; }
+    while (have) {
+        const int nitem = item + stride;
+        const bool nhave = nitem < total;
+        if (PREFETCH && nhave) { RtGemmItem nx; locate(nitem, ncur, nx); load_a(nx, 0, n0, n1); }       // in flight while the current piece is multiplied
+        const int n = it.n, k = it.k, cols = it.cols;
+        const int nfr = (cols + 7) >> 3;
+        double acc[2][4][2];
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+        for (int kc = 0; kc < k; kc += 16) {
+            if (kc > 0) load_a(it, kc, a0, a1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ks = kc + 4 * j;
+                if (ks < k) {
+                    const bool kin = ks + q < k;
+                    double bv[4];
+                    if (b_smem) {
+                        const double* bp = Bs + it.boff + (ks + q) * n + it.c0 + g;
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) bv[y] = (kin && y < nfr && y * 8 + g < cols) ? bp[y * 8] : 0.0;
+                    } else {
+                        const double* bp = bb + it.boff + (long long)(ks + q) * n + it.c0 + g;
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) bv[y] = (kin && y < nfr && y * 8 + g < cols) ? __ldg(bp + y * 8) : 0.0;
+                    }
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        if (y < nfr) {
+                            rt_dmma(acc[0][y][0], acc[0][y][1], a0[j], bv[y]);
+                            rt_dmma(acc[1][y][0], acc[1][y][1], a1[j], bv[y]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            const int r = it.r0 + x * 8 + g;
+            if (r < it.m) {
+                double* cp = c + it.coff + (long long)r * n + it.c0;
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int cc = y * 8 + 2 * q;
+                    if (cc < cols) cp[cc] = acc[x][y][0];
+                    if (cc + 1 < cols) cp[cc + 1] = acc[x][y][1];
+                }
+            }
+        }
+        if (it.first && lane == 0 && ((it.m * n) & 1)) c[it.coff + (long long)it.m * n] = 0.0;     // alignment pad of an odd-sized sector
+        item = nitem; have = nhave;
+        if (have) {
+            locate(item, cur, it);          // (descriptor re-read from shared memory: cheaper than keeping it in registers)
+            if (PREFETCH) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { a0[j] = n0[j]; a1[j] = n1[j]; }
+            } else load_a(it, 0, a0, a1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // elementwise over the stored sectors (per-chain sizes from the match table)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rt_scale_kernel(const double* __restrict__ x, long long xs, const int* __restrict__ match, long long mts,
@@ -1051,6 +1274,21 @@ extern "C" int tnsp_rt_match_i32(const int32_t* rt, int64_t rt_stride, int rs, c
     return check_launch("tnsp_rt_match_i32");
 }
 
+// CTA size of the tile regrouping kernels (TNSP_RT_REPACK_THREADS = 256 | 128 | 64 overrides the default)
+// Measured on cfg2 (B200, 2368 chains, ms per 3 steps): single regrouping 401 / 305 / 368 at 256 / 128 / 64 threads, the pair kernel
+// 510 / 455 / 422 -- a chain regroups ~1.7 k elements, so CTAs in flight per SM matter more than threads per CTA.
+static int repack_threads(bool pair = false) {
+    static int v[2] = {0, 0};
+    if (!v[0]) {
+        const char* e = getenv("TNSP_RT_REPACK_THREADS");
+        const int x = e ? atoi(e) : 0;
+        const bool ok = x == 256 || x == 128 || x == 64;
+        v[0] = ok ? x : kRepackTileThreads;
+        v[1] = ok ? x : kRepackPairThreads;
+    }
+    return v[pair ? 1 : 0];
+}
+
 // tiles of the densest possible layout / 2 (a CTA loops over its tiles; sectors only cover a fraction of the M x N index space)
 static dim3 tile_grid(int64_t M, int64_t N, int nb, int nz) {
     int64_t gx = (M * N / 2048 + 7) / 8;
@@ -1080,7 +1318,9 @@ extern "C" int tnsp_rt_repack_f64(const int32_t* plan, const tnsp_rt_form* src, 
     cudaStream_t st = (cudaStream_t)stream;
     if (sd) rt_repack_kernel<true, false><<<grid, kRepackThreads, 0, st>>>(p, rt_stats_ptr());
     else if (dd) rt_repack_kernel<false, true><<<grid, kRepackThreads, 0, st>>>(p, rt_stats_ptr());
-    else rt_repack_tile_kernel<<<tile_grid(dst->M, dst->N, nb, 1), kRepackThreads, 0, st>>>(p, rt_stats_ptr());
+    else if (repack_threads() == 128) rt_repack_tile_kernel<128><<<tile_grid(dst->M, dst->N, nb, 1), 128, 0, st>>>(p, rt_stats_ptr());
+    else if (repack_threads() == 64) rt_repack_tile_kernel<64><<<tile_grid(dst->M, dst->N, nb, 1), 64, 0, st>>>(p, rt_stats_ptr());
+    else rt_repack_tile_kernel<256><<<tile_grid(dst->M, dst->N, nb, 1), 256, 0, st>>>(p, rt_stats_ptr());
     return check_launch("tnsp_rt_repack_f64");
 }
 
@@ -1096,7 +1336,9 @@ extern "C" int tnsp_rt_repack_signed_f64(const int32_t* plan, const tnsp_rt_form
     RtSign sg;
     sg.quad = quad; sg.per_chain = per_chain; sg.pcs = per_chain_stride; sg.fermi = fermi_mask;
     for (int i = 0; i < 24; ++i) { sg.lab[i] = i < n_entries ? labels[i] : nullptr; sg.lst[i] = i < n_entries ? lstrides[i] : 0; }
-    rt_repack_signed_kernel<<<tile_grid(dst->M, dst->N, nb, 1), kRepackThreads, 0, (cudaStream_t)stream>>>(p, sg, rt_stats_ptr());
+    if (repack_threads() == 128) rt_repack_signed_kernel<128><<<tile_grid(dst->M, dst->N, nb, 1), 128, 0, (cudaStream_t)stream>>>(p, sg, rt_stats_ptr());
+    else if (repack_threads() == 64) rt_repack_signed_kernel<64><<<tile_grid(dst->M, dst->N, nb, 1), 64, 0, (cudaStream_t)stream>>>(p, sg, rt_stats_ptr());
+    else rt_repack_signed_kernel<256><<<tile_grid(dst->M, dst->N, nb, 1), 256, 0, (cudaStream_t)stream>>>(p, sg, rt_stats_ptr());
     return check_launch("tnsp_rt_repack_signed_f64");
 }
 
@@ -1112,7 +1354,10 @@ extern "C" int tnsp_rt_repack_pair_f64(const int32_t* plan0, const tnsp_rt_form*
     p.a[1].plan = plan1; p.a[1].S = to_form(src1); p.a[1].D = to_form(dst1); p.a[1].spec = to_spec(match1); p.a[1].dst = dst_data1;
     p.a[1].dst_stride = dst_stride1; p.a[1].dense_size = 0;
     const dim3 g0 = tile_grid(dst0->M, dst0->N, nb, 2), g1 = tile_grid(dst1->M, dst1->N, nb, 2);
-    rt_repack_tile_pair_kernel<<<dim3(g0.x > g1.x ? g0.x : g1.x, nb, 2), kRepackThreads, 0, (cudaStream_t)stream>>>(p, rt_stats_ptr());
+    const dim3 gp(g0.x > g1.x ? g0.x : g1.x, nb, 2);
+    if (repack_threads(true) == 128) rt_repack_tile_pair_kernel<128><<<gp, 128, 0, (cudaStream_t)stream>>>(p, rt_stats_ptr());
+    else if (repack_threads(true) == 64) rt_repack_tile_pair_kernel<64><<<gp, 64, 0, (cudaStream_t)stream>>>(p, rt_stats_ptr());
+    else rt_repack_tile_pair_kernel<256><<<gp, 256, 0, (cudaStream_t)stream>>>(p, rt_stats_ptr());
     return check_launch("tnsp_rt_repack_pair_f64");
 }
 
@@ -1123,10 +1368,21 @@ extern "C" int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, co
         // small sectors: warp-autonomous kernel; the grid covers the most items a chain can have (every sector adds at most one
         // partial piece per direction), spare CTAs leave at once
         int64_t items = ((a->M + WR - 1) / WR + RT_SMAX / 4) * ((b->N + WC - 1) / WC);
-        int64_t gx = (items + 8 * kGemmWarps - 1) / (8 * kGemmWarps);      // several items per warp: the CTA prologue is amortised
-        if (gx > 256) gx = 256;
-        rt_gemm_warp_kernel<<<dim3((unsigned)gx, (unsigned)nb), kGemmWarps * 32, 0, (cudaStream_t)stream>>>(
-            to_form(a), to_form(b), to_form(c), to_spec(c_match), c_data, c_stride, ksign, rt_stats_ptr());
+        // TNSP_RT_GEMM = <generation><warps>: 18 / 14 / 12 first generation with 8 / 4 / 2 warps per CTA; 24 = TMA-fed B (16 KiB) without the
+        // cross-item prefetch, 4 warps; 25 = TMA-fed B (32 KiB) + prefetch, 4 warps
+        static int gen = -1;
+        if (gen < 0) { const char* e = getenv("TNSP_RT_GEMM"); gen = e ? atoi(e) : kGemmDefault; }
+        cudaStream_t st = (cudaStream_t)stream;
+        const RtForm fa = to_form(a), fb = to_form(b), fc = to_form(c);
+        const RtSpec sp = to_spec(c_match);
+        auto grid = [&](int warps) { int64_t gx = (items + 8 * warps - 1) / (8 * warps); if (gx > 256) gx = 256; return dim3((unsigned)gx, (unsigned)nb); };
+        switch (gen) {
+        case 25: rt_gemm_warp2_kernel<4, true, 4096, 5><<<grid(4), 128, 0, st>>>(fa, fb, fc, sp, c_data, c_stride, ksign, rt_stats_ptr()); break;
+        case 24: rt_gemm_warp2_kernel<4, false, 2048, 8><<<grid(4), 128, 0, st>>>(fa, fb, fc, sp, c_data, c_stride, ksign, rt_stats_ptr()); break;
+        case 14: rt_gemm_warp_kernel<4><<<grid(4), 128, 0, st>>>(fa, fb, fc, sp, c_data, c_stride, ksign, rt_stats_ptr()); break;
+        case 12: rt_gemm_warp_kernel<2><<<grid(2), 64, 0, st>>>(fa, fb, fc, sp, c_data, c_stride, ksign, rt_stats_ptr()); break;
+        default: rt_gemm_warp_kernel<8><<<grid(8), 256, 0, st>>>(fa, fb, fc, sp, c_data, c_stride, ksign, rt_stats_ptr()); break;
+        }
         return check_launch("tnsp_rt_gemm_f64(warp)");
     }
     int64_t tiles = ((a->M + GT - 1) / GT) * ((b->N + GT - 1) / GT);
