@@ -1,6 +1,13 @@
 # call G: ncu launch list of the default bench command at 2368 chains + ncu --set full of steady-state sector kernels (reports exported
 # to csv on the box: gpurun_out/ carries at most 64 MiB back)
+# (first: the pair-parallel rotation variant of the sector SVD, TNSP_RT_JACOBI=3)
 mkdir -p gpurun_out
+( for v in 2 3; do echo "== TNSP_RT_JACOBI=$v"; TNSP_RT_JACOBI=$v timeout 300 python scripts/mb_rt_factor.py 2368 5 2>&1 | tail -3; done ) > gpurun_out/r2g_mb_jacobi.txt 2>&1
+cat gpurun_out/r2g_mb_jacobi.txt
+( TNSP_RT_JACOBI=3 timeout 900 python -m pytest tests/test_sector_kernels_gpu.py tests/test_cfg2_at_size_gpu.py tests/test_sector_fermi_gpu.py -m gpu -x -q 2>&1 | tail -3 ) > gpurun_out/r2g_tests_jacobi3.txt; cat gpurun_out/r2g_tests_jacobi3.txt
+TNSP_RT_JACOBI=3 timeout 600 python bench.py --workload cfg2 --steps 3 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/r2g_cfg2_jacobi3.json 2> gpurun_out/r2g_cfg2_jacobi3.err
+python -c "
+import json; d=json.loads(open('gpurun_out/r2g_cfg2_jacobi3.json').read().strip().splitlines()[-1]); kb=d['kernel_breakdown']; print('jacobi3', d['value'], d['e2e']['value'], d['ms_per_step'], d['parity_check']['ok'], {k: round(kb[k]['ms']) for k in ('rt_svd_work','rt_qr_work','rt_gemm')})"
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2g_launches_cfg2_nb2368.csv \
   python bench.py --workload cfg2 --steps 1 --warmup 2 --no-cpu-baseline --no-secondary > gpurun_out/r2g_ncu_bench.json 2> gpurun_out/r2g_ncu_bench.err
 tail -c 300 gpurun_out/r2g_ncu_bench.err

@@ -107,3 +107,18 @@ def test_kernels_equal_specification(shape):
         assert np.allclose(got[k], want[k], rtol=1e-13, atol=0)
     for k in ("scaled", "sum"):
         assert np.abs(got[k] - want[k]).max() <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("env", [{"TNSP_RT_GEMM": "24"}, {"TNSP_RT_GEMM": "25", "TNSP_RT_REPACK_THREADS": "256"},
+                                 {"TNSP_RT_GEMM": "12", "TNSP_RT_JACOBI": "3", "TNSP_RT_REPACK_THREADS": "64"}])
+def test_kernel_variants_equal_specification(env):
+    """the alternative kernels kept beside the defaults (TMA-fed GEMM with / without the cross-item prefetch, 2-warp GEMM CTAs, the
+    pair-parallel Jacobi rotation phase, other regrouping CTA sizes) are selected per process by environment variables: the
+    specification test above, re-run in a child process with them set"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_sector_kernels_gpu.py"), "-m", "gpu", "-q", "-x", "-k",
+                        "test_kernels_equal_specification"], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]

@@ -990,6 +990,101 @@ __device__ void jacobi_svd2(double* G, int ldp, double* V, int ldq, int p, int q
     }
 }
 
+// Third variant of the CTA-wide Jacobi: the scalar part of a rotation (one square root, one reciprocal, one reciprocal square
+// root in double precision: ~45 FP64 instructions) is the same for all lanes of a pair's group, so in jacobi_svd2 every warp spends
+// 40 - 50 % of its FP64 issue slots recomputing what its neighbours compute.  Here a round has three phases: (A) dot products per group,
+// leaders park (aa, bb, cc) in shared memory; (B) ONE thread per pair derives (cs, sn); (C) the groups apply them.  Two more block
+// barriers per round against ~45 % fewer FP64 instructions.  prm: 5 doubles per pair (3 q doubles reserved by svd_sector_need).
+__device__ void jacobi_svd3(double* G, int ldp, double* V, int ldq, int p, int q, int* sh_rot, double* prm) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int pe = p + (p & 1), qe_rows = q + (q & 1);
+    const int qe = q + (q & 1), npairs = qe / 2;
+    int gs = 32;
+    while (gs > 4 && gs >= pe) gs >>= 1;
+    while (gs > 4 && npairs * gs > nthreads) gs >>= 1;
+    const int groups = nthreads / gs, grp = tid / gs, gl = tid % gs;
+    const double tol = fmax(1e-15, sqrt((double)p) * 2.3e-16), tol2 = tol * tol;
+    for (int e = tid; e < q * ldq; e += nthreads) { const int cidx = e / ldq, t = e - cidx * ldq; V[e] = (cidx == t) ? 1.0 : 0.0; }
+    __syncthreads();
+    for (int sweep = 0; sweep < 60 && q > 1; ++sweep) {
+        if (tid == 0) *sh_rot = 0;
+        __syncthreads();
+        for (int round = 0; round < qe - 1; ++round) {
+            // (A) dot products
+            for (int base = 0; base < npairs; base += groups) {
+                const int pr = base + grp;
+                int i = 0, j = 0;
+                bool valid = pr < npairs;
+                if (valid) {
+                    if (pr == 0) { i = qe - 1; j = round; }
+                    else { i = round + pr; if (i >= qe - 1) i -= qe - 1; j = round - pr; if (j < 0) j += qe - 1; }
+                    valid = i < q && j < q;
+                    if (i > j) { const int t = i; i = j; j = t; }
+                }
+                const double2* gi = reinterpret_cast<const double2*>(G + i * ldp);
+                const double2* gj = reinterpret_cast<const double2*>(G + j * ldp);
+                double aa = 0.0, bb = 0.0, cc = 0.0;
+                if (valid)
+                    for (int r = gl; 2 * r < pe; r += gs) {
+                        const double2 x = gi[r], y = gj[r];
+                        aa = fma(x.x, x.x, aa); aa = fma(x.y, x.y, aa);
+                        bb = fma(y.x, y.x, bb); bb = fma(y.y, y.y, bb);
+                        cc = fma(x.x, y.x, cc); cc = fma(x.y, y.y, cc);
+                    }
+                aa = gsum(aa, gs); bb = gsum(bb, gs); cc = gsum(cc, gs);
+                if (gl == 0 && pr < npairs) { prm[5 * pr] = aa; prm[5 * pr + 1] = bb; prm[5 * pr + 2] = valid ? cc : 0.0; }
+            }
+            __syncthreads();
+            // (B) one thread per pair: rotation (cs, sn); sn == 0 means "leave the pair alone"
+            for (int pr = tid; pr < npairs; pr += nthreads) {
+                const double aa = prm[5 * pr], bb = prm[5 * pr + 1], cc = prm[5 * pr + 2];
+                const double ab = aa * bb, c2q = cc * cc;
+                double cs = 1.0, sn = 0.0;
+                if (c2q > tol2 * ab && ab > 0.0) {
+                    const double dd = bb - aa, c2 = 2.0 * cc;
+                    const double x2 = fma(dd, dd, c2 * c2);
+                    const double hh = x2 > 1e-280 ? x2 * rsqrt(x2) : sqrt(x2);
+                    const double tt = (dd >= 0.0 ? c2 : -c2) * __drcp_rn(fabs(dd) + hh);
+                    cs = rsqrt(fma(tt, tt, 1.0));
+                    sn = cs * tt;
+                    if (c2q > 1e-16 * ab) *sh_rot = 1;
+                }
+                prm[5 * pr + 3] = cs; prm[5 * pr + 4] = sn;
+            }
+            __syncthreads();
+            // (C) apply
+            for (int base = 0; base < npairs; base += groups) {
+                const int pr = base + grp;
+                if (pr >= npairs) continue;
+                const double cs = prm[5 * pr + 3], sn = prm[5 * pr + 4];
+                if (sn == 0.0) continue;
+                int i, j;
+                if (pr == 0) { i = qe - 1; j = round; }
+                else { i = round + pr; if (i >= qe - 1) i -= qe - 1; j = round - pr; if (j < 0) j += qe - 1; }
+                if (i > j) { const int t = i; i = j; j = t; }
+                double2* gi = reinterpret_cast<double2*>(G + i * ldp);
+                double2* gj = reinterpret_cast<double2*>(G + j * ldp);
+                for (int r = gl; 2 * r < pe; r += gs) {
+                    const double2 x = gi[r], y = gj[r];
+                    gi[r] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+                    gj[r] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+                }
+                double2* vi = reinterpret_cast<double2*>(V + i * ldq);
+                double2* vj = reinterpret_cast<double2*>(V + j * ldq);
+                for (int r = gl; 2 * r < qe_rows; r += gs) {
+                    const double2 x = vi[r], y = vj[r];
+                    vi[r] = make_double2(cs * x.x - sn * y.x, cs * x.y - sn * y.y);
+                    vj[r] = make_double2(sn * x.x + cs * y.x, sn * x.y + cs * y.y);
+                }
+            }
+            __syncthreads();
+        }
+        const int any = *sh_rot;
+        __syncthreads();
+        if (!any) break;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Block Jacobi for a sector whose G (q columns of p rows) and V (q x q) do not fit shared memory: the columns are cut into
 // blocks of B, every pair of blocks is staged in shared memory (G and V panels of 2 B columns), swept once there and written
@@ -1394,7 +1489,8 @@ __host__ __device__ inline int64_t qr_sector_need(int64_t p, int64_t q) {
     const int64_t k = p < q ? p : q;
     return p * (q | 1) + 3 * k + k * q + 8 * ((p + 7) & ~(int64_t)7) + 128;   // W | tau, scl, dia | R | panel reflectors | G, T
 }
-__host__ __device__ inline int64_t svd_sector_need(int64_t p, int64_t q) { return q * (p + (p & 1)) + q * (q + (q & 1)) + q + (q & 1); }
+// G | V | sigma | 3 q doubles of per-pair scratch (jacobi_svd3: the rotation parameters of a round are computed pair-parallel)
+__host__ __device__ inline int64_t svd_sector_need(int64_t p, int64_t q) { return q * (p + (p & 1)) + q * (q + (q & 1)) + q + (q & 1) + 3 * q; }
 
 // kind: 0 = QR of M_s, 1 = LQ of M_s (QR of its transpose), 2 = SVD
 __global__ void __launch_bounds__(kSecThreads, 2) sector_discover_kernel(const int64_t* __restrict__ sect, const double* __restrict__ a,
@@ -2115,6 +2211,7 @@ __device__ __forceinline__ bool rt_pop_warp(int which, int* qctl, const int2* qi
     return true;
 }
 
+constexpr int kRtJacobiDefault = 2;
 constexpr int RT_WS_HDR = 8;
 constexpr int RT_WS_SEC = 6;
 __host__ __device__ inline int64_t rt_ws_stride(int64_t kfull) { return RT_WS_HDR + RT_WS_SEC * RT_SMAX + kfull; }
@@ -2242,7 +2339,7 @@ template <bool BLOCKED>
 __global__ void __launch_bounds__(kQBigThreads) rt_svd_work_kernel(RtForm F, double* __restrict__ workg, long long wbs, const int* __restrict__ ws,
                                                                    long long wss, int kfull, int* qctl, const int2* __restrict__ qitems,
                                                                    long long qcap, int which, int64_t cap, double* __restrict__ scratch,
-                                                                   int64_t scratch_per_cta) {
+                                                                   int64_t scratch_per_cta, int variant) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int sh_ticket;
     __shared__ int sh_rot;
@@ -2275,9 +2372,10 @@ __global__ void __launch_bounds__(kQBigThreads) rt_svd_work_kernel(RtForm F, dou
         }
         if (p & 1) for (int c = tid; c < q; c += nt) G[(int64_t)c * ldp + p] = 0.0;
         __syncthreads();
-        if (!BLOCKED || svd_sector_need(p, q) <= cap || jacobi_block_width(ldp, ldq, cap) < 2)
-            jacobi_svd2(G, ldp, V, ldq, p, q, &sh_rot, g_jacobi_cached_norms ? sig : nullptr);
-        else
+        if (!BLOCKED || svd_sector_need(p, q) <= cap || jacobi_block_width(ldp, ldq, cap) < 2) {
+            if (variant == 3 && q >= 8) jacobi_svd3(G, ldp, V, ldq, p, q, &sh_rot, sig + q + (q & 1));
+            else jacobi_svd2(G, ldp, V, ldq, p, q, &sh_rot, g_jacobi_cached_norms ? sig : nullptr);
+        } else
             jacobi_svd_blocked(G, ldp, V, ldq, p, q, work, cap, sh_flags);
         for (int c = warp; c < q; c += nwarps) {
             double s2 = 0.0;
@@ -2781,6 +2879,12 @@ static int rt_mid_doubles() {
     if (!v) { const char* e = getenv("TNSP_RT_MID_DOUBLES"); v = (e && atoi(e) >= 2560 && atoi(e) <= kQSmallDoubles) ? atoi(e) : kQMidDoubles; }
     return v;
 }
+// Jacobi variant of the sector SVD: 2 = rotations derived per group (default), 3 = pair-parallel rotation phase (TNSP_RT_JACOBI)
+static int rt_jacobi_variant() {
+    static int v = 0;
+    if (!v) { const char* e = getenv("TNSP_RT_JACOBI"); v = (e && atoi(e) == 3) ? 3 : kRtJacobiDefault; }
+    return v;
+}
 static int rt_mid_ctas() { return std::max(1, (int)(227 * 1024 / (rt_mid_doubles() * 8 + 1024))); }
 static int rt_svd_threads(int cls) {
     static int t[4] = {0, 0, 0, 0};
@@ -2901,22 +3005,22 @@ extern "C" int tnsp_rt_svd_work_f64(const tnsp_rt_form* f, double* work, int64_t
     }
     if (full > kQSmallDoubles) {
         rt_svd_work_kernel<true><<<kSMs, rt_svd_threads(0), kQBigDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl, g_qws.qitems,
-                                                                                qcap, 0, kQBigDoubles, g_qws.scratch, per_cta);
+                                                                                qcap, 0, kQBigDoubles, g_qws.scratch, per_cta, rt_jacobi_variant());
         if (check_launch("tnsp_rt_svd_work_f64(big)")) return 1;
     }
     if (full > rt_mid_doubles()) {
         rt_svd_work_kernel<false><<<3 * kSMs, rt_svd_threads(1), kQSmallDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
-                                                                                        g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0);
+                                                                                        g_qws.qitems, qcap, 1, kQSmallDoubles, nullptr, 0, rt_jacobi_variant());
         if (check_launch("tnsp_rt_svd_work_f64(72 KiB class)")) return 1;
     }
     if (!kRtUseWarpClass) {
         rt_svd_work_kernel<false><<<8 * kSMs, rt_svd_threads(3), kRtTinyDoubles * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull, g_qws.qctl,
-                                                                                        g_qws.qitems, qcap, 3, kRtTinyDoubles, nullptr, 0);
+                                                                                        g_qws.qitems, qcap, 3, kRtTinyDoubles, nullptr, 0, rt_jacobi_variant());
         if (check_launch("tnsp_rt_svd_work_f64(tiny class)")) return 1;
         if (full <= kRtTinyDoubles) return 0;
     }
     rt_svd_work_kernel<false><<<rt_mid_ctas() * kSMs, rt_svd_threads(2), rt_mid_doubles() * 8, st>>>(F, work, work_stride, ws, ws_stride, kfull,
-                                                                                  g_qws.qctl, g_qws.qitems, qcap, 2, rt_mid_doubles(), nullptr, 0);
+                                                                                  g_qws.qctl, g_qws.qitems, qcap, 2, rt_mid_doubles(), nullptr, 0, rt_jacobi_variant());
     return check_launch("tnsp_rt_svd_work_f64(55 KiB class)");
 }
 

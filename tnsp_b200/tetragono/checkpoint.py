@@ -297,6 +297,12 @@ def read_configurations(file_name):
         stored, ndim = np.frombuffer(f.read(16), dtype=np.int64)
         shape = np.frombuffer(f.read(8 * int(ndim)), dtype=np.int64)
         count = int(np.prod(shape))
-        choose = rank if stored >= size else _random.uniform_int(0, int(stored) - 1)()
+        if stored >= size:
+            choose = rank
+        else:
+            # fewer blocks than ranks: every rank draws its own block (the reference draws under `seed_differ`, utility.py:398-412:
+            # a common base from the shared engine, then a rank-dependent stream)
+            base = _random.uniform_int(0, 2**31 - 1)()
+            choose = int(np.random.RandomState((base + rank) % 2**31).randint(0, int(stored)))
         f.seek(16 + 8 * int(ndim) + choose * count * 8)
         return np.frombuffer(f.read(count * 8), dtype=np.int64).reshape(tuple(int(x) for x in shape)).copy()
