@@ -8,6 +8,9 @@ cat gpurun_out/r2g_mb_jacobi.txt
 TNSP_RT_JACOBI=3 timeout 600 python bench.py --workload cfg2 --steps 3 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/r2g_cfg2_jacobi3.json 2> gpurun_out/r2g_cfg2_jacobi3.err
 python -c "
 import json; d=json.loads(open('gpurun_out/r2g_cfg2_jacobi3.json').read().strip().splitlines()[-1]); kb=d['kernel_breakdown']; print('jacobi3', d['value'], d['e2e']['value'], d['ms_per_step'], d['parity_check']['ok'], {k: round(kb[k]['ms']) for k in ('rt_svd_work','rt_qr_work','rt_gemm')})"
+TNSP_RT_GEMM=38 timeout 600 python bench.py --workload cfg2 --steps 3 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/r2g_cfg2_gemm38.json 2> gpurun_out/r2g_cfg2_gemm38.err
+python -c "
+import json; d=json.loads(open('gpurun_out/r2g_cfg2_gemm38.json').read().strip().splitlines()[-1]); kb=d['kernel_breakdown']; print('gemm38', d['value'], d['e2e']['value'], d['ms_per_step'], d['parity_check']['ok'], {k: round(kb[k]['ms']) for k in ('rt_svd_work','rt_qr_work','rt_gemm')})"
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2g_launches_cfg2_nb2368.csv \
   python bench.py --workload cfg2 --steps 1 --warmup 2 --no-cpu-baseline --no-secondary > gpurun_out/r2g_ncu_bench.json 2> gpurun_out/r2g_ncu_bench.err
 tail -c 300 gpurun_out/r2g_ncu_bench.err

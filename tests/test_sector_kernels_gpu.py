@@ -109,7 +109,7 @@ def test_kernels_equal_specification(shape):
         assert np.abs(got[k] - want[k]).max() <= 1e-12 * scale
 
 
-@pytest.mark.parametrize("env", [{"TNSP_RT_GEMM": "24"}, {"TNSP_RT_GEMM": "25", "TNSP_RT_REPACK_THREADS": "256"},
+@pytest.mark.parametrize("env", [{"TNSP_RT_GEMM": "24"}, {"TNSP_RT_GEMM": "38"}, {"TNSP_RT_GEMM": "25", "TNSP_RT_REPACK_THREADS": "256"},
                                  {"TNSP_RT_GEMM": "12", "TNSP_RT_JACOBI": "3", "TNSP_RT_REPACK_THREADS": "64"}])
 def test_kernel_variants_equal_specification(env):
     """the alternative kernels kept beside the defaults (TMA-fed GEMM with / without the cross-item prefetch, 2-warp GEMM CTAs, the

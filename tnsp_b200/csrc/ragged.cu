@@ -844,8 +844,8 @@ constexpr int WC = 32;          // columns per warp item (4 DMMA fragments)
 // per-sector descriptor built once per CTA in shared memory: the warps then find their items without touching the tables again
 struct RtGemmDesc { int m, n, k, tn, start; long long aoff, boff, coff; };
 
-template <int kGemmWarps>
-__global__ void __launch_bounds__(kGemmWarps * 32, 32 / kGemmWarps) rt_gemm_warp_kernel(RtForm A, RtForm B, RtForm C, RtSpec spec, double* __restrict__ cdata,
+template <int kGemmWarps, int WC = 32, int MINB = 32 / kGemmWarps>
+__global__ void __launch_bounds__(kGemmWarps * 32, MINB) rt_gemm_warp_kernel(RtForm A, RtForm B, RtForm C, RtSpec spec, double* __restrict__ cdata,
                                                                           long long cstride, int ksign, unsigned long long* stats) {
     __shared__ int mC[RT_MSTRIDE];
     __shared__ RtGemmDesc dsc[RT_SMAX];
@@ -934,11 +934,12 @@ __global__ void __launch_bounds__(kGemmWarps * 32, 32 / kGemmWarps) rt_gemm_warp
         const int r0 = (t / e.tn) * WR, c0 = (t % e.tn) * WC;
         const int cols = min(WC, n - c0);
         const int nfr = (cols + 7) >> 3;
-        double acc[2][4][2];
+        constexpr int NF = WC / 8;
+        double acc[2][NF][2];
 #pragma unroll
         for (int x = 0; x < 2; ++x)
 #pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+            for (int y = 0; y < NF; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
         const bool row0 = r0 + g < m, row1 = r0 + 8 + g < m;
         const double* ap0 = a + e.aoff + (long long)(r0 + g) * k + q;
         const double* ap1 = ap0 + 8ll * k;
@@ -948,7 +949,7 @@ __global__ void __launch_bounds__(kGemmWarps * 32, 32 / kGemmWarps) rt_gemm_warp
             const double a0 = (kin && row0) ? __ldg(ap0 + ks) : 0.0;
             const double a1 = (kin && row1) ? __ldg(ap1 + ks) : 0.0;
 #pragma unroll
-            for (int y = 0; y < 4; ++y) {
+            for (int y = 0; y < NF; ++y) {
                 if (y < nfr) {
                     const double bv = (kin && y * 8 + g < cols) ? __ldg(bp + (long long)ks * n + y * 8) : 0.0;
                     rt_dmma(acc[0][y][0], acc[0][y][1], a0, bv);
@@ -962,7 +963,7 @@ __global__ void __launch_bounds__(kGemmWarps * 32, 32 / kGemmWarps) rt_gemm_warp
             if (r < m) {
                 double* cp = c + e.coff + (long long)r * n + c0;
 #pragma unroll
-                for (int y = 0; y < 4; ++y) {
+                for (int y = 0; y < NF; ++y) {
                     const int cc = y * 8 + 2 * q;
                     if (cc < cols) cp[cc] = acc[x][y][0];
                     if (cc + 1 < cols) cp[cc + 1] = acc[x][y][1];
@@ -1367,8 +1368,8 @@ extern "C" int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, co
     if (a->N <= 512 && b->N <= 512) {
         // small sectors: warp-autonomous kernel; the grid covers the most items a chain can have (every sector adds at most one
         // partial piece per direction), spare CTAs leave at once
-        int64_t items = ((a->M + WR - 1) / WR + RT_SMAX / 4) * ((b->N + WC - 1) / WC);
-        // TNSP_RT_GEMM = <generation><warps>: 18 / 14 / 12 first generation with 8 / 4 / 2 warps per CTA; 24 = TMA-fed B (16 KiB) without the
+        int64_t items = ((a->M + WR - 1) / WR + RT_SMAX / 4) * ((b->N + 32 - 1) / 32);
+        // TNSP_RT_GEMM = <generation><warps>: 18 / 14 / 12 first generation with 8 / 4 / 2 warps per CTA; 38 = 8 warps, 16-column pieces; 24 = TMA-fed B (16 KiB) without the
         // cross-item prefetch, 4 warps; 25 = TMA-fed B (32 KiB) + prefetch, 4 warps
         static int gen = -1;
         if (gen < 0) { const char* e = getenv("TNSP_RT_GEMM"); gen = e ? atoi(e) : kGemmDefault; }
@@ -1381,6 +1382,8 @@ extern "C" int tnsp_rt_gemm_f64(const tnsp_rt_form* a, const tnsp_rt_form* b, co
         case 24: rt_gemm_warp2_kernel<4, false, 2048, 8><<<grid(4), 128, 0, st>>>(fa, fb, fc, sp, c_data, c_stride, ksign, rt_stats_ptr()); break;
         case 14: rt_gemm_warp_kernel<4><<<grid(4), 128, 0, st>>>(fa, fb, fc, sp, c_data, c_stride, ksign, rt_stats_ptr()); break;
         case 12: rt_gemm_warp_kernel<2><<<grid(2), 64, 0, st>>>(fa, fb, fc, sp, c_data, c_stride, ksign, rt_stats_ptr()); break;
+        case 38: items = ((a->M + WR - 1) / WR + RT_SMAX / 4) * ((b->N + 15) / 16);     // 16-column pieces: 8 accumulators, 5 CTAs per SM
+                 rt_gemm_warp_kernel<8, 16, 5><<<grid(8), 256, 0, st>>>(fa, fb, fc, sp, c_data, c_stride, ksign, rt_stats_ptr()); break;
         default: rt_gemm_warp_kernel<8><<<grid(8), 256, 0, st>>>(fa, fb, fc, sp, c_data, c_stride, ksign, rt_stats_ptr()); break;
         }
         return check_launch("tnsp_rt_gemm_f64(warp)");
