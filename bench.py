@@ -457,6 +457,8 @@ def run_own(args):
     wl = WORKLOADS[args.workload]
     L1, L2, Dc, desc = wl["L1"], wl["L2"], wl["Dc"], wl["desc"]
     nb = args.chains or wl["chains"]
+    if getattr(args, "strong", False):
+        nb = max(1, nb // world)          # fixed total work: the curve whose limiter is the host path of a step
     sym_lat, hopping, points = build_workload(TAT, wl)
     sector = wl["sym"] != "No" and (args.engine == "sector" or wl["sym"].startswith("Fermi"))
     if wl["sym"] == "No":
@@ -666,7 +668,8 @@ def run_own(args):
     if rank == 0:
         out = {
             "metric": "VMC samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if getattr(args, "strong", False) else "weak",
+            "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (randn_ PEPS seed 2333, Neel start, per-chain mt19937_64 seeds)",
             "config": {"workload": f"{args.workload}: {desc}", "chains_per_gpu": nb, "samples_per_step": nb * world,
                        "observer": "energy+gradient" + ("+SR natural gradient (CG %d)" % wl["cg"] if wl["sr"] else ""),
@@ -712,6 +715,8 @@ def main():
     ap.add_argument("--engine", default="sector", choices=["sector", "dense"],
                     help="lock-step engine of symmetric models: sector-compact tensors (default) or the charge-dense embedding of round 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's chain count is the TOTAL over all ranks "
+                                                          "(chains per GPU = total / world size) instead of the per-GPU count")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short runs of the other BASELINE configurations (`secondary` key)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -5,3 +5,6 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mast
 tail -c 300 gpurun_out/r2h_cfg2_2gpu.err
 python -c "
 import json; d=json.loads(open('gpurun_out/r2h_cfg2_2gpu.json').read().strip().splitlines()[-1]); print(d['n_gpus'], d['value'], d['e2e'], d['ms_per_step'])"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29535 bench.py --gpus 2 --steps 2 --warmup 3 --no-cpu-baseline --strong > gpurun_out/r2h_cfg2_2gpu_strong.json 2> gpurun_out/r2h_cfg2_2gpu_strong.err
+python -c "
+import json; d=json.loads(open('gpurun_out/r2h_cfg2_2gpu_strong.json').read().strip().splitlines()[-1]); print('strong', d['n_gpus'], d['config']['chains_per_gpu'], d['value'], d['e2e'], d['ms_per_step'])"
