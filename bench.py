@@ -551,6 +551,11 @@ def run_own(args):
     # ---- device-resident timing -------------------------------------------------------------------
     for _ in range(args.warmup):
         step()
+    # the long-lived objects (lattice, plan caches, lazy graphs: ~1e6 of them) leave the cyclic collector's generations, so that a full
+    # collection inside a step only walks what the step itself created (one was seen to cost ~1 s of a 592-chain run)
+    import gc
+    gc.collect()
+    gc.freeze()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
