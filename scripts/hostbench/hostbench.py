@@ -136,6 +136,7 @@ def main():
         times.append(time.perf_counter() - t0)
     n = (B.launch_count() - l0) / steps
     dt = min(times)
+    print({k: v for k, v in ragged.STATS.items()})
     print(f"{workload}: min {dt * 1e3:.1f} ms / median {sorted(times)[len(times) // 2] * 1e3:.1f} ms per step on the host, {n:.0f} C-ABI calls per step, "
           f"{dt / n * 1e6:.1f} us per call")
 

@@ -36,7 +36,7 @@ SMAX = 64                    # sectors per edge group and chain (device tables a
 HDR = 3 + 2 * SMAX           # group table header: nsec, nvalid, skey[SMAX], sstart[SMAX + 1]
 MSTRIDE = 4 + 2 * SMAX       # match table: size, flag, moff[SMAX + 1], mcol[SMAX] (+1 pad)
 DEAD = 1 << 30               # label of a bond index that carries no state (|label| >= 2^29)
-STATS = {"contract": 0, "qr": 0, "svd": 0, "repack": 0, "sort": 0, "match": 0}
+STATS = {"contract": 0, "qr": 0, "svd": 0, "repack": 0, "sort": 0, "match": 0, "signed_hit": 0}
 
 _PLANS: dict = {}
 
@@ -118,17 +118,25 @@ class Edge:
     """one edge of a sector-compact tensor: dimension, charge labels (device int32 [nbL, dim] with nbL in {1, nb}) and a sign
     (effective label = sign * array, so that conjugation and contraction results never copy label arrays).  A *unit* edge has
     dimension 1 and host-known labels `harr` [nbL] (physical P edges, total-symmetry edge): it never reaches a kernel."""
-    __slots__ = ("dim", "arr", "sign", "arrow", "harr")
+    __slots__ = ("dim", "arr", "sign", "arrow", "harr", "par")
 
-    def __init__(self, dim, arr, sign=1, arrow=False, harr=None):
+    def __init__(self, dim, arr, sign=1, arrow=False, harr=None, par=None):
         self.dim, self.arr, self.sign, self.arrow, self.harr = int(dim), arr, int(sign), bool(arrow), harr
+        self.par = par          # (fermi mask, parity bits of harr): cached by unit_parity, shared by flipped copies
 
     @property
     def unit(self):
         return self.harr is not None
 
     def flipped(self, s):
-        return self if s == 1 else Edge(self.dim, self.arr, -self.sign, not self.arrow, self.harr)
+        return self if s == 1 else Edge(self.dim, self.arr, -self.sign, not self.arrow, self.harr, self.par)
+
+    def unit_parity(self, mask):
+        """parity bits [nbL] of a unit edge's charges (the parity of a label does not depend on its sign)"""
+        p = self.par
+        if p is None or p[0] != mask:
+            p = self.par = (mask, label_parity(np.asarray(self.harr, dtype=np.int64).reshape(-1), mask))
+        return p[1]
 
     def host_labels(self):
         if self.harr is not None:
@@ -148,13 +156,14 @@ class Form:
 
 class Core:
     """edges + data of a tensor, shared by renamed / conjugated views (the reference's refcounted Core, tensor.hpp:129-135)"""
-    __slots__ = ("edges", "nb", "target", "tsign", "forms", "primary", "tables", "fermi", "dims", "sig", "_gd")
+    __slots__ = ("edges", "nb", "target", "tsign", "forms", "primary", "tables", "fermi", "dims", "sig", "_gd", "sforms")
 
     def __init__(self, edges, nb, target, tsign, fermi=0):
         self.edges = tuple(edges)
         self.dims = tuple([e.dim for e in self.edges])
         self.sig = (self.dims, tuple([e.harr is not None for e in self.edges]))      # what a plan depends on: dimensions, unit flags
         self._gd = {}
+        self.sforms = None                           # signed regroupings of a fermionic tensor (ragged_fermi.signed_form), a few most recent
         self.nb = nb
         self.fermi = fermi                           # mask of the fermionic label components (0: bosonic symmetry)
         self.target, self.tsign = target, tsign      # device int32 [nbt] or None: sum of non-unit labels of a stored element

@@ -65,8 +65,8 @@ def unit_parities(t, mask):
     """{position: int array [nbL] of parities} of the unit edges of tensor view `t` (effective labels)"""
     out = {}
     for i, e in enumerate(t.core.edges):
-        if e.unit:
-            out[i] = label_parity(e.sign * t.sign * np.asarray(e.harr, dtype=np.int64).reshape(-1), mask)
+        if e.harr is not None:
+            out[i] = e.unit_parity(mask)
     return out
 
 
@@ -81,42 +81,72 @@ def fold_units(form, t, entries):
     n = len(entries)
     if n > 30:
         raise NotImplementedError("sign form over more than 30 indexed edges")
-    quad = np.zeros(max(n, 1), dtype=np.int64)
-    nb = max([v.shape[0] for v in up.values()] + [1])
-    const = np.zeros(nb, dtype=np.int64)
-    lin = np.zeros(nb, dtype=np.int64)
+    quad = [0] * max(n, 1)
+    lin0, const0 = 0, 0          # chain-independent parts (Python ints); the unit parities enter as arrays
+    lin_a, const_a = None, None
     for i in form.lin:
-        if i in slot:
-            lin ^= 1 << slot[i]
+        k = slot.get(i)
+        if k is not None:
+            lin0 ^= 1 << k
         elif i in up:
-            const ^= up[i]
+            const_a = up[i] if const_a is None else const_a ^ up[i]
     for pr in form.quad:
         i, j = tuple(pr)
-        if i in slot and j in slot:
-            a, b = sorted((slot[i], slot[j]))
-            quad[a] ^= 1 << b
-        elif i in slot and j in up:
-            lin ^= up[j] << slot[i]
-        elif j in slot and i in up:
-            lin ^= up[i] << slot[j]
+        ki, kj = slot.get(i), slot.get(j)
+        if ki is not None and kj is not None:
+            if ki > kj:
+                ki, kj = kj, ki
+            quad[ki] ^= 1 << kj
+        elif ki is not None and j in up:
+            v = up[j] << ki
+            lin_a = v if lin_a is None else lin_a ^ v
+        elif kj is not None and i in up:
+            v = up[i] << kj
+            lin_a = v if lin_a is None else lin_a ^ v
         elif i in up and j in up:
-            const ^= up[i] & up[j]
-    if not quad.any() and not lin.any() and not const.any():
-        return None, None
-    per_chain = (lin & 0x7FFFFFFF) | ((const & 1) << 31)
+            v = up[i] & up[j]
+            const_a = v if const_a is None else const_a ^ v
+    if lin_a is None and const_a is None:
+        if not any(quad) and lin0 == 0:
+            return None, None
+        per_chain = np.array([lin0 & 0x7FFFFFFF], dtype=np.int64)
+    else:
+        lin = (lin0 if lin_a is None else (lin_a ^ lin0)) & 0x7FFFFFFF
+        const = 0 if const_a is None else (const_a & 1)
+        per_chain = np.atleast_1d(np.asarray(lin | (const << 31), dtype=np.int64))
+        if not any(quad) and not per_chain.any():
+            return None, None
     per_chain = np.where(per_chain >= (1 << 31), per_chain - (1 << 32), per_chain).astype(np.int32)
-    return quad.astype(np.int32), per_chain
+    return np.array(quad, dtype=np.int32), per_chain
 
 
 # -------------------------------------------------------------------------------------------------
 # signed regrouping
 # -------------------------------------------------------------------------------------------------
 def signed_form(t, rows, cols, form):
-    """storage of tensor view `t` regrouped as rows | cols with the sign form applied (a fresh Form; never cached: it belongs to
-    one operation).  Falls back to the cached unsigned regrouping when the form vanishes."""
+    """storage of tensor view `t` regrouped as rows | cols with the sign form applied.  Falls back to the cached unsigned regrouping
+    when the form vanishes.  The result depends on the (immutable) core, the grouping and the form only, so the few most recent ones
+    are kept with the core: a site tensor or an environment enters several contractions of a sweep with the same signs."""
     core = t.core
     if form.empty():
         return core.form(rows, cols)
+    skey = (rows, cols, form.key())
+    if core.sforms is not None:
+        hit = core.sforms.get(skey)
+        if hit is not None:
+            STATS["signed_hit"] += 1
+            return hit
+    f = _build_signed_form(t, rows, cols, form)
+    if core.sforms is None:
+        core.sforms = {}
+    elif len(core.sforms) >= 3:
+        core.sforms.pop(next(iter(core.sforms)))
+    core.sforms[skey] = f
+    return f
+
+
+def _build_signed_form(t, rows, cols, form):
+    core = t.core
     entries = list(rows) + list(cols)          # every device-labelled edge, dimension 1 included: its parity is only known there
     quad, per_chain = fold_units(form, t, entries)
     if quad is None:
@@ -126,7 +156,7 @@ def signed_form(t, rows, cols, form):
     rt, rs = core.table(rows)
     ct, cs = core.table(cols)
     M, N = core.group_dim(rows), core.group_dim(cols)
-    ckey = ("form", tuple(e.dim for e in core.edges), src.rows, src.cols, rows, cols)
+    ckey = ("form", core.dims, src.rows, src.cols, rows, cols)
     nbd = max(src.data.shape[0], src.match.shape[0], rt.shape[0], ct.shape[0], per_chain.shape[0], 1 if core.target is None else core.target.shape[0])
     cap, learning = ragged._cap(ckey, M * N, nbd)
     f = Form(rows, cols, rt, rs, ct, cs, None, B.rt_alloc(nbd, cap), M, N)
@@ -186,44 +216,50 @@ def fermi_contract(a, b, pairs):
       operand 1: common edges are brought to arrow true WITH sign (the odd ones among those that had arrow false), free edges to
                  arrow false without; transposition to (free..., common...); merge sign (n_odd & 2) on the common group;
       operand 2: reversals without sign; transposition to (common in the order of operand 1..., free...)."""
-    pairs = list(pairs)
-    map12 = dict(pairs)
-    for x, y in pairs:
-        if x not in a.names or y not in b.names:
-            raise RuntimeError("Missing name in contract")
-    used_b = set(map12.values())
-    ka_all = [i for i, n in enumerate(a.names) if n in map12]
-    kb_all = [b.names.index(map12[a.names[i]]) for i in ka_all]
-    fa = [i for i, n in enumerate(a.names) if n not in map12]
-    fb = [j for j, n in enumerate(b.names) if n not in used_b]
-    form_a, form_b = SignForm(), SignForm()
-    for i in ka_all:
-        if not a.effective_edge(i).arrow:
-            form_a.add_lin(i)
-    form_a.add_transposition(fa + ka_all)
-    form_a.add_clique(ka_all)
-    form_b.add_transposition(kb_all + fb)
     ea, eb = a.core.edges, b.core.edges
-    for i, j in zip(ka_all, kb_all):
-        if ea[i].dim != eb[j].dim:
-            raise RuntimeError("Contracting two edge with different dimension")
-        if ea[i].unit != eb[j].unit:
-            raise NotImplementedError("contract of a host-labelled dimension-1 edge with a device-labelled one")
-    fa_n = tuple(i for i in fa if not ea[i].unit)
-    fb_n = tuple(j for j in fb if not eb[j].unit)
-    ka = tuple(i for i in ka_all if not ea[i].unit)
-    kb = tuple(j for i, j in zip(ka_all, kb_all) if not ea[i].unit)
-    names = [a.names[i] for i in fa] + [b.names[j] for j in fb]
+    pkey = ("fplan", tuple(a.names), a.core.sig, a.sign, tuple([e.arrow for e in ea]), tuple(b.names), b.core.sig, b.sign,
+            tuple([e.arrow for e in eb]), frozenset(pairs))
+    plan = _PLANS.get(pkey)
+    if plan is None:
+        pairs = list(pairs)
+        map12 = dict(pairs)
+        for x, y in pairs:
+            if x not in a.names or y not in b.names:
+                raise RuntimeError("Missing name in contract")
+        used_b = set(map12.values())
+        ka_all = [i for i, n in enumerate(a.names) if n in map12]
+        kb_all = [b.names.index(map12[a.names[i]]) for i in ka_all]
+        fa = [i for i, n in enumerate(a.names) if n not in map12]
+        fb = [j for j, n in enumerate(b.names) if n not in used_b]
+        form_a, form_b = SignForm(), SignForm()
+        for i in ka_all:
+            if not a.effective_edge(i).arrow:
+                form_a.add_lin(i)
+        form_a.add_transposition(fa + ka_all)
+        form_a.add_clique(ka_all)
+        form_b.add_transposition(kb_all + fb)
+        for i, j in zip(ka_all, kb_all):
+            if ea[i].dim != eb[j].dim:
+                raise RuntimeError("Contracting two edge with different dimension")
+            if ea[i].unit != eb[j].unit:
+                raise NotImplementedError("contract of a host-labelled dimension-1 edge with a device-labelled one")
+        fa_n = tuple(i for i in fa if not ea[i].unit)
+        fb_n = tuple(j for j in fb if not eb[j].unit)
+        ka = tuple(i for i in ka_all if not ea[i].unit)
+        kb = tuple(j for i, j in zip(ka_all, kb_all) if not ea[i].unit)
+        names = [a.names[i] for i in fa] + [b.names[j] for j in fb]
+        rows = tuple(k for k, i in enumerate(fa) if not ea[i].unit)
+        cols = tuple(len(fa) + k for k, j in enumerate(fb) if not eb[j].unit)
+        plan = _PLANS[pkey] = (fa, fb, fa_n, fb_n, ka, kb, names, rows, cols, form_a, form_b)
+    fa, fb, fa_n, fb_n, ka, kb, names, rows, cols, form_a, form_b = plan
     B = _bk.get()
     STATS["contract"] += 1
     A = signed_form(a, fa_n, ka, form_a)
     Bf = signed_form(b, kb, fb_n, form_b)
     nb = max(a.core.nb, b.core.nb, A.match.shape[0], Bf.match.shape[0], A.data.shape[0], Bf.data.shape[0])
     edges = [ea[i].flipped(a.sign) for i in fa] + [eb[j].flipped(b.sign) for j in fb]
-    rows = tuple(k for k, i in enumerate(fa) if not ea[i].unit)
-    cols = tuple(len(fa) + k for k, j in enumerate(fb) if not eb[j].unit)
     rs, cs = A.rs * a.sign, Bf.cs * b.sign
-    key = ("fct", tuple(e.dim for e in ea), fa_n, ka, tuple(e.dim for e in eb), kb, fb_n)
+    key = ("fct", a.core.dims, fa_n, ka, b.core.dims, kb, fb_n)
     cap, learning = ragged._cap(key, A.M * Bf.N, nb)
     C = Form(rows, cols, A.rt, rs, Bf.ct, cs, None, B.rt_alloc(nb, cap), A.M, Bf.N)
     ksign = -(a.sign * A.cs) * (b.sign * Bf.rs)
