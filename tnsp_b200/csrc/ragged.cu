@@ -41,13 +41,15 @@ struct RtEdges {
     int sign[8];
     int n;
 };
-constexpr int kSortThreads = 256;
-constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kHash = 256;
 
 __device__ __forceinline__ int rt_hash(int key) { return (int)(((unsigned)key * 2654435761u) >> 24) & (kHash - 1); }
 
+// (kSortThreads = 256, or 1024 for merged dimensions beyond 32 k: few chains x huge groups -- cfg4's 10^6 indices -- leave most SMs idle,
+// so a chain gets as many threads as a CTA can have)
+template <int kSortThreads>
 __global__ void __launch_bounds__(kSortThreads) rt_sort_kernel(RtEdges E, int M, int* __restrict__ table, long long tstride) {
+    constexpr int kSortWarps = kSortThreads / 32;
     __shared__ int hkey[kHash];
     __shared__ int hval[kHash];
     __shared__ int skeys[RT_SMAX + 1];
@@ -1262,7 +1264,8 @@ extern "C" int tnsp_rt_sort_i32(int n_edges, const int32_t* const* labels, const
         rt_sort_warp_kernel<<<(nbT + kSortWarpPerCta - 1) / kSortWarpPerCta, 32 * kSortWarpPerCta, 0, (cudaStream_t)stream>>>(E, (int)M, table,
                                                                                                                     RT_HDR + 2 * M, nbT);
     else
-        rt_sort_kernel<<<nbT, kSortThreads, 0, (cudaStream_t)stream>>>(E, (int)M, table, RT_HDR + 2 * M);
+        if (M > 32768) rt_sort_kernel<1024><<<nbT, 1024, 0, (cudaStream_t)stream>>>(E, (int)M, table, RT_HDR + 2 * M);
+        else rt_sort_kernel<256><<<nbT, 256, 0, (cudaStream_t)stream>>>(E, (int)M, table, RT_HDR + 2 * M);
     return check_launch("tnsp_rt_sort_i32");
 }
 
