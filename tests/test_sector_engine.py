@@ -155,3 +155,60 @@ def test_sweep_trajectory_sector_equals_reference_trajectory():
             if got.names != want.names:
                 got = got.transpose(want.names)
             assert np.abs(np.asarray(got.storage) - np.asarray(want.storage)).max() <= 1e-9 * gs
+
+
+def test_learnt_capacities_and_overflow_correction():
+    """buffer capacities: a calibration batch learns the largest stored size per operation, later batches allocate CAP_FACTOR x that and
+    still give the same amplitudes; a capacity that is too small stores the chain EMPTY (amplitude zero), is counted, reported by the
+    sampler as a warning and corrected by a larger factor -- never silent, never out of bounds"""
+    import warnings
+    from tnsp_b200.tetragono import sampling
+    from tnsp_b200.tetragono.sampling import calibrate_sector_engine
+    meta, z, lat = _u1_lattice()
+    L1, L2, Dc = meta["L1"], meta["L2"], meta["Dc"]
+    nb = 4
+    confs = _sz0_configurations(nb, L1, L2, 5)
+    saved = (dict(ragged._CAPS), dict(ragged._LEARN), ragged.CAP_FACTOR, ragged.CAP_MIN_CHAINS, dict(sampling._CAPACITY_BUMPS))
+    try:
+        ragged._CAPS.clear()
+        ragged.CAP_MIN_CHAINS = 1
+        ref = Configuration(lat, Dc, nb)                                   # learning phase: dense bounds
+        ragged._LEARN.update(all=True, cycles=0)
+        ref.import_configuration(confs)
+        ws_ref = np.asarray(ref.hole(()).storage).reshape(-1).copy()
+        calibrate_sector_engine(lat, Dc, confs[0], models.nearest_neighbour_terms(lat), chains=nb, sweeps=1)
+        assert not ragged._LEARN["all"] and len(ragged._CAPS) > 0
+        capped = Configuration(lat, Dc, nb)
+        capped.import_configuration(confs)
+        ws = np.asarray(capped.hole(()).storage).reshape(-1)
+        assert np.abs(ws - ws_ref).max() <= RTOL * np.abs(ws_ref).max()
+        assert TAT.tensor._bk.get().rt_overflow() == 0
+        # now far too small (this lattice's tensors store <= 42 elements, below the floor of a learnt capacity, so the allocation
+        # itself is shrunk): tensors beyond 8 elements are dropped -- stored EMPTY, counted, nothing written out of bounds
+        B = TAT.tensor._bk.get()
+        import torch
+        ragged.CAP_FACTOR = 1.0
+        sampling._CAPACITY_BUMPS.update(n=0, dropped=0)
+        real_cap, real_alloc = ragged._cap, B.rt_alloc
+        ragged._cap = lambda key, dense, nb=None: (min(dense, 8), False)
+        B.rt_alloc = lambda nb_, size: torch.zeros((nb_, max(int(size), 2)), dtype=torch.float64)
+        try:
+            small = Configuration(lat, Dc, nb)
+            small.import_configuration(confs)
+            ws0 = np.asarray(small.hole(()).storage).reshape(-1)
+        finally:
+            ragged._cap, B.rt_alloc = real_cap, real_alloc
+        assert np.all(ws0 == 0.0)
+        assert B.rt_overflow(clear=False) > 0
+        with warnings.catch_warnings(record=True) as rec:
+            warnings.simplefilter("always")
+            sampling._check_capacity()
+        assert any("exceeded their learnt capacity" in str(w.message) for w in rec)
+        assert ragged.CAP_FACTOR == 1.5 and sampling._CAPACITY_BUMPS["n"] == 1
+        assert TAT.tensor._bk.get().rt_overflow() == 0                       # the counter was cleared
+    finally:
+        ragged._CAPS.clear()
+        ragged._CAPS.update(saved[0])
+        ragged._LEARN.update(saved[1])
+        ragged.CAP_FACTOR, ragged.CAP_MIN_CHAINS = saved[2], saved[3]
+        sampling._CAPACITY_BUMPS.update(saved[4])
