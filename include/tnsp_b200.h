@@ -206,6 +206,16 @@ int tnsp_rt_sort_i32(int n_edges, const int32_t* const* labels, const int64_t* l
 int tnsp_rt_match_i32(const int32_t* rt, int64_t rt_stride, int rs, const int32_t* ct, int64_t ct_stride, int cs, const int32_t* t1,
                       int t1_stride, int s1, const int32_t* t2, int t2_stride, int s2, int32_t* match, int32_t* tsum, int nbm, int64_t cap,
                       void* stream);
+/* up to four pairings in ONE launch (the two / three pairing tables a factorisation needs for its factors: qr.hpp:419-429,
+ * svd.hpp:405-427): job j uses entry j of every array; same rule and outputs as tnsp_rt_match_i32 (tsum entries may be NULL) */
+typedef struct {
+    const int32_t* rt; int64_t rt_stride; int32_t rs;
+    const int32_t* ct; int64_t ct_stride; int32_t cs;
+    const int32_t* t1; int32_t t1_stride; int32_t s1;
+    const int32_t* t2; int32_t t2_stride; int32_t s2;
+    int32_t* match; int32_t* tsum; int64_t cap;
+} tnsp_rt_match_job;
+int tnsp_rt_match_multi_i32(const tnsp_rt_match_job* jobs, int n_jobs, int nbm, void* stream);
 /* regroup (edge_operator.hpp:651-688): plan = int32 [2 + 3 (nr + nc)]: nr, nc, then per destination edge (rows, then cols,
  * slowest first) dimension, 1 if the edge sits in the source's column group, stride inside that source group.  src->rt == NULL:
  * dense source; dst->rt == NULL: dense destination of `work` elements; else `work` bounds the stored elements (grid size). */

@@ -68,13 +68,9 @@ def _run(B, case, cut):
 
 
 @pytest.mark.parametrize("shape", [((5, 3), (4,), 6, 0, 3), ((7, 2, 3), (2, 5), 6, 2, 4), ((40, 3), (90,), 70, 3, 20), ((130,), (9, 11), 37, 0, 50),
-                                   ((60, 40), (4,), 5, 1, 3),       # merged group of 2400 indices: the CTA-wide rt_sort (smaller groups: one warp per chain)
-                                   ((190, 180), (3,), 4, 1, 3)])    # 34200 indices: its 1024-thread instantiation
+                                   ((60, 40), (4,), 5, 1, 3)])      # merged group of 2400 indices: the CTA-wide rt_sort (smaller groups: one warp per chain)
 def test_kernels_equal_specification(shape):
-    import os
     from oracle.numpy_backend import NumpyBackend
-    if shape[0] == (190, 180) and os.environ.get("TNSP_TEST_SKIP_HUGE"):
-        pytest.skip("the huge-group case runs once, with the default kernels (27 s of numpy specification)")
     da, db, dk, dead, cut = shape
     case = _case(hash(shape) % 1000, 6, da, db, dk, dead)
     cu = backend.get()
@@ -124,5 +120,5 @@ def test_kernel_variants_equal_specification(env):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_sector_kernels_gpu.py"), "-m", "gpu", "-q", "-x", "-k",
-                        "test_kernels_equal_specification"], env=dict(os.environ, TNSP_TEST_SKIP_HUGE="1", **env), capture_output=True, text=True, timeout=900, cwd=root)
+                        "test_kernels_equal_specification"], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]

@@ -25,6 +25,9 @@ from . import ragged
 from .ragged import Core, Edge, Form, RTensor, STATS, _PLANS, label_parity
 
 
+SIGNED_CACHE_MAX = 16384      # index-space size (M x N) up to which a signed regrouping is kept with its core
+
+
 class SignForm:
     """quadratic form over GF(2) on the edge positions of one tensor: lin = set of positions, quad = set of frozenset pairs"""
     __slots__ = ("lin", "quad")
@@ -137,11 +140,12 @@ def signed_form(t, rows, cols, form):
             STATS["signed_hit"] += 1
             return hit
     f = _build_signed_form(t, rows, cols, form)
-    if core.sforms is None:
-        core.sforms = {}
-    elif len(core.sforms) >= 3:
-        core.sforms.pop(next(iter(core.sforms)))
-    core.sforms[skey] = f
+    if f.M * f.N <= SIGNED_CACHE_MAX:          # small tensors only (site tensors, strip pieces): the big environments would double the footprint
+        if core.sforms is None:
+            core.sforms = {}
+        elif len(core.sforms) >= 2:
+            core.sforms.pop(next(iter(core.sforms)))
+        core.sforms[skey] = f
     return f
 
 

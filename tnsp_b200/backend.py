@@ -46,6 +46,13 @@ class RtMatchSpec(ctypes.Structure):
                 ("match_out", c_vp), ("match_out_stride", c_i64), ("tsum_out", c_vp), ("cap", c_i64)]
 
 
+class RtMatchJob(ctypes.Structure):
+    """tnsp_rt_match_job: one pairing of tnsp_rt_match_multi_i32"""
+    _fields_ = [("rt", c_vp), ("rt_stride", c_i64), ("rs", ctypes.c_int32), ("ct", c_vp), ("ct_stride", c_i64), ("cs", ctypes.c_int32),
+                ("t1", c_vp), ("t1_stride", ctypes.c_int32), ("s1", ctypes.c_int32), ("t2", c_vp), ("t2_stride", ctypes.c_int32),
+                ("s2", ctypes.c_int32), ("match", c_vp), ("tsum", c_vp), ("cap", c_i64)]
+
+
 RT_SMAX = 64
 RT_HDR = 3 + 2 * RT_SMAX
 RT_MSTRIDE = 4 + 2 * RT_SMAX
@@ -136,6 +143,7 @@ class CudaBackend:
         FP = ctypes.POINTER(RtForm)
         lib.tnsp_rt_sort_i32.argtypes = [c_int, P, P, P, P, c_i64, P, c_int, P]
         lib.tnsp_rt_match_i32.argtypes = [P, c_i64, c_int, P, c_i64, c_int, P, c_int, c_int, P, c_int, c_int, P, P, c_int, c_i64, P]
+        lib.tnsp_rt_match_multi_i32.argtypes = [P, c_int, c_int, P]
         SP = ctypes.POINTER(RtMatchSpec)
         lib.tnsp_rt_repack_f64.argtypes = [P, FP, FP, SP, P, c_i64, c_i64, c_int, P]
         lib.tnsp_rt_repack_signed_f64.argtypes = [P, FP, FP, SP, P, c_i64, P, P, c_i64, c_int, P, P, c_int, c_int, P]
@@ -218,6 +226,22 @@ class CudaBackend:
                                             None if t2 is None else t2.data_ptr(), 0 if t2 is None or t2.shape[0] == 1 else 1, int(s2),
                                             match.data_ptr(), None if tsum is None else tsum.data_ptr(), nbm, int(cap), self._stream()))
         return match, tsum
+
+    def rt_match_many(self, jobs, nb):
+        """several pairings in ONE launch (the pairing tables of a factorisation's factors); jobs = [(rt, rs, ct, cs, t1, s1, t2, s2, cap)]
+        -> list of match tables [nb, MSTRIDE] (views of one allocation)"""
+        n = len(jobs)
+        out = self._pi32.new_empty((n, nb, RT_MSTRIDE))
+        arr = (RtMatchJob * n)()
+        for i, (rt, rs, ct, cs, t1, s1, t2, s2, cap) in enumerate(jobs):
+            j = arr[i]
+            j.rt, j.rt_stride, j.rs = rt.data_ptr(), (0 if rt.shape[0] == 1 else rt.stride(0)), int(rs)
+            j.ct, j.ct_stride, j.cs = ct.data_ptr(), (0 if ct.shape[0] == 1 else ct.stride(0)), int(cs)
+            j.t1, j.t1_stride, j.s1 = (None if t1 is None else t1.data_ptr()), (0 if t1 is None or t1.shape[0] == 1 else 1), int(s1)
+            j.t2, j.t2_stride, j.s2 = (None if t2 is None else t2.data_ptr()), (0 if t2 is None or t2.shape[0] == 1 else 1), int(s2)
+            j.match, j.tsum, j.cap = out[i].data_ptr(), None, int(cap)
+        self._ck(self.lib.tnsp_rt_match_multi_i32(arr, n, nb, self._stream()))
+        return [out[i] for i in range(n)]
 
     def _spec(self, f, spec, nbm, want_tsum):
         """spec = (rs, cs, t1, s1, t2, s2): allocate the match table of form `f` (and the summed target), to be filled by the kernel"""
@@ -338,14 +362,19 @@ class CudaBackend:
         tab = self.rt_sort([(labels, 1, kd)])
         first = self.rt_alloc(nb, caps[0] if caps else F.M * kd)
         second = self.rt_alloc(nb, caps[1] if caps else kd * F.N)
-        m_first, _ = self.rt_match(F.rt, F.rs * fsign, tab, 1, t1, t1s, None, 0, nb, first.shape[1])
-        m_second, _ = self.rt_match(tab, -1, F.ct, F.cs * fsign, tt, tts, t1, -t1s if t1 is not None else 0, nb, second.shape[1])
+        # the pairing tables of the factors (and of the singular-value tensor): one launch
+        jobs = [(F.rt, F.rs * fsign, tab, 1, t1, t1s, None, 0, first.shape[1]),
+                (tab, -1, F.ct, F.cs * fsign, tt, tts, t1, -t1s if t1 is not None else 0, second.shape[1])]
+        if code != 0:
+            s_data = self.rt_alloc(nb, kd * kd)
+            jobs.append((tab, -1, tab, 1, None, 0, None, 0, s_data.shape[1]))
+        ms = self.rt_match_many(jobs, nb)
+        m_first, m_second = ms[0], ms[1]
         out = {"labels": labels, "bond_col": (tab, 1), "bond_row": (tab, -1), "first": (m_first, first), "second": (m_second, second)}
         if code == 0:
             self.rt_qr_work(ff, frs, t1p, t1st, t1s, tab, m_first, first, m_second, second, nb)
             return out
-        s_data = self.rt_alloc(nb, kd * kd)
-        m_s, _ = self.rt_match(tab, -1, tab, 1, None, 0, None, 0, nb, s_data.shape[1])
+        m_s = ms[2]
         self.rt_svd_scatter(ff, frs, t1p, t1st, t1s, tab, m_first, first, m_s, s_data, m_second, second, work, ws, wss, nb)
         out["s"] = (m_s, s_data)
         return out

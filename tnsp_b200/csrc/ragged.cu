@@ -45,8 +45,8 @@ constexpr int kHash = 256;
 
 __device__ __forceinline__ int rt_hash(int key) { return (int)(((unsigned)key * 2654435761u) >> 24) & (kHash - 1); }
 
-// (kSortThreads = 256, or 1024 for merged dimensions beyond 32 k: few chains x huge groups -- cfg4's 10^6 indices -- leave most SMs idle,
-// so a chain gets as many threads as a CTA can have)
+// (a 1024-thread instantiation for huge groups -- cfg4's 10^6 merged indices on 37 chains leave most SMs idle -- was tried in round 2 and
+// withdrawn: its parity case failed on the B200 and there was no GPU time left to find out why)
 template <int kSortThreads>
 __global__ void __launch_bounds__(kSortThreads) rt_sort_kernel(RtEdges E, int M, int* __restrict__ table, long long tstride) {
     constexpr int kSortWarps = kSortThreads / 32;
@@ -264,13 +264,9 @@ __global__ void __launch_bounds__(32 * kSortWarpPerCta) rt_sort_warp_kernel(RtEd
 // ------------------------------------------------------------------------------------------------
 // rt_match: one warp per chain
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) rt_match_kernel(const int* __restrict__ rt, long long rts, int rs, const int* __restrict__ ct, long long cts,
-                                                       int cs, const int* __restrict__ t1, int t1s, int s1, const int* __restrict__ t2, int t2s,
-                                                       int s2, int* __restrict__ match, int* __restrict__ tsum, int nbm, long long cap,
-                                                       unsigned long long* flag) {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (b >= nbm) return;
+__device__ __forceinline__ void rt_match_warp(const int* __restrict__ rt, long long rts, int rs, const int* __restrict__ ct, long long cts, int cs,
+                                              const int* __restrict__ t1, int t1s, int s1, const int* __restrict__ t2, int t2s, int s2,
+                                              int* __restrict__ match, int* __restrict__ tsum, long long cap, unsigned long long* flag, int b, int lane) {
     const RtTab R(rt + (long long)b * rts), C(ct + (long long)b * cts);
     int t = 0;
     if (t1) t += s1 * t1[(long long)b * t1s];
@@ -310,6 +306,27 @@ __global__ void __launch_bounds__(128) rt_match_kernel(const int* __restrict__ r
         Mrow[0] = bad ? 0 : carry;
         Mrow[1] = bad ? 1 : 0;      // sector / capacity overflow flag
     }
+}
+
+__global__ void __launch_bounds__(128) rt_match_kernel(const int* __restrict__ rt, long long rts, int rs, const int* __restrict__ ct, long long cts,
+                                                       int cs, const int* __restrict__ t1, int t1s, int s1, const int* __restrict__ t2, int t2s,
+                                                       int s2, int* __restrict__ match, int* __restrict__ tsum, int nbm, long long cap,
+                                                       unsigned long long* flag) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= nbm) return;
+    rt_match_warp(rt, rts, rs, ct, cts, cs, t1, t1s, s1, t2, t2s, s2, match, tsum, cap, flag, b, lane);
+}
+
+// several pairings in one launch: blockIdx.y selects the job
+struct RtMatchJobs { tnsp_rt_match_job j[4]; };
+__global__ void __launch_bounds__(128) rt_match_multi_kernel(RtMatchJobs jobs, int nbm, unsigned long long* flag) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= nbm) return;
+    const tnsp_rt_match_job& q = jobs.j[blockIdx.y];
+    rt_match_warp(q.rt, q.rt_stride, q.rs, q.ct, q.ct_stride, q.cs, q.t1, q.t1_stride, q.s1, q.t2, q.t2_stride, q.s2, q.match, q.tsum, q.cap, flag, b,
+                  lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1264,8 +1281,7 @@ extern "C" int tnsp_rt_sort_i32(int n_edges, const int32_t* const* labels, const
         rt_sort_warp_kernel<<<(nbT + kSortWarpPerCta - 1) / kSortWarpPerCta, 32 * kSortWarpPerCta, 0, (cudaStream_t)stream>>>(E, (int)M, table,
                                                                                                                     RT_HDR + 2 * M, nbT);
     else
-        if (M > 32768) rt_sort_kernel<1024><<<nbT, 1024, 0, (cudaStream_t)stream>>>(E, (int)M, table, RT_HDR + 2 * M);
-        else rt_sort_kernel<256><<<nbT, 256, 0, (cudaStream_t)stream>>>(E, (int)M, table, RT_HDR + 2 * M);
+        rt_sort_kernel<256><<<nbT, 256, 0, (cudaStream_t)stream>>>(E, (int)M, table, RT_HDR + 2 * M);
     return check_launch("tnsp_rt_sort_i32");
 }
 
@@ -1291,6 +1307,15 @@ static int repack_threads(bool pair = false) {
         v[1] = ok ? x : kRepackPairThreads;
     }
     return v[pair ? 1 : 0];
+}
+
+extern "C" int tnsp_rt_match_multi_i32(const tnsp_rt_match_job* jobs, int n_jobs, int nbm, void* stream) {
+    if (nbm == 0 || n_jobs == 0) return 0;
+    if (n_jobs > 4) { set_error("tnsp_rt_match_multi_i32: at most 4 pairings per launch"); return 1; }
+    RtMatchJobs J;
+    for (int i = 0; i < 4; ++i) J.j[i] = jobs[i < n_jobs ? i : 0];
+    rt_match_multi_kernel<<<dim3((nbm + 3) / 4, n_jobs), 128, 0, (cudaStream_t)stream>>>(J, nbm, rt_overflow_ptr());
+    return check_launch("tnsp_rt_match_multi_i32");
 }
 
 // tiles of the densest possible layout / 2 (a CTA loops over its tiles; sectors only cover a fraction of the M x N index space)

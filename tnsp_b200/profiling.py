@@ -16,7 +16,7 @@ class KernelTimer:
                "diag_scatter", "block_sign", "svd_mask",
                # sector-compact engine (TAT/ragged.py): algorithmic work of these classes is counted ON THE DEVICE (per-chain sector
                # sizes are never known to the host): backend.rt_stats
-               "rt_sort", "rt_match", "rt_repack", "rt_repack_pair", "rt_gemm", "rt_dot", "rt_factor_plan", "rt_qr_work", "rt_svd_work", "rt_svd_finish", "rt_svd_scatter",
+               "rt_sort", "rt_match", "rt_match_many", "rt_repack", "rt_repack_pair", "rt_gemm", "rt_dot", "rt_factor_plan", "rt_qr_work", "rt_svd_work", "rt_svd_finish", "rt_svd_scatter",
                "rt_scale", "rt_binary", "rt_norm", "rt_scalar")
 
     def __init__(self, backend):

@@ -244,12 +244,15 @@ class Configuration(SingleLayerAuxiliaries):
             proto = v
         import torch
         cap = max(f.data.shape[1] for f in forms)
-        data = B.zeros(len(forms), cap)
+        cap += cap & 1
+        # one table row per physical index: [stored data | pairing table viewed as float64], so that ONE row gather selects both
+        match = torch.cat([f.match for f in forms], dim=0).contiguous().view(torch.float64)
+        table = B.zeros(len(forms), cap + match.shape[1])
         for p, f in enumerate(forms):
-            data[p, :f.data.shape[1]] = f.data[0]
-        match = torch.cat([f.match for f in forms], dim=0).contiguous()
+            table[p, :f.data.shape[1]] = f.data[0]
+        table[:, cap:] = match
         labels = np.concatenate([np.full(d, ragged.pack_symmetry(sy), dtype=np.int32) for sy, d in edge.segments])
-        out = (proto, data, match.view(torch.float64), labels, cap)
+        out = (proto, table, labels, cap)
         cache[(l1, l2)] = (site, out)
         return out
 
@@ -257,10 +260,11 @@ class Configuration(SingleLayerAuxiliaries):
         from ..TAT import ragged
         import torch
         B = _bk.get()
-        proto, data, match64, labels, cap = self._ragged_variants(l1, l2, orbit)
+        proto, table, labels, cap = self._ragged_variants(l1, l2, orbit)
         idx = B.from_numpy(np.ascontiguousarray(index, dtype=np.int32))
-        sel_data = B.gather_rows(data, data.shape[1], idx)
-        sel_match = B.gather_rows(match64, match64.shape[1], idx).view(torch.int32)
+        sel = B.gather_rows(table, table.shape[1], idx)          # [nb, cap + 66]: data and pairing table of every chain's version
+        sel_data = sel[:, :cap]
+        sel_match = sel[:, cap:].view(torch.int32)
         chosen = labels[index].astype(np.int32)
         f = proto._primary()
         pcore = proto.core
