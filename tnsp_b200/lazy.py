@@ -66,6 +66,9 @@ class Node:
                 stack.extend(missing)
                 continue
             node._value = node._func(*[a._value if isinstance(a, Node) else a for a in node._args])
+            if node._value is None and len(stack) > 1:
+                # an unset Root (or a function returning None) UPSTREAM of the node asked for: its parent would ask for it again for ever
+                raise RuntimeError("lazy graph: an upstream node evaluated to None (a Root is not set)")
             stack.pop()
         return self._value
 
