@@ -20,17 +20,33 @@ from .. import backend as _bk
 from .state import AbstractLattice, AbstractState, SamplingLattice
 
 
+_SAVED: dict = {}
+
+
+def release_backend_flags():
+    """undo the process-wide backend switches `embed_lattice` sets (sector discovery, zero-fragment skipping): a truly dense model
+    run later in the same process must not take the block-sparse paths.  The optimisation driver calls this when it returns."""
+    B = _bk.get()
+    if "sector_discovery" in _SAVED:
+        B.sector_discovery = _SAVED.pop("sector_discovery")
+    if _SAVED.pop("skip", False) and hasattr(B, "lib") and hasattr(B.lib, "tnsp_gemm_skip_zero_fragments"):
+        B.lib.tnsp_gemm_skip_zero_fragments(0)
+
+
 def embed_lattice(lattice, NoTensor=None):
     """NoSymmetry SamplingLattice with the same PEPS (dense site tensors), physical edges and
     Hamiltonian terms as the symmetric `lattice`."""
     No = NoTensor if NoTensor is not None else TAT.No.D.Tensor
     # from here on every single-descriptor QR / SVD finds its symmetry sectors on the device (zero pattern)
-    _bk.get().sector_discovery = True
+    B = _bk.get()
+    if "sector_discovery" not in _SAVED:
+        _SAVED["sector_discovery"] = getattr(B, "sector_discovery", False)
+    B.sector_discovery = True
     # ... and the dense contractions test their operand fragments for the exact zeros of charge conservation (block-sparse
     # operands: 13 % of the fragment pairs of cfg2's heaviest contraction are non-zero); truly dense models keep it off
-    B = _bk.get()
     if hasattr(B, "lib") and hasattr(B.lib, "tnsp_gemm_skip_zero_fragments"):
         B.lib.tnsp_gemm_skip_zero_fragments(2)      # coarse tests: marginally the fastest of the four variants (profiles/r01_s9_mb_gemm_sparse.txt)
+        _SAVED["skip"] = True
     state = AbstractState(No, lattice.L1, lattice.L2)
     for (l1, l2, orbit), edge in lattice.physics_edges:
         state.physics_edges[l1, l2, orbit] = edge.dimension

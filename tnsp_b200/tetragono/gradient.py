@@ -314,6 +314,10 @@ def gradient_descent(
             observer.normalize_lattice(state if embedded else None)
             bcast_lattice(state)
 
+        if embedded:
+            # the embedding's process-wide backend switches end with the step (the next step's embed_lattice sets them again): a truly
+            # dense model evaluated by the caller between two steps, or after the last one, takes the dense paths
+            dense_embedding.release_backend_flags()
         yield (measurement_whole_result, measurement_result)
 
         # checkpoints in the reference's own formats (utility.py:340-418): its `pickle.load` / `read_configurations` read them

@@ -349,8 +349,9 @@ class SamplingLattice(AbstractLattice):
         a_r = a_r.edge_rename({n: f"A_{n}" for n in a_r.names})
         b_r = b_r.edge_rename({n: f"B_{n}" for n in b_r.names})
         core = a_r.contract(b_r, {(f"A_{bond_1}", f"B_{bond_2}")})
+        noise = core.same_shape().randn_()      # drawn unconditionally, as the reference does (lattice.py:881, 909): the global stream stays in step
         if epsilon != 0:
-            core = core + core.same_shape().randn_() * (epsilon * float(core.norm_max()))
+            core = core + noise * (epsilon * float(core.norm_max()))
         u, sv, v = core.svd({n for n in core.names if n.startswith("A_")}, bond_1, bond_2, bond_2, bond_1, new_dimension)
         root = sv.sqrt()
         eye = sv.same_shape().identity_({(bond_2, bond_1)})
