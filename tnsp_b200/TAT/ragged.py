@@ -592,11 +592,6 @@ def _reordered(t, target_names):
     return RTensor(target_names, new, t.sign)
 
 
-def _split_names(t, pairs_side):
-    """positions of the non-unit / unit edges of `t` that are contracted (in the order of `pairs_side`) and free"""
-    return None
-
-
 def _contract(a, b, pairs):
     B = _bk.get()
     STATS["contract"] += 1

@@ -22,7 +22,7 @@ import numpy as np
 
 from .. import backend as _bk
 from . import ragged
-from .ragged import Core, Edge, Form, RTensor, STATS, _PLANS, label_parity
+from .ragged import Core, Form, RTensor, STATS, _PLANS
 
 
 SIGNED_CACHE_MAX = 16384      # index-space size (M x N) up to which a signed regrouping is kept with its core
