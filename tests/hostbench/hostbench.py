@@ -1,11 +1,11 @@
 """Host-overhead benchmark of the lock-step engine WITHOUT a GPU (development tool, not a product or test path).
 
 The Python drivers + TAT/ragged.py + backend.py run exactly as on the B200, but the C-ABI is a library of no-ops
-(scripts/hostbench/stub.c, generated from the exported symbols) and the buffers are CPU tensors holding garbage: nothing is
+(tests/hostbench/stub.c, generated from the exported symbols) and the buffers are CPU tensors holding garbage: nothing is
 computed, only the interpreter time per lock-step step is measured.  On the B200 a cfg2 step is host-bound (the same ~1.3 s at
 148 and at 2368 chains), so this number IS the step time there.
 
-    python scripts/hostbench/hostbench.py [workload] [steps] [--profile]
+    python tests/hostbench/hostbench.py [workload] [steps] [--profile]
 """
 import ctypes
 import os
@@ -16,7 +16,7 @@ import warnings
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))      # tests/hostbench -> repository root
 sys.path.insert(0, ROOT)
 warnings.filterwarnings("ignore")
 np.seterr(all="ignore")
@@ -28,7 +28,7 @@ from tnsp_b200 import backend  # noqa: E402
 def build_stub():
     import subprocess
     so = "/tmp/libtnsp_stub.so"
-    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-w", "-o", so, os.path.join(ROOT, "scripts", "hostbench", "stub.c"),
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-w", "-o", so, os.path.join(ROOT, "tests", "hostbench", "stub.c"),
                            os.path.join(ROOT, "tnsp_b200", "lib", "capi.o"), "-lstdc++"])
     return so
 

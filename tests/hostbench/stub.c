@@ -1,4 +1,4 @@
-/* generated by scripts/hostbench: no-op stand-ins of the C-ABI (host-overhead benchmark only; NOT a product or test path) */
+/* generated for tests/hostbench: no-op stand-ins of the C-ABI (host-overhead benchmark only; NOT a product or test path) */
 #include <stdint.h>
 static long long n_calls = 0;
 int tnsp_binary_f64() { ++n_calls; return 0; }
