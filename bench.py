@@ -28,7 +28,9 @@ WORKLOADS = {
     # name: dict(L1, L2, D, Dc, sym, J2, sr (SR natural gradient by CG with `cg` iterations per step), chains, desc)
     "cfg1": dict(L1=4, L2=4, D=4, Dc=16, sym="No", J2=0.0, sr=False, cg=0, chains=4096,
                  desc="tetragono sampling VMC 4x4 Heisenberg square lattice, no symmetry, D=4, Dc=16, float64"),
-    "cfg2": dict(L1=6, L2=6, D=6, Dc=36, sym="BoseU1", J2=0.5, sr=True, cg=20, chains=2368,
+    # chains: 20 x 148; measured 2258 samples/s at 2960 chains (120 GB) against 1970 - 2090 at 2368 (104 - 111 GB): the kernels of a larger
+    # batch outlast more of the host's per-launch time (profiles/r02_bench_cfg2_nb2960.json)
+    "cfg2": dict(L1=6, L2=6, D=6, Dc=36, sym="BoseU1", J2=0.5, sr=True, cg=20, chains=2960,
                  desc="6x6 J1-J2 Heisenberg (J2=0.5) with U(1) symmetry, D=6 (2+2+2), Dc=36, sweep sampling + SR natural gradient (CG 20), float64"),
     "cfg2s": dict(L1=4, L2=4, D=3, Dc=9, sym="BoseU1", J2=0.5, sr=True, cg=4, chains=64,
                   desc="4x4 J1-J2 Heisenberg with U(1) symmetry, D=3, Dc=9, sweep + SR (smoke size of cfg2)"),
