@@ -212,3 +212,37 @@ def test_learnt_capacities_and_overflow_correction():
         ragged._LEARN.update(saved[1])
         ragged.CAP_FACTOR, ragged.CAP_MIN_CHAINS = saved[2], saved[3]
         sampling._CAPACITY_BUMPS.update(saved[4])
+
+
+def test_table_cache_does_not_grow_with_the_number_of_sweeps():
+    """group tables are cached on their first label array; entries keyed on label arrays of environments that no longer exist must be
+    purged -- the bond labels of the PEPS site tensors live as long as the lattice, and their caches once grew by ~2.4 GB per step of
+    the cfg2 bench (one sorted table per regrouping of every environment of every sweep)"""
+    import gc
+    import torch
+    meta, z, lat = _u1_lattice()
+    L1, L2, Dc = meta["L1"], meta["L2"], meta["Dc"]
+    nb = 3
+    rng = ChainRng(nb)
+    rng.seed([11, 12, 13])
+    s = SweepSampling(lat, Dc, None, models.nearest_neighbour_terms(lat), nb=nb, rng=rng)
+    s.configuration.import_configuration(_sz0_configurations(nb, L1, L2, 9))
+    obs = Observer(lat, enable_energy=True, enable_gradient=True)
+
+    def cached():
+        gc.collect()
+        n = 0
+        for o in gc.get_objects():
+            if isinstance(o, torch.Tensor):
+                n += len(getattr(o, "__dict__", {}).get("_rt_tables", ()))
+        return n
+
+    counts = []
+    for _ in range(5):
+        with obs:
+            p, c = s()
+            obs(p, c)
+        del p, c
+        counts.append(cached())
+    # steady state after the first sweeps: no systematic growth (accept / reject patterns make the count fluctuate a little)
+    assert counts[4] <= 1.25 * counts[1] + 16, counts

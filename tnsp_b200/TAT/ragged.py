@@ -206,6 +206,12 @@ class Core:
                         hit = None          # an id was recycled by another array
                     if hit is None:
                         STATS["sort"] += 1
+                        if len(store) >= 8:
+                            # entries whose other label arrays are gone (the bonds of environments of earlier sweeps) can never hit
+                            # again: without this a persistent first array -- the bond labels of a PEPS site tensor -- collected
+                            # ~2.4 GB of dead tables per cfg2 step at 2368 chains
+                            for k in [k for k, h in store.items() if any(r() is None for r in h[1])]:
+                                del store[k]
                         # weak references to the other arrays: no reference cycles through the cache (device memory is freed by
                         # reference counting, not by the cycle collector)
                         hit = store[key] = (B.rt_sort([(e.arr, e.sign * g, e.dim) for e in es]), tuple(weakref.ref(e.arr) for e in es[1:]))
