@@ -19,9 +19,17 @@ _PLAN_CACHE: dict = {}
 STATS = {"contract": 0, "svd": 0, "qr": 0, "pack": 0, "flops": 0, "pack_elems": 0}
 
 
+PLAN_CACHE_MAX = 20000      # plans (host tables + their device copies); a lock-step model needs a few hundred
+
+
 def _cached(key, builder):
     p = _PLAN_CACHE.get(key)
     if p is None:
+        if len(_PLAN_CACHE) >= PLAN_CACHE_MAX:
+            # single chains of a symmetric model meet new block structures for ever (per-sample sectors, per-sample cuts): the oldest half
+            # goes -- a plan can always be rebuilt
+            for k in list(_PLAN_CACHE)[:PLAN_CACHE_MAX // 2]:
+                del _PLAN_CACHE[k]
         p = _PLAN_CACHE[key] = builder()
     return p
 
