@@ -524,7 +524,8 @@ def run_own(args):
     if sector and wl["sym"].startswith("Fermi"):
         # few chains per GPU and strongly fluctuating sector sizes (hopping moves charge between the bonds): memory is not the limit
         # here, so batches up to 148 chains allocate the dense bound of every tensor (no learnt capacities, nothing can overflow)
-        _ragged.CAP_FACTOR = 3.0
+        # (larger batches learn capacities; measured at 296 chains of cfg3: a factor of 3 needed three corrections up to 10, 89 GB -- start at 8)
+        _ragged.CAP_FACTOR = 8.0
         _ragged.CAP_MIN_CHAINS = 160
     if sector and nb > n_cal and nb >= _ragged.CAP_MIN_CHAINS:
         # buffer capacities of the sector-compact engine are learnt on a small throw-away batch first (TAT/ragged.py)
