@@ -480,12 +480,17 @@ def run_own(args):
     # ---- parity line: cache-cold amplitude and local energy of the start configuration, ALL through the engine being timed, against
     # the fixture the unmodified reference wrote for exactly this PEPS (tests/golden/make_golden.py cfg2size) -------------------------
     parity = None
-    fixture = {"cfg2": "j1j2U1_6x6_d2_Dc36", "cfg2s": "j1j2U1_4x4_d1_Dc9"}.get(args.workload)
+    # (cfg2: tests/golden/make_golden.py cfg2size; the fermionic workloads: tests/golden/make_bench_fixtures.py, which also stores the
+    # start configuration it evaluated)
+    fixture = {"cfg2": "j1j2U1_6x6_d2_Dc36", "cfg2s": "j1j2U1_4x4_d1_Dc9", "cfg3s": "bench_cfg3s", "cfg4s": "bench_cfg4s", "cfg3": "bench_cfg3",
+               "cfg4": "bench_cfg4"}.get(args.workload)
     fpath = os.path.join(ROOT, "tests", "golden", f"{fixture}.npz") if fixture else None
     # (EVERY rank runs it: the Observer's exit is a collective -- summed numerator and denominator leave the ratio unchanged)
-    if fpath and os.path.exists(fpath) and (args.workload != "cfg2s"):
+    if fpath and os.path.exists(fpath) and (args.workload != "cfg2s") and sector:
         from tnsp_b200.tetragono.configuration import Configuration
         z = np.load(fpath)
+        if "conf" in z.files and not np.array_equal(z["conf"], conf0):
+            raise RuntimeError("bench parity check: the fixture was written for another start configuration")
         n_par = min(nb, 148)
         pc = Configuration(lat, Dc, n_par)
         pc.import_configuration(np.broadcast_to(conf0, (n_par,) + conf0.shape))
@@ -494,7 +499,7 @@ def run_own(args):
         with po:
             po(ws_p**2, pc)
         e_p = po._whole_result_reweight["energy"] / po._total_weight
-        parity = {"fixture": f"tests/golden/{fixture}.npz (unmodified reference, cache-cold Neel configuration)", "chains": n_par,
+        parity = {"fixture": f"tests/golden/{fixture}.npz (unmodified reference, cache-cold start configuration)", "chains": n_par,
                   "ws_reference": float(z["ws"][0]), "ws_max_rel_err": float(np.abs(ws_p - z["ws"][0]).max() / abs(z["ws"][0])),
                   "local_energy_reference": float(z["energy_s"][0]),
                   "local_energy_rel_err": float(abs(e_p - z["energy_s"][0]) / abs(z["energy_s"][0])), "tolerance": 1e-10}
