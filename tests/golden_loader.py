@@ -8,7 +8,7 @@ import tnsp_b200.TAT as TAT
 from tnsp_b200.tetragono.state import AbstractLattice, AbstractState, SamplingLattice
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(f[:-4] for f in os.listdir(HERE) if f.endswith(".npz") and not f.startswith(("driver_", "gauge_", "direct_", "simple_", "long_", "hamiltonian_", "common_", "model_")))
+CASES = sorted(f[:-4] for f in os.listdir(HERE) if f.endswith(".npz") and not f.startswith(("driver_", "gauge_", "direct_", "simple_", "long_", "hamiltonian_", "common_", "model_", "bench_")))
 DRIVER_CASES = sorted(f[:-4] for f in os.listdir(HERE) if f.endswith(".npz") and f.startswith("driver_"))
 
 
