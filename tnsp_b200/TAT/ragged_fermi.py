@@ -149,6 +149,21 @@ def signed_form(t, rows, cols, form):
     return f
 
 
+_DEVICE_CONSTANTS: dict = {}
+
+
+def _device_constant(B, array):
+    """device copy of a small chain-independent int32 array (the quadratic part of a sign form, a chain-independent linear part): the same
+    few hundred arrays recur at every program point of every sweep, so they are uploaded once instead of once per regrouping"""
+    key = (id(B), array.shape, array.tobytes())
+    got = _DEVICE_CONSTANTS.get(key)
+    if got is None:
+        if len(_DEVICE_CONSTANTS) >= 8192:
+            _DEVICE_CONSTANTS.clear()
+        got = _DEVICE_CONSTANTS[key] = B.upload(array)
+    return got
+
+
 def _build_signed_form(t, rows, cols, form):
     core = t.core
     entries = list(rows) + list(cols)          # every device-labelled edge, dimension 1 included: its parity is only known there
@@ -167,7 +182,7 @@ def _build_signed_form(t, rows, cols, form):
     STATS["repack"] += 1
     labels = [(core.edges[i].arr, core.edges[i].dim) for i in entries]
     B.rt_repack(ragged._repack_plan(core, src, f, True), src, f, (rs, cs, core.target, core.tsign, None, 0),
-                sign=(B.upload(quad), B.upload(per_chain), labels, core.fermi))
+                sign=(_device_constant(B, quad), _device_constant(B, per_chain) if per_chain.shape[0] == 1 else B.upload(per_chain), labels, core.fermi))
     if learning:
         ragged._learn(ckey, f.match)
     return f
