@@ -132,10 +132,10 @@ class Edge:
         return self if s == 1 else Edge(self.dim, self.arr, -self.sign, not self.arrow, self.harr, self.par)
 
     def unit_parity(self, mask):
-        """parity bits [nbL] of a unit edge's charges (the parity of a label does not depend on its sign)"""
+        """parity bits (uint32 [nbL]) of a unit edge's charges (the parity of a label does not depend on its sign)"""
         p = self.par
         if p is None or p[0] != mask:
-            p = self.par = (mask, label_parity(np.asarray(self.harr, dtype=np.int64).reshape(-1), mask))
+            p = self.par = (mask, label_parity(np.asarray(self.harr, dtype=np.int64).reshape(-1), mask).astype(np.uint32))
         return p[1]
 
     def host_labels(self):

@@ -29,19 +29,25 @@ SIGNED_CACHE_MAX = 16384      # index-space size (M x N) up to which a signed re
 
 
 class SignForm:
-    """quadratic form over GF(2) on the edge positions of one tensor: lin = set of positions, quad = set of frozenset pairs"""
-    __slots__ = ("lin", "quad")
+    """quadratic form over GF(2) on the edge positions of one tensor: lin = set of positions, quad = set of frozenset pairs.
+    A form is built once (add_*), then only read; `key()` and the folds of `fold_units` are remembered on it (the forms of a
+    contraction live in its cached plan, so a program point pays for them once)"""
+    __slots__ = ("lin", "quad", "_key", "_folds")
 
     def __init__(self):
         self.lin = set()
         self.quad = set()
+        self._key = None
+        self._folds = None
 
     def add_lin(self, i):
         self.lin ^= {i}
+        self._key = self._folds = None
 
     def add_pair(self, i, j):
         if i != j:
             self.quad ^= {frozenset((i, j))}
+            self._key = self._folds = None
 
     def add_clique(self, group):
         """(n_odd & 2) of a group of edges = sum over its pairs"""
@@ -61,38 +67,35 @@ class SignForm:
         return not self.lin and not self.quad
 
     def key(self):
-        return (tuple(sorted(self.lin)), tuple(sorted(tuple(sorted(p)) for p in self.quad)))
+        k = self._key
+        if k is None:
+            k = self._key = (tuple(sorted(self.lin)), tuple(sorted(tuple(sorted(p)) for p in self.quad)))
+        return k
 
 
 def unit_parities(t, mask):
     """{position: int array [nbL] of parities} of the unit edges of tensor view `t` (effective labels)"""
-    out = {}
-    for i, e in enumerate(t.core.edges):
-        if e.harr is not None:
-            out[i] = e.unit_parity(mask)
-    return out
+    edges = t.core.edges
+    return {i: edges[i].unit_parity(mask) for i, u in enumerate(t.core.sig[1]) if u}
 
 
-def fold_units(form, t, entries):
-    """Reduce a sign form to the indexed edges `entries` (positions of the non-unit edges in the order the kernel sees them).
-
-    Returns (quad masks int32 [n_ent]: bit j of entry k set iff Q_kj = 1 and j > k; per-chain int32 [nb or 1]: bits 0..n_ent-1
-    the linear coefficients, bit 31 the constant).  None, None when the form vanishes identically."""
-    mask = t.core.fermi
-    up = unit_parities(t, mask)
+def _compile_fold(form, entries, units):
+    """the chain-independent part of folding `form` onto the indexed edges `entries` when the edges at `units` are unit edges:
+    (quad int32 [n] | None when it vanishes, constant linear bits, [(unit position, shift)] linear terms carried by a unit parity,
+    [unit position] constant terms, [(unit, unit)] constant products)"""
     slot = {pos: k for k, pos in enumerate(entries)}
     n = len(entries)
     if n > 30:
         raise NotImplementedError("sign form over more than 30 indexed edges")
     quad = [0] * max(n, 1)
-    lin0, const0 = 0, 0          # chain-independent parts (Python ints); the unit parities enter as arrays
-    lin_a, const_a = None, None
+    lin0 = 0
+    lin_terms, const_terms, const_pairs = [], [], []
     for i in form.lin:
         k = slot.get(i)
         if k is not None:
             lin0 ^= 1 << k
-        elif i in up:
-            const_a = up[i] if const_a is None else const_a ^ up[i]
+        elif i in units:
+            const_terms.append(i)
     for pr in form.quad:
         i, j = tuple(pr)
         ki, kj = slot.get(i), slot.get(j)
@@ -100,27 +103,53 @@ def fold_units(form, t, entries):
             if ki > kj:
                 ki, kj = kj, ki
             quad[ki] ^= 1 << kj
-        elif ki is not None and j in up:
-            v = up[j] << ki
-            lin_a = v if lin_a is None else lin_a ^ v
-        elif kj is not None and i in up:
-            v = up[i] << kj
-            lin_a = v if lin_a is None else lin_a ^ v
-        elif i in up and j in up:
-            v = up[i] & up[j]
-            const_a = v if const_a is None else const_a ^ v
-    if lin_a is None and const_a is None:
-        if not any(quad) and lin0 == 0:
+        elif ki is not None and j in units:
+            lin_terms.append((j, ki))
+        elif kj is not None and i in units:
+            lin_terms.append((i, kj))
+        elif i in units and j in units:
+            const_pairs.append((i, j))
+    return (np.array(quad, dtype=np.int32), any(quad), lin0, tuple(lin_terms), tuple(const_terms), tuple(const_pairs))
+
+
+def fold_units(form, t, entries):
+    """Reduce a sign form to the indexed edges `entries` (positions of the non-unit edges in the order the kernel sees them).
+
+    Returns (quad masks int32 [n_ent]: bit j of entry k set iff Q_kj = 1 and j > k; per-chain int32 [nb or 1]: bits 0..n_ent-1
+    the linear coefficients, bit 31 the constant).  None, None when the form vanishes identically."""
+    up = unit_parities(t, t.core.fermi)
+    ckey = (tuple(entries), tuple(up))
+    folds = form._folds
+    if folds is None:
+        folds = form._folds = {}
+    comp = folds.get(ckey)
+    if comp is None:
+        comp = folds[ckey] = _compile_fold(form, entries, set(up))
+    quad, any_quad, lin0, lin_terms, const_terms, const_pairs = comp
+    if not lin_terms and not const_terms and not const_pairs:
+        if not any_quad and lin0 == 0:
             return None, None
-        per_chain = np.array([lin0 & 0x7FFFFFFF], dtype=np.int64)
-    else:
-        lin = (lin0 if lin_a is None else (lin_a ^ lin0)) & 0x7FFFFFFF
-        const = 0 if const_a is None else (const_a & 1)
-        per_chain = np.atleast_1d(np.asarray(lin | (const << 31), dtype=np.int64))
-        if not any(quad) and not per_chain.any():
-            return None, None
-    per_chain = np.where(per_chain >= (1 << 31), per_chain - (1 << 32), per_chain).astype(np.int32)
-    return np.array(quad, dtype=np.int32), per_chain
+        return quad, np.array([lin0], dtype=np.int32)
+    # unit parities are uint32 arrays [nbL]: bits 0..30 the linear coefficients, bit 31 the constant, reinterpreted as int32 at the end
+    acc = None
+    for j, k in lin_terms:
+        v = up[j] << np.uint32(k)
+        acc = v if acc is None else acc ^ v
+    const_a = None
+    for i in const_terms:
+        const_a = up[i] if const_a is None else const_a ^ up[i]
+    for i, j in const_pairs:
+        v = up[i] & up[j]
+        const_a = v if const_a is None else const_a ^ v
+    if const_a is not None:
+        v = (const_a & np.uint32(1)) << np.uint32(31)
+        acc = v if acc is None else acc ^ v
+    if lin0:
+        acc = acc ^ np.uint32(lin0)
+    acc = np.atleast_1d(acc)
+    if not any_quad and not acc.any():
+        return None, None
+    return quad, acc.view(np.int32)
 
 
 # -------------------------------------------------------------------------------------------------
