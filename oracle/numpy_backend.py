@@ -12,7 +12,7 @@ Each function follows the reference's per-sector algorithm:
   svd_cut         svd.hpp:429-481 (greedy cross-sector cut, literal restatement)
   diag_scatter    svd.hpp:213-254
   norm/scale/...  tensor.hpp:631-660, scalar.hpp:46-118, conjugate.hpp:99-116
-Parity is pinned through tests/test_oracle_vs_reference.py (the real reference in oracle/_ref and
+Parity is pinned through tests/test_tat_vs_reference.py and tests/test_reference_kats.py (the real reference in oracle/_ref and
 the golden vectors of PyTAT/tests).
 """
 from __future__ import annotations
